@@ -1,0 +1,403 @@
+// candmc_b200 — FP64 GEMM for sm_100a:  C = alpha * op(A) * op(B) + beta * C   (column-major, Fortran dgemm
+// semantics).  Replaces the vendor `dgemm_` behind the reference's `cdgemm` wrapper
+// (reference alg/shared/lapack.cxx:425-434) at its hot call sites: summa.cxx:96-97, d25_summa.cxx:138-148,200-201,
+// dual_cannon.cxx:164-193, spcannon.cxx:117,195 ('N','T'), qr_2d.cxx:259 ('T','N') and :275 ('N','N').
+//
+// Design (B200-first, not a translation of any BLAS):
+//   * FP64 has no tcgen05/UMMA kind on sm_100a; the FP64 tensor atom is mma.sync.m8n8k4 (SASS DMMA.8x8x4) with
+//     register accumulators.  One persistent CTA per SM owns 128x128 C tiles; 8 consumer warps each hold a 64x32
+//     register tile (64 accumulator doubles/lane), one producer warp drives TMA.
+//   * Operand tiles (128 x 16 doubles = 16 KiB each) are brought in by TMA (`cp.async.bulk.tensor.2d`, 128-byte
+//     swizzle) into a 6-stage mbarrier ring (192 KiB smem).  Two smem layouts exist, chosen per operand by the
+//     transpose flag:
+//       K-major  (A with 'T', B with 'N'): one 128 B line per m/n index holding the tile's 16 k values; one TMA box.
+//       MN-major (A with 'N', B with 'T'): 8 slabs of 16 m/n indices; in a slab one 128 B line per k; 8 TMA boxes.
+//   * The DMMA slot -> (index, k) assignment is permuted so that every fragment `ld.shared.f64` is bank-conflict
+//     free under the hardware swizzle for BOTH layouts (see frag maps below): index slots g=0..7 map to
+//     {0,1,4,5,2,3,6,7}; the 4 DMMA k-steps of a 16-wide k tile use k = 8*(s>>1) + 2j + ((j&1)^(s&1)).
+//     Sums over k and the set of output elements are unchanged — only which lane/step touches which element.
+//   * Tiles are rasterised in groups of 8 tile-rows so a wave of 148 CTAs re-uses A/B panels out of the 126 MB L2.
+//   * Out-of-range rows/cols/k are zero-filled by TMA (exact), stores are predicated: any m,n,k >= 0 works on the
+//     TMA path as long as the base pointers are 16 B aligned and lda/ldb are even.  Otherwise a plain tiled
+//     CUDA-core kernel (`gemm_f64_generic`) is used — still on the GPU; there is no CPU path.
+#include "common.cuh"
+#include "runtime.h"
+
+namespace candmc {
+
+namespace {
+
+constexpr int BM = 128;            // CTA tile rows
+constexpr int BN = 128;            // CTA tile cols
+constexpr int BK = 16;             // k per stage (one 128 B swizzle span of doubles)
+constexpr int NSTAGE = 6;          // 6 x 32 KiB = 192 KiB
+constexpr int OPER_BYTES = BM * BK * 8;          // 16 KiB per operand per stage
+constexpr int STAGE_BYTES = 2 * OPER_BYTES;      // 32 KiB
+constexpr int NCONSUMER_WARPS = 8;
+constexpr int NTHREADS = (NCONSUMER_WARPS + 4) * 32;  // + 1 producer warpgroup (setmaxnreg works per 4 warps)
+constexpr int PRODUCER_REGS = 40;                     // 4 warps x 40 + 8 warps x 232 regs = 64512 <= 65536
+constexpr int CONSUMER_REGS = 232;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int RASTER_GROUP = 8;
+
+// index-slot permutation shared by A rows and B cols (see header comment)
+__device__ __forceinline__ int cf_map(int g) { return ((g & 1) | ((g & 2) << 1) | ((g & 4) >> 1)); }
+// k handled by lane slot j in DMMA step s of a 16-wide k tile
+__device__ __forceinline__ int k_map(int s, int j) { return 8 * (s >> 1) + 2 * j + ((j & 1) ^ (s & 1)); }
+
+// Byte offset of (index slot cf in an 8-aligned group, k) inside an operand tile; `par` = bit 3 of the index
+// (only matters for the MN-major layout where 16 indices share a slab).
+template <bool KMAJ>
+__device__ __forceinline__ uint32_t lane_off(int cf, int k, int par) {
+  if (KMAJ) {
+    return cf * 128 + ((((k >> 1) ^ cf) & 7) << 4) + (k & 1) * 8;
+  } else {
+    return k * 128 + ((((par * 4 + (cf >> 1)) ^ (k & 7)) & 7) << 4) + (cf & 1) * 8;
+  }
+}
+// Byte offset of fragment f (8 indices each) relative to the warp's first index (a multiple of 32).
+template <bool KMAJ>
+__device__ __forceinline__ constexpr uint32_t frag_off(int f) {
+  return KMAJ ? f * 8 * 128 : (f >> 1) * 2048;
+}
+template <bool KMAJ>
+__device__ __forceinline__ constexpr uint32_t warp_off(int first_index /*multiple of 32*/) {
+  return KMAJ ? first_index * 128 : (first_index >> 4) * 2048;
+}
+
+struct TileCoord {
+  int tm, tn;
+};
+
+__device__ __forceinline__ TileCoord tile_coord(int t, int tilesM, int tilesN) {
+  // groups of RASTER_GROUP tile-rows; inside a group walk down the rows first, then across columns
+  const int per_group = RASTER_GROUP * tilesN;
+  const int grp = t / per_group;
+  const int first_m = grp * RASTER_GROUP;
+  const int rows = min(RASTER_GROUP, tilesM - first_m);
+  const int r = t - grp * per_group;
+  TileCoord c;
+  c.tm = first_m + r % rows;
+  c.tn = r / rows;
+  return c;
+}
+
+template <bool A_KMAJ, bool B_KMAJ>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    double* __restrict__ C, int64_t ldc, int M, int N, int K, double alpha, double beta,
+                    int tilesM, int tilesN) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024 B alignment for the 128 B swizzle atom; pointer arithmetic keeps the shared address space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + NSTAGE;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int KT = (K + BK - 1) / BK;
+  const int ntiles = tilesM * tilesN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], NCONSUMER_WARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp >= NCONSUMER_WARPS) {
+    // ===================== TMA producer warpgroup (one lane works; the rest only donate registers) =========
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+    if (warp == NCONSUMER_WARPS && lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(t, tilesM, tilesN);
+        const int m0 = tc.tm * BM, n0 = tc.tn * BN;
+        for (int kt = 0; kt < KT; ++kt) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + OPER_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          const int k0 = kt * BK;
+          if (A_KMAJ) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) tma_load_2d(sa + s * 2048, &tmA, &full_bar[stage], m0 + 16 * s, k0);
+          }
+          if (B_KMAJ) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) tma_load_2d(sb + s * 2048, &tmB, &full_bar[stage], n0 + 16 * s, k0);
+          }
+          if (++stage == NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== DMMA consumers =====================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
+  const int g = lane >> 2;  // index slot
+  const int j = lane & 3;   // k slot
+  const int cf = cf_map(g);
+  const int wm = warp & 1;   // 2 warps along M (64 rows each)
+  const int wn = warp >> 1;  // 4 warps along N (32 cols each)
+
+  // per-lane smem byte offsets for the 4 k-steps (and, for MN-major, the two slab halves)
+  const uint32_t smem_base = smem_u32(smem);
+  uint32_t aoff[4][2], boff[4][2];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int k = k_map(s, j);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      aoff[s][p] = smem_base + warp_off<A_KMAJ>(wm * 64) + lane_off<A_KMAJ>(cf, k, p);
+      boff[s][p] = smem_base + OPER_BYTES + warp_off<B_KMAJ>(wn * 32) + lane_off<B_KMAJ>(cf, k, p);
+    }
+  }
+
+  double acc[8][4][2];
+  double fa[2][8], fb[2][4];
+
+  // `st` = byte offset of the stage inside the ring
+  auto load_frags = [&](int buf, uint32_t st, int s) {
+#pragma unroll
+    for (int f = 0; f < 8; ++f)
+      fa[buf][f] = lds_f64(aoff[s][A_KMAJ ? 0 : (f & 1)] + st + frag_off<A_KMAJ>(f));
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+      fb[buf][f] = lds_f64(boff[s][B_KMAJ ? 0 : (f & 1)] + st + frag_off<B_KMAJ>(f));
+  };
+  auto mma_step = [&](int buf) {
+#pragma unroll
+    for (int f = 0; f < 8; ++f)
+#pragma unroll
+      for (int h = 0; h < 4; ++h) dmma884(acc[f][h][0], acc[f][h][1], fa[buf][f], fb[buf][h]);
+  };
+
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const TileCoord tc = tile_coord(t, tilesM, tilesN);
+#pragma unroll
+    for (int f = 0; f < 8; ++f)
+#pragma unroll
+      for (int h = 0; h < 4; ++h) acc[f][h][0] = acc[f][h][1] = 0.0;
+
+    if (KT > 0) {
+      mbar_wait(&full_bar[stage], phase);
+      load_frags(0, stage * STAGE_BYTES, 0);
+    }
+    for (int kt = 0; kt < KT; ++kt) {
+      const uint32_t st = stage * STAGE_BYTES;
+      load_frags(1, st, 1);
+      mma_step(0);
+      load_frags(0, st, 2);
+      mma_step(1);
+      load_frags(1, st, 3);
+      mma_step(0);
+      // all of this warp's reads of `stage` are now in registers (fa/fb[1] are consumed below; the loads were
+      // issued above and mbarrier.arrive has release semantics)
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == NSTAGE) {
+        nstage = 0;
+        nphase ^= 1;
+      }
+      if (kt + 1 < KT) {
+        mbar_wait(&full_bar[nstage], nphase);
+        load_frags(0, nstage * STAGE_BYTES, 0);
+      }
+      mma_step(1);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      stage = nstage;
+      phase = nphase;
+    }
+
+    // ---- epilogue: registers -> global, predicated, alpha/beta (beta==0 never reads C) ----
+    const int row_base = tc.tm * BM + wm * 64 + cf;
+    const int col_base = tc.tn * BN + wn * 32 + cf_map(2 * j);  // slots 2j, 2j+1 -> adjacent columns
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col = col_base + h * 8 + c;
+        if (col < N) {
+          double* cp = C + static_cast<int64_t>(col) * ldc;
+#pragma unroll
+          for (int f = 0; f < 8; ++f) {
+            const int row = row_base + f * 8;
+            if (row < M) {
+              double v = alpha * acc[f][h][c];
+              if (beta != 0.0) v += beta * cp[row];
+              cp[row] = v;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic CUDA-core kernel: any alignment / leading dimension.  64x64 tile, 16x16 threads, 4x4 micro-tile.
+// Only used when the TMA path's alignment preconditions do not hold (odd lda, 8-byte-aligned pointers).
+// ---------------------------------------------------------------------------------------------
+constexpr int GT = 64, GK = 16;
+
+__global__ void __launch_bounds__(256)
+gemm_f64_generic_kernel(int transA, int transB, int M, int N, int K, double alpha, const double* __restrict__ A,
+                        int64_t lda, const double* __restrict__ B, int64_t ldb, double beta,
+                        double* __restrict__ C, int64_t ldc) {
+  __shared__ double sA[GK][GT + 1];
+  __shared__ double sB[GK][GT + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
+  double acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    for (int e = threadIdx.x; e < GT * GK; e += 256) {
+      int i, kk;
+      if (!transA) { i = e % GT; kk = e / GT; } else { kk = e % GK; i = e / GK; }
+      const int gm = m0 + i, gk = k0 + kk;
+      double v = 0.0;
+      if (gm < M && gk < K) v = transA ? A[gk + static_cast<int64_t>(gm) * lda] : A[gm + static_cast<int64_t>(gk) * lda];
+      sA[kk][i] = v;
+    }
+    for (int e = threadIdx.x; e < GT * GK; e += 256) {
+      int i, kk;
+      if (!transB) { kk = e % GK; i = e / GK; } else { i = e % GT; kk = e / GT; }
+      const int gn = n0 + i, gk = k0 + kk;
+      double v = 0.0;
+      if (gn < N && gk < K) v = transB ? B[gn + static_cast<int64_t>(gk) * ldb] : B[gk + static_cast<int64_t>(gn) * ldb];
+      sB[kk][i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sA[kk][tx + 16 * i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = sB[kk][ty + 16 * i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fma(a[i], b[jj], acc[i][jj]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int col = n0 + ty + 16 * jj;
+    if (col >= N) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = m0 + tx + 16 * i;
+      if (row >= M) continue;
+      double* cp = C + row + static_cast<int64_t>(col) * ldc;
+      double v = alpha * acc[i][jj];
+      if (beta != 0.0) v += beta * *cp;
+      *cp = v;
+    }
+  }
+}
+
+// C = beta * C (k == 0 or alpha == 0 degenerate case of dgemm)
+__global__ void scale_c_kernel(int M, int N, double beta, double* __restrict__ C, int64_t ldc) {
+  const int64_t total = static_cast<int64_t>(M) * N;
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = e % M, c = e / M;
+    double* cp = C + r + c * ldc;
+    *cp = (beta == 0.0) ? 0.0 : beta * *cp;
+  }
+}
+
+bool is_trans(char t) { return t == 'T' || t == 't' || t == 'C' || t == 'c'; }
+bool is_notrans(char t) { return t == 'N' || t == 'n'; }
+
+template <bool AK, bool BK_>
+int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_t ldc, int M, int N, int K,
+               double alpha, double beta, cudaStream_t stream) {
+  static bool configured = false;  // per template instantiation
+  auto kern = gemm_f64_tma_kernel<AK, BK_>;
+  if (!configured) {
+    CANDMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  const int tilesM = (M + BM - 1) / BM, tilesN = (N + BN - 1) / BN;
+  const int64_t ntiles = static_cast<int64_t>(tilesM) * tilesN;
+  const int grid = static_cast<int>(ntiles < runtime().num_sms ? ntiles : runtime().num_sms);
+  kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmB, C, ldc, M, N, K, alpha, beta, tilesM, tilesN);
+  CANDMC_CUDA(cudaGetLastError());
+  runtime().launches++;
+  return OK;
+}
+
+}  // namespace
+
+int gemm_f64(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+             int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
+             cudaStream_t stream) {
+  CANDMC_TRY(runtime_require());
+  CANDMC_CHECK(is_trans(transa) || is_notrans(transa), "dgemm: bad transa '%c'", transa);
+  CANDMC_CHECK(is_trans(transb) || is_notrans(transb), "dgemm: bad transb '%c'", transb);
+  const bool tA = is_trans(transa), tB = is_trans(transb);
+  CANDMC_CHECK(m >= 0 && n >= 0 && k >= 0, "dgemm: negative dimension m=%lld n=%lld k=%lld", (long long)m,
+               (long long)n, (long long)k);
+  CANDMC_CHECK(m < (1LL << 31) && n < (1LL << 31) && k < (1LL << 31), "dgemm: dimension exceeds 2^31-1");
+  const int64_t rowsA = tA ? k : m, rowsB = tB ? n : k;
+  CANDMC_CHECK(lda >= (rowsA > 1 ? rowsA : 1), "dgemm: lda=%lld < %lld", (long long)lda, (long long)rowsA);
+  CANDMC_CHECK(ldb >= (rowsB > 1 ? rowsB : 1), "dgemm: ldb=%lld < %lld", (long long)ldb, (long long)rowsB);
+  CANDMC_CHECK(ldc >= (m > 1 ? m : 1), "dgemm: ldc=%lld < %lld", (long long)ldc, (long long)m);
+  if (m == 0 || n == 0) return OK;
+  const int M = (int)m, N = (int)n, K = (int)k;
+
+  if (k == 0 || alpha == 0.0) {
+    if (beta == 1.0) return OK;
+    const int64_t total = m * n;
+    int grid = (int)((total + 255) / 256);
+    const int cap = runtime().num_sms * 8;
+    if (grid > cap) grid = cap;
+    scale_c_kernel<<<grid, 256, 0, stream>>>(M, N, beta, C, ldc);
+    CANDMC_CUDA(cudaGetLastError());
+    runtime().launches++;
+    return OK;
+  }
+
+  const bool aligned = (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(B) % 16 == 0) &&
+                       (lda % 2 == 0) && (ldb % 2 == 0) && !runtime().force_generic;
+  if (aligned) {
+    // tensor maps: dim0 is the contiguous (stored-row) dimension of the operand
+    CUtensorMap tmA, tmB;
+    const bool AK = tA;    // op(A)(m,kk) = A[kk + m*lda]  -> K contiguous
+    const bool BKm = !tB;  // op(B)(kk,n) = B[kk + n*ldb]  -> K contiguous
+    CANDMC_TRY(encode_tmap_f64(&tmA, A, AK ? k : m, AK ? m : k, lda, 16, AK ? BM : 16));
+    CANDMC_TRY(encode_tmap_f64(&tmB, B, BKm ? k : n, BKm ? n : k, ldb, 16, BKm ? BN : 16));
+    if (AK && BKm) return launch_tma<true, true>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream);
+    if (AK && !BKm) return launch_tma<true, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream);
+    if (!AK && BKm) return launch_tma<false, true>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream);
+    return launch_tma<false, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream);
+  }
+
+  dim3 grid((M + GT - 1) / GT, (N + GT - 1) / GT);
+  CANDMC_CHECK(grid.y <= 65535, "dgemm(generic path): n too large for unaligned operands");
+  gemm_f64_generic_kernel<<<grid, 256, 0, stream>>>(tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  CANDMC_CUDA(cudaGetLastError());
+  runtime().launches++;
+  return OK;
+}
+
+}  // namespace candmc

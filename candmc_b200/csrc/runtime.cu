@@ -1,0 +1,119 @@
+// candmc_b200 — runtime: device binding, error string, workspace, TMA descriptor encoding.
+#include "runtime.h"
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace candmc {
+
+namespace {
+thread_local char g_err[1024] = "";
+Runtime g_rt;
+}  // namespace
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+Runtime& runtime() { return g_rt; }
+
+int runtime_init(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_last_error("candmc_b200: no CUDA device visible (%s); this library has no CPU path",
+                   e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return ERR_NODEVICE;
+  }
+  if (device < 0) CANDMC_CUDA(cudaGetDevice(&device));
+  CANDMC_CHECK(device < count, "candmc_init: device %d out of range (%d visible)", device, count);
+  if (g_rt.initialized && g_rt.device == device) return OK;
+  CANDMC_CHECK(!g_rt.initialized, "candmc_init: already bound to device %d (one GPU per process)", g_rt.device);
+  CANDMC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CANDMC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_last_error("candmc_b200: device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major,
+                   prop.minor);
+    return ERR_NODEVICE;
+  }
+  g_rt.device = device;
+  g_rt.num_sms = prop.multiProcessorCount;
+  g_rt.cc_major = prop.major;
+  g_rt.cc_minor = prop.minor;
+  CANDMC_CUDA(cudaStreamCreateWithFlags(&g_rt.comm_stream, cudaStreamNonBlocking));
+  CANDMC_CUDA(cudaStreamCreateWithFlags(&g_rt.aux_stream, cudaStreamNonBlocking));
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  CANDMC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  CANDMC_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess,
+               "candmc_init: driver does not export cuTensorMapEncodeTiled");
+  g_rt.pfn_encode_tiled = fn;
+  g_rt.initialized = true;
+  return OK;
+}
+
+int runtime_require() {
+  if (g_rt.initialized) return OK;
+  return runtime_init(-1);
+}
+
+int runtime_finalize() {
+  if (!g_rt.initialized) return OK;
+  if (g_rt.workspace) cudaFree(g_rt.workspace);
+  if (g_rt.comm_stream) cudaStreamDestroy(g_rt.comm_stream);
+  if (g_rt.aux_stream) cudaStreamDestroy(g_rt.aux_stream);
+  g_rt = Runtime();
+  return OK;
+}
+
+int workspace_get(size_t bytes, void** out) {
+  CANDMC_TRY(runtime_require());
+  if (bytes > g_rt.workspace_bytes) {
+    if (g_rt.workspace) {
+      CANDMC_CUDA(cudaDeviceSynchronize());
+      CANDMC_CUDA(cudaFree(g_rt.workspace));
+      g_rt.workspace = nullptr;
+      g_rt.workspace_bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&g_rt.workspace, bytes);
+    if (e != cudaSuccess) {
+      set_last_error("workspace: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+      return ERR_NOMEM;
+    }
+    g_rt.workspace_bytes = bytes;
+  }
+  *out = g_rt.workspace;
+  return OK;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_tmap_f64(CUtensorMap* out, const double* base, int64_t dim0, int64_t dim1, int64_t ld, int box0,
+                    int box1) {
+  CANDMC_TRY(runtime_require());
+  CANDMC_CHECK(dim0 > 0 && dim1 > 0, "tensor map: empty operand");
+  cuuint64_t gdim[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<PFN_encodeTiled>(g_rt.pfn_encode_tiled)(
+      out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (CUresult %d) dims=%lldx%lld ld=%lld box=%dx%d ptr=%p", (int)r,
+                   (long long)dim0, (long long)dim1, (long long)ld, box0, box1, (const void*)base);
+    return ERR_CUDA;
+  }
+  return OK;
+}
+
+}  // namespace candmc

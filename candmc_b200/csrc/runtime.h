@@ -1,0 +1,56 @@
+// candmc_b200 — per-process runtime state (device binding, streams, workspace, TMA descriptor encoding).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace candmc {
+
+struct Runtime {
+  bool initialized = false;
+  int device = -1;
+  int num_sms = 0;
+  int cc_major = 0, cc_minor = 0;
+  bool force_generic = false;        // test hook: route dgemm through the CUDA-core kernel
+  unsigned long long launches = 0;   // kernels launched by this library (bench.py's gpu_launches)
+  cudaStream_t comm_stream = nullptr;   // NCCL panel traffic
+  cudaStream_t aux_stream = nullptr;    // second compute/copy stream
+  void* workspace = nullptr;            // grow-only device scratch
+  size_t workspace_bytes = 0;
+  void* pfn_encode_tiled = nullptr;     // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
+};
+
+Runtime& runtime();
+
+// Binds to `device` (or the current device if < 0), verifies compute capability 10.x, creates streams.
+int runtime_init(int device);
+// Lazily initialises on the current device; fails with ERR_NODEVICE when no usable GPU exists.
+int runtime_require();
+int runtime_finalize();
+// Grow-only scratch; contents undefined.  Not thread safe (one rank = one host thread, as in the reference).
+int workspace_get(size_t bytes, void** out);
+
+// 2-D FP64 tensor map with 128 B swizzle: dim0 contiguous (dim0 x dim1 elements, leading dimension `ld`),
+// box = box0 x box1 elements (box0 * 8 bytes must be <= 128).
+int encode_tmap_f64(CUtensorMap* out, const double* base, int64_t dim0, int64_t dim1, int64_t ld, int box0,
+                    int box1);
+
+// ---- kernels' host entry points (device pointers only) ---------------------------------------
+int gemm_f64(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+             int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
+             cudaStream_t stream);
+int lda_copy_f64(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B,
+                 cudaStream_t stream);
+int lda_axpby_f64(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B, double a,
+                  double b, cudaStream_t stream);
+int transpose_f64(int64_t rows, int64_t cols, const double* A, int64_t lda, double* B, int64_t ldb,
+                  cudaStream_t stream);
+int fill_f64(double* X, int64_t count, double value, cudaStream_t stream);
+// sum_k parts[k] -> out (count doubles each; parts may alias out for k==0)
+int drand48_fill_f64(double* X, int64_t nrow, int64_t ncol, int64_t ld, int64_t row0, int64_t col0, int64_t n_global,
+                     int which, cudaStream_t stream);
+int frob_diff_f64(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t nrow, int64_t ncol,
+                  double* out2 /* device: {||X-Y||_F^2, ||Y||_F^2} */, cudaStream_t stream);
+
+}  // namespace candmc

@@ -1,0 +1,149 @@
+/* candmc_b200 — C ABI of the B200-native CANMM hot path (libcandmc_b200.so).
+ *
+ * This is the drop-in boundary: plain C, pointers and sizes only, no CUDA / torch / NCCL types.  Each entry
+ * point names the reference interface (solomonik/CANDMC, path:line) it replaces.  The C++ headers next to this
+ * file (CANDMC.h and candmc/...) re-export the reference's own C++ signatures on top of these calls; the Python
+ * package `candmc_b200` binds the same symbols with ctypes.  See INTEGRATION.md.
+ *
+ * Conventions
+ *  - All matrices are FP64, column-major, exactly as in the reference.
+ *  - Matrix pointers may be DEVICE pointers (fast path; what bench.py's device-resident leg uses) or HOST
+ *    pointers (what the reference's own tests pass); host operands are staged through device memory inside the
+ *    call.  The kind is detected with cudaPointerGetAttributes.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls with device pointers are
+ *    asynchronous on that stream; calls with any host operand return after the result is back in host memory.
+ *  - Every function returns CANDMC_OK (0) or an error code; candmc_last_error() gives the text.  There is NO
+ *    CPU fallback: without a compute-capability-10.x GPU every compute call returns CANDMC_ERR_NODEVICE.
+ *    (The reference has no return codes — it asserts/ABORTs, alg/shared/util.h:127-138; the C++ shim keeps that.)
+ */
+#ifndef CANDMC_B200_H
+#define CANDMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CANDMC_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+  CANDMC_OK = 0,
+  CANDMC_ERR_INVALID = 1,
+  CANDMC_ERR_CUDA = 2,
+  CANDMC_ERR_NCCL = 3,
+  CANDMC_ERR_NOMEM = 4,
+  CANDMC_ERR_NODEVICE = 5
+};
+
+/* ---- runtime ---------------------------------------------------------------------------------------------- */
+int candmc_version(void);
+const char* candmc_last_error(void);
+/* Bind this process to one GPU (device < 0: the current CUDA device).  One process per GPU, like one MPI rank
+ * per grid point in the reference (alg/shared/comm.h:125-136 INIT_COMM). */
+int candmc_init(int device);
+int candmc_finalize(void);
+int candmc_device_sm_count(int* out);
+/* Number of kernels this library has launched so far in this process (bench.py reports the delta). */
+unsigned long long candmc_launch_count(void);
+/* Test hook: 1 routes candmc_dgemm through the generic CUDA-core kernel instead of the TMA+DMMA kernel. */
+int candmc_debug_force_generic_gemm(int on);
+
+/* ---- local kernels ---------------------------------------------------------------------------------------- */
+/* C = alpha*op(A)*op(B) + beta*C.  Replaces cdgemm (alg/shared/lapack.h:10-16, lapack.cxx:425-434) and the
+ * direct dgemm_ wrapper of split-dim Cannon (alg/MM/splitdim_cannon/spcannon_internal.h:51-63). */
+int candmc_dgemm(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                 int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, void* stream);
+/* B(nrow x ncol, lda_B) = A(nrow x ncol, lda_A).  Replaces lda_cpy (alg/shared/util.h:459-471). */
+int candmc_lda_cpy(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B,
+                   void* stream);
+/* B = b*B + a*A.  Replaces the scaled lda_cpy overload (alg/shared/util.h:484-501). */
+int candmc_lda_cpy_scaled(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B,
+                          double a, double b, void* stream);
+/* B(cols x rows, ldb) = A(rows x cols, lda)^T, out of place.  Replaces TRANSPOSE/naive_transp
+ * (alg/MM/splitdim_cannon/spcannon_internal.h:66-72; that one copies back in place). */
+int candmc_transpose(int64_t rows, int64_t cols, const double* A, int64_t lda, double* B, int64_t ldb,
+                     void* stream);
+/* Fill X(nrow x ncol, ld) with the reference unit test's per-element generator
+ * (test/MM/topo_pdgemm_unit.cxx:250-256,301-307): element at global (row0+r, col0+c) is the `which`-th (0=A, 1=B)
+ * drand48() draw after srand48((col0+c)*n_global + (row0+r)).  X must be a device pointer. */
+int candmc_fill_drand48(double* X, int64_t nrow, int64_t ncol, int64_t ld, int64_t row0, int64_t col0,
+                        int64_t n_global, int which, void* stream);
+/* out[0] = ||X - Y||_F^2, out[1] = ||Y||_F^2 (host doubles; synchronises).  X, Y device pointers. */
+int candmc_frob_diff(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t nrow, int64_t ncol,
+                     double* out_host2, void* stream);
+
+/* ---- processor-grid communicators ------------------------------------------------------------------------- */
+/* Opaque handle standing in for the reference's CommData_t.cm / MPI_Comm (alg/shared/comm.h:32-37). */
+typedef struct candmc_comm candmc_comm_t;
+
+#define CANDMC_UNIQUE_ID_BYTES 128
+/* Rank 0 calls this and ships the 128 bytes to every rank by any out-of-band channel (bench.py uses
+ * torch.distributed; the native launcher uses a file) — the role MPI_Init plays in INIT_COMM (comm.h:125-136). */
+int candmc_get_unique_id(void* out_128_bytes);
+/* Collective over all ranks: builds the world communicator (an NCCL communicator on this process's GPU). */
+int candmc_comm_init_rank(const void* unique_id_128_bytes, int nranks, int rank, candmc_comm_t** out);
+/* Collective over `parent`: MPI_Comm_split semantics (same color -> same child, ordered by key).  Replaces the
+ * MPI_Comm_split calls inside SETUP_SUB_COMM / RSETUP_KDIR_COMM / RSETUP_LAYER_COMM (comm.h:145-195). */
+int candmc_comm_split(candmc_comm_t* parent, int color, int key, candmc_comm_t** out);
+int candmc_comm_free(candmc_comm_t* comm); /* FREE_CDT, comm.h:199-201 */
+int candmc_comm_rank(const candmc_comm_t* comm, int* rank);
+int candmc_comm_size(const candmc_comm_t* comm, int* size);
+int candmc_comm_barrier(candmc_comm_t* comm); /* device-side barrier + host sync */
+/* Collectives on FP64 buffers (device or host pointers) — the MPI calls of the hot path:
+ * MPI_Bcast (summa.cxx:63-84 via POST_BCAST comm.h:110-112), MPI_Allreduce(SUM) (d25_summa.cxx:149,221; qr_2d.cxx:265). */
+int candmc_comm_bcast(candmc_comm_t* comm, double* buf, int64_t count, int root, void* stream);
+int candmc_comm_allreduce_sum(candmc_comm_t* comm, const double* sendbuf, double* recvbuf, int64_t count,
+                              void* stream);
+
+/* ---- distributed multiplies (alg/MM) ---------------------------------------------------------------------- */
+/* Same fields and meaning as ctb_args_t (alg/MM/topo_pdgemm/topo_pdgemm_algs.h:6-15). */
+typedef struct candmc_ctb_args {
+  char trans_A;
+  char trans_B;
+  int64_t n;           /* global matrix dimension */
+  int64_t lda_A;
+  int64_t lda_B;
+  int64_t lda_C;
+  int64_t buffer_size; /* BYTES available in `buffer`; checked like the reference's ASSERTs */
+  int ovp;
+} candmc_ctb_args_t;
+
+/* 2D SUMMA, C = A*B on a q x q grid.  Replaces summa (topo_pdgemm_algs.h:17-23, summa.cxx:26-101).
+ * cdt_row: communicator along my grid row (rank = my column); cdt_col: along my grid column (rank = my row).
+ * `buffer` may be NULL (an internal device workspace is used); if non-NULL it must hold buffer_size >= 4*b*b*8 bytes. */
+int candmc_summa(const candmc_ctb_args_t* args, const double* mat_A, const double* mat_B, double* mat_C,
+                 double* buffer, candmc_comm_t* cdt_row, candmc_comm_t* cdt_col, void* stream);
+/* 2.5D SUMMA on q x q x c: layer l multiplies k-panels [l*q/c, (l+1)*q/c), then the depth sum leaves the full C
+ * block on every layer.  Replaces d25_summa / d25_summa_ovp (topo_pdgemm_algs.h:25-49, d25_summa.cxx:33-281);
+ * `ovp` picks the reference's buffer-size rule (3 vs 5 b^2 doubles) — on this implementation communication is
+ * always overlapped.  Unlike the reference (SURVEY App. A-1,A-3) the first panel of every layer uses beta = 0 and
+ * mat_A / mat_B are preserved.  Extension: cdt_row/cdt_col of size 1 with cdt_kdir of size c splits k across
+ * the c ranks (the 1 x 1 x c grid the reference's q % c == 0 assert forbids). */
+int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const double* mat_B, double* mat_C,
+                     double* buffer, candmc_comm_t* cdt_row, candmc_comm_t* cdt_col, candmc_comm_t* cdt_kdir,
+                     int ovp, void* stream);
+/* SUMMA over (x1,y1) nested in Cannon over (x2,y2).  Replaces bcast_cannon_4d (topo_pdgemm_algs.h:51-59,
+ * dual_cannon.cxx:40-215) with its *intended* semantics (the reference deadlocks for x2_np > 1). */
+int candmc_bcast_cannon_4d(const candmc_ctb_args_t* args, const double* mat_A, const double* mat_B, double* mat_C,
+                           double* buffer, candmc_comm_t* cdt_x1, candmc_comm_t* cdt_y1, candmc_comm_t* cdt_x2,
+                           candmc_comm_t* cdt_y2, void* stream);
+/* Split-dimensional Cannon, C <- alpha*A*B + beta*C with rectangular local blocks (A m x k, B k x n or n x k
+ * per transp_B, C m x n).  Replaces kput_cannon (bidir != 0) / kuni_cannon (bidir == 0)
+ * (alg/MM/splitdim_cannon/spcannon.h:31-59, spcannon.cxx:237-347).  `world` must contain kary^ndim ranks laid out
+ * as in spcannon.cxx:59-62; only ndim == 2 is implemented (an NVSwitch crossbar has no torus dimensions to split
+ * over).  A and B are preserved (the reference destroys them). */
+int candmc_spcannon(int bidir, int rank, int kary, int ndim, candmc_comm_t* world, int n, int m, int k,
+                    char transp_A, double alpha, const double* A, char transp_B, double beta, const double* B,
+                    double* C, void* stream);
+/* CAQR trailing update A <- A - Y * (T^-1 * (Y^T A)) on one grid column.  Replaces the GEMM pair + allreduce of
+ * upd_A (alg/QR/qr_2d/qr_2d.cxx:259,265,271,275) for the W_is_T case: Tinv is the b x b lower-triangular factor the
+ * reference applies with cdtrsm('L','L','N','N'); here the caller passes it already inverted (Tinv = T^-1, lower
+ * triangular) and it is applied as a GEMM.  ccol may be NULL (single process column). */
+int candmc_upd_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
+                 const double* Tinv, candmc_comm_t* ccol, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CANDMC_B200_H */

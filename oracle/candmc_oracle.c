@@ -1,0 +1,402 @@
+/* candmc_oracle.c — TEST INFRASTRUCTURE ONLY: plain-C restatement of the reference CANMM hot path.
+ * See candmc_oracle.h for scope, pinning and who may load this.  Every routine cites the reference lines
+ * (solomonik/CANDMC, relative to /root/reference) whose data movement it follows; arithmetic is a plain
+ * C = alpha*op(A)*op(B) + beta*C loop nest (the reference delegates it to an unpinned vendor dgemm_).
+ */
+#include "candmc_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------------------------
+ * glibc srand48 / drand48 (used by test/MM/topo_pdgemm_unit.cxx:250-256 and test/MM/test_spc.cxx:66-76)
+ * X0 = (seed mod 2^32) * 2^16 + 0x330E ;  X <- (0x5DEECE66D * X + 0xB) mod 2^48 ;  value = X / 2^48
+ * ---------------------------------------------------------------------------------------------------------- */
+void oracle_srand48(uint64_t* state, int64_t seed) { *state = (((uint64_t)seed & 0xffffffffULL) << 16) | 0x330EULL; }
+
+double oracle_drand48(uint64_t* state) {
+  *state = (0x5DEECE66DULL * *state + 0xBULL) & ((1ULL << 48) - 1);
+  return (double)*state * (1.0 / 281474976710656.0);
+}
+
+double oracle_unit_elem(int64_t r, int64_t c, int64_t n, int which) {
+  uint64_t s;
+  double v;
+  oracle_srand48(&s, c * n + r);
+  v = oracle_drand48(&s);
+  if (which) v = oracle_drand48(&s);
+  return v;
+}
+
+void oracle_fill_unit_block(double* X, int64_t nrow, int64_t ncol, int64_t ld, int64_t row0, int64_t col0, int64_t n,
+                            int which) {
+  for (int64_t c = 0; c < ncol; ++c)
+    for (int64_t r = 0; r < nrow; ++r) X[r + c * ld] = oracle_unit_elem(row0 + r, col0 + c, n, which);
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * cdgemm (alg/shared/lapack.cxx:425-434 -> Fortran dgemm_ semantics, column-major)
+ * ---------------------------------------------------------------------------------------------------------- */
+static int is_t(char t) { return t == 'T' || t == 't' || t == 'C' || t == 'c'; }
+
+void oracle_dgemm(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                  int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
+  const int ta = is_t(transa), tb = is_t(transb);
+  double* At = NULL;
+  if (m <= 0 || n <= 0) return;
+  for (int64_t j = 0; j < n; ++j)
+    for (int64_t i = 0; i < m; ++i) C[i + j * ldc] = (beta == 0.0) ? 0.0 : beta * C[i + j * ldc];
+  if (k <= 0 || alpha == 0.0) return;
+  if (ta) { /* make op(A) column-major m x k so the inner loop is unit stride */
+    At = (double*)malloc(sizeof(double) * (size_t)m * (size_t)k);
+    for (int64_t p = 0; p < k; ++p)
+      for (int64_t i = 0; i < m; ++i) At[i + p * m] = A[p + i * lda];
+    A = At;
+    lda = m;
+  }
+  for (int64_t j = 0; j < n; ++j) {
+    double* cj = C + j * ldc;
+    for (int64_t p = 0; p < k; ++p) {
+      const double bpj = alpha * (tb ? B[j + p * ldb] : B[p + j * ldb]);
+      const double* ap = A + p * lda;
+      for (int64_t i = 0; i < m; ++i) cj[i] += ap[i] * bpj;
+    }
+  }
+  free(At);
+}
+
+/* lda_cpy (alg/shared/util.h:459-471) */
+void oracle_lda_cpy(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B) {
+  for (int64_t i = 0; i < ncol; ++i) memcpy(B + lda_B * i, A + lda_A * i, (size_t)nrow * sizeof(double));
+}
+
+/* scaled lda_cpy (alg/shared/util.h:484-501): B = B*b + A*a */
+void oracle_lda_cpy_scaled(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B,
+                           double a, double b) {
+  for (int64_t i = 0; i < ncol; ++i)
+    for (int64_t j = 0; j < nrow; ++j) B[lda_B * i + j] = B[lda_B * i + j] * b + A[lda_A * i + j] * a;
+}
+
+/* out-of-place transpose, the arithmetic of TRANSPOSE/naive_transp (alg/MM/splitdim_cannon/spcannon_internal.h:66-72):
+ * B(cols x rows) = A(rows x cols)^T */
+void oracle_transpose(int64_t rows, int64_t cols, const double* A, int64_t lda, double* B, int64_t ldb) {
+  for (int64_t c = 0; c < cols; ++c)
+    for (int64_t r = 0; r < rows; ++r) B[c + r * ldb] = A[r + c * lda];
+}
+
+static double* dalloc(size_t n) {
+  double* p = (double*)calloc(n ? n : 1, sizeof(double));
+  if (!p) abort();
+  return p;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * summa (alg/MM/topo_pdgemm/summa.cxx:26-101).  World rank r = row*q + col (comm.h:183-195 with one layer).
+ * For i < q: the rank in grid column i broadcasts its A block along its row (:59-73), the rank in grid row i
+ * broadcasts its B block along its column (:74-88), every rank multiplies with beta = (i > 0) (:96-97).
+ * ---------------------------------------------------------------------------------------------------------- */
+int oracle_summa(int64_t n, int q, char trans_A, char trans_B, double* const* A, int64_t lda_A, double* const* B,
+                 int64_t lda_B, double* const* C, int64_t lda_C) {
+  if (q <= 0 || n % q != 0) return -1;
+  const int64_t b = n / q;
+  const int P = q * q;
+  double** loc_A = (double**)malloc(sizeof(double*) * (size_t)P);
+  double** loc_B = (double**)malloc(sizeof(double*) * (size_t)P);
+  for (int r = 0; r < P; ++r) { /* :53-54 — inputs are copied out of their lda */
+    loc_A[r] = dalloc((size_t)(b * b));
+    loc_B[r] = dalloc((size_t)(b * b));
+    oracle_lda_cpy(b, b, lda_A, b, A[r], loc_A[r]);
+    oracle_lda_cpy(b, b, lda_B, b, B[r], loc_B[r]);
+  }
+  for (int i = 0; i < q; ++i)
+    for (int row = 0; row < q; ++row)
+      for (int col = 0; col < q; ++col) {
+        const double* buf_A = loc_A[row * q + i]; /* bcast along cdt_row, root = column i */
+        const double* buf_B = loc_B[i * q + col]; /* bcast along cdt_col, root = row i    */
+        oracle_dgemm(trans_A, trans_B, b, b, b, 1.0, buf_A, b, buf_B, b, (i > 0) * 1.0, C[row * q + col], lda_C);
+      }
+  for (int r = 0; r < P; ++r) {
+    free(loc_A[r]);
+    free(loc_B[r]);
+  }
+  free(loc_A);
+  free(loc_B);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * d25_summa / d25_summa_ovp (alg/MM/topo_pdgemm/d25_summa.cxx:33-281).  World rank r = layer*q*q + row*q + col
+ * (comm.h:171-195).  Layer l handles panels i in [l*q/c, (l+1)*q/c) (:124,151), accumulating into a zeroed buf_C
+ * with beta = (i > 0) (:200-201) — the reference relies on the buffer being zero, which this
+ * restatement makes explicit.  The ovp variant defers each multiply by one step through the ovp_A/ovp_B swap
+ * (:125-148); with zeroed buffers its sums are the same panels in the same order.  Finally MPI_Allreduce(SUM) over
+ * the depth communicator leaves sum_l buf_C on every layer (:149,221).
+ * Extension (NOT in the reference, whose q % c == 0 assert forbids it): q == 1 with c > 1 splits k across the c
+ * ranks — rank l multiplies A[:, l*b/c:(l+1)*b/c] * B[l*b/c:(l+1)*b/c, :] — the 2-GPU configuration of SURVEY §8e.
+ * ---------------------------------------------------------------------------------------------------------- */
+int oracle_d25_summa(int64_t n, int q, int c, int ovp, char trans_A, char trans_B, double* const* A, double* const* B,
+                     double* const* C) {
+  if (q <= 0 || c <= 0 || n % q != 0) return -1;
+  const int64_t b = n / q;
+  const int q2 = q * q;
+  const int ksplit = (q == 1 && c > 1);
+  if (!ksplit && q % c != 0) return -1; /* :63 */
+  if (ksplit && (b % c != 0 || is_t(trans_A) || is_t(trans_B))) return -1;
+  double** buf_C = (double**)malloc(sizeof(double*) * (size_t)(q2 * c));
+  for (int l = 0; l < c; ++l)
+    for (int row = 0; row < q; ++row)
+      for (int col = 0; col < q; ++col) {
+        const int r = l * q2 + row * q + col;
+        double* bc = buf_C[r] = dalloc((size_t)(b * b));
+        if (ksplit) {
+          const int64_t kb = b / c;
+          oracle_dgemm('N', 'N', b, b, kb, 1.0, A[r] + l * kb * b, b, B[r] + l * kb, b, 0.0, bc, b);
+          continue;
+        }
+        if (!ovp) {
+          for (int i = l * (q / c); i < (l + 1) * (q / c); ++i) {
+            const double* pa = A[l * q2 + row * q + i]; /* root column i of my row, same layer (:153-158) */
+            const double* pb = B[l * q2 + i * q + col]; /* root row i of my column         (:159-164) */
+            oracle_dgemm(trans_A, trans_B, b, b, b, 1.0, pa, b, pb, b, (i > 0) * 1.0, bc, b);
+          }
+        } else {
+          double* zero = dalloc((size_t)(b * b)); /* never-written ovp_A / ovp_B of a zeroed buffer */
+          const double *ovp_A = zero, *ovp_B = zero;
+          int i;
+          for (i = l * (q / c); i < (l + 1) * (q / c); ++i) {
+            const double* pa = A[l * q2 + row * q + i];
+            const double* pb = B[l * q2 + i * q + col];
+            if (i > 0) oracle_dgemm(trans_A, trans_B, b, b, b, 1.0, ovp_A, b, ovp_B, b, 1.0, bc, b); /* :136-139 */
+            ovp_A = pa; /* :141-142 swap */
+            ovp_B = pb;
+          }
+          oracle_dgemm(trans_A, trans_B, b, b, b, 1.0, ovp_A, b, ovp_B, b, (i > 0) * 1.0, bc, b); /* :147-148 */
+          free(zero);
+        }
+      }
+  for (int row = 0; row < q; ++row)
+    for (int col = 0; col < q; ++col) {
+      double* sum = dalloc((size_t)(b * b));
+      for (int l = 0; l < c; ++l) {
+        const double* bc = buf_C[l * q2 + row * q + col];
+        for (int64_t e = 0; e < b * b; ++e) sum[e] += bc[e];
+      }
+      for (int l = 0; l < c; ++l) memcpy(C[l * q2 + row * q + col], sum, sizeof(double) * (size_t)(b * b));
+      free(sum);
+    }
+  for (int r = 0; r < q2 * c; ++r) free(buf_C[r]);
+  free(buf_C);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * bcast_cannon_4d (alg/MM/topo_pdgemm/dual_cannon.cxx:40-215), INTENDED semantics: the reference's stagger has
+ * mismatched tags / waits (:116-135) and deadlocks for x2_np > 1, so for x2_np > 1 this follows
+ * the algorithm the code spells out rather than an observable run:
+ *   rank r = x1 + x1_np*(y1 + x1_np*(x2 + x2_np*y2))  (test/MM/topo_pdgemm_unit.cxx:53-68),
+ *   stagger: A moves along x2 to (x2 - y2), B along y2 to (y2 - x2)            (:107-137),
+ *   for i2 < x2_np { for i1 < x1_np { bcast A along x1 from x1==i1, B along y1 from y1==i1; multiply } (:149-195)
+ *                    shift A along x2 by -1, B along y2 by -1 }                (:196-213).
+ * ---------------------------------------------------------------------------------------------------------- */
+static int wrap(int a, int b) { return ((a % b) + b) % b; }
+
+int oracle_bcast_cannon_4d(int64_t n, int x1_np, int x2_np, int ovp, double* const* A, double* const* B,
+                           double* const* C) {
+  (void)ovp; /* only changes when the multiply is issued (:163-166,191-194), not what is summed */
+  if (x1_np <= 0 || x2_np <= 0 || n % ((int64_t)x1_np * x2_np) != 0) return -1;
+  const int64_t b = n / ((int64_t)x1_np * x2_np);
+  const int P = x1_np * x1_np * x2_np * x2_np;
+#define RK(x1, y1, x2, y2) ((x1) + x1_np * ((y1) + x1_np * ((x2) + x2_np * (y2))))
+  const double** curA = (const double**)malloc(sizeof(double*) * (size_t)P);
+  const double** curB = (const double**)malloc(sizeof(double*) * (size_t)P);
+  const double** nxtA = (const double**)malloc(sizeof(double*) * (size_t)P);
+  const double** nxtB = (const double**)malloc(sizeof(double*) * (size_t)P);
+  for (int y2 = 0; y2 < x2_np; ++y2)
+    for (int x2 = 0; x2 < x2_np; ++x2)
+      for (int y1 = 0; y1 < x1_np; ++y1)
+        for (int x1 = 0; x1 < x1_np; ++x1) { /* after the stagger I hold what (x2+y2) resp. (y2+x2) owned */
+          curA[RK(x1, y1, x2, y2)] = A[RK(x1, y1, wrap(x2 + y2, x2_np), y2)];
+          curB[RK(x1, y1, x2, y2)] = B[RK(x1, y1, x2, wrap(y2 + x2, x2_np))];
+        }
+  for (int i2 = 0; i2 < x2_np; ++i2) {
+    for (int i1 = 0; i1 < x1_np; ++i1)
+      for (int y2 = 0; y2 < x2_np; ++y2)
+        for (int x2 = 0; x2 < x2_np; ++x2)
+          for (int y1 = 0; y1 < x1_np; ++y1)
+            for (int x1 = 0; x1 < x1_np; ++x1) {
+              const double* mul_A = curA[RK(i1, y1, x2, y2)]; /* bcast along cdt_x1, root i1 */
+              const double* mul_B = curB[RK(x1, i1, x2, y2)]; /* bcast along cdt_y1, root i1 */
+              oracle_dgemm('N', 'N', b, b, b, 1.0, mul_A, b, mul_B, b, (i1 > 0 || i2 > 0) * 1.0,
+                           C[RK(x1, y1, x2, y2)], b);
+            }
+    if (i2 < x2_np - 1) {
+      for (int y2 = 0; y2 < x2_np; ++y2)
+        for (int x2 = 0; x2 < x2_np; ++x2)
+          for (int y1 = 0; y1 < x1_np; ++y1)
+            for (int x1 = 0; x1 < x1_np; ++x1) { /* receive from +1 (:198-209) */
+              nxtA[RK(x1, y1, x2, y2)] = curA[RK(x1, y1, wrap(x2 + 1, x2_np), y2)];
+              nxtB[RK(x1, y1, x2, y2)] = curB[RK(x1, y1, x2, wrap(y2 + 1, x2_np))];
+            }
+      const double** t;
+      t = curA, curA = nxtA, nxtA = t;
+      t = curB, curB = nxtB, nxtB = t;
+    }
+  }
+#undef RK
+  free(curA);
+  free(curB);
+  free(nxtA);
+  free(nxtB);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * kput_cannon / kuni_cannon (alg/MM/splitdim_cannon/spcannon.cxx:237-347): C <- alpha*A*B + beta*C on a
+ * kary-ary ndim-cube.  Rank digits base kary: digit 2j = A-direction coordinate, digit 2j+1 = B-direction
+ * coordinate (:59-62).  A is canonicalised to m x k, B to B^T = n x k (:262-267); slices are contiguous ranges of
+ * those arrays.  uni_stagger (:33-84), bdr_shift (:87-162), uni_shift (:165-234) are simulated for all ranks in
+ * lockstep: every MPI_Put between two fences becomes a copy into the target's fresh buffer, then A = buf_A,
+ * B = buf_B (:76-77,159-160,231-232).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int P, kary, ndim, n, m, k, bidir;
+  double alpha;
+  double **A, **B, **bufA, **bufB; /* per rank, m*k and n*k doubles */
+  double* const* C;
+} spc_t;
+
+static int digit(int rank, int kary, int pos) {
+  for (int i = 0; i < pos; ++i) rank /= kary;
+  return rank % kary;
+}
+static int ipow(int a, int e) {
+  int r = 1;
+  while (e-- > 0) r *= a;
+  return r;
+}
+static void spc_swap(spc_t* s) {
+  for (int r = 0; r < s->P; ++r) { /* memcpy(A, buf_A), memcpy(B, buf_B) */
+    memcpy(s->A[r], s->bufA[r], sizeof(double) * (size_t)s->m * (size_t)s->k);
+    memcpy(s->B[r], s->bufB[r], sizeof(double) * (size_t)s->n * (size_t)s->k);
+  }
+}
+
+static void spc_stagger(spc_t* s, int level) { /* :33-84 */
+  const int half = s->ndim / 2;
+  const int64_t bA = 2 * (int64_t)s->m * s->k / s->ndim, bB = 2 * (int64_t)s->k * s->n / s->ndim;
+  for (int r = 0; r < s->P; ++r)
+    for (int j = 0; j < half; ++j) {
+      const int i = (j + level) % half;
+      const int tA = digit(r, s->kary, 2 * j), tB = digit(r, s->kary, 2 * j + 1);
+      const int dstA = r + (wrap(tA - tB, s->kary) - tA) * ipow(s->kary, 2 * j);
+      const int dstB = r + (wrap(tB - tA, s->kary) - tB) * ipow(s->kary, 2 * j + 1);
+      memcpy(s->bufA[dstA] + i * bA, s->A[r] + i * bA, sizeof(double) * (size_t)bA);
+      memcpy(s->bufB[dstB] + i * bB, s->B[r] + i * bB, sizeof(double) * (size_t)bB);
+    }
+  spc_swap(s);
+  if (level < half - 1) spc_stagger(s, level + 1);
+}
+
+static void spc_shift(spc_t* s, int level, double beta) { /* bdr_shift :87-162 / uni_shift :165-234 */
+  const int half = s->ndim / 2;
+  double dbeta = beta;
+  for (int ka = 0; ka < s->kary; ++ka) {
+    if (level < half - 1) {
+      spc_shift(s, level + 1, dbeta);
+    } else {
+      for (int r = 0; r < s->P; ++r) /* DGEMM('N','T',m,n,k,alpha,A,m,B,n,dbeta,C,m) :117,195 */
+        oracle_dgemm('N', 'T', s->m, s->n, s->k, s->alpha, s->A[r], s->m, s->B[r], s->n, dbeta, s->C[r], s->m);
+    }
+    dbeta = 1.0;
+    for (int r = 0; r < s->P; ++r)
+      for (int j = 0; j < half; ++j) {
+        const int i = (j + level) % half;
+        const int tA = digit(r, s->kary, 2 * j), tB = digit(r, s->kary, 2 * j + 1);
+        const int sA = ipow(s->kary, 2 * j), sB = ipow(s->kary, 2 * j + 1);
+        const int upA = r + (wrap(tA + 1, s->kary) - tA) * sA, dnA = r + (wrap(tA - 1, s->kary) - tA) * sA;
+        const int upB = r + (wrap(tB + 1, s->kary) - tB) * sB, dnB = r + (wrap(tB - 1, s->kary) - tB) * sB;
+        if (s->bidir) { /* halves 2i and 2i+1 travel in opposite directions (:139-152) */
+          const int64_t bA = (int64_t)s->m * s->k / s->ndim, bB = (int64_t)s->k * s->n / s->ndim;
+          memcpy(s->bufA[upA] + 2 * i * bA, s->A[r] + 2 * i * bA, sizeof(double) * (size_t)bA);
+          memcpy(s->bufA[dnA] + (2 * i + 1) * bA, s->A[r] + (2 * i + 1) * bA, sizeof(double) * (size_t)bA);
+          memcpy(s->bufB[upB] + 2 * i * bB, s->B[r] + 2 * i * bB, sizeof(double) * (size_t)bB);
+          memcpy(s->bufB[dnB] + (2 * i + 1) * bB, s->B[r] + (2 * i + 1) * bB, sizeof(double) * (size_t)bB);
+        } else { /* whole slice i travels +1 (:217-224) */
+          const int64_t bA = 2 * (int64_t)s->m * s->k / s->ndim, bB = 2 * (int64_t)s->k * s->n / s->ndim;
+          memcpy(s->bufA[upA] + i * bA, s->A[r] + i * bA, sizeof(double) * (size_t)bA);
+          memcpy(s->bufB[upB] + i * bB, s->B[r] + i * bB, sizeof(double) * (size_t)bB);
+        }
+      }
+    spc_swap(s);
+  }
+}
+
+int oracle_spcannon(int bidir, int kary, int ndim, int n, int m, int k, char transp_A, double alpha, double* const* A,
+                    char transp_B, double beta, double* const* B, double* const* C) {
+  if (ndim < 2 || ndim % 2 != 0 || kary < 1 || k % ndim != 0) return -1; /* :252 assert(k%ndim == 0) */
+  spc_t s;
+  s.P = ipow(kary, ndim);
+  s.kary = kary;
+  s.ndim = ndim;
+  s.n = n;
+  s.m = m;
+  s.k = k;
+  s.bidir = bidir;
+  s.alpha = alpha;
+  s.C = C;
+  s.A = (double**)malloc(sizeof(double*) * (size_t)s.P);
+  s.B = (double**)malloc(sizeof(double*) * (size_t)s.P);
+  s.bufA = (double**)malloc(sizeof(double*) * (size_t)s.P);
+  s.bufB = (double**)malloc(sizeof(double*) * (size_t)s.P);
+  for (int r = 0; r < s.P; ++r) {
+    s.A[r] = dalloc((size_t)m * (size_t)k);
+    s.B[r] = dalloc((size_t)n * (size_t)k);
+    s.bufA[r] = dalloc((size_t)m * (size_t)k);
+    s.bufB[r] = dalloc((size_t)n * (size_t)k);
+    /* canonicalise (:262-267): A -> m x k, B -> B^T (n x k) */
+    if (is_t(transp_A)) oracle_transpose(k, m, A[r], k, s.A[r], m); else memcpy(s.A[r], A[r], sizeof(double) * (size_t)m * (size_t)k);
+    if (!is_t(transp_B)) oracle_transpose(k, n, B[r], k, s.B[r], n); else memcpy(s.B[r], B[r], sizeof(double) * (size_t)n * (size_t)k);
+  }
+  spc_stagger(&s, 0);
+  spc_shift(&s, 0, beta);
+  for (int r = 0; r < s.P; ++r) {
+    free(s.A[r]);
+    free(s.B[r]);
+    free(s.bufA[r]);
+    free(s.bufB[r]);
+  }
+  free(s.A);
+  free(s.B);
+  free(s.bufA);
+  free(s.bufB);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * upd_A GEMM pair (alg/QR/qr_2d/qr_2d.cxx:259,265,271,275), W_is_T case, one process column of nprow ranks:
+ *   W_r = Y_r^T A_r ; W = sum_r W_r (MPI_Allreduce over ccol) ; W <- T^-1 W (cdtrsm L,L,N,N) ; A_r -= Y_r W
+ * ---------------------------------------------------------------------------------------------------------- */
+int oracle_upd_A(int nprow, const int64_t* mb, int64_t kb, int64_t b, double* const* Y, const int64_t* lda_Y,
+                 double* const* A, const int64_t* lda_A, const double* T) {
+  if (nprow <= 0 || kb < 0 || b <= 0) return -1;
+  double* W = dalloc((size_t)(b * kb));
+  double* Wr = dalloc((size_t)(b * kb));
+  for (int r = 0; r < nprow; ++r) {
+    if (mb[r] > 0 && kb > 0) {
+      oracle_dgemm('T', 'N', b, kb, mb[r], 1.0, Y[r], lda_Y[r], A[r], lda_A[r], 0.0, Wr, b); /* :259 */
+      for (int64_t e = 0; e < b * kb; ++e) W[e] += Wr[e];                                     /* :265 */
+    }
+  }
+  for (int64_t j = 0; j < kb; ++j) /* :271 forward substitution with lower-triangular, non-unit T (ld = b) */
+    for (int64_t i = 0; i < b; ++i) {
+      double x = W[i + j * b];
+      for (int64_t p = 0; p < i; ++p) x -= T[i + p * b] * W[p + j * b];
+      W[i + j * b] = x / T[i + i * b];
+    }
+  for (int r = 0; r < nprow; ++r)
+    if (mb[r] > 0 && kb > 0)
+      oracle_dgemm('N', 'N', mb[r], kb, b, -1.0, Y[r], lda_Y[r], W, b, 1.0, A[r], lda_A[r]); /* :275 */
+  free(W);
+  free(Wr);
+  return 0;
+}

@@ -1,0 +1,56 @@
+/* candmc_oracle — TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C, single-process restatement of the reference CANMM hot path (solomonik/CANDMC), used as the parity
+ * checker for the CUDA library.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference legs may
+ * load this; the product (candmc_b200/, include/) never does.
+ *
+ * Pinning: the reference ships no golden vectors (its tests recompute the serial product with BLAS at run time and
+ * compare to 1e-6 absolute, test/MM/topo_pdgemm_unit.cxx:321-333, test/MM/test_spc.cxx:116-126).  This oracle is
+ * pinned against OUTPUTS OF THE UNMODIFIED REFERENCE run in the build container (oracle/_ref/ref_dump under the
+ * mini-MPI shim; fixtures in tests/golden/, generator tests/golden/make_golden.py).  The local multiply in the
+ * reference is a vendor `dgemm_` whose version is not pinned by the reference (configure accepts any BLAS), so
+ * bit-level equality is not defined; the bar is BASELINE.json's rel-Frobenius <= 10*n*eps.
+ *
+ * All "distributed" routines simulate every rank of the processor grid inside one process: `blocks` arguments are
+ * arrays of P pointers, one local block per world rank, in the reference's rank order.
+ */
+#ifndef CANDMC_ORACLE_H
+#define CANDMC_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* glibc srand48/drand48 (the reference tests' generator) */
+void oracle_srand48(uint64_t* state, int64_t seed);
+double oracle_drand48(uint64_t* state);
+/* element (row r, col c) of the unit-test matrices: which = 0 -> A, 1 -> B  (test/MM/topo_pdgemm_unit.cxx:250-256) */
+double oracle_unit_elem(int64_t r, int64_t c, int64_t n, int which);
+void oracle_fill_unit_block(double* X, int64_t nrow, int64_t ncol, int64_t ld, int64_t row0, int64_t col0, int64_t n,
+                            int which);
+
+/* local kernels */
+void oracle_dgemm(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                  int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
+void oracle_lda_cpy(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B);
+void oracle_lda_cpy_scaled(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B,
+                           double a, double b);
+void oracle_transpose(int64_t rows, int64_t cols, const double* A, int64_t lda, double* B, int64_t ldb);
+
+/* distributed multiplies; P = number of simulated ranks, blocks indexed by world rank.  Return 0 or -1 (bad grid). */
+int oracle_summa(int64_t n, int q, char trans_A, char trans_B, double* const* A, int64_t lda_A, double* const* B,
+                 int64_t lda_B, double* const* C, int64_t lda_C);
+int oracle_d25_summa(int64_t n, int q, int c, int ovp, char trans_A, char trans_B, double* const* A, double* const* B,
+                     double* const* C);
+int oracle_bcast_cannon_4d(int64_t n, int x1_np, int x2_np, int ovp, double* const* A, double* const* B,
+                           double* const* C);
+int oracle_spcannon(int bidir, int kary, int ndim, int n, int m, int k, char transp_A, double alpha, double* const* A,
+                    char transp_B, double beta, double* const* B, double* const* C);
+/* CAQR trailing update on one process column of nprow ranks: A_r <- A_r - Y_r * (T^-1 * sum_r(Y_r^T A_r)) */
+int oracle_upd_A(int nprow, const int64_t* mb, int64_t kb, int64_t b, double* const* Y, const int64_t* lda_Y,
+                 double* const* A, const int64_t* lda_A, const double* T);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

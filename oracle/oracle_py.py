@@ -1,0 +1,184 @@
+"""ctypes binding of oracle/liboracle.so — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module; the
+product package `candmc_b200` never does (tests/test_boundary.py checks that).
+All matrices are numpy float64, column-major ("F" order) like the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_pd = C.POINTER(C.c_double)
+_ppd = C.POINTER(_pd)
+_i64 = C.c_int64
+
+
+def build() -> str:
+    """Compile the C restatement (gcc only; no GPU, no reference sources needed)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+    return os.path.join(_HERE, "liboracle.so")
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        src = os.path.join(_HERE, "candmc_oracle.c")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            build()
+        L = C.CDLL(path)
+        L.oracle_unit_elem.restype = C.c_double
+        L.oracle_unit_elem.argtypes = [_i64, _i64, _i64, C.c_int]
+        L.oracle_fill_unit_block.argtypes = [_pd, _i64, _i64, _i64, _i64, _i64, _i64, C.c_int]
+        L.oracle_dgemm.argtypes = [C.c_char, C.c_char, _i64, _i64, _i64, C.c_double, _pd, _i64, _pd, _i64,
+                                   C.c_double, _pd, _i64]
+        L.oracle_lda_cpy.argtypes = [_i64, _i64, _i64, _i64, _pd, _pd]
+        L.oracle_lda_cpy_scaled.argtypes = [_i64, _i64, _i64, _i64, _pd, _pd, C.c_double, C.c_double]
+        L.oracle_transpose.argtypes = [_i64, _i64, _pd, _i64, _pd, _i64]
+        L.oracle_summa.argtypes = [_i64, C.c_int, C.c_char, C.c_char, _ppd, _i64, _ppd, _i64, _ppd, _i64]
+        L.oracle_d25_summa.argtypes = [_i64, C.c_int, C.c_int, C.c_int, C.c_char, C.c_char, _ppd, _ppd, _ppd]
+        L.oracle_bcast_cannon_4d.argtypes = [_i64, C.c_int, C.c_int, C.c_int, _ppd, _ppd, _ppd]
+        L.oracle_spcannon.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char, C.c_double,
+                                      _ppd, C.c_char, C.c_double, _ppd, _ppd]
+        L.oracle_upd_A.argtypes = [C.c_int, C.POINTER(_i64), _i64, _i64, _ppd, C.POINTER(_i64), _ppd,
+                                   C.POINTER(_i64), _pd]
+        _LIB = L
+    return _LIB
+
+
+def _p(a: np.ndarray):
+    assert a.dtype == np.float64
+    return a.ctypes.data_as(_pd)
+
+
+def _pp(blocks):
+    arr = (_pd * len(blocks))(*[_p(b) for b in blocks])
+    return arr
+
+
+def _ch(c: str) -> bytes:
+    return c.encode("ascii")
+
+
+# ---- generators ---------------------------------------------------------------------------------------------
+def unit_block(nrow, ncol, row0, col0, n, which):
+    """Block of the reference unit-test matrices (test/MM/topo_pdgemm_unit.cxx:250-256), column-major."""
+    X = np.zeros((nrow, ncol), dtype=np.float64, order="F")
+    lib().oracle_fill_unit_block(_p(X), nrow, ncol, nrow, row0, col0, n, which)
+    return X
+
+
+def drand48_stream(seed, count):
+    """`count` successive drand48() draws after srand48(seed) — vectorised LCG (test/MM/test_spc.cxx:66-76)."""
+    a, c, mask = 0x5DEECE66D, 0xB, (1 << 48) - 1
+    x = ((seed & 0xFFFFFFFF) << 16) | 0x330E
+    out = np.empty(count, dtype=np.float64)
+    for i in range(count):
+        x = (a * x + c) & mask
+        out[i] = x / 281474976710656.0
+    return out
+
+
+# ---- local kernels --------------------------------------------------------------------------------------------
+def dgemm(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, Cm, ldc):
+    lib().oracle_dgemm(_ch(ta), _ch(tb), m, n, k, alpha, _p(A), lda, _p(B), ldb, beta, _p(Cm), ldc)
+
+
+def lda_cpy(nrow, ncol, lda_A, lda_B, A, B, a=None, b=None):
+    if a is None:
+        lib().oracle_lda_cpy(nrow, ncol, lda_A, lda_B, _p(A), _p(B))
+    else:
+        lib().oracle_lda_cpy_scaled(nrow, ncol, lda_A, lda_B, _p(A), _p(B), a, b)
+
+
+def transpose(rows, cols, A, lda, B, ldb):
+    lib().oracle_transpose(rows, cols, _p(A), lda, _p(B), ldb)
+
+
+# ---- distributed (all ranks simulated in-process; blocks = list of per-rank arrays) -------------------------------
+def summa(n, q, A, B, Cb, lda_A=None, lda_B=None, lda_C=None, trans_A="N", trans_B="N"):
+    b = n // q
+    rc = lib().oracle_summa(n, q, _ch(trans_A), _ch(trans_B), _pp(A), lda_A or b, _pp(B), lda_B or b, _pp(Cb),
+                            lda_C or b)
+    assert rc == 0, "oracle_summa: bad grid"
+
+
+def d25_summa(n, q, c, ovp, A, B, Cb, trans_A="N", trans_B="N"):
+    rc = lib().oracle_d25_summa(n, q, c, ovp, _ch(trans_A), _ch(trans_B), _pp(A), _pp(B), _pp(Cb))
+    assert rc == 0, "oracle_d25_summa: bad grid"
+
+
+def bcast_cannon_4d(n, x1_np, x2_np, ovp, A, B, Cb):
+    rc = lib().oracle_bcast_cannon_4d(n, x1_np, x2_np, ovp, _pp(A), _pp(B), _pp(Cb))
+    assert rc == 0, "oracle_bcast_cannon_4d: bad grid"
+
+
+def spcannon(bidir, kary, ndim, n, m, k, tA, alpha, A, tB, beta, B, Cb):
+    rc = lib().oracle_spcannon(bidir, kary, ndim, n, m, k, _ch(tA), alpha, _pp(A), _ch(tB), beta, _pp(B), _pp(Cb))
+    assert rc == 0, "oracle_spcannon: bad grid"
+
+
+def upd_A(mb, kb, b, Y, lda_Y, A, lda_A, T):
+    nprow = len(mb)
+    I = _i64 * nprow
+    rc = lib().oracle_upd_A(nprow, I(*mb), kb, b, _pp(Y), I(*lda_Y), _pp(A), I(*lda_A), _p(T))
+    assert rc == 0, "oracle_upd_A: bad arguments"
+
+
+# ---- the reference tests' data layouts ------------------------------------------------------------------------------
+def d25_blocks(n, q, c):
+    """Per-rank A, B blocks of d25_unit (test/MM/topo_pdgemm_unit.cxx:250-256): rank = layer*q*q + row*q + col holds
+    global rows [row*b,(row+1)*b) x cols [col*b,(col+1)*b) of both A and B (replicated over layers)."""
+    b = n // q
+    A, B = [], []
+    for layer in range(c):
+        for row in range(q):
+            for col in range(q):
+                A.append(unit_block(b, b, row * b, col * b, n, 0))
+                B.append(unit_block(b, b, row * b, col * b, n, 1))
+    return A, B
+
+
+def dcn_blocks(n, x1_np, x2_np):
+    """Per-rank blocks of dcn_unit (test/MM/topo_pdgemm_unit.cxx:87-94): col = (x1*x2_np+x2)*b, row = (y1*x2_np+y2)*b."""
+    b = n // (x1_np * x2_np)
+    A, B = [], []
+    for r in range(x1_np * x1_np * x2_np * x2_np):
+        x1 = r % x1_np
+        y1 = (r // x1_np) % x1_np
+        x2 = (r // (x1_np * x1_np)) % x2_np
+        y2 = r // (x1_np * x1_np * x2_np)
+        A.append(unit_block(b, b, (y1 * x2_np + y2) * b, (x1 * x2_np + x2) * b, n, 0))
+        B.append(unit_block(b, b, (y1 * x2_np + y2) * b, (x1 * x2_np + x2) * b, n, 1))
+    return A, B
+
+
+def spc_blocks(kary, ndim, seed, n, m, k, tB="N"):
+    """Per-rank A (m x k), B (k x n, or n x k when tB == 'T'), C (m x n) blocks and the full matrices of test_spc
+    (test/MM/test_spc.cxx:56-102)."""
+    khalf = kary ** (ndim // 2)
+    s = drand48_stream(seed, (m * k + k * n + m * n) * khalf * khalf)
+    o = 0
+    full_A = s[o:o + m * khalf * k * khalf].reshape((m * khalf, k * khalf), order="F"); o += full_A.size
+    full_B = s[o:o + k * khalf * n * khalf].reshape((k * khalf, n * khalf), order="F"); o += full_B.size
+    full_C = s[o:o + m * khalf * n * khalf].reshape((m * khalf, n * khalf), order="F")
+    A, B, Cb = [], [], []
+    for rank in range(kary ** ndim):
+        px = py = 0
+        sc, tr = 1, rank
+        for _ in range(ndim // 2):
+            px += (tr % kary) * sc; tr //= kary
+            py += (tr % kary) * sc; tr //= kary
+            sc *= kary
+        A.append(np.asfortranarray(full_A[py * m:(py + 1) * m, px * k:(px + 1) * k]))
+        Bb = full_B[py * k:(py + 1) * k, px * n:(px + 1) * n]
+        B.append(np.asfortranarray(Bb.T if tB == "T" else Bb))
+        Cb.append(np.asfortranarray(full_C[py * m:(py + 1) * m, px * n:(px + 1) * n]))
+    return A, B, Cb, (full_A, full_B, full_C)

@@ -1,0 +1,193 @@
+// ref_dump — TEST INFRASTRUCTURE (oracle/).  A driver of OURS around the UNMODIFIED reference CANMM entry points:
+// it builds the processor grid exactly as the reference's own tests do, fills the blocks with the reference
+// unit-test generators, calls the reference routine and writes every rank's C block to <prefix>.r<rank>.f64
+// (raw little-endian doubles, column-major, in the routine's local layout).  tests/golden/make_golden.py packs those
+// files into the committed fixtures, and tests use them to pin both oracle/candmc_oracle.c and the CUDA path.
+//
+//   ref_dump d25   <n> <c_rep> <ovp 0|1> <prefix>      d25_summa / d25_summa_ovp  (grid + data: test/MM/topo_pdgemm_unit.cxx:178-283)
+//   ref_dump summa <n> <prefix>                         summa                      (grid + data: :349-486, ctb_unit)
+//   ref_dump dcn   <n> <x2_np> <ovp> <prefix>           bcast_cannon_4d            (grid + data: :13-175, dcn_unit); x2_np must be 1
+//   ref_dump spc   <bidir> <ndim> <seed> <n> <m> <k> <alpha> <beta> <tB N|T> <prefix>   kput_cannon / kuni_cannon (test/MM/test_spc.cxx:36-114)
+#include <assert.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+
+#include "CANDMC.h"
+
+static void dump(const char* prefix, int rank, const double* C, size_t count) {
+  std::string fn = std::string(prefix) + ".r" + std::to_string(rank) + ".f64";
+  FILE* f = fopen(fn.c_str(), "wb");
+  if (!f || fwrite(C, sizeof(double), count, f) != count) {
+    fprintf(stderr, "ref_dump: cannot write %s\n", fn.c_str());
+    MPI_Abort(MPI_COMM_WORLD, 3);
+  }
+  fclose(f);
+}
+
+static double* alloc_d(size_t n) {
+  void* p = NULL;
+  if (posix_memalign(&p, ALIGN_BYTES, (n ? n : 1) * sizeof(double)) != 0) MPI_Abort(MPI_COMM_WORLD, 4);
+  return (double*)p;
+}
+
+static int run_d25(int myRank, int numPes, int64_t n, int c_rep, int ovp, const char* prefix, bool use_summa) {
+  const int num_pes_dim = (int)sqrt((double)(numPes / c_rep));
+  if (num_pes_dim * num_pes_dim * c_rep != numPes || n % num_pes_dim != 0) {
+    if (myRank == 0) fprintf(stderr, "ref_dump: grid mismatch\n");
+    return 2;
+  }
+  const int64_t b = n / num_pes_dim;
+  int layerRank, intraLayerRank, myRow, myCol;
+  CommData_t cdt_row, cdt_col, cdt_kdir;
+  RSETUP_KDIR_COMM(myRank, numPes, c_rep, cdt_kdir, layerRank, intraLayerRank);
+  RSETUP_LAYER_COMM(num_pes_dim, layerRank, intraLayerRank, cdt_row, cdt_col, myRow, myCol);
+  double* mat_A = alloc_d(b * b);
+  double* mat_B = alloc_d(b * b);
+  double* mat_C = alloc_d(b * b);
+  double* buffer = alloc_d(5 * b * b);
+  memset(buffer, 0, 5 * b * b * sizeof(double));  // the reference needs a zeroed buffer
+  memset(mat_C, 0, b * b * sizeof(double));
+  for (int64_t i = 0; i < b; i++)
+    for (int64_t j = 0; j < b; j++) {
+      srand48((myCol * b + i) * n + myRow * b + j);
+      mat_A[i * b + j] = drand48();
+      mat_B[i * b + j] = drand48();
+    }
+  ctb_args_t p;
+  p.n = n;
+  p.lda_A = b;
+  p.lda_B = b;
+  p.lda_C = b;
+  p.buffer_size = 5 * b * b * sizeof(double);
+  p.trans_A = 'N';
+  p.trans_B = 'N';
+  p.ovp = ovp;
+  if (use_summa)
+    summa(&p, mat_A, mat_B, mat_C, buffer, cdt_row, cdt_col);
+  else if (ovp)
+    d25_summa_ovp(&p, mat_A, mat_B, mat_C, buffer, cdt_row, cdt_col, cdt_kdir);
+  else
+    d25_summa(&p, mat_A, mat_B, mat_C, buffer, cdt_row, cdt_col, cdt_kdir);
+  dump(prefix, myRank, mat_C, b * b);
+  return 0;
+}
+
+static int run_dcn(int myRank, int numPes, int64_t n, int x2_np, int ovp, const char* prefix) {
+  // grid + generator of dcn_unit (test/MM/topo_pdgemm_unit.cxx:13-175)
+  const int x1_np = (int)sqrt((double)(numPes / (x2_np * x2_np)));
+  if (x1_np * x1_np * x2_np * x2_np != numPes || x2_np != 1) {
+    if (myRank == 0) fprintf(stderr, "ref_dump dcn: need x2_np == 1 (the reference deadlocks otherwise) and a square x1 grid\n");
+    return 2;
+  }
+  const int64_t b = n / (x1_np * x2_np);
+  const int x1 = myRank % x1_np, y1 = (myRank / x1_np) % x1_np;
+  const int x2 = (myRank / (x1_np * x1_np)) % x2_np, y2 = myRank / (x1_np * x1_np * x2_np);
+  CommData_t cdt_glb, cdt_x1, cdt_y1, cdt_x2, cdt_y2;
+  SET_COMM(MPI_COMM_WORLD, myRank, numPes, cdt_glb);
+  // same colour/key choice as the driver: x1-communicator = ranks sharing (y1,x2,y2), ordered by x1, etc.
+  SETUP_SUB_COMM(cdt_glb, cdt_x1, x1, (y1 + x1_np * (x2 + x2_np * y2)), x1_np);
+  SETUP_SUB_COMM(cdt_glb, cdt_y1, y1, (x1 + x1_np * (x2 + x2_np * y2)), x1_np);
+  SETUP_SUB_COMM(cdt_glb, cdt_x2, x2, (x1 + x1_np * (y1 + x1_np * y2)), x2_np);
+  SETUP_SUB_COMM(cdt_glb, cdt_y2, y2, (x1 + x1_np * (y1 + x1_np * x2)), x2_np);
+  double* mat_A = alloc_d(b * b);
+  double* mat_B = alloc_d(b * b);
+  double* mat_C = alloc_d(b * b);
+  double* buffer = alloc_d(5 * b * b);
+  memset(buffer, 0, 5 * b * b * sizeof(double));
+  const int64_t col0 = (int64_t)(x1 * x2_np + x2) * b, row0 = (int64_t)(y1 * x2_np + y2) * b;
+  for (int64_t i = 0; i < b; i++)
+    for (int64_t j = 0; j < b; j++) {
+      srand48((col0 + i) * n + row0 + j);
+      mat_A[i * b + j] = drand48();
+      mat_B[i * b + j] = drand48();
+    }
+  ctb_args_t p;
+  p.n = n;
+  p.lda_A = b;
+  p.lda_B = b;
+  p.lda_C = b;
+  p.buffer_size = 5 * b * b * sizeof(double);
+  p.trans_A = 'N';
+  p.trans_B = 'N';
+  p.ovp = ovp;
+  bcast_cannon_4d(&p, mat_A, mat_B, mat_C, buffer, cdt_x1, cdt_y1, cdt_x2, cdt_y2);
+  dump(prefix, myRank, mat_C, b * b);
+  return 0;
+}
+
+static int run_spc(int rank, int numPes, int bidir, int ndim, int seed, int n, int m, int k, double alpha, double beta,
+                   char tB, const char* prefix) {
+  int kary = 1;
+  for (; pow(kary, ndim) < numPes; kary++) {
+  }
+  int p = 1;
+  for (int l = 0; l < ndim; l++) p *= kary;
+  if (p != numPes || ndim < 2 || ndim % 2 != 0 || k % ndim != 0) {
+    if (rank == 0) fprintf(stderr, "ref_dump spc: bad grid\n");
+    return 2;
+  }
+  int khalf = 1;
+  for (int i = 0; i < ndim / 2; i++) khalf *= kary;
+  // single-stream generator of test_spc.cxx:66-76
+  double* full_A = (double*)malloc(sizeof(double) * m * khalf * k * khalf);
+  double* full_B = (double*)malloc(sizeof(double) * k * khalf * n * khalf);
+  double* full_C = (double*)malloc(sizeof(double) * m * khalf * n * khalf);
+  srand48(seed);
+  for (int i = 0; i < m * khalf * k * khalf; i++) full_A[i] = drand48();
+  for (int i = 0; i < k * khalf * n * khalf; i++) full_B[i] = drand48();
+  for (int i = 0; i < m * khalf * n * khalf; i++) full_C[i] = drand48();
+  int px = 0, py = 0, s = 1, tr = rank;
+  for (int i = 0; i < ndim / 2; i++) {
+    px += (tr % kary) * s;
+    tr = tr / kary;
+    py += (tr % kary) * s;
+    tr = tr / kary;
+    s = s * kary;
+  }
+  double* A = alloc_d((size_t)m * k);
+  double* B = alloc_d((size_t)k * n);
+  double* C = alloc_d((size_t)m * n);
+  for (int i = 0; i < k; i++)
+    for (int j = 0; j < m; j++) A[i * m + j] = full_A[(px * k + i) * khalf * m + (py * m + j)];
+  if (tB == 'N') {
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < k; j++) B[i * k + j] = full_B[(px * n + i) * khalf * k + (py * k + j)];
+  } else {  // B block stored transposed (n x k, column-major): Bt[j*n + i] = B(j, i)
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < k; j++) B[j * n + i] = full_B[(px * n + i) * khalf * k + (py * k + j)];
+  }
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < m; j++) C[i * m + j] = full_C[(px * n + i) * khalf * m + (py * m + j)];
+  if (bidir)
+    kput_cannon(rank, kary, ndim, MPI_COMM_WORLD, n, m, k, 'N', alpha, A, tB, beta, B, C);
+  else
+    kuni_cannon(rank, kary, ndim, MPI_COMM_WORLD, n, m, k, 'N', alpha, A, tB, beta, B, C);
+  dump(prefix, rank, C, (size_t)m * n);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  int myRank, numPes;
+  MPI_Init(&argc, &argv);
+  MPI_Comm_size(MPI_COMM_WORLD, &numPes);
+  MPI_Comm_rank(MPI_COMM_WORLD, &myRank);
+  int rc = 2;
+  if (argc >= 6 && !strcmp(argv[1], "d25"))
+    rc = run_d25(myRank, numPes, atoll(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5], false);
+  else if (argc >= 4 && !strcmp(argv[1], "summa"))
+    rc = run_d25(myRank, numPes, atoll(argv[2]), 1, 0, argv[3], true);
+  else if (argc >= 6 && !strcmp(argv[1], "dcn"))
+    rc = run_dcn(myRank, numPes, atoll(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5]);
+  else if (argc >= 12 && !strcmp(argv[1], "spc"))
+    rc = run_spc(myRank, numPes, atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]),
+                 atoi(argv[7]), atof(argv[8]), atof(argv[9]), argv[10][0], argv[11]);
+  else if (myRank == 0)
+    fprintf(stderr, "usage: see the header of oracle/ref_dump.cxx\n");
+  if (rc != 0) MPI_Abort(MPI_COMM_WORLD, rc);
+  MPI_Finalize();
+  return 0;
+}

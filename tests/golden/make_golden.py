@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Generate tests/golden/canmm_ref_outputs.npz from the UNMODIFIED reference CANMM.
+
+Runs oracle/_ref/ref_dump (our dump driver linked against the reference's own objects, built by `make -C oracle ref`
+from /root/reference under the mini-MPI shim and scipy-OpenBLAS) for a handful of small grids and stores every
+rank's C block.  Only runnable where /root/reference exists (the build container); the fixture it writes is
+committed and is what the CPU and GPU parity tests read.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+# name -> (ranks, ref_dump argv, elements per rank)
+CASES = {
+    # d25_summa / d25_summa_ovp: the reference test's own configurations (scripts/test_all.sh: P=4 -> 2x2x1, P=8 -> 2x2x2)
+    "d25_n96_q2_c1_ovp0": (4, ["d25", "96", "1", "0"], 48 * 48),
+    "d25_n96_q2_c1_ovp1": (4, ["d25", "96", "1", "1"], 48 * 48),
+    "d25_n64_q2_c2_ovp0": (8, ["d25", "64", "2", "0"], 32 * 32),
+    "d25_n64_q2_c2_ovp1": (8, ["d25", "64", "2", "1"], 32 * 32),
+    "d25_n40_q1_c1_ovp0": (1, ["d25", "40", "1", "0"], 40 * 40),
+    "d25_n96_q4_c2_ovp0": (32, ["d25", "96", "2", "0"], 24 * 24),
+    "d25_n90_q3_c1_ovp1": (9, ["d25", "90", "1", "1"], 30 * 30),
+    # summa (never called by a live reference main, but its body is complete: summa.cxx:26-101)
+    "summa_n64_q2": (4, ["summa", "64"], 32 * 32),
+    "summa_n96_q3": (9, ["summa", "96"], 32 * 32),
+    # bcast_cannon_4d with x2_np = 1 (the only configuration in which the reference terminates)
+    "dcn_n64_x2_1_ovp0": (4, ["dcn", "64", "1", "0"], 32 * 32),
+    "dcn_n64_x2_1_ovp1": (4, ["dcn", "64", "1", "1"], 32 * 32),
+    # split-dimensional Cannon: spc <bidir> <ndim> <seed> <n> <m> <k> <alpha> <beta> <tB>
+    "spc_bidir1_p4_m24_k16_n20_N": (4, ["spc", "1", "2", "3", "20", "24", "16", "1.2", "0.8", "N"], 24 * 20),
+    "spc_bidir0_p4_m24_k16_n20_N": (4, ["spc", "0", "2", "3", "20", "24", "16", "1.2", "0.8", "N"], 24 * 20),
+    "spc_bidir1_p4_m24_k16_n20_T": (4, ["spc", "1", "2", "3", "20", "24", "16", "1.2", "0.8", "T"], 24 * 20),
+    "spc_bidir1_p9_m16_k12_n8_N": (9, ["spc", "1", "2", "3", "8", "16", "12", "1.2", "0.8", "N"], 16 * 8),
+    "spc_bidir0_p9_m16_k12_n8_N": (9, ["spc", "0", "2", "3", "8", "16", "12", "1.2", "0.8", "N"], 16 * 8),
+    "spc_bidir1_p16_ndim4_m8_k16_n8_N": (16, ["spc", "1", "4", "3", "8", "8", "16", "1.2", "0.8", "N"], 8 * 8),
+    "spc_bidir0_p16_ndim4_m8_k16_n8_N": (16, ["spc", "0", "4", "3", "8", "8", "16", "1.2", "0.8", "N"], 8 * 8),
+}
+
+
+def main():
+    if not os.path.exists(os.path.join(REFDIR, "ref_dump")):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, (ranks, argv, elems) in CASES.items():
+            prefix = os.path.join(tmp, name)
+            cmd = [os.path.join(REFDIR, "mpirun"), "-np", str(ranks), "-timeout", "120", "-threads", "1",
+                   os.path.join(REFDIR, "ref_dump")] + argv + [prefix]
+            subprocess.check_call(cmd)
+            blocks = []
+            for r in range(ranks):
+                a = np.fromfile(f"{prefix}.r{r}.f64", dtype="<f8")
+                assert a.size == elems, (name, r, a.size, elems)
+                blocks.append(a)
+            out[name] = np.stack(blocks)
+            print(f"{name}: {ranks} ranks x {elems} doubles")
+    path = os.path.join(ROOT, "tests", "golden", "canmm_ref_outputs.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    sys.exit(main())

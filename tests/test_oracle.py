@@ -1,0 +1,173 @@
+"""CPU tests: oracle/candmc_oracle.c (our restatement) against outputs of the UNMODIFIED reference
+(tests/golden/canmm_ref_outputs.npz, made by tests/golden/make_golden.py) and against numpy."""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as orc
+
+EPS = 2.220446049250313e-16
+
+
+def rel_frob(x, ref):
+    x = np.asarray(x, dtype=np.float64).ravel(order="F")  # column-major, like the reference's raw buffers
+    ref = np.asarray(ref, dtype=np.float64).ravel(order="F")
+    return np.linalg.norm(x - ref) / max(np.linalg.norm(ref), 1e-300)
+
+
+def zeros_like_blocks(blocks, shape=None):
+    return [np.zeros(shape or b.shape, dtype=np.float64, order="F") for b in blocks]
+
+
+def test_drand48_generator_matches_libc():
+    import ctypes
+
+    libc = ctypes.CDLL("libc.so.6")
+    libc.drand48.restype = ctypes.c_double
+    libc.srand48.argtypes = [ctypes.c_long]
+    for seed in (0, 3, 1000, 12345678901):
+        libc.srand48(seed)
+        want = [libc.drand48() for _ in range(5)]
+        got = orc.drand48_stream(seed, 5)
+        assert list(got) == want
+    n = 96
+    for (r, c) in [(0, 0), (5, 7), (95, 95)]:
+        libc.srand48(c * n + r)
+        a, b = libc.drand48(), libc.drand48()
+        assert orc.lib().oracle_unit_elem(r, c, n, 0) == a
+        assert orc.lib().oracle_unit_elem(r, c, n, 1) == b
+
+
+@pytest.mark.parametrize("ta", ["N", "T"])
+@pytest.mark.parametrize("tb", ["N", "T"])
+def test_oracle_dgemm_vs_numpy(ta, tb):
+    rng = np.random.default_rng(7)
+    m, n, k = 37, 29, 53
+    A = np.asfortranarray(rng.random((m, k) if ta == "N" else (k, m)))
+    B = np.asfortranarray(rng.random((k, n) if tb == "N" else (n, k)))
+    Cm = np.asfortranarray(rng.random((m + 3, n)))
+    want = 1.2 * (A if ta == "N" else A.T) @ (B if tb == "N" else B.T) + 0.8 * Cm[:m]
+    orc.dgemm(ta, tb, m, n, k, 1.2, A, A.shape[0], B, B.shape[0], 0.8, Cm, m + 3)
+    assert rel_frob(Cm[:m], want) < 10 * k * EPS
+    # beta == 0 must overwrite NaNs (BLAS semantics)
+    Cn = np.full((m, n), np.nan, order="F")
+    orc.dgemm(ta, tb, m, n, k, 1.0, A, A.shape[0], B, B.shape[0], 0.0, Cn, m)
+    assert np.isfinite(Cn).all()
+
+
+def test_oracle_pack_kernels():
+    rng = np.random.default_rng(3)
+    A = np.asfortranarray(rng.random((11, 7)))
+    B = np.zeros((9, 7), order="F")
+    orc.lda_cpy(5, 7, 11, 9, A, B)
+    assert (B[:5] == A[:5]).all() and (B[5:] == 0).all()
+    B2 = np.asfortranarray(rng.random((9, 7)))
+    want = B2.copy()
+    want[:5] = want[:5] * 0.25 + A[:5] * 0.5
+    orc.lda_cpy(5, 7, 11, 9, A, B2, 0.5, 0.25)
+    assert np.array_equal(B2, want)
+    T = np.zeros((7, 11), order="F")
+    orc.transpose(11, 7, A, 11, T, 7)
+    assert np.array_equal(T, A.T)
+
+
+D25 = [("d25_n96_q2_c1_ovp0", 96, 2, 1, 0), ("d25_n96_q2_c1_ovp1", 96, 2, 1, 1), ("d25_n64_q2_c2_ovp0", 64, 2, 2, 0),
+       ("d25_n64_q2_c2_ovp1", 64, 2, 2, 1), ("d25_n40_q1_c1_ovp0", 40, 1, 1, 0), ("d25_n96_q4_c2_ovp0", 96, 4, 2, 0),
+       ("d25_n90_q3_c1_ovp1", 90, 3, 1, 1)]
+
+
+@pytest.mark.parametrize("name,n,q,c,ovp", D25)
+def test_oracle_d25_matches_reference(golden, name, n, q, c, ovp):
+    A, B = orc.d25_blocks(n, q, c)
+    Cb = zeros_like_blocks(A)
+    orc.d25_summa(n, q, c, ovp, A, B, Cb)
+    ref = golden[name]
+    for r in range(q * q * c):
+        assert rel_frob(Cb[r], ref[r]) <= 10 * n * EPS, (name, r)
+
+
+@pytest.mark.parametrize("name,n,q", [("summa_n64_q2", 64, 2), ("summa_n96_q3", 96, 3)])
+def test_oracle_summa_matches_reference(golden, name, n, q):
+    A, B = orc.d25_blocks(n, q, 1)
+    Cb = zeros_like_blocks(A)
+    orc.summa(n, q, A, B, Cb)
+    for r in range(q * q):
+        assert rel_frob(Cb[r], golden[name][r]) <= 10 * n * EPS
+
+
+@pytest.mark.parametrize("ovp", [0, 1])
+def test_oracle_dcn_matches_reference(golden, ovp):
+    n, x1, x2 = 64, 2, 1
+    A, B = orc.dcn_blocks(n, x1, x2)
+    Cb = zeros_like_blocks(A)
+    orc.bcast_cannon_4d(n, x1, x2, ovp, A, B, Cb)
+    for r in range(4):
+        assert rel_frob(Cb[r], golden[f"dcn_n64_x2_1_ovp{ovp}"][r]) <= 10 * n * EPS
+
+
+@pytest.mark.parametrize("x1,x2,n", [(1, 2, 32), (2, 2, 64), (1, 3, 48)])
+def test_oracle_dcn_cannon_level_vs_serial(x1, x2, n):
+    """x2_np > 1 cannot be run in the reference (it deadlocks); the expected output is by definition the serial product
+    in the dcn_unit layout (test/MM/topo_pdgemm_unit.cxx:139-160)."""
+    A, B = orc.dcn_blocks(n, x1, x2)
+    Cb = zeros_like_blocks(A)
+    orc.bcast_cannon_4d(n, x1, x2, 0, A, B, Cb)
+    fullA = orc.unit_block(n, n, 0, 0, n, 0)
+    fullB = orc.unit_block(n, n, 0, 0, n, 1)
+    full = fullA @ fullB
+    b = n // (x1 * x2)
+    for r in range(len(A)):
+        xa, ya = r % x1, (r // x1) % x1
+        xb, yb = (r // (x1 * x1)) % x2, r // (x1 * x1 * x2)
+        row0, col0 = (ya * x2 + yb) * b, (xa * x2 + xb) * b
+        assert rel_frob(Cb[r], full[row0:row0 + b, col0:col0 + b]) <= 10 * n * EPS
+
+
+SPC = [("spc_bidir1_p4_m24_k16_n20_N", 1, 2, 2, 20, 24, 16, "N"), ("spc_bidir0_p4_m24_k16_n20_N", 0, 2, 2, 20, 24, 16, "N"),
+       ("spc_bidir1_p4_m24_k16_n20_T", 1, 2, 2, 20, 24, 16, "T"), ("spc_bidir1_p9_m16_k12_n8_N", 1, 3, 2, 8, 16, 12, "N"),
+       ("spc_bidir0_p9_m16_k12_n8_N", 0, 3, 2, 8, 16, 12, "N"),
+       ("spc_bidir1_p16_ndim4_m8_k16_n8_N", 1, 2, 4, 8, 8, 16, "N"),
+       ("spc_bidir0_p16_ndim4_m8_k16_n8_N", 0, 2, 4, 8, 8, 16, "N")]
+
+
+@pytest.mark.parametrize("name,bidir,kary,ndim,n,m,k,tB", SPC)
+def test_oracle_spcannon_matches_reference(golden, name, bidir, kary, ndim, n, m, k, tB):
+    A, B, Cb, (fA, fB, fC) = orc.spc_blocks(kary, ndim, 3, n, m, k, tB)
+    orc.spcannon(bidir, kary, ndim, n, m, k, "N", 1.2, A, tB, 0.8, B, Cb)
+    ref = golden[name]
+    khalf = kary ** (ndim // 2)
+    full = 1.2 * fA @ fB + 0.8 * fC
+    for r in range(kary ** ndim):
+        assert rel_frob(Cb[r], ref[r]) <= 10 * k * khalf * EPS, (name, r)
+    # and the reference test's own criterion: serial product, |diff| <= 1e-6 (test/MM/test_spc.cxx:116-126)
+    A, B, Cb, _ = orc.spc_blocks(kary, ndim, 3, n, m, k, tB)
+    orc.spcannon(bidir, kary, ndim, n, m, k, "N", 1.2, A, tB, 0.8, B, Cb)
+    for rank in range(kary ** ndim):
+        px = py = 0
+        sc, tr = 1, rank
+        for _ in range(ndim // 2):
+            px += (tr % kary) * sc; tr //= kary
+            py += (tr % kary) * sc; tr //= kary
+            sc *= kary
+        assert np.abs(Cb[rank] - full[py * m:(py + 1) * m, px * n:(px + 1) * n]).max() <= 1e-6
+
+
+def test_oracle_d25_ksplit_extension_vs_serial():
+    n, c = 48, 2
+    A = [orc.unit_block(n, n, 0, 0, n, 0) for _ in range(c)]
+    B = [orc.unit_block(n, n, 0, 0, n, 1) for _ in range(c)]
+    Cb = zeros_like_blocks(A)
+    orc.d25_summa(n, 1, c, 0, A, B, Cb)
+    for r in range(c):
+        assert rel_frob(Cb[r], A[0] @ B[0]) <= 10 * n * EPS
+
+
+def test_oracle_upd_A_vs_numpy():
+    rng = np.random.default_rng(11)
+    b, kb, mbs = 8, 12, [20, 16]
+    T = np.asfortranarray(np.eye(b) + 0.01 * np.tril(rng.random((b, b))))
+    Y = [np.asfortranarray(rng.random((mb, b))) for mb in mbs]
+    A = [np.asfortranarray(rng.random((mb, kb))) for mb in mbs]
+    Yf, Af = np.vstack(Y), np.vstack(A)
+    want = Af - Yf @ np.linalg.solve(T, Yf.T @ Af)
+    orc.upd_A(mbs, kb, b, Y, mbs, A, mbs, T)
+    assert rel_frob(np.vstack(A), want) <= 1e-13

@@ -1,0 +1,109 @@
+"""ctypes loader for libcandmc_b200.so (the C ABI declared in include/candmc_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libcandmc_b200.so")
+_lib = None
+
+i64 = C.c_int64
+pd = C.c_void_p  # device or host pointers travel as integers
+comm_p = C.c_void_p
+
+
+class CandmcError(RuntimeError):
+    """Raised for every non-zero status of the C ABI (the reference would assert/ABORT, alg/shared/util.h:127-138)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"candmc_b200 error {code}: {msg}")
+        self.code = code
+
+
+class CtbArgs(C.Structure):
+    """candmc_ctb_args_t == ctb_args_t (alg/MM/topo_pdgemm/topo_pdgemm_algs.h:6-15)."""
+    _fields_ = [("trans_A", C.c_char), ("trans_B", C.c_char), ("n", i64), ("lda_A", i64), ("lda_B", i64),
+                ("lda_C", i64), ("buffer_size", i64), ("ovp", C.c_int)]
+
+
+# name -> (restype, argtypes); every symbol include/candmc_b200.h declares
+SIGNATURES = {
+    "candmc_version": (C.c_int, []),
+    "candmc_last_error": (C.c_char_p, []),
+    "candmc_init": (C.c_int, [C.c_int]),
+    "candmc_finalize": (C.c_int, []),
+    "candmc_device_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "candmc_launch_count": (C.c_ulonglong, []),
+    "candmc_debug_force_generic_gemm": (C.c_int, [C.c_int]),
+    "candmc_debug_static_schedule": (C.c_int, [C.c_int]),
+    "candmc_profile_enable": (C.c_int, [C.c_int]),
+    "candmc_profile_gemm_stats": (C.c_int, [C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "candmc_dgemm": (C.c_int, [C.c_char, C.c_char, i64, i64, i64, C.c_double, pd, i64, pd, i64, C.c_double, pd, i64,
+                               C.c_void_p]),
+    "candmc_lda_cpy": (C.c_int, [i64, i64, i64, i64, pd, pd, C.c_void_p]),
+    "candmc_lda_cpy_scaled": (C.c_int, [i64, i64, i64, i64, pd, pd, C.c_double, C.c_double, C.c_void_p]),
+    "candmc_transpose": (C.c_int, [i64, i64, pd, i64, pd, i64, C.c_void_p]),
+    "candmc_fill_drand48": (C.c_int, [pd, i64, i64, i64, i64, i64, i64, C.c_int, C.c_void_p]),
+    "candmc_frob_diff": (C.c_int, [pd, i64, pd, i64, i64, i64, C.POINTER(C.c_double), C.c_void_p]),
+    "candmc_get_unique_id": (C.c_int, [C.c_void_p]),
+    "candmc_comm_init_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(comm_p)]),
+    "candmc_comm_split": (C.c_int, [comm_p, C.c_int, C.c_int, C.POINTER(comm_p)]),
+    "candmc_comm_free": (C.c_int, [comm_p]),
+    "candmc_comm_rank": (C.c_int, [comm_p, C.POINTER(C.c_int)]),
+    "candmc_comm_size": (C.c_int, [comm_p, C.POINTER(C.c_int)]),
+    "candmc_comm_barrier": (C.c_int, [comm_p]),
+    "candmc_comm_bcast": (C.c_int, [comm_p, pd, i64, C.c_int, C.c_void_p]),
+    "candmc_comm_allreduce_sum": (C.c_int, [comm_p, pd, pd, i64, C.c_void_p]),
+    "candmc_summa": (C.c_int, [C.POINTER(CtbArgs), pd, pd, pd, pd, comm_p, comm_p, C.c_void_p]),
+    "candmc_d25_summa": (C.c_int, [C.POINTER(CtbArgs), pd, pd, pd, pd, comm_p, comm_p, comm_p, C.c_int, C.c_void_p]),
+    "candmc_bcast_cannon_4d": (C.c_int, [C.POINTER(CtbArgs), pd, pd, pd, pd, comm_p, comm_p, comm_p, comm_p,
+                                         C.c_void_p]),
+    "candmc_spcannon": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, comm_p, C.c_int, C.c_int, C.c_int, C.c_char,
+                                  C.c_double, pd, C.c_char, C.c_double, pd, pd, C.c_void_p]),
+    "candmc_upd_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, comm_p, C.c_void_p]),
+    "candmc_set_min_kchunk": (C.c_int, [i64]),
+}
+
+
+def build_native(verbose: bool = False) -> str:
+    """Compile libcandmc_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    if not verbose:
+        cmd.insert(1, "-s")
+    subprocess.check_call(cmd)
+    return _SO
+
+
+def lib() -> C.CDLL:
+    """The loaded shared library.  Fails loudly when it is missing — there is no pure-Python or CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise CandmcError(-1, f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                  "(or `make -C candmc_b200/csrc`). candmc_b200 has no fallback implementation.")
+        L = C.CDLL(_SO, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return lib().candmc_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int):
+    if rc != 0:
+        raise CandmcError(rc, last_error())
+
+
+def init(device: int = -1):
+    check(lib().candmc_init(device))
+
+
+def launch_count() -> int:
+    return int(lib().candmc_launch_count())

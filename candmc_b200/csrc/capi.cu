@@ -33,6 +33,21 @@ int candmc_debug_force_generic_gemm(int on) {
   return OK;
 }
 
+int candmc_debug_static_schedule(int on) {
+  runtime().static_schedule = (on != 0);
+  return OK;
+}
+
+int candmc_profile_enable(int on) {
+  runtime().profile = (on != 0);
+  return profile_reset();
+}
+
+int candmc_profile_gemm_stats(int64_t* launches, double* total_ms, double* total_flops) {
+  CANDMC_CHECK(launches && total_ms && total_flops, "candmc_profile_gemm_stats: null output");
+  return profile_collect(launches, total_ms, total_flops);
+}
+
 int candmc_dgemm(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                  int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, void* stream) {
   CANDMC_TRY(runtime_require());

@@ -6,7 +6,8 @@
 // Design (B200-first, not a translation of any BLAS):
 //   * FP64 has no tcgen05/UMMA kind on sm_100a; the FP64 tensor atom is mma.sync.m8n8k4 (SASS DMMA.8x8x4) with
 //     register accumulators.  One persistent CTA per SM owns 128x128 C tiles; 8 consumer warps each hold a 64x32
-//     register tile (64 accumulator doubles/lane), one producer warp drives TMA.
+//     register tile (64 accumulator doubles/lane), one producer warp drives TMA and claims tiles from an atomic
+//     counter (dynamic scheduling keeps the tail short and lets the kernel co-run with NCCL kernels).
 //   * Operand tiles (128 x 16 doubles = 16 KiB each) are brought in by TMA (`cp.async.bulk.tensor.2d`, 128-byte
 //     swizzle) into a 6-stage mbarrier ring (192 KiB smem).  Two smem layouts exist, chosen per operand by the
 //     transpose flag:
@@ -37,7 +38,7 @@ constexpr int NCONSUMER_WARPS = 8;
 constexpr int NTHREADS = (NCONSUMER_WARPS + 4) * 32;  // + 1 producer warpgroup (setmaxnreg works per 4 warps)
 constexpr int PRODUCER_REGS = 40;                     // 4 warps x 40 + 8 warps x 232 regs = 64512 <= 65536
 constexpr int CONSUMER_REGS = 232;
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers + tile ids*/;
 constexpr int RASTER_GROUP = 8;
 
 // index-slot permutation shared by A rows and B cols (see header comment)
@@ -86,12 +87,15 @@ template <bool A_KMAJ, bool B_KMAJ>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     double* __restrict__ C, int64_t ldc, int M, int N, int K, double alpha, double beta,
-                    int tilesM, int tilesN) {
+                    int tilesM, int tilesN, int* __restrict__ tile_counter) {
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment for the 128 B swizzle atom; pointer arithmetic keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + NSTAGE;
+  // tile id published with the first k-stage of every tile (dynamic scheduler: tiles are claimed with an atomic
+  // counter so CTAs that start late — e.g. behind an NCCL kernel holding their SM — simply take fewer tiles)
+  volatile int* stage_tile = reinterpret_cast<volatile int*>(empty_bar + NSTAGE);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -115,11 +119,20 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tma_prefetch_desc(&tmB);
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (int iter = 0;; ++iter) {
+        // dynamic: claim the next tile; static (tile_counter == nullptr): round-robin over the grid
+        const int t = tile_counter ? atomicAdd(tile_counter, 1) : static_cast<int>(blockIdx.x + iter * gridDim.x);
+        if (t >= ntiles) {  // sentinel: an empty stage whose tile id is -1
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          stage_tile[stage] = -1;
+          mbar_arrive(&full_bar[stage]);
+          break;
+        }
         const TileCoord tc = tile_coord(t, tilesM, tilesN);
         const int m0 = tc.tm * BM, n0 = tc.tn * BN;
         for (int kt = 0; kt < KT; ++kt) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (kt == 0) stage_tile[stage] = t;
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + OPER_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -188,17 +201,16 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   int stage = 0;
   uint32_t phase = 0;
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  for (;;) {
+    mbar_wait(&full_bar[stage], phase);
+    const int t = stage_tile[stage];
+    if (t < 0) break;
     const TileCoord tc = tile_coord(t, tilesM, tilesN);
 #pragma unroll
     for (int f = 0; f < 8; ++f)
 #pragma unroll
       for (int h = 0; h < 4; ++h) acc[f][h][0] = acc[f][h][1] = 0.0;
-
-    if (KT > 0) {
-      mbar_wait(&full_bar[stage], phase);
-      load_frags(0, stage * STAGE_BYTES, 0);
-    }
+    load_frags(0, stage * STAGE_BYTES, 0);
     for (int kt = 0; kt < KT; ++kt) {
       const uint32_t st = stage * STAGE_BYTES;
       load_frags(1, st, 1);
@@ -340,8 +352,12 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_
   const int tilesM = (M + BM - 1) / BM, tilesN = (N + BN - 1) / BN;
   const int64_t ntiles = static_cast<int64_t>(tilesM) * tilesN;
   const int grid = static_cast<int>(ntiles < runtime().num_sms ? ntiles : runtime().num_sms);
-  kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmB, C, ldc, M, N, K, alpha, beta, tilesM, tilesN);
+  int* counter = nullptr;
+  if (!runtime().static_schedule) CANDMC_TRY(next_tile_counter(&counter, stream));
+  if (runtime().profile) CANDMC_TRY(profile_begin_launch(stream, 2.0 * M * (double)N * (double)K));
+  kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmB, C, ldc, M, N, K, alpha, beta, tilesM, tilesN, counter);
   CANDMC_CUDA(cudaGetLastError());
+  if (runtime().profile) CANDMC_TRY(profile_end_launch(stream));
   runtime().launches++;
   return OK;
 }

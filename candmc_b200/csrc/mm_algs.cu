@@ -1,0 +1,630 @@
+// candmc_b200 — host schedules of the distributed multiplies (the CANMM algorithms) on CUDA streams + NCCL.
+//
+//   candmc_summa            <- summa            (alg/MM/topo_pdgemm/summa.cxx:26-101)
+//   candmc_d25_summa        <- d25_summa[_ovp]  (alg/MM/topo_pdgemm/d25_summa.cxx:33-281)
+//   candmc_bcast_cannon_4d  <- bcast_cannon_4d  (alg/MM/topo_pdgemm/dual_cannon.cxx:40-215, intended semantics)
+//   candmc_spcannon         <- kput_cannon / kuni_cannon (alg/MM/splitdim_cannon/spcannon.cxx:33-347)
+//   candmc_upd_A            <- the GEMM pair + allreduce + trsm of upd_A (alg/QR/qr_2d/qr_2d.cxx:259-275)
+//
+// What is kept from the reference: which block every rank owns, which rank is the root of every panel, the order of
+// the panels, what is summed into C and where the result lives.  What is new: every panel is cut into k-chunks whose
+// NCCL broadcast (comm stream) runs under the DMMA GEMM of the previous chunk (compute stream = the caller's stream);
+// the root multiplies straight out of the caller's matrices (no self-copy); the B panel is re-laid out chunk-major
+// by the pack kernel while it is being copied out of its lda anyway, so every message is contiguous; Cannon shifts
+// land in the alternate buffer while the current step multiplies (pointer swap instead of the reference's memcpy
+// back, spcannon.cxx:76-77); the transposes of split-dim Cannon are folded into the NT GEMM where possible.
+#include <algorithm>
+#include <vector>
+
+#include "../../include/candmc_b200.h"
+#include "comm.h"
+#include "common.cuh"
+#include "runtime.h"
+#include "staging.h"
+
+namespace candmc {
+
+namespace {
+
+// ---- small utilities ------------------------------------------------------------------------------------------
+class EventPool {
+ public:
+  cudaEvent_t get() {
+    if (next_ == ev_.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      ev_.push_back(e);
+    }
+    return ev_[next_++];
+  }
+  void reset() { next_ = 0; }
+
+ private:
+  std::vector<cudaEvent_t> ev_;
+  size_t next_ = 0;
+};
+EventPool g_events;
+
+// `to` waits for everything enqueued so far on `from`
+int stream_wait(cudaStream_t to, cudaStream_t from) {
+  if (to == from) return OK;
+  cudaEvent_t e = g_events.get();
+  CANDMC_CHECK(e != nullptr, "event pool: cudaEventCreate failed");
+  CANDMC_CUDA(cudaEventRecord(e, from));
+  CANDMC_CUDA(cudaStreamWaitEvent(to, e, 0));
+  return OK;
+}
+
+bool is_t(char t) { return t == 'T' || t == 't' || t == 'C' || t == 'c'; }
+bool is_n(char t) { return t == 'N' || t == 'n'; }
+
+// number of k-chunks a b-wide panel is cut into: as many as 8, each at least `min_kchunk` wide and even
+int pick_chunks(int64_t b) {
+  const int64_t min_kc = runtime().min_kchunk;
+  for (int nc = 8; nc > 1; nc >>= 1)
+    if (b % nc == 0 && (b / nc) >= min_kc && (b / nc) % 2 == 0) return nc;
+  return 1;
+}
+
+// ---- one SUMMA sweep: C (+)= sum_{i in [i0,i1)} A_i * B_i over a q x q grid ---------------------------------------
+struct SummaArgs {
+  char tA, tB;
+  int64_t b;
+  int i0, i1;
+  const double* myA;  // my block of A (device), used when I am the root of an A panel
+  int64_t ldA;
+  const double* myB;
+  int64_t ldB;
+  double* C;
+  int64_t ldC;
+  bool first_beta_zero;  // beta = 0 on the very first multiply (reference: (i>0)*1.0, summa.cxx:97)
+  candmc_comm* row;      // along my grid row: rank = my column (cdt_row)
+  candmc_comm* col;      // along my grid column: rank = my row (cdt_col)
+  double* ws;            // >= 4*b*b doubles: packA | locB | bufA | bufB
+  cudaStream_t compute;
+};
+
+int summa_sweep(const SummaArgs& a) {
+  const int64_t b = a.b, bb = b * b;
+  const int my_col = a.row->rank, my_row = a.col->rank;
+  cudaStream_t comm = runtime().comm_stream;
+  double* packA = a.ws;
+  double* locB = a.ws + bb;
+  double* bufA = a.ws + 2 * bb;
+  double* bufB = a.ws + 3 * bb;
+  const bool nn = is_n(a.tA) && is_n(a.tB);
+  const bool need_comm = a.row->size > 1 || a.col->size > 1;
+  // transposed panels are moved whole (the flags only reach the local GEMM); a 1x1 grid has nothing to pipeline
+  const int nchunks = (nn && need_comm) ? pick_chunks(b) : 1;
+  const int64_t kc = b / nchunks;
+
+  if (need_comm) CANDMC_TRY(stream_wait(comm, a.compute));  // inputs (and earlier users of ws) are ready
+  std::vector<cudaEvent_t> done_prev(nchunks, nullptr);
+  bool first = a.first_beta_zero;
+  for (int i = a.i0; i < a.i1; ++i) {
+    const bool rootA = (my_col == i), rootB = (my_row == i);
+    std::vector<cudaEvent_t> ready(nchunks, nullptr);
+    // ---- communication for panel i, chunk by chunk, on the comm stream ----
+    if (need_comm) {
+      for (int t = 0; t < nchunks; ++t) {
+        if (done_prev[t]) CANDMC_CUDA(cudaStreamWaitEvent(comm, done_prev[t], 0));  // buf slot t is free again
+        if (a.row->size > 1) {
+          double* slot = bufA + t * kc * b;
+          if (rootA) {
+            const double* src = a.myA + t * kc * a.ldA;  // column slab: contiguous iff ldA == b
+            if (a.ldA != b) {
+              CANDMC_TRY(lda_copy_f64(b, kc, a.ldA, b, src, packA + t * kc * b, comm));
+              src = packA + t * kc * b;
+            }
+            CANDMC_TRY(comm_bcast(a.row, src, const_cast<double*>(src), kc * b, i, comm));
+          } else {
+            CANDMC_TRY(comm_bcast(a.row, slot, slot, kc * b, i, comm));
+          }
+        }
+        if (a.col->size > 1) {
+          double* slot = bufB + t * kc * b;
+          if (rootB) {
+            const double* src = a.myB + t * kc;  // row slab of B: never contiguous unless it is the whole block
+            if (nchunks > 1 || a.ldB != b) {
+              CANDMC_TRY(lda_copy_f64(kc, b, a.ldB, kc, src, locB + t * kc * b, comm));  // chunk-major, ld = kc
+              src = locB + t * kc * b;
+            }
+            CANDMC_TRY(comm_bcast(a.col, src, const_cast<double*>(src), kc * b, i, comm));
+          } else {
+            CANDMC_TRY(comm_bcast(a.col, slot, slot, kc * b, i, comm));
+          }
+        }
+        ready[t] = g_events.get();
+        CANDMC_CHECK(ready[t] != nullptr, "event pool exhausted");
+        CANDMC_CUDA(cudaEventRecord(ready[t], comm));
+      }
+    }
+    // ---- multiplies for panel i on the compute stream ----
+    for (int t = 0; t < nchunks; ++t) {
+      if (ready[t]) CANDMC_CUDA(cudaStreamWaitEvent(a.compute, ready[t], 0));
+      const double* pa;
+      const double* pb;
+      int64_t lda, ldb;
+      if (rootA || a.row->size == 1) {
+        pa = a.myA + t * kc * a.ldA;
+        lda = a.ldA;
+      } else {
+        pa = bufA + t * kc * b;
+        lda = b;
+      }
+      if (rootB || a.col->size == 1) {
+        pb = a.myB + t * kc;
+        ldb = a.ldB;
+      } else {
+        pb = bufB + t * kc * b;
+        ldb = kc;  // chunk-major
+      }
+      CANDMC_TRY(gemm_f64(a.tA, a.tB, b, b, kc, 1.0, pa, lda, pb, ldb, first ? 0.0 : 1.0, a.C, a.ldC, a.compute));
+      first = false;
+      if (need_comm && i + 1 < a.i1) {
+        done_prev[t] = g_events.get();
+        CANDMC_CHECK(done_prev[t] != nullptr, "event pool exhausted");
+        CANDMC_CUDA(cudaEventRecord(done_prev[t], a.compute));
+      }
+    }
+  }
+  return OK;
+}
+
+int check_grid_args(const candmc_ctb_args_t* args, candmc_comm* row, candmc_comm* col, int64_t* b_out) {
+  CANDMC_CHECK(args != nullptr && row != nullptr && col != nullptr, "null argument");
+  CANDMC_CHECK(row->size == col->size, "processor grid must be square (np_row=%d, np_col=%d)", col->size,
+               row->size);  // ASSERT(np_row == np_col), summa.cxx:45
+  CANDMC_CHECK(args->n > 0 && args->n % row->size == 0, "n=%lld must be a positive multiple of the grid dimension %d",
+               (long long)args->n, row->size);  // ASSERT(n % np_row == 0), summa.cxx:46
+  CANDMC_CHECK((is_t(args->trans_A) || is_n(args->trans_A)) && (is_t(args->trans_B) || is_n(args->trans_B)),
+               "bad transpose flags");
+  *b_out = args->n / row->size;
+  return OK;
+}
+
+// ---- lower-triangular solve W <- T^-1 W (T b x b lower, non-unit; W b x kb) — cdtrsm('L','L','N','N') of qr_2d.cxx:271
+constexpr int TRSM_NC = 8;    // right-hand sides per CTA
+constexpr int TRSM_NB = 32;   // diagonal block
+__global__ void __launch_bounds__(256)
+trsm_llnn_kernel(int b, int kb, const double* __restrict__ T, int64_t ldt, double* __restrict__ W, int64_t ldw) {
+  extern __shared__ double sw[];  // b x TRSM_NC, column-major
+  const int c0 = blockIdx.x * TRSM_NC;
+  const int nc = min(TRSM_NC, kb - c0);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int e = tid; e < b * nc; e += nt) sw[e] = W[(e % b) + static_cast<int64_t>(c0 + e / b) * ldw];
+  __syncthreads();
+  for (int i0 = 0; i0 < b; i0 += TRSM_NB) {
+    const int ib = min(TRSM_NB, b - i0);
+    for (int r = i0; r < i0 + ib; ++r) {
+      if (tid < nc) sw[r + tid * b] /= T[r + static_cast<int64_t>(r) * ldt];
+      __syncthreads();
+      const int rem = i0 + ib - r - 1;
+      for (int e = tid; e < rem * nc; e += nt) {
+        const int rr = r + 1 + e % rem, c = e / rem;
+        sw[rr + c * b] -= T[rr + static_cast<int64_t>(r) * ldt] * sw[r + c * b];
+      }
+      __syncthreads();
+    }
+    const int i1 = i0 + ib, rest = b - i1;
+    for (int e = tid; e < rest * nc; e += nt) {
+      const int row = i1 + e % rest, c = e / rest;
+      double acc = 0.0;
+      for (int p = 0; p < ib; ++p) acc += T[row + static_cast<int64_t>(i0 + p) * ldt] * sw[i0 + p + c * b];
+      sw[row + c * b] -= acc;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < b * nc; e += nt) W[(e % b) + static_cast<int64_t>(c0 + e / b) * ldw] = sw[e];
+}
+
+int trsm_llnn(int64_t b, int64_t kb, const double* T, int64_t ldt, double* W, int64_t ldw, cudaStream_t st) {
+  if (b <= 0 || kb <= 0) return OK;
+  const size_t smem = sizeof(double) * b * TRSM_NC;
+  CANDMC_CHECK(smem <= 200 * 1024, "upd_A: panel width b=%lld too large for the triangular solve kernel", (long long)b);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    CANDMC_CUDA(cudaFuncSetAttribute(trsm_llnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int grid = (int)((kb + TRSM_NC - 1) / TRSM_NC);
+  trsm_llnn_kernel<<<grid, 256, smem, st>>>((int)b, (int)kb, T, ldt, W, ldw);
+  CANDMC_CUDA(cudaGetLastError());
+  runtime().launches++;
+  return OK;
+}
+
+}  // namespace
+}  // namespace candmc
+
+using namespace candmc;
+
+extern "C" {
+
+int candmc_set_min_kchunk(int64_t min_kchunk) {
+  CANDMC_CHECK(min_kchunk >= 2, "candmc_set_min_kchunk: must be >= 2");
+  runtime().min_kchunk = min_kchunk;
+  return OK;
+}
+
+// ================================================================================================================
+int candmc_summa(const candmc_ctb_args_t* args, const double* mat_A, const double* mat_B, double* mat_C,
+                 double* buffer, candmc_comm_t* cdt_row, candmc_comm_t* cdt_col, void* stream) {
+  CANDMC_TRY(runtime_require());
+  g_events.reset();
+  int64_t b;
+  CANDMC_TRY(check_grid_args(args, cdt_row, cdt_col, &b));
+  // "make sure we have enough buffer space", summa.cxx:22-24,44 — kept for drop-in behaviour even though the
+  // device workspace is internal
+  CANDMC_CHECK(buffer == nullptr || args->buffer_size >= 4 * b * b * (int64_t)sizeof(double),
+               "summa: buffer_size %lld < 4*b*b*8", (long long)args->buffer_size);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StagedMatrix sA, sB, sC;
+  CANDMC_TRY(sA.open(mat_A, b, b, args->lda_A, true, st));
+  CANDMC_TRY(sB.open(mat_B, b, b, args->lda_B, true, st));
+  CANDMC_TRY(sC.open(mat_C, b, b, args->lda_C, false, st));
+  void* ws = nullptr;
+  CANDMC_TRY(workspace_get(sizeof(double) * (cdt_row->size > 1 ? 4 * b * b : 2), &ws));
+  SummaArgs a;
+  a.tA = args->trans_A; a.tB = args->trans_B; a.b = b; a.i0 = 0; a.i1 = cdt_row->size;
+  a.myA = sA.ptr(); a.ldA = sA.ld(); a.myB = sB.ptr(); a.ldB = sB.ld();
+  a.C = sC.ptr(); a.ldC = sC.ld(); a.first_beta_zero = true;
+  a.row = cdt_row; a.col = cdt_col; a.ws = static_cast<double*>(ws); a.compute = st;
+  CANDMC_TRY(summa_sweep(a));
+  CANDMC_TRY(sC.close_out(st));
+  if (sA.staged() || sB.staged() || sC.staged()) CANDMC_CUDA(cudaStreamSynchronize(st));
+  return OK;
+}
+
+// ================================================================================================================
+int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const double* mat_B, double* mat_C,
+                     double* buffer, candmc_comm_t* cdt_row, candmc_comm_t* cdt_col, candmc_comm_t* cdt_kdir,
+                     int ovp, void* stream) {
+  CANDMC_TRY(runtime_require());
+  g_events.reset();
+  int64_t b;
+  CANDMC_TRY(check_grid_args(args, cdt_row, cdt_col, &b));
+  CANDMC_CHECK(cdt_kdir != nullptr, "d25_summa: null depth communicator");
+  const int q = cdt_row->size, c = cdt_kdir->size, layer = cdt_kdir->rank;
+  const bool ksplit = (q == 1 && c > 1);  // extension: 1 x 1 x c grid splits k; the reference asserts q % c == 0
+  CANDMC_CHECK(ksplit || q % c == 0, "d25_summa: grid dimension %d not divisible by replication factor %d", q,
+               c);  // ASSERT(np_row % c_rep == 0), d25_summa.cxx:63
+  CANDMC_CHECK(!ksplit || (b % c == 0 && is_n(args->trans_A) && is_n(args->trans_B)),
+               "d25_summa (1x1xc k-split): n must be divisible by c and the operands untransposed");
+  const int64_t need = (ovp ? 5 : 3) * b * b * (int64_t)sizeof(double);  // buffer_space_req, d25_summa.cxx:25-31
+  CANDMC_CHECK(buffer == nullptr || args->buffer_size >= need, "d25_summa: buffer_size %lld < %lld",
+               (long long)args->buffer_size, (long long)need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StagedMatrix sA, sB, sC;
+  CANDMC_TRY(sA.open(mat_A, b, b, args->lda_A, true, st));
+  CANDMC_TRY(sB.open(mat_B, b, b, args->lda_B, true, st));
+  CANDMC_TRY(sC.open(mat_C, b, b, args->lda_C, false, st));
+  void* wsv = nullptr;
+  // packA | locB | bufA | bufB only when panels travel (q > 1); bufC only when there is a depth sum (c > 1)
+  const int64_t ws_panels = (q > 1) ? 4 * b * b : 0;
+  CANDMC_TRY(workspace_get(sizeof(double) * (ws_panels + (c > 1 ? b * b : 0) + 2), &wsv));
+  double* ws = static_cast<double*>(wsv);
+  double* bufC = ws + ws_panels;
+  // with replication the partial product goes to a contiguous scratch block and the depth sum writes mat_C
+  double* Cpart = (c > 1) ? bufC : sC.ptr();
+  const int64_t ldCpart = (c > 1) ? b : sC.ld();
+
+  if (ksplit) {
+    const int64_t kb = b / c;
+    CANDMC_TRY(gemm_f64('N', 'N', b, b, kb, 1.0, sA.ptr() + layer * kb * sA.ld(), sA.ld(), sB.ptr() + layer * kb,
+                        sB.ld(), 0.0, Cpart, ldCpart, st));
+  } else {
+    SummaArgs a;
+    a.tA = args->trans_A; a.tB = args->trans_B; a.b = b;
+    a.i0 = layer * (q / c); a.i1 = (layer + 1) * (q / c);  // d25_summa.cxx:124,151
+    a.myA = sA.ptr(); a.ldA = sA.ld(); a.myB = sB.ptr(); a.ldB = sB.ld();
+    a.C = Cpart; a.ldC = ldCpart; a.first_beta_zero = true;  // intended semantics, SURVEY App. A-1
+    a.row = cdt_row; a.col = cdt_col; a.ws = ws; a.compute = st;
+    CANDMC_TRY(summa_sweep(a));
+  }
+  if (c > 1) {
+    // MPI_Allreduce(buf_C, mat_C, b*b, SUM, cdt_kdir) — d25_summa.cxx:149,221 (result on every layer)
+    if (sC.ld() == b) {
+      CANDMC_TRY(comm_allreduce(cdt_kdir, bufC, sC.ptr(), b * b, st));
+    } else {
+      CANDMC_TRY(comm_allreduce(cdt_kdir, bufC, bufC, b * b, st));
+      CANDMC_TRY(lda_copy_f64(b, b, b, sC.ld(), bufC, sC.ptr(), st));
+    }
+  }
+  CANDMC_TRY(sC.close_out(st));
+  if (sA.staged() || sB.staged() || sC.staged()) CANDMC_CUDA(cudaStreamSynchronize(st));
+  return OK;
+}
+
+// ================================================================================================================
+int candmc_bcast_cannon_4d(const candmc_ctb_args_t* args, const double* mat_A, const double* mat_B, double* mat_C,
+                           double* buffer, candmc_comm_t* cdt_x1, candmc_comm_t* cdt_y1, candmc_comm_t* cdt_x2,
+                           candmc_comm_t* cdt_y2, void* stream) {
+  CANDMC_TRY(runtime_require());
+  g_events.reset();
+  CANDMC_CHECK(args && cdt_x1 && cdt_y1 && cdt_x2 && cdt_y2, "bcast_cannon_4d: null argument");
+  const int x1_np = cdt_x1->size, x2_np = cdt_x2->size;
+  CANDMC_CHECK(x1_np == cdt_y1->size && x2_np == cdt_y2->size, "bcast_cannon_4d: grids must be square");  // :71-72
+  CANDMC_CHECK(args->n > 0 && args->n % ((int64_t)x1_np * x2_np) == 0, "bcast_cannon_4d: n %% (x1_np*x2_np) != 0");
+  CANDMC_CHECK(is_n(args->trans_A) && is_n(args->trans_B),
+               "bcast_cannon_4d: only 'N','N' (the reference passes the flags to the local dgemm only)");
+  const int64_t b = args->n / ((int64_t)x1_np * x2_np), bb = b * b;
+  const int64_t need = (args->ovp ? 5 : 3) * bb * (int64_t)sizeof(double);  // dual_cannon.cxx:31-37
+  CANDMC_CHECK(buffer == nullptr || args->buffer_size >= need, "bcast_cannon_4d: buffer_size too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaStream_t shift = runtime().aux_stream;
+  StagedMatrix sA, sB, sC;
+  CANDMC_TRY(sA.open(mat_A, b, b, args->lda_A, true, st));
+  CANDMC_TRY(sB.open(mat_B, b, b, args->lda_B, true, st));
+  CANDMC_TRY(sC.open(mat_C, b, b, args->lda_C, false, st));
+  void* wsv = nullptr;
+  // 4 b^2 for the inner SUMMA sweep + two ping-pong pairs for the Cannon level
+  CANDMC_TRY(workspace_get(sizeof(double) * 8 * bb, &wsv));
+  double* ws = static_cast<double*>(wsv);
+  double* pingA[2] = {ws + 4 * bb, ws + 5 * bb};
+  double* pingB[2] = {ws + 6 * bb, ws + 7 * bb};
+
+  const double* curA = sA.ptr();
+  const double* curB = sB.ptr();
+  int64_t ldA = sA.ld(), ldB = sB.ld();
+  int nextA = 0, nextB = 0;  // ping-pong slot the next incoming block lands in (never the current block)
+  const int x2 = cdt_x2->rank, y2 = cdt_y2->rank;
+  auto wrap = [](int a, int m) { return ((a % m) + m) % m; };
+
+  if (x2_np > 1) {
+    CANDMC_TRY(stream_wait(shift, st));
+    // messages must be contiguous: get the blocks out of their lda first (dual_cannon.cxx:89-102)
+    if (ldA != b) {
+      CANDMC_TRY(lda_copy_f64(b, b, ldA, b, curA, pingA[0], shift));
+      curA = pingA[0]; ldA = b; nextA = 1;
+    }
+    if (ldB != b) {
+      CANDMC_TRY(lda_copy_f64(b, b, ldB, b, curB, pingB[0], shift));
+      curB = pingB[0]; ldB = b; nextB = 1;
+    }
+    // stagger (dual_cannon.cxx:106-137, with the tags/waits it meant): A to x2-y2 along cdt_x2, B to y2-x2 along cdt_y2
+    const int tgtA = wrap(x2 - y2, x2_np), srcA = wrap(x2 + y2, x2_np);
+    const int tgtB = wrap(y2 - x2, x2_np), srcB = wrap(y2 + x2, x2_np);
+    if (tgtA != x2) {
+      CANDMC_TRY(comm_sendrecv(cdt_x2, curA, bb, tgtA, pingA[nextA], bb, srcA, shift));
+      curA = pingA[nextA]; nextA ^= 1;
+    }
+    if (tgtB != y2) {
+      CANDMC_TRY(comm_sendrecv(cdt_y2, curB, bb, tgtB, pingB[nextB], bb, srcB, shift));
+      curB = pingB[nextB]; nextB ^= 1;
+    }
+    CANDMC_TRY(stream_wait(st, shift));
+  }
+
+  for (int i2 = 0; i2 < x2_np; ++i2) {
+    const double* nxtA = curA;
+    const double* nxtB = curB;
+    cudaEvent_t shift_done = nullptr;
+    if (i2 < x2_np - 1) {
+      // shift by -1 (dual_cannon.cxx:196-213) into the alternate buffers WHILE this step multiplies.  The wait makes
+      // sure the previous step's multiplies (the last readers of the alternate buffers) are finished.
+      CANDMC_TRY(stream_wait(shift, st));
+      CANDMC_TRY(comm_sendrecv(cdt_x2, curA, bb, wrap(x2 - 1, x2_np), pingA[nextA], bb, wrap(x2 + 1, x2_np), shift));
+      CANDMC_TRY(comm_sendrecv(cdt_y2, curB, bb, wrap(y2 - 1, x2_np), pingB[nextB], bb, wrap(y2 + 1, x2_np), shift));
+      nxtA = pingA[nextA]; nextA ^= 1;
+      nxtB = pingB[nextB]; nextB ^= 1;
+      shift_done = g_events.get();
+      CANDMC_CHECK(shift_done != nullptr, "event pool exhausted");
+      CANDMC_CUDA(cudaEventRecord(shift_done, shift));
+    }
+    SummaArgs a;
+    a.tA = 'N'; a.tB = 'N'; a.b = b; a.i0 = 0; a.i1 = x1_np;
+    a.myA = curA; a.ldA = ldA; a.myB = curB; a.ldB = ldB;
+    a.C = sC.ptr(); a.ldC = sC.ld(); a.first_beta_zero = (i2 == 0);  // beta = (i1>0 || i2>0), dual_cannon.cxx:188
+    a.row = cdt_x1; a.col = cdt_y1; a.ws = ws; a.compute = st;
+    CANDMC_TRY(summa_sweep(a));
+    if (shift_done) {
+      CANDMC_CUDA(cudaStreamWaitEvent(st, shift_done, 0));
+      curA = nxtA; curB = nxtB;
+    }
+  }
+  CANDMC_TRY(sC.close_out(st));
+  if (sA.staged() || sB.staged() || sC.staged()) CANDMC_CUDA(cudaStreamSynchronize(st));
+  return OK;
+}
+
+// ================================================================================================================
+// split-dimensional Cannon.  Slices are contiguous ranges of the canonical A (m x k) and B^T (n x k) arrays, exactly
+// as in the reference; every MPI_Put between two fences becomes a matched ncclSend/ncclRecv inside one group.
+namespace {
+
+struct Spc {
+  candmc_comm* world;
+  int rank, kary, ndim, half;
+  int64_t n, m, k;
+  double alpha;
+  double* A[2];
+  double* B[2];
+  int cur = 0;
+  double* C;
+  int64_t ldc;
+  cudaStream_t compute, comm;
+  cudaEvent_t last_reader[2] = {nullptr, nullptr};  // latest GEMM that read buffer pair p
+  cudaEvent_t last_xchg = nullptr;                  // latest exchange (produced the current pair)
+};
+
+int digit(int r, int kary, int pos) {
+  for (int i = 0; i < pos; ++i) r /= kary;
+  return r % kary;
+}
+int ipow(int a, int e) {
+  int r = 1;
+  while (e-- > 0) r *= a;
+  return r;
+}
+int wrapi(int a, int m) { return ((a % m) + m) % m; }
+
+struct Xfer {
+  const double* send;
+  double* recv;
+  int64_t count;
+  int dst, src;
+};
+
+int spc_exchange(Spc& s, const std::vector<Xfer>& xs) {
+  const int p = s.cur;
+  // destination pair 1-p must no longer be read by a GEMM; the source pair p must have been produced
+  if (s.last_reader[1 - p]) CANDMC_CUDA(cudaStreamWaitEvent(s.comm, s.last_reader[1 - p], 0));
+  bool any_remote = false;
+  for (const Xfer& x : xs) {
+    if (x.dst == s.rank) {
+      CANDMC_CHECK(x.src == s.rank, "spcannon: asymmetric self transfer");
+      CANDMC_CUDA(cudaMemcpyAsync(x.recv, x.send, sizeof(double) * x.count, cudaMemcpyDeviceToDevice, s.comm));
+    } else {
+      any_remote = true;
+    }
+  }
+  if (any_remote) {
+    CANDMC_NCCL(ncclGroupStart());
+    for (const Xfer& x : xs) {
+      if (x.dst == s.rank) continue;
+      CANDMC_NCCL(ncclSend(x.send, (size_t)x.count, ncclDouble, x.dst, s.world->nccl, s.comm));
+      CANDMC_NCCL(ncclRecv(x.recv, (size_t)x.count, ncclDouble, x.src, s.world->nccl, s.comm));
+    }
+    CANDMC_NCCL(ncclGroupEnd());
+  }
+  s.last_xchg = g_events.get();
+  CANDMC_CHECK(s.last_xchg != nullptr, "event pool exhausted");
+  CANDMC_CUDA(cudaEventRecord(s.last_xchg, s.comm));
+  s.cur = 1 - p;  // A = buf_A, B = buf_B (spcannon.cxx:76-77) as a pointer swap
+  return OK;
+}
+
+int spc_stagger(Spc& s, int level) {  // uni_stagger, spcannon.cxx:33-84
+  const int64_t bA = 2 * s.m * s.k / s.ndim, bB = 2 * s.k * s.n / s.ndim;
+  std::vector<Xfer> xs;
+  const int p = s.cur;
+  for (int j = 0; j < s.half; ++j) {
+    const int i = (j + level) % s.half;
+    const int tA = digit(s.rank, s.kary, 2 * j), tB = digit(s.rank, s.kary, 2 * j + 1);
+    const int sA = ipow(s.kary, 2 * j), sB = ipow(s.kary, 2 * j + 1);
+    // I put to the rank whose digit is (tA - tB); the rank whose digit is (tA + tB) puts to me
+    xs.push_back({s.A[p] + i * bA, s.A[1 - p] + i * bA, bA, s.rank + (wrapi(tA - tB, s.kary) - tA) * sA,
+                  s.rank + (wrapi(tA + tB, s.kary) - tA) * sA});
+    xs.push_back({s.B[p] + i * bB, s.B[1 - p] + i * bB, bB, s.rank + (wrapi(tB - tA, s.kary) - tB) * sB,
+                  s.rank + (wrapi(tB + tA, s.kary) - tB) * sB});
+  }
+  CANDMC_TRY(spc_exchange(s, xs));
+  if (level < s.half - 1) return spc_stagger(s, level + 1);
+  return OK;
+}
+
+int spc_shift(Spc& s, int bidir, int level, double beta) {  // bdr_shift :87-162 / uni_shift :165-234
+  double dbeta = beta;
+  for (int ka = 0; ka < s.kary; ++ka) {
+    if (level < s.half - 1) {
+      CANDMC_TRY(spc_shift(s, bidir, level + 1, dbeta));
+    } else {
+      const int p = s.cur;
+      if (s.last_xchg) CANDMC_CUDA(cudaStreamWaitEvent(s.compute, s.last_xchg, 0));
+      // DGEMM('N','T',m,n,k,alpha,A,m,B,n,dbeta,C,m) — spcannon.cxx:117,195
+      CANDMC_TRY(gemm_f64('N', 'T', s.m, s.n, s.k, s.alpha, s.A[p], s.m, s.B[p], s.n, dbeta, s.C, s.ldc, s.compute));
+      s.last_reader[p] = g_events.get();
+      CANDMC_CHECK(s.last_reader[p] != nullptr, "event pool exhausted");
+      CANDMC_CUDA(cudaEventRecord(s.last_reader[p], s.compute));
+    }
+    dbeta = 1.0;
+    if (s.kary == 1) continue;  // every shift is the identity
+    std::vector<Xfer> xs;
+    const int p = s.cur;
+    for (int j = 0; j < s.half; ++j) {
+      const int i = (j + level) % s.half;
+      const int tA = digit(s.rank, s.kary, 2 * j), tB = digit(s.rank, s.kary, 2 * j + 1);
+      const int sA = ipow(s.kary, 2 * j), sB = ipow(s.kary, 2 * j + 1);
+      const int upA = s.rank + (wrapi(tA + 1, s.kary) - tA) * sA, dnA = s.rank + (wrapi(tA - 1, s.kary) - tA) * sA;
+      const int upB = s.rank + (wrapi(tB + 1, s.kary) - tB) * sB, dnB = s.rank + (wrapi(tB - 1, s.kary) - tB) * sB;
+      if (bidir) {  // halves 2i and 2i+1 travel in opposite directions (spcannon.cxx:139-152)
+        const int64_t bA = s.m * s.k / s.ndim, bB = s.k * s.n / s.ndim;
+        xs.push_back({s.A[p] + 2 * i * bA, s.A[1 - p] + 2 * i * bA, bA, upA, dnA});
+        xs.push_back({s.A[p] + (2 * i + 1) * bA, s.A[1 - p] + (2 * i + 1) * bA, bA, dnA, upA});
+        xs.push_back({s.B[p] + 2 * i * bB, s.B[1 - p] + 2 * i * bB, bB, upB, dnB});
+        xs.push_back({s.B[p] + (2 * i + 1) * bB, s.B[1 - p] + (2 * i + 1) * bB, bB, dnB, upB});
+      } else {  // the whole slice travels +1 (spcannon.cxx:217-224)
+        const int64_t bA = 2 * s.m * s.k / s.ndim, bB = 2 * s.k * s.n / s.ndim;
+        xs.push_back({s.A[p] + i * bA, s.A[1 - p] + i * bA, bA, upA, dnA});
+        xs.push_back({s.B[p] + i * bB, s.B[1 - p] + i * bB, bB, upB, dnB});
+      }
+    }
+    CANDMC_TRY(spc_exchange(s, xs));
+  }
+  return OK;
+}
+
+}  // namespace
+
+int candmc_spcannon(int bidir, int rank, int kary, int ndim, candmc_comm_t* world, int n, int m, int k,
+                    char transp_A, double alpha, const double* A, char transp_B, double beta, const double* B,
+                    double* C, void* stream) {
+  CANDMC_TRY(runtime_require());
+  g_events.reset();
+  CANDMC_CHECK(world != nullptr, "spcannon: null communicator");
+  CANDMC_CHECK(ndim >= 2 && ndim % 2 == 0 && kary >= 1, "spcannon: need an even ndim >= 2 and kary >= 1");
+  CANDMC_CHECK(k % ndim == 0, "spcannon: k %% ndim != 0");  // assert(k%ndim == 0), spcannon.cxx:252
+  CANDMC_CHECK(ipow(kary, ndim) == world->size, "spcannon: kary^ndim = %d but communicator has %d ranks",
+               ipow(kary, ndim), world->size);
+  CANDMC_CHECK(rank == world->rank, "spcannon: rank argument %d != communicator rank %d", rank, world->rank);
+  CANDMC_CHECK(n >= 0 && m >= 0 && k >= 0, "spcannon: negative dimension");
+  CANDMC_CHECK((is_t(transp_A) || is_n(transp_A)) && (is_t(transp_B) || is_n(transp_B)), "spcannon: bad transpose");
+  if (m == 0 || n == 0) return OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool tA = is_t(transp_A), tB = is_t(transp_B);
+  if (k == 0) return candmc_dgemm('N', 'N', m, n, 0, alpha, A, m, B, 1, beta, C, m, stream);  // C <- beta*C
+  StagedMatrix sA, sB, sC;
+  CANDMC_TRY(sA.open(A, tA ? k : m, tA ? m : k, tA ? k : m, true, st));
+  CANDMC_TRY(sB.open(B, tB ? n : k, tB ? k : n, tB ? n : k, true, st));
+  CANDMC_TRY(sC.open(C, m, n, m, beta != 0.0, st));
+  const int64_t mk = (int64_t)m * k, nk = (int64_t)n * k;
+  void* wsv = nullptr;
+  CANDMC_TRY(workspace_get(sizeof(double) * 2 * (mk + nk + 2), &wsv));
+  double* ws = static_cast<double*>(wsv);
+  Spc s;
+  s.world = world; s.rank = rank; s.kary = kary; s.ndim = ndim; s.half = ndim / 2;
+  s.n = n; s.m = m; s.k = k; s.alpha = alpha;
+  s.A[0] = ws; s.A[1] = ws + mk + (mk & 1);
+  s.B[0] = s.A[1] + mk + (mk & 1); s.B[1] = s.B[0] + nk + (nk & 1);
+  s.C = sC.ptr(); s.ldc = sC.ld(); s.compute = st; s.comm = runtime().comm_stream;
+  // canonicalise (spcannon.cxx:262-267): A -> m x k, B -> B^T = n x k; out of place, so the caller's A/B survive
+  if (k > 0) {
+    if (tA) CANDMC_TRY(transpose_f64(k, m, sA.ptr(), sA.ld(), s.A[0], m, st));
+    else CANDMC_TRY(lda_copy_f64(m, k, sA.ld(), m, sA.ptr(), s.A[0], st));
+    if (!tB) CANDMC_TRY(transpose_f64(k, n, sB.ptr(), sB.ld(), s.B[0], n, st));
+    else CANDMC_TRY(lda_copy_f64(n, k, sB.ld(), n, sB.ptr(), s.B[0], st));
+  }
+  CANDMC_TRY(stream_wait(s.comm, st));
+  if (kary > 1 && k > 0) CANDMC_TRY(spc_stagger(s, 0));
+  CANDMC_TRY(spc_shift(s, bidir, 0, beta));
+  CANDMC_TRY(stream_wait(st, s.comm));
+  CANDMC_TRY(sC.close_out(st));
+  if (sA.staged() || sB.staged() || sC.staged()) CANDMC_CUDA(cudaStreamSynchronize(st));
+  return OK;
+}
+
+// ================================================================================================================
+int candmc_upd_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
+                 const double* T, candmc_comm_t* ccol, void* stream) {
+  CANDMC_TRY(runtime_require());
+  g_events.reset();
+  CANDMC_CHECK(mb >= 0 && kb >= 0 && b > 0, "upd_A: bad extents");
+  CANDMC_CHECK(is_device_ptr(Y) && is_device_ptr(A) && is_device_ptr(T), "upd_A: operands must be device pointers");
+  if (kb == 0) return OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* wsv = nullptr;
+  CANDMC_TRY(workspace_get(sizeof(double) * b * kb, &wsv));
+  double* W = static_cast<double*>(wsv);
+  // W = Y^T A (qr_2d.cxx:259); ranks without rows contribute zeros (:262)
+  if (mb > 0) CANDMC_TRY(gemm_f64('T', 'N', b, kb, mb, 1.0, Y, lda_Y, A, lda_A, 0.0, W, b, st));
+  else CANDMC_TRY(fill_f64(W, b * kb, 0.0, st));
+  if (ccol != nullptr && ccol->size > 1) CANDMC_TRY(comm_allreduce(ccol, W, W, b * kb, st));  // :265
+  if (mb > 0) {
+    CANDMC_TRY(trsm_llnn(b, kb, T, b, W, b, st));                                              // :271
+    CANDMC_TRY(gemm_f64('N', 'N', mb, kb, b, -1.0, Y, lda_Y, W, b, 1.0, A, lda_A, st));        // :275
+  }
+  return OK;
+}
+
+}  // extern "C"

@@ -5,11 +5,14 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 namespace candmc {
 
 namespace {
 thread_local char g_err[1024] = "";
 Runtime g_rt;
+constexpr unsigned kTileCounters = 1024;
 }  // namespace
 
 void set_last_error(const char* fmt, ...) {
@@ -54,6 +57,8 @@ int runtime_init(int device) {
   CANDMC_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess,
                "candmc_init: driver does not export cuTensorMapEncodeTiled");
   g_rt.pfn_encode_tiled = fn;
+  CANDMC_CUDA(cudaMalloc(&g_rt.tile_counters, sizeof(int) * kTileCounters));
+  CANDMC_CUDA(cudaMemset(g_rt.tile_counters, 0, sizeof(int) * kTileCounters));
   g_rt.initialized = true;
   return OK;
 }
@@ -66,6 +71,7 @@ int runtime_require() {
 int runtime_finalize() {
   if (!g_rt.initialized) return OK;
   if (g_rt.workspace) cudaFree(g_rt.workspace);
+  if (g_rt.tile_counters) cudaFree(g_rt.tile_counters);
   if (g_rt.comm_stream) cudaStreamDestroy(g_rt.comm_stream);
   if (g_rt.aux_stream) cudaStreamDestroy(g_rt.aux_stream);
   g_rt = Runtime();
@@ -89,6 +95,57 @@ int workspace_get(size_t bytes, void** out) {
     g_rt.workspace_bytes = bytes;
   }
   *out = g_rt.workspace;
+  return OK;
+}
+
+int next_tile_counter(int** out, cudaStream_t stream) {
+  int* c = g_rt.tile_counters + (g_rt.tile_counter_seq++ % kTileCounters);
+  CANDMC_CUDA(cudaMemsetAsync(c, 0, sizeof(int), stream));
+  *out = c;
+  return OK;
+}
+
+namespace {
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  double flops;
+};
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+int profile_begin_launch(cudaStream_t stream, double flops) {
+  ProfRec r;
+  CANDMC_CUDA(cudaEventCreate(&r.e0));
+  CANDMC_CUDA(cudaEventCreate(&r.e1));
+  r.flops = flops;
+  CANDMC_CUDA(cudaEventRecord(r.e0, stream));
+  g_prof.push_back(r);
+  return OK;
+}
+int profile_end_launch(cudaStream_t stream) {
+  CANDMC_CUDA(cudaEventRecord(g_prof.back().e1, stream));
+  return OK;
+}
+int profile_reset() {
+  for (ProfRec& r : g_prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  return OK;
+}
+int profile_collect(int64_t* launches, double* total_ms, double* total_flops) {
+  CANDMC_CUDA(cudaDeviceSynchronize());
+  double ms = 0, fl = 0;
+  for (ProfRec& r : g_prof) {
+    float t = 0;
+    CANDMC_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms += t;
+    fl += r.flops;
+  }
+  *launches = (int64_t)g_prof.size();
+  *total_ms = ms;
+  *total_flops = fl;
   return OK;
 }
 

@@ -19,6 +19,11 @@ struct Runtime {
   void* workspace = nullptr;            // grow-only device scratch
   size_t workspace_bytes = 0;
   void* pfn_encode_tiled = nullptr;     // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
+  int* tile_counters = nullptr;         // ring of device counters for the GEMM's dynamic tile scheduler
+  unsigned tile_counter_seq = 0;
+  bool static_schedule = false;         // debug: round-robin tile schedule instead of the atomic counter
+  bool profile = false;                 // bracket every DMMA GEMM launch with events (bench.py's roofline leg)
+  int64_t min_kchunk = 1024;            // smallest k-chunk the SUMMA pipeline cuts a panel into
 };
 
 Runtime& runtime();
@@ -30,6 +35,15 @@ int runtime_require();
 int runtime_finalize();
 // Grow-only scratch; contents undefined.  Not thread safe (one rank = one host thread, as in the reference).
 int workspace_get(size_t bytes, void** out);
+
+// GEMM launch profiling (candmc_profile_*): events around each TMA+DMMA launch on its own stream.
+int profile_begin_launch(cudaStream_t stream, double flops);
+int profile_end_launch(cudaStream_t stream);
+int profile_reset();
+int profile_collect(int64_t* launches, double* total_ms, double* total_flops);
+
+// Hands out a zeroed device counter (memset is enqueued on `stream`) for one GEMM launch.
+int next_tile_counter(int** out, cudaStream_t stream);
 
 // 2-D FP64 tensor map with 128 B swizzle: dim0 contiguous (dim0 x dim1 elements, leading dimension `ld`),
 // box = box0 x box1 elements (box0 * 8 bytes must be <= 128).

@@ -1,0 +1,163 @@
+"""Host-side mirror of the reference's CANMM operator interface, over the C ABI.
+
+Names, argument order and meaning follow the reference headers (alg/MM/topo_pdgemm/topo_pdgemm_algs.h:6-59,
+alg/MM/splitdim_cannon/spcannon.h:31-59, alg/shared/lapack.h:10-16, alg/shared/util.h:403-412); matrices are torch
+CUDA tensors (float64, column-major storage: a b x b block is `torch.empty((cols, rows)).T` or any tensor whose
+`data_ptr()` addresses column-major data), numpy arrays (host path, staged inside the library) or raw integer
+addresses.  Errors raise CandmcError where the reference would assert/ABORT.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+from . import _lib
+from ._lib import check, lib
+
+
+def _ptr(x):
+    """Address of a matrix operand: torch tensor, numpy array, ctypes pointer or int."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if hasattr(x, "ctypes"):
+        return x.ctypes.data
+    raise TypeError(f"cannot take the address of {type(x)!r}")
+
+
+def _stream(stream):
+    if stream is None:
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                return torch.cuda.current_stream().cuda_stream
+        except Exception:  # pragma: no cover - torch always present in this image
+            pass
+        return None
+    if isinstance(stream, int):
+        return stream
+    return stream.cuda_stream
+
+
+def _ch(c):
+    return c.encode("ascii") if isinstance(c, str) else c
+
+
+@dataclass
+class CommData_t:
+    """Mirror of `CommData_t` (alg/shared/comm.h:32-63): communicator handle + cached np / rank."""
+    cm: int = 0          # candmc_comm_t* (stands where the reference has an MPI_Comm)
+    np: int = 1
+    rank: int = 0
+    color: int = 0
+    alive: int = 1
+
+    def free(self):       # FREE_CDT (comm.h:199-201)
+        if self.cm:
+            check(lib().candmc_comm_free(self.cm))
+            self.cm = 0
+
+
+@dataclass
+class ctb_args_t:
+    """Mirror of `ctb_args_t` (alg/MM/topo_pdgemm/topo_pdgemm_algs.h:6-15)."""
+    n: int
+    lda_A: int
+    lda_B: int
+    lda_C: int
+    buffer_size: int = 0
+    trans_A: str = "N"
+    trans_B: str = "N"
+    ovp: int = 0
+
+    def _c(self):
+        return _lib.CtbArgs(_ch(self.trans_A), _ch(self.trans_B), self.n, self.lda_A, self.lda_B, self.lda_C,
+                            self.buffer_size, self.ovp)
+
+
+# ---- local kernels ------------------------------------------------------------------------------------------------
+def cdgemm(transa, transb, m, n, k, a, A, lda, B, ldb, b, Cm, ldc, stream=None):
+    """cdgemm (alg/shared/lapack.h:10-16): C = a*op(A)*op(B) + b*C."""
+    check(lib().candmc_dgemm(_ch(transa), _ch(transb), m, n, k, a, _ptr(A), lda, _ptr(B), ldb, b, _ptr(Cm), ldc,
+                             _stream(stream)))
+
+
+def lda_cpy(nrow, ncol, lda_A, lda_B, A, B, a=None, b=None, stream=None):
+    """lda_cpy and its scaled overload (alg/shared/util.h:459-501)."""
+    if a is None:
+        check(lib().candmc_lda_cpy(nrow, ncol, lda_A, lda_B, _ptr(A), _ptr(B), _stream(stream)))
+    else:
+        check(lib().candmc_lda_cpy_scaled(nrow, ncol, lda_A, lda_B, _ptr(A), _ptr(B), a, b, _stream(stream)))
+
+
+def transpose(rows, cols, A, lda, B, ldb, stream=None):
+    """Out-of-place TRANSPOSE (alg/MM/splitdim_cannon/spcannon_internal.h:66-72)."""
+    check(lib().candmc_transpose(rows, cols, _ptr(A), lda, _ptr(B), ldb, _stream(stream)))
+
+
+def fill_drand48(X, nrow, ncol, ld, row0, col0, n_global, which, stream=None):
+    check(lib().candmc_fill_drand48(_ptr(X), nrow, ncol, ld, row0, col0, n_global, which, _stream(stream)))
+
+
+def frob_diff(X, ldx, Y, ldy, nrow, ncol, stream=None):
+    """(||X-Y||_F^2, ||Y||_F^2) computed on the device."""
+    out = (C.c_double * 2)()
+    check(lib().candmc_frob_diff(_ptr(X), ldx, _ptr(Y), ldy, nrow, ncol, out, _stream(stream)))
+    return out[0], out[1]
+
+
+def set_min_kchunk(v):
+    check(lib().candmc_set_min_kchunk(v))
+
+
+# ---- distributed multiplies -----------------------------------------------------------------------------------------
+def summa(args: ctb_args_t, mat_A, mat_B, mat_C, buffer, cdt_row: CommData_t, cdt_col: CommData_t, stream=None):
+    """summa (topo_pdgemm_algs.h:17-23)."""
+    a = args._c()
+    check(lib().candmc_summa(C.byref(a), _ptr(mat_A), _ptr(mat_B), _ptr(mat_C), _ptr(buffer), cdt_row.cm, cdt_col.cm,
+                             _stream(stream)))
+
+
+def _d25(args, mat_A, mat_B, mat_C, buffer, cdt_row, cdt_col, cdt_kdir, ovp, stream):
+    a = args._c()
+    check(lib().candmc_d25_summa(C.byref(a), _ptr(mat_A), _ptr(mat_B), _ptr(mat_C), _ptr(buffer), cdt_row.cm,
+                                 cdt_col.cm, cdt_kdir.cm, ovp, _stream(stream)))
+
+
+def d25_summa(args, mat_A, mat_B, mat_C, buffer, cdt_row, cdt_col, cdt_kdir, stream=None):
+    """d25_summa (topo_pdgemm_algs.h:25-36)."""
+    _d25(args, mat_A, mat_B, mat_C, buffer, cdt_row, cdt_col, cdt_kdir, 0, stream)
+
+
+def d25_summa_ovp(args, mat_A, mat_B, mat_C, buffer, cdt_row, cdt_col, cdt_kdir, stream=None):
+    """d25_summa_ovp (topo_pdgemm_algs.h:38-49)."""
+    _d25(args, mat_A, mat_B, mat_C, buffer, cdt_row, cdt_col, cdt_kdir, 1, stream)
+
+
+def bcast_cannon_4d(args, mat_A, mat_B, mat_C, buffer, cdt_x1, cdt_y1, cdt_x2, cdt_y2, stream=None):
+    """bcast_cannon_4d (topo_pdgemm_algs.h:51-59)."""
+    a = args._c()
+    check(lib().candmc_bcast_cannon_4d(C.byref(a), _ptr(mat_A), _ptr(mat_B), _ptr(mat_C), _ptr(buffer), cdt_x1.cm,
+                                       cdt_y1.cm, cdt_x2.cm, cdt_y2.cm, _stream(stream)))
+
+
+def kput_cannon(rank, kary, ndim, comm: CommData_t, n, m, k, transp_A, alpha, A, transp_B, beta, B, Cm, stream=None):
+    """kput_cannon (alg/MM/splitdim_cannon/spcannon.h:31-44), bidirectional."""
+    check(lib().candmc_spcannon(1, rank, kary, ndim, comm.cm, n, m, k, _ch(transp_A), alpha, _ptr(A), _ch(transp_B),
+                                beta, _ptr(B), _ptr(Cm), _stream(stream)))
+
+
+def kuni_cannon(rank, kary, ndim, comm: CommData_t, n, m, k, transp_A, alpha, A, transp_B, beta, B, Cm, stream=None):
+    """kuni_cannon (alg/MM/splitdim_cannon/spcannon.h:46-59), unidirectional."""
+    check(lib().candmc_spcannon(0, rank, kary, ndim, comm.cm, n, m, k, _ch(transp_A), alpha, _ptr(A), _ch(transp_B),
+                                beta, _ptr(B), _ptr(Cm), _stream(stream)))
+
+
+def upd_A(Y, lda_Y, A, lda_A, mb, kb, b, T, ccol: CommData_t | None = None, stream=None):
+    """The GEMM pair + allreduce + trsm of upd_A (alg/QR/qr_2d/qr_2d.cxx:259-275), W_is_T case."""
+    check(lib().candmc_upd_A(_ptr(Y), lda_Y, _ptr(A), lda_A, mb, kb, b, _ptr(T), ccol.cm if ccol else None,
+                             _stream(stream)))

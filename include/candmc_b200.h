@@ -46,6 +46,13 @@ int candmc_finalize(void);
 int candmc_device_sm_count(int* out);
 /* Number of kernels this library has launched so far in this process (bench.py reports the delta). */
 unsigned long long candmc_launch_count(void);
+/* Test/measurement hook: 1 makes the GEMM walk its tiles round-robin instead of claiming them from an atomic counter. */
+int candmc_debug_static_schedule(int on);
+/* Measurement hook (bench.py's roofline leg): while enabled every TMA+DMMA GEMM launch is bracketed by CUDA events on
+ * its own stream; candmc_profile_gemm_stats synchronises and returns the number of launches, the sum of their device
+ * durations and of their algorithmic flops (2*m*n*k) since the last enable. */
+int candmc_profile_enable(int on);
+int candmc_profile_gemm_stats(int64_t* launches, double* total_ms, double* total_flops);
 /* Test hook: 1 routes candmc_dgemm through the generic CUDA-core kernel instead of the TMA+DMMA kernel. */
 int candmc_debug_force_generic_gemm(int on);
 
@@ -136,12 +143,16 @@ int candmc_bcast_cannon_4d(const candmc_ctb_args_t* args, const double* mat_A, c
 int candmc_spcannon(int bidir, int rank, int kary, int ndim, candmc_comm_t* world, int n, int m, int k,
                     char transp_A, double alpha, const double* A, char transp_B, double beta, const double* B,
                     double* C, void* stream);
-/* CAQR trailing update A <- A - Y * (T^-1 * (Y^T A)) on one grid column.  Replaces the GEMM pair + allreduce of
- * upd_A (alg/QR/qr_2d/qr_2d.cxx:259,265,271,275) for the W_is_T case: Tinv is the b x b lower-triangular factor the
- * reference applies with cdtrsm('L','L','N','N'); here the caller passes it already inverted (Tinv = T^-1, lower
- * triangular) and it is applied as a GEMM.  ccol may be NULL (single process column). */
+/* CAQR trailing update A <- A - Y * (T^-1 * (Y^T A)) on one grid column.  Replaces the W_is_T path of upd_A
+ * (alg/QR/qr_2d/qr_2d.cxx:224-282): cdgemm('T','N') :259, MPI_Allreduce over ccol :265, cdtrsm('L','L','N','N') with the
+ * b x b lower-triangular T (ld = b) :271, cdgemm('N','N', alpha=-1, beta=1) :275.  Y is mb x b, A is mb x kb (local
+ * extents), all device pointers.  ccol may be NULL (single process column). */
 int candmc_upd_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
-                 const double* Tinv, candmc_comm_t* ccol, void* stream);
+                 const double* T, candmc_comm_t* ccol, void* stream);
+/* Tuning: the SUMMA pipeline cuts each b-wide panel into up to 8 k-chunks of at least this many columns
+ * (default 1024) so the broadcast of chunk t+1 runs under the GEMM of chunk t.  Tests lower it to exercise the
+ * chunked path on small matrices. */
+int candmc_set_min_kchunk(int64_t min_kchunk);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,276 @@
+"""Multi-GPU parity worker (run under torchrun by tests/test_dist_gpu.py, one rank per GPU, NCCL).
+
+Every rank builds the reference's processor grid through candmc_b200.grid, fills its blocks with the reference
+generators, calls the CUDA path through the C ABI and compares with (a) the committed outputs of the unmodified
+reference (tests/golden/) and (b) the CPU oracle run for the whole simulated grid.  Tolerance: relative Frobenius
+<= 10*n*eps (BASELINE.json north_star).  Prints one JSON line on rank 0 and exits non-zero on any failure.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import candmc_b200 as cb  # noqa: E402
+from oracle import oracle_py as orc  # noqa: E402  (checker only)
+
+EPS = 2.220446049250313e-16
+RESULTS = []
+
+
+def rel_frob(x, ref):
+    x = np.asarray(x, dtype=np.float64).ravel(order="F")
+    ref = np.asarray(ref, dtype=np.float64).ravel(order="F")
+    return float(np.linalg.norm(x - ref) / max(np.linalg.norm(ref), 1e-300))
+
+
+def dev(a):
+    """numpy column-major matrix -> CUDA tensor whose storage is the same column-major bytes."""
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a).T)).cuda()
+
+
+def host(t, rows, cols):
+    return t.cpu().numpy().reshape(cols, -1).T[:rows]
+
+
+def record(name, err, tol):
+    ok = bool(err <= tol)
+    RESULTS.append((name, ok, err, tol))
+    return ok
+
+
+def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_golden=True):
+    g = cb.d25_grid(world, c)
+    q = g["q"]
+    b = n // q
+    row0, col0 = g["row"] * b, g["col"] * b
+    if q == 1 and c > 1:
+        row0 = col0 = 0
+    ld = b + lda_pad
+    A = np.zeros((ld, b), order="F"); B = np.zeros((ld, b), order="F")
+    A[:b] = orc.unit_block(b, b, row0, col0, n, 0)
+    B[:b] = orc.unit_block(b, b, row0, col0, n, 1)
+    args = cb.ctb_args_t(n=n, lda_A=ld, lda_B=ld, lda_C=b, buffer_size=5 * b * b * 8)
+    fn = cb.d25_summa_ovp if ovp else cb.d25_summa
+    if use_host:
+        Ch = np.full((b, b), np.nan, order="F")
+        fn(args, A, B, Ch, None, g["cdt_row"], g["cdt_col"], g["cdt_kdir"])
+        got = Ch
+    else:
+        dA, dB = dev(A), dev(B)
+        dC = torch.full((b * b,), float("nan"), dtype=torch.float64, device="cuda")
+        fn(args, dA, dB, dC, None, g["cdt_row"], g["cdt_col"], g["cdt_kdir"])
+        torch.cuda.synchronize()
+        got = host(dC, b, b)
+    # oracle for the whole grid
+    Ab, Bb = orc.d25_blocks(n, q, c) if not (q == 1 and c > 1) else (
+        [orc.unit_block(n, n, 0, 0, n, 0) for _ in range(c)], [orc.unit_block(n, n, 0, 0, n, 1) for _ in range(c)])
+    Cb = [np.zeros((b, b), order="F") for _ in Ab]
+    orc.d25_summa(n, q, c, ovp, Ab, Bb, Cb)
+    ok = record(f"{name}:oracle", rel_frob(got, Cb[world.rank]), 10 * n * EPS)
+    if check_golden and name in golden:
+        ok &= record(f"{name}:golden", rel_frob(got, golden[name][world.rank]), 10 * n * EPS)
+    for k in ("cdt_row", "cdt_col", "cdt_kdir"):
+        g[k].free()
+    return ok
+
+
+def case_summa(world, golden, name, n, lda_pad=0, trans=("N", "N")):
+    g = cb.d25_grid(world, 1)
+    q = g["q"]
+    b = n // q
+    ld = b + lda_pad
+    A = np.zeros((ld, b), order="F"); B = np.zeros((ld, b), order="F")
+    A[:b] = orc.unit_block(b, b, g["row"] * b, g["col"] * b, n, 0)
+    B[:b] = orc.unit_block(b, b, g["row"] * b, g["col"] * b, n, 1)
+    dA, dB = dev(A), dev(B)
+    ldc = b + lda_pad
+    dC = torch.full((ldc * b,), float("nan"), dtype=torch.float64, device="cuda")
+    args = cb.ctb_args_t(n=n, lda_A=ld, lda_B=ld, lda_C=ldc, buffer_size=4 * b * b * 8, trans_A=trans[0],
+                         trans_B=trans[1])
+    cb.summa(args, dA, dB, dC, None, g["cdt_row"], g["cdt_col"])
+    torch.cuda.synchronize()
+    got = host(dC, b, b)
+    Ab, Bb = orc.d25_blocks(n, q, 1)
+    Cb = [np.zeros((b, b), order="F") for _ in Ab]
+    orc.summa(n, q, Ab, Bb, Cb, trans_A=trans[0], trans_B=trans[1])
+    ok = record(f"{name}:oracle", rel_frob(got, Cb[world.rank]), 10 * n * EPS)
+    if name in golden and lda_pad == 0 and trans == ("N", "N"):
+        ok &= record(f"{name}:golden", rel_frob(got, golden[name][world.rank]), 10 * n * EPS)
+    g["cdt_row"].free(); g["cdt_col"].free(); g["cdt_kdir"].free()
+    return ok
+
+
+def case_dcn(world, golden, name, n, x2_np, ovp, lda_pad=0):
+    g = cb.dcn_grid(world, x2_np)
+    x1_np = g["x1_np"]
+    b = n // (x1_np * x2_np)
+    row0 = (g["y1"] * x2_np + g["y2"]) * b
+    col0 = (g["x1"] * x2_np + g["x2"]) * b
+    ld = b + lda_pad
+    A = np.zeros((ld, b), order="F"); B = np.zeros((ld, b), order="F")
+    A[:b] = orc.unit_block(b, b, row0, col0, n, 0)
+    B[:b] = orc.unit_block(b, b, row0, col0, n, 1)
+    dA, dB = dev(A), dev(B)
+    dC = torch.full((b * b,), float("nan"), dtype=torch.float64, device="cuda")
+    args = cb.ctb_args_t(n=n, lda_A=ld, lda_B=ld, lda_C=b, buffer_size=5 * b * b * 8, ovp=ovp)
+    cb.bcast_cannon_4d(args, dA, dB, dC, None, g["cdt_x1"], g["cdt_y1"], g["cdt_x2"], g["cdt_y2"])
+    torch.cuda.synchronize()
+    got = host(dC, b, b)
+    Ab, Bb = orc.dcn_blocks(n, x1_np, x2_np)
+    Cb = [np.zeros((b, b), order="F") for _ in Ab]
+    orc.bcast_cannon_4d(n, x1_np, x2_np, ovp, Ab, Bb, Cb)
+    ok = record(f"{name}:oracle", rel_frob(got, Cb[world.rank]), 10 * n * EPS)
+    if name in golden and lda_pad == 0:
+        ok &= record(f"{name}:golden", rel_frob(got, golden[name][world.rank]), 10 * n * EPS)
+    # the reference test's own criterion: serial product in the dcn_unit layout, |diff| <= 1e-6
+    full = orc.unit_block(n, n, 0, 0, n, 0) @ orc.unit_block(n, n, 0, 0, n, 1)
+    ok &= record(f"{name}:serial_abs", float(np.abs(got - full[row0:row0 + b, col0:col0 + b]).max()), 1e-6)
+    for k in ("cdt_x1", "cdt_y1", "cdt_x2", "cdt_y2"):
+        g[k].free()
+    return ok
+
+
+def case_spc(world, golden, name, bidir, kary, ndim, n, m, k, tB, use_host=False):
+    A, B, Cb, _ = orc.spc_blocks(kary, ndim, 3, n, m, k, tB)
+    r = world.rank
+    fn = cb.kput_cannon if bidir else cb.kuni_cannon
+    if use_host:
+        Ah, Bh, Ch = A[r].copy(order="F"), B[r].copy(order="F"), Cb[r].copy(order="F")
+        fn(r, kary, ndim, world, n, m, k, "N", 1.2, Ah, tB, 0.8, Bh, Ch)
+        got = Ch
+    else:
+        dA, dB, dC = dev(A[r]), dev(B[r]), dev(Cb[r])
+        fn(r, kary, ndim, world, n, m, k, "N", 1.2, dA, tB, 0.8, dB, dC)
+        torch.cuda.synchronize()
+        got = host(dC, m, n)
+    orc.spcannon(bidir, kary, ndim, n, m, k, "N", 1.2, A, tB, 0.8, B, Cb)
+    tol = 10 * k * kary ** (ndim // 2) * EPS
+    ok = record(f"{name}:oracle", rel_frob(got, Cb[r]), tol)
+    if name in golden:
+        ok &= record(f"{name}:golden", rel_frob(got, golden[name][r]), tol)
+    return ok
+
+
+def case_upd_A(world, name, mb, kb, b):
+    """One process column of world.np ranks; every rank owns mb rows of Y and A."""
+    rng = np.random.default_rng(5)
+    P = world.np
+    T = np.asfortranarray(np.eye(b) + 0.01 * np.tril(rng.random((b, b))))
+    Y = [np.asfortranarray(rng.random((mb, b))) for _ in range(P)]
+    A = [np.asfortranarray(rng.random((mb, kb))) for _ in range(P)]
+    dY, dA, dT = dev(Y[world.rank]), dev(A[world.rank]), dev(T)
+    cb.upd_A(dY, mb, dA, mb, mb, kb, b, dT, world)
+    torch.cuda.synchronize()
+    got = host(dA, mb, kb)
+    orc.upd_A([mb] * P, kb, b, Y, [mb] * P, A, [mb] * P, T)
+    return record(f"{name}:oracle", rel_frob(got, A[world.rank]), 10 * mb * P * EPS)
+
+
+def case_big_d25(world, n, c):
+    """Full-size property check: d25 result vs a direct GEMM of the gathered operands on every rank (cross-check only),
+    with inputs generated on the device by the same per-element generator."""
+    g = cb.d25_grid(world, c)
+    q, c = g["q"], g["c"]
+    b = n // q
+    row0, col0 = (0, 0) if (q == 1 and c > 1) else (g["row"] * b, g["col"] * b)
+    dA = torch.empty(b * b, dtype=torch.float64, device="cuda")
+    dB = torch.empty(b * b, dtype=torch.float64, device="cuda")
+    dC = torch.empty(b * b, dtype=torch.float64, device="cuda")
+    cb.fill_drand48(dA, b, b, b, row0, col0, n, 0)
+    cb.fill_drand48(dB, b, b, b, row0, col0, n, 1)
+    args = cb.ctb_args_t(n=n, lda_A=b, lda_B=b, lda_C=b, buffer_size=5 * b * b * 8)
+    cb.d25_summa(args, dA, dB, dC, None, g["cdt_row"], g["cdt_col"], g["cdt_kdir"])
+    torch.cuda.synchronize()
+    # reference block: rows [row0,row0+b) of A times cols [col0,col0+b) of B, regenerated locally
+    fa = torch.empty(b * n, dtype=torch.float64, device="cuda")   # b x n
+    fb = torch.empty(n * b, dtype=torch.float64, device="cuda")   # n x b
+    cb.fill_drand48(fa, b, n, b, row0, 0, n, 0)
+    cb.fill_drand48(fb, n, b, n, 0, col0, n, 1)
+    ref = torch.empty(b * b, dtype=torch.float64, device="cuda")
+    cb.cdgemm("N", "N", b, b, n, 1.0, fa, b, fb, n, 0.0, ref, b)
+    d2, r2 = cb.frob_diff(dC, b, ref, b, b, b)
+    ok = record(f"big_d25_n{n}_c{c}:local_gemm", float(np.sqrt(d2 / r2)), 10 * n * EPS)
+    # and against cuBLAS (torch.matmul) as an independent cross-check
+    Cx = (fb.view(b, n) @ fa.view(n, b)).reshape(-1)  # (A_rows B_cols)^T stored row-major == column-major product
+    d2, r2 = cb.frob_diff(dC, b, Cx, b, b, b)
+    ok &= record(f"big_d25_n{n}_c{c}:cublas", float(np.sqrt(d2 / r2)), 10 * n * EPS)
+    for k in ("cdt_row", "cdt_col", "cdt_kdir"):
+        g[k].free()
+    return ok
+
+
+def main():
+    rank = int(os.environ.get("RANK", 0))
+    world_size = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    world = cb.init_world(rank, world_size, local)
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "canmm_ref_outputs.npz"))
+    P = world_size
+    for min_kc in (1024, 8):   # default (whole panels at these sizes) and a tiny chunk to exercise the k-chunk pipeline
+        cb.set_min_kchunk(min_kc)
+        tag = f"kc{min_kc}"
+        if P == 1:
+            case_d25(world, golden, "d25_n40_q1_c1_ovp0", 40, 1, 0)
+            case_d25(world, golden, "d25_n40_q1_c1_ovp0", 40, 1, 1, use_host=True, check_golden=False)
+            case_spc(world, golden, f"spc_p1_{tag}", 1, 1, 2, 20, 24, 16, "N")
+        if P == 2:
+            case_d25(world, golden, f"d25_ksplit_n64_{tag}", 64, 2, 0)
+            case_d25(world, golden, f"d25_ksplit_n96_pad_{tag}", 96, 2, 1, lda_pad=2)
+            case_upd_A(world, f"upd_A_p2_{tag}", 64, 48, 16)
+        if P == 4:
+            case_d25(world, golden, "d25_n96_q2_c1_ovp0", 96, 1, 0)
+            case_d25(world, golden, "d25_n96_q2_c1_ovp1", 96, 1, 1)
+            case_d25(world, golden, "d25_n96_q2_c1_ovp0", 96, 1, 0, lda_pad=2, check_golden=True)
+            case_d25(world, golden, "d25_n96_q2_c1_ovp0", 96, 1, 0, use_host=True)
+            case_d25(world, golden, f"d25_n1024_{tag}", 1024, 1, 0)
+            case_summa(world, golden, "summa_n64_q2", 64)
+            case_summa(world, golden, "summa_n64_q2", 64, lda_pad=4)
+            case_summa(world, golden, f"summa_n96_TN_{tag}", 96, trans=("T", "N"))
+            case_summa(world, golden, f"summa_n96_NT_{tag}", 96, trans=("N", "T"))
+            case_dcn(world, golden, "dcn_n64_x2_1_ovp0", 64, 1, 0)
+            case_dcn(world, golden, "dcn_n64_x2_1_ovp1", 64, 1, 1)
+            case_dcn(world, golden, f"dcn_n64_x2_2_{tag}", 64, 2, 0)          # pure Cannon: the reference deadlocks here
+            case_dcn(world, golden, f"dcn_n96_x2_2_pad_{tag}", 96, 2, 1, lda_pad=2)
+            case_spc(world, golden, "spc_bidir1_p4_m24_k16_n20_N", 1, 2, 2, 20, 24, 16, "N")
+            case_spc(world, golden, "spc_bidir0_p4_m24_k16_n20_N", 0, 2, 2, 20, 24, 16, "N")
+            case_spc(world, golden, "spc_bidir1_p4_m24_k16_n20_T", 1, 2, 2, 20, 24, 16, "T")
+            case_spc(world, golden, "spc_bidir1_p4_m24_k16_n20_N", 1, 2, 2, 20, 24, 16, "N", use_host=True)
+            case_spc(world, golden, f"spc_p4_big_{tag}", 1, 2, 2, 256, 384, 128, "N")
+            case_upd_A(world, f"upd_A_p4_{tag}", 96, 80, 32)
+        if P == 8:
+            case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0)
+            case_d25(world, golden, "d25_n64_q2_c2_ovp1", 64, 2, 1)
+            case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0, lda_pad=2)
+            case_d25(world, golden, f"d25_n1024_c2_{tag}", 1024, 2, 0)
+    cb.set_min_kchunk(1024)
+    big = int(os.environ.get("CANDMC_TEST_BIG_N", "0"))
+    if big:
+        case_big_d25(world, big, None)
+
+    fails = [r for r in RESULTS if not r[1]]
+    flag = torch.tensor([len(fails)], dtype=torch.int64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(flag)
+    for name, ok, err, tol in fails:
+        print(f"[rank {rank}] FAIL {name}: err={err:.3e} tol={tol:.3e}", flush=True)
+    if rank == 0:
+        print(json.dumps({"world_size": world_size, "checks_rank0": len(RESULTS), "failed_all_ranks": int(flag.item()),
+                          "max_err_rank0": max((r[2] for r in RESULTS), default=0.0),
+                          "launches_rank0": cb.launch_count()}), flush=True)
+    world.free()
+    if world_size > 1:
+        dist.destroy_process_group()
+    sys.exit(1 if flag.item() else 0)
+
+
+if __name__ == "__main__":
+    main()

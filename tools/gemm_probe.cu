@@ -231,6 +231,20 @@ int main(int argc, char** argv) {
     pack_speed();
     return 0;
   }
+  if (!strcmp(mode, "sched")) {  // A/B: static round-robin vs dynamic (atomic counter) tile schedule
+    cublasHandle_t h;
+    cublasCreate(&h);
+    for (int rep = 0; rep < 2; ++rep)
+      for (int st = 1; st >= 0; --st) {
+        candmc_debug_static_schedule(st);
+        printf("{\"probe\":\"sched\",\"static\":%d}\n", st);
+        speed_one(h, 'N', 'N', 4096, 4096, 4096, 5);
+        speed_one(h, 'N', 'N', 8192, 8192, 8192, 5);
+      }
+    candmc_debug_static_schedule(0);
+    cublasDestroy(h);
+    return 0;
+  }
   if (!strcmp(mode, "speed")) {
     cublasHandle_t h;
     cublasCreate(&h);

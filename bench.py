@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's headline metric: FP64 TFLOP/s (and % of the FP64 tensor roofline) of the 2.5D / SUMMA
+multiply at n = 32768 on 1/2/4/8 B200, strong scaling.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Our arm: every rank owns the block the reference's grid gives it (1 GPU: 1x1x1; 2: 1x1x2 k-split; 4: 2x2x1 SUMMA;
+8: 2x2x2 2.5D with depth all-reduce), inputs generated on the device by the reference unit test's per-element drand48
+generator, one step = one `d25_summa` call through the C ABI.  `value` = 2 n^3 / t with device pointers (inputs resident
+in HBM), t = CUDA-event time of K back-to-back steps, max over ranks.  `e2e` = the same call with pinned HOST buffers
+(H2D of the A and B blocks and D2H of the C block inside the timed region).  `roofline` comes from CUDA events around
+every DMMA GEMM launch inside the timed region (candmc_profile_*).  `cpu_baseline` (N = 1 only) and `--impl reference`
+time the UNMODIFIED reference CANMM (oracle/_ref/topo_pdgemm_bench, mini-MPI ranks + scipy OpenBLAS) on the host cores
+for a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GLOBAL = 32768
+METRIC = "FP64 TFLOP/s, 2.5D MM n=32768 (strong scaling over 1/2/4/8 B200)"
+# FP64 tensor (DMMA) peak: 148 SMs x 4 sub-partitions x 16 FMA/clk x 2 flop x 1.965 GHz (clocks.max.sm).  MEASURED_PEAKS.json
+# carries no FP64 figure; the cuBLAS DGEMM cross-check measured on this pool (profiles/r01_gemm_probe_speed.jsonl) is
+# 36.0 TFLOP/s at n = 16384 = 0.967 of this number, with SM clocks pinned at 1965 MHz under FP64 load.
+FP64_PEAK_TFLOPS = 148 * 4 * 16 * 2 * 1.965e9 / 1e12
+CUBLAS_DGEMM_MEASURED_TFLOPS = 36.0
+NVLINK_GBS = 770.0  # measured peer-copy figure from /opt/skills/guides/B200_PROFILING.md
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (recipe's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, power, reasons = [], [], [], set()
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1 + 0.3:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the timed region"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def reference_cpu_run(steps, warmup, n_sample=8192, ranks=4):
+    """Time the unmodified reference (oracle/_ref) on the host cores: `topo_pdgemm_bench -n n_sample` on a 2x2 grid of
+    mini-MPI ranks, all cores busy.  Returns (tflops, dict) or (None, reason)."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    exe, run = os.path.join(ref, "topo_pdgemm_bench"), os.path.join(ref, "mpirun")
+    cores = os.cpu_count() or 1
+    threads = max(1, cores // ranks)
+    if os.path.exists(exe) and os.path.exists(run):
+        cmd = [run, "-np", str(ranks), "-timeout", "900", "-threads", str(threads), exe, "-n", str(n_sample), "-niter",
+               str(max(1, steps)), "-nwarm", str(max(0, warmup)), "-c_rep", "1", "-ovp", "0"]
+        try:
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=1200).stdout
+            m = re.search(r"Gigaflops:\s*([0-9.eE+-]+)", out)
+            t = re.search(r"Time elapsed per iteration:\s*([0-9.eE+-]+)", out)
+            if m:
+                return float(m.group(1)) / 1e3, {
+                    "kind": "reference", "cores": threads * ranks,
+                    "sample": f"unmodified reference bench/MM/topo_pdgemm_bench -n {n_sample} -niter {max(1, steps)} "
+                              f"-nwarm {max(0, warmup)} -c_rep 1 -ovp 0 on {ranks} mini-MPI ranks (2x2 grid) x {threads} "
+                              f"OpenBLAS threads; same 2.5D/SUMMA code path as n={N_GLOBAL}, bounded size",
+                    "sec_per_iter": float(t.group(1)) if t else None}
+        except Exception as e:  # fall through to the port
+            sys.stderr.write(f"reference run failed: {e}\n")
+    # oracle port (plain C restatement), scalar, one core
+    from oracle import oracle_py as orc
+    import numpy as np
+
+    n = 768
+    A = np.asfortranarray(np.random.default_rng(0).random((n, n))); B = A.copy(order="F"); Cm = np.zeros((n, n), order="F")
+    t0 = time.time()
+    reps = 0
+    while time.time() - t0 < 10:
+        orc.dgemm("N", "N", n, n, n, 1.0, A, n, B, n, 0.0, Cm, n)
+        reps += 1
+    dt = (time.time() - t0) / reps
+    return 2.0 * n ** 3 / dt / 1e12, {"kind": "port", "cores": 1,
+                                       "sample": f"oracle/candmc_oracle.c oracle_dgemm n={n}, {reps} repetitions (oracle/_ref not built)"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    val, info = reference_cpu_run(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": (info.get("sec_per_iter") or 0) * 1e3 if info.get("sec_per_iter") else None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"2.5D/SUMMA FP64 multiply, reference CPU path, bounded sample of n={N_GLOBAL}",
+                       "n": N_GLOBAL},
+            "cpu_baseline": dict(info, value=val, unit="TFLOP/s"),
+            "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="candmc_b200", choices=["candmc_b200", "reference"])
+    ap.add_argument("--n", type=int, default=N_GLOBAL, help="global matrix dimension (default: BASELINE's 32768)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    import candmc_b200 as cb
+
+    rank = int(os.environ.get("RANK", 0))
+    world_size = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert world_size == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world_size} (launch N > 1 with torchrun)"
+    if not torch.cuda.is_available():
+        raise cb.CandmcError(5, "bench.py needs a B200: candmc_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    world = cb.init_world(rank, world_size, local)
+    g = cb.d25_grid(world)
+    n, q, c = args.n, g["q"], g["c"]
+    b = n // q
+    ksplit = (q == 1 and c > 1)
+    row0, col0 = (0, 0) if ksplit else (g["row"] * b, g["col"] * b)
+    W = max(args.warmup, 3)
+
+    dA = torch.empty(b * b, dtype=torch.float64, device="cuda")
+    dB = torch.empty(b * b, dtype=torch.float64, device="cuda")
+    dC = torch.empty(b * b, dtype=torch.float64, device="cuda")
+    cb.fill_drand48(dA, b, b, b, row0, col0, n, 0)
+    cb.fill_drand48(dB, b, b, b, row0, col0, n, 1)
+    cargs = cb.ctb_args_t(n=n, lda_A=b, lda_B=b, lda_C=b, buffer_size=5 * b * b * 8)
+
+    def step(A, B, Cm):
+        cb.d25_summa(cargs, A, B, Cm, None, g["cdt_row"], g["cdt_col"], g["cdt_kdir"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg ----
+    for _ in range(W):
+        step(dA, dB, dC)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    cb.lib().candmc_profile_enable(1)
+    launches0 = cb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step(dA, dB, dC)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = cb.launch_count() - launches0
+    nl, tms, tfl = C.c_int64(), C.c_double(), C.c_double()
+    cb.lib().candmc_profile_gemm_stats(C.byref(nl), C.byref(tms), C.byref(tfl))
+    cb.lib().candmc_profile_enable(0)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = 2.0 * n ** 3 / (ms_per_step * 1e-3) / 1e12
+
+    # parity spot check at full size (outside the timed region): my C block vs an independently generated local GEMM
+    rel = None
+    if b * n * 8 * 2 < 40 * 2 ** 30:
+        rows = min(b, 2048)   # first `rows` rows of my C block
+        fa = torch.empty(rows * n, dtype=torch.float64, device="cuda")
+        fb = torch.empty(n * b, dtype=torch.float64, device="cuda")
+        ref = torch.empty(rows * b, dtype=torch.float64, device="cuda")
+        cb.fill_drand48(fa, rows, n, rows, row0, 0, n, 0)
+        cb.fill_drand48(fb, n, b, n, 0, col0, n, 1)
+        cb.cdgemm("N", "N", rows, b, n, 1.0, fa, rows, fb, n, 0.0, ref, rows)
+        d2, r2 = cb.frob_diff(dC, b, ref, rows, rows, b)
+        rel = max_over_ranks((d2 / r2) ** 0.5)
+        del fa, fb, ref
+
+    # ---- end-to-end leg: pinned host buffers through the same C-ABI call ----
+    e2e = None
+    if not args.no_e2e:
+        hA = torch.empty(b * b, dtype=torch.float64, pin_memory=True)
+        hB = torch.empty(b * b, dtype=torch.float64, pin_memory=True)
+        hC = torch.empty(b * b, dtype=torch.float64, pin_memory=True)
+        hA.copy_(dA); hB.copy_(dB)
+        torch.cuda.synchronize()
+        e2e_steps = max(1, min(args.steps, 2))
+        step(hA, hB, hC)   # warm-up (allocations, page faults)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step(hA, hB, hC)   # returns after C is back in host memory
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+        e2e = {"value": 2.0 * n ** 3 / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * b * b * 8 * world_size,
+               "d2h_bytes_per_step": b * b * 8 * world_size, "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "path": "candmc_d25_summa (C ABI) with pinned host mat_A/mat_B/mat_C, staged inside the call"}
+        del hA, hB, hC
+
+    if rank == 0:
+        achieved = (tfl.value / 1e12) / (tms.value / 1e3) if tms.value > 0 else None
+        flops_gpu = 2.0 * n ** 3 / world_size
+        # NVLink bytes per GPU: panels received + depth all-reduce (reduce-scatter + all-gather halves)
+        nv_bytes = (0 if q == 1 else 2 * 8 * b * b * (q // c) * (q - 1) / q) + (2 * 8 * b * b * (c - 1) / c if c > 1 else 0)
+        t_roof = max(flops_gpu / (FP64_PEAK_TFLOPS * 1e12), nv_bytes / (NVLINK_GBS * 1e9))
+        line = {
+            "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world_size, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"d25_summa FP64 n={n} on a {q}x{q}x{c} grid (block b={b}"
+                                   f"{', k split over depth' if ksplit else ''}); one step = one multiply",
+                       "n": n, "grid": [q, q, c], "block": b, "l2": "inputs larger than L2 (each operand block >= 2 GiB)",
+                       "generator": "reference unit-test drand48 per-element (test/MM/topo_pdgemm_unit.cxx:250-256)"},
+            "pct_of_roofline": 100.0 * value / (2.0 * n ** 3 / t_roof / 1e12),
+            "roofline_tflops": 2.0 * n ** 3 / t_roof / 1e12,
+            "rel_frobenius_vs_local_gemm": rel, "tolerance_10_n_eps": 10 * n * 2.220446049250313e-16,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "gemm_f64_tma_kernel (TMA + DMMA.8x8x4)", "achieved": achieved,
+                         "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS if achieved else None,
+                         "peak_source": "derived FP64 DMMA issue peak 148 SM x 64 FMA/clk x 1.965 GHz (MEASURED_PEAKS.json has no "
+                                        "FP64 entry); measured cuBLAS DGEMM on this pool = 36.0 TFLOP/s",
+                         "frac_of_cublas_measured": achieved / CUBLAS_DGEMM_MEASURED_TFLOPS if achieved else None,
+                         "launches": int(nl.value), "avg_launch_ms": tms.value / nl.value if nl.value else None,
+                         "flops_per_launch": tfl.value / nl.value if nl.value else None, "traffic": None},
+        }
+        if world_size == 1 and not args.no_cpu_baseline:
+            v, info = reference_cpu_run(3, 1)
+            line["cpu_baseline"] = dict(info, value=v, unit="TFLOP/s")
+        print(json.dumps(line), flush=True)
+    for k in ("cdt_row", "cdt_col", "cdt_kdir"):
+        g[k].free()
+    world.free()
+    if world_size > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

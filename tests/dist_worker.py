@@ -231,7 +231,7 @@ def main():
             case_d25(world, golden, "d25_n96_q2_c1_ovp1", 96, 1, 1)
             case_d25(world, golden, "d25_n96_q2_c1_ovp0", 96, 1, 0, lda_pad=2, check_golden=True)
             case_d25(world, golden, "d25_n96_q2_c1_ovp0", 96, 1, 0, use_host=True)
-            case_d25(world, golden, f"d25_n1024_{tag}", 1024, 1, 0)
+            case_d25(world, golden, f"d25_n512_{tag}", 512, 1, 0)
             case_summa(world, golden, "summa_n64_q2", 64)
             case_summa(world, golden, "summa_n64_q2", 64, lda_pad=4)
             case_summa(world, golden, f"summa_n96_TN_{tag}", 96, trans=("T", "N"))
@@ -250,7 +250,7 @@ def main():
             case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0)
             case_d25(world, golden, "d25_n64_q2_c2_ovp1", 64, 2, 1)
             case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0, lda_pad=2)
-            case_d25(world, golden, f"d25_n1024_c2_{tag}", 1024, 2, 0)
+            case_d25(world, golden, f"d25_n512_c2_{tag}", 512, 2, 0)
     cb.set_min_kchunk(1024)
     big = int(os.environ.get("CANDMC_TEST_BIG_N", "0"))
     if big:

@@ -29,6 +29,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_REAL_STDOUT = 1
 N_GLOBAL = 32768
 METRIC = "FP64 TFLOP/s, 2.5D MM n=32768 (strong scaling over 1/2/4/8 B200)"
 # FP64 tensor (DMMA) peak: 148 SMs x 4 sub-partitions x 16 FMA/clk x 2 flop x 1.965 GHz (clocks.max.sm).  MEASURED_PEAKS.json
@@ -142,11 +143,17 @@ def run_reference_arm(args):
                        "n": N_GLOBAL},
             "cpu_baseline": dict(info, value=val, unit="TFLOP/s"),
             "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else any library prints (NCCL banners,
+    torchrun notices) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -156,6 +163,8 @@ def main():
     ap.add_argument("--n", type=int, default=N_GLOBAL, help="global matrix dimension (default: BASELINE's 32768)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timeline", action="store_true", help="print rank 0's per-launch GEMM timeline to stderr")
+    ap.add_argument("--bg-ctas", type=int, default=None, help="CTA cap of the overlapped-traffic communicators")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -177,6 +186,8 @@ def main():
     if world_size > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     world = cb.init_world(rank, world_size, local)
+    if args.bg_ctas is not None:
+        cb.lib().candmc_set_background_ctas(args.bg_ctas)
     g = cb.d25_grid(world)
     n, q, c = args.n, g["q"], g["c"]
     b = n // q
@@ -229,6 +240,15 @@ def main():
     launches = cb.launch_count() - launches0
     nl, tms, tfl = C.c_int64(), C.c_double(), C.c_double()
     cb.lib().candmc_profile_gemm_stats(C.byref(nl), C.byref(tms), C.byref(tfl))
+    if args.timeline and rank == 0:
+        cap = 4096
+        ts, te, cnt = (C.c_double * cap)(), (C.c_double * cap)(), C.c_int64()
+        cb.lib().candmc_profile_gemm_timeline(ts, te, cap, C.byref(cnt))
+        per_step = max(1, cnt.value // max(1, args.steps))
+        sys.stderr.write("GEMM timeline, rank 0 (ms since first launch): idx start end dur gap_before\n")
+        for i in range(min(cnt.value, 2 * per_step)):
+            gap = ts[i] - te[i - 1] if i else 0.0
+            sys.stderr.write(f"  {i:3d} {ts[i]:9.3f} {te[i]:9.3f} {te[i] - ts[i]:8.3f} {gap:8.3f}\n")
     cb.lib().candmc_profile_enable(0)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     ms_per_step = ms_total / args.steps
@@ -299,7 +319,7 @@ def main():
         if world_size == 1 and not args.no_cpu_baseline:
             v, info = reference_cpu_run(3, 1)
             line["cpu_baseline"] = dict(info, value=v, unit="TFLOP/s")
-        print(json.dumps(line), flush=True)
+        emit(line)
     for k in ("cdt_row", "cdt_col", "cdt_kdir"):
         g[k].free()
     world.free()
@@ -309,4 +329,7 @@ def main():
 
 
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)   # anything a library prints to fd 1 goes to stderr; emit() writes the JSON line to the real stdout
     sys.exit(main())

@@ -39,6 +39,8 @@ SIGNATURES = {
     "candmc_debug_force_generic_gemm": (C.c_int, [C.c_int]),
     "candmc_debug_static_schedule": (C.c_int, [C.c_int]),
     "candmc_profile_enable": (C.c_int, [C.c_int]),
+    "candmc_profile_gemm_timeline": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), i64, C.POINTER(i64)]),
+    "candmc_set_background_ctas": (C.c_int, [C.c_int]),
     "candmc_profile_gemm_stats": (C.c_int, [C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "candmc_dgemm": (C.c_int, [C.c_char, C.c_char, i64, i64, i64, C.c_double, pd, i64, pd, i64, C.c_double, pd, i64,
                                C.c_void_p]),
@@ -64,6 +66,7 @@ SIGNATURES = {
                                   C.c_double, pd, C.c_char, C.c_double, pd, pd, C.c_void_p]),
     "candmc_upd_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, comm_p, C.c_void_p]),
     "candmc_set_min_kchunk": (C.c_int, [i64]),
+    "candmc_set_host_pipeline_min": (C.c_int, [i64]),
 }
 
 

@@ -48,6 +48,17 @@ int candmc_profile_gemm_stats(int64_t* launches, double* total_ms, double* total
   return profile_collect(launches, total_ms, total_flops);
 }
 
+int candmc_profile_gemm_timeline(double* start_ms, double* end_ms, int64_t cap, int64_t* n) {
+  CANDMC_CHECK(start_ms && end_ms && n, "candmc_profile_gemm_timeline: null output");
+  return profile_timeline(start_ms, end_ms, cap, n);
+}
+
+int candmc_set_background_ctas(int max_ctas) {
+  CANDMC_CHECK(max_ctas >= 0 && max_ctas <= 64, "candmc_set_background_ctas: 0..64");
+  runtime().bg_max_ctas = max_ctas;
+  return OK;
+}
+
 int candmc_dgemm(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                  int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, void* stream) {
   CANDMC_TRY(runtime_require());

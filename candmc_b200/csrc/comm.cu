@@ -13,7 +13,23 @@
 
 namespace candmc {
 
-int comm_bcast(candmc_comm* c, const double* send, double* recv, int64_t count, int root, cudaStream_t st) {
+int comm_background(candmc_comm* c, ncclComm_t* out) {
+  if (c->nccl_bg == nullptr) {
+    if (runtime().bg_max_ctas <= 0) {
+      c->nccl_bg = c->nccl;
+    } else {
+      ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+      cfg.minCTAs = 1;
+      cfg.maxCTAs = runtime().bg_max_ctas;
+      CANDMC_NCCL(ncclCommSplit(c->nccl, 0, c->rank, &c->nccl_bg, &cfg));
+    }
+  }
+  *out = c->nccl_bg;
+  return OK;
+}
+
+int comm_bcast(candmc_comm* c, const double* send, double* recv, int64_t count, int root, cudaStream_t st,
+               bool background) {
   CANDMC_CHECK(c != nullptr, "bcast: null communicator");
   CANDMC_CHECK(root >= 0 && root < c->size, "bcast: root %d outside communicator of size %d", root, c->size);
   if (count <= 0) return OK;
@@ -22,7 +38,9 @@ int comm_bcast(candmc_comm* c, const double* send, double* recv, int64_t count, 
       CANDMC_CUDA(cudaMemcpyAsync(recv, send, sizeof(double) * count, cudaMemcpyDeviceToDevice, st));
     return OK;
   }
-  CANDMC_NCCL(ncclBroadcast(send, recv, (size_t)count, ncclDouble, root, c->nccl, st));
+  ncclComm_t comm = c->nccl;
+  if (background) CANDMC_TRY(comm_background(c, &comm));
+  CANDMC_NCCL(ncclBroadcast(send, recv, (size_t)count, ncclDouble, root, comm, st));
   return OK;
 }
 
@@ -39,7 +57,7 @@ int comm_allreduce(candmc_comm* c, const double* send, double* recv, int64_t cou
 }
 
 int comm_sendrecv(candmc_comm* c, const double* send, int64_t scount, int dst, double* recv, int64_t rcount, int src,
-                  cudaStream_t st) {
+                  cudaStream_t st, bool background) {
   CANDMC_CHECK(c != nullptr, "sendrecv: null communicator");
   const bool do_send = dst >= 0 && scount > 0, do_recv = src >= 0 && rcount > 0;
   if (do_send && do_recv && dst == c->rank && src == c->rank) {
@@ -50,9 +68,11 @@ int comm_sendrecv(candmc_comm* c, const double* send, int64_t scount, int dst, d
   }
   CANDMC_CHECK(!(do_send && dst == c->rank) && !(do_recv && src == c->rank), "sendrecv: unmatched self transfer");
   if (!do_send && !do_recv) return OK;
+  ncclComm_t comm = c->nccl;
+  if (background) CANDMC_TRY(comm_background(c, &comm));
   CANDMC_NCCL(ncclGroupStart());
-  if (do_send) CANDMC_NCCL(ncclSend(send, (size_t)scount, ncclDouble, dst, c->nccl, st));
-  if (do_recv) CANDMC_NCCL(ncclRecv(recv, (size_t)rcount, ncclDouble, src, c->nccl, st));
+  if (do_send) CANDMC_NCCL(ncclSend(send, (size_t)scount, ncclDouble, dst, comm, st));
+  if (do_recv) CANDMC_NCCL(ncclRecv(recv, (size_t)rcount, ncclDouble, src, comm, st));
   CANDMC_NCCL(ncclGroupEnd());
   return OK;
 }
@@ -117,6 +137,7 @@ int candmc_comm_split(candmc_comm_t* parent, int color, int key, candmc_comm_t**
 
 int candmc_comm_free(candmc_comm_t* comm) {
   if (!comm) return OK;
+  if (comm->nccl_bg && comm->nccl_bg != comm->nccl) ncclCommDestroy(comm->nccl_bg);
   if (comm->nccl) ncclCommDestroy(comm->nccl);
   delete comm;
   return OK;

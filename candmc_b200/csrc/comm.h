@@ -9,7 +9,8 @@
 #include "common.cuh"
 
 struct candmc_comm {
-  ncclComm_t nccl = nullptr;
+  ncclComm_t nccl = nullptr;      // full-width communicator: exposed collectives (depth all-reduce, host bookkeeping)
+  ncclComm_t nccl_bg = nullptr;   // same ranks, few CTAs: panel traffic that runs UNDER a GEMM (created on first use)
   int rank = 0;
   int size = 1;
 };
@@ -25,12 +26,19 @@ namespace candmc {
     }                                                                                              \
   } while (0)
 
+// Communicator for traffic overlapped with compute: NCCL moves data with SM-resident kernels, and a persistent GEMM
+// that owns every SM loses ~10 % when a full-width NCCL kernel co-runs (measured, profiles/).  A second communicator
+// capped at `runtime().bg_max_ctas` CTAs keeps the links busy enough (panels are ~8x smaller than the GEMM they hide
+// under) while holding only a handful of SMs.  Collective over the communicator on first use.
+int comm_background(candmc_comm* c, ncclComm_t* out);
+
 // thin wrappers, device pointers only, size-1 communicators short-circuit (no NCCL call)
-int comm_bcast(candmc_comm* c, const double* send, double* recv, int64_t count, int root, cudaStream_t st);
+int comm_bcast(candmc_comm* c, const double* send, double* recv, int64_t count, int root, cudaStream_t st,
+               bool background = false);
 int comm_allreduce(candmc_comm* c, const double* send, double* recv, int64_t count, cudaStream_t st);
 // grouped point-to-point exchange: send `scount` doubles to `dst`, receive `rcount` from `src` (either may be
 // skipped with a negative peer); self-exchange degenerates to a device copy.
 int comm_sendrecv(candmc_comm* c, const double* send, int64_t scount, int dst, double* recv, int64_t rcount, int src,
-                  cudaStream_t st);
+                  cudaStream_t st, bool background = false);
 
 }  // namespace candmc

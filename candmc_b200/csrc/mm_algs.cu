@@ -116,9 +116,9 @@ int summa_sweep(const SummaArgs& a) {
               CANDMC_TRY(lda_copy_f64(b, kc, a.ldA, b, src, packA + t * kc * b, comm));
               src = packA + t * kc * b;
             }
-            CANDMC_TRY(comm_bcast(a.row, src, const_cast<double*>(src), kc * b, i, comm));
+            CANDMC_TRY(comm_bcast(a.row, src, const_cast<double*>(src), kc * b, i, comm, true));
           } else {
-            CANDMC_TRY(comm_bcast(a.row, slot, slot, kc * b, i, comm));
+            CANDMC_TRY(comm_bcast(a.row, slot, slot, kc * b, i, comm, true));
           }
         }
         if (a.col->size > 1) {
@@ -129,9 +129,9 @@ int summa_sweep(const SummaArgs& a) {
               CANDMC_TRY(lda_copy_f64(kc, b, a.ldB, kc, src, locB + t * kc * b, comm));  // chunk-major, ld = kc
               src = locB + t * kc * b;
             }
-            CANDMC_TRY(comm_bcast(a.col, src, const_cast<double*>(src), kc * b, i, comm));
+            CANDMC_TRY(comm_bcast(a.col, src, const_cast<double*>(src), kc * b, i, comm, true));
           } else {
-            CANDMC_TRY(comm_bcast(a.col, slot, slot, kc * b, i, comm));
+            CANDMC_TRY(comm_bcast(a.col, slot, slot, kc * b, i, comm, true));
           }
         }
         ready[t] = g_events.get();
@@ -168,6 +168,67 @@ int summa_sweep(const SummaArgs& a) {
       }
     }
   }
+  return OK;
+}
+
+// ---- host-resident operands on a 1x1 grid: stream the multiply through PCIe -----------------------------------------
+// C(m x n) = A(m x k) * B(k x n) with A, B, C in HOST memory (what the reference's callers own).  Instead of
+// "copy everything in, multiply, copy everything out" the product is cut into column panels of C: panel j+1's slice of B
+// is uploaded and panel j-1's slice of C is downloaded while panel j multiplies; the first panel is additionally cut
+// along k so that its GEMMs start as soon as the first column slab of A has landed.  Only the first A slab and the last
+// C panel are exposed.  Three streams: H2D (aux), compute (caller's), D2H (comm — idle on a 1x1 grid).
+int host_pipelined_gemm_nn(int64_t m, int64_t n, int64_t k, const double* hA, int64_t lda, const double* hB, int64_t ldb,
+                           double* hC, int64_t ldc, cudaStream_t st) {
+  const int NP = 8;
+  const int64_t nb = ((n + NP - 1) / NP + 127) / 128 * 128;   // panel width (multiple of the CTA tile)
+  const int64_t kc = ((k + NP - 1) / NP + 15) / 16 * 16;      // k-chunk of the first panel
+  const int npanels = (int)((n + nb - 1) / nb), nchunks = (int)((k + kc - 1) / kc);
+  cudaStream_t h2d = runtime().aux_stream, d2h = runtime().comm_stream;
+  void* wsv = nullptr;
+  CANDMC_TRY(workspace_get(sizeof(double) * (m * k + 2 * k * nb + 2 * m * nb + 8), &wsv));
+  double* dA = static_cast<double*>(wsv);
+  double* dB[2] = {dA + m * k + (m * k & 1), nullptr};
+  dB[1] = dB[0] + k * nb;
+  double* dC[2] = {dB[1] + k * nb, nullptr};
+  dC[1] = dC[0] + m * nb;
+  CANDMC_TRY(stream_wait(h2d, st));
+  CANDMC_TRY(stream_wait(d2h, st));
+  std::vector<cudaEvent_t> g_done(npanels, nullptr), c_free(npanels, nullptr);
+  auto ev = [&](cudaEvent_t* e, cudaStream_t s) -> int {
+    *e = g_events.get();
+    CANDMC_CHECK(*e != nullptr, "event pool exhausted");
+    CANDMC_CUDA(cudaEventRecord(*e, s));
+    return OK;
+  };
+  for (int j = 0; j < npanels; ++j) {
+    const int slot = j & 1;
+    const int64_t c0 = j * nb, nbj = std::min(nb, n - c0);
+    if (j == 0) {
+      for (int t = 0; t < nchunks; ++t) {
+        const int64_t k0 = t * kc, kct = std::min(kc, k - k0);
+        CANDMC_CUDA(cudaMemcpy2DAsync(dA + k0 * m, m * 8, hA + k0 * lda, lda * 8, m * 8, kct, cudaMemcpyHostToDevice, h2d));
+        CANDMC_CUDA(cudaMemcpy2DAsync(dB[0] + k0, k * 8, hB + k0, ldb * 8, kct * 8, nbj, cudaMemcpyHostToDevice, h2d));
+        cudaEvent_t ready;
+        CANDMC_TRY(ev(&ready, h2d));
+        CANDMC_CUDA(cudaStreamWaitEvent(st, ready, 0));
+        CANDMC_TRY(gemm_f64('N', 'N', m, nbj, kct, 1.0, dA + k0 * m, m, dB[0] + k0, k, t ? 1.0 : 0.0, dC[0], m, st));
+      }
+    } else {
+      if (j >= 2) CANDMC_CUDA(cudaStreamWaitEvent(h2d, g_done[j - 2], 0));  // dB[slot] no longer read
+      CANDMC_CUDA(cudaMemcpy2DAsync(dB[slot], k * 8, hB + c0 * ldb, ldb * 8, k * 8, nbj, cudaMemcpyHostToDevice, h2d));
+      cudaEvent_t ready;
+      CANDMC_TRY(ev(&ready, h2d));
+      CANDMC_CUDA(cudaStreamWaitEvent(st, ready, 0));
+      if (j >= 2) CANDMC_CUDA(cudaStreamWaitEvent(st, c_free[j - 2], 0));   // dC[slot] has been downloaded
+      CANDMC_TRY(gemm_f64('N', 'N', m, nbj, k, 1.0, dA, m, dB[slot], k, 0.0, dC[slot], m, st));
+    }
+    CANDMC_TRY(ev(&g_done[j], st));
+    CANDMC_CUDA(cudaStreamWaitEvent(d2h, g_done[j], 0));
+    CANDMC_CUDA(cudaMemcpy2DAsync(hC + c0 * ldc, ldc * 8, dC[slot], m * 8, m * 8, nbj, cudaMemcpyDeviceToHost, d2h));
+    CANDMC_TRY(ev(&c_free[j], d2h));
+  }
+  CANDMC_TRY(stream_wait(st, d2h));
+  CANDMC_CUDA(cudaStreamSynchronize(st));
   return OK;
 }
 
@@ -241,6 +302,12 @@ using namespace candmc;
 
 extern "C" {
 
+int candmc_set_host_pipeline_min(int64_t min_n) {
+  CANDMC_CHECK(min_n >= 1, "candmc_set_host_pipeline_min: must be >= 1");
+  runtime().host_pipeline_min = min_n;
+  return OK;
+}
+
 int candmc_set_min_kchunk(int64_t min_kchunk) {
   CANDMC_CHECK(min_kchunk >= 2, "candmc_set_min_kchunk: must be >= 2");
   runtime().min_kchunk = min_kchunk;
@@ -295,6 +362,9 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   CANDMC_CHECK(buffer == nullptr || args->buffer_size >= need, "d25_summa: buffer_size %lld < %lld",
                (long long)args->buffer_size, (long long)need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (q == 1 && c == 1 && b >= runtime().host_pipeline_min && is_n(args->trans_A) && is_n(args->trans_B) && !is_device_ptr(mat_A) &&
+      !is_device_ptr(mat_B) && !is_device_ptr(mat_C))
+    return host_pipelined_gemm_nn(b, b, b, mat_A, args->lda_A, mat_B, args->lda_B, mat_C, args->lda_C, st);
   StagedMatrix sA, sB, sC;
   CANDMC_TRY(sA.open(mat_A, b, b, args->lda_A, true, st));
   CANDMC_TRY(sB.open(mat_B, b, b, args->lda_B, true, st));
@@ -404,8 +474,8 @@ int candmc_bcast_cannon_4d(const candmc_ctb_args_t* args, const double* mat_A, c
       // shift by -1 (dual_cannon.cxx:196-213) into the alternate buffers WHILE this step multiplies.  The wait makes
       // sure the previous step's multiplies (the last readers of the alternate buffers) are finished.
       CANDMC_TRY(stream_wait(shift, st));
-      CANDMC_TRY(comm_sendrecv(cdt_x2, curA, bb, wrap(x2 - 1, x2_np), pingA[nextA], bb, wrap(x2 + 1, x2_np), shift));
-      CANDMC_TRY(comm_sendrecv(cdt_y2, curB, bb, wrap(y2 - 1, x2_np), pingB[nextB], bb, wrap(y2 + 1, x2_np), shift));
+      CANDMC_TRY(comm_sendrecv(cdt_x2, curA, bb, wrap(x2 - 1, x2_np), pingA[nextA], bb, wrap(x2 + 1, x2_np), shift, true));
+      CANDMC_TRY(comm_sendrecv(cdt_y2, curB, bb, wrap(y2 - 1, x2_np), pingB[nextB], bb, wrap(y2 + 1, x2_np), shift, true));
       nxtA = pingA[nextA]; nextA ^= 1;
       nxtB = pingB[nextB]; nextB ^= 1;
       shift_done = g_events.get();
@@ -466,7 +536,7 @@ struct Xfer {
   int dst, src;
 };
 
-int spc_exchange(Spc& s, const std::vector<Xfer>& xs) {
+int spc_exchange(Spc& s, const std::vector<Xfer>& xs, bool background) {
   const int p = s.cur;
   // destination pair 1-p must no longer be read by a GEMM; the source pair p must have been produced
   if (s.last_reader[1 - p]) CANDMC_CUDA(cudaStreamWaitEvent(s.comm, s.last_reader[1 - p], 0));
@@ -480,11 +550,13 @@ int spc_exchange(Spc& s, const std::vector<Xfer>& xs) {
     }
   }
   if (any_remote) {
+    ncclComm_t comm = s.world->nccl;
+    if (background) CANDMC_TRY(comm_background(s.world, &comm));  // shifts run under the GEMM; the stagger does not
     CANDMC_NCCL(ncclGroupStart());
     for (const Xfer& x : xs) {
       if (x.dst == s.rank) continue;
-      CANDMC_NCCL(ncclSend(x.send, (size_t)x.count, ncclDouble, x.dst, s.world->nccl, s.comm));
-      CANDMC_NCCL(ncclRecv(x.recv, (size_t)x.count, ncclDouble, x.src, s.world->nccl, s.comm));
+      CANDMC_NCCL(ncclSend(x.send, (size_t)x.count, ncclDouble, x.dst, comm, s.comm));
+      CANDMC_NCCL(ncclRecv(x.recv, (size_t)x.count, ncclDouble, x.src, comm, s.comm));
     }
     CANDMC_NCCL(ncclGroupEnd());
   }
@@ -509,7 +581,7 @@ int spc_stagger(Spc& s, int level) {  // uni_stagger, spcannon.cxx:33-84
     xs.push_back({s.B[p] + i * bB, s.B[1 - p] + i * bB, bB, s.rank + (wrapi(tB - tA, s.kary) - tB) * sB,
                   s.rank + (wrapi(tB + tA, s.kary) - tB) * sB});
   }
-  CANDMC_TRY(spc_exchange(s, xs));
+  CANDMC_TRY(spc_exchange(s, xs, false));
   if (level < s.half - 1) return spc_stagger(s, level + 1);
   return OK;
 }
@@ -550,7 +622,7 @@ int spc_shift(Spc& s, int bidir, int level, double beta) {  // bdr_shift :87-162
         xs.push_back({s.B[p] + i * bB, s.B[1 - p] + i * bB, bB, upB, dnB});
       }
     }
-    CANDMC_TRY(spc_exchange(s, xs));
+    CANDMC_TRY(spc_exchange(s, xs, true));
   }
   return OK;
 }

@@ -149,6 +149,22 @@ int profile_collect(int64_t* launches, double* total_ms, double* total_flops) {
   return OK;
 }
 
+int profile_timeline(double* start_ms, double* end_ms, int64_t cap, int64_t* n) {
+  CANDMC_CUDA(cudaDeviceSynchronize());
+  int64_t cnt = 0;
+  for (ProfRec& r : g_prof) {
+    if (cnt >= cap) break;
+    float a = 0, b = 0;
+    CANDMC_CUDA(cudaEventElapsedTime(&a, g_prof.front().e0, r.e0));
+    CANDMC_CUDA(cudaEventElapsedTime(&b, g_prof.front().e0, r.e1));
+    start_ms[cnt] = a;
+    end_ms[cnt] = b;
+    ++cnt;
+  }
+  *n = cnt;
+  return OK;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

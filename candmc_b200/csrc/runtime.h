@@ -23,6 +23,8 @@ struct Runtime {
   unsigned tile_counter_seq = 0;
   bool static_schedule = false;         // debug: round-robin tile schedule instead of the atomic counter
   bool profile = false;                 // bracket every DMMA GEMM launch with events (bench.py's roofline leg)
+  int bg_max_ctas = 4;                  // CTA cap of the communicators used for traffic overlapped with GEMMs (0 = no cap)
+  int64_t host_pipeline_min = 2048;     // smallest n for which host operands on a 1x1 grid are streamed panel-wise
   int64_t min_kchunk = 1024;            // smallest k-chunk the SUMMA pipeline cuts a panel into
 };
 
@@ -41,6 +43,7 @@ int profile_begin_launch(cudaStream_t stream, double flops);
 int profile_end_launch(cudaStream_t stream);
 int profile_reset();
 int profile_collect(int64_t* launches, double* total_ms, double* total_flops);
+int profile_timeline(double* start_ms, double* end_ms, int64_t cap, int64_t* n);
 
 // Hands out a zeroed device counter (memset is enqueued on `stream`) for one GEMM launch.
 int next_tile_counter(int** out, cudaStream_t stream);

@@ -53,6 +53,11 @@ int candmc_debug_static_schedule(int on);
  * durations and of their algorithmic flops (2*m*n*k) since the last enable. */
 int candmc_profile_enable(int on);
 int candmc_profile_gemm_stats(int64_t* launches, double* total_ms, double* total_flops);
+/* Start / end (ms, relative to the first profiled launch) of up to `cap` profiled GEMM launches; *n = how many. */
+int candmc_profile_gemm_timeline(double* start_ms, double* end_ms, int64_t cap, int64_t* n);
+/* Tuning: CTA cap of the second NCCL communicator each grid axis uses for panel traffic that runs under a GEMM
+ * (default 4; 0 = use the full-width communicator).  Must be set before the first multiply on a communicator. */
+int candmc_set_background_ctas(int max_ctas);
 /* Test hook: 1 routes candmc_dgemm through the generic CUDA-core kernel instead of the TMA+DMMA kernel. */
 int candmc_debug_force_generic_gemm(int on);
 
@@ -153,6 +158,9 @@ int candmc_upd_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64
  * (default 1024) so the broadcast of chunk t+1 runs under the GEMM of chunk t.  Tests lower it to exercise the
  * chunked path on small matrices. */
 int candmc_set_min_kchunk(int64_t min_kchunk);
+/* Tuning: on a 1x1x1 grid with HOST operands and n >= this (default 2048) the multiply is streamed through PCIe in
+ * column panels (upload of panel j+1 and download of panel j-1 under the GEMM of panel j) instead of staged whole. */
+int candmc_set_host_pipeline_min(int64_t min_n);
 
 #ifdef __cplusplus
 }

@@ -222,6 +222,10 @@ def main():
             case_d25(world, golden, "d25_n40_q1_c1_ovp0", 40, 1, 0)
             case_d25(world, golden, "d25_n40_q1_c1_ovp0", 40, 1, 1, use_host=True, check_golden=False)
             case_spc(world, golden, f"spc_p1_{tag}", 1, 1, 2, 20, 24, 16, "N")
+            cb.lib().candmc_set_host_pipeline_min(64)   # stream host operands panel-wise even at this size
+            case_d25(world, golden, f"d25_hostpipe_n320_{tag}", 320, 1, 0, use_host=True, check_golden=False)
+            case_d25(world, golden, f"d25_hostpipe_n200_pad_{tag}", 200, 1, 0, lda_pad=3, use_host=True, check_golden=False)
+            cb.lib().candmc_set_host_pipeline_min(2048)
         if P == 2:
             case_d25(world, golden, f"d25_ksplit_n64_{tag}", 64, 2, 0)
             case_d25(world, golden, f"d25_ksplit_n96_pad_{tag}", 96, 2, 1, lda_pad=2)

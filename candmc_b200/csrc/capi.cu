@@ -33,6 +33,11 @@ int candmc_debug_force_generic_gemm(int on) {
   return OK;
 }
 
+int candmc_debug_splitk(int on) {
+  runtime().splitk = (on != 0);
+  return OK;
+}
+
 int candmc_debug_static_schedule(int on) {
   runtime().static_schedule = (on != 0);
   return OK;

@@ -18,6 +18,8 @@
 //     {0,1,4,5,2,3,6,7}; the 4 DMMA k-steps of a 16-wide k tile use k = 8*(s>>1) + 2j + ((j&1)^(s&1)).
 //     Sums over k and the set of output elements are unchanged — only which lane/step touches which element.
 //   * Tiles are rasterised in groups of 8 tile-rows so a wave of 148 CTAs re-uses A/B panels out of the 126 MB L2.
+//   * Small tile counts (< 3 waves) are cut along k as well (split-K): the partial tiles are parked in an L2-resident
+//     scratch and the last unit of a tile to arrive sums them in a fixed order, so the result is deterministic.
 //   * Out-of-range rows/cols/k are zero-filled by TMA (exact), stores are predicated: any m,n,k >= 0 works on the
 //     TMA path as long as the base pointers are 16 B aligned and lda/ldb are even.  Otherwise a plain tiled
 //     CUDA-core kernel (`gemm_f64_generic`) is used — still on the GPU; there is no CPU path.
@@ -40,6 +42,7 @@ constexpr int PRODUCER_REGS = 40;                     // 4 warps x 40 + 8 warps 
 constexpr int CONSUMER_REGS = 232;
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers + tile ids*/;
 constexpr int RASTER_GROUP = 8;
+constexpr int kSplitSemCount = 4096;  // tiles a split-K launch may have (it is only used for small tile counts)
 
 // index-slot permutation shared by A rows and B cols (see header comment)
 __device__ __forceinline__ int cf_map(int g) { return ((g & 1) | ((g & 2) << 1) | ((g & 4) >> 1)); }
@@ -87,7 +90,8 @@ template <bool A_KMAJ, bool B_KMAJ>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     double* __restrict__ C, int64_t ldc, int M, int N, int K, double alpha, double beta,
-                    int tilesM, int tilesN, int* __restrict__ tile_counter) {
+                    int tilesM, int tilesN, int* __restrict__ tile_counter, int ksplit, double* __restrict__ part,
+                    int* __restrict__ tile_sem) {
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment for the 128 B swizzle atom; pointer arithmetic keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -100,7 +104,9 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int KT = (K + BK - 1) / BK;
-  const int ntiles = tilesM * tilesN;
+  // split-K: work unit u = tile * ksplit + s covers k-tiles [s*KTS, min(KT, (s+1)*KTS)); ksplit == 1 is the plain GEMM
+  const int KTS = (KT + ksplit - 1) / ksplit;
+  const int ntiles = tilesM * tilesN * ksplit;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -128,11 +134,12 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_arrive(&full_bar[stage]);
           break;
         }
-        const TileCoord tc = tile_coord(t, tilesM, tilesN);
+        const TileCoord tc = tile_coord(t / ksplit, tilesM, tilesN);
         const int m0 = tc.tm * BM, n0 = tc.tn * BN;
-        for (int kt = 0; kt < KT; ++kt) {
+        const int kt0 = (t % ksplit) * KTS, kt1 = min(KT, kt0 + KTS);
+        for (int kt = kt0; kt < kt1; ++kt) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (kt == 0) stage_tile[stage] = t;
+          if (kt == kt0) stage_tile[stage] = t;
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + OPER_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -205,13 +212,15 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     mbar_wait(&full_bar[stage], phase);
     const int t = stage_tile[stage];
     if (t < 0) break;
-    const TileCoord tc = tile_coord(t, tilesM, tilesN);
+    const int tile = t / ksplit, ks = t - tile * ksplit;
+    const TileCoord tc = tile_coord(tile, tilesM, tilesN);
+    const int nkt = min(KT, (ks + 1) * KTS) - ks * KTS;
 #pragma unroll
     for (int f = 0; f < 8; ++f)
 #pragma unroll
       for (int h = 0; h < 4; ++h) acc[f][h][0] = acc[f][h][1] = 0.0;
     load_frags(0, stage * STAGE_BYTES, 0);
-    for (int kt = 0; kt < KT; ++kt) {
+    for (int kt = 0; kt < nkt; ++kt) {
       const uint32_t st = stage * STAGE_BYTES;
       load_frags(1, st, 1);
       mma_step(0);
@@ -227,7 +236,7 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         nstage = 0;
         nphase ^= 1;
       }
-      if (kt + 1 < KT) {
+      if (kt + 1 < nkt) {
         mbar_wait(&full_bar[nstage], nphase);
         load_frags(0, nstage * STAGE_BYTES, 0);
       }
@@ -238,11 +247,63 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       phase = nphase;
     }
 
+    if (ksplit > 1) {
+      // ---- split-K: park the partial tile (thread-major, fully coalesced), the last of the `ksplit` units of this tile
+      // to arrive sums all partials in the fixed order s = 0..ksplit-1 (deterministic) and runs the epilogue ----
+      double* mine = part + (static_cast<int64_t>(tile) * ksplit + ks) * (BM * BN) + threadIdx.x;
+#pragma unroll
+      for (int f = 0; f < 8; ++f)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          __stcg(mine + (f * 8 + h * 2 + 0) * 256, acc[f][h][0]);
+          __stcg(mine + (f * 8 + h * 2 + 1) * 256, acc[f][h][1]);
+        }
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      __shared__ int s_last;
+      if (threadIdx.x == 0) {
+        const int old = atomicAdd(&tile_sem[tile], 1);
+        s_last = (old == ksplit - 1);
+        if (s_last) tile_sem[tile] = 0;  // ready for the next launch
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (!s_last) continue;
+      __threadfence();
+      const double* all = part + static_cast<int64_t>(tile) * ksplit * (BM * BN) + threadIdx.x;
+#pragma unroll
+      for (int f = 0; f < 8; ++f)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          double s0 = 0.0, s1 = 0.0;
+          for (int q2 = 0; q2 < ksplit; ++q2) {
+            s0 += __ldcg(all + static_cast<int64_t>(q2) * (BM * BN) + (f * 8 + h * 2 + 0) * 256);
+            s1 += __ldcg(all + static_cast<int64_t>(q2) * (BM * BN) + (f * 8 + h * 2 + 1) * 256);
+          }
+          acc[f][h][0] = s0;
+          acc[f][h][1] = s1;
+        }
+    }
     // ---- epilogue: registers -> global, predicated, alpha/beta (beta==0 never reads C) ----
+    // beta != 0: the 16 C values of one 8-column group are fetched together (L2 path, 16 loads in flight per lane — the
+    // fragment registers are dead here) before they are combined; a load-use-store chain per element would leave the
+    // DMMA pipe idle for tens of microseconds per tile.
     const int row_base = tc.tm * BM + wm * 64 + cf;
     const int col_base = tc.tn * BN + wn * 32 + cf_map(2 * j);  // slots 2j, 2j+1 -> adjacent columns
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
+      double cv[2][8];
+      if (beta != 0.0) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = col_base + h * 8 + c;
+          const double* cp = C + static_cast<int64_t>(col) * ldc;
+#pragma unroll
+          for (int f = 0; f < 8; ++f) {
+            const int row = row_base + f * 8;
+            cv[c][f] = (col < N && row < M) ? __ldcg(cp + row) : 0.0;
+          }
+        }
+      }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int col = col_base + h * 8 + c;
@@ -253,7 +314,7 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int row = row_base + f * 8;
             if (row < M) {
               double v = alpha * acc[f][h][c];
-              if (beta != 0.0) v += beta * cp[row];
+              if (beta != 0.0) v += beta * cv[c][f];
               cp[row] = v;
             }
           }
@@ -350,12 +411,36 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_
     configured = true;
   }
   const int tilesM = (M + BM - 1) / BM, tilesN = (N + BN - 1) / BN;
-  const int64_t ntiles = static_cast<int64_t>(tilesM) * tilesN;
-  const int grid = static_cast<int>(ntiles < runtime().num_sms ? ntiles : runtime().num_sms);
+  const int64_t tiles = static_cast<int64_t>(tilesM) * tilesN;
+  // split-K when the tiles alone cannot fill a few waves: pick the split that wastes the least of the last wave
+  int ksplit = 1;
+  const int sms = runtime().num_sms;
+  const int KT = (K + BK - 1) / BK;
+  if (runtime().splitk && tiles < 3 * sms && tiles <= kSplitSemCount) {
+    double best = static_cast<double>(tiles) / (static_cast<double>(sms) * ((tiles + sms - 1) / sms));
+    for (int sp = 2; sp <= 16; ++sp) {
+      if (KT / sp < 16) break;  // keep >= 256 k per unit so the partial-tile traffic stays small
+      const int64_t u = tiles * sp;
+      const double eff = static_cast<double>(u) / (static_cast<double>(sms) * ((u + sms - 1) / sms));
+      if (eff > best + 0.02) {
+        best = eff;
+        ksplit = sp;
+      }
+    }
+    if ((KT + ksplit - 1) / ksplit * (ksplit - 1) >= KT) ksplit = 1;  // would leave an empty unit
+  }
+  double* part = nullptr;
+  int* sem = nullptr;
+  if (ksplit > 1) CANDMC_TRY(splitk_buffers(tiles * ksplit * BM * BN, &part, &sem));
+  const int64_t ntiles = tiles * ksplit;
+  // leave `gemm_reserve_sms` SMs free when a schedule wants NCCL kernels to run beside this persistent kernel
+  const int avail = sms - runtime().gemm_reserve_sms > 0 ? sms - runtime().gemm_reserve_sms : 1;
+  const int grid = static_cast<int>(ntiles < avail ? ntiles : avail);
   int* counter = nullptr;
   if (!runtime().static_schedule) CANDMC_TRY(next_tile_counter(&counter, stream));
   if (runtime().profile) CANDMC_TRY(profile_begin_launch(stream, 2.0 * M * (double)N * (double)K));
-  kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmB, C, ldc, M, N, K, alpha, beta, tilesM, tilesN, counter);
+  kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmB, C, ldc, M, N, K, alpha, beta, tilesM, tilesN, counter, ksplit,
+                                               part, sem);
   CANDMC_CUDA(cudaGetLastError());
   if (runtime().profile) CANDMC_TRY(profile_end_launch(stream));
   runtime().launches++;

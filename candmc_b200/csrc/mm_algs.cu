@@ -99,6 +99,14 @@ int summa_sweep(const SummaArgs& a) {
   const int64_t kc = b / nchunks;
 
   if (need_comm) CANDMC_TRY(stream_wait(comm, a.compute));  // inputs (and earlier users of ws) are ready
+  // NCCL moves data with SM-resident kernels, and the persistent GEMM owns every SM it is given (all registers, 193 KiB
+  // smem), so a broadcast enqueued while a GEMM runs would only start when that GEMM ends.  While panels are in flight
+  // the GEMMs therefore leave as many SMs free as the background communicators may use.
+  struct ReserveGuard {
+    int saved;
+    explicit ReserveGuard(int r) : saved(runtime().gemm_reserve_sms) { runtime().gemm_reserve_sms = r; }
+    ~ReserveGuard() { runtime().gemm_reserve_sms = saved; }
+  } reserve_guard(need_comm ? runtime().bg_max_ctas : runtime().gemm_reserve_sms);
   std::vector<cudaEvent_t> done_prev(nchunks, nullptr);
   bool first = a.first_beta_zero;
   for (int i = a.i0; i < a.i1; ++i) {
@@ -107,6 +115,7 @@ int summa_sweep(const SummaArgs& a) {
     // ---- communication for panel i, chunk by chunk, on the comm stream ----
     if (need_comm) {
       for (int t = 0; t < nchunks; ++t) {
+        const bool bg = !(i == a.i0 && t == 0);  // the very first chunk has nothing to hide under: full-width communicator
         if (done_prev[t]) CANDMC_CUDA(cudaStreamWaitEvent(comm, done_prev[t], 0));  // buf slot t is free again
         if (a.row->size > 1) {
           double* slot = bufA + t * kc * b;
@@ -116,9 +125,9 @@ int summa_sweep(const SummaArgs& a) {
               CANDMC_TRY(lda_copy_f64(b, kc, a.ldA, b, src, packA + t * kc * b, comm));
               src = packA + t * kc * b;
             }
-            CANDMC_TRY(comm_bcast(a.row, src, const_cast<double*>(src), kc * b, i, comm, true));
+            CANDMC_TRY(comm_bcast(a.row, src, const_cast<double*>(src), kc * b, i, comm, bg));
           } else {
-            CANDMC_TRY(comm_bcast(a.row, slot, slot, kc * b, i, comm, true));
+            CANDMC_TRY(comm_bcast(a.row, slot, slot, kc * b, i, comm, bg));
           }
         }
         if (a.col->size > 1) {
@@ -129,9 +138,9 @@ int summa_sweep(const SummaArgs& a) {
               CANDMC_TRY(lda_copy_f64(kc, b, a.ldB, kc, src, locB + t * kc * b, comm));  // chunk-major, ld = kc
               src = locB + t * kc * b;
             }
-            CANDMC_TRY(comm_bcast(a.col, src, const_cast<double*>(src), kc * b, i, comm, true));
+            CANDMC_TRY(comm_bcast(a.col, src, const_cast<double*>(src), kc * b, i, comm, bg));
           } else {
-            CANDMC_TRY(comm_bcast(a.col, slot, slot, kc * b, i, comm, true));
+            CANDMC_TRY(comm_bcast(a.col, slot, slot, kc * b, i, comm, bg));
           }
         }
         ready[t] = g_events.get();

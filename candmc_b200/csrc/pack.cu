@@ -89,7 +89,7 @@ int lda_dispatch(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const
 // B(cols x rows, ldb) = A(rows x cols, lda)^T, 64x64 tiles through padded shared memory; both the global
 // read and the global write are row-contiguous (coalesced 512 B per warp-row pair).
 constexpr int TT = 64;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 transpose_kernel(int64_t rows, int64_t cols, const double* __restrict__ A, int64_t lda, double* __restrict__ B,
                  int64_t ldb, int64_t tiles_r, int64_t tiles_c) {
   __shared__ double tile[TT][TT + 1];
@@ -97,16 +97,22 @@ transpose_kernel(int64_t rows, int64_t cols, const double* __restrict__ A, int64
   const int64_t ntiles = tiles_r * tiles_c;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t r0 = (t % tiles_r) * TT, c0 = (t / tiles_r) * TT;
-#pragma unroll 4
-    for (int cc = ty; cc < TT; cc += 4) {
-      const int64_t r = r0 + tx, c = c0 + cc;
-      if (r < rows && c < cols) tile[cc][tx] = __ldg(A + r + c * lda);
+    double v[16];
+    // all 16 loads of a thread are issued before the first use (memory-level parallelism: 128 B in flight per thread)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int64_t r = r0 + tx, c = c0 + ty + 4 * i;
+      v[i] = (r < rows && c < cols) ? __ldg(A + r + c * lda) : 0.0;
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tile[ty + 4 * i][tx] = v[i];
     __syncthreads();
-#pragma unroll 4
-    for (int rr = ty; rr < TT; rr += 4) {
-      const int64_t c = c0 + tx, r = r0 + rr;
-      if (r < rows && c < cols) B[c + r * ldb] = tile[tx][rr];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = tile[tx][ty + 4 * i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int64_t c = c0 + tx, r = r0 + ty + 4 * i;
+      if (r < rows && c < cols) B[c + r * ldb] = v[i];
     }
     __syncthreads();
   }
@@ -190,7 +196,7 @@ int transpose_f64(int64_t rows, int64_t cols, const double* A, int64_t lda, doub
   if (rows == 0 || cols == 0) return OK;
   const int64_t tr = (rows + TT - 1) / TT, tc = (cols + TT - 1) / TT;
   int64_t grid = tr * tc;
-  const int64_t cap = static_cast<int64_t>(runtime().num_sms) * 4;
+  const int64_t cap = static_cast<int64_t>(runtime().num_sms) * 6;
   if (grid > cap) grid = cap;
   transpose_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(rows, cols, A, lda, B, ldb, tr, tc);
   CANDMC_CUDA(cudaGetLastError());

@@ -72,6 +72,8 @@ int runtime_finalize() {
   if (!g_rt.initialized) return OK;
   if (g_rt.workspace) cudaFree(g_rt.workspace);
   if (g_rt.tile_counters) cudaFree(g_rt.tile_counters);
+  if (g_rt.splitk_part) cudaFree(g_rt.splitk_part);
+  if (g_rt.splitk_sem) cudaFree(g_rt.splitk_sem);
   if (g_rt.comm_stream) cudaStreamDestroy(g_rt.comm_stream);
   if (g_rt.aux_stream) cudaStreamDestroy(g_rt.aux_stream);
   g_rt = Runtime();
@@ -95,6 +97,30 @@ int workspace_get(size_t bytes, void** out) {
     g_rt.workspace_bytes = bytes;
   }
   *out = g_rt.workspace;
+  return OK;
+}
+
+int splitk_buffers(int64_t part_elems, double** part, int** sem) {
+  if (g_rt.splitk_sem == nullptr) {
+    CANDMC_CUDA(cudaMalloc(&g_rt.splitk_sem, sizeof(int) * 4096));
+    CANDMC_CUDA(cudaMemset(g_rt.splitk_sem, 0, sizeof(int) * 4096));
+  }
+  if ((size_t)part_elems > g_rt.splitk_part_elems) {
+    if (g_rt.splitk_part) {
+      CANDMC_CUDA(cudaDeviceSynchronize());
+      CANDMC_CUDA(cudaFree(g_rt.splitk_part));
+      g_rt.splitk_part = nullptr;
+      g_rt.splitk_part_elems = 0;
+    }
+    cudaError_t e = cudaMalloc(&g_rt.splitk_part, sizeof(double) * part_elems);
+    if (e != cudaSuccess) {
+      set_last_error("split-K scratch: cudaMalloc(%lld doubles) failed: %s", (long long)part_elems, cudaGetErrorString(e));
+      return ERR_NOMEM;
+    }
+    g_rt.splitk_part_elems = (size_t)part_elems;
+  }
+  *part = g_rt.splitk_part;
+  *sem = g_rt.splitk_sem;
   return OK;
 }
 

@@ -21,8 +21,13 @@ struct Runtime {
   void* pfn_encode_tiled = nullptr;     // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
   int* tile_counters = nullptr;         // ring of device counters for the GEMM's dynamic tile scheduler
   unsigned tile_counter_seq = 0;
+  bool splitk = true;                   // cut small-tile-count GEMMs along k too
+  double* splitk_part = nullptr;        // split-K partial tiles (grow-only) and per-tile arrival counters
+  size_t splitk_part_elems = 0;
+  int* splitk_sem = nullptr;
   bool static_schedule = false;         // debug: round-robin tile schedule instead of the atomic counter
   bool profile = false;                 // bracket every DMMA GEMM launch with events (bench.py's roofline leg)
+  int gemm_reserve_sms = 0;             // SMs a GEMM launch leaves free (set by schedules that overlap NCCL traffic)
   int bg_max_ctas = 4;                  // CTA cap of the communicators used for traffic overlapped with GEMMs (0 = no cap)
   int64_t host_pipeline_min = 2048;     // smallest n for which host operands on a 1x1 grid are streamed panel-wise
   int64_t min_kchunk = 1024;            // smallest k-chunk the SUMMA pipeline cuts a panel into
@@ -37,6 +42,9 @@ int runtime_require();
 int runtime_finalize();
 // Grow-only scratch; contents undefined.  Not thread safe (one rank = one host thread, as in the reference).
 int workspace_get(size_t bytes, void** out);
+
+// Scratch for split-K GEMM launches (one launch in flight at a time per process, like the reference's single-threaded ranks).
+int splitk_buffers(int64_t part_elems, double** part, int** sem);
 
 // GEMM launch profiling (candmc_profile_*): events around each TMA+DMMA launch on its own stream.
 int profile_begin_launch(cudaStream_t stream, double flops);

@@ -46,6 +46,8 @@ int candmc_finalize(void);
 int candmc_device_sm_count(int* out);
 /* Number of kernels this library has launched so far in this process (bench.py reports the delta). */
 unsigned long long candmc_launch_count(void);
+/* Test/measurement hook: 0 disables the split-K path the GEMM takes for small tile counts (default on). */
+int candmc_debug_splitk(int on);
 /* Test/measurement hook: 1 makes the GEMM walk its tiles round-robin instead of claiming them from an atomic counter. */
 int candmc_debug_static_schedule(int on);
 /* Measurement hook (bench.py's roofline leg): while enabled every TMA+DMMA GEMM launch is bracketed by CUDA events on

@@ -30,7 +30,8 @@ def rel_frob(x, ref):
 
 
 SHAPES = [(128, 128, 16), (128, 128, 128), (256, 384, 64), (1, 1, 1), (7, 5, 3), (130, 70, 33), (64, 200, 100),
-          (257, 129, 17), (512, 96, 40), (31, 1000, 8), (1000, 31, 9), (333, 222, 111), (640, 512, 300)]
+          (257, 129, 17), (512, 96, 40), (31, 1000, 8), (1000, 31, 9), (333, 222, 111), (640, 512, 300),
+          (128, 128, 4096), (256, 250, 3000), (130, 5, 2049)]   # the last three take the split-K path
 
 
 @pytest.mark.parametrize("ta", ["N", "T"])
@@ -119,6 +120,24 @@ def test_drand48_generator_bit_exact():
         X = torch.zeros(b * b, dtype=torch.float64, device="cuda")
         cb.fill_drand48(X, b, b, b, 48, 0, n, which); torch.cuda.synchronize()
         assert np.array_equal(host(X, b, b), orc.unit_block(b, b, 48, 0, n, which))
+
+
+def test_splitk_matches_plain_kernel_and_is_deterministic():
+    """Small tile counts are cut along k (partials summed in a fixed order): same result to rounding as the unsplit kernel,
+    bit-identical from run to run."""
+    m, n, k = 512, 384, 8192
+    A = torch.empty(m * k, dtype=torch.float64, device="cuda"); B = torch.empty(k * n, dtype=torch.float64, device="cuda")
+    cb.fill_drand48(A, m, k, m, 0, 0, m, 0); cb.fill_drand48(B, k, n, k, 0, 0, k, 1)
+    outs = []
+    for on in (1, 1, 0):
+        cb.lib().candmc_debug_splitk(on)
+        Cm = torch.zeros(m * n, dtype=torch.float64, device="cuda")
+        cb.cdgemm("N", "N", m, n, k, 1.0, A, m, B, k, 0.0, Cm, m)
+        torch.cuda.synchronize()
+        outs.append(Cm.cpu().numpy())
+    cb.lib().candmc_debug_splitk(1)
+    assert np.array_equal(outs[0], outs[1])
+    assert rel_frob(outs[0], outs[2]) <= 10 * k * EPS
 
 
 def test_frob_diff():

@@ -104,7 +104,8 @@ static int run_check() {
   const char tr[2] = {'N', 'T'};
   const int shapes[][3] = {{128, 128, 16},  {128, 128, 128}, {256, 384, 64}, {1, 1, 1},      {7, 5, 3},
                            {130, 70, 33},   {64, 200, 100},  {257, 129, 17}, {100, 300, 250}, {512, 96, 40},
-                           {31, 1000, 8},   {1000, 31, 9},   {384, 256, 512}, {128, 128, 0},  {333, 222, 111}};
+                           {31, 1000, 8},   {1000, 31, 9},   {384, 256, 512}, {128, 128, 0},  {333, 222, 111},
+                           {128, 128, 4096}, {250, 256, 3000}};
   for (auto& s : shapes)
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
@@ -250,7 +251,7 @@ int main(int argc, char** argv) {
     cublasCreate(&h);
     std::vector<int> ns;
     for (int i = 2; i < argc; ++i) ns.push_back(atoi(argv[i]));
-    if (ns.empty()) ns = {2048, 4096, 8192, 16384};
+    if (ns.empty()) ns = {1024, 2048, 4096, 8192, 16384};
     for (int n : ns) speed_one(h, 'N', 'N', n, n, n, n >= 16384 ? 3 : 5);
     speed_one(h, 'N', 'T', 8192, 8192, 8192, 5);
     speed_one(h, 'T', 'N', 8192, 8192, 8192, 5);

@@ -417,17 +417,25 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_
   const int sms = runtime().num_sms;
   const int KT = (K + BK - 1) / BK;
   if (runtime().splitk && tiles < 3 * sms && tiles <= kSplitSemCount) {
-    double best = static_cast<double>(tiles) / (static_cast<double>(sms) * ((tiles + sms - 1) / sms));
-    for (int sp = 2; sp <= 16; ++sp) {
-      if (KT / sp < 16) break;  // keep >= 256 k per unit so the partial-tile traffic stays small
+    // cost model in k-tile units: waves x (k-tiles per unit + per-unit overhead); the overhead of a split unit (park the
+    // partial tile, the last arriver re-reads `sp` of them) was measured at ~9 k-tiles + 1 per partial, an unsplit
+    // tile's epilogue at ~3 (profiles/r01_gemm_probe_speed*.jsonl)
+    auto cost = [&](int sp) {
       const int64_t u = tiles * sp;
-      const double eff = static_cast<double>(u) / (static_cast<double>(sms) * ((u + sms - 1) / sms));
-      if (eff > best + 0.02) {
-        best = eff;
+      const double waves = static_cast<double>((u + sms - 1) / sms);
+      const double per_unit = static_cast<double>((KT + sp - 1) / sp) + (sp == 1 ? 3.0 : 8.0 + sp);
+      return waves * per_unit;
+    };
+    double best = cost(1);
+    for (int sp = 2; sp <= 16; ++sp) {
+      if (KT / sp < 8) break;
+      if ((KT + sp - 1) / sp * (sp - 1) >= KT) continue;  // would leave an empty unit
+      const double c = cost(sp);
+      if (c < 0.97 * best) {
+        best = c;
         ksplit = sp;
       }
     }
-    if ((KT + ksplit - 1) / ksplit * (ksplit - 1) >= KT) ksplit = 1;  // would leave an empty unit
   }
   double* part = nullptr;
   int* sem = nullptr;

@@ -58,7 +58,7 @@ int candmc_profile_gemm_stats(int64_t* launches, double* total_ms, double* total
 /* Start / end (ms, relative to the first profiled launch) of up to `cap` profiled GEMM launches; *n = how many. */
 int candmc_profile_gemm_timeline(double* start_ms, double* end_ms, int64_t cap, int64_t* n);
 /* Tuning: CTA cap of the second NCCL communicator each grid axis uses for panel traffic that runs under a GEMM
- * (default 4; 0 = use the full-width communicator).  Must be set before the first multiply on a communicator. */
+ * (default 2; 0 = use the full-width communicator).  Must be set before the first multiply on a communicator. */
 int candmc_set_background_ctas(int max_ctas);
 /* Test hook: 1 routes candmc_dgemm through the generic CUDA-core kernel instead of the TMA+DMMA kernel. */
 int candmc_debug_force_generic_gemm(int on);

@@ -33,6 +33,11 @@ int candmc_debug_force_generic_gemm(int on) {
   return OK;
 }
 
+int candmc_set_fused_reduce(int on) {
+  runtime().fused_reduce = (on != 0);
+  return OK;
+}
+
 int candmc_debug_splitk(int on) {
   runtime().splitk = (on != 0);
   return OK;

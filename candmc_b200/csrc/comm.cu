@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include "../../include/candmc_b200.h"
+#include "ipc.h"
 #include "runtime.h"
 #include "staging.h"
 
@@ -137,6 +138,12 @@ int candmc_comm_split(candmc_comm_t* parent, int color, int key, candmc_comm_t**
 
 int candmc_comm_free(candmc_comm_t* comm) {
   if (!comm) return OK;
+  if (comm->fused_ctx) {
+    candmc::FusedCtx* f = static_cast<candmc::FusedCtx*>(comm->fused_ctx);
+    cudaDeviceSynchronize();
+    candmc::window_destroy(f->win);
+    delete f;
+  }
   if (comm->nccl_bg && comm->nccl_bg != comm->nccl) ncclCommDestroy(comm->nccl_bg);
   if (comm->nccl) ncclCommDestroy(comm->nccl);
   delete comm;

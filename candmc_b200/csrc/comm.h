@@ -13,6 +13,8 @@ struct candmc_comm {
   ncclComm_t nccl_bg = nullptr;   // same ranks, few CTAs: panel traffic that runs UNDER a GEMM (created on first use)
   int rank = 0;
   int size = 1;
+  void* fused_ctx = nullptr;      // candmc::FusedCtx* of the fused GEMM + depth all-reduce (ipc.h), owned by this handle
+  bool fused_failed = false;      // CUDA IPC unavailable: stay on ncclAllReduce
 };
 
 namespace candmc {

@@ -24,6 +24,7 @@
 //     TMA path as long as the base pointers are 16 B aligned and lda/ldb are even.  Otherwise a plain tiled
 //     CUDA-core kernel (`gemm_f64_generic`) is used — still on the GPU; there is no CPU path.
 #include "common.cuh"
+#include "ipc.h"
 #include "runtime.h"
 
 namespace candmc {
@@ -86,12 +87,36 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int tilesM, int tilesN) {
   return c;
 }
 
-template <bool A_KMAJ, bool B_KMAJ>
+// Tile of work unit `u`.  Plain: the rastered tile grid.  FUSED (GEMM + depth all-reduce): the tile columns are split
+// into `c` contiguous owner ranges and every rank walks the ranges of the OTHER owners first ((me+1)%c, (me+2)%c, ...)
+// and its own last, so the partial tiles it must send leave early and the partials it needs have long arrived.
+struct UnitTile {
+  int tm, tn, owner, within;
+};
+template <bool FUSED>
+__device__ __forceinline__ UnitTile unit_tile(int tile, int tilesM, int tilesN, const FusedParams& fp) {
+  UnitTile u;
+  if (!FUSED) {
+    const TileCoord tc = tile_coord(tile, tilesM, tilesN);
+    u.tm = tc.tm; u.tn = tc.tn; u.owner = 0; u.within = tile;
+  } else {
+    const int per_owner = tilesM * fp.tiles_n_per_owner;
+    const int phase = tile / per_owner;
+    u.within = tile - phase * per_owner;
+    u.owner = (fp.me + 1 + phase) % fp.c;
+    const TileCoord tc = tile_coord(u.within, tilesM, fp.tiles_n_per_owner);
+    u.tm = tc.tm;
+    u.tn = tc.tn + u.owner * fp.tiles_n_per_owner;
+  }
+  return u;
+}
+
+template <bool A_KMAJ, bool B_KMAJ, bool FUSED>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     double* __restrict__ C, int64_t ldc, int M, int N, int K, double alpha, double beta,
                     int tilesM, int tilesN, int* __restrict__ tile_counter, int ksplit, double* __restrict__ part,
-                    int* __restrict__ tile_sem) {
+                    int* __restrict__ tile_sem, const __grid_constant__ FusedParams fp) {
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment for the 128 B swizzle atom; pointer arithmetic keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -134,7 +159,7 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_arrive(&full_bar[stage]);
           break;
         }
-        const TileCoord tc = tile_coord(t / ksplit, tilesM, tilesN);
+        const UnitTile tc = unit_tile<FUSED>(t / ksplit, tilesM, tilesN, fp);
         const int m0 = tc.tm * BM, n0 = tc.tn * BN;
         const int kt0 = (t % ksplit) * KTS, kt1 = min(KT, kt0 + KTS);
         for (int kt = kt0; kt < kt1; ++kt) {
@@ -213,7 +238,7 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int t = stage_tile[stage];
     if (t < 0) break;
     const int tile = t / ksplit, ks = t - tile * ksplit;
-    const TileCoord tc = tile_coord(tile, tilesM, tilesN);
+    const UnitTile tc = unit_tile<FUSED>(tile, tilesM, tilesN, fp);
     const int nkt = min(KT, (ks + 1) * KTS) - ks * KTS;
 #pragma unroll
     for (int f = 0; f < 8; ++f)
@@ -287,37 +312,99 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // beta != 0: the 16 C values of one 8-column group are fetched together (L2 path, 16 loads in flight per lane — the
     // fragment registers are dead here) before they are combined; a load-use-store chain per element would leave the
     // DMMA pipe idle for tens of microseconds per tile.
+    //
+    // FUSED: the depth all-reduce happens here, tile by tile, over peer memory (NVLink P2P stores into the IPC-mapped
+    // windows of the other depth ranks).  A tile owned by another rank: v = alpha*acc + beta*Cin is stored into the
+    // owner's stage slot, then one release-store raises the tile's flag there.  A tile I own: wait for the flags of the
+    // c-1 other sources (their partials were sent in THEIR first phases), add their partials, write the final value to
+    // my C and into every peer's final slab, then bump the peers' delivery counters.
     const int row_base = tc.tm * BM + wm * 64 + cf;
     const int col_base = tc.tn * BN + wn * 32 + cf_map(2 * j);  // slots 2j, 2j+1 -> adjacent columns
+    const bool owned = !FUSED || tc.owner == fp.me;
+    const double* Cin = FUSED ? fp.Cin : C;
+    const int64_t ldin = FUSED ? fp.ldin : ldc;
+    const int owner_col0 = FUSED ? tc.owner * fp.tiles_n_per_owner * BN : 0;
+    const int64_t slab = FUSED ? fp.ld * static_cast<int64_t>(fp.tiles_n_per_owner) * BN : 0;
+    if (FUSED && owned) {
+      if (threadIdx.x == 0) {
+        const int per_owner = tilesM * fp.tiles_n_per_owner;
+        for (int sidx = 0; sidx < fp.c - 1; ++sidx) {
+          const uint32_t* fl = fp.sflag_local + static_cast<int64_t>(sidx) * per_owner + tc.within;
+          uint32_t v;
+          do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
+          } while (v != fp.epoch);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
       double cv[2][8];
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int f = 0; f < 8; ++f) cv[c][f] = 0.0;
       if (beta != 0.0) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const int col = col_base + h * 8 + c;
-          const double* cp = C + static_cast<int64_t>(col) * ldc;
+          const double* cp = Cin + static_cast<int64_t>(col) * ldin;
 #pragma unroll
           for (int f = 0; f < 8; ++f) {
             const int row = row_base + f * 8;
-            cv[c][f] = (col < N && row < M) ? __ldcg(cp + row) : 0.0;
+            cv[c][f] = (col < N && row < M) ? beta * __ldcg(cp + row) : 0.0;
           }
+        }
+      }
+      if (FUSED && owned) {
+        for (int sidx = 0; sidx < fp.c - 1; ++sidx) {
+          double sv[2][8];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int col = col_base + h * 8 + c;
+            const double* sp = fp.stage_local + sidx * slab + static_cast<int64_t>(col - owner_col0) * fp.ld;
+#pragma unroll
+            for (int f = 0; f < 8; ++f) sv[c][f] = __ldcg(sp + row_base + f * 8);
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int f = 0; f < 8; ++f) cv[c][f] += sv[c][f];
         }
       }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int col = col_base + h * 8 + c;
         if (col < N) {
-          double* cp = C + static_cast<int64_t>(col) * ldc;
 #pragma unroll
           for (int f = 0; f < 8; ++f) {
             const int row = row_base + f * 8;
             if (row < M) {
-              double v = alpha * acc[f][h][c];
-              if (beta != 0.0) v += beta * cv[c][f];
-              cp[row] = v;
+              const double v = alpha * acc[f][h][c] + cv[c][f];
+              if (!FUSED) {
+                C[row + static_cast<int64_t>(col) * ldc] = v;
+              } else if (!owned) {
+                fp.stage[tc.owner][row + static_cast<int64_t>(col - owner_col0) * fp.ld] = v;
+              } else {
+                C[row + static_cast<int64_t>(col) * ldc] = v;
+                for (int p = 0; p < fp.c; ++p)
+                  if (p != fp.me) fp.cfinal[p][row + static_cast<int64_t>(col - owner_col0) * fp.ld] = v;
+              }
             }
           }
+        }
+      }
+    }
+    if (FUSED) {
+      __threadfence_system();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) {
+        if (!owned) {
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(fp.sflag[tc.owner] + tc.within), "r"(fp.epoch) : "memory");
+        } else {
+          for (int p = 0; p < fp.c; ++p)
+            if (p != fp.me) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(fp.done[p]) : "memory");
         }
       }
     }
@@ -401,11 +488,11 @@ __global__ void scale_c_kernel(int M, int N, double beta, double* __restrict__ C
 bool is_trans(char t) { return t == 'T' || t == 't' || t == 'C' || t == 'c'; }
 bool is_notrans(char t) { return t == 'N' || t == 'n'; }
 
-template <bool AK, bool BK_>
+template <bool AK, bool BK_, bool FUSED>
 int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_t ldc, int M, int N, int K,
-               double alpha, double beta, cudaStream_t stream) {
+               double alpha, double beta, cudaStream_t stream, const FusedParams* fused) {
   static bool configured = false;  // per template instantiation
-  auto kern = gemm_f64_tma_kernel<AK, BK_>;
+  auto kern = gemm_f64_tma_kernel<AK, BK_, FUSED>;
   if (!configured) {
     CANDMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
@@ -416,7 +503,7 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_
   int ksplit = 1;
   const int sms = runtime().num_sms;
   const int KT = (K + BK - 1) / BK;
-  if (runtime().splitk && tiles < 3 * sms && tiles <= kSplitSemCount) {
+  if (!FUSED && runtime().splitk && tiles < 3 * sms && tiles <= kSplitSemCount) {
     // cost model in k-tile units: waves x (k-tiles per unit + per-unit overhead); the overhead of a split unit (park the
     // partial tile, the last arriver re-reads `sp` of them) was measured at ~9 k-tiles + 1 per partial, an unsplit
     // tile's epilogue at ~3 (profiles/r01_gemm_probe_speed*.jsonl)
@@ -447,8 +534,10 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_
   int* counter = nullptr;
   if (!runtime().static_schedule) CANDMC_TRY(next_tile_counter(&counter, stream));
   if (runtime().profile) CANDMC_TRY(profile_begin_launch(stream, 2.0 * M * (double)N * (double)K));
+  FusedParams fp;
+  if (FUSED) fp = *fused;
   kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmB, C, ldc, M, N, K, alpha, beta, tilesM, tilesN, counter, ksplit,
-                                               part, sem);
+                                               part, sem, fp);
   CANDMC_CUDA(cudaGetLastError());
   if (runtime().profile) CANDMC_TRY(profile_end_launch(stream));
   runtime().launches++;
@@ -460,6 +549,12 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_
 int gemm_f64(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
              int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
              cudaStream_t stream) {
+  return gemm_f64_fused(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, stream, nullptr);
+}
+
+int gemm_f64_fused(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                   int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, cudaStream_t stream,
+                   const FusedParams* fused) {
   CANDMC_TRY(runtime_require());
   CANDMC_CHECK(is_trans(transa) || is_notrans(transa), "dgemm: bad transa '%c'", transa);
   CANDMC_CHECK(is_trans(transb) || is_notrans(transb), "dgemm: bad transb '%c'", transb);
@@ -474,6 +569,7 @@ int gemm_f64(char transa, char transb, int64_t m, int64_t n, int64_t k, double a
   if (m == 0 || n == 0) return OK;
   const int M = (int)m, N = (int)n, K = (int)k;
 
+  CANDMC_CHECK(fused == nullptr || (k > 0 && alpha != 0.0), "fused GEMM+all-reduce needs k > 0");
   if (k == 0 || alpha == 0.0) {
     if (beta == 1.0) return OK;
     const int64_t total = m * n;
@@ -488,6 +584,8 @@ int gemm_f64(char transa, char transb, int64_t m, int64_t n, int64_t k, double a
 
   const bool aligned = (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(B) % 16 == 0) &&
                        (lda % 2 == 0) && (ldb % 2 == 0) && !runtime().force_generic;
+  CANDMC_CHECK(fused == nullptr || (aligned && m == n && m % (128 * fused->c) == 0),
+               "fused GEMM+all-reduce needs aligned square blocks with whole tile columns per depth rank");
   if (aligned) {
     // tensor maps: dim0 is the contiguous (stored-row) dimension of the operand
     CUtensorMap tmA, tmB;
@@ -495,10 +593,16 @@ int gemm_f64(char transa, char transb, int64_t m, int64_t n, int64_t k, double a
     const bool BKm = !tB;  // op(B)(kk,n) = B[kk + n*ldb]  -> K contiguous
     CANDMC_TRY(encode_tmap_f64(&tmA, A, AK ? k : m, AK ? m : k, lda, 16, AK ? BM : 16));
     CANDMC_TRY(encode_tmap_f64(&tmB, B, BKm ? k : n, BKm ? n : k, ldb, 16, BKm ? BN : 16));
-    if (AK && BKm) return launch_tma<true, true>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream);
-    if (AK && !BKm) return launch_tma<true, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream);
-    if (!AK && BKm) return launch_tma<false, true>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream);
-    return launch_tma<false, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream);
+    if (fused) {
+      if (AK && BKm) return launch_tma<true, true, true>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused);
+      if (AK && !BKm) return launch_tma<true, false, true>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused);
+      if (!AK && BKm) return launch_tma<false, true, true>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused);
+      return launch_tma<false, false, true>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused);
+    }
+    if (AK && BKm) return launch_tma<true, true, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr);
+    if (AK && !BKm) return launch_tma<true, false, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr);
+    if (!AK && BKm) return launch_tma<false, true, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr);
+    return launch_tma<false, false, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr);
   }
 
   dim3 grid((M + GT - 1) / GT, (N + GT - 1) / GT);

@@ -19,6 +19,7 @@
 #include "../../include/candmc_b200.h"
 #include "comm.h"
 #include "common.cuh"
+#include "ipc.h"
 #include "runtime.h"
 #include "staging.h"
 
@@ -82,9 +83,23 @@ struct SummaArgs {
   candmc_comm* col;      // along my grid column: rank = my row (cdt_col)
   double* ws;            // >= 4*b*b doubles: packA | locB | bufA | bufB
   cudaStream_t compute;
+  // when set, the LAST multiply of the sweep also performs the depth all-reduce in its epilogue (ipc.h): it reads the
+  // partial sums of the earlier multiplies from C (beta) and writes the reduced block to fused_out
+  FusedParams* fused = nullptr;
+  double* fused_out = nullptr;
+  int64_t fused_ldout = 0;
 };
 
-int summa_sweep(const SummaArgs& a) {
+// The fused epilogue only exists in the TMA kernel: give it 16-byte aligned operands with even leading dimensions.
+int tma_ready_operand(const double** p, int64_t* ld, int64_t rows, int64_t cols, double* scratch, cudaStream_t st) {
+  if (reinterpret_cast<uintptr_t>(*p) % 16 == 0 && *ld % 2 == 0) return OK;
+  CANDMC_TRY(lda_copy_f64(rows, cols, *ld, rows, *p, scratch, st));
+  *p = scratch;
+  *ld = rows;
+  return OK;
+}
+
+int summa_sweep(SummaArgs& a) {
   const int64_t b = a.b, bb = b * b;
   const int my_col = a.row->rank, my_row = a.col->rank;
   cudaStream_t comm = runtime().comm_stream;
@@ -168,7 +183,20 @@ int summa_sweep(const SummaArgs& a) {
         pb = bufB + t * kc * b;
         ldb = kc;  // chunk-major
       }
-      CANDMC_TRY(gemm_f64(a.tA, a.tB, b, b, kc, 1.0, pa, lda, pb, ldb, first ? 0.0 : 1.0, a.C, a.ldC, a.compute));
+      const bool last = (i + 1 == a.i1 && t + 1 == nchunks);
+      if (last && a.fused != nullptr) {
+        // operands of this last chunk must be TMA-able; packA / locB chunk slots of this rank are free to use as scratch
+        // only if it is not the root of the panel (a root multiplies out of the caller's matrices), so use bufA/bufB
+        // slots of the chunk, which a root never receives into
+        CANDMC_TRY(tma_ready_operand(&pa, &lda, is_t(a.tA) ? kc : b, is_t(a.tA) ? b : kc, bufA + t * kc * b, a.compute));
+        CANDMC_TRY(tma_ready_operand(&pb, &ldb, is_t(a.tB) ? b : kc, is_t(a.tB) ? kc : b, bufB + t * kc * b, a.compute));
+        a.fused->Cin = a.C;
+        a.fused->ldin = a.ldC;
+        CANDMC_TRY(gemm_f64_fused(a.tA, a.tB, b, b, kc, 1.0, pa, lda, pb, ldb, first ? 0.0 : 1.0, a.fused_out,
+                                  a.fused_ldout, a.compute, a.fused));
+      } else {
+        CANDMC_TRY(gemm_f64(a.tA, a.tB, b, b, kc, 1.0, pa, lda, pb, ldb, first ? 0.0 : 1.0, a.C, a.ldC, a.compute));
+      }
       first = false;
       if (need_comm && i + 1 < a.i1) {
         done_prev[t] = g_events.get();
@@ -388,10 +416,31 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   double* Cpart = (c > 1) ? bufC : sC.ptr();
   const int64_t ldCpart = (c > 1) ? b : sC.ld();
 
+  // depth all-reduce: fused into the epilogue of the last GEMM over peer memory when the block shape allows it
+  // (whole 128-wide tile columns per depth rank, CUDA IPC available), otherwise ncclAllReduce
+  FusedCtx* fctx = nullptr;
+  FusedParams fparams;
+  if (c > 1) CANDMC_TRY(fused_ctx_get(cdt_kdir, b, &fctx));
+  if (fctx) fused_params_next(fctx, layer, &fparams);
+
   if (ksplit) {
     const int64_t kb = b / c;
-    CANDMC_TRY(gemm_f64('N', 'N', b, b, kb, 1.0, sA.ptr() + layer * kb * sA.ld(), sA.ld(), sB.ptr() + layer * kb,
-                        sB.ld(), 0.0, Cpart, ldCpart, st));
+    const double* pa = sA.ptr() + layer * kb * sA.ld();
+    const double* pb = sB.ptr() + layer * kb;
+    int64_t lda = sA.ld(), ldb = sB.ld();
+    if (fctx) {
+      void* scr = nullptr;
+      const bool need_scratch = reinterpret_cast<uintptr_t>(pa) % 16 || lda % 2 || reinterpret_cast<uintptr_t>(pb) % 16 || ldb % 2;
+      if (need_scratch) {
+        CANDMC_TRY(workspace_get(sizeof(double) * (2 * b * kb + 4), &scr));
+        CANDMC_TRY(tma_ready_operand(&pa, &lda, b, kb, static_cast<double*>(scr), st));
+        CANDMC_TRY(tma_ready_operand(&pb, &ldb, kb, b, static_cast<double*>(scr) + b * kb + (b * kb & 1), st));
+      }
+      fparams.Cin = nullptr;
+      CANDMC_TRY(gemm_f64_fused('N', 'N', b, b, kb, 1.0, pa, lda, pb, ldb, 0.0, sC.ptr(), sC.ld(), st, &fparams));
+    } else {
+      CANDMC_TRY(gemm_f64('N', 'N', b, b, kb, 1.0, pa, lda, pb, ldb, 0.0, Cpart, ldCpart, st));
+    }
   } else {
     SummaArgs a;
     a.tA = args->trans_A; a.tB = args->trans_B; a.b = b;
@@ -399,9 +448,16 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
     a.myA = sA.ptr(); a.ldA = sA.ld(); a.myB = sB.ptr(); a.ldB = sB.ld();
     a.C = Cpart; a.ldC = ldCpart; a.first_beta_zero = true;  // intended semantics, SURVEY App. A-1
     a.row = cdt_row; a.col = cdt_col; a.ws = ws; a.compute = st;
+    if (fctx) {
+      a.fused = &fparams;
+      a.fused_out = sC.ptr();
+      a.fused_ldout = sC.ld();
+    }
     CANDMC_TRY(summa_sweep(a));
   }
-  if (c > 1) {
+  if (fctx) {
+    CANDMC_TRY(fused_finish(fctx, layer, fparams, sC.ptr(), sC.ld(), st));
+  } else if (c > 1) {
     // MPI_Allreduce(buf_C, mat_C, b*b, SUM, cdt_kdir) — d25_summa.cxx:149,221 (result on every layer)
     if (sC.ld() == b) {
       CANDMC_TRY(comm_allreduce(cdt_kdir, bufC, sC.ptr(), b * b, st));

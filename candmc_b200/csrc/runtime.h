@@ -21,6 +21,7 @@ struct Runtime {
   void* pfn_encode_tiled = nullptr;     // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
   int* tile_counters = nullptr;         // ring of device counters for the GEMM's dynamic tile scheduler
   unsigned tile_counter_seq = 0;
+  bool fused_reduce = true;             // depth all-reduce fused into the last GEMM's epilogue over peer memory
   bool splitk = true;                   // cut small-tile-count GEMMs along k too
   double* splitk_part = nullptr;        // split-K partial tiles (grow-only) and per-tile arrival counters
   size_t splitk_part_elems = 0;
@@ -65,6 +66,11 @@ int encode_tmap_f64(CUtensorMap* out, const double* base, int64_t dim0, int64_t 
 int gemm_f64(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
              int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
              cudaStream_t stream);
+struct FusedParams;
+// GEMM whose epilogue also performs the depth all-reduce over peer memory (fused == nullptr: plain GEMM)
+int gemm_f64_fused(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                   int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, cudaStream_t stream,
+                   const FusedParams* fused);
 int lda_copy_f64(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B,
                  cudaStream_t stream);
 int lda_axpby_f64(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B, double a,

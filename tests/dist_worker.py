@@ -230,6 +230,13 @@ def main():
             case_d25(world, golden, f"d25_ksplit_n64_{tag}", 64, 2, 0)
             case_d25(world, golden, f"d25_ksplit_n96_pad_{tag}", 96, 2, 1, lda_pad=2)
             case_upd_A(world, f"upd_A_p2_{tag}", 64, 48, 16)
+            # b multiple of 128*c: the depth sum is fused into the GEMM epilogue over peer memory (CUDA IPC windows)
+            case_d25(world, golden, f"d25_ksplit_fused_n512_{tag}", 512, 2, 0)
+            case_d25(world, golden, f"d25_ksplit_fused_n256_pad_{tag}", 256, 2, 0, lda_pad=3)
+            case_d25(world, golden, f"d25_ksplit_fused_n768_again_{tag}", 768, 2, 1)
+            cb.lib().candmc_set_fused_reduce(0)
+            case_d25(world, golden, f"d25_ksplit_nccl_n512_{tag}", 512, 2, 0)
+            cb.lib().candmc_set_fused_reduce(1)
         if P == 4:
             case_d25(world, golden, "d25_n96_q2_c1_ovp0", 96, 1, 0)
             case_d25(world, golden, "d25_n96_q2_c1_ovp1", 96, 1, 1)
@@ -254,7 +261,9 @@ def main():
             case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0)
             case_d25(world, golden, "d25_n64_q2_c2_ovp1", 64, 2, 1)
             case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0, lda_pad=2)
-            case_d25(world, golden, f"d25_n512_c2_{tag}", 512, 2, 0)
+            case_d25(world, golden, f"d25_n512_c2_{tag}", 512, 2, 0)            # b = 256: fused depth sum
+            case_d25(world, golden, f"d25_n1024_c2_fused_{tag}", 1024, 2, 1)
+            case_d25(world, golden, f"d25_n512_c2_fused_pad_{tag}", 512, 2, 0, lda_pad=1)
     cb.set_min_kchunk(1024)
     big = int(os.environ.get("CANDMC_TEST_BIG_N", "0"))
     if big:

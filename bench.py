@@ -284,9 +284,20 @@ def main():
             step(hA, hB, hC)   # returns after C is back in host memory
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0) / e2e_steps
-        e2e = {"value": 2.0 * n ** 3 / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * b * b * 8 * world_size,
-               "d2h_bytes_per_step": b * b * 8 * world_size, "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "path": "candmc_d25_summa (C ABI) with pinned host mat_A/mat_B/mat_C, staged inside the call"}
+        # bytes this rank's call really moves: a 1x1xc grid uploads only its k-slice of A and B; on a q x q x c grid a rank
+        # uploads its A (B) block only if its column (row) is one of its layer's panels; every rank downloads its C block
+        if ksplit:
+            my_h2d = 2 * b * (b // c) * 8
+        else:
+            i0, i1 = g["layer"] * (q // c), (g["layer"] + 1) * (q // c)
+            my_h2d = ((i0 <= g["col"] < i1) + (i0 <= g["row"] < i1)) * b * b * 8
+        tot = torch.tensor([float(my_h2d), float(b * b * 8)], dtype=torch.float64, device="cuda")
+        if world_size > 1:
+            dist.all_reduce(tot)
+        e2e = {"value": 2.0 * n ** 3 / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(tot[0].item()),
+               "d2h_bytes_per_step": int(tot[1].item()), "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "path": "candmc_d25_summa (C ABI) with pinned host mat_A/mat_B/mat_C; operands are uploaded in k-chunks "
+                       "under the running multiply, C is downloaded at the end"}
         del hA, hB, hC
 
     if rank == 0:

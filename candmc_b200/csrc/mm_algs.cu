@@ -83,6 +83,11 @@ struct SummaArgs {
   candmc_comm* col;      // along my grid column: rank = my row (cdt_col)
   double* ws;            // >= 4*b*b doubles: packA | locB | bufA | bufB
   cudaStream_t compute;
+  // operands that are still being uploaded from host memory chunk by chunk (see upload_chunks): chunk t of myA / myB is
+  // valid once a_ready[t] / b_ready[t] has fired; an uploaded B is already chunk-major (chunk t = kc x b, ld = kc)
+  const std::vector<cudaEvent_t>* a_ready = nullptr;
+  const std::vector<cudaEvent_t>* b_ready = nullptr;
+  bool b_chunk_major = false;
   // when set, the LAST multiply of the sweep also performs the depth all-reduce in its epilogue (ipc.h): it reads the
   // partial sums of the earlier multiplies from C (beta) and writes the reduced block to fused_out
   FusedParams* fused = nullptr;
@@ -99,6 +104,39 @@ int tma_ready_operand(const double** p, int64_t* ld, int64_t rows, int64_t cols,
   return OK;
 }
 
+// number of k-chunks a sweep over b-wide panels uses (callers that upload operands chunk-wise must agree with it)
+int sweep_chunks(int64_t b, char tA, char tB, const candmc_comm* row, const candmc_comm* col) {
+  const bool need_comm = row->size > 1 || col->size > 1;
+  return (is_n(tA) && is_n(tB) && need_comm) ? pick_chunks(b) : 1;
+}
+
+// Host -> device upload of an NN operand pair in k-chunks on `h2d`: A lands column-major (ld = rows), B lands CHUNK-MAJOR
+// (chunk t = kc x cols with ld = kc) — the 2-D DMA does the re-layout for free.  One event per chunk and operand.
+int upload_chunks(const double* hA, int64_t lda, const double* hB, int64_t ldb, int64_t rows, int64_t cols, int64_t k,
+                  int nchunks, double* dA, double* dB, cudaStream_t h2d, std::vector<cudaEvent_t>* a_ready,
+                  std::vector<cudaEvent_t>* b_ready) {
+  const int64_t kc = k / nchunks;
+  a_ready->assign(nchunks, nullptr);
+  b_ready->assign(nchunks, nullptr);
+  for (int t = 0; t < nchunks; ++t) {
+    if (hA) {
+      CANDMC_CUDA(cudaMemcpy2DAsync(dA + t * kc * rows, rows * 8, hA + t * kc * lda, lda * 8, rows * 8, kc,
+                                    cudaMemcpyHostToDevice, h2d));
+      (*a_ready)[t] = g_events.get();
+      CANDMC_CHECK((*a_ready)[t] != nullptr, "event pool exhausted");
+      CANDMC_CUDA(cudaEventRecord((*a_ready)[t], h2d));
+    }
+    if (hB) {
+      CANDMC_CUDA(cudaMemcpy2DAsync(dB + t * kc * cols, kc * 8, hB + t * kc, ldb * 8, kc * 8, cols, cudaMemcpyHostToDevice,
+                                    h2d));
+      (*b_ready)[t] = g_events.get();
+      CANDMC_CHECK((*b_ready)[t] != nullptr, "event pool exhausted");
+      CANDMC_CUDA(cudaEventRecord((*b_ready)[t], h2d));
+    }
+  }
+  return OK;
+}
+
 int summa_sweep(SummaArgs& a) {
   const int64_t b = a.b, bb = b * b;
   const int my_col = a.row->rank, my_row = a.col->rank;
@@ -107,11 +145,14 @@ int summa_sweep(SummaArgs& a) {
   double* locB = a.ws + bb;
   double* bufA = a.ws + 2 * bb;
   double* bufB = a.ws + 3 * bb;
-  const bool nn = is_n(a.tA) && is_n(a.tB);
   const bool need_comm = a.row->size > 1 || a.col->size > 1;
   // transposed panels are moved whole (the flags only reach the local GEMM); a 1x1 grid has nothing to pipeline
-  const int nchunks = (nn && need_comm) ? pick_chunks(b) : 1;
+  const int nchunks = sweep_chunks(b, a.tA, a.tB, a.row, a.col);
   const int64_t kc = b / nchunks;
+  auto wait_ready = [](cudaStream_t s, const std::vector<cudaEvent_t>* ev, int t) -> int {
+    if (ev && t < (int)ev->size() && (*ev)[t]) CANDMC_CUDA(cudaStreamWaitEvent(s, (*ev)[t], 0));
+    return OK;
+  };
 
   if (need_comm) CANDMC_TRY(stream_wait(comm, a.compute));  // inputs (and earlier users of ws) are ready
   // NCCL moves data with SM-resident kernels, and the persistent GEMM owns every SM it is given (all registers, 193 KiB
@@ -135,6 +176,7 @@ int summa_sweep(SummaArgs& a) {
         if (a.row->size > 1) {
           double* slot = bufA + t * kc * b;
           if (rootA) {
+            CANDMC_TRY(wait_ready(comm, a.a_ready, t));
             const double* src = a.myA + t * kc * a.ldA;  // column slab: contiguous iff ldA == b
             if (a.ldA != b) {
               CANDMC_TRY(lda_copy_f64(b, kc, a.ldA, b, src, packA + t * kc * b, comm));
@@ -148,8 +190,9 @@ int summa_sweep(SummaArgs& a) {
         if (a.col->size > 1) {
           double* slot = bufB + t * kc * b;
           if (rootB) {
-            const double* src = a.myB + t * kc;  // row slab of B: never contiguous unless it is the whole block
-            if (nchunks > 1 || a.ldB != b) {
+            CANDMC_TRY(wait_ready(comm, a.b_ready, t));
+            const double* src = a.b_chunk_major ? a.myB + t * kc * b : a.myB + t * kc;  // row slab of B
+            if (!a.b_chunk_major && (nchunks > 1 || a.ldB != b)) {
               CANDMC_TRY(lda_copy_f64(kc, b, a.ldB, kc, src, locB + t * kc * b, comm));  // chunk-major, ld = kc
               src = locB + t * kc * b;
             }
@@ -170,6 +213,7 @@ int summa_sweep(SummaArgs& a) {
       const double* pb;
       int64_t lda, ldb;
       if (rootA || a.row->size == 1) {
+        CANDMC_TRY(wait_ready(a.compute, a.a_ready, t));
         pa = a.myA + t * kc * a.ldA;
         lda = a.ldA;
       } else {
@@ -177,8 +221,9 @@ int summa_sweep(SummaArgs& a) {
         lda = b;
       }
       if (rootB || a.col->size == 1) {
-        pb = a.myB + t * kc;
-        ldb = a.ldB;
+        CANDMC_TRY(wait_ready(a.compute, a.b_ready, t));
+        pb = a.b_chunk_major ? a.myB + t * kc * b : a.myB + t * kc;
+        ldb = a.b_chunk_major ? kc : a.ldB;
       } else {
         pb = bufB + t * kc * b;
         ldb = kc;  // chunk-major
@@ -402,14 +447,56 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   if (q == 1 && c == 1 && b >= runtime().host_pipeline_min && is_n(args->trans_A) && is_n(args->trans_B) && !is_device_ptr(mat_A) &&
       !is_device_ptr(mat_B) && !is_device_ptr(mat_C))
     return host_pipelined_gemm_nn(b, b, b, mat_A, args->lda_A, mat_B, args->lda_B, mat_C, args->lda_C, st);
+  // Host operands (what the reference's callers own): with untransposed inputs they are uploaded in k-chunks on a copy
+  // stream while the multiply is already running on the chunks that have landed (a 1x1xc grid uploads only its k-slice);
+  // otherwise they are staged whole.
+  // a layer only ever sends/multiplies its own A block if it owns one of the layer's panel columns (B: panel rows)
+  const int pi0 = ksplit ? 0 : layer * (q / c), pi1 = ksplit ? 1 : (layer + 1) * (q / c);
+  const bool useA = ksplit || (cdt_row->rank >= pi0 && cdt_row->rank < pi1);
+  const bool useB = ksplit || (cdt_col->rank >= pi0 && cdt_col->rank < pi1);
+  if (!useA) mat_A = nullptr;
+  if (!useB) mat_B = nullptr;
+  const bool hostA = useA && !is_device_ptr(mat_A), hostB = useB && !is_device_ptr(mat_B);
+  const bool nn = is_n(args->trans_A) && is_n(args->trans_B);
+  const int64_t kloc = ksplit ? b / c : b;                       // k extent this rank touches of its own blocks
+  int up_chunks = 1;
+  if (nn && (hostA || hostB)) {
+    if (q > 1) up_chunks = sweep_chunks(b, args->trans_A, args->trans_B, cdt_row, cdt_col);
+    else for (int nc = 8; nc > 1; nc >>= 1) if (kloc % (2 * nc) == 0 && kloc / nc >= 256) { up_chunks = nc; break; }
+  }
+  const bool chunked = nn && (hostA || hostB) && (up_chunks > 1 || ksplit);
+  std::vector<cudaEvent_t> a_ready, b_ready;
   StagedMatrix sA, sB, sC;
-  CANDMC_TRY(sA.open(mat_A, b, b, args->lda_A, true, st));
-  CANDMC_TRY(sB.open(mat_B, b, b, args->lda_B, true, st));
+  const double* dA_ptr = nullptr; const double* dB_ptr = nullptr;
+  int64_t dA_ld = 0, dB_ld = 0;
+  bool b_chunk_major = false;
+  if (chunked) {
+    void* pool = nullptr;
+    const int64_t needA = hostA ? b * kloc : 0, needB = hostB ? kloc * b : 0;
+    CANDMC_TRY(stage_pool_get(sizeof(double) * (needA + needB + 4), &pool));
+    double* upA = static_cast<double*>(pool);
+    double* upB = upA + needA + (needA & 1);
+    cudaStream_t h2d = runtime().aux_stream;
+    CANDMC_TRY(stream_wait(h2d, st));
+    const double* hA = hostA ? mat_A + (ksplit ? layer * kloc * args->lda_A : 0) : nullptr;
+    const double* hB = hostB ? mat_B + (ksplit ? layer * kloc : 0) : nullptr;
+    CANDMC_TRY(upload_chunks(hA, args->lda_A, hB, args->lda_B, b, b, kloc, up_chunks, upA, upB, h2d, &a_ready, &b_ready));
+    if (hostA) { dA_ptr = upA; dA_ld = b; }
+    else if (useA) { dA_ptr = mat_A + (ksplit ? layer * kloc * args->lda_A : 0); dA_ld = args->lda_A; }
+    if (hostB) { dB_ptr = upB; dB_ld = kloc / up_chunks; b_chunk_major = true; }
+    else if (useB) { dB_ptr = mat_B + (ksplit ? layer * kloc : 0); dB_ld = args->lda_B; }
+  } else {
+    CANDMC_TRY(sA.open(mat_A, b, b, args->lda_A, true, st));
+    CANDMC_TRY(sB.open(mat_B, b, b, args->lda_B, true, st));
+    if (useA) { dA_ptr = sA.ptr() + (ksplit ? layer * kloc * sA.ld() : 0); dA_ld = sA.ld(); }
+    if (useB) { dB_ptr = sB.ptr() + (ksplit ? layer * kloc : 0); dB_ld = sB.ld(); }
+  }
   CANDMC_TRY(sC.open(mat_C, b, b, args->lda_C, false, st));
   void* wsv = nullptr;
   // packA | locB | bufA | bufB only when panels travel (q > 1); bufC only when there is a depth sum (c > 1)
   const int64_t ws_panels = (q > 1) ? 4 * b * b : 0;
-  CANDMC_TRY(workspace_get(sizeof(double) * (ws_panels + (c > 1 ? b * b : 0) + 2), &wsv));
+  const int64_t ws_scratch = ksplit ? 2 * b * (kloc / (chunked ? up_chunks : 1)) + 8 : 0;  // TMA-alignment scratch
+  CANDMC_TRY(workspace_get(sizeof(double) * (ws_panels + (c > 1 ? b * b : 0) + 2 + ws_scratch), &wsv));
   double* ws = static_cast<double*>(wsv);
   double* bufC = ws + ws_panels;
   // with replication the partial product goes to a contiguous scratch block and the depth sum writes mat_C
@@ -424,30 +511,42 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   if (fctx) fused_params_next(fctx, layer, &fparams);
 
   if (ksplit) {
-    const int64_t kb = b / c;
-    const double* pa = sA.ptr() + layer * kb * sA.ld();
-    const double* pb = sB.ptr() + layer * kb;
-    int64_t lda = sA.ld(), ldb = sB.ld();
-    if (fctx) {
-      void* scr = nullptr;
-      const bool need_scratch = reinterpret_cast<uintptr_t>(pa) % 16 || lda % 2 || reinterpret_cast<uintptr_t>(pb) % 16 || ldb % 2;
-      if (need_scratch) {
-        CANDMC_TRY(workspace_get(sizeof(double) * (2 * b * kb + 4), &scr));
-        CANDMC_TRY(tma_ready_operand(&pa, &lda, b, kb, static_cast<double*>(scr), st));
-        CANDMC_TRY(tma_ready_operand(&pb, &ldb, kb, b, static_cast<double*>(scr) + b * kb + (b * kb & 1), st));
+    // my k-slice, multiplied chunk by chunk as the chunks land (one chunk when the operands are already on the device)
+    const int nch = chunked ? up_chunks : 1;
+    const int64_t kc = kloc / nch;
+    for (int t = 0; t < nch; ++t) {
+      if (t < (int)a_ready.size() && a_ready[t]) CANDMC_CUDA(cudaStreamWaitEvent(st, a_ready[t], 0));
+      if (t < (int)b_ready.size() && b_ready[t]) CANDMC_CUDA(cudaStreamWaitEvent(st, b_ready[t], 0));
+      const double* pa = dA_ptr + t * kc * dA_ld;
+      const double* pb = b_chunk_major ? dB_ptr + t * kc * b : dB_ptr + t * kc;
+      int64_t lda = dA_ld, ldb = b_chunk_major ? kc : dB_ld;
+      const bool last = (t + 1 == nch);
+      if (last && fctx) {
+        const bool need_scratch = reinterpret_cast<uintptr_t>(pa) % 16 || lda % 2 || reinterpret_cast<uintptr_t>(pb) % 16 || ldb % 2;
+        if (need_scratch) {
+          double* s0 = ws + ws_panels + (c > 1 ? b * b : 0) + 2;
+          CANDMC_TRY(tma_ready_operand(&pa, &lda, b, kc, s0, st));
+          CANDMC_TRY(tma_ready_operand(&pb, &ldb, kc, b, s0 + b * kc + (b * kc & 1), st));
+        }
+        fparams.Cin = Cpart;
+        fparams.ldin = ldCpart;
+        CANDMC_TRY(gemm_f64_fused('N', 'N', b, b, kc, 1.0, pa, lda, pb, ldb, t ? 1.0 : 0.0, sC.ptr(), sC.ld(), st, &fparams));
+      } else {
+        CANDMC_TRY(gemm_f64('N', 'N', b, b, kc, 1.0, pa, lda, pb, ldb, t ? 1.0 : 0.0, Cpart, ldCpart, st));
       }
-      fparams.Cin = nullptr;
-      CANDMC_TRY(gemm_f64_fused('N', 'N', b, b, kb, 1.0, pa, lda, pb, ldb, 0.0, sC.ptr(), sC.ld(), st, &fparams));
-    } else {
-      CANDMC_TRY(gemm_f64('N', 'N', b, b, kb, 1.0, pa, lda, pb, ldb, 0.0, Cpart, ldCpart, st));
     }
   } else {
     SummaArgs a;
     a.tA = args->trans_A; a.tB = args->trans_B; a.b = b;
     a.i0 = layer * (q / c); a.i1 = (layer + 1) * (q / c);  // d25_summa.cxx:124,151
-    a.myA = sA.ptr(); a.ldA = sA.ld(); a.myB = sB.ptr(); a.ldB = sB.ld();
+    a.myA = dA_ptr; a.ldA = dA_ld; a.myB = dB_ptr; a.ldB = dB_ld;
     a.C = Cpart; a.ldC = ldCpart; a.first_beta_zero = true;  // intended semantics, SURVEY App. A-1
     a.row = cdt_row; a.col = cdt_col; a.ws = ws; a.compute = st;
+    if (chunked) {
+      a.a_ready = &a_ready;
+      a.b_ready = &b_ready;
+      a.b_chunk_major = b_chunk_major;
+    }
     if (fctx) {
       a.fused = &fparams;
       a.fused_out = sC.ptr();
@@ -467,7 +566,8 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
     }
   }
   CANDMC_TRY(sC.close_out(st));
-  if (sA.staged() || sB.staged() || sC.staged()) CANDMC_CUDA(cudaStreamSynchronize(st));
+  if (chunked) CANDMC_TRY(stream_wait(st, runtime().aux_stream));
+  if (chunked || sA.staged() || sB.staged() || sC.staged()) CANDMC_CUDA(cudaStreamSynchronize(st));
   return OK;
 }
 

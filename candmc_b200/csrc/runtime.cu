@@ -71,6 +71,7 @@ int runtime_require() {
 int runtime_finalize() {
   if (!g_rt.initialized) return OK;
   if (g_rt.workspace) cudaFree(g_rt.workspace);
+  if (g_rt.stage_pool) cudaFree(g_rt.stage_pool);
   if (g_rt.tile_counters) cudaFree(g_rt.tile_counters);
   if (g_rt.splitk_part) cudaFree(g_rt.splitk_part);
   if (g_rt.splitk_sem) cudaFree(g_rt.splitk_sem);
@@ -97,6 +98,26 @@ int workspace_get(size_t bytes, void** out) {
     g_rt.workspace_bytes = bytes;
   }
   *out = g_rt.workspace;
+  return OK;
+}
+
+int stage_pool_get(size_t bytes, void** out) {
+  CANDMC_TRY(runtime_require());
+  if (bytes > g_rt.stage_pool_bytes) {
+    if (g_rt.stage_pool) {
+      CANDMC_CUDA(cudaDeviceSynchronize());
+      CANDMC_CUDA(cudaFree(g_rt.stage_pool));
+      g_rt.stage_pool = nullptr;
+      g_rt.stage_pool_bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&g_rt.stage_pool, bytes);
+    if (e != cudaSuccess) {
+      set_last_error("staging pool: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+      return ERR_NOMEM;
+    }
+    g_rt.stage_pool_bytes = bytes;
+  }
+  *out = g_rt.stage_pool;
   return OK;
 }
 

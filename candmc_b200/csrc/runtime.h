@@ -18,6 +18,8 @@ struct Runtime {
   cudaStream_t aux_stream = nullptr;    // second compute/copy stream
   void* workspace = nullptr;            // grow-only device scratch
   size_t workspace_bytes = 0;
+  void* stage_pool = nullptr;           // grow-only staging buffer for chunk-wise uploads of host operands
+  size_t stage_pool_bytes = 0;
   void* pfn_encode_tiled = nullptr;     // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
   int* tile_counters = nullptr;         // ring of device counters for the GEMM's dynamic tile scheduler
   unsigned tile_counter_seq = 0;
@@ -53,6 +55,9 @@ int profile_end_launch(cudaStream_t stream);
 int profile_reset();
 int profile_collect(int64_t* launches, double* total_ms, double* total_flops);
 int profile_timeline(double* start_ms, double* end_ms, int64_t cap, int64_t* n);
+
+// Second grow-only device buffer: staging of host operands that are uploaded while the multiply runs.
+int stage_pool_get(size_t bytes, void** out);
 
 // Hands out a zeroed device counter (memset is enqueued on `stream`) for one GEMM launch.
 int next_tile_counter(int** out, cudaStream_t stream);

@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Measure BASELINE.json's other configurations (parity-test cases, not bench.py lines) on the GPUs at hand:
+  config 2: 2D SUMMA FP64 n=16384 on 4 GPUs (2x2)                         -> summa
+  config 4: Cannon FP64 n=24576 on 4 GPUs, shift overlap                   -> bcast_cannon_4d (x1_np=1, x2_np=2), kput_cannon
+  config 5: CAQR trailing-update shape m=65536, n=8192, k=512 on 1/2/4 GPUs -> upd_A (TN GEMM, all-reduce, trsm, NN GEMM)
+Launch: python tools/bench_configs.py            (1 GPU: config 5 on a 1x1 grid)
+        torchrun --nproc-per-node 4 tools/bench_configs.py
+Prints one JSON line per configuration on rank 0 (device-timed with CUDA events, max over ranks)."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import candmc_b200 as cb  # noqa: E402
+
+PEAK = 148 * 4 * 16 * 2 * 1.965e9 / 1e12
+
+
+def main():
+    rank = int(os.environ.get("RANK", 0)); ws = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    world = cb.init_world(rank, ws, local)
+
+    def timed(fn, steps=3, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if ws > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+        if ws > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def report(name, flops, ms, extra=None):
+        if rank == 0:
+            tf = flops / (ms * 1e-3) / 1e12
+            line = {"config": name, "n_gpus": ws, "ms": ms, "tflops": tf, "pct_of_fp64_tensor_peak": 100 * tf / (PEAK * ws)}
+            line.update(extra or {})
+            print(json.dumps(line), flush=True)
+
+    def blocks(b, row0, col0, n):
+        A = torch.empty(b * b, dtype=torch.float64, device="cuda"); B = torch.empty_like(A); Cm = torch.empty_like(A)
+        cb.fill_drand48(A, b, b, b, row0, col0, n, 0); cb.fill_drand48(B, b, b, b, row0, col0, n, 1)
+        return A, B, Cm
+
+    if ws == 4:
+        # ---- config 2: SUMMA n = 16384, 2x2 ----
+        n = 16384; g = cb.d25_grid(world, 1); b = n // 2
+        A, B, Cm = blocks(b, g["row"] * b, g["col"] * b, n)
+        args = cb.ctb_args_t(n=n, lda_A=b, lda_B=b, lda_C=b, buffer_size=4 * b * b * 8)
+        ms = timed(lambda: cb.summa(args, A, B, Cm, None, g["cdt_row"], g["cdt_col"]))
+        report("config2: summa n=16384 2x2", 2.0 * n ** 3, ms)
+        del A, B, Cm
+        # ---- config 4a: bcast_cannon_4d as pure Cannon, n = 24576 ----
+        n = 24576; d = cb.dcn_grid(world, 2); b = n // 2
+        A, B, Cm = blocks(b, (d["y1"] * 2 + d["y2"]) * b, (d["x1"] * 2 + d["x2"]) * b, n)
+        args = cb.ctb_args_t(n=n, lda_A=b, lda_B=b, lda_C=b, buffer_size=5 * b * b * 8, ovp=1)
+        ms = timed(lambda: cb.bcast_cannon_4d(args, A, B, Cm, None, d["cdt_x1"], d["cdt_y1"], d["cdt_x2"], d["cdt_y2"]))
+        report("config4: bcast_cannon_4d (Cannon level) n=24576 2x2", 2.0 * n ** 3, ms)
+        # ---- config 4b: split-dim Cannon kput, 12288^3 blocks ----
+        ms = timed(lambda: cb.kput_cannon(rank, 2, 2, world, b, b, b, "N", 1.0, A, "T", 0.0, B, Cm))
+        report("config4: kput_cannon 2-ary 2-cube, 12288^3 blocks", 2.0 * n ** 3, ms)
+        del A, B, Cm
+    # ---- config 5: CAQR trailing update ----
+    m, ncol, k = 65536, 8192, 512
+    nprow, npcol = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[ws]
+    prow, pcol = rank % nprow, rank // nprow
+    ccol = cb.setup_sub_comm(world, prow, pcol, nprow) if ws > 1 else None   # ranks sharing my grid column
+    mb, kb = m // nprow, ncol // npcol
+    Y = torch.empty(mb * k, dtype=torch.float64, device="cuda"); Am = torch.empty(mb * kb, dtype=torch.float64, device="cuda")
+    cb.fill_drand48(Y, mb, k, mb, prow * mb, 0, m, 0); cb.fill_drand48(Am, mb, kb, mb, prow * mb, pcol * kb, m, 1)
+    Y.mul_(1.0 / 256.0)   # keep the update well scaled
+    T = (torch.eye(k, dtype=torch.float64, device="cuda") + 0.01 * torch.tril(torch.rand(k, k, dtype=torch.float64, device="cuda"))).T.contiguous()
+    ms = timed(lambda: cb.upd_A(Y, mb, Am, mb, mb, kb, k, T, ccol))
+    report(f"config5: upd_A m=65536 n=8192 k=512 on {nprow}x{npcol}", 2 * 2.0 * m * ncol * k, ms,
+           {"note": "flops = the two GEMMs (SURVEY §8d); all-reduce of W and the triangular solve are inside the time"})
+    # 1-GPU local GEMM roofline at the Cannon block size (config 4, second half)
+    if ws == 1:
+        for n in (12288, 16384):
+            A, B, Cm = blocks(n, 0, 0, n)
+            ms = timed(lambda: cb.cdgemm("N", "N", n, n, n, 1.0, A, n, B, n, 0.0, Cm, n))
+            report(f"config4: 1-GPU local GEMM n={n}", 2.0 * n ** 3, ms)
+            del A, B, Cm
+    world.free()
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

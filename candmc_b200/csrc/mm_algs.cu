@@ -83,8 +83,8 @@ struct SummaArgs {
   candmc_comm* col;      // along my grid column: rank = my row (cdt_col)
   double* ws;            // >= 4*b*b doubles: packA | locB | bufA | bufB
   cudaStream_t compute;
-  // operands that are still being uploaded from host memory chunk by chunk (see upload_chunks): chunk t of myA / myB is
-  // valid once a_ready[t] / b_ready[t] has fired; an uploaded B is already chunk-major (chunk t = kc x b, ld = kc)
+  // operands that are still being uploaded from host memory (see upload_chunks): chunk t of myA / myB is valid once
+  // a_ready[t] / b_ready[t] has fired; b_chunk_major: myB is already laid out chunk-major (chunk t = kc x b, ld = kc)
   const std::vector<cudaEvent_t>* a_ready = nullptr;
   const std::vector<cudaEvent_t>* b_ready = nullptr;
   bool b_chunk_major = false;
@@ -110,14 +110,24 @@ int sweep_chunks(int64_t b, char tA, char tB, const candmc_comm* row, const cand
   return (is_n(tA) && is_n(tB) && need_comm) ? pick_chunks(b) : 1;
 }
 
-// Host -> device upload of an NN operand pair in k-chunks on `h2d`: A lands column-major (ld = rows), B lands CHUNK-MAJOR
-// (chunk t = kc x cols with ld = kc) — the 2-D DMA does the re-layout for free.  One event per chunk and operand.
+// Host -> device upload of an NN operand pair on `h2d`.  B goes first and whole: a k-chunk of B is a ROW slab, and a 2-D DMA
+// of 16 KiB-wide rows is descriptor-bound (measured: it made the N = 2 end-to-end step 0.5 s slower than staging the block
+// whole), so B is moved with full-height columns (one event for every chunk) and re-laid out per chunk on the device by the
+// pack kernel.  A follows in k-chunks (contiguous column slabs), one event each, so the multiply of chunk t starts while
+// chunk t+1 is still on the wire.
 int upload_chunks(const double* hA, int64_t lda, const double* hB, int64_t ldb, int64_t rows, int64_t cols, int64_t k,
                   int nchunks, double* dA, double* dB, cudaStream_t h2d, std::vector<cudaEvent_t>* a_ready,
                   std::vector<cudaEvent_t>* b_ready) {
   const int64_t kc = k / nchunks;
   a_ready->assign(nchunks, nullptr);
   b_ready->assign(nchunks, nullptr);
+  if (hB) {
+    CANDMC_CUDA(cudaMemcpy2DAsync(dB, k * 8, hB, ldb * 8, k * 8, cols, cudaMemcpyHostToDevice, h2d));  // k x cols, ld = k
+    cudaEvent_t e = g_events.get();
+    CANDMC_CHECK(e != nullptr, "event pool exhausted");
+    CANDMC_CUDA(cudaEventRecord(e, h2d));
+    for (int t = 0; t < nchunks; ++t) (*b_ready)[t] = e;
+  }
   for (int t = 0; t < nchunks; ++t) {
     if (hA) {
       CANDMC_CUDA(cudaMemcpy2DAsync(dA + t * kc * rows, rows * 8, hA + t * kc * lda, lda * 8, rows * 8, kc,
@@ -125,13 +135,6 @@ int upload_chunks(const double* hA, int64_t lda, const double* hB, int64_t ldb, 
       (*a_ready)[t] = g_events.get();
       CANDMC_CHECK((*a_ready)[t] != nullptr, "event pool exhausted");
       CANDMC_CUDA(cudaEventRecord((*a_ready)[t], h2d));
-    }
-    if (hB) {
-      CANDMC_CUDA(cudaMemcpy2DAsync(dB + t * kc * cols, kc * 8, hB + t * kc, ldb * 8, kc * 8, cols, cudaMemcpyHostToDevice,
-                                    h2d));
-      (*b_ready)[t] = g_events.get();
-      CANDMC_CHECK((*b_ready)[t] != nullptr, "event pool exhausted");
-      CANDMC_CUDA(cudaEventRecord((*b_ready)[t], h2d));
     }
   }
   return OK;
@@ -483,7 +486,7 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
     CANDMC_TRY(upload_chunks(hA, args->lda_A, hB, args->lda_B, b, b, kloc, up_chunks, upA, upB, h2d, &a_ready, &b_ready));
     if (hostA) { dA_ptr = upA; dA_ld = b; }
     else if (useA) { dA_ptr = mat_A + (ksplit ? layer * kloc * args->lda_A : 0); dA_ld = args->lda_A; }
-    if (hostB) { dB_ptr = upB; dB_ld = kloc / up_chunks; b_chunk_major = true; }
+    if (hostB) { dB_ptr = upB; dB_ld = kloc; }
     else if (useB) { dB_ptr = mat_B + (ksplit ? layer * kloc : 0); dB_ld = args->lda_B; }
   } else {
     CANDMC_TRY(sA.open(mat_A, b, b, args->lda_A, true, st));

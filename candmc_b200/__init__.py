@@ -20,6 +20,8 @@ from .mm import (  # noqa: F401
     kput_cannon,
     kuni_cannon,
     upd_A,
+    update_A,
+    pview,
     fill_drand48,
     frob_diff,
     set_min_kchunk,

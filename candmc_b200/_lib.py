@@ -28,6 +28,11 @@ class CtbArgs(C.Structure):
                 ("lda_C", i64), ("buffer_size", i64), ("ovp", C.c_int)]
 
 
+class PView(C.Structure):
+    """candmc_pview_t == pview (alg/shared/comm.h:66-84)."""
+    _fields_ = [("rrow", C.c_int), ("rcol", C.c_int), ("crow", C.c_void_p), ("ccol", C.c_void_p), ("cworld", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/candmc_b200.h declares
 SIGNATURES = {
     "candmc_version": (C.c_int, []),
@@ -67,6 +72,7 @@ SIGNATURES = {
     "candmc_spcannon": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, comm_p, C.c_int, C.c_int, C.c_int, C.c_char,
                                   C.c_double, pd, C.c_char, C.c_double, pd, pd, C.c_void_p]),
     "candmc_upd_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, comm_p, C.c_void_p]),
+    "candmc_update_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, C.POINTER(PView), pd, i64, C.c_int, C.c_void_p]),
     "candmc_set_min_kchunk": (C.c_int, [i64]),
     "candmc_set_host_pipeline_min": (C.c_int, [i64]),
 }

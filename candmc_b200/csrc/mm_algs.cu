@@ -845,17 +845,41 @@ int candmc_spcannon(int bidir, int rank, int kary, int ndim, candmc_comm_t* worl
 }
 
 // ================================================================================================================
-int candmc_upd_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
-                 const double* T, candmc_comm_t* ccol, void* stream) {
-  CANDMC_TRY(runtime_require());
-  g_events.reset();
-  CANDMC_CHECK(mb >= 0 && kb >= 0 && b > 0, "upd_A: bad extents");
-  CANDMC_CHECK(is_device_ptr(Y) && is_device_ptr(A) && is_device_ptr(T), "upd_A: operands must be device pointers");
+}  // extern "C"
+
+namespace candmc {
+namespace {
+
+// Ybuf = Y panel out of its lda; on the root grid row the upper triangle is zeroed and the diagonal set to one
+// (copy_lower(..., zero_square = 1) + the explicit 1.0 of update_A, alg/QR/qr_2d/qr_2d.cxx:157-163)
+__global__ void pack_y_panel_kernel(const double* __restrict__ Y, int64_t lda_Y, double* __restrict__ Ybuf, int64_t mb,
+                                    int64_t b, int root_row) {
+  const int64_t total = mb * b;
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t j = e / mb, r = e - j * mb;
+    double v = Y[r + j * lda_Y];
+    if (root_row) {
+      if (r < j) v = 0.0;
+      if (r == j) v = 1.0;
+    }
+    Ybuf[e] = v;
+  }
+}
+
+// T = lower triangle of S with halved diagonal, zero above (compute_invT_from_Y, qr_2d.cxx:36-50; T zero-filled :235)
+__global__ void tril_halve_diag_kernel(const double* __restrict__ S, double* __restrict__ T, int64_t b) {
+  const int64_t total = b * b;
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t j = e / b, i = e - j * b;
+    T[e] = (i > j) ? S[e] : (i == j ? 0.5 * S[e] : 0.0);
+  }
+}
+
+int upd_A_impl(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
+               const double* T, candmc_comm* ccol, double* W, cudaStream_t st) {
   if (kb == 0) return OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  void* wsv = nullptr;
-  CANDMC_TRY(workspace_get(sizeof(double) * b * kb, &wsv));
-  double* W = static_cast<double*>(wsv);
   // W = Y^T A (qr_2d.cxx:259); ranks without rows contribute zeros (:262)
   if (mb > 0) CANDMC_TRY(gemm_f64('T', 'N', b, kb, mb, 1.0, Y, lda_Y, A, lda_A, 0.0, W, b, st));
   else CANDMC_TRY(fill_f64(W, b * kb, 0.0, st));
@@ -865,6 +889,75 @@ int candmc_upd_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64
     CANDMC_TRY(gemm_f64('N', 'N', mb, kb, b, -1.0, Y, lda_Y, W, b, 1.0, A, lda_A, st));        // :275
   }
   return OK;
+}
+
+}  // namespace
+}  // namespace candmc
+
+extern "C" {
+
+int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
+                    const double* W, const candmc_pview_t* pv, double* aggreg_Y, int64_t lda_aY, int W_is_T,
+                    void* stream) {
+  CANDMC_TRY(runtime_require());
+  g_events.reset();
+  CANDMC_CHECK(pv != nullptr && pv->crow != nullptr && pv->ccol != nullptr, "update_A: null processor view");
+  CANDMC_CHECK(b > 0 && m >= 0 && k >= 0 && m % b == 0 && k % b == 0, "update_A: m and k must be multiples of b");
+  CANDMC_CHECK(W == nullptr || W_is_T, "update_A: only W == NULL (T from Y) and W_is_T are implemented on the device");
+  CANDMC_CHECK(is_device_ptr(Y) && is_device_ptr(A) && is_device_ptr(W) && is_device_ptr(aggreg_Y),
+               "update_A: operands must be device pointers");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nprow = pv->ccol->size, npcol = pv->crow->size, myrow = pv->ccol->rank, mycol = pv->crow->rank;
+  CANDMC_CHECK(pv->rrow >= 0 && pv->rrow < nprow && pv->rcol >= 0 && pv->rcol < npcol, "update_A: bad root row/col");
+  // block-cyclic local extents of the remaining matrix, qr_2d.cxx:140-147
+  int64_t mb = (m / b) / nprow;
+  if ((myrow + nprow - pv->rrow) % nprow < (m / b) % nprow) mb++;
+  mb *= b;
+  int64_t kb = (k / b) / npcol;
+  if ((mycol + npcol - pv->rcol - 1) % npcol < (k / b) % npcol) kb++;
+  kb *= b;
+  void* wsv = nullptr;
+  CANDMC_TRY(workspace_get(sizeof(double) * (mb * b + 2 * b * b + b * kb + 8), &wsv));
+  double* Ybuf = static_cast<double*>(wsv);
+  double* S = Ybuf + mb * b + (mb * b & 1);
+  double* T = S + b * b;
+  double* Wbuf = T + b * b;
+  // Ybuf on the root column (:155-165), then MPI_Bcast along the grid row (:168)
+  if (mycol == pv->rcol && mb > 0) {
+    int64_t g = (mb * b + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(runtime().num_sms) * 8;
+    if (g > cap) g = cap;
+    pack_y_panel_kernel<<<static_cast<int>(g), 256, 0, st>>>(Y, lda_Y, Ybuf, mb, b, myrow == pv->rrow);
+    CANDMC_CUDA(cudaGetLastError());
+    runtime().launches++;
+  }
+  if (mb > 0) CANDMC_TRY(comm_bcast(pv->crow, Ybuf, Ybuf, mb * b, pv->rcol, st));
+  const double* Tuse = W;
+  if (W == nullptr) {
+    // T^-1 form from Y: lower triangle of sum over the grid column of Ybuf^T Ybuf, diagonal halved (:22-60)
+    if (mb > 0) CANDMC_TRY(gemm_f64('T', 'N', b, b, mb, 1.0, Ybuf, mb, Ybuf, mb, 0.0, S, b, st));
+    else CANDMC_TRY(fill_f64(S, b * b, 0.0, st));
+    if (nprow > 1) CANDMC_TRY(comm_allreduce(pv->ccol, S, S, b * b, st));
+    tril_halve_diag_kernel<<<static_cast<int>((b * b + 255) / 256), 256, 0, st>>>(S, T, b);
+    CANDMC_CUDA(cudaGetLastError());
+    runtime().launches++;
+    Tuse = T;
+  }
+  CANDMC_TRY(upd_A_impl(Ybuf, mb, A, lda_A, mb, kb, b, Tuse, pv->ccol, Wbuf, st));
+  if (aggreg_Y != nullptr && mb > 0) CANDMC_TRY(lda_copy_f64(mb, b, mb, lda_aY, Ybuf, aggreg_Y, st));  // :172-174
+  return OK;
+}
+
+int candmc_upd_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
+                 const double* T, candmc_comm_t* ccol, void* stream) {
+  CANDMC_TRY(runtime_require());
+  g_events.reset();
+  CANDMC_CHECK(mb >= 0 && kb >= 0 && b > 0, "upd_A: bad extents");
+  CANDMC_CHECK(is_device_ptr(Y) && is_device_ptr(A) && is_device_ptr(T), "upd_A: operands must be device pointers");
+  if (kb == 0) return OK;
+  void* wsv = nullptr;
+  CANDMC_TRY(workspace_get(sizeof(double) * b * kb, &wsv));
+  return upd_A_impl(Y, lda_Y, A, lda_A, mb, kb, b, T, ccol, static_cast<double*>(wsv), static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

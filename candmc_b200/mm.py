@@ -161,3 +161,20 @@ def upd_A(Y, lda_Y, A, lda_A, mb, kb, b, T, ccol: CommData_t | None = None, stre
     """The GEMM pair + allreduce + trsm of upd_A (alg/QR/qr_2d/qr_2d.cxx:259-275), W_is_T case."""
     check(lib().candmc_upd_A(_ptr(Y), lda_Y, _ptr(A), lda_A, mb, kb, b, _ptr(T), ccol.cm if ccol else None,
                              _stream(stream)))
+
+
+@dataclass
+class pview:
+    """Mirror of `pview` (alg/shared/comm.h:66-84)."""
+    rrow: int
+    rcol: int
+    crow: CommData_t
+    ccol: CommData_t
+    cworld: CommData_t | None = None
+
+
+def update_A(Y, lda_Y, A, lda_A, m, k, b, W, pv: pview, aggreg_Y=None, lda_aY=0, W_is_T=False, stream=None):
+    """update_A (alg/QR/qr_2d/qr_2d.h:74-85): (I - Y T^-1 Y^T) A on a block-cyclic grid; W None -> T from Y."""
+    cpv = _lib.PView(pv.rrow, pv.rcol, pv.crow.cm, pv.ccol.cm, pv.cworld.cm if pv.cworld else None)
+    check(lib().candmc_update_A(_ptr(Y), lda_Y, _ptr(A), lda_A, m, k, b, _ptr(W), C.byref(cpv), _ptr(aggreg_Y), lda_aY,
+                                1 if W_is_T else 0, _stream(stream)))

@@ -161,6 +161,23 @@ int candmc_spcannon(int bidir, int rank, int kary, int ndim, candmc_comm_t* worl
  * extents), all device pointers.  ccol may be NULL (single process column). */
 int candmc_upd_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
                  const double* T, candmc_comm_t* ccol, void* stream);
+/* Processor-grid view of the CAQR drivers: mirror of `pview` (alg/shared/comm.h:66-84; the diagonal communicator is not
+ * used on this path).  crow: ranks of my grid row (rank = my column); ccol: ranks of my grid column (rank = my row). */
+typedef struct candmc_pview {
+  int rrow; /* current root row */
+  int rcol; /* current root column */
+  candmc_comm_t* crow;
+  candmc_comm_t* ccol;
+  candmc_comm_t* cworld;
+} candmc_pview_t;
+/* (I - Y T^-1 Y^T) A on a block-cyclic nprow x npcol grid.  Replaces update_A (alg/QR/qr_2d/qr_2d.cxx:124-177): local
+ * extents by the block-cyclic formulas (:140-147), Y panel packed with zeroed upper triangle and unit diagonal on the root
+ * row (:155-165), MPI_Bcast along the grid row (:168), then upd_A (:224-282); with W == NULL the triangular factor is formed
+ * from Y (compute_invT_from_Y, :22-60), with W_is_T != 0 W is the b x b lower-triangular T.  (The third form, W = Y1^T T from
+ * the panel factorisation, is not implemented.)  aggreg_Y may be NULL.  All matrix operands are device pointers. */
+int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
+                    const double* W, const candmc_pview_t* pv, double* aggreg_Y, int64_t lda_aY, int W_is_T,
+                    void* stream);
 /* Tuning: the SUMMA pipeline cuts each b-wide panel into up to 8 k-chunks of at least this many columns
  * (default 1024) so the broadcast of chunk t+1 runs under the GEMM of chunk t.  Tests lower it to exercise the
  * chunked path on small matrices. */

@@ -400,3 +400,86 @@ int oracle_upd_A(int nprow, const int64_t* mb, int64_t kb, int64_t b, double* co
   free(Wr);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * update_A (alg/QR/qr_2d/qr_2d.cxx:124-177) + upd_A (:224-282) + compute_invT_from_Y (:22-60), all ranks simulated.
+ * ---------------------------------------------------------------------------------------------------------- */
+void oracle_update_A_extents(int nprow, int npcol, int rrow, int rcol, int myrow, int mycol, int64_t m, int64_t k,
+                             int64_t b, int64_t* mb, int64_t* kb) {
+  int64_t x = (m / b) / nprow; /* :140-147 */
+  if ((myrow + nprow - rrow) % nprow < (m / b) % nprow) x++;
+  *mb = x * b;
+  x = (k / b) / npcol;
+  if ((mycol + npcol - rcol - 1) % npcol < (k / b) % npcol) x++;
+  *kb = x * b;
+}
+
+int oracle_update_A(int nprow, int npcol, int rrow, int rcol, int64_t m, int64_t k, int64_t b, double* const* Y,
+                    double* const* A, const double* W, int mode, int64_t* mb_out, int64_t* kb_out) {
+  if (nprow <= 0 || npcol <= 0 || b <= 0 || m % b || k % b) return -1;
+  /* Ybuf of every grid row: the root column's panel, on the root row with zeroed upper triangle and unit diagonal
+   * (copy_lower + the explicit 1.0, :157-163), then MPI_Bcast along the row (:168) */
+  double** Ybuf = (double**)malloc(sizeof(double*) * (size_t)nprow);
+  int64_t* mbs = (int64_t*)malloc(sizeof(int64_t) * (size_t)nprow);
+  for (int pr = 0; pr < nprow; ++pr) {
+    int64_t mb, kb;
+    oracle_update_A_extents(nprow, npcol, rrow, rcol, pr, rcol, m, k, b, &mb, &kb);
+    mbs[pr] = mb;
+    Ybuf[pr] = dalloc((size_t)(mb * b));
+    const double* src = Y[pr + rcol * nprow];
+    for (int64_t j = 0; j < b; ++j)
+      for (int64_t r = 0; r < mb; ++r) {
+        double v = src[r + j * mb];
+        if (pr == rrow) {
+          if (r < j) v = 0.0;
+          if (r == j) v = 1.0;
+        }
+        Ybuf[pr][r + j * mb] = v;
+      }
+  }
+  /* T: mode 1 -> W; mode 0 -> lower triangle of sum_rows Ybuf^T Ybuf with halved diagonal (:36-50), rest zero (:235) */
+  double* T = dalloc((size_t)(b * b));
+  if (mode == 1) {
+    memcpy(T, W, sizeof(double) * (size_t)(b * b));
+  } else {
+    double* S = dalloc((size_t)(b * b));
+    for (int pr = 0; pr < nprow; ++pr)
+      if (mbs[pr] > 0) oracle_dgemm('T', 'N', b, b, mbs[pr], 1.0, Ybuf[pr], mbs[pr], Ybuf[pr], mbs[pr], 1.0, S, b);
+    for (int64_t j = 0; j < b; ++j)
+      for (int64_t i = j; i < b; ++i) T[i + j * b] = (i == j) ? S[i + j * b] / 2.0 : S[i + j * b];
+    free(S);
+  }
+  /* per grid column: W = sum_rows Ybuf^T A (:259,265), W <- T^-1 W (:271), A -= Ybuf W (:275) */
+  for (int pc = 0; pc < npcol; ++pc) {
+    int64_t mb0, kb;
+    oracle_update_A_extents(nprow, npcol, rrow, rcol, 0, pc, m, k, b, &mb0, &kb);
+    if (kb_out) kb_out[pc] = kb;
+    if (kb == 0) continue;
+    double* Wm = dalloc((size_t)(b * kb));
+    double* Wr = dalloc((size_t)(b * kb));
+    for (int pr = 0; pr < nprow; ++pr)
+      if (mbs[pr] > 0) {
+        oracle_dgemm('T', 'N', b, kb, mbs[pr], 1.0, Ybuf[pr], mbs[pr], A[pr + pc * nprow], mbs[pr], 0.0, Wr, b);
+        for (int64_t e = 0; e < b * kb; ++e) Wm[e] += Wr[e];
+      }
+    for (int64_t j = 0; j < kb; ++j)
+      for (int64_t i = 0; i < b; ++i) {
+        double x = Wm[i + j * b];
+        for (int64_t p = 0; p < i; ++p) x -= T[i + p * b] * Wm[p + j * b];
+        Wm[i + j * b] = x / T[i + i * b];
+      }
+    for (int pr = 0; pr < nprow; ++pr)
+      if (mbs[pr] > 0)
+        oracle_dgemm('N', 'N', mbs[pr], kb, b, -1.0, Ybuf[pr], mbs[pr], Wm, b, 1.0, A[pr + pc * nprow], mbs[pr]);
+    free(Wm);
+    free(Wr);
+  }
+  for (int pr = 0; pr < nprow; ++pr) {
+    if (mb_out) mb_out[pr] = mbs[pr];
+    free(Ybuf[pr]);
+  }
+  free(Ybuf);
+  free(mbs);
+  free(T);
+  return 0;
+}

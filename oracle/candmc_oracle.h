@@ -50,6 +50,15 @@ int oracle_spcannon(int bidir, int kary, int ndim, int n, int m, int k, char tra
 int oracle_upd_A(int nprow, const int64_t* mb, int64_t kb, int64_t b, double* const* Y, const int64_t* lda_Y,
                  double* const* A, const int64_t* lda_A, const double* T);
 
+/* update_A on an nprow x npcol grid (rank = myrow + mycol*nprow, test/QR/test_qr_2d.cxx:367-374) with the current root
+ * (rrow, rcol): local extents follow the block-cyclic formulas of qr_2d.cxx:140-147.  Y[r]: local mb x b panel of the ranks
+ * in the root column (others ignored), A[r]: local mb x kb trailing block (ld = mb).  mode 0: W == NULL (T from Y,
+ * qr_2d.cxx:22-60); mode 1: W is the b x b lower-triangular T (W_is_T).  mb_out/kb_out (may be NULL) receive the extents. */
+int oracle_update_A(int nprow, int npcol, int rrow, int rcol, int64_t m, int64_t k, int64_t b, double* const* Y,
+                    double* const* A, const double* W, int mode, int64_t* mb_out, int64_t* kb_out);
+void oracle_update_A_extents(int nprow, int npcol, int rrow, int rcol, int myrow, int mycol, int64_t m, int64_t k,
+                             int64_t b, int64_t* mb, int64_t* kb);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,10 @@ def lib() -> C.CDLL:
                                       _ppd, C.c_char, C.c_double, _ppd, _ppd]
         L.oracle_upd_A.argtypes = [C.c_int, C.POINTER(_i64), _i64, _i64, _ppd, C.POINTER(_i64), _ppd,
                                    C.POINTER(_i64), _pd]
+        L.oracle_update_A.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _i64, _i64, _i64, _ppd, _ppd, _pd, C.c_int,
+                                      C.POINTER(_i64), C.POINTER(_i64)]
+        L.oracle_update_A_extents.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i64, _i64, _i64,
+                                              C.POINTER(_i64), C.POINTER(_i64)]
         _LIB = L
     return _LIB
 
@@ -182,3 +186,48 @@ def spc_blocks(kary, ndim, seed, n, m, k, tB="N"):
         B.append(np.asfortranarray(Bb.T if tB == "T" else Bb))
         Cb.append(np.asfortranarray(full_C[py * m:(py + 1) * m, px * n:(px + 1) * n]))
     return A, B, Cb, (full_A, full_B, full_C)
+
+
+# ---- CAQR trailing update (N1): update_A on a block-cyclic nprow x npcol grid -------------------------------------------
+def update_A_extents(nprow, npcol, rrow, rcol, myrow, mycol, m, k, b):
+    mb, kb = _i64(), _i64()
+    lib().oracle_update_A_extents(nprow, npcol, rrow, rcol, myrow, mycol, m, k, b, C.byref(mb), C.byref(kb))
+    return mb.value, kb.value
+
+
+def _lcg48(seed):
+    x = ((seed & 0xFFFFFFFF) << 16) | 0x330E
+    x = (0x5DEECE66D * x + 0xB) & ((1 << 48) - 1)
+    return x / 281474976710656.0
+
+
+def update_A_blocks(nprow, npcol, rrow, rcol, m, k, b):
+    """Per-rank Y (mb x b) and A (mb x kb) blocks of oracle/ref_dump.cxx's `upda` mode (rank = myrow + mycol*nprow):
+    elements are seeded by their global coordinates in the remaining matrix."""
+    Y, A = [], []
+    for rank in range(nprow * npcol):
+        myrow, mycol = rank % nprow, rank // nprow
+        mb, kb = update_A_extents(nprow, npcol, rrow, rcol, myrow, mycol, m, k, b)
+        Yb = np.zeros((max(mb, 1), b), order="F")
+        Ab = np.zeros((max(mb, 1), max(kb, 1)), order="F")
+        for r in range(mb):
+            gr = ((r // b) * nprow + (myrow - rrow + nprow) % nprow) * b + r % b
+            for j in range(b):
+                Yb[r, j] = (_lcg48(7000 + gr * b + j) - .5) * 0.25
+            for cc in range(kb):
+                gc = ((cc // b) * npcol + (mycol - rcol - 1 + npcol) % npcol) * b + cc % b
+                Ab[r, cc] = _lcg48(900000 + gc * m + gr) - .5
+        Y.append(Yb[:mb] if mb else Yb[:0])
+        A.append(Ab[:mb, :kb] if (mb and kb) else np.zeros((mb, kb), order="F"))
+    Y = [np.asfortranarray(y) for y in Y]
+    A = [np.asfortranarray(a) for a in A]
+    return Y, A
+
+
+def update_A(nprow, npcol, rrow, rcol, m, k, b, Y, A, W=None):
+    """All ranks simulated; A blocks are updated in place.  W None -> T from Y; otherwise W is the lower-triangular T."""
+    Yp = [y if y.size else np.zeros(1) for y in Y]
+    Ap = [a if a.size else np.zeros(1) for a in A]
+    rc = lib().oracle_update_A(nprow, npcol, rrow, rcol, m, k, b, _pp(Yp), _pp(Ap),
+                               _p(W) if W is not None else None, 0 if W is None else 1, None, None)
+    assert rc == 0, "oracle_update_A: bad arguments"

@@ -178,6 +178,41 @@ def case_upd_A(world, name, mb, kb, b):
     return record(f"{name}:oracle", rel_frob(got, A[world.rank]), 10 * mb * P * EPS)
 
 
+def case_update_A(world, golden, name, m, k, b, nprow, rrow, rcol, with_T=False):
+    """update_A on a block-cyclic nprow x npcol grid with rotated roots, vs the reference's own outputs
+    (tests/golden, W == NULL) and the oracle.  rank = myrow + mycol*nprow (test/QR/test_qr_2d.cxx:367-374)."""
+    P = world.np
+    npcol = P // nprow
+    myrow, mycol = world.rank % nprow, world.rank // nprow
+    crow = cb.setup_sub_comm(world, mycol, myrow, npcol)    # ranks of my grid row, ordered by column
+    ccol = cb.setup_sub_comm(world, myrow, mycol, nprow)    # ranks of my grid column, ordered by row
+    Y, A = orc.update_A_blocks(nprow, npcol, rrow, rcol, m, k, b)
+    mb, kb = orc.update_A_extents(nprow, npcol, rrow, rcol, myrow, mycol, m, k, b)
+    Yl, Al = Y[world.rank], A[world.rank]
+    lda_Y, lda_A = max(mb, 1) + 2, max(mb, 1)
+    Yp = np.zeros((lda_Y, b), order="F"); Yp[:mb] = Yl
+    dY = dev(Yp)
+    dA = dev(Al) if Al.size else torch.zeros(1, dtype=torch.float64, device="cuda")
+    agg = torch.zeros(max(mb, 1) * b, dtype=torch.float64, device="cuda")
+    W = None
+    Wnp = None
+    if with_T:   # W_is_T: a well-conditioned lower-triangular T handed in by the caller
+        Wnp = np.asfortranarray(np.eye(b) + 0.01 * np.tril(np.random.default_rng(9).random((b, b))))
+        W = dev(Wnp)
+    pv = cb.pview(rrow, rcol, crow, ccol, world)
+    cb.update_A(dY, lda_Y, dA, lda_A, m, k, b, W, pv, aggreg_Y=agg, lda_aY=max(mb, 1), W_is_T=with_T)
+    torch.cuda.synchronize()
+    got = host(dA, mb, kb) if (mb and kb) else np.zeros((mb, kb))
+    orc.update_A(nprow, npcol, rrow, rcol, m, k, b, Y, A, Wnp)
+    ok = True
+    if mb and kb:
+        ok &= record(f"{name}:oracle", rel_frob(got, A[world.rank]), 10 * m * EPS)
+        if not with_T and f"{name}.r{world.rank}" in golden:
+            ok &= record(f"{name}:golden", rel_frob(got, golden[f"{name}.r{world.rank}"]), 10 * m * EPS)
+    crow.free(); ccol.free()
+    return ok
+
+
 def case_big_d25(world, n, c):
     """Full-size property check: d25 result vs a direct GEMM of the gathered operands on every rank (cross-check only),
     with inputs generated on the device by the same per-element generator."""
@@ -228,6 +263,7 @@ def main():
             case_d25(world, golden, "d25_n40_q1_c1_ovp0", 40, 1, 0)
             case_d25(world, golden, "d25_n40_q1_c1_ovp0", 40, 1, 1, use_host=True, check_golden=False)
             case_spc(world, golden, f"spc_p1_{tag}", 1, 1, 2, 20, 24, 16, "N")
+            case_update_A(world, golden, "upda_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0)
             cb.lib().candmc_set_host_pipeline_min(64)   # stream host operands panel-wise even at this size
             case_d25(world, golden, f"d25_hostpipe_n320_{tag}", 320, 1, 0, use_host=True, check_golden=False)
             case_d25(world, golden, f"d25_hostpipe_n200_pad_{tag}", 200, 1, 0, lda_pad=3, use_host=True, check_golden=False)
@@ -267,6 +303,9 @@ def main():
             case_spc(world, golden, "spc_bidir1_p4_m24_k16_n20_N", 1, 2, 2, 20, 24, 16, "N", use_host=True)
             case_spc(world, golden, f"spc_p4_big_{tag}", 1, 2, 2, 256, 384, 128, "N")
             case_upd_A(world, f"upd_A_p4_{tag}", 96, 80, 32)
+            case_update_A(world, golden, "upda_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 0, 0)
+            case_update_A(world, golden, "upda_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 2, 0)
+            case_update_A(world, golden, f"upda_T_2x2_{tag}", 128, 96, 16, 2, 1, 1, with_T=True)
         if P == 8:
             case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0)
             case_d25(world, golden, "d25_n64_q2_c2_ovp1", 64, 2, 1)

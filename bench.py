@@ -185,9 +185,9 @@ def main():
     torch.cuda.set_device(local)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    world = cb.init_world(rank, world_size, local)
     if args.bg_ctas is not None:
         cb.lib().candmc_set_background_ctas(args.bg_ctas)
+    world = cb.init_world(rank, world_size, local)
     g = cb.d25_grid(world)
     n, q, c = args.n, g["q"], g["c"]
     b = n // q
@@ -284,13 +284,9 @@ def main():
             step(hA, hB, hC)   # returns after C is back in host memory
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0) / e2e_steps
-        # bytes this rank's call really moves: a 1x1xc grid uploads only its k-slice of A and B; on a q x q x c grid a rank
-        # uploads its A (B) block only if its column (row) is one of its layer's panels; every rank downloads its C block
-        if ksplit:
-            my_h2d = 2 * b * (b // c) * 8
-        else:
-            i0, i1 = g["layer"] * (q // c), (g["layer"] + 1) * (q // c)
-            my_h2d = ((i0 <= g["col"] < i1) + (i0 <= g["row"] < i1)) * b * b * 8
+        # bytes this rank's call really moves: a 1x1xc grid uploads only its k-slice of A and B, a q x q x c grid both of
+        # its blocks; every rank downloads its C block
+        my_h2d = 2 * b * (b // c) * 8 if ksplit else 2 * b * b * 8
         tot = torch.tensor([float(my_h2d), float(b * b * 8)], dtype=torch.float64, device="cuda")
         if world_size > 1:
             dist.all_reduce(tot)

@@ -35,6 +35,12 @@ int candmc_debug_force_generic_gemm(int on) {
 
 int candmc_set_fused_reduce(int on) {
   runtime().fused_reduce = (on != 0);
+  runtime().fused_reduce_grids = (on >= 2);
+  return OK;
+}
+
+int candmc_set_skip_unused_uploads(int on) {
+  runtime().skip_unused_uploads = (on != 0);
   return OK;
 }
 

@@ -16,9 +16,13 @@ namespace candmc {
 
 int comm_background(candmc_comm* c, ncclComm_t* out) {
   if (c->nccl_bg == nullptr) {
-    if (runtime().bg_max_ctas <= 0) {
+    if (runtime().bg_max_ctas <= 0 || c->size == 1) {
       c->nccl_bg = c->nccl;
     } else {
+      // ncclCommSplit must not race with outstanding operations on the parent: the background communicator is normally
+      // created together with its parent (candmc_comm_split / candmc_comm_init_rank); on this late path every rank
+      // drains its device first (all ranks reach this point in the same call, so the parent's operations complete)
+      CANDMC_CUDA(cudaDeviceSynchronize());
       ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
       cfg.minCTAs = 1;
       cfg.maxCTAs = runtime().bg_max_ctas;
@@ -109,6 +113,10 @@ int candmc_comm_init_rank(const void* unique_id_128_bytes, int nranks, int rank,
     delete c;
     return ERR_NCCL;
   }
+  if (nranks > 1) {
+    ncclComm_t bg;
+    CANDMC_TRY(comm_background(c, &bg));  // eager: nothing is in flight on the new communicator yet
+  }
   *out = c;
   return OK;
 }
@@ -132,6 +140,10 @@ int candmc_comm_split(candmc_comm_t* parent, int color, int key, candmc_comm_t**
   }
   CANDMC_NCCL(ncclCommUserRank(c->nccl, &c->rank));
   CANDMC_NCCL(ncclCommCount(c->nccl, &c->size));
+  if (c->size > 1) {
+    ncclComm_t bg;
+    CANDMC_TRY(comm_background(c, &bg));  // eager: nothing is in flight on the new communicator yet
+  }
   *out = c;
   return OK;
 }

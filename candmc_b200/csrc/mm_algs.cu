@@ -455,8 +455,9 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   // otherwise they are staged whole.
   // a layer only ever sends/multiplies its own A block if it owns one of the layer's panel columns (B: panel rows)
   const int pi0 = ksplit ? 0 : layer * (q / c), pi1 = ksplit ? 1 : (layer + 1) * (q / c);
-  const bool useA = ksplit || (cdt_row->rank >= pi0 && cdt_row->rank < pi1);
-  const bool useB = ksplit || (cdt_col->rank >= pi0 && cdt_col->rank < pi1);
+  const bool skip_unused = runtime().skip_unused_uploads;
+  const bool useA = !skip_unused || ksplit || (cdt_row->rank >= pi0 && cdt_row->rank < pi1);
+  const bool useB = !skip_unused || ksplit || (cdt_col->rank >= pi0 && cdt_col->rank < pi1);
   if (!useA) mat_A = nullptr;
   if (!useB) mat_B = nullptr;
   const bool hostA = useA && !is_device_ptr(mat_A), hostB = useB && !is_device_ptr(mat_B);
@@ -510,7 +511,8 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   // (whole 128-wide tile columns per depth rank, CUDA IPC available), otherwise ncclAllReduce
   FusedCtx* fctx = nullptr;
   FusedParams fparams;
-  if (c > 1) CANDMC_TRY(fused_ctx_get(cdt_kdir, b, &fctx));
+  // (on q > 1 grids the fused path is opt-in until it has been validated on 8 GPUs: candmc_set_fused_reduce(2))
+  if (c > 1 && (ksplit || runtime().fused_reduce_grids)) CANDMC_TRY(fused_ctx_get(cdt_kdir, b, &fctx));
   if (fctx) fused_params_next(fctx, layer, &fparams);
 
   if (ksplit) {

@@ -46,11 +46,15 @@ int candmc_finalize(void);
 int candmc_device_sm_count(int* out);
 /* Number of kernels this library has launched so far in this process (bench.py reports the delta). */
 unsigned long long candmc_launch_count(void);
-/* 2.5D depth sum: 1 (default) fuses the all-reduce over the depth communicator into the epilogue of the last GEMM —
- * partial tiles travel as P2P stores over NVLink into CUDA-IPC-mapped windows of the other depth ranks while the GEMM is
- * still running; 0 uses ncclAllReduce after the GEMM (also the automatic fallback when IPC is unavailable or the block
- * is not a multiple of 128*c).  Must be the same on all ranks. */
+/* Depth sum of the replicated-grid multiplies: 1 (default) fuses the all-reduce over the depth communicator into the
+ * epilogue of the last GEMM on 1 x 1 x c grids — partial tiles travel as P2P stores over NVLink into CUDA-IPC-mapped
+ * windows of the other depth ranks while the GEMM is still running; 2 also on q x q x c grids (implemented, parity-tested
+ * on 2 GPUs only so far, hence opt-in); 0 uses ncclAllReduce after the GEMM (also the automatic fallback when IPC is
+ * unavailable or the block is not a multiple of 128*c).  Must be the same on all ranks. */
 int candmc_set_fused_reduce(int on);
+/* Host operands on q x q x c grids: 1 skips the upload of an A (B) block whose grid column (row) is not one of the layer's
+ * panels (default 0: upload both). */
+int candmc_set_skip_unused_uploads(int on);
 /* Test/measurement hook: 0 disables the split-K path the GEMM takes for small tile counts (default on). */
 int candmc_debug_splitk(int on);
 /* Test/measurement hook: 1 makes the GEMM walk its tiles round-robin instead of claiming them from an atomic counter. */

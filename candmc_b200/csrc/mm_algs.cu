@@ -59,6 +59,13 @@ int stream_wait(cudaStream_t to, cudaStream_t from) {
 bool is_t(char t) { return t == 'T' || t == 't' || t == 'C' || t == 'c'; }
 bool is_n(char t) { return t == 'N' || t == 'n'; }
 
+// While background NCCL traffic is in flight the GEMMs leave that many SMs free (see summa_sweep).
+struct ReserveGuard {
+  int saved;
+  explicit ReserveGuard(int r) : saved(runtime().gemm_reserve_sms) { runtime().gemm_reserve_sms = r; }
+  ~ReserveGuard() { runtime().gemm_reserve_sms = saved; }
+};
+
 // number of k-chunks a b-wide panel is cut into: as many as 8, each at least `min_kchunk` wide and even
 int pick_chunks(int64_t b) {
   const int64_t min_kc = runtime().min_kchunk;
@@ -161,11 +168,8 @@ int summa_sweep(SummaArgs& a) {
   // NCCL moves data with SM-resident kernels, and the persistent GEMM owns every SM it is given (all registers, 193 KiB
   // smem), so a broadcast enqueued while a GEMM runs would only start when that GEMM ends.  While panels are in flight
   // the GEMMs therefore leave as many SMs free as the background communicators may use.
-  struct ReserveGuard {
-    int saved;
-    explicit ReserveGuard(int r) : saved(runtime().gemm_reserve_sms) { runtime().gemm_reserve_sms = r; }
-    ~ReserveGuard() { runtime().gemm_reserve_sms = saved; }
-  } reserve_guard(need_comm ? runtime().bg_max_ctas : runtime().gemm_reserve_sms);
+  ReserveGuard reserve_guard(need_comm ? std::max(runtime().bg_max_ctas, runtime().gemm_reserve_sms)
+                                       : runtime().gemm_reserve_sms);
   std::vector<cudaEvent_t> done_prev(nchunks, nullptr);
   bool first = a.first_beta_zero;
   for (int i = a.i0; i < a.i1; ++i) {
@@ -636,6 +640,9 @@ int candmc_bcast_cannon_4d(const candmc_ctb_args_t* args, const double* mat_A, c
     CANDMC_TRY(stream_wait(st, shift));
   }
 
+  // NOTE: the shifts use the full-width communicators — grouped ncclSend/ncclRecv on the CTA-capped background
+  // communicators hung in the 4-GPU parity run (profiles/r01_cannon_bg_hang.txt), so their overlap with the multiplies
+  // is only as good as the SMs NCCL can get at GEMM boundaries; a copy-engine transport is the planned fix.
   for (int i2 = 0; i2 < x2_np; ++i2) {
     const double* nxtA = curA;
     const double* nxtB = curB;
@@ -644,8 +651,8 @@ int candmc_bcast_cannon_4d(const candmc_ctb_args_t* args, const double* mat_A, c
       // shift by -1 (dual_cannon.cxx:196-213) into the alternate buffers WHILE this step multiplies.  The wait makes
       // sure the previous step's multiplies (the last readers of the alternate buffers) are finished.
       CANDMC_TRY(stream_wait(shift, st));
-      CANDMC_TRY(comm_sendrecv(cdt_x2, curA, bb, wrap(x2 - 1, x2_np), pingA[nextA], bb, wrap(x2 + 1, x2_np), shift, true));
-      CANDMC_TRY(comm_sendrecv(cdt_y2, curB, bb, wrap(y2 - 1, x2_np), pingB[nextB], bb, wrap(y2 + 1, x2_np), shift, true));
+      CANDMC_TRY(comm_sendrecv(cdt_x2, curA, bb, wrap(x2 - 1, x2_np), pingA[nextA], bb, wrap(x2 + 1, x2_np), shift));
+      CANDMC_TRY(comm_sendrecv(cdt_y2, curB, bb, wrap(y2 - 1, x2_np), pingB[nextB], bb, wrap(y2 + 1, x2_np), shift));
       nxtA = pingA[nextA]; nextA ^= 1;
       nxtB = pingB[nextB]; nextB ^= 1;
       shift_done = g_events.get();
@@ -772,6 +779,9 @@ int spc_shift(Spc& s, int bidir, int level, double beta) {  // bdr_shift :87-162
     }
     dbeta = 1.0;
     if (s.kary == 1) continue;  // every shift is the identity
+    // the shift after the very last multiply only restores the reference's in-place operands; A and B are private copies
+    // here, so nobody would read it
+    if (level == 0 && ka == s.kary - 1) continue;
     std::vector<Xfer> xs;
     const int p = s.cur;
     for (int j = 0; j < s.half; ++j) {
@@ -792,7 +802,7 @@ int spc_shift(Spc& s, int bidir, int level, double beta) {  // bdr_shift :87-162
         xs.push_back({s.B[p] + i * bB, s.B[1 - p] + i * bB, bB, upB, dnB});
       }
     }
-    CANDMC_TRY(spc_exchange(s, xs, true));
+    CANDMC_TRY(spc_exchange(s, xs, false));  // full-width communicator, see the note in candmc_bcast_cannon_4d
   }
   return OK;
 }

@@ -284,6 +284,13 @@ def main():
             step(hA, hB, hC)   # returns after C is back in host memory
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+        # the end-to-end path must deliver the same block as the device-resident path (different k-chunking, so equal to
+        # rounding, not bit for bit)
+        chk = torch.empty(b * b, dtype=torch.float64, device="cuda")
+        chk.copy_(hC)
+        d2, r2 = cb.frob_diff(chk, b, dC, b, b, b)
+        e2e_rel = max_over_ranks((d2 / r2) ** 0.5)
+        del chk
         # bytes this rank's call really moves: a 1x1xc grid uploads only its k-slice of A and B, a q x q x c grid both of
         # its blocks; every rank downloads its C block
         my_h2d = 2 * b * (b // c) * 8 if ksplit else 2 * b * b * 8
@@ -292,6 +299,7 @@ def main():
             dist.all_reduce(tot)
         e2e = {"value": 2.0 * n ** 3 / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(tot[0].item()),
                "d2h_bytes_per_step": int(tot[1].item()), "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "rel_frobenius_vs_device_path": e2e_rel, "valid": bool(e2e_rel <= 10 * n * 2.220446049250313e-16),
                "path": "candmc_d25_summa (C ABI) with pinned host mat_A/mat_B/mat_C; operands are uploaded in k-chunks "
                        "under the running multiply, C is downloaded at the end"}
         del hA, hB, hC

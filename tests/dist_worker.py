@@ -309,8 +309,6 @@ def main():
             case_update_A(world, golden, "upda_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 2, 0)
             case_update_A(world, golden, f"upda_T_2x2_{tag}", 128, 96, 16, 2, 1, 1, with_T=True)
         if P == 8:
-            cb.lib().candmc_set_fused_reduce(2)            # opt in: fused depth sum on the 2x2x2 grid
-            cb.lib().candmc_set_skip_unused_uploads(1)
             case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0)
             case_d25(world, golden, "d25_n64_q2_c2_ovp1", 64, 2, 1)
             case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0, lda_pad=2)

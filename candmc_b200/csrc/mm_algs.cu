@@ -469,8 +469,10 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   const int64_t kloc = ksplit ? b / c : b;                       // k extent this rank touches of its own blocks
   int up_chunks = 1;
   if (nn && (hostA || hostB)) {
+    // the chunking must be the one the consumer uses: the sweep's own for q > 1, the k-slice loop below for 1 x 1 x c;
+    // a 1 x 1 x 1 grid below the streaming threshold multiplies in one piece, so it stages whole
     if (q > 1) up_chunks = sweep_chunks(b, args->trans_A, args->trans_B, cdt_row, cdt_col);
-    else for (int nc = 8; nc > 1; nc >>= 1) if (kloc % (2 * nc) == 0 && kloc / nc >= 256) { up_chunks = nc; break; }
+    else if (ksplit) for (int nc = 8; nc > 1; nc >>= 1) if (kloc % (2 * nc) == 0 && kloc / nc >= 256) { up_chunks = nc; break; }
   }
   const bool chunked = nn && (hostA || hostB) && (up_chunks > 1 || ksplit);
   std::vector<cudaEvent_t> a_ready, b_ready;

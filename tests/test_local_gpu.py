@@ -102,8 +102,10 @@ def test_pack_kernels_bit_exact(nrow, ncol, lda, ldb):
     assert np.array_equal(host(dB, ldb, ncol), want)
     want = B.copy(order="F"); orc.lda_cpy(nrow, ncol, lda, ldb, A, want, 1.5, -0.25)
     dB = dev(B); cb.lda_cpy(nrow, ncol, lda, ldb, dev(A), dB, 1.5, -0.25); torch.cuda.synchronize()
-    # b*B + a*A may contract to an fma on the GPU: identical up to one rounding
-    assert np.allclose(host(dB, ldb, ncol), want, rtol=4 * EPS, atol=0)
+    # b*B + a*A may contract to an fma on the GPU: identical up to one rounding of the larger product
+    got = host(dB, ldb, ncol)
+    bound = 4 * EPS * (1.5 * np.abs(A[:nrow]) + 0.25 * np.abs(B[:nrow]))
+    assert (np.abs(got[:nrow] - want[:nrow]) <= bound).all() and np.array_equal(got[nrow:], want[nrow:])
     T = np.zeros((ncol + 1, nrow), order="F"); wantT = T.copy(order="F")
     orc.transpose(nrow, ncol, A, lda, wantT, ncol + 1)
     dT = dev(T); cb.transpose(nrow, ncol, dev(A), lda, dT, ncol + 1); torch.cuda.synchronize()

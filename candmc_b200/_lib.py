@@ -76,6 +76,25 @@ SIGNATURES = {
     "candmc_update_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, C.POINTER(PView), pd, i64, C.c_int, C.c_void_p]),
     "candmc_set_min_kchunk": (C.c_int, [i64]),
     "candmc_set_host_pipeline_min": (C.c_int, [i64]),
+    # accelerator seam of the 2.5D LU (alg/LU/lu_offload.h)
+    "candmc_off_set_device": (C.c_int, [C.c_int]),
+    "candmc_off_alloc": (C.c_int, [C.c_int, i64, pd]),
+    "candmc_off_free": (C.c_int, [C.c_int]),
+    "candmc_off_alloc_transfer": (C.c_int, [i64]),
+    "candmc_off_free_transfer": (C.c_int, []),
+    "candmc_off_device_ptr": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(i64)]),
+    "candmc_off_size": (C.c_int, [C.c_int, C.POINTER(i64)]),
+    "candmc_off_host_mirror": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "candmc_off_gemm": (C.c_int, [C.c_char, C.c_char, i64, i64, i64, C.c_double, i64, C.c_int, i64, i64, C.c_int, i64,
+                                  C.c_double, i64, C.c_int, i64]),
+    "candmc_off_wait_gemm": (C.c_int, []),
+    "candmc_off_upload": (C.c_int, [i64, i64, i64, i64, pd, i64, C.c_int]),
+    "candmc_off_download": (C.c_int, [i64, i64, i64, i64, i64, pd, C.c_int]),
+    "candmc_off_sparse_rw": (C.c_int, [i64, i64, i64, pd, i64, C.POINTER(C.c_int), C.c_int, C.c_char]),
+    "candmc_off_sync": (C.c_int, []),
+    "candmc_off_set_overlap": (C.c_int, [C.c_int]),
+    "candmc_off_stats": (C.c_int, [C.POINTER(i64)]),
+    "candmc_off_blocks_overlap": (C.c_int, [i64] * 8),
 }
 
 

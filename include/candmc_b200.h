@@ -190,6 +190,68 @@ int candmc_set_min_kchunk(int64_t min_kchunk);
  * column panels (upload of panel j+1 and download of panel j-1 under the GEMM of panel j) instead of staged whole. */
 int candmc_set_host_pipeline_min(int64_t min_n);
 
+/* ---- accelerator seam of the 2.5D LU -------------------------------------------------------
+ * The reference keeps three matrices on an accelerator, enum OFF_MAT { OFF_A, OFF_L, OFF_U } (alg/LU/lu_offload.h:19),
+ * and addresses sub-blocks by (matrix, element offset, leading dimension).  Here they live in HBM.  `mat` is 0, 1, 2
+ * for OFF_A, OFF_L, OFF_U.  Offsets and sizes count doubles and are 64-bit (the reference's are int).  All calls come
+ * from one host thread.  The observable results are those of executing the calls one after the other (the
+ * reference's host fallback); internally GEMMs and transfers run on two streams and are ordered only where they touch
+ * overlapping elements. */
+#define CANDMC_OFF_A 0
+#define CANDMC_OFF_L 1
+#define CANDMC_OFF_U 2
+/* Binds the offload runtime to GPU (rank mod #GPUs).  Replaces set_mic_rank (lu_offload.cxx:126-128).  Optional: without
+ * it the device is LOCAL_RANK mod #GPUs (CANDMC_OFF_DEVICE overrides), else the current device. */
+int candmc_off_set_device(int rank);
+/* Allocates `size` doubles of HBM for `mat` (an existing allocation is released first).  Replaces alloc_A / alloc_L /
+ * alloc_U (lu_offload.cxx:479-531).  host_init, if not NULL, is uploaded — what alloc_A(size, ptr) does on the
+ * reference's accelerator build (:482-486); the contents are undefined otherwise. */
+int candmc_off_alloc(int mat, int64_t size, const double* host_init);
+/* Replaces free_offload_A / _L / _U (lu_offload.cxx:545-573).  Waits for queued work first. */
+int candmc_off_free(int mat);
+/* Capacity hint (doubles) for the pinned + device staging used by sparse row traffic.  Replaces alloc_transfer /
+ * free_offload_transfer (lu_offload.cxx:533-543, :575-585); the staging also grows on demand. */
+int candmc_off_alloc_transfer(int64_t size);
+int candmc_off_free_transfer(void);
+/* Device pointer and size of `mat`: what get_mat_handle returns ON the accelerator (lu_offload.cxx:159-175).  The pointer
+ * can be handed to candmc_dgemm / candmc_d25_summa etc.; call candmc_off_sync first. */
+int candmc_off_device_ptr(int mat, double** out, int64_t* size);
+/* Allocated size of `mat` in doubles. */
+int candmc_off_size(int mat, int64_t* size);
+/* Host-side get_mat_handle (the reference's caller memcpy's the local matrix through it, lu_25d_pvt.cxx:1600-1602):
+ * returns a pinned host mirror holding the current contents; whatever the host writes there is uploaded before the next
+ * operation on `mat`.  Later device-side changes are NOT reflected in a pointer obtained earlier — call again. */
+int candmc_off_host_mirror(int mat, double** out);
+/* C <- alpha * op(A) * op(B) + beta * C between blocks of offloaded matrices; asynchronous.  Replaces offload_gemm_A
+ * (lu_offload.cxx:216-251).  C must not overlap A or B. */
+int candmc_off_gemm(char tA, char tB, int64_t m, int64_t n, int64_t k, double alpha, int64_t offset_A, int mat_A,
+                    int64_t lda_A, int64_t offset_B, int mat_B, int64_t lda_B, double beta, int64_t offset_C,
+                    int mat_C, int64_t lda_C);
+/* Blocks until every GEMM issued so far has finished.  Replaces wait_gemm (lu_offload.cxx:130-134). */
+int candmc_off_wait_gemm(void);
+/* Host (or device) block A, nrow x ncol with leading dimension lda_A  ->  mat_B at offset_B with leading dimension
+ * lda_B.  Replaces upload_lda_cpy (lu_offload.cxx:366-392).  A may be reused when the call returns. */
+int candmc_off_upload(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, int64_t offset_B,
+                      int mat_B);
+/* mat_A at offset_A, leading dimension lda_A  ->  host (or device) block B with leading dimension lda_B.  Replaces
+ * download_lda_cpy (lu_offload.cxx:338-364).  B holds the data when the call returns. */
+int candmc_off_download(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, int64_t offset_A, double* B,
+                        int mat_A);
+/* Row traffic for pivoting.  Row i lives at elements offsets[i] + j*lda_B (j < ncol) of mat_B and at A + i*lda_A
+ * (ncol contiguous doubles) on the host.  rw = 'r': matrix -> host, 'w': host -> matrix, 's': swap.  Replaces
+ * offload_sparse_rw (lu_offload.cxx:424-476). */
+int candmc_off_sparse_rw(int64_t nrow, int64_t ncol, int64_t lda_B, double* A, int64_t lda_A, const int* offsets,
+                         int mat_B, char rw);
+/* Waits for every queued GEMM and transfer. */
+int candmc_off_sync(void);
+/* 0: run GEMMs and transfers on one stream (strictly serial); 1 (default): two streams + conflict scoreboard. */
+int candmc_off_set_overlap(int enable);
+/* Counters since load: {GEMMs, uploads, downloads, sparse calls, cross-stream waits inserted, GEMMs still tracked}. */
+int candmc_off_stats(int64_t* out6);
+/* The scoreboard's overlap test on two strided blocks of one matrix (exposed for the CPU-side tests). */
+int candmc_off_blocks_overlap(int64_t off_x, int64_t ld_x, int64_t rows_x, int64_t cols_x, int64_t off_y,
+                              int64_t ld_y, int64_t rows_y, int64_t cols_y);
+
 #ifdef __cplusplus
 }
 #endif

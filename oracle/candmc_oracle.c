@@ -483,3 +483,89 @@ int oracle_update_A(int nprow, int npcol, int rrow, int rcol, int64_t m, int64_t
   free(T);
   return 0;
 }
+
+/* ===== LU accelerator seam: host-fallback semantics of alg/LU/lu_offload.cxx ======================================== */
+void oracle_off_init(oracle_off_t* o) { memset(o, 0, sizeof(*o)); }
+
+void oracle_off_destroy(oracle_off_t* o) {
+  for (int i = 0; i < 3; i++) free(o->mat[i]);
+  memset(o, 0, sizeof(*o));
+}
+
+/* alloc_A / alloc_L / alloc_U, non-accelerator branch (lu_offload.cxx:488,513,524): posix_memalign of `size` doubles */
+int oracle_off_alloc(oracle_off_t* o, int mat, int64_t size) {
+  if (mat < 0 || mat > 2 || size < 0) return -1;
+  free(o->mat[mat]);
+  o->mat[mat] = (double*)malloc(sizeof(double) * (size_t)(size > 0 ? size : 1));
+  o->size[mat] = size;
+  return o->mat[mat] ? 0 : -1;
+}
+
+/* get_mat_handle (lu_offload.cxx:159-175): the host array itself */
+double* oracle_off_handle(oracle_off_t* o, int mat) { return (mat < 0 || mat > 2) ? NULL : o->mat[mat]; }
+
+/* offload_gemm_A, non-accelerator branch (lu_offload.cxx:238-249): cdgemm on handle + offset */
+int oracle_off_gemm(oracle_off_t* o, char tA, char tB, int64_t m, int64_t n, int64_t k, double alpha, int64_t offset_A,
+                    int mat_A, int64_t lda_A, int64_t offset_B, int mat_B, int64_t lda_B, double beta, int64_t offset_C,
+                    int mat_C, int64_t lda_C) {
+  double *a = oracle_off_handle(o, mat_A), *b = oracle_off_handle(o, mat_B), *c = oracle_off_handle(o, mat_C);
+  if (!a || !b || !c) return -1;
+  oracle_dgemm(tA, tB, m, n, k, alpha, a + offset_A, lda_A, b + offset_B, lda_B, beta, c + offset_C, lda_C);
+  return 0;
+}
+
+/* upload_lda_cpy, non-accelerator branch (lu_offload.cxx:381-382): lda_cpy(host A -> handle + offset_B) */
+int oracle_off_upload(oracle_off_t* o, int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A,
+                      int64_t offset_B, int mat_B) {
+  double* b = oracle_off_handle(o, mat_B);
+  if (!b) return -1;
+  oracle_lda_cpy(nrow, ncol, lda_A, lda_B, A, b + offset_B);
+  return 0;
+}
+
+/* download_lda_cpy, non-accelerator branch (lu_offload.cxx:353-354): lda_cpy(handle + offset_A -> host B) */
+int oracle_off_download(oracle_off_t* o, int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, int64_t offset_A,
+                        double* B, int mat_A) {
+  double* a = oracle_off_handle(o, mat_A);
+  if (!a) return -1;
+  oracle_lda_cpy(nrow, ncol, lda_A, lda_B, a + offset_A, B);
+  return 0;
+}
+
+/* offload_sparse_rw, non-accelerator branch (lu_offload.cxx:459-475): row i is the strided vector
+ * handle[offsets[i] + j*lda_B], j < ncol, and the contiguous host vector A + i*lda_A; rows are processed in order */
+int oracle_off_sparse_rw(oracle_off_t* o, int64_t nrow, int64_t ncol, int64_t lda_B, double* A, int64_t lda_A,
+                         const int* offsets, int mat_B, char rw) {
+  if (ncol == 0 || nrow == 0) return 0;
+  double* b = oracle_off_handle(o, mat_B);
+  if (!b) return -1;
+  if (rw != 'r' && rw != 'w' && rw != 's') return -1;
+  for (int64_t i = 0; i < nrow; i++) {
+    double* row = b + offsets[i];
+    double* host = A + i * lda_A;
+    for (int64_t j = 0; j < ncol; j++) {
+      double* e = row + j * lda_B;
+      if (rw == 'r') {
+        host[j] = *e;
+      } else if (rw == 'w') {
+        *e = host[j];
+      } else {
+        double t = *e;
+        *e = host[j];
+        host[j] = t;
+      }
+    }
+  }
+  return 0;
+}
+
+/* splitmix64 finaliser -> [-0.5, 0.5) */
+double oracle_off_value(uint64_t seed, uint64_t idx) {
+  uint64_t x = seed * 0x9E3779B97F4A7C15ull + idx;
+  x ^= x >> 30;
+  x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27;
+  x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (double)(x >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}

@@ -59,6 +59,30 @@ int oracle_update_A(int nprow, int npcol, int rrow, int rcol, int64_t m, int64_t
 void oracle_update_A_extents(int nprow, int npcol, int rrow, int rcol, int myrow, int mycol, int64_t m, int64_t k,
                              int64_t b, int64_t* mb, int64_t* kb);
 
+/* ---- accelerator seam of the 2.5D LU: restatement of the reference's HOST FALLBACK of
+ * alg/LU/lu_offload.cxx (the #else branches: three host arrays, lda_cpy and cdgemm on them).  `mat` is 0/1/2 for
+ * OFF_A/OFF_L/OFF_U (lu_offload.h:19).  Pinned by tests/golden (oracle/ref_off_dump.cxx runs the same scripts through the
+ * unmodified lu_offload.cxx). */
+typedef struct oracle_off {
+  double* mat[3];
+  int64_t size[3];
+} oracle_off_t;
+void oracle_off_init(oracle_off_t* o);
+void oracle_off_destroy(oracle_off_t* o);
+int oracle_off_alloc(oracle_off_t* o, int mat, int64_t size);                       /* lu_offload.cxx:479-531 */
+double* oracle_off_handle(oracle_off_t* o, int mat);                                /* get_mat_handle :159-175 */
+int oracle_off_gemm(oracle_off_t* o, char tA, char tB, int64_t m, int64_t n, int64_t k, double alpha, int64_t offset_A,
+                    int mat_A, int64_t lda_A, int64_t offset_B, int mat_B, int64_t lda_B, double beta, int64_t offset_C,
+                    int mat_C, int64_t lda_C);                                      /* offload_gemm_A :216-251 */
+int oracle_off_upload(oracle_off_t* o, int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A,
+                      int64_t offset_B, int mat_B);                                 /* upload_lda_cpy :366-392 */
+int oracle_off_download(oracle_off_t* o, int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, int64_t offset_A,
+                        double* B, int mat_A);                                      /* download_lda_cpy :338-364 */
+int oracle_off_sparse_rw(oracle_off_t* o, int64_t nrow, int64_t ncol, int64_t lda_B, double* A, int64_t lda_A,
+                         const int* offsets, int mat_B, char rw);                   /* offload_sparse_rw :424-476 */
+/* test-data generator shared by the script drivers (ours, not the reference's): element idx of stream `seed` in [-0.5,0.5) */
+double oracle_off_value(uint64_t seed, uint64_t idx);
+
 #ifdef __cplusplus
 }
 #endif

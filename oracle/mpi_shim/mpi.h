@@ -82,6 +82,14 @@ int MPI_Wait(MPI_Request* req, MPI_Status* status);
 int MPI_Waitall(int n, MPI_Request* reqs, MPI_Status* statuses);
 int MPI_Sendrecv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, int dest, int sendtag, void* recvbuf,
                  int recvcount, MPI_Datatype recvtype, int source, int recvtag, MPI_Comm comm, MPI_Status* status);
+int MPI_Sendrecv_replace(void* buf, int count, MPI_Datatype type, int dest, int sendtag, int source, int recvtag,
+                         MPI_Comm comm, MPI_Status* status);
+int MPI_Gather(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, int recvcount,
+               MPI_Datatype recvtype, int root, MPI_Comm comm);
+int MPI_Gatherv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, const int* recvcounts,
+                const int* displs, MPI_Datatype recvtype, int root, MPI_Comm comm);
+int MPI_Allgather(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, int recvcount,
+                  MPI_Datatype recvtype, MPI_Comm comm);
 int MPI_Win_create(void* base, MPI_Aint size, int disp_unit, MPI_Info info, MPI_Comm comm, MPI_Win* win);
 int MPI_Win_fence(int assert_, MPI_Win win);
 int MPI_Win_free(MPI_Win* win);

@@ -654,6 +654,70 @@ int MPI_Sendrecv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, int 
   return MPI_SUCCESS;
 }
 
+int MPI_Sendrecv_replace(void* buf, int count, MPI_Datatype type, int dest, int sendtag, int source, int recvtag,
+                         MPI_Comm comm, MPI_Status* status) {
+  const int64_t n = (int64_t)count * dt_size(type);
+  char* tmp = (char*)malloc(n > 0 ? (size_t)n : 1);
+  memcpy(tmp, buf, (size_t)n);
+  int r = irecv_bytes(buf, n, source, recvtag, comm);
+  int s = isend_bytes(tmp, n, dest, sendtag, comm);
+  wait_req(s);
+  wait_req(r);
+  free(tmp);
+  if (status) { status->MPI_SOURCE = source; status->MPI_TAG = recvtag; status->MPI_ERROR = 0; }
+  return MPI_SUCCESS;
+}
+
+#define TAG_GATHER 0x40000007
+
+int MPI_Gatherv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, const int* recvcounts,
+                const int* displs, MPI_Datatype recvtype, int root, MPI_Comm comm) {
+  comm_t* c = get_comm(comm);
+  const int64_t sn = (int64_t)sendcount * dt_size(sendtype);
+  if (c->rank == root) {
+    const int rs = dt_size(recvtype);
+    for (int r = 0; r < c->np; ++r) {
+      char* dst = (char*)recvbuf + (int64_t)displs[r] * rs;
+      if (r == root) {
+        if (sendbuf != MPI_IN_PLACE) memcpy(dst, sendbuf, (size_t)sn);
+      } else {
+        recv_bytes(dst, (int64_t)recvcounts[r] * rs, r, TAG_GATHER, comm);
+      }
+    }
+  } else {
+    send_bytes(sendbuf, sn, root, TAG_GATHER, comm);
+  }
+  return MPI_SUCCESS;
+}
+
+int MPI_Gather(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, int recvcount,
+               MPI_Datatype recvtype, int root, MPI_Comm comm) {
+  comm_t* c = get_comm(comm);
+  int* counts = (int*)malloc(sizeof(int) * (size_t)c->np);
+  int* displs = (int*)malloc(sizeof(int) * (size_t)c->np);
+  for (int r = 0; r < c->np; ++r) { counts[r] = recvcount; displs[r] = r * recvcount; }
+  MPI_Gatherv(sendbuf, sendcount, sendtype, recvbuf, counts, displs, recvtype, root, comm);
+  free(counts);
+  free(displs);
+  return MPI_SUCCESS;
+}
+
+int MPI_Allgather(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, int recvcount,
+                  MPI_Datatype recvtype, MPI_Comm comm) {
+  comm_t* c = get_comm(comm);
+  if (sendbuf == MPI_IN_PLACE) {  /* my contribution already sits in its slot */
+    char* mine = (char*)recvbuf + (int64_t)c->rank * recvcount * dt_size(recvtype);
+    char* tmp = (char*)malloc((size_t)recvcount * dt_size(recvtype) + 1);
+    memcpy(tmp, mine, (size_t)recvcount * dt_size(recvtype));
+    MPI_Gather(tmp, recvcount, recvtype, recvbuf, recvcount, recvtype, 0, comm);
+    free(tmp);
+  } else {
+    MPI_Gather(sendbuf, sendcount, sendtype, recvbuf, recvcount, recvtype, 0, comm);
+  }
+  bcast_bytes(recvbuf, (int64_t)c->np * recvcount * dt_size(recvtype), 0, comm);
+  return MPI_SUCCESS;
+}
+
 /* ---- one-sided: Put is queued, data moves at the closing fence ---- */
 int MPI_Win_create(void* base, MPI_Aint size, int disp_unit, MPI_Info info, MPI_Comm comm, MPI_Win* win) {
   (void)info;

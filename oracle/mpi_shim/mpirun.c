@@ -80,6 +80,7 @@ int main(int argc, char** argv) {
       setenv("MINIMPI_SHM", name, 1);
       setenv("OPENBLAS_NUM_THREADS", sthreads, 0);
       setenv("OMP_NUM_THREADS", sthreads, 0);
+      setenv("LOCAL_RANK", srank, 0); /* programs that drive an accelerator pick device (LOCAL_RANK mod #devices) */
       execvp(argv[i], &argv[i]);
       perror("execvp");
       _exit(127);

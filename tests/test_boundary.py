@@ -62,3 +62,39 @@ def test_product_never_references_the_oracle():
                     if re.search(r"oracle[/_.]|liboracle|mpi_shim", text):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, f"product files reference oracle/: {bad}"
+
+
+def test_lu_offload_library_exports_the_reference_entry_points():
+    """libcandmc_lu_offload.so must define, with C++ linkage, exactly what alg/LU/lu_offload.h:19-101 declares, so that the
+    reference's LU objects link against it instead of alg/LU/lu_offload.cxx."""
+    import subprocess
+
+    so = os.path.join(ROOT, "candmc_b200", "libcandmc_lu_offload.so")
+    assert os.path.exists(so), "run __graft_entry__.build()"
+    out = subprocess.run(["nm", "-D", "--defined-only", "-C", so], capture_output=True, text=True, check=True).stdout
+    want = ["get_mat_handle(OFF_MAT)", "set_mic_rank(int)", "wait_gemm()",
+            "offload_gemm_A(char, char, int, int, int, double, int, OFF_MAT, int, int, OFF_MAT, int, double, int, OFF_MAT, int)",
+            "download_lda_cpy(int, int, int, int, int, double*, OFF_MAT)",
+            "upload_lda_cpy(int, int, int, int, double const*, int, OFF_MAT)",
+            "offload_sparse_rw(int, int, int, double*, int, int*, OFF_MAT, char)", "alloc_A(long, double*)", "alloc_L(long)",
+            "alloc_U(long)", "alloc_transfer(long)", "free_offload_A()", "free_offload_L()", "free_offload_U()",
+            "free_offload_transfer()"]
+    for w in want:
+        assert w in out, f"{w} not exported by libcandmc_lu_offload.so"
+    # and the header that mirrors the reference interface declares the same names
+    hdr = open(os.path.join(ROOT, "include", "candmc", "lu_offload.h")).read()
+    for w in want:
+        assert w.split("(")[0] in hdr
+
+
+def test_lu_offload_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU box")
+    import candmc_b200 as cb
+    from candmc_b200 import lu_offload as lo
+
+    with pytest.raises(cb.CandmcError) as e:
+        lo.alloc_L(16)
+    assert e.value.code == 5

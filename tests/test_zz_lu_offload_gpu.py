@@ -1,0 +1,80 @@
+"""GPU tests of the LU accelerator seam (candmc_off_* / candmc_b200.lu_offload / libcandmc_lu_offload.so).
+
+STATUS: this path was written after the round's GPU budget was spent; it has been compiled for sm_100a and its checker is
+pinned to the reference (tests/test_lu_offload_oracle.py), but these tests have not yet run on a B200.  They are therefore
+marked xfail(strict=False) — they report XPASS when the path is right, never mask a failure of the validated suite, and run
+every case in its own process (a CUDA fault cannot poison the session).  The marker goes away once a round has seen them
+pass.  The file name sorts last on purpose.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = np.load(os.path.join(HERE, "golden", "lu_offload_ref_outputs.npz"))
+NAMES = sorted(k[: -len("__script")] for k in GOLD.files if k.endswith("__script"))
+PENDING = pytest.mark.xfail(strict=False, reason="LU offload seam: first B200 run pending (written after the GPU budget was spent)")
+
+
+def _worker(*args, timeout=300):
+    p = subprocess.run([sys.executable, os.path.join(HERE, "off_worker.py"), *map(str, args)], capture_output=True,
+                       text=True, timeout=timeout, cwd=ROOT)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    return json.loads(p.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.gpu
+@PENDING
+@pytest.mark.parametrize("overlap", [0, 1])
+@pytest.mark.parametrize("name", NAMES)
+def test_script_parity_with_reference_outputs(name, overlap):
+    """same scripts, same data as the golden vectors produced by the unmodified lu_offload.cxx: copies bit-exact
+    (sentinel padding untouched), GEMM-touched elements within 1e-12 absolute (k <= 64, |values| <= 0.5)"""
+    r = _worker("script", name, overlap)
+    assert r["padding_untouched"]
+    assert r["max_abs_vs_reference"] <= 1e-12 and r["max_abs_vs_oracle"] <= 1e-12
+    assert r["exact_fraction"] > 0.5
+    assert r["launches"] > 0  # our kernels ran (GEMMs, sparse row kernels)
+    if not overlap:
+        assert r["stats"]["cross_stream_waits"] == 0
+
+
+@pytest.mark.gpu
+@PENDING
+@pytest.mark.parametrize("n,k,overlap", [(1024, 128, 1), (4096, 256, 1), (4096, 256, 0), (2050, 130, 1)])
+def test_trailing_update_pattern_at_size(n, k, overlap):
+    """LU step at a size the oracle cannot do in seconds: numpy float64 is the checker, bound 10*k*eps (rel. Frobenius)"""
+    r = _worker("trailing", n, k, overlap, timeout=600)
+    assert r["first_block_exact"]
+    assert r["rel_frobenius"] <= r["bound"] and r["panel_rel"] <= r["bound"] and r["rows_rel"] <= r["bound"]
+    if overlap:
+        # the download of the untouched block column did not have to wait for the GEMM; the later ones did
+        assert r["waits_after_independent_download"] == 0
+        assert r["stats"]["cross_stream_waits"] >= 1
+
+
+def _lu_dropin(exe, *args):
+    path = os.path.join(ROOT, "oracle", "_ref", "dropin", exe)
+    run = os.path.join(ROOT, "oracle", "_ref", "mpirun")
+    if not (os.path.exists(path) and os.path.exists(run)):
+        pytest.skip("LU drop-in binaries not built (needs /root/reference at build time)")
+    p = subprocess.run([run, "-np", "4", "-timeout", "300", path, *args], capture_output=True, text=True, timeout=400,
+                       cwd=ROOT)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return p.stdout
+
+
+@pytest.mark.gpu
+@PENDING
+@pytest.mark.parametrize("exe", ["lu_pp_gpu", "lu_tp_gpu"])
+@pytest.mark.parametrize("args", [["-n", "256", "-b_sm", "8", "-b_lrg", "32"], ["-n", "1024", "-b_sm", "32", "-b_lrg", "128"]])
+def test_reference_lu_unit_test_passes_with_gpu_offload(exe, args):
+    """the reference's own 2.5D LU test (test/LU/lu_25d_pvt_unit_test.cxx, unmodified, -DOFFLOAD -DOFFLOAD_FAT_GEMM) with its
+    sixteen offload calls served by libcandmc_lu_offload.so; 4 ranks (mini-MPI processes) share the visible GPUs"""
+    out = _lu_dropin(exe, *args)
+    assert "test passed" in out and "test failed" not in out.lower()

@@ -283,7 +283,6 @@ using namespace candmc;
 extern "C" {
 
 int candmc_off_set_device(int rank) {
-  CANDMC_CHECK(!g_off.ready, "set_mic_rank: the offload runtime is already bound to a device");
   CANDMC_CHECK(rank >= 0, "set_mic_rank: negative rank");
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -293,6 +292,8 @@ int candmc_off_set_device(int rank) {
     return ERR_NODEVICE;
   }
   if (runtime().initialized) {
+    // the reference calls this at the top of every factorisation (lu_25d_pvt.cxx:1569): repeating the binding is fine,
+    // changing it is not (the offloaded matrices live on the bound device)
     CANDMC_CHECK(runtime().device == rank % count, "set_mic_rank: the library is already bound to device %d",
                  runtime().device);
     return OK;
@@ -383,10 +384,13 @@ int candmc_off_host_mirror(int mat, double** out) {
       return ERR_NOMEM;
     }
   }
-  // hand the caller the CURRENT contents (all queued work on the matrix finishes first) ...
-  CANDMC_CUDA(cudaStreamSynchronize(g_off.gemm_stream));
-  CANDMC_CUDA(cudaMemcpyAsync(m.mirror, m.dev, sizeof(double) * m.size, cudaMemcpyDeviceToHost, xfer_stream()));
-  CANDMC_CUDA(cudaStreamSynchronize(xfer_stream()));
+  // hand the caller the CURRENT contents (all queued work on the matrix finishes first); if the mirror already holds
+  // writes that have not been pushed yet, it IS the current contents
+  if (!m.mirror_dirty) {
+    CANDMC_CUDA(cudaStreamSynchronize(g_off.gemm_stream));
+    CANDMC_CUDA(cudaMemcpyAsync(m.mirror, m.dev, sizeof(double) * m.size, cudaMemcpyDeviceToHost, xfer_stream()));
+    CANDMC_CUDA(cudaStreamSynchronize(xfer_stream()));
+  }
   // ... and assume it writes them: the mirror goes back to HBM before the next operation on this matrix
   m.mirror_dirty = true;
   *out = m.mirror;

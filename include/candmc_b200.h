@@ -214,7 +214,7 @@ int candmc_off_free(int mat);
 int candmc_off_alloc_transfer(int64_t size);
 int candmc_off_free_transfer(void);
 /* Device pointer and size of `mat`: what get_mat_handle returns ON the accelerator (lu_offload.cxx:159-175).  The pointer
- * can be handed to candmc_dgemm / candmc_d25_summa etc.; call candmc_off_sync first. */
+ * can be handed to candmc_dgemm / candmc_d25_summa etc.; call candmc_off_sync before using it on another stream. */
 int candmc_off_device_ptr(int mat, double** out, int64_t* size);
 /* Allocated size of `mat` in doubles. */
 int candmc_off_size(int mat, int64_t* size);

@@ -244,6 +244,8 @@ def _edge_cases(seed: int) -> str:
     L.append("gemm N N 32 32 0 1.0 0 1 32 0 2 1 0.25 0 0 64")
     L.append("gemm N N 64 16 64 1.0 0 0 64 0 1 64 0.0 0 2 64")   # A as an INPUT, U as the output
     L.append("down 64 16 64 64 0 2")
+    L.append("gemm N N 16 16 16 1.0 0 1 16 256 1 16 1.0 3301 0 16")  # aligned inputs (tensor path), odd C offset
+    L.append("down 16 16 16 16 3301 0")
     # back-to-back GEMMs into the same block without wait (in-order on the device)
     L.append("gemm N N 8 8 8 1.0 0 1 8 64 1 8 1.0 3000 0 8")
     L.append("gemm N N 8 8 8 1.0 128 1 8 192 1 8 1.0 3000 0 8")

@@ -165,6 +165,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timeline", action="store_true", help="print rank 0's per-launch GEMM timeline to stderr")
     ap.add_argument("--bg-ctas", type=int, default=None, help="CTA cap of the overlapped-traffic communicators")
+    ap.add_argument("--fused-reduce", type=int, default=None, choices=[0, 1, 2],
+                    help="depth sum: 0 NCCL, 1 fused on 1x1xc (default), 2 fused on q x q x c too (experimental)")
+    ap.add_argument("--skip-unused-uploads", action="store_true",
+                    help="e2e leg: do not upload blocks a layer never multiplies (experimental)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -187,6 +191,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.bg_ctas is not None:
         cb.lib().candmc_set_background_ctas(args.bg_ctas)
+    if args.fused_reduce is not None:
+        cb.lib().candmc_set_fused_reduce(args.fused_reduce)
+    if args.skip_unused_uploads:
+        cb.lib().candmc_set_skip_unused_uploads(1)
     world = cb.init_world(rank, world_size, local)
     g = cb.d25_grid(world)
     n, q, c = args.n, g["q"], g["c"]
@@ -331,6 +339,10 @@ def main():
                          "launches": int(nl.value), "avg_launch_ms": tms.value / nl.value if nl.value else None,
                          "flops_per_launch": tfl.value / nl.value if nl.value else None, "traffic": None},
         }
+        knobs = {k: v for k, v in (("bg_ctas", args.bg_ctas), ("fused_reduce", args.fused_reduce),
+                                   ("skip_unused_uploads", args.skip_unused_uploads or None)) if v is not None}
+        if knobs:
+            line["config"]["knobs"] = knobs  # non-default tuning switches used for this run
         if world_size == 1 and not args.no_cpu_baseline:
             v, info = reference_cpu_run(3, 1)
             line["cpu_baseline"] = dict(info, value=v, unit="TFLOP/s")

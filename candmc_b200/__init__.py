@@ -25,6 +25,8 @@ from .mm import (  # noqa: F401
     fill_drand48,
     frob_diff,
     set_min_kchunk,
+    cyclic_to_blocked,
+    blocked_to_cyclic,
 )
 from .grid import (  # noqa: F401
     init_world,

@@ -76,6 +76,12 @@ SIGNATURES = {
     "candmc_update_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, C.POINTER(PView), pd, i64, C.c_int, C.c_void_p]),
     "candmc_set_min_kchunk": (C.c_int, [i64]),
     "candmc_set_host_pipeline_min": (C.c_int, [i64]),
+    "candmc_redistribute": (C.c_int, [C.c_int, i64, i64, i64, pd, i64, pd, i64, C.POINTER(PView), C.c_void_p]),
+    "candmc_redist_axis_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, i64, C.c_int] + [C.POINTER(C.c_int)] * 4),
+    "candmc_redist_strided_index": (C.c_int, [C.c_int, C.c_int, C.c_int, i64, C.c_int, C.c_int, i64, C.c_int, i64, i64,
+                                              C.POINTER(i64), C.POINTER(C.c_int)]),
+    "candmc_debug_redist_permute": (C.c_int, [C.c_int, C.c_int, C.c_int, i64, C.c_int, C.c_int, C.c_int, pd, i64, pd, i64,
+                                              i64, C.c_void_p]),
     # accelerator seam of the 2.5D LU (alg/LU/lu_offload.h)
     "candmc_off_set_device": (C.c_int, [C.c_int]),
     "candmc_off_alloc": (C.c_int, [C.c_int, i64, pd]),

@@ -455,7 +455,6 @@ int candmc_off_upload(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, 
   cudaStream_t s = xfer_stream();
   if (is_device_ptr(A)) {
     CANDMC_TRY(lda_copy_f64(nrow, ncol, lda_A, lda_B, A, d, s));
-    ++runtime().launches;
   } else if ((lda_A == nrow && lda_B == nrow) || ncol == 1) {
     CANDMC_CUDA(cudaMemcpyAsync(d, A, sizeof(double) * nrow * ncol, cudaMemcpyHostToDevice, s));
   } else {
@@ -479,7 +478,6 @@ int candmc_off_download(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B
   cudaStream_t s = xfer_stream();
   if (is_device_ptr(B)) {
     CANDMC_TRY(lda_copy_f64(nrow, ncol, lda_A, lda_B, d, B, s));
-    ++runtime().launches;
   } else if ((lda_A == nrow && lda_B == nrow) || ncol == 1) {
     CANDMC_CUDA(cudaMemcpyAsync(B, d, sizeof(double) * nrow * ncol, cudaMemcpyDeviceToHost, s));
   } else {

@@ -178,3 +178,16 @@ def update_A(Y, lda_Y, A, lda_A, m, k, b, W, pv: pview, aggreg_Y=None, lda_aY=0,
     cpv = _lib.PView(pv.rrow, pv.rcol, pv.crow.cm, pv.ccol.cm, pv.cworld.cm if pv.cworld else None)
     check(lib().candmc_update_A(_ptr(Y), lda_Y, _ptr(A), lda_A, m, k, b, _ptr(W), C.byref(cpv), _ptr(aggreg_Y), lda_aY,
                                 1 if W_is_T else 0, _stream(stream)))
+
+
+def cyclic_to_blocked(m, n, nb, A_cyc, lda_cyc, A_blk, lda_blk, pv: pview, stream=None):
+    """Local piece of an m x n block-cyclic matrix (block nb, roots pv.rrow / pv.rcol: the layout of the reference's
+    QR / SE drivers, test/QR/test_qr_2d.cxx:87-94) -> the blocked layout of the CANMM multiplies."""
+    cpv = _lib.PView(pv.rrow, pv.rcol, pv.crow.cm, pv.ccol.cm, pv.cworld.cm if pv.cworld else None)
+    check(lib().candmc_redistribute(0, m, n, nb, _ptr(A_cyc), lda_cyc, _ptr(A_blk), lda_blk, C.byref(cpv), _stream(stream)))
+
+
+def blocked_to_cyclic(m, n, nb, A_blk, lda_blk, A_cyc, lda_cyc, pv: pview, stream=None):
+    """Inverse of cyclic_to_blocked."""
+    cpv = _lib.PView(pv.rrow, pv.rcol, pv.crow.cm, pv.ccol.cm, pv.cworld.cm if pv.cworld else None)
+    check(lib().candmc_redistribute(1, m, n, nb, _ptr(A_blk), lda_blk, _ptr(A_cyc), lda_cyc, C.byref(cpv), _stream(stream)))

@@ -11,6 +11,9 @@
 /* Split-dimensional Cannon's algorithm */
 #include "candmc/spcannon.h"
 
+/* block-cyclic <-> blocked layout bridge (no reference counterpart; see the header) */
+#include "candmc/redist.h"
+
 /* local multiply + packing */
 #include "candmc/lapack.h"
 #include "candmc/util.h"

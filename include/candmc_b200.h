@@ -190,6 +190,31 @@ int candmc_set_min_kchunk(int64_t min_kchunk);
  * column panels (upload of panel j+1 and download of panel j-1 under the GEMM of panel j) instead of staged whole. */
 int candmc_set_host_pipeline_min(int64_t min_n);
 
+/* ---- block-cyclic <-> blocked redistribution ------------------------------------------------
+ * Converts the local piece of an m x n matrix between the ScaLAPACK-style block-cyclic layout of the reference's QR / SE
+ * drivers (block nb, global block row I on grid row (I + pv->rrow) mod nprow at local block row I div nprow; columns
+ * likewise with rcol — test/QR/test_qr_2d.cxx:87-94, alg/QR/qr_2d/qr_2d.cxx:140-147, alg/SE/dmatrix.cxx:194-203) and the
+ * blocked layout of the CANMM multiplies (grid row i owns rows [i*m/nprow, (i+1)*m/nprow), test/MM/topo_pdgemm_unit.cxx:
+ * 250-256).  to_cyclic = 0: src is block-cyclic, dst blocked; 1: the reverse.  Both local pieces are (m/nprow) x
+ * (n/npcol), column-major, device pointers, src != dst.  Requires m % (nb*nprow) == 0 and n % (nb*npcol) == 0.
+ * pv->crow / pv->ccol are the row / column communicators (rank = my column / my row); pv->cworld is not used.
+ * Collective over both communicators; asynchronous on `stream`. */
+int candmc_redistribute(int to_cyclic, int64_t m, int64_t n, int64_t nb, const double* src, int64_t ld_src, double* dst,
+                        int64_t ld_dst, const candmc_pview_t* pv, void* stream);
+/* The redistribution's index plan on one grid axis (pure host code; exposed for the CPU-side tests).  P ranks, K blocks
+ * per rank, cyclic root `root`.  For every peer p: [lo[p], lo[p]+ccnt[p]) = my cyclic-local blocks that rank p owns in
+ * the blocked layout; first[p] + t*P (t < scnt[p]) = my blocked-local blocks that rank p owns in the cyclic layout. */
+int candmc_redist_axis_plan(int P, int me, int root, int64_t K, int nb, int* lo, int* ccnt, int* first, int* scnt);
+/* Where the kernels put element (block blk, offset w, other-axis index o) of the blocked-side matrix inside the segmented
+ * exchange buffer, and which peer's segment that is. */
+int candmc_redist_strided_index(int P, int me, int root, int64_t K, int nb, int rows_axis, int64_t blk, int w, int64_t o,
+                                int64_t other, int64_t* idx, int* peer);
+
+/* Test hook: one launch of the redistribution's permute kernel for the plan of rank `me` of `P` (no communicator), so a
+ * single GPU can stand in for every rank of an axis.  gather != 0: SEG <- X (blocked side -> segments), else X <- SEG. */
+int candmc_debug_redist_permute(int P, int me, int root, int64_t K, int nb, int rows_axis, int gather, double* X,
+                                int64_t ldx, double* SEG, int64_t rows, int64_t cols, void* stream);
+
 /* ---- accelerator seam of the 2.5D LU -------------------------------------------------------
  * The reference keeps three matrices on an accelerator, enum OFF_MAT { OFF_A, OFF_L, OFF_U } (alg/LU/lu_offload.h:19),
  * and addresses sub-blocks by (matrix, element offset, leading dimension).  Here they live in HBM.  `mat` is 0, 1, 2

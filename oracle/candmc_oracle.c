@@ -569,3 +569,35 @@ double oracle_off_value(uint64_t seed, uint64_t idx) {
   x ^= x >> 31;
   return (double)(x >> 11) * (1.0 / 9007199254740992.0) - 0.5;
 }
+
+/* ===== block-cyclic <-> blocked redistribution ========================================================================= */
+/* test/QR/test_qr_2d.cxx:87-94: global = myrow*b + (row%b) + (row/b)*b*nprow, with the root rotation of
+ * qr_2d.cxx:140-147 (the rank holding global block 0 is `root`) */
+int64_t oracle_cyclic_global_index(int64_t loc, int64_t nb, int me, int np, int root) {
+  const int mc = ((me - root) % np + np) % np;
+  return (int64_t)mc * nb + loc % nb + (loc / nb) * nb * np;
+}
+
+int oracle_redistribute(int to_cyclic, int64_t m, int64_t n, int64_t nb, int nprow, int npcol, int rrow, int rcol,
+                        double* const* in, double* const* out) {
+  if (nprow < 1 || npcol < 1 || nb < 1 || m % (nb * nprow) || n % (nb * npcol)) return -1;
+  const int64_t rows = m / nprow, cols = n / npcol;
+  for (int pc = 0; pc < npcol; pc++)
+    for (int pr = 0; pr < nprow; pr++) {
+      /* walk the CYCLIC local piece of (pr, pc); find where each element lives in the blocked layout */
+      const double* cyc_in = in[pr + pc * nprow];
+      double* cyc_out = out[pr + pc * nprow];
+      for (int64_t c = 0; c < cols; c++) {
+        const int64_t gc = oracle_cyclic_global_index(c, nb, pc, npcol, rcol);
+        const int bc = (int)(gc / cols);
+        for (int64_t r = 0; r < rows; r++) {
+          const int64_t gr = oracle_cyclic_global_index(r, nb, pr, nprow, rrow);
+          const int br = (int)(gr / rows);
+          const int64_t blk_idx = (gr % rows) + (gc % cols) * rows; /* inside blocked owner (br, bc) */
+          if (to_cyclic) cyc_out[r + c * rows] = in[br + bc * nprow][blk_idx];
+          else out[br + bc * nprow][blk_idx] = cyc_in[r + c * rows];
+        }
+      }
+    }
+  return 0;
+}

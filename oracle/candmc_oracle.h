@@ -59,6 +59,18 @@ int oracle_update_A(int nprow, int npcol, int rrow, int rcol, int64_t m, int64_t
 void oracle_update_A_extents(int nprow, int npcol, int rrow, int rcol, int myrow, int mycol, int64_t m, int64_t k,
                              int64_t b, int64_t* mb, int64_t* kb);
 
+/* ---- block-cyclic <-> blocked redistribution by the global index map, all ranks simulated.
+ * Block-cyclic: local (row, col) of grid rank (myrow, mycol) is global row ((myrow - rrow) mod nprow)*nb + row%nb +
+ * (row/nb)*nb*nprow, columns likewise — the generator of test/QR/test_qr_2d.cxx:87-94 (there rrow = rcol = 0), rotated
+ * roots as in qr_2d.cxx:140-147 / dmatrix.cxx:194-203.  Blocked: global row myrow*(m/nprow) + row
+ * (test/MM/topo_pdgemm_unit.cxx:250-256).  in/out[myrow + mycol*nprow] are the (m/nprow) x (n/npcol) local pieces, ld = m/nprow.
+ * There is no reference routine that performs this conversion (the reference never mixes the two layouts), so this
+ * restatement pins the LAYOUT DEFINITIONS only; see tests/test_redist.py. */
+int oracle_redistribute(int to_cyclic, int64_t m, int64_t n, int64_t nb, int nprow, int npcol, int rrow, int rcol,
+                        double* const* in, double* const* out);
+/* global row (or column) index of local index `loc` on grid coordinate `me` of `np` in the block-cyclic layout */
+int64_t oracle_cyclic_global_index(int64_t loc, int64_t nb, int me, int np, int root);
+
 /* ---- accelerator seam of the 2.5D LU: restatement of the reference's HOST FALLBACK of
  * alg/LU/lu_offload.cxx (the #else branches: three host arrays, lda_cpy and cdgemm on them).  `mat` is 0/1/2 for
  * OFF_A/OFF_L/OFF_U (lu_offload.h:19).  Pinned by tests/golden (oracle/ref_off_dump.cxx runs the same scripts through the

@@ -1,0 +1,57 @@
+"""GPU tests of the block-cyclic <-> blocked redistribution (candmc_redistribute).
+
+STATUS: written after the round's GPU budget was spent — compiled for sm_100a, index plan and two-exchange algorithm verified
+on the CPU (tests/test_redist.py), never run on a B200.  Same policy as tests/test_zz_lu_offload_gpu.py: every case in its
+own process, xfail(strict=False) until a round has seen it pass.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+PENDING = pytest.mark.xfail(strict=False, reason="redistribution: first B200 run pending (written after the GPU budget was spent)")
+
+
+def _ngpu():
+    try:
+        import torch
+
+        return torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@PENDING
+@pytest.mark.parametrize("case", [(24, 36, 2, 2, 3, 0, 0), (36, 24, 3, 3, 2, 1, 1), (30, 30, 5, 3, 3, 0, 2),
+                                  (16, 16, 4, 1, 4, 0, 3), (2048, 1024, 64, 2, 2, 1, 0), (8192, 8192, 128, 2, 2, 0, 0)])
+def test_kernels_play_every_rank_on_one_gpu(case):
+    """permute + pack kernels exactly as candmc_redistribute launches them, the all-to-all replaced by device copies"""
+    p = subprocess.run([sys.executable, os.path.join(HERE, "redist_worker.py"), *map(str, case)], capture_output=True,
+                       text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    r = json.loads(p.stdout.strip().splitlines()[-1])
+    assert r["to_blocked_exact"] and r["to_blocked_matches_generator"] and r["to_cyclic_exact"]
+    assert r["single_rank_identity"] and r["launches"] > 0
+
+
+@pytest.mark.gpu
+@PENDING
+@pytest.mark.parametrize("nproc", [1, 2, 4, 8])
+def test_redistribute_over_nccl(nproc):
+    if _ngpu() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    env = dict(os.environ, CANDMC_TEST_PENDING="1")
+    env.setdefault("NCCL_DEBUG", "WARN")
+    worker = os.path.join(HERE, "dist_worker.py")
+    cmd = [sys.executable, worker] if nproc == 1 else [
+        sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+        "--master-port", str(29600 + nproc), worker]
+    p = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    out = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["failed_all_ranks"] == 0 and out["checks_rank0"] > 0

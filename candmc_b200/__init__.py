@@ -25,6 +25,8 @@ from .mm import (  # noqa: F401
     fill_drand48,
     frob_diff,
     set_min_kchunk,
+    upd_Yamamoto_A,
+    update_Yamamoto_A,
     cyclic_to_blocked,
     blocked_to_cyclic,
 )

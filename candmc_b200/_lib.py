@@ -74,6 +74,8 @@ SIGNATURES = {
                                   C.c_double, pd, C.c_char, C.c_double, pd, pd, C.c_void_p]),
     "candmc_upd_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, comm_p, C.c_void_p]),
     "candmc_update_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, C.POINTER(PView), pd, i64, C.c_int, C.c_void_p]),
+    "candmc_upd_Yamamoto_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, comm_p, C.c_void_p]),
+    "candmc_update_Yamamoto_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, C.POINTER(PView), C.c_void_p]),
     "candmc_set_min_kchunk": (C.c_int, [i64]),
     "candmc_set_host_pipeline_min": (C.c_int, [i64]),
     "candmc_redistribute": (C.c_int, [C.c_int, i64, i64, i64, pd, i64, pd, i64, C.POINTER(PView), C.c_void_p]),

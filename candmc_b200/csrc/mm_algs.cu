@@ -905,10 +905,70 @@ int upd_A_impl(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t
   return OK;
 }
 
+// A <- A + Qm * (T * (Qm^T A)) on one grid column: the Yamamoto form keeps T = (Q1 - S)^-1 explicitly, so the middle step is
+// a GEMM with alpha = -1 instead of a triangular solve (qr_y2d.cxx:123-169).  W, W2: b x kb scratch each.
+int upd_Yamamoto_A_impl(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
+                        const double* T, candmc_comm* ccol, double* W, double* W2, cudaStream_t st) {
+  if (kb == 0) return OK;
+  if (mb > 0) CANDMC_TRY(gemm_f64('T', 'N', b, kb, mb, 1.0, Qm, lda_Qm, A, lda_A, 0.0, W, b, st));  // :140
+  else CANDMC_TRY(fill_f64(W, b * kb, 0.0, st));                                                      // :143
+  if (ccol != nullptr && ccol->size > 1) CANDMC_TRY(comm_allreduce(ccol, W, W, b * kb, st));          // :146
+  if (mb > 0) {
+    CANDMC_TRY(gemm_f64('N', 'N', b, kb, b, -1.0, T, b, W, b, 0.0, W2, b, st));                       // :156
+    CANDMC_TRY(gemm_f64('N', 'N', mb, kb, b, -1.0, Qm, lda_Qm, W2, b, 1.0, A, lda_A, st));            // :160
+  }
+  return OK;
+}
+
 }  // namespace
 }  // namespace candmc
 
 extern "C" {
+
+int candmc_update_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
+                             double* T, const candmc_pview_t* pv, void* stream) {
+  CANDMC_TRY(runtime_require());
+  g_events.reset();
+  CANDMC_CHECK(pv != nullptr && pv->crow != nullptr && pv->ccol != nullptr, "update_Yamamoto_A: null processor view");
+  CANDMC_CHECK(b > 0 && m >= 0 && k >= 0 && m % b == 0 && k % b == 0, "update_Yamamoto_A: m and k must be multiples of b");
+  CANDMC_CHECK(T != nullptr && is_device_ptr(Qm) && is_device_ptr(A) && is_device_ptr(T),
+               "update_Yamamoto_A: operands must be device pointers");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nprow = pv->ccol->size, npcol = pv->crow->size, myrow = pv->ccol->rank, mycol = pv->crow->rank;
+  CANDMC_CHECK(pv->rrow >= 0 && pv->rrow < nprow && pv->rcol >= 0 && pv->rcol < npcol, "update_Yamamoto_A: bad root row/col");
+  // block-cyclic local extents of the remaining matrix, qr_y2d.cxx:81-88 (same formulas as update_A)
+  int64_t mb = (m / b) / nprow;
+  if ((myrow + nprow - pv->rrow) % nprow < (m / b) % nprow) mb++;
+  mb *= b;
+  int64_t kb = (k / b) / npcol;
+  if ((mycol + npcol - pv->rcol - 1) % npcol < (k / b) % npcol) kb++;
+  kb *= b;
+  CANDMC_CHECK(mb == 0 || mycol != pv->rcol || (Qm != nullptr && lda_Qm >= mb),
+               "update_Yamamoto_A: the root column needs its Qm panel (lda_Qm >= %lld)", (long long)mb);
+  void* wsv = nullptr;
+  CANDMC_TRY(workspace_get(sizeof(double) * (mb * b + 2 * b * kb + 8), &wsv));
+  double* Qbuf = static_cast<double*>(wsv);
+  double* W = Qbuf + mb * b + (mb * b & 1);
+  double* W2 = W + b * kb;
+  // packed panel on the root column (:101-106), MPI_Bcast of the panel and of T along the grid row (:109-113)
+  if (mycol == pv->rcol && mb > 0) CANDMC_TRY(lda_copy_f64(mb, b, lda_Qm, mb, Qm, Qbuf, st));
+  if (mb > 0) CANDMC_TRY(comm_bcast(pv->crow, Qbuf, Qbuf, mb * b, pv->rcol, st));
+  CANDMC_TRY(comm_bcast(pv->crow, T, T, b * b, pv->rcol, st));
+  return upd_Yamamoto_A_impl(Qbuf, mb, A, lda_A, mb, kb, b, T, pv->ccol, W, W2, st);
+}
+
+int candmc_upd_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
+                          const double* T, candmc_comm_t* ccol, void* stream) {
+  CANDMC_TRY(runtime_require());
+  g_events.reset();
+  CANDMC_CHECK(mb >= 0 && kb >= 0 && b > 0, "upd_Yamamoto_A: bad extents");
+  CANDMC_CHECK(is_device_ptr(Qm) && is_device_ptr(A) && is_device_ptr(T), "upd_Yamamoto_A: operands must be device pointers");
+  if (kb == 0) return OK;
+  void* wsv = nullptr;
+  CANDMC_TRY(workspace_get(sizeof(double) * 2 * b * kb, &wsv));
+  double* W = static_cast<double*>(wsv);
+  return upd_Yamamoto_A_impl(Qm, lda_Qm, A, lda_A, mb, kb, b, T, ccol, W, W + b * kb, static_cast<cudaStream_t>(stream));
+}
 
 int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
                     const double* W, const candmc_pview_t* pv, double* aggreg_Y, int64_t lda_aY, int W_is_T,

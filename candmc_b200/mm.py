@@ -180,6 +180,20 @@ def update_A(Y, lda_Y, A, lda_A, m, k, b, W, pv: pview, aggreg_Y=None, lda_aY=0,
                                 1 if W_is_T else 0, _stream(stream)))
 
 
+def upd_Yamamoto_A(Qm, lda_Qm, A, lda_A, mb, kb, b, T, ccol: CommData_t | None = None, stream=None):
+    """upd_Yamamoto_A (alg/QR/qr_2d/qr_y2d.cxx:123-169): A <- A + Qm (T (Qm^T A)) summed over one grid column."""
+    check(lib().candmc_upd_Yamamoto_A(_ptr(Qm), lda_Qm, _ptr(A), lda_A, mb, kb, b, _ptr(T), ccol.cm if ccol else None,
+                                      _stream(stream)))
+
+
+def update_Yamamoto_A(Qm, lda_Qm, A, lda_A, m, k, b, T, pv: pview, agg=None, stream=None):
+    """update_Yamamoto_A (alg/QR/qr_2d/qr_y2d.h:59-68) with agg == NULL; T is broadcast along the grid row in place."""
+    if agg is not None:
+        raise NotImplementedError("the aggregator (qr_y2d.cxx:12-66) is host-side bookkeeping of the reference's drivers")
+    cpv = _lib.PView(pv.rrow, pv.rcol, pv.crow.cm, pv.ccol.cm, pv.cworld.cm if pv.cworld else None)
+    check(lib().candmc_update_Yamamoto_A(_ptr(Qm), lda_Qm, _ptr(A), lda_A, m, k, b, _ptr(T), C.byref(cpv), _stream(stream)))
+
+
 def cyclic_to_blocked(m, n, nb, A_cyc, lda_cyc, A_blk, lda_blk, pv: pview, stream=None):
     """Local piece of an m x n block-cyclic matrix (block nb, roots pv.rrow / pv.rcol: the layout of the reference's
     QR / SE drivers, test/QR/test_qr_2d.cxx:87-94) -> the blocked layout of the CANMM multiplies."""

@@ -182,6 +182,16 @@ typedef struct candmc_pview {
 int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
                     const double* W, const candmc_pview_t* pv, double* aggreg_Y, int64_t lda_aY, int W_is_T,
                     void* stream);
+/* Yamamoto form of the CAQR trailing update, A <- A + Qm * (T * (Qm^T A)) with T = (Q1 - S)^-1 kept explicitly.
+ * candmc_upd_Yamamoto_A replaces upd_Yamamoto_A (alg/QR/qr_2d/qr_y2d.cxx:123-169): cdgemm('T','N') :140, MPI_Allreduce over
+ * ccol :146, cdgemm('N','N', alpha=-1) with the b x b T (ld = b) :156, cdgemm('N','N', alpha=-1, beta=1) :160.
+ * candmc_update_Yamamoto_A replaces update_Yamamoto_A (:68-120) with agg == NULL: block-cyclic local extents (:81-88), the
+ * root column's panel packed and MPI_Bcast along the grid row (:101-110), T MPI_Bcast along the grid row IN PLACE (:112,
+ * so T is an output on the other columns), then the update.  Device pointers; Qm is read on the root column only. */
+int candmc_upd_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
+                          const double* T, candmc_comm_t* ccol, void* stream);
+int candmc_update_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
+                             double* T, const candmc_pview_t* pv, void* stream);
 /* Tuning: the SUMMA pipeline cuts each b-wide panel into up to 8 k-chunks of at least this many columns
  * (default 1024) so the broadcast of chunk t+1 runs under the GEMM of chunk t.  Tests lower it to exercise the
  * chunked path on small matrices. */

@@ -484,6 +484,39 @@ int oracle_update_A(int nprow, int npcol, int rrow, int rcol, int64_t m, int64_t
   return 0;
 }
 
+/* update_Yamamoto_A / upd_Yamamoto_A, qr_y2d.cxx:68-169: per grid column W = sum_rows Qm^T A (:140,146), W2 = -T W (:156),
+ * A -= Qm W2 (:160); the panel and T are those of the root column (MPI_Bcast :109-112) */
+int oracle_update_Yamamoto_A(int nprow, int npcol, int rrow, int rcol, int64_t m, int64_t k, int64_t b, double* const* Qm,
+                             double* const* A, const double* T) {
+  if (nprow <= 0 || npcol <= 0 || b <= 0 || m % b || k % b) return -1;
+  for (int pc = 0; pc < npcol; ++pc) {
+    int64_t mb0, kb;
+    oracle_update_A_extents(nprow, npcol, rrow, rcol, 0, pc, m, k, b, &mb0, &kb);
+    if (kb == 0) continue;
+    double* W = dalloc((size_t)(b * kb));
+    double* Wr = dalloc((size_t)(b * kb));
+    double* W2 = dalloc((size_t)(b * kb));
+    for (int pr = 0; pr < nprow; ++pr) {
+      int64_t mb, kb2;
+      oracle_update_A_extents(nprow, npcol, rrow, rcol, pr, pc, m, k, b, &mb, &kb2);
+      if (mb == 0) continue;
+      oracle_dgemm('T', 'N', b, kb, mb, 1.0, Qm[pr + rcol * nprow], mb, A[pr + pc * nprow], mb, 0.0, Wr, b);
+      for (int64_t e = 0; e < b * kb; ++e) W[e] += Wr[e];
+    }
+    oracle_dgemm('N', 'N', b, kb, b, -1.0, T, b, W, b, 0.0, W2, b);
+    for (int pr = 0; pr < nprow; ++pr) {
+      int64_t mb, kb2;
+      oracle_update_A_extents(nprow, npcol, rrow, rcol, pr, pc, m, k, b, &mb, &kb2);
+      if (mb == 0) continue;
+      oracle_dgemm('N', 'N', mb, kb, b, -1.0, Qm[pr + rcol * nprow], mb, W2, b, 1.0, A[pr + pc * nprow], mb);
+    }
+    free(W);
+    free(Wr);
+    free(W2);
+  }
+  return 0;
+}
+
 /* ===== LU accelerator seam: host-fallback semantics of alg/LU/lu_offload.cxx ======================================== */
 void oracle_off_init(oracle_off_t* o) { memset(o, 0, sizeof(*o)); }
 

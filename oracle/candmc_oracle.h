@@ -56,6 +56,11 @@ int oracle_upd_A(int nprow, const int64_t* mb, int64_t kb, int64_t b, double* co
  * qr_2d.cxx:22-60); mode 1: W is the b x b lower-triangular T (W_is_T).  mb_out/kb_out (may be NULL) receive the extents. */
 int oracle_update_A(int nprow, int npcol, int rrow, int rcol, int64_t m, int64_t k, int64_t b, double* const* Y,
                     double* const* A, const double* W, int mode, int64_t* mb_out, int64_t* kb_out);
+/* update_Yamamoto_A with agg == NULL (alg/QR/qr_2d/qr_y2d.cxx:68-169) on the same grid / layout conventions as
+ * oracle_update_A: Qm[r] = the root column's local mb x b panels, T = the root column's b x b matrix (every column uses it
+ * after the MPI_Bcast of :112).  A_r <- A_r + Qm_r * (T * sum_rows(Qm^T A)). */
+int oracle_update_Yamamoto_A(int nprow, int npcol, int rrow, int rcol, int64_t m, int64_t k, int64_t b, double* const* Qm,
+                             double* const* A, const double* T);
 void oracle_update_A_extents(int nprow, int npcol, int rrow, int rcol, int myrow, int mycol, int64_t m, int64_t k,
                              int64_t b, int64_t* mb, int64_t* kb);
 

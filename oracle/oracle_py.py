@@ -51,6 +51,7 @@ def lib() -> C.CDLL:
                                    C.POINTER(_i64), _pd]
         L.oracle_update_A.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _i64, _i64, _i64, _ppd, _ppd, _pd, C.c_int,
                                       C.POINTER(_i64), C.POINTER(_i64)]
+        L.oracle_update_Yamamoto_A.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _i64, _i64, _i64, _ppd, _ppd, _pd]
         L.oracle_update_A_extents.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i64, _i64, _i64,
                                               C.POINTER(_i64), C.POINTER(_i64)]
         _LIB = L
@@ -231,3 +232,20 @@ def update_A(nprow, npcol, rrow, rcol, m, k, b, Y, A, W=None):
     rc = lib().oracle_update_A(nprow, npcol, rrow, rcol, m, k, b, _pp(Yp), _pp(Ap),
                                _p(W) if W is not None else None, 0 if W is None else 1, None, None)
     assert rc == 0, "oracle_update_A: bad arguments"
+
+
+def yamamoto_T(b):
+    """The b x b T of oracle/ref_dump.cxx's `updy` mode (a generic dense matrix: the update never assumes structure)."""
+    T = np.zeros((b, b), order="F")
+    for j in range(b):
+        for i in range(b):
+            T[i, j] = (_lcg48(555000 + i + j * b) - .5) * 0.5
+    return T
+
+
+def update_Yamamoto_A(nprow, npcol, rrow, rcol, m, k, b, Qm, A, T):
+    """All ranks simulated; A blocks are updated in place (alg/QR/qr_2d/qr_y2d.cxx:68-169, agg == NULL)."""
+    Qp = [q if q.size else np.zeros(1) for q in Qm]
+    Ap = [a if a.size else np.zeros(1) for a in A]
+    rc = lib().oracle_update_Yamamoto_A(nprow, npcol, rrow, rcol, m, k, b, _pp(Qp), _pp(Ap), _p(T))
+    assert rc == 0, "oracle_update_Yamamoto_A: bad arguments"

@@ -8,6 +8,7 @@
 //   ref_dump summa <n> <prefix>                         summa                      (grid + data: :349-486, ctb_unit)
 //   ref_dump dcn   <n> <x2_np> <ovp> <prefix>           bcast_cannon_4d            (grid + data: :13-175, dcn_unit); x2_np must be 1
 //   ref_dump upda  <m> <k> <b> <nprow> <rrow> <rcol> <prefix>   update_A, W == NULL (alg/QR/qr_2d/qr_2d.cxx:124-177)
+//   ref_dump updy  <m> <k> <b> <nprow> <rrow> <rcol> <prefix>   update_Yamamoto_A, agg == NULL (alg/QR/qr_2d/qr_y2d.cxx:68-120)
 //   ref_dump spc   <bidir> <ndim> <seed> <n> <m> <k> <alpha> <beta> <tB N|T> <prefix>   kput_cannon / kuni_cannon (test/MM/test_spc.cxx:36-114)
 #include <assert.h>
 #include <math.h>
@@ -212,6 +213,51 @@ static int run_upda(int myRank, int numPes, int64_t m, int64_t k, int64_t b, int
   return 0;
 }
 
+// update_Yamamoto_A (alg/QR/qr_2d/qr_y2d.cxx:68-120) with agg == NULL, same grid, layout and element seeds as run_upda.  T is
+// a generic dense b x b matrix on the root column; the other columns start with zeros and must receive it (:112).
+static int run_updy(int myRank, int numPes, int64_t m, int64_t k, int64_t b, int nprow, int rrow, int rcol,
+                    const char* prefix) {
+  const int npcol = numPes / nprow;
+  if (nprow * npcol != numPes || m % b || k % b) return 2;
+  const int myrow = myRank % nprow, mycol = myRank / nprow;
+  CommData_t cdt_glb, cdt_row, cdt_col;
+  SET_COMM(MPI_COMM_WORLD, myRank, numPes, cdt_glb);
+  SETUP_SUB_COMM(cdt_glb, cdt_row, myRank / nprow, myRank % nprow, npcol);
+  SETUP_SUB_COMM(cdt_glb, cdt_col, myRank % nprow, myRank / nprow, nprow);
+  pview pv;
+  pv.rrow = rrow; pv.rcol = rcol; pv.crow = cdt_row; pv.ccol = cdt_col; pv.cworld = cdt_glb;
+  int64_t mb = (m / b) / nprow;
+  if ((myrow + nprow - rrow) % nprow < (m / b) % nprow) mb++;
+  mb *= b;
+  int64_t kb = (k / b) / npcol;
+  if ((mycol + npcol - rcol - 1) % npcol < (k / b) % npcol) kb++;
+  kb *= b;
+  double* Qm = alloc_d((size_t)(mb ? mb : 1) * b);
+  double* A = alloc_d((size_t)(mb ? mb : 1) * (kb ? kb : 1));
+  double* T = alloc_d((size_t)b * b);
+  for (int64_t j = 0; j < b; j++)
+    for (int64_t r = 0; r < mb; r++) {
+      const int64_t gr = ((r / b) * nprow + (myrow - rrow + nprow) % nprow) * b + r % b;
+      srand48(7000 + gr * b + j);
+      Qm[r + j * mb] = mycol == rcol ? (drand48() - .5) * 0.25 : 77.0;  // only the root column's panel counts
+    }
+  for (int64_t cc = 0; cc < kb; cc++)
+    for (int64_t r = 0; r < mb; r++) {
+      const int64_t gr = ((r / b) * nprow + (myrow - rrow + nprow) % nprow) * b + r % b;
+      const int64_t gc = ((cc / b) * npcol + (mycol - rcol - 1 + npcol) % npcol) * b + cc % b;
+      srand48(900000 + gc * m + gr);
+      A[r + cc * mb] = drand48() - .5;
+    }
+  for (int64_t j = 0; j < b; j++)
+    for (int64_t i = 0; i < b; i++) {
+      srand48(555000 + i + j * b);
+      T[i + j * b] = mycol == rcol ? (drand48() - .5) * 0.5 : 0.0;
+    }
+  update_Yamamoto_A(Qm, mb, A, mb, m, k, b, T, &pv, NULL);
+  dump(prefix, myRank, A, (size_t)mb * kb);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   int myRank, numPes;
   MPI_Init(&argc, &argv);
@@ -229,6 +275,9 @@ int main(int argc, char** argv) {
                  atoi(argv[7]), atof(argv[8]), atof(argv[9]), argv[10][0], argv[11]);
   else if (argc >= 9 && !strcmp(argv[1], "upda"))
     rc = run_upda(myRank, numPes, atoll(argv[2]), atoll(argv[3]), atoll(argv[4]), atoi(argv[5]), atoi(argv[6]),
+                  atoi(argv[7]), argv[8]);
+  else if (argc >= 9 && !strcmp(argv[1], "updy"))
+    rc = run_updy(myRank, numPes, atoll(argv[2]), atoll(argv[3]), atoll(argv[4]), atoi(argv[5]), atoi(argv[6]),
                   atoi(argv[7]), argv[8]);
   else if (myRank == 0)
     fprintf(stderr, "usage: see the header of oracle/ref_dump.cxx\n");

@@ -243,9 +243,48 @@ def case_redistribute(world, name, m, n, nb, nprow, rrow, rcol, pad=0):
     return ok
 
 
-def pending_cases(world):
+def case_update_Yamamoto_A(world, golden, name, m, k, b, nprow, rrow, rcol):
+    """update_Yamamoto_A vs the reference's own outputs (tests/golden `updy_*`) and the oracle; as in the
+    fixture's run, only the root column starts with the panel and T."""
+    P = world.np
+    npcol = P // nprow
+    myrow, mycol = world.rank % nprow, world.rank // nprow
+    crow = cb.setup_sub_comm(world, mycol, myrow, npcol)
+    ccol = cb.setup_sub_comm(world, myrow, mycol, nprow)
+    Qm, A = orc.update_A_blocks(nprow, npcol, rrow, rcol, m, k, b)
+    T = orc.yamamoto_T(b)
+    mb, kb = orc.update_A_extents(nprow, npcol, rrow, rcol, myrow, mycol, m, k, b)
+    lda_Q = max(mb, 1) + 2
+    Qp = np.full((lda_Q, b), 77.0, order="F")
+    if mycol == rcol:
+        Qp[:mb] = Qm[world.rank]
+    dQ = dev(Qp)
+    dA = dev(A[world.rank]) if A[world.rank].size else torch.zeros(1, dtype=torch.float64, device="cuda")
+    dT = dev(T if mycol == rcol else np.zeros((b, b), order="F"))
+    pv = cb.pview(rrow, rcol, crow, ccol, world)
+    cb.update_Yamamoto_A(dQ, lda_Q, dA, max(mb, 1), m, k, b, dT, pv)
+    torch.cuda.synchronize()
+    ok = record(f"{name}:T_bcast", 0.0 if np.array_equal(host(dT, b, b), T) else 1.0, 0.5)
+    got = host(dA, mb, kb) if (mb and kb) else np.zeros((mb, kb))
+    orc.update_Yamamoto_A(nprow, npcol, rrow, rcol, m, k, b, Qm, A, T)
+    if mb and kb:
+        ok &= record(f"{name}:oracle", rel_frob(got, A[world.rank]), 10 * m * EPS)
+        if f"{name}.r{world.rank}" in golden:
+            ok &= record(f"{name}:golden", rel_frob(got, golden[f"{name}.r{world.rank}"]), 10 * m * EPS)
+    crow.free(); ccol.free()
+    return ok
+
+
+def pending_cases(world, golden):
     """Paths that have not run on a B200 yet (tests/test_zz_redist_gpu.py runs these apart from the validated suite)."""
     P = world.np
+    if P == 1:
+        case_update_Yamamoto_A(world, golden, "updy_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0)
+        case_update_Yamamoto_A(world, golden, "updy_big_1x1", 1024, 512, 128, 1, 0, 0)
+    if P == 4:
+        case_update_Yamamoto_A(world, golden, "updy_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 0, 0)
+        case_update_Yamamoto_A(world, golden, "updy_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 2, 0)
+        case_update_Yamamoto_A(world, golden, "updy_big_2x2_r11", 1024, 768, 64, 2, 1, 1)
     shapes = {1: [(1,)], 2: [(2,), (1,)], 4: [(2,), (4,), (1,)], 8: [(2,), (4,)]}.get(P, [])
     for (nprow,) in shapes:
         npcol = P // nprow
@@ -299,7 +338,7 @@ def main():
     P = world_size
     only_pending = os.environ.get("CANDMC_TEST_PENDING") == "1"
     if only_pending:
-        pending_cases(world)
+        pending_cases(world, golden)
     for min_kc in (() if only_pending else (1024, 8)):   # default (whole panels at these sizes) and a tiny chunk to exercise the k-chunk pipeline
         cb.set_min_kchunk(min_kc)
         tag = f"kc{min_kc}"

@@ -188,3 +188,20 @@ def test_oracle_update_A_matches_reference(golden, name, m, k, b, nprow, npcol, 
         assert A[r].size == ref.size, (name, r)
         if ref.size:
             assert rel_frob(A[r], ref) <= 10 * m * EPS, (name, r)
+
+
+UPDY = [("updy_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 2, 0, 0), ("updy_m80_k48_b8_2x3_r12", 80, 48, 8, 2, 3, 1, 2),
+        ("updy_m64_k32_b16_1x1", 64, 32, 16, 1, 1, 0, 0), ("updy_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 1, 2, 0)]
+
+
+@pytest.mark.parametrize("name,m,k,b,nprow,npcol,rrow,rcol", UPDY)
+def test_oracle_update_Yamamoto_A_matches_reference(golden, name, m, k, b, nprow, npcol, rrow, rcol):
+    """the reference's own update_Yamamoto_A (alg/QR/qr_2d/qr_y2d.cxx:68-120, agg == NULL); in the fixture's
+    run only the root column holds the panel and T, the other columns must receive both."""
+    Qm, A = orc.update_A_blocks(nprow, npcol, rrow, rcol, m, k, b)
+    orc.update_Yamamoto_A(nprow, npcol, rrow, rcol, m, k, b, Qm, A, orc.yamamoto_T(b))
+    for r in range(nprow * npcol):
+        ref = golden[f"{name}.r{r}"]
+        assert A[r].size == ref.size, (name, r)
+        if ref.size:
+            assert rel_frob(A[r], ref) <= 10 * m * EPS, (name, r)

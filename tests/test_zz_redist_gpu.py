@@ -1,4 +1,5 @@
-"""GPU tests of the block-cyclic <-> blocked redistribution (candmc_redistribute).
+"""GPU tests of the block-cyclic <-> blocked redistribution (candmc_redistribute) and of the Yamamoto form
+of the CAQR trailing update (N1, candmc_update_Yamamoto_A).
 
 STATUS: written after the round's GPU budget was spent — compiled for sm_100a, index plan and two-exchange algorithm verified
 on the CPU (tests/test_redist.py), never run on a B200.  Same policy as tests/test_zz_lu_offload_gpu.py: every case in its
@@ -42,7 +43,9 @@ def test_kernels_play_every_rank_on_one_gpu(case):
 @pytest.mark.gpu
 @PENDING
 @pytest.mark.parametrize("nproc", [1, 2, 4, 8])
-def test_redistribute_over_nccl(nproc):
+def test_pending_distributed_cases(nproc):
+    """tests/dist_worker.py's pending group: candmc_redistribute over NCCL (every grid shape the world size allows) and
+    update_Yamamoto_A against the reference's own outputs"""
     if _ngpu() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
     env = dict(os.environ, CANDMC_TEST_PENDING="1")

@@ -5,7 +5,10 @@
   config 5: CAQR trailing-update shape m=65536, n=8192, k=512 on 1/2/4 GPUs -> upd_A (TN GEMM, all-reduce, trsm, NN GEMM)
 Launch: python tools/bench_configs.py            (1 GPU: config 5 on a 1x1 grid)
         torchrun --nproc-per-node 4 tools/bench_configs.py
-Prints one JSON line per configuration on rank 0 (device-timed with CUDA events, max over ranks)."""
+Prints one JSON line per configuration on rank 0 (device-timed with CUDA events, max over ranks).
+`--pending` adds the SURVEY §8f widening rows that have not been measured yet: upd_Yamamoto_A at the config-5 shape, the
+redistribution's permute kernels (GB/s against the HBM copy peak) and candmc_redistribute over NCCL, and the LU seam's
+trailing-update step (GEMM + the panel download queued behind it)."""
 import json
 import os
 import sys
@@ -94,9 +97,72 @@ def main():
             ms = timed(lambda: cb.cdgemm("N", "N", n, n, n, 1.0, A, n, B, n, 0.0, Cm, n))
             report(f"config4: 1-GPU local GEMM n={n}", 2.0 * n ** 3, ms)
             del A, B, Cm
+    if "--pending" in sys.argv:
+        pending(world, rank, ws, timed, report, ccol, Y, Am, mb, kb, k)
     world.free()
     if ws > 1:
         dist.destroy_process_group()
+
+
+def pending(world, rank, ws, timed, report, ccol, Y, Am, mb, kb, k):
+    import numpy as np
+    HBM = 6456.2  # MEASURED_PEAKS.json hbm_gbs
+    # ---- N1: Yamamoto form at the config-5 shape (three GEMMs: 2*mb*kb*k twice + 2*k*k*kb) ----
+    T = torch.rand(k * k, dtype=torch.float64, device="cuda") * (1.0 / k)
+    ms = timed(lambda: cb.upd_Yamamoto_A(Y, mb, Am, mb, mb, kb, k, T, ccol))
+    report("N1: upd_Yamamoto_A m=65536 n=8192 k=512", ws * (2 * 2.0 * mb * kb * k + 2.0 * k * k * kb), ms)
+    # ---- N3: permute kernels alone (one GPU plays rank 1 of a 4-rank axis), 8192 x 8192 local piece, nb = 64 ----
+    rows = cols = 8192; nb = 64
+    X = torch.rand(rows * cols, dtype=torch.float64, device="cuda"); S = torch.empty_like(X)
+    st = torch.cuda.current_stream().cuda_stream
+    for rows_axis in (1, 0):
+        for gather in (1, 0):
+            fn = lambda: cb.lib().candmc_debug_redist_permute(4, 1, 0, rows // nb, nb, rows_axis, gather, X.data_ptr(), rows,  # noqa: E731
+                                                              S.data_ptr(), rows, cols, st)
+            ms = timed(fn, steps=10)
+            if rank == 0:
+                gbs = 16.0 * rows * cols / (ms * 1e-3) / 1e9
+                print(json.dumps({"config": f"N3: permute_blocks_kernel rows_axis={rows_axis} gather={gather} 8192x8192 nb=64",
+                                  "ms": ms, "GBps": gbs, "pct_of_hbm_copy_peak": 100 * gbs / HBM}), flush=True)
+    del X, S
+    # ---- N3: the whole redistribution over NCCL (n = 16384 * sqrt-ish grid) ----
+    nprow = {1: 1, 2: 2, 4: 2, 8: 4}[ws]; npcol = ws // nprow
+    myrow, mycol = rank % nprow, rank // nprow
+    crow = cb.setup_sub_comm(world, mycol, myrow, npcol); ccol2 = cb.setup_sub_comm(world, myrow, mycol, nprow)
+    pv = cb.pview(0, 0, crow, ccol2, world)
+    m = 8192 * nprow; n = 8192 * npcol
+    src = torch.rand(8192 * 8192, dtype=torch.float64, device="cuda"); dst = torch.empty_like(src)
+    ms = timed(lambda: cb.cyclic_to_blocked(m, n, 64, src, 8192, dst, 8192, pv))
+    if rank == 0:
+        print(json.dumps({"config": f"N3: cyclic_to_blocked {m}x{n} nb=64 on {nprow}x{npcol}", "ms": ms,
+                          "GBps_per_gpu_algorithmic": 16.0 * 8192 * 8192 / (ms * 1e-3) / 1e9}), flush=True)
+    crow.free(); ccol2.free()
+    del src, dst
+    # ---- N2: LU seam, one trailing-update step on a 16384^2 local matrix, panel width 512 ----
+    from candmc_b200 import lu_offload as lo
+    nloc, kp = 16384, 512
+    lo.alloc_A(nloc * nloc, None); lo.alloc_L(nloc * kp); lo.alloc_U(kp * nloc); lo.alloc_transfer(kp * nloc)
+    hA = np.random.rand(nloc * kp) - 0.5
+    lo.upload_lda_cpy(nloc, kp, nloc, nloc, hA, 0, lo.OFF_L); lo.upload_lda_cpy(kp, nloc, kp, kp, hA, 0, lo.OFF_U)
+    for c0 in range(0, nloc, kp):
+        lo.upload_lda_cpy(nloc, kp, nloc, nloc, hA, c0 * nloc, lo.OFF_A)
+    panel = np.empty((nloc - kp) * kp)
+    import time
+    for overlap in (1, 0):
+        lo.set_overlap(overlap)
+        best = 1e9
+        for _ in range(3):
+            lo.sync(); t0 = time.perf_counter()
+            lo.offload_gemm_A("N", "N", nloc - kp, nloc - kp, kp, -1.0, 0, lo.OFF_L, nloc, 0, lo.OFF_U, kp, 1.0, kp * nloc + kp, lo.OFF_A, nloc)
+            t_issue = time.perf_counter() - t0
+            lo.download_lda_cpy(nloc - kp, kp, nloc, nloc - kp, kp * nloc + kp, panel, lo.OFF_A)   # waits for the GEMM by itself
+            best = min(best, time.perf_counter() - t0)
+        if rank == 0:
+            fl = 2.0 * (nloc - kp) ** 2 * kp
+            print(json.dumps({"config": f"N2: LU seam step, local 16384^2, panel 512, overlap={overlap}", "ms_gemm_plus_panel_download": best * 1e3,
+                              "tflops_incl_download": fl / best / 1e12, "ms_host_blocked_issuing_gemm": t_issue * 1e3,
+                              "timing": "host wall clock around the seam calls (the download is synchronous by contract)"}), flush=True)
+    lo.free_offload_A(); lo.free_offload_L(); lo.free_offload_U(); lo.free_offload_transfer()
 
 
 if __name__ == "__main__":

@@ -3,7 +3,7 @@
 #   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh lu ncu'            (1 GPU)
 #   gpurun --gpus 4 --timeout 1200 -- 'bash tools/gpu_session.sh dist4'    (4 GPUs)
 #   gpurun --gpus 8 --timeout 1200 -- 'bash tools/gpu_session.sh dist8'    (8 GPUs)
-# Sections: lu (LU seam tests + LU bench host vs GPU), ncu (full capture at n=32768 for roofline.traffic, pack kernels),
+# Sections: lu (LU seam tests + LU bench host vs GPU), pending1 (redistribution / Yamamoto tests + their measurements), ncu (full capture at n=32768 for roofline.traffic, pack kernels),
 #           dist4 (second-pass parity cases, update_A with T), dist8 (fused depth sum on 2x2x2, skip_unused_uploads)
 set -u
 cd "$(dirname "$0")/.."
@@ -35,10 +35,23 @@ for section in "$@"; do
         -o gpurun_out/ncu_full_pack -f tools/gemm_probe pack 16384 > gpurun_out/ncu_full_pack.log 2>&1
       python tools/ncu_summary.py gpurun_out/ncu_full_pack.ncu-rep gpurun_out/ncu_full_pack.csv | tail -14
       ;;
+    pending1)
+      # redistribution / Yamamoto tests on one GPU and the not-yet-measured widening rows
+      timeout 1200 python -m pytest tests/test_zz_redist_gpu.py -m gpu -q -rA -p no:cacheprovider > gpurun_out/redist_pytest.log 2>&1
+      tail -25 gpurun_out/redist_pytest.log
+      timeout 900 python tools/bench_configs.py --pending > gpurun_out/bench_pending_1gpu.jsonl 2> gpurun_out/bench_pending_1gpu.err
+      cat gpurun_out/bench_pending_1gpu.jsonl
+      ;;
     dist4)
       CANDMC_TEST_VERBOSE=1 timeout 1100 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
         --master-port 29533 tests/dist_worker.py > gpurun_out/dist4_worker.log 2>&1
       tail -15 gpurun_out/dist4_worker.log
+      CANDMC_TEST_PENDING=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
+        --master-port 29535 tests/dist_worker.py > gpurun_out/dist4_pending.log 2>&1
+      tail -8 gpurun_out/dist4_pending.log
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29536 \
+        tools/bench_configs.py --pending > gpurun_out/bench_pending_4gpu.jsonl 2> gpurun_out/bench_pending_4gpu.err
+      cat gpurun_out/bench_pending_4gpu.jsonl
       ;;
     dist8)
       for knobs in "" "--fused-reduce 2" "--skip-unused-uploads"; do

@@ -7,10 +7,11 @@ own process, xfail(strict=False) until a round has seen it pass.
 """
 import json
 import os
-import subprocess
 import sys
 
 import pytest
+
+from pending_util import run_guarded
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -32,10 +33,9 @@ def _ngpu():
                                   (16, 16, 4, 1, 4, 0, 3), (2048, 1024, 64, 2, 2, 1, 0), (8192, 8192, 128, 2, 2, 0, 0)])
 def test_kernels_play_every_rank_on_one_gpu(case):
     """permute + pack kernels exactly as candmc_redistribute launches them, the all-to-all replaced by device copies"""
-    p = subprocess.run([sys.executable, os.path.join(HERE, "redist_worker.py"), *map(str, case)], capture_output=True,
-                       text=True, timeout=600, cwd=ROOT)
-    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
-    r = json.loads(p.stdout.strip().splitlines()[-1])
+    rc, out, err = run_guarded("redist", [sys.executable, os.path.join(HERE, "redist_worker.py"), *map(str, case)], 300, ROOT)
+    assert rc == 0, out[-2000:] + err[-3000:]
+    r = json.loads(out.strip().splitlines()[-1])
     assert r["to_blocked_exact"] and r["to_blocked_matches_generator"] and r["to_cyclic_exact"]
     assert r["single_rank_identity"] and r["launches"] > 0
 
@@ -54,7 +54,7 @@ def test_pending_distributed_cases(nproc):
     cmd = [sys.executable, worker] if nproc == 1 else [
         sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
         "--master-port", str(29600 + nproc), worker]
-    p = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
-    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    out = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    rc, so, se = run_guarded("redist", cmd, 400, ROOT, env=env)
+    assert rc == 0, so[-3000:] + se[-3000:]
+    out = json.loads([l for l in so.splitlines() if l.startswith("{")][-1])
     assert out["failed_all_ranks"] == 0 and out["checks_rank0"] > 0

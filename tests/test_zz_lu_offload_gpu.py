@@ -53,9 +53,9 @@ def test_trailing_update_pattern_at_size(n, k, overlap):
     assert r["first_block_exact"]
     assert r["rel_frobenius"] <= r["bound"] and r["panel_rel"] <= r["bound"] and r["rows_rel"] <= r["bound"]
     if overlap:
-        # the download of the untouched block column did not have to wait for the GEMM; the later ones did
+        # the download of the untouched block column never has to wait for the GEMM (whether the later ones do depends on
+        # whether the GEMM is still running when they are issued, so that count is reported, not asserted)
         assert r["waits_after_independent_download"] == 0
-        assert r["stats"]["cross_stream_waits"] >= 1
 
 
 def _lu_dropin(exe, *args):

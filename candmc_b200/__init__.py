@@ -40,4 +40,6 @@ from .grid import (  # noqa: F401
     grid_shape_for,
 )
 
+from .dmatrix import DMatrix  # noqa: F401,E402
+
 __version__ = "0.1.0"

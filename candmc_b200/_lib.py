@@ -33,6 +33,11 @@ class PView(C.Structure):
     _fields_ = [("rrow", C.c_int), ("rcol", C.c_int), ("crow", C.c_void_p), ("ccol", C.c_void_p), ("cworld", C.c_void_p)]
 
 
+class DMat(C.Structure):
+    """candmc_dmat_t: DMatrix (alg/SE/dmatrix.h:7-33) without the ScaLAPACK descriptor."""
+    _fields_ = [("nrow", i64), ("ncol", i64), ("b", i64), ("lda", i64), ("data", C.c_void_p), ("pv", PView)]
+
+
 # name -> (restype, argtypes); every symbol include/candmc_b200.h declares
 SIGNATURES = {
     "candmc_version": (C.c_int, []),
@@ -82,6 +87,15 @@ SIGNATURES = {
     "candmc_redist_axis_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, i64, C.c_int] + [C.POINTER(C.c_int)] * 4),
     "candmc_redist_strided_index": (C.c_int, [C.c_int, C.c_int, C.c_int, i64, C.c_int, C.c_int, i64, C.c_int, i64, i64,
                                               C.POINTER(i64), C.POINTER(C.c_int)]),
+    "candmc_dmat_local_extents": (C.c_int, [C.POINTER(DMat), C.POINTER(i64), C.POINTER(i64)]),
+    "candmc_dmat_slice": (C.c_int, [C.POINTER(DMat), i64, i64, i64, i64, C.POINTER(DMat)]),
+    "candmc_dmat_get_contig": (C.c_int, [C.POINTER(DMat), pd, C.c_void_p]),
+    "candmc_dmat_replicate_vertical": (C.c_int, [C.POINTER(DMat), pd, C.c_void_p]),
+    "candmc_dmat_replicate_horizontal": (C.c_int, [C.POINTER(DMat), pd, C.c_void_p]),
+    "candmc_dmat_reduce_scatter_horizontal": (C.c_int, [C.POINTER(DMat), pd, C.c_void_p]),
+    "candmc_dmat_transpose_data": (C.c_int, [C.POINTER(DMat), pd, C.c_void_p]),
+    "candmc_dmat_foldcols": (C.c_int, [C.POINTER(DMat), i64, pd, C.c_void_p]),
+    "candmc_dmat_foldrows": (C.c_int, [C.POINTER(DMat), i64, pd, C.c_void_p]),
     "candmc_debug_redist_permute": (C.c_int, [C.c_int, C.c_int, C.c_int, i64, C.c_int, C.c_int, C.c_int, pd, i64, pd, i64,
                                               i64, C.c_void_p]),
     # accelerator seam of the 2.5D LU (alg/LU/lu_offload.h)

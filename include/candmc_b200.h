@@ -220,6 +220,42 @@ int candmc_redist_axis_plan(int P, int me, int root, int64_t K, int nb, int* lo,
 int candmc_redist_strided_index(int P, int me, int root, int64_t K, int nb, int rows_axis, int64_t blk, int w, int64_t o,
                                 int64_t other, int64_t* idx, int* peer);
 
+/* ---- DMatrix pack / replication operations ----------------------------------------------------
+ * candmc_dmat_t is the reference's DMatrix (alg/SE/dmatrix.h:7-33) without its ScaLAPACK descriptor: an nrow x ncol matrix
+ * in block-cyclic layout (block b) on the grid of `pv`, whose current roots pv.rrow / pv.rcol own global block (0, 0);
+ * `data` is the DEVICE pointer to the local piece, `lda` its leading dimension.  Local extents follow dmatrix.cxx:194-203.
+ * Outputs are caller-allocated device buffers; sizes are given per call in doubles (mr x mc = the local extents). */
+typedef struct candmc_dmat {
+  int64_t nrow, ncol, b, lda;
+  double* data;
+  candmc_pview_t pv;
+} candmc_dmat_t;
+/* get_mynrow / get_myncol (dmatrix.cxx:194-203); host arithmetic only. */
+int candmc_dmat_local_extents(const candmc_dmat_t* A, int64_t* mynrow, int64_t* myncol);
+/* slice (dmatrix.cxx:367-394): the numrows x numcols sub-matrix at (firstrow, firstcol), by reference — rotated roots and a
+ * moved data pointer, no copy; host arithmetic only. */
+int candmc_dmat_slice(const candmc_dmat_t* A, int64_t firstrow, int64_t numrows, int64_t firstcol, int64_t numcols,
+                      candmc_dmat_t* out);
+/* get_contig (dmatrix.cxx:470-484): out (mr x mc, ld = mr) = the local piece. */
+int candmc_dmat_get_contig(const candmc_dmat_t* A, double* out, void* stream);
+/* replicate_vertical (dmatrix.cxx:268-289): rep (nrow * mc doubles) = the packed local pieces of the ranks of my grid
+ * column, in rank order (MPI_Allgather over ccol).  Needs (nrow / b) % nprow == 0. */
+int candmc_dmat_replicate_vertical(const candmc_dmat_t* A, double* rep, void* stream);
+/* replicate_horizontal (dmatrix.cxx:294-304): rep (ncol * mr doubles), MPI_Allgather over crow. */
+int candmc_dmat_replicate_horizontal(const candmc_dmat_t* A, double* rep, void* stream);
+/* reduce_scatter_horizontal (dmatrix.cxx:310-355): cntrb holds ncol * mr doubles = npcol chunks of mr x mc; afterwards
+ * A.data += the sum over my grid row of everyone's chunk number <my column>.  cntrb is scratch on return.  (Any npcol, any
+ * lda; the reference needs a power of two and lda == mr.  Summation order differs from the reference's butterfly.) */
+int candmc_dmat_reduce_scatter_horizontal(const candmc_dmat_t* A, double* cntrb, void* stream);
+/* transpose_data (dmatrix.cxx:252-263): out (mr x mc) = the packed local piece of my transposed grid partner, world rank
+ * crow.rank + ccol.rank * npcol (square grids, world rank = myrow + mycol * nprow as in test/QR/test_qr_2d.cxx:367-374). */
+int candmc_dmat_transpose_data(const candmc_dmat_t* A, double* out, void* stream);
+/* foldcols (dmatrix.cxx:527-552): out = the (mr/factor) x (mc*factor) local piece (ld = mr/factor) of the nrow/factor x
+ * ncol*factor matrix whose column group i holds local block rows j*factor + i.  Needs mr % (b*factor) == 0. */
+int candmc_dmat_foldcols(const candmc_dmat_t* A, int64_t factor, double* out, void* stream);
+/* foldrows (dmatrix.cxx:560-584): the inverse regrouping, out = (mr*factor) x (mc/factor), ld = mr*factor. */
+int candmc_dmat_foldrows(const candmc_dmat_t* A, int64_t factor, double* out, void* stream);
+
 /* Test hook: one launch of the redistribution's permute kernel for the plan of rank `me` of `P` (no communicator), so a
  * single GPU can stand in for every rank of an axis.  gather != 0: SEG <- X (blocked side -> segments), else X <- SEG. */
 int candmc_debug_redist_permute(int P, int me, int root, int64_t K, int nb, int rows_axis, int gather, double* X,

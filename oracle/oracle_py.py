@@ -249,3 +249,77 @@ def update_Yamamoto_A(nprow, npcol, rrow, rcol, m, k, b, Qm, A, T):
     Ap = [a if a.size else np.zeros(1) for a in A]
     rc = lib().oracle_update_Yamamoto_A(nprow, npcol, rrow, rcol, m, k, b, _pp(Qp), _pp(Ap), _p(T))
     assert rc == 0, "oracle_update_Yamamoto_A: bad arguments"
+
+
+# ---- DMatrix pack / replication operations (alg/SE/dmatrix.cxx), all ranks simulated in numpy ------------------------------
+# Data movement only (plus one sum), so numpy index arithmetic is the restatement; pinned to the unmodified reference by
+# tests/golden/dmat_ref_outputs.npz (oracle/ref_dmat_dump.cxx).  Grid rank = myrow + mycol*nprow (test_qr_2d.cxx:367-374).
+def dmat_extent(n, b, np_, rank, root):
+    """get_mynrow / get_myncol, dmatrix.cxx:194-203"""
+    nb = n // b
+    return (nb // np_ + (1 if (nb % np_) > (rank + np_ - root) % np_ else 0)) * b
+
+
+def dmat_local(nrow, ncol, b, nprow, npcol, rrow, rcol, myrow, mycol, value):
+    """Local piece of the matrix whose global element (gr, gc) is value(gr, gc) (vectorised callable)."""
+    mr, mc = dmat_extent(nrow, b, nprow, myrow, rrow), dmat_extent(ncol, b, npcol, mycol, rcol)
+    r, c = np.arange(mr), np.arange(mc)
+    gr = ((r // b) * nprow + (myrow - rrow) % nprow) * b + r % b
+    gc = ((c // b) * npcol + (mycol - rcol) % npcol) * b + c % b
+    return np.asfortranarray(value(gr[:, None], gc[None, :]))
+
+
+def dmat_replicate_vertical(pieces, nprow, npcol):
+    """dmatrix.cxx:268-289: per rank, the packed pieces of its grid column in row-rank order"""
+    return [np.concatenate([pieces[pr + (rank // nprow) * nprow].reshape(-1, order="F") for pr in range(nprow)])
+            for rank in range(nprow * npcol)]
+
+
+def dmat_replicate_horizontal(pieces, nprow, npcol):
+    """dmatrix.cxx:294-304"""
+    return [np.concatenate([pieces[(rank % nprow) + pc * nprow].reshape(-1, order="F") for pc in range(npcol)])
+            for rank in range(nprow * npcol)]
+
+
+def dmat_reduce_scatter_horizontal(pieces, cntrbs, nprow, npcol):
+    """dmatrix.cxx:310-355: data += sum over my grid row of chunk <my column> of every contribution"""
+    out = []
+    for rank in range(nprow * npcol):
+        myrow, mycol = rank % nprow, rank // nprow
+        d = pieces[rank].reshape(-1, order="F").copy()
+        for pc in range(npcol):
+            d += cntrbs[myrow + pc * nprow][mycol * d.size:(mycol + 1) * d.size]
+        out.append(d)
+    return out
+
+
+def dmat_transpose_data(pieces, nprow, npcol):
+    """dmatrix.cxx:252-263: the packed piece of world rank crow.rank + ccol.rank*npcol"""
+    return [pieces[(rank // nprow) + (rank % nprow) * npcol].reshape(-1, order="F").copy() for rank in range(nprow * npcol)]
+
+
+def dmat_foldcols(piece, b, factor):
+    """dmatrix.cxx:527-552 on one local piece (mr x mc) -> (mr/f) x (mc*f)"""
+    mr, mc = piece.shape
+    blocks = piece.reshape(mr // (b * factor), factor, b, mc)            # [j, i, w, c]
+    return np.asfortranarray(np.concatenate([blocks[:, i].reshape(mr // factor, mc) for i in range(factor)], axis=1))
+
+
+def dmat_foldrows(piece, b, factor):
+    """dmatrix.cxx:560-584 on one local piece (mr x mc) -> (mr*f) x (mc/f)"""
+    mr, mc = piece.shape
+    bcol = mc // factor
+    out = np.empty((mr // b, factor, b, bcol))
+    for i in range(factor):
+        out[:, i] = piece[:, i * bcol:(i + 1) * bcol].reshape(mr // b, b, bcol)
+    return np.asfortranarray(out.reshape(mr * factor, bcol))
+
+
+def dmat_slice(piece, nrow, ncol, b, nprow, npcol, rrow, rcol, myrow, mycol, firstrow, numrows, firstcol, numcols):
+    """slice, dmatrix.cxx:367-394: returns (view of the local piece, new rrow, new rcol).  The roots rotate to the owner of the
+    corner block; the local pointer moves past the rows / columns this rank owns above / left of the corner."""
+    nr, nc = (rrow + firstrow // b) % nprow, (rcol + firstcol // b) % npcol
+    mr0, mc0 = dmat_extent(nrow, b, nprow, myrow, rrow), dmat_extent(ncol, b, npcol, mycol, rcol)
+    mr1, mc1 = dmat_extent(nrow - firstrow, b, nprow, myrow, nr), dmat_extent(ncol - firstcol, b, npcol, mycol, nc)
+    mr2, mc2 = dmat_extent(numrows, b, nprow, myrow, nr), dmat_extent(numcols, b, npcol, mycol, nc)
+    return piece[mr0 - mr1:mr0 - mr1 + mr2, mc0 - mc1:mc0 - mc1 + mc2], nr, nc

@@ -275,6 +275,53 @@ def case_update_Yamamoto_A(world, golden, name, m, k, b, nprow, rrow, rcol):
     return ok
 
 
+def case_dmat(world, gold, name):
+    """one DMatrix pack operation (candmc_b200.dmatrix, the C ABI candmc_dmat_*) against the outputs of the
+    unmodified reference (tests/golden/dmat_ref_outputs.npz) and the numpy oracle.  rank = myrow + mycol*nprow."""
+    from candmc_b200.dmatrix import DMatrix
+    from dmat_cases import build_case, op_of
+    op = op_of(name)
+    case = build_case(op, gold[f"{name}.args"])
+    nprow, npcol, b, r = case["nprow"], case["npcol"], case["b"], world.rank
+    myrow, mycol = r % nprow, r // nprow
+    crow = cb.setup_sub_comm(world, mycol, myrow, npcol)
+    ccol = cb.setup_sub_comm(world, myrow, mycol, nprow)
+    pv = cb.pview(case["rrow"], case["rcol"], crow, ccol, world)
+    A = DMatrix(case["nrow"], case["ncol"], b, pv)
+    parent = case["parents"][r]
+    A.tensor[:parent.size] = torch.from_numpy(parent.reshape(-1, order="F").copy()).cuda()
+    X = A
+    if case["sliced"]:
+        fr, fc = nprow * b, npcol * b
+        X = A.slice(fr, case["nrow"] - fr, fc, case["ncol"] - fc)
+    f = case["factor"]
+    if op == "repv":
+        got = X.replicate_vertical()
+    elif op == "reph":
+        got = X.replicate_horizontal()
+    elif op == "rsh":
+        X.reduce_scatter_horizontal(torch.from_numpy(case["cntrbs"][r].copy()).cuda())
+        got = X.get_contig().tensor
+    elif op == "tpd":
+        got = X.transpose_data().tensor
+    elif op == "fc":
+        got = X.foldcols(f).tensor
+    else:
+        got = X.foldrows(f).tensor
+    torch.cuda.synchronize()
+    want = np.asarray(case["want"][r]).reshape(-1, order="F")
+    got = got.cpu().numpy()[:want.size]
+    ref = gold[f"{name}.r{r}"]
+    if op == "rsh":
+        ok = record(f"{name}:oracle", float(np.abs(got - want).max()), 4 * npcol * EPS)
+        ok &= record(f"{name}:golden", float(np.abs(got - ref).max()), 4 * npcol * EPS)
+    else:
+        ok = record(f"{name}:oracle", 0.0 if np.array_equal(got, want) else 1.0, 0.5)
+        ok &= record(f"{name}:golden", 0.0 if np.array_equal(got, ref) else 1.0, 0.5)
+    crow.free(); ccol.free()
+    return ok
+
+
 def pending_cases(world, golden):
     """Paths that have not run on a B200 yet (tests/test_zz_redist_gpu.py runs these apart from the validated suite)."""
     P = world.np
@@ -285,6 +332,11 @@ def pending_cases(world, golden):
         case_update_Yamamoto_A(world, golden, "updy_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 0, 0)
         case_update_Yamamoto_A(world, golden, "updy_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 2, 0)
         case_update_Yamamoto_A(world, golden, "updy_big_2x2_r11", 1024, 768, 64, 2, 1, 1)
+    from dmat_cases import case_names, load_golden
+    dgold = load_golden()
+    for name in case_names(dgold):
+        if int(dgold[f"{name}.args"][0]) == P:
+            case_dmat(world, dgold, name)
     shapes = {1: [(1,)], 2: [(2,), (1,)], 4: [(2,), (4,), (1,)], 8: [(2,), (4,)]}.get(P, [])
     for (nprow,) in shapes:
         npcol = P // nprow

@@ -96,6 +96,7 @@ SIGNATURES = {
     "candmc_dmat_transpose_data": (C.c_int, [C.POINTER(DMat), pd, C.c_void_p]),
     "candmc_dmat_foldcols": (C.c_int, [C.POINTER(DMat), i64, pd, C.c_void_p]),
     "candmc_dmat_foldrows": (C.c_int, [C.POINTER(DMat), i64, pd, C.c_void_p]),
+    "candmc_debug_fold_src_index": (C.c_int, [C.c_int] + [i64] * 7 + [C.POINTER(i64)]),
     "candmc_debug_redist_permute": (C.c_int, [C.c_int, C.c_int, C.c_int, i64, C.c_int, C.c_int, C.c_int, pd, i64, pd, i64,
                                               i64, C.c_void_p]),
     # accelerator seam of the 2.5D LU (alg/LU/lu_offload.h)

@@ -76,27 +76,31 @@ int replicate(const candmc_dmat_t* A, candmc_comm* c, int64_t n_axis, double* re
   return OK;
 }
 
+// Source element of output element (rr, cc) of a fold; shared by the kernel and the CPU-side test hook.
+template <bool FOLDCOLS>
+__host__ __device__ __forceinline__ int64_t fold_src_index(unsigned rr, int64_t cc, int64_t ocol, int64_t mc, unsigned b,
+                                                           unsigned f, int64_t lda) {
+  const unsigned blk = rr / b, w = rr - blk * b;
+  if (FOLDCOLS) {
+    const int64_t i_col = cc / mc, c_in = cc - i_col * mc;  // column group of the folded matrix, column inside it
+    return (static_cast<int64_t>(blk) * f + i_col) * b + w + c_in * lda;
+  }
+  const unsigned j = blk / f, i = blk - j * f;
+  return (static_cast<int64_t>(i) * ocol + cc) * lda + static_cast<int64_t>(j) * b + w;
+}
+
 // FOLDCOLS: out is (mr/f) x (mc*f), ld = mr/f:  out[(i*mc + c)*(mr/f) + j*b + w] = in[(j*f + i)*b + w + c*lda]
 // else    : out is (mr*f) x (mc/f), ld = mr*f:  out[c*(mr*f) + (j*f + i)*b + w]  = in[(i*(mc/f) + c)*lda + j*b + w]
+// grid.y strides the output columns, grid.x * block the rows of one output column (32-bit arithmetic per element).
 template <bool FOLDCOLS>
 __global__ void __launch_bounds__(256)
-fold_kernel(const double* __restrict__ in, int64_t lda, double* __restrict__ out, int64_t mr, int64_t mc, int64_t b, int64_t f) {
-  const int64_t orow = FOLDCOLS ? mr / f : mr * f;
-  const int64_t ocol = FOLDCOLS ? mc * f : mc / f;
-  const int64_t total = orow * ocol;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total; e += stride) {
-    const int64_t cc = e / orow, rr = e - cc * orow;
-    const int64_t blk = rr / b, w = rr - blk * b;
-    int64_t src;
-    if (FOLDCOLS) {
-      const int64_t i = cc / mc, c = cc - i * mc;
-      src = (blk * f + i) * b + w + c * lda;
-    } else {
-      const int64_t j = blk / f, i = blk - j * f;
-      src = (i * ocol + cc) * lda + j * b + w;
-    }
-    out[e] = __ldg(in + src);
+fold_kernel(const double* __restrict__ in, int64_t lda, double* __restrict__ out, unsigned orow, int64_t ocol, int64_t mc,
+            unsigned b, unsigned f) {
+  const unsigned xstride = gridDim.x * blockDim.x;
+  for (int64_t cc = blockIdx.y; cc < ocol; cc += gridDim.y) {
+    double* ocolp = out + cc * static_cast<int64_t>(orow);
+    for (unsigned rr = blockIdx.x * blockDim.x + threadIdx.x; rr < orow; rr += xstride)
+      ocolp[rr] = __ldg(in + fold_src_index<FOLDCOLS>(rr, cc, ocol, mc, b, f, lda));
   }
 }
 
@@ -104,16 +108,22 @@ int fold(const candmc_dmat_t* A, int64_t f, double* out, bool cols, cudaStream_t
   const char* what = cols ? "foldcols" : "foldrows";
   int64_t mr, mc;
   CANDMC_TRY(check_dmat(A, what, &mr, &mc));
-  CANDMC_CHECK(f >= 1, "%s: factor must be positive", what);
+  CANDMC_CHECK(f >= 1 && f < (1LL << 31), "%s: factor must be positive", what);
   CANDMC_CHECK(cols ? mr % (A->b * f) == 0 : mc % f == 0, "%s: local extent not divisible by the factor", what);
   CANDMC_CHECK(out != nullptr && is_device_ptr(out) && out != A->data, "%s: needs a distinct device output", what);
-  const int64_t total = mr * mc;
-  if (total == 0) return OK;
-  int64_t g = (total + 255) / 256;
+  if (mr == 0 || mc == 0) return OK;
+  const int64_t orow = cols ? mr / f : mr * f, ocol = cols ? mc * f : mc / f;
+  CANDMC_CHECK(orow < (1LL << 31) && A->b < (1LL << 31), "%s: more than 2^31-1 local rows", what);
   const int64_t cap = static_cast<int64_t>(runtime().num_sms) * 8;
-  if (g > cap) g = cap;
-  if (cols) fold_kernel<true><<<(int)g, 256, 0, st>>>(A->data, A->lda, out, mr, mc, A->b, f);
-  else fold_kernel<false><<<(int)g, 256, 0, st>>>(A->data, A->lda, out, mr, mc, A->b, f);
+  int64_t gx = (orow + 255) / 256;
+  if (gx > cap) gx = cap;
+  int64_t gy = cap / gx;
+  if (gy < 1) gy = 1;
+  if (gy > ocol) gy = ocol;
+  if (gy > 65535) gy = 65535;
+  const dim3 grid((unsigned)gx, (unsigned)gy);
+  if (cols) fold_kernel<true><<<grid, 256, 0, st>>>(A->data, A->lda, out, (unsigned)orow, ocol, mc, (unsigned)A->b, (unsigned)f);
+  else fold_kernel<false><<<grid, 256, 0, st>>>(A->data, A->lda, out, (unsigned)orow, ocol, mc, (unsigned)A->b, (unsigned)f);
   CANDMC_CUDA(cudaGetLastError());
   ++runtime().launches;
   return OK;
@@ -215,6 +225,17 @@ int candmc_dmat_transpose_data(const candmc_dmat_t* A, double* out, void* stream
   CANDMC_TRY(packed(A, mr, mc, static_cast<double*>(ws), &src, st));
   const int partner = crow->rank + ccol->rank * crow->size;  // dmatrix.cxx:257-259
   return comm_sendrecv(world, src, mine, partner, out, mine, partner, st);
+}
+
+// CPU-testable index map of the fold kernels (pure host code)
+int candmc_debug_fold_src_index(int foldcols, int64_t mr, int64_t mc, int64_t b, int64_t f, int64_t lda, int64_t rr, int64_t cc,
+                                int64_t* src) {
+  CANDMC_CHECK(src != nullptr && b > 0 && f > 0 && mr >= 0 && mc >= 0, "fold index: bad arguments");
+  const int64_t orow = foldcols ? mr / f : mr * f, ocol = foldcols ? mc * f : mc / f;
+  CANDMC_CHECK(rr >= 0 && rr < orow && cc >= 0 && cc < ocol, "fold index: out of range");
+  *src = foldcols ? fold_src_index<true>((unsigned)rr, cc, ocol, mc, (unsigned)b, (unsigned)f, lda)
+                  : fold_src_index<false>((unsigned)rr, cc, ocol, mc, (unsigned)b, (unsigned)f, lda);
+  return OK;
 }
 
 int candmc_dmat_foldcols(const candmc_dmat_t* A, int64_t factor, double* out, void* stream) {

@@ -224,36 +224,43 @@ int offs_scratch(int64_t n) {
 // pivoting, so there is nothing better to coalesce on).  MODE 0 = gather (read), 1 = scatter (write), 2 = swap.
 template <int MODE>
 __global__ void __launch_bounds__(256)
-sparse_rows_kernel(double* __restrict__ M, int64_t ld, const int64_t* __restrict__ offs, int64_t nrow, int64_t ncol,
+sparse_rows_kernel(double* __restrict__ M, int64_t ld, const int64_t* __restrict__ offs, int64_t nrow, unsigned ncol,
                    double* __restrict__ rows_in_out, int64_t row0) {
-  const int64_t total = nrow * ncol;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total; e += stride) {
-    const int64_t i = e / ncol, j = e - i * ncol;
-    double* mp = M + offs[row0 + i] + j * ld;
-    double* rp = rows_in_out + (row0 + i) * ncol + j;
-    if (MODE == 0) {
-      *rp = *mp;
-    } else if (MODE == 1) {
-      *mp = *rp;
-    } else {
-      const double old = *mp;
-      *mp = *rp;
-      *rp = old;
+  // grid.y strides the rows, grid.x * block the elements of a row
+  const unsigned xstride = gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.y; i < nrow; i += gridDim.y) {
+    double* mrow = M + offs[row0 + i];
+    double* prow = rows_in_out + (row0 + i) * static_cast<int64_t>(ncol);
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < ncol; j += xstride) {
+      double* mp = mrow + static_cast<int64_t>(j) * ld;
+      if (MODE == 0) {
+        prow[j] = *mp;
+      } else if (MODE == 1) {
+        *mp = prow[j];
+      } else {
+        const double old = *mp;
+        *mp = prow[j];
+        prow[j] = old;
+      }
     }
   }
 }
 
 int launch_sparse(int mode, double* M, int64_t ld, int64_t nrow, int64_t ncol, int64_t row0, cudaStream_t s) {
-  const int64_t total = nrow * ncol;
-  if (total == 0) return OK;
-  int64_t g = (total + 255) / 256;
+  if (nrow == 0 || ncol == 0) return OK;
+  CANDMC_CHECK(ncol < (1LL << 31), "offload_sparse_rw: more than 2^31-1 columns");
   const int64_t cap = static_cast<int64_t>(runtime().num_sms) * 8;
-  if (g > cap) g = cap;
-  const int grid = static_cast<int>(g);
-  if (mode == 0) sparse_rows_kernel<0><<<grid, 256, 0, s>>>(M, ld, g_off.d_offs, nrow, ncol, g_off.d_rows, row0);
-  else if (mode == 1) sparse_rows_kernel<1><<<grid, 256, 0, s>>>(M, ld, g_off.d_offs, nrow, ncol, g_off.d_rows, row0);
-  else sparse_rows_kernel<2><<<grid, 256, 0, s>>>(M, ld, g_off.d_offs, nrow, ncol, g_off.d_rows, row0);
+  int64_t gx = (ncol + 255) / 256;
+  if (gx > cap) gx = cap;
+  int64_t gy = cap / gx;
+  if (gy < 1) gy = 1;
+  if (gy > nrow) gy = nrow;
+  if (gy > 65535) gy = 65535;
+  const dim3 grid((unsigned)gx, (unsigned)gy);
+  const unsigned nc = (unsigned)ncol;
+  if (mode == 0) sparse_rows_kernel<0><<<grid, 256, 0, s>>>(M, ld, g_off.d_offs, nrow, nc, g_off.d_rows, row0);
+  else if (mode == 1) sparse_rows_kernel<1><<<grid, 256, 0, s>>>(M, ld, g_off.d_offs, nrow, nc, g_off.d_rows, row0);
+  else sparse_rows_kernel<2><<<grid, 256, 0, s>>>(M, ld, g_off.d_offs, nrow, nc, g_off.d_rows, row0);
   CANDMC_CUDA(cudaGetLastError());
   ++runtime().launches;
   return OK;

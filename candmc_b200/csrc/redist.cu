@@ -25,29 +25,41 @@ constexpr int RD_THREADS = 256;
 // X is the local rows x cols matrix (leading dimension ldx) in BLOCKED order along the permuted axis; SEG is the
 // segmented exchange buffer.  GATHER: SEG <- X (blocked -> cyclic, before the exchange); otherwise X <- SEG.
 // VEC = 2 moves double2 (requires even nb / rows / ldx and 16 B aligned bases).
+// grid.y strides the columns, grid.x * block the rows of a column; everything per element is 32-bit arithmetic (two
+// divisions by nb and P when block rows are permuted, none when block columns are: their terms are per column).
 template <bool ROWS_AXIS, bool GATHER, int VEC>
 __global__ void __launch_bounds__(RD_THREADS)
-permute_blocks_kernel(AxisPlan pl, double* __restrict__ X, int64_t ldx, double* __restrict__ SEG, int64_t rows,
+permute_blocks_kernel(AxisPlan pl, double* __restrict__ X, int64_t ldx, double* __restrict__ SEG, unsigned rows,
                       int64_t cols) {
-  const int64_t rv = rows / VEC;
-  const int64_t total = rv * cols;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total; e += stride) {
-    const int64_t c = e / rv, r = (e - c * rv) * VEC;
-    int64_t idx;
-    if (ROWS_AXIS) {
-      idx = strided_segment_index(pl, true, r / pl.nb, (int)(r % pl.nb), c, cols);
-    } else {
-      idx = strided_segment_index(pl, false, c / pl.nb, (int)(c % pl.nb), r, rows);
-    }
-    double* xp = X + c * ldx + r;
-    double* sp = SEG + idx;
-    if (VEC == 2) {
-      if (GATHER) *reinterpret_cast<double2*>(sp) = *reinterpret_cast<const double2*>(xp);
-      else *reinterpret_cast<double2*>(xp) = *reinterpret_cast<const double2*>(sp);
-    } else {
-      if (GATHER) *sp = *xp;
-      else *xp = *sp;
+  const unsigned rv = rows / VEC;
+  const unsigned nb = (unsigned)pl.nb;
+  const unsigned xstride = gridDim.x * blockDim.x;
+  for (int64_t c = blockIdx.y; c < cols; c += gridDim.y) {
+    int64_t col_base = 0;  // block columns: position of (row 0, column c) inside the segments
+    if (!ROWS_AXIS) col_base = strided_segment_index(pl, false, c / nb, (int)(c % nb), 0, rows);
+    double* xcol = X + c * ldx;
+    for (unsigned r2 = blockIdx.x * blockDim.x + threadIdx.x; r2 < rv; r2 += xstride) {
+      const unsigned r = r2 * VEC;
+      int64_t idx;
+      if (ROWS_AXIS) {
+        const unsigned blk = r / nb, w = r - blk * nb;
+        int p;
+        unsigned t;
+        strided_owner(pl, blk, &p, &t);
+        const int64_t seg_rows = (int64_t)pl.scnt[p] * nb;
+        idx = pl.soff[p] * nb * cols + c * seg_rows + (int64_t)t * nb + w;
+      } else {
+        idx = col_base + r;
+      }
+      double* xp = xcol + r;
+      double* sp = SEG + idx;
+      if (VEC == 2) {
+        if (GATHER) *reinterpret_cast<double2*>(sp) = *reinterpret_cast<const double2*>(xp);
+        else *reinterpret_cast<double2*>(xp) = *reinterpret_cast<const double2*>(sp);
+      } else {
+        if (GATHER) *sp = *xp;
+        else *xp = *sp;
+      }
     }
   }
 }
@@ -56,14 +68,21 @@ template <bool ROWS_AXIS, bool GATHER>
 int launch_permute(const AxisPlan& pl, double* X, int64_t ldx, double* SEG, int64_t rows, int64_t cols,
                    cudaStream_t st) {
   if (rows == 0 || cols == 0) return OK;
+  CANDMC_CHECK(rows < (1LL << 31), "redistribute: more than 2^31-1 local rows");
   const bool vec = pl.nb % 2 == 0 && rows % 2 == 0 && ldx % 2 == 0 && reinterpret_cast<uintptr_t>(X) % 16 == 0 &&
                    reinterpret_cast<uintptr_t>(SEG) % 16 == 0;
-  const int64_t total = (vec ? rows / 2 : rows) * cols;
-  int64_t g = (total + RD_THREADS - 1) / RD_THREADS;
+  const int64_t rv = vec ? rows / 2 : rows;
+  // about 8 CTAs per SM in total: as many along a column as it has work for, the rest across columns
   const int64_t cap = static_cast<int64_t>(runtime().num_sms) * 8;
-  if (g > cap) g = cap;
-  if (vec) permute_blocks_kernel<ROWS_AXIS, GATHER, 2><<<(int)g, RD_THREADS, 0, st>>>(pl, X, ldx, SEG, rows, cols);
-  else permute_blocks_kernel<ROWS_AXIS, GATHER, 1><<<(int)g, RD_THREADS, 0, st>>>(pl, X, ldx, SEG, rows, cols);
+  int64_t gx = (rv + RD_THREADS - 1) / RD_THREADS;
+  if (gx > cap) gx = cap;
+  int64_t gy = cap / gx;
+  if (gy < 1) gy = 1;
+  if (gy > cols) gy = cols;
+  if (gy > 65535) gy = 65535;
+  const dim3 grid((unsigned)gx, (unsigned)gy);
+  if (vec) permute_blocks_kernel<ROWS_AXIS, GATHER, 2><<<grid, RD_THREADS, 0, st>>>(pl, X, ldx, SEG, (unsigned)rows, cols);
+  else permute_blocks_kernel<ROWS_AXIS, GATHER, 1><<<grid, RD_THREADS, 0, st>>>(pl, X, ldx, SEG, (unsigned)rows, cols);
   CANDMC_CUDA(cudaGetLastError());
   ++runtime().launches;
   return OK;

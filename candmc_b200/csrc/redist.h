@@ -28,6 +28,7 @@ struct AxisPlan {
   int root;                       // cyclic root: rank `root` holds global block 0
   int nb;                         // block size (elements)
   int64_t K;                      // blocks per rank
+  unsigned base_mod;              // (me*K + root) mod P: cyclic owner of my blocked-local block blk is (base_mod + blk) mod P
   int lo[REDIST_MAX_P];           // contiguous side: first local (cyclic) block exchanged with p
   int ccnt[REDIST_MAX_P];         //                  number of blocks
   int first[REDIST_MAX_P];        // strided side: first local (blocked) block exchanged with p (stride P)
@@ -48,6 +49,7 @@ inline bool axis_plan(int P, int me, int root, int64_t K, int nb, AxisPlan* pl) 
   pl->root = root;
   pl->nb = nb;
   pl->K = K;
+  pl->base_mod = (unsigned)(((int64_t)me * K + root) % P);
   const int mc = (me - root + P) % P;  // my cyclic index
   int64_t cacc = 0, sacc = 0;
   for (int p = 0; p < P; ++p) {
@@ -73,18 +75,27 @@ inline bool axis_plan(int P, int me, int root, int64_t K, int nb, AxisPlan* pl) 
   return cacc == K && sacc == K;
 }
 
+// Strided side: which peer owns (cyclically) my blocked-local block `blk`, and which of that peer's blocks it is.
+// 32-bit arithmetic on purpose (blk < 2^30): this runs once per element in the row-permuting kernel.
+CANDMC_HD void strided_owner(const AxisPlan& pl, unsigned blk, int* p, unsigned* t) {
+  const unsigned P = (unsigned)pl.P;
+  const int owner = (int)((pl.base_mod + blk) % P);
+  *p = owner;
+  *t = (blk - (unsigned)pl.first[owner]) / P;
+}
+
 // Strided side, element level.  `blk` = local blocked block index on the permuted axis, `w` = offset inside the block,
 // `o` = index along the other axis, `other` = local extent of the other axis.  Returns the element's position in the
 // segmented exchange buffer (segment p = everything exchanged with rank p, in rank order):
 //   rows axis (permuting block ROWS of a column-major matrix): segment p is (scnt[p]*nb) x other, column-major;
 //   cols axis (permuting block COLUMNS): segment p is other x (scnt[p]*nb), column-major.
 CANDMC_HD int64_t strided_segment_index(const AxisPlan& pl, bool rows_axis, int64_t blk, int w, int64_t o, int64_t other) {
-  const int64_t I = (int64_t)pl.me * pl.K + blk;
-  int p = (int)((I + pl.root) % pl.P);  // cyclic owner of global block I
-  const int64_t t = (blk - pl.first[p]) / pl.P;
+  int p;
+  unsigned t;
+  strided_owner(pl, (unsigned)blk, &p, &t);
   const int64_t seg = pl.soff[p] * pl.nb * other;
-  if (rows_axis) return seg + o * ((int64_t)pl.scnt[p] * pl.nb) + t * pl.nb + w;
-  return seg + (t * pl.nb + w) * other + o;
+  if (rows_axis) return seg + o * ((int64_t)pl.scnt[p] * pl.nb) + (int64_t)t * pl.nb + w;
+  return seg + ((int64_t)t * pl.nb + w) * other + o;
 }
 
 }  // namespace candmc

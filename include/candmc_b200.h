@@ -256,6 +256,10 @@ int candmc_dmat_foldcols(const candmc_dmat_t* A, int64_t factor, double* out, vo
 /* foldrows (dmatrix.cxx:560-584): the inverse regrouping, out = (mr*factor) x (mc/factor), ld = mr*factor. */
 int candmc_dmat_foldrows(const candmc_dmat_t* A, int64_t factor, double* out, void* stream);
 
+/* The fold kernels' index map (pure host code, for the CPU-side tests): source offset in the mr x mc (lda) local piece of
+ * output element (rr, cc) of foldcols (foldcols != 0) or foldrows. */
+int candmc_debug_fold_src_index(int foldcols, int64_t mr, int64_t mc, int64_t b, int64_t f, int64_t lda, int64_t rr, int64_t cc,
+                                int64_t* src);
 /* Test hook: one launch of the redistribution's permute kernel for the plan of rank `me` of `P` (no communicator), so a
  * single GPU can stand in for every rank of an axis.  gather != 0: SEG <- X (blocked side -> segments), else X <- SEG. */
 int candmc_debug_redist_permute(int P, int me, int root, int64_t K, int nb, int rows_axis, int gather, double* X,

@@ -28,8 +28,8 @@ int64_t local_extent(int64_t n, int64_t b, int np, int rank, int root) {
 
 int check_dmat(const candmc_dmat_t* A, const char* what, int64_t* mr, int64_t* mc) {
   CANDMC_CHECK(A != nullptr && A->pv.crow != nullptr && A->pv.ccol != nullptr, "%s: null matrix or processor view", what);
-  CANDMC_CHECK(A->b > 0 && A->nrow >= 0 && A->ncol >= 0 && A->nrow % A->b == 0 && A->ncol % A->b == 0,
-               "%s: extents must be multiples of the block size", what);
+  // extents need not be multiples of b: like the reference (dmatrix.cxx:194-203) only whole blocks are distributed
+  CANDMC_CHECK(A->b > 0 && A->nrow >= 0 && A->ncol >= 0, "%s: negative extent or block size", what);
   const int nprow = A->pv.ccol->size, npcol = A->pv.crow->size;
   CANDMC_CHECK(A->pv.rrow >= 0 && A->pv.rrow < nprow && A->pv.rcol >= 0 && A->pv.rcol < npcol, "%s: root outside the grid", what);
   *mr = local_extent(A->nrow, A->b, nprow, A->pv.ccol->rank, A->pv.rrow);
@@ -149,8 +149,7 @@ int candmc_dmat_slice(const candmc_dmat_t* A, int64_t firstrow, int64_t numrows,
   CANDMC_CHECK(A != nullptr && out != nullptr && A->pv.crow != nullptr && A->pv.ccol != nullptr && A->b > 0, "slice: null argument");
   CANDMC_CHECK(firstrow >= 0 && firstcol >= 0 && firstrow % A->b == 0 && firstcol % A->b == 0,
                "slice: the corner must sit on a block boundary");  // LIBT_ASSERT, dmatrix.cxx:380-381
-  CANDMC_CHECK(numrows >= 0 && numcols >= 0 && firstrow + numrows <= A->nrow && firstcol + numcols <= A->ncol &&
-                   numrows % A->b == 0 && numcols % A->b == 0,
+  CANDMC_CHECK(numrows >= 0 && numcols >= 0 && firstrow + numrows <= A->nrow && firstcol + numcols <= A->ncol,
                "slice: outside the matrix");
   const int nprow = A->pv.ccol->size, npcol = A->pv.crow->size;
   candmc_dmat_t rest = *A;  // everything below / right of the corner, with the roots rotated to the corner's owner

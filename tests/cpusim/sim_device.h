@@ -1,0 +1,113 @@
+// tests/cpusim — CPU functional simulator of the CUDA execution model, TEST INFRASTRUCTURE ONLY.
+//
+// Force-included (g++ -include) in front of every translated candmc_b200/csrc/*.cu so that the product's host schedules
+// and its simple (non-TMA, non-DMMA) kernels can be EXECUTED in the CPU test suite: a kernel launch runs every thread of
+// every block as a fiber (ucontext), __syncthreads / warp shuffles are fiber barriers, streams are synchronous.  The hot
+// GEMM kernel (TMA + DMMA, inline PTX) cannot be simulated and is replaced by plain loops (sim_gemm.cxx); what this buys is
+// a CPU run of everything AROUND it — index arithmetic of the pack kernels, staging, stream/event ordering logic, NCCL call
+// sequences on real multi-process grids — before GPU minutes are spent.  The product library never loads or links any of
+// this (tests/test_boundary.py checks), and nothing here is a fallback: libcandmc_b200.so still fails without a B200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <functional>
+
+namespace cpusim {
+
+struct Idx {
+  unsigned x = 0, y = 0, z = 0;
+};
+struct ThreadState {
+  Idx thread, block, bdim, gdim;
+};
+ThreadState& ts();        // state of the fiber that is running
+void* dyn_smem();         // dynamic shared memory of the running block
+void sync_threads();      // block barrier
+void sync_warp_exchange(const void* in, void* out, int src_lane, size_t bytes);  // one warp shuffle
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+
+}  // namespace cpusim
+
+#define threadIdx (::cpusim::ts().thread)
+#define blockIdx (::cpusim::ts().block)
+#define blockDim (::cpusim::ts().bdim)
+#define gridDim (::cpusim::ts().gdim)
+#define warpSize 32
+
+#define __launch_bounds__(...)
+#undef __forceinline__
+#define __forceinline__ inline
+// a __shared__ array is shared by the fibers of a block, which run one block at a time on one OS thread: `static` is it
+#undef __shared__
+#define __shared__ static
+
+#define CPUSIM_LAUNCH(kern, grid, block, smem, stream, ...) \
+  ::cpusim::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); })
+
+static inline void __syncthreads() { ::cpusim::sync_threads(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+
+template <class T>
+static inline T __ldg(const T* p) {
+  return *p;
+}
+template <class T>
+static inline T __ldcg(const T* p) {
+  return *p;
+}
+template <class T>
+static inline void __stcg(T* p, T v) {
+  *p = v;
+}
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+  T out;
+  ::cpusim::sync_warp_exchange(&v, &out, (int)((::cpusim::ts().thread.x & 31u) ^ (unsigned)lane_mask), sizeof(T));
+  return out;
+}
+template <class T>
+static inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
+  T out;
+  int lane = (int)(::cpusim::ts().thread.x & 31u);
+  ::cpusim::sync_warp_exchange(&v, &out, lane + (int)delta < 32 ? lane + (int)delta : lane, sizeof(T));
+  return out;
+}
+// one OS thread per process executes all fibers: plain read-modify-write is atomic here
+template <class T>
+static inline T atomicAdd(T* p, T v) {
+  T old = *p;
+  *p = old + v;
+  return old;
+}
+static inline unsigned atomicInc(unsigned* p, unsigned lim) {
+  unsigned old = *p;
+  *p = old >= lim ? 0 : old + 1;
+  return old;
+}
+static inline void __threadfence() {}
+static inline void __threadfence_system() {}
+template <class T>
+static inline T min(T a, T b) {
+  return a < b ? a : b;
+}
+template <class T>
+static inline T max(T a, T b) {
+  return a > b ? a : b;
+}
+static inline long long __double_as_longlong(double d) {
+  long long v;
+  memcpy(&v, &d, 8);
+  return v;
+}
+static inline double __longlong_as_double(long long v) {
+  double d;
+  memcpy(&d, &v, 8);
+  return d;
+}
+// the typed overload nvcc's cuda_runtime.h provides for kernels
+template <class T>
+static inline cudaError_t cudaFuncSetAttribute(T* f, cudaFuncAttribute a, int v) {
+  return ::cudaFuncSetAttribute(reinterpret_cast<const void*>(f), a, v);
+}

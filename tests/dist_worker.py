@@ -16,6 +16,11 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+if os.environ.get("CANDMC_CPUSIM") == "1":   # CPU suite: the same worker on the functional simulator (tests/cpusim)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cpusim"))
+    import simtorch
+    simtorch.install()
+
 import candmc_b200 as cb  # noqa: E402
 from oracle import oracle_py as orc  # noqa: E402  (checker only)
 
@@ -415,7 +420,8 @@ def main():
             case_d25(world, golden, f"d25_ksplit_nccl_n512_{tag}", 512, 2, 0)
             cb.lib().candmc_set_fused_reduce(1)
             # host operands: only the k-slice is uploaded, in chunks, under the running multiply
-            case_d25(world, golden, f"d25_ksplit_host_n4096_{tag}", 4096, 2, 0, use_host=True, check_golden=False, oracle=False)
+            n_host = 512 if os.environ.get("CANDMC_CPUSIM") == "1" else 4096   # plain-loop GEMM in the simulator
+            case_d25(world, golden, f"d25_ksplit_host_n{n_host}_{tag}", n_host, 2, 0, use_host=True, check_golden=False, oracle=False)
             case_d25(world, golden, f"d25_ksplit_host_n96_{tag}", 96, 2, 0, use_host=True, lda_pad=2)
         if P == 4:
             case_d25(world, golden, "d25_n96_q2_c1_ovp0", 96, 1, 0)

@@ -14,6 +14,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 
+if os.environ.get("CANDMC_CPUSIM") == "1":   # CPU suite: the same worker on the functional simulator (tests/cpusim)
+    sys.path.insert(0, os.path.join(HERE, "cpusim"))
+    import simtorch
+    simtorch.install()
+
 from off_script import GpuBackend, OracleBackend, run_script  # noqa: E402
 
 

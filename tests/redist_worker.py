@@ -16,6 +16,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 
+if os.environ.get("CANDMC_CPUSIM") == "1":   # CPU suite: the same worker on the functional simulator (tests/cpusim)
+    sys.path.insert(0, os.path.join(HERE, "cpusim"))
+    import simtorch
+    simtorch.install()
+
 import torch  # noqa: E402
 
 import candmc_b200 as cb  # noqa: E402

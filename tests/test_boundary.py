@@ -1,5 +1,5 @@
 """CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/candmc_b200.h declares,
-fails loudly without a GPU, and the product never touches oracle/."""
+fails loudly without a GPU, and the product never touches oracle/ or tests/cpusim."""
 import ctypes
 import os
 import re
@@ -59,9 +59,19 @@ def test_product_never_references_the_oracle():
             for f in files:
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".cxx", ".cpp", "Makefile")):
                     text = open(os.path.join(dirpath, f), errors="replace").read()
-                    if re.search(r"oracle[/_.]|liboracle|mpi_shim", text):
+                    if re.search(r"oracle[/_.]|liboracle|mpi_shim|cpusim|CPUSIM", text):
                         bad.append(os.path.join(dirpath, f))
-    assert not bad, f"product files reference oracle/: {bad}"
+    assert not bad, f"product files reference oracle/ or the test-only simulator: {bad}"
+
+
+def test_product_library_does_not_contain_the_simulator():
+    """tests/cpusim builds its own library out of the product sources; the shipped library must not know about it"""
+    import subprocess
+
+    so = os.path.join(ROOT, "candmc_b200", "libcandmc_b200.so")
+    out = subprocess.run(["nm", "-D", so], capture_output=True, text=True, check=True).stdout
+    assert "cpusim" not in out
+    assert " T cudaMalloc" not in out   # the real (static) CUDA runtime is linked, nothing re-exports a fake one
 
 
 def test_lu_offload_library_exports_the_reference_entry_points():

@@ -22,3 +22,17 @@ elif mode == "uninit":       # beta = 0 must not read C; beta = 1 on never-writt
 elif mode == "gemm_range":   # a GEMM operand that runs past its allocation
     a = torch.ones(16, dtype=torch.float64, device="cuda"); c = torch.empty(16, dtype=torch.float64, device="cuda")
     cb.cdgemm("N", "N", 4, 4, 5, 1.0, a, 4, a, 5, 0.0, c, 4)
+elif mode in ("race", "ordered"):
+    # stream 1 clears a buffer, stream 2 copies it: without an event between them the copy may run first — the lifo
+    # scheduler makes sure it does; with cudaEventRecord / cudaStreamWaitEvent the result is the same under every policy
+    sim = simtorch.sim()
+    x = torch.ones(8, dtype=torch.float64, device="cuda"); y = torch.zeros(8, dtype=torch.float64, device="cuda")
+    s1, s2, ev = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    assert sim.cudaStreamCreateWithFlags(C.byref(s1), 1) == 0 and sim.cudaStreamCreateWithFlags(C.byref(s2), 1) == 0
+    assert sim.cudaEventCreateWithFlags(C.byref(ev), 2) == 0
+    assert sim.cudaMemsetAsync(C.c_void_p(x.data_ptr()), 0, C.c_size_t(64), s1) == 0
+    if mode == "ordered":
+        assert sim.cudaEventRecord(ev, s1) == 0 and sim.cudaStreamWaitEvent(s2, ev, 0) == 0
+    assert sim.cudaMemcpyAsync(C.c_void_p(y.data_ptr()), C.c_void_p(x.data_ptr()), C.c_size_t(64), 3, s2) == 0
+    assert sim.cudaDeviceSynchronize() == 0
+    print("copied", float(y.sum()))

@@ -13,7 +13,15 @@
 #include <string.h>
 #include <time.h>
 
+#include <sched.h>
+
+#include <algorithm>
+#include <deque>
+#include <functional>
 #include <map>
+#include <vector>
+
+#include "sim_internal.h"
 
 namespace {
 
@@ -28,14 +36,62 @@ std::map<uintptr_t, Alloc> g_allocs;   // user base -> allocation
 cudaError_t g_last = cudaSuccess;
 int g_device = 0;
 
-struct SimStream {
-  int id;
-};
 struct SimEvent {
-  double ms;
-  bool recorded;
+  double ms = 0.0;
+  uint64_t gen_enq = 0;    // cudaEventRecord calls issued
+  uint64_t gen_done = 0;   // ... and executed
 };
+
+enum TaskKind { T_RUN, T_RECORD, T_WAIT, T_NCCL };
+struct Task {
+  TaskKind kind = T_RUN;
+  uint64_t seq = 0;
+  std::function<void()> fn;
+  SimEvent* ev = nullptr;
+  uint64_t gen = 0;
+  cpusim::NcclBatch* batch = nullptr;
+  bool started = false;
+};
+struct SimStream {
+  int id = 0;
+  std::deque<Task> q;
+};
+enum Policy { P_SYNC, P_FIFO, P_LIFO, P_RANDOM };
+Policy g_policy = P_SYNC;
+uint64_t g_rng = 0x9E3779B97F4A7C15ull;
+SimStream g_null;
+std::vector<SimStream*> g_streams{&g_null};
+uint64_t g_seq = 0;
 int g_next_stream = 1;
+bool g_draining = false;
+uint64_t g_executed = 0, g_reordered = 0, g_max_seq_run = 0;   // tasks run / run after a task that was enqueued later
+
+struct PolicyInit {
+  PolicyInit() {
+    const char* e = getenv("CPUSIM_SCHED");
+    if (!e || !strcmp(e, "sync")) return;
+    if (!strcmp(e, "fifo")) g_policy = P_FIFO;
+    else if (!strcmp(e, "lifo")) g_policy = P_LIFO;
+    else if (!strncmp(e, "random", 6)) {
+      g_policy = P_RANDOM;
+      if (e[6] == ':') g_rng ^= strtoull(e + 7, nullptr, 10) * 0xD1B54A32D192ED03ull;
+    } else {
+      fprintf(stderr, "cpusim: unknown CPUSIM_SCHED=%s (sync | fifo | lifo | random:<seed>)\n", e);
+      abort();
+    }
+  }
+} g_policy_init;
+
+SimStream* S(cudaStream_t s) {
+  // 0, cudaStreamLegacy (1) and cudaStreamPerThread (2) are one queue here; the product's own streams are all created
+  // cudaStreamNonBlocking, so the legacy stream's implicit synchronisation with blocking streams never applies
+  return reinterpret_cast<uintptr_t>(s) <= 2 ? &g_null : reinterpret_cast<SimStream*>(s);
+}
+
+void push(SimStream* st, Task&& t) {
+  t.seq = g_seq++;
+  st->q.push_back(std::move(t));
+}
 
 double now_ms() {
   timespec t;
@@ -145,8 +201,124 @@ void check_copy(void* dst, const void* src, size_t dst_span, size_t src_span, cu
   }
 }
 
+double now_s2() { return now_ms() * 1e-3; }
+
+// Runs queued work until pred() holds.  Exactly one runnable stream head is executed per iteration (chosen by the policy);
+// every NCCL batch that has started is progressed a step per iteration, so batches on different streams overlap as they
+// do on a GPU.
+void drain(const std::function<bool()>& pred, const char* why) {
+  if (g_policy == P_SYNC) return;
+  if (g_draining) {
+    fprintf(stderr, "cpusim: synchronisation (%s) from inside a queued task\n", why);
+    abort();
+  }
+  g_draining = true;
+  static double timeout = getenv("CPUSIM_TIMEOUT") ? atof(getenv("CPUSIM_TIMEOUT")) : 60.0;
+  static std::vector<cpusim::NcclBatch*> active;
+  double last = now_s2();
+  long idle = 0;
+  while (!pred()) {
+    bool any = false;
+    SimStream* pick = nullptr;
+    int ncand = 0;
+    for (SimStream* st : g_streams) {
+      if (st->q.empty()) continue;
+      Task& t = st->q.front();
+      if (t.kind == T_NCCL && t.started) continue;
+      if (t.kind == T_WAIT && t.ev->gen_done < t.gen) continue;
+      ++ncand;
+      if (!pick) {
+        pick = st;
+      } else if (g_policy == P_FIFO) {
+        if (t.seq < pick->q.front().seq) pick = st;
+      } else if (g_policy == P_LIFO) {
+        if (t.seq > pick->q.front().seq) pick = st;
+      } else {  // reservoir sampling
+        g_rng ^= g_rng << 13;
+        g_rng ^= g_rng >> 7;
+        g_rng ^= g_rng << 17;
+        if (g_rng % (uint64_t)ncand == 0) pick = st;
+      }
+    }
+    if (pick) {
+      Task& t = pick->q.front();
+      ++g_executed;
+      if (t.seq < g_max_seq_run) ++g_reordered;
+      else g_max_seq_run = t.seq;
+      if (t.kind == T_NCCL) {
+        t.started = true;
+        active.push_back(t.batch);
+      } else {
+        Task run = std::move(t);
+        pick->q.pop_front();
+        if (run.kind == T_RUN) {
+          run.fn();
+        } else if (run.kind == T_RECORD) {
+          if (run.gen > run.ev->gen_done) run.ev->gen_done = run.gen;
+          run.ev->ms = now_ms();
+        }
+      }
+      any = true;
+    }
+    if (!active.empty()) {
+      any |= cpusim::nccl_progress(active);
+      for (size_t i = 0; i < active.size();) {
+        if (!cpusim::nccl_done(active[i])) {
+          ++i;
+          continue;
+        }
+        cpusim::NcclBatch* b = active[i];
+        active.erase(active.begin() + i);
+        for (SimStream* st : g_streams)
+          if (!st->q.empty() && st->q.front().kind == T_NCCL && st->q.front().batch == b) st->q.pop_front();
+        cpusim::nccl_finish(b);
+        any = true;
+      }
+    }
+    if (any) {
+      idle = 0;
+      last = now_s2();
+      continue;
+    }
+    if (!pick && active.empty()) {
+      fprintf(stderr, "cpusim: %s can never complete: every queued stream waits on an event that nobody will record\n", why);
+      abort();
+    }
+    if (++idle < 200) {
+      sched_yield();
+    } else {
+      timespec ts = {0, 50000};
+      nanosleep(&ts, nullptr);
+      if ((idle & 1023) == 0 && now_s2() - last > timeout) {
+        fprintf(stderr, "cpusim nccl: NO PROGRESS for %.0f s in %s — deadlock in the communication schedule?  Active operations:\n",
+                timeout, why);
+        for (cpusim::NcclBatch* b : active) cpusim::nccl_describe(b);
+        abort();
+      }
+    }
+  }
+  g_draining = false;
+}
+
+void drain_stream(cudaStream_t s) {
+  SimStream* st = S(s);
+  drain([st]() { return st->q.empty(); }, "a stream synchronisation");
+}
+void drain_all(const char* why) {
+  drain([]() {
+    for (SimStream* st : g_streams)
+      if (!st->q.empty()) return false;
+    return true;
+  }, why);
+}
+
 struct AtExit {
-  ~AtExit() { check_canaries("process exit"); }
+  ~AtExit() {
+    check_canaries("process exit");
+    if (getenv("CPUSIM_VERBOSE"))
+      fprintf(stderr, "cpusim: %llu queued tasks executed, %llu of them after a task that was enqueued later\n",
+              (unsigned long long)g_executed, (unsigned long long)g_reordered);
+  }
 } g_at_exit;
 
 CUresult fake_encode_tiled(CUtensorMap* out, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -158,12 +330,45 @@ CUresult fake_encode_tiled(CUtensorMap* out, CUtensorMapDataType, cuuint32_t, vo
 
 }  // namespace
 
+namespace cpusim {
+
+void stream_submit(cudaStream_t s, std::function<void()> fn) {
+  if (g_policy == P_SYNC) {
+    fn();
+    return;
+  }
+  Task t;
+  t.kind = T_RUN;
+  t.fn = std::move(fn);
+  push(S(s), std::move(t));
+}
+
+void stream_submit_nccl(cudaStream_t s, NcclBatch* b) {
+  if (g_policy == P_SYNC) {
+    run_batch_blocking(b);
+    return;
+  }
+  Task t;
+  t.kind = T_NCCL;
+  t.batch = b;
+  push(S(s), std::move(t));
+}
+
+}  // namespace cpusim
+
 extern "C" {
 
 // helpers for the Python side of the tests (simtorch.py)
 void* cpusim_malloc(size_t bytes) { return sim_alloc(bytes, true); }
-void cpusim_check(void) { check_canaries("cpusim_check"); }
+void cpusim_check(void) {   // what torch.cuda.synchronize() becomes
+  drain_all("torch.cuda.synchronize");
+  check_canaries("cpusim_check");
+}
 void cpusim_require_device_range(const void* p, size_t bytes, const char* what) { check_range(p, bytes, true, what); }
+void cpusim_sched_stats(unsigned long long* executed, unsigned long long* reordered) {
+  *executed = g_executed;
+  *reordered = g_reordered;
+}
 int cpusim_is_device(const void* p) {
   const Alloc* a = find_alloc(p);
   return a && a->device;
@@ -199,6 +404,7 @@ cudaError_t cudaGetLastError(void) {
   return e;
 }
 cudaError_t cudaDeviceSynchronize(void) {
+  drain_all("cudaDeviceSynchronize");
   check_canaries("cudaDeviceSynchronize");
   return cudaSuccess;
 }
@@ -207,7 +413,10 @@ cudaError_t cudaMalloc(void** p, size_t bytes) {
   *p = sim_alloc(bytes, true);
   return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
-cudaError_t cudaFree(void* p) { return sim_free(p, true); }
+cudaError_t cudaFree(void* p) {
+  if (p) drain_all("cudaFree");  // cudaFree synchronises the device
+  return sim_free(p, true);
+}
 cudaError_t cudaMallocHost(void** p, size_t bytes) {
   *p = sim_alloc(bytes, false);
   return *p ? cudaSuccess : cudaErrorMemoryAllocation;
@@ -225,18 +434,36 @@ cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* attr, const void* p)
   return cudaSuccess;
 }
 
-cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t) {
+static bool pageable(const void* p) { return find_alloc(p) == nullptr; }
+
+// CUDA's rules for "async" copies that touch pageable host memory: host->device waits for the stream, stages the source
+// and may return before the DMA has landed (modelled: stream sync, then the copy happens now); device->pageable host
+// returns only when the copy has completed (modelled: enqueue, then stream sync).  Pinned and device memory: truly async.
+static void submit_copy(cudaStream_t st, void* dst, const void* src, cudaMemcpyKind kind, std::function<void()> body) {
+  const bool src_pageable = pageable(src), dst_pageable = pageable(dst);
+  if (src_pageable) {
+    drain_stream(st);
+    body();
+    return;
+  }
+  cpusim::stream_submit(st, std::move(body));
+  if (dst_pageable) drain_stream(st);
+  (void)kind;
+}
+
+cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
   check_copy(dst, src, bytes, bytes, kind, "cudaMemcpyAsync");
-  memmove(dst, src, bytes);
+  submit_copy(st, dst, src, kind, [=]() { memmove(dst, src, bytes); });
   return cudaSuccess;
 }
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
   check_copy(dst, src, bytes, bytes, kind, "cudaMemcpy");
-  memmove(dst, src, bytes);
+  cpusim::stream_submit(nullptr, [=]() { memmove(dst, src, bytes); });
+  drain_stream(nullptr);
   return cudaSuccess;
 }
 cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
-                              cudaMemcpyKind kind, cudaStream_t) {
+                              cudaMemcpyKind kind, cudaStream_t st) {
   if (width == 0 || height == 0) return cudaSuccess;
   if (width > dpitch || width > spitch) {
     fprintf(stderr, "cpusim: cudaMemcpy2DAsync: width %zu exceeds a pitch (%zu, %zu)\n", width, dpitch, spitch);
@@ -244,57 +471,94 @@ cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t 
     return cudaErrorInvalidPitchValue;
   }
   check_copy(dst, src, dpitch * (height - 1) + width, spitch * (height - 1) + width, kind, "cudaMemcpy2DAsync");
-  for (size_t r = 0; r < height; ++r) memmove((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
+  submit_copy(st, dst, src, kind, [=]() {
+    for (size_t r = 0; r < height; ++r) memmove((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
+  });
   return cudaSuccess;
 }
-cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t) {
+cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t st) {
   check_range(p, bytes, true, "cudaMemsetAsync");
-  memset(p, v, bytes);
+  cpusim::stream_submit(st, [=]() { memset(p, v, bytes); });
   return cudaSuccess;
 }
-cudaError_t cudaMemset(void* p, int v, size_t bytes) { return cudaMemsetAsync(p, v, bytes, nullptr); }
+cudaError_t cudaMemset(void* p, int v, size_t bytes) {
+  cudaMemsetAsync(p, v, bytes, nullptr);
+  drain_stream(nullptr);
+  return cudaSuccess;
+}
 
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
-  SimStream* st = new SimStream{g_next_stream++};
+  SimStream* st = new SimStream();
+  st->id = g_next_stream++;
+  g_streams.push_back(st);
   *s = reinterpret_cast<cudaStream_t>(st);
   return cudaSuccess;
 }
 cudaError_t cudaStreamCreate(cudaStream_t* s) { return cudaStreamCreateWithFlags(s, 0); }
 cudaError_t cudaStreamDestroy(cudaStream_t s) {
-  delete reinterpret_cast<SimStream*>(s);
+  drain_stream(s);  // CUDA lets pending work finish before the stream goes away
+  SimStream* st = S(s);
+  g_streams.erase(std::find(g_streams.begin(), g_streams.end(), st));
+  delete st;
   return cudaSuccess;
 }
-cudaError_t cudaStreamSynchronize(cudaStream_t) {
+cudaError_t cudaStreamSynchronize(cudaStream_t s) {
+  drain_stream(s);
   check_canaries("cudaStreamSynchronize");
   return cudaSuccess;
 }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t e, unsigned) {
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) {
   if (!e) {
     fprintf(stderr, "cpusim: cudaStreamWaitEvent on a null event\n");
     abort();
   }
-  return cudaSuccess;  // synchronous streams: whatever the event covers has already happened
+  SimEvent* ev = reinterpret_cast<SimEvent*>(e);
+  if (g_policy == P_SYNC || ev->gen_enq == 0) return cudaSuccess;  // nothing recorded yet: a no-op, as in CUDA
+  Task t;
+  t.kind = T_WAIT;
+  t.ev = ev;
+  t.gen = ev->gen_enq;  // the most recent record at the time of THIS call
+  push(S(s), std::move(t));
+  return cudaSuccess;
 }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) {
-  *e = reinterpret_cast<cudaEvent_t>(new SimEvent{0.0, false});
+  *e = reinterpret_cast<cudaEvent_t>(new SimEvent());
   return cudaSuccess;
 }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { return cudaEventCreateWithFlags(e, 0); }
 cudaError_t cudaEventDestroy(cudaEvent_t e) {
-  delete reinterpret_cast<SimEvent*>(e);
-  return cudaSuccess;
-}
-cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
   SimEvent* ev = reinterpret_cast<SimEvent*>(e);
-  ev->ms = now_ms();
-  ev->recorded = true;
+  if (ev->gen_done >= ev->gen_enq) delete ev;  // else: queued tasks still point at it; CUDA defers the release too (leaked here)
   return cudaSuccess;
 }
-cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) {
+  SimEvent* ev = reinterpret_cast<SimEvent*>(e);
+  ev->gen_enq++;
+  if (g_policy == P_SYNC) {
+    ev->gen_done = ev->gen_enq;
+    ev->ms = now_ms();
+    return cudaSuccess;
+  }
+  Task t;
+  t.kind = T_RECORD;
+  t.ev = ev;
+  t.gen = ev->gen_enq;
+  push(S(s), std::move(t));
+  return cudaSuccess;
+}
+cudaError_t cudaEventQuery(cudaEvent_t e) {
+  SimEvent* ev = reinterpret_cast<SimEvent*>(e);
+  return ev->gen_done >= ev->gen_enq ? cudaSuccess : cudaErrorNotReady;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t e) {
+  SimEvent* ev = reinterpret_cast<SimEvent*>(e);
+  drain([&]() { return ev->gen_done >= ev->gen_enq; }, "cudaEventSynchronize");
+  return cudaSuccess;
+}
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
   SimEvent *ea = reinterpret_cast<SimEvent*>(a), *eb = reinterpret_cast<SimEvent*>(b);
-  if (!ea->recorded || !eb->recorded) return cudaErrorInvalidResourceHandle;
+  if (ea->gen_enq == 0 || eb->gen_enq == 0) return cudaErrorInvalidResourceHandle;
+  if (ea->gen_done < ea->gen_enq || eb->gen_done < eb->gen_enq) return cudaErrorNotReady;
   *ms = (float)(eb->ms - ea->ms);
   return cudaSuccess;
 }

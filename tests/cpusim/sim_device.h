@@ -26,7 +26,7 @@ ThreadState& ts();        // state of the fiber that is running
 void* dyn_smem();         // dynamic shared memory of the running block
 void sync_threads();      // block barrier
 void sync_warp_exchange(const void* in, void* out, int src_lane, size_t bytes);  // one warp shuffle
-void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+void launch(cudaStream_t stream, dim3 grid, dim3 block, size_t smem, std::function<void()> body);
 
 }  // namespace cpusim
 
@@ -43,8 +43,15 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 #undef __shared__
 #define __shared__ static
 
+// kernel arguments are evaluated and copied when the launch is issued (as CUDA does), the body runs when the stream gets to it
+namespace cpusim {
+template <class K, class... Args>
+static inline void launch_args(cudaStream_t stream, dim3 grid, dim3 block, size_t smem, K kern, Args... args) {
+  launch(stream, grid, block, smem, [=]() { kern(args...); });
+}
+}  // namespace cpusim
 #define CPUSIM_LAUNCH(kern, grid, block, smem, stream, ...) \
-  ::cpusim::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); })
+  ::cpusim::launch_args((cudaStream_t)(stream), dim3(grid), dim3(block), (size_t)(smem), kern, ##__VA_ARGS__)
 
 static inline void __syncthreads() { ::cpusim::sync_threads(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}

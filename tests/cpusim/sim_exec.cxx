@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "sim_device.h"
+#include "sim_internal.h"
 
 namespace cpusim {
 
@@ -99,7 +100,21 @@ void sync_warp_exchange(const void* in, void* out, int src_lane, size_t bytes) {
   memcpy(out, w.slot[gen & 1][src_lane], bytes);
 }
 
-void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+static void execute(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+
+void launch(cudaStream_t stream, dim3 grid, dim3 block, size_t smem, std::function<void()> body) {
+  // the launch configuration is validated when the launch is issued, the kernel runs when its stream gets to it
+  const long nthreads = (long)block.x * block.y * block.z;
+  if (nthreads <= 0 || nthreads > kMaxThreads || smem > 227 * 1024 || grid.x == 0 || grid.y == 0 || grid.z == 0 ||
+      grid.y > 65535 || grid.z > 65535) {
+    fprintf(stderr, "cpusim: invalid launch configuration grid=(%u,%u,%u) block=(%u,%u,%u) smem=%zu\n", grid.x, grid.y,
+            grid.z, block.x, block.y, block.z, smem);
+    abort();
+  }
+  stream_submit(stream, [=]() { execute(grid, block, smem, body); });
+}
+
+static void execute(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
   if (g_cur >= 0) {
     fprintf(stderr, "cpusim: nested kernel launch\n");
     abort();

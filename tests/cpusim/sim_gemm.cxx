@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "ipc.h"
 #include "runtime.h"
+#include "sim_internal.h"
 
 #include <algorithm>
 #include <vector>
@@ -48,31 +49,32 @@ int gemm_f64_fused(char transa, char transb, int64_t m, int64_t n, int64_t k, do
     cpusim_require_device_range(B, span(rowsB, colsB, ldb), "dgemm B");
   }
   if ((k == 0 || alpha == 0.0) && beta == 1.0) return OK;
+  cpusim::stream_submit(stream, [=]() {
   // op(A) packed m x k, then column-by-column axpy (vectorisable inner loop); summation order over k is 0..k-1
-  std::vector<double> Ap, acc((size_t)m);
-  const double* Aop = A;
-  int64_t lda_op = lda;
-  if (tA && k > 0 && alpha != 0.0) {
-    Ap.resize((size_t)m * k);
-    for (int64_t p = 0; p < k; ++p)
-      for (int64_t i = 0; i < m; ++i) Ap[i + p * m] = A[p + i * lda];
-    Aop = Ap.data();
-    lda_op = m;
-  }
-  for (int64_t j = 0; j < n; ++j) {
-    std::fill(acc.begin(), acc.end(), 0.0);
-    if (alpha != 0.0)
-      for (int64_t p = 0; p < k; ++p) {
-        const double bv = tB ? B[j + p * ldb] : B[p + j * ldb];
-        const double* a = Aop + p * lda_op;
-        for (int64_t i = 0; i < m; ++i) acc[i] += a[i] * bv;
-      }
-    double* c = C + j * ldc;
-    for (int64_t i = 0; i < m; ++i)
-      c[i] = beta == 0.0 ? alpha * acc[i] : alpha * acc[i] + beta * c[i];  // beta == 0 never reads C, as in the kernel
-  }
+    std::vector<double> Ap, acc((size_t)m);
+    const double* Aop = A;
+    int64_t lda_op = lda;
+    if (tA && k > 0 && alpha != 0.0) {
+      Ap.resize((size_t)m * k);
+      for (int64_t p = 0; p < k; ++p)
+        for (int64_t i = 0; i < m; ++i) Ap[i + p * m] = A[p + i * lda];
+      Aop = Ap.data();
+      lda_op = m;
+    }
+    for (int64_t j = 0; j < n; ++j) {
+      std::fill(acc.begin(), acc.end(), 0.0);
+      if (alpha != 0.0)
+        for (int64_t p = 0; p < k; ++p) {
+          const double bv = tB ? B[j + p * ldb] : B[p + j * ldb];
+          const double* a = Aop + p * lda_op;
+          for (int64_t i = 0; i < m; ++i) acc[i] += a[i] * bv;
+        }
+      double* c = C + j * ldc;
+      for (int64_t i = 0; i < m; ++i)
+        c[i] = beta == 0.0 ? alpha * acc[i] : alpha * acc[i] + beta * c[i];  // beta == 0 never reads C, as in the kernel
+    }
+  });
   runtime().launches++;
-  (void)stream;
   return OK;
 }
 

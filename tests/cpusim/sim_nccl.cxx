@@ -29,6 +29,8 @@
 #include <functional>
 #include <vector>
 
+#include "sim_internal.h"
+
 namespace {
 
 constexpr int kMaxRanks = 16;
@@ -111,9 +113,20 @@ namespace {
 
 struct Request {
   std::vector<Op> ops;
-  std::function<void()> finish;
+  std::function<void()> start;    // local copies that belong to the operation (root's send -> recv, own all-gather slot)
+  std::function<void()> finish;   // reductions, once every contribution has arrived
   World* w;
+  cudaStream_t stream = nullptr;
 };
+
+}  // namespace
+
+struct cpusim::NcclBatch {
+  std::vector<Request*> reqs;
+  bool started = false;
+};
+
+namespace {
 
 int g_group_depth = 0;
 std::vector<Request*> g_pending;
@@ -290,31 +303,89 @@ bool progress_recvs(World* w, std::vector<Op*>& ops) {
   return any;
 }
 
-void run_requests(std::vector<Request*>& reqs) {
-  if (reqs.empty()) return;
-  static double timeout = getenv("CPUSIM_TIMEOUT") ? atof(getenv("CPUSIM_TIMEOUT")) : 60.0;
-  // group by world (in practice one)
-  std::vector<World*> worlds;
+// group the requests of one ncclGroup (or one ungrouped call) by stream and hand them to the stream scheduler
+void flush_pending() {
+  std::vector<Request*> reqs;
+  reqs.swap(g_pending);
+  std::vector<cudaStream_t> streams;
   for (Request* r : reqs)
-    if (std::find(worlds.begin(), worlds.end(), r->w) == worlds.end()) worlds.push_back(r->w);
-  std::vector<std::vector<Op*>> per_world(worlds.size());
-  for (Request* r : reqs) {
-    size_t wi = std::find(worlds.begin(), worlds.end(), r->w) - worlds.begin();
-    for (Op& o : r->ops) per_world[wi].push_back(&o);
+    if (std::find(streams.begin(), streams.end(), r->stream) == streams.end()) streams.push_back(r->stream);
+  for (cudaStream_t st : streams) {
+    cpusim::NcclBatch* b = new cpusim::NcclBatch();
+    for (Request* r : reqs)
+      if (r->stream == st) b->reqs.push_back(r);
+    cpusim::stream_submit_nccl(st, b);
   }
-  double last_progress = now_s();
+}
+
+void submit(Request* r, cudaStream_t st) {
+  r->stream = st;
+  g_pending.push_back(r);
+  if (g_group_depth == 0) flush_pending();
+}
+
+}  // namespace
+
+namespace cpusim {
+
+bool nccl_progress(std::vector<NcclBatch*>& active) {
+  std::vector<World*> worlds;
+  std::vector<std::vector<Op*>> ops;
+  for (NcclBatch* b : active) {
+    if (!b->started) {
+      b->started = true;
+      for (Request* r : b->reqs)
+        if (r->start) r->start();
+    }
+    for (Request* r : b->reqs) {
+      size_t wi = std::find(worlds.begin(), worlds.end(), r->w) - worlds.begin();
+      if (wi == worlds.size()) {
+        worlds.push_back(r->w);
+        ops.emplace_back();
+      }
+      for (Op& o : r->ops) ops[wi].push_back(&o);
+    }
+  }
+  bool any = false;
+  for (size_t wi = 0; wi < worlds.size(); ++wi) {
+    any |= progress_sends(worlds[wi], ops[wi]);
+    any |= progress_recvs(worlds[wi], ops[wi]);
+  }
+  return any;
+}
+
+bool nccl_done(const NcclBatch* b) {
+  if (!b->started) return false;
+  for (const Request* r : b->reqs)
+    for (const Op& o : r->ops)
+      if (!o.complete) return false;
+  return true;
+}
+
+void nccl_finish(NcclBatch* b) {
+  for (Request* r : b->reqs) {
+    if (r->finish) r->finish();
+    delete r;
+  }
+  delete b;
+}
+
+void nccl_describe(const NcclBatch* b) {
+  for (const Request* r : b->reqs)
+    for (const Op& o : r->ops) describe(o, r->w->rank);
+}
+
+void run_batch_blocking(NcclBatch* b) {
+  static double timeout = getenv("CPUSIM_TIMEOUT") ? atof(getenv("CPUSIM_TIMEOUT")) : 60.0;
+  std::vector<NcclBatch*> active{b};
+  double last = now_s();
   long idle = 0;
   for (;;) {
-    bool all = true, any = false;
-    for (size_t wi = 0; wi < worlds.size(); ++wi) {
-      any |= progress_sends(worlds[wi], per_world[wi]);
-      any |= progress_recvs(worlds[wi], per_world[wi]);
-      for (Op* o : per_world[wi]) all &= o->complete;
-    }
-    if (all) break;
+    const bool any = nccl_progress(active);
+    if (nccl_done(b)) break;
     if (any) {
       idle = 0;
-      last_progress = now_s();
+      last = now_s();
       continue;
     }
     if (++idle < 200) {
@@ -322,26 +393,20 @@ void run_requests(std::vector<Request*>& reqs) {
     } else {
       timespec ts = {0, 50000};
       nanosleep(&ts, nullptr);
-      if ((idle & 1023) == 0 && now_s() - last_progress > timeout) {
+      if ((idle & 1023) == 0 && now_s() - last > timeout) {
         fprintf(stderr, "cpusim nccl: NO PROGRESS for %.0f s — deadlock in the communication schedule?  Operations of this call:\n",
                 timeout);
-        for (size_t wi = 0; wi < worlds.size(); ++wi)
-          for (Op* o : per_world[wi]) describe(*o, worlds[wi]->rank);
+        nccl_describe(b);
         abort();
       }
     }
   }
-  for (Request* r : reqs) {
-    if (r->finish) r->finish();
-    delete r;
-  }
-  reqs.clear();
+  nccl_finish(b);
 }
 
-void submit(Request* r) {
-  g_pending.push_back(r);
-  if (g_group_depth == 0) run_requests(g_pending);
-}
+}  // namespace cpusim
+
+namespace {
 
 Request* new_request(ncclComm* c) {
   Request* r = new Request();
@@ -380,8 +445,9 @@ void allgather_now(ncclComm* c, const void* mine, void* all, size_t bytes, uint3
     add_op(r, c, false, p, static_cast<char*>(all) + (size_t)p * bytes, bytes, kind, seq);
   }
   memmove(static_cast<char*>(all) + (size_t)c->rank * bytes, mine, bytes);
-  std::vector<Request*> one{r};
-  run_requests(one);
+  cpusim::NcclBatch* b = new cpusim::NcclBatch();
+  b->reqs.push_back(r);
+  cpusim::run_batch_blocking(b);
 }
 
 void world_release(World* w) {
@@ -502,11 +568,11 @@ ncclResult_t ncclGroupStart(void) {
 }
 ncclResult_t ncclGroupEnd(void) {
   if (g_group_depth <= 0) return ncclInvalidUsage;
-  if (--g_group_depth == 0) run_requests(g_pending);
+  if (--g_group_depth == 0) flush_pending();
   return ncclSuccess;
 }
 
-ncclResult_t ncclSend(const void* buf, size_t count, ncclDataType_t t, int peer, ncclComm_t c, cudaStream_t) {
+ncclResult_t ncclSend(const void* buf, size_t count, ncclDataType_t t, int peer, ncclComm_t c, cudaStream_t st) {
   if (peer < 0 || peer >= (int)c->members.size() || peer == c->rank) {
     snprintf(g_errbuf, sizeof(g_errbuf), "cpusim: ncclSend to invalid peer %d (comm size %zu, my rank %d)", peer, c->members.size(),
              c->rank);
@@ -514,10 +580,10 @@ ncclResult_t ncclSend(const void* buf, size_t count, ncclDataType_t t, int peer,
   }
   Request* r = new_request(c);
   add_op(r, c, true, peer, buf, count * type_size(t), K_P2P, 0);
-  submit(r);
+  submit(r, st);
   return ncclSuccess;
 }
-ncclResult_t ncclRecv(void* buf, size_t count, ncclDataType_t t, int peer, ncclComm_t c, cudaStream_t) {
+ncclResult_t ncclRecv(void* buf, size_t count, ncclDataType_t t, int peer, ncclComm_t c, cudaStream_t st) {
   if (peer < 0 || peer >= (int)c->members.size() || peer == c->rank) {
     snprintf(g_errbuf, sizeof(g_errbuf), "cpusim: ncclRecv from invalid peer %d (comm size %zu, my rank %d)", peer,
              c->members.size(), c->rank);
@@ -525,29 +591,29 @@ ncclResult_t ncclRecv(void* buf, size_t count, ncclDataType_t t, int peer, ncclC
   }
   Request* r = new_request(c);
   add_op(r, c, false, peer, buf, count * type_size(t), K_P2P, 0);
-  submit(r);
+  submit(r, st);
   return ncclSuccess;
 }
 
-ncclResult_t ncclBroadcast(const void* send, void* recv, size_t count, ncclDataType_t t, int root, ncclComm_t c, cudaStream_t) {
+ncclResult_t ncclBroadcast(const void* send, void* recv, size_t count, ncclDataType_t t, int root, ncclComm_t c, cudaStream_t st) {
   const int P = (int)c->members.size();
   if (root < 0 || root >= P) return ncclInvalidArgument;
   const size_t bytes = count * type_size(t);
   Request* r = new_request(c);
   const uint32_t seq = c->seq++;
   if (c->rank == root) {
-    if (send != recv) memmove(recv, send, bytes);
+    if (send != recv) r->start = [=]() { memmove(recv, send, bytes); };
     for (int p = 0; p < P; ++p)
       if (p != root) add_op(r, c, true, p, recv, bytes, K_BCAST, seq);
   } else {
     add_op(r, c, false, root, recv, bytes, K_BCAST, seq);
   }
-  submit(r);
+  submit(r, st);
   return ncclSuccess;
 }
 
 static ncclResult_t reduce_common(const void* send, void* recv, size_t count, ncclDataType_t t, ncclRedOp_t op, ncclComm_t c,
-                                  bool scatter) {
+                                  bool scatter, cudaStream_t st) {
   if (t != ncclFloat64 || op != ncclSum) {
     snprintf(g_errbuf, sizeof(g_errbuf), "cpusim: only float64 sums are implemented");
     return ncclInvalidArgument;
@@ -574,32 +640,32 @@ static ncclResult_t reduce_common(const void* send, void* recv, size_t count, nc
     }
     delete tmp;
   };
-  submit(r);
+  submit(r, st);
   return ncclSuccess;
 }
 
 ncclResult_t ncclAllReduce(const void* send, void* recv, size_t count, ncclDataType_t t, ncclRedOp_t op, ncclComm_t c,
-                           cudaStream_t) {
-  return reduce_common(send, recv, count, t, op, c, false);
+                           cudaStream_t st) {
+  return reduce_common(send, recv, count, t, op, c, false, st);
 }
 ncclResult_t ncclReduceScatter(const void* send, void* recv, size_t recvcount, ncclDataType_t t, ncclRedOp_t op, ncclComm_t c,
-                               cudaStream_t) {
-  return reduce_common(send, recv, recvcount, t, op, c, true);
+                               cudaStream_t st) {
+  return reduce_common(send, recv, recvcount, t, op, c, true, st);
 }
 
-ncclResult_t ncclAllGather(const void* send, void* recv, size_t sendcount, ncclDataType_t t, ncclComm_t c, cudaStream_t) {
+ncclResult_t ncclAllGather(const void* send, void* recv, size_t sendcount, ncclDataType_t t, ncclComm_t c, cudaStream_t st) {
   const int P = (int)c->members.size(), me = c->rank;
   const size_t bytes = sendcount * type_size(t);
   Request* r = new_request(c);
   const uint32_t seq = c->seq++;
   char* out = static_cast<char*>(recv);
-  if (out + (size_t)me * bytes != send) memmove(out + (size_t)me * bytes, send, bytes);
+  if (out + (size_t)me * bytes != send) r->start = [=]() { memmove(out + (size_t)me * bytes, send, bytes); };
   for (int p = 0; p < P; ++p) {
     if (p == me) continue;
     add_op(r, c, true, p, out + (size_t)me * bytes, bytes, K_ALLGATHER, seq);
     add_op(r, c, false, p, out + (size_t)p * bytes, bytes, K_ALLGATHER, seq);
   }
-  submit(r);
+  submit(r, st);
   return ncclSuccess;
 }
 

@@ -29,6 +29,8 @@ from .mm import (  # noqa: F401
     update_Yamamoto_A,
     cyclic_to_blocked,
     blocked_to_cyclic,
+    sym_full2band_update,
+    sym_full2band_extents,
 )
 from .grid import (  # noqa: F401
     init_world,

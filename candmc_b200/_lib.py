@@ -81,6 +81,8 @@ SIGNATURES = {
     "candmc_update_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, C.POINTER(PView), pd, i64, C.c_int, C.c_void_p]),
     "candmc_upd_Yamamoto_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, comm_p, C.c_void_p]),
     "candmc_update_Yamamoto_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, C.POINTER(PView), C.c_void_p]),
+    "candmc_sym_full2band_update": (C.c_int, [pd, i64, i64, i64, i64, C.POINTER(PView), comm_p, pd, i64, C.c_void_p]),
+    "candmc_sym_full2band_extents": (C.c_int, [i64, i64, i64] + [C.c_int] * 5 + [C.POINTER(i64)] * 4),
     "candmc_set_min_kchunk": (C.c_int, [i64]),
     "candmc_set_host_pipeline_min": (C.c_int, [i64]),
     "candmc_redistribute": (C.c_int, [C.c_int, i64, i64, i64, pd, i64, pd, i64, C.POINTER(PView), C.c_void_p]),

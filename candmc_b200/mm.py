@@ -194,6 +194,22 @@ def update_Yamamoto_A(Qm, lda_Qm, A, lda_A, m, k, b, T, pv: pview, agg=None, str
     check(lib().candmc_update_Yamamoto_A(_ptr(Qm), lda_Qm, _ptr(A), lda_A, m, k, b, _ptr(T), C.byref(cpv), _stream(stream)))
 
 
+def sym_full2band_extents(n, b, b_sub, np_, myrow, mycol, rrow, rcol):
+    """(loc_row_offset, loc_col_offset, mb, kb) of one level of sym_full2band (alg/SE/full_to_band.cxx:57-79)."""
+    out = [C.c_int64() for _ in range(4)]
+    check(lib().candmc_sym_full2band_extents(n, b, b_sub, np_, myrow, mycol, rrow, rcol, *[C.byref(o) for o in out]))
+    return tuple(o.value for o in out)
+
+
+def sym_full2band_update(A, lda_A, n, b, b_sub, pv: pview, cdiag: CommData_t | None, Y, lda_Y, stream=None):
+    """The trailing update of one level of sym_full2band (alg/SE/full_to_band.cxx:90-239) given the panel QR's aggregated Y:
+    A (pointer at the level's working corner) -= U V' + V U' on the trailing block.  pv is NOT rotated (the caller does,
+    :90,245); the panel QR itself (QR_2D_pipe, :96) is host-side TSQR and outside this library's scope."""
+    cpv = _lib.PView(pv.rrow, pv.rcol, pv.crow.cm, pv.ccol.cm, pv.cworld.cm if pv.cworld else None)
+    check(lib().candmc_sym_full2band_update(_ptr(A), lda_A, n, b, b_sub, C.byref(cpv), cdiag.cm if cdiag else None, _ptr(Y),
+                                            lda_Y, _stream(stream)))
+
+
 def cyclic_to_blocked(m, n, nb, A_cyc, lda_cyc, A_blk, lda_blk, pv: pview, stream=None):
     """Local piece of an m x n block-cyclic matrix (block nb, roots pv.rrow / pv.rcol: the layout of the reference's
     QR / SE drivers, test/QR/test_qr_2d.cxx:87-94) -> the blocked layout of the CANMM multiplies."""

@@ -200,6 +200,25 @@ int candmc_set_min_kchunk(int64_t min_kchunk);
  * column panels (upload of panel j+1 and download of panel j-1 under the GEMM of panel j) instead of staged whole. */
 int candmc_set_host_pipeline_min(int64_t min_n);
 
+/* ---- symmetric full -> band reduction, trailing update ----------------------------------------
+ * One level of sym_full2band (alg/SE/full_to_band.cxx:28-250) after its panel QR (:96): given the aggregated Householder
+ * panel Y the QR left on every rank (mb x b, replicated along grid rows), forms invT (compute_invT_from_Y,
+ * alg/QR/qr_2d/qr_2d.cxx:22-60), W = Y^T A (:122) summed over the grid column (:126-130), on the diagonal ranks
+ * Z = Y^T W^T (:157, all-reduced over `cdiag` :161), U = Y invT^-1 (:172), V' = W - Z U^T / 2 (:186), broadcasts V' down
+ * the columns and U along the rows (:205-207), multiplies UV' (:213), swaps it with the transposed grid partner (:222-224)
+ * and applies A -= UV' + VU' to the trailing block (:239-241).
+ * A points at the level's working corner (the reference's `A` argument, NOT the trailing block), pv holds the roots at
+ * that corner as on entry to the reference routine (it is not modified: the caller rotates rrow / rcol by b / b_sub for
+ * the next level, :90,245), cdiag is the communicator of the diagonal ranks (ignored elsewhere; test/SE/test_full2band.cxx:
+ * 161-173).  Square grid, rank = row + col * np.  Requires (b / b_sub) and ((n - b) / b_sub) to be multiples of the grid
+ * dimension (outside that the reference itself corrupts its heap).  Device pointers; asynchronous on `stream`. */
+int candmc_sym_full2band_update(double* A, int64_t lda_A, int64_t n, int64_t b, int64_t b_sub, const candmc_pview_t* pv,
+                                candmc_comm_t* cdiag, const double* Y, int64_t lda_Y, void* stream);
+/* The offsets and extents of that level on grid position (myrow, mycol) (full_to_band.cxx:57-79): where the trailing block
+ * starts inside the local array (rows, columns) and its local size.  Host arithmetic only. */
+int candmc_sym_full2band_extents(int64_t n, int64_t b, int64_t b_sub, int np, int myrow, int mycol, int rrow, int rcol,
+                                 int64_t* loc_row_offset, int64_t* loc_col_offset, int64_t* mb, int64_t* kb);
+
 /* ---- block-cyclic <-> blocked redistribution ------------------------------------------------
  * Converts the local piece of an m x n matrix between the ScaLAPACK-style block-cyclic layout of the reference's QR / SE
  * drivers (block nb, global block row I on grid row (I + pv->rrow) mod nprow at local block row I div nprow; columns

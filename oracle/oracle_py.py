@@ -323,3 +323,87 @@ def dmat_slice(piece, nrow, ncol, b, nprow, npcol, rrow, rcol, myrow, mycol, fir
     mr1, mc1 = dmat_extent(nrow - firstrow, b, nprow, myrow, nr), dmat_extent(ncol - firstcol, b, npcol, mycol, nc)
     mr2, mc2 = dmat_extent(numrows, b, nprow, myrow, nr), dmat_extent(numcols, b, npcol, mycol, nc)
     return piece[mr0 - mr1:mr0 - mr1 + mr2, mc0 - mc1:mc0 - mc1 + mc2], nr, nc
+
+
+# ---- symmetric full -> band trailing update (alg/SE/full_to_band.cxx:28-250), all ranks simulated ------------
+def _cmod(a, p):
+    """C's truncating % (the reference's extent formulas subtract before taking the remainder, full_to_band.cxx:70,77)."""
+    return int(np.fmod(a, p))
+
+
+def f2b_level(n, b, b_sub, pr, rrow, rcol, myrow, mycol):
+    """Offsets and extents one level of sym_full2band uses on rank (myrow, mycol) of a pr x pr grid (full_to_band.cxx:57-79):
+    (loc_row_offset, loc_col_offset in columns, mb, kb)."""
+    s = b // b_sub
+    ro = b_sub * (b // (b_sub * pr)) + (b_sub if (myrow + pr - rrow) % pr < s % pr else 0)
+    co = b_sub * (b // (b_sub * pr)) + (b_sub if (mycol + pr - rcol) % pr < s % pr else 0)
+    t = (n - b) // b_sub
+    mb = (t // pr + (1 if _cmod(myrow + pr - rrow - s % pr, pr) < t % pr else 0)) * b_sub
+    kb = (t // pr + (1 if _cmod(mycol + pr - rcol - s % pr, pr) < t % pr else 0)) * b_sub
+    return ro, co, mb, kb
+
+
+def f2b_invT(Ycol, b):
+    """compute_invT_from_Y (alg/QR/qr_2d/qr_2d.cxx:22-60): lower triangle of the column sum of Y_i^T Y_i, diagonal halved."""
+    S = np.zeros((b, b))
+    for Y in Ycol:
+        if Y.shape[0]:
+            S += Y.T @ Y
+    T = np.tril(S)
+    T[np.diag_indices(b)] *= 0.5
+    return T
+
+
+def f2b_update(n, b, b_sub, pr, rrow, rcol, A, Y):
+    """One level's trailing update of sym_full2band, in place on A.
+    A[r]: rank r's local array with its corner at this level's working corner (any lda; a numpy view), r = myrow + mycol*pr;
+    Y[r]: the aggregated panel the QR left on rank r (mb x b).  Follows full_to_band.cxx:90,103-239 step by step."""
+    lev = {(i, j): f2b_level(n, b, b_sub, pr, rrow, rcol, i, j) for i in range(pr) for j in range(pr)}
+    rk = lambda i, j: i + j * pr  # noqa: E731
+    rrow2 = (rrow + b // b_sub) % pr                                     # :90
+    invT = f2b_invT([Y[rk(i, rcol)][:lev[(i, rcol)][2]] for i in range(pr)], b)     # root column, then bcast (:103)
+    W = {}
+    for j in range(pr):                                                  # W = Y^T A reduced onto the diagonal (:121-131)
+        acc = None
+        for i in range(pr):
+            ro, co, mb, kb = lev[(i, j)]
+            Wi = Y[rk(i, j)][:mb].T @ A[rk(i, j)][ro:ro + mb, co:co + kb] if (mb and kb) else np.zeros((b, kb))
+            acc = Wi if acc is None else acc + Wi
+        W[j] = acc
+    Z = np.zeros((b, b))
+    for d in range(pr):                                                  # Z = Y^T W^T summed over the diagonal (:156-161)
+        lb = lev[(d, d)][2]
+        assert lb == lev[(d, d)][3]
+        if lb:
+            Z += Y[rk(d, d)][:lb].T @ W[d].T
+    U, V = {}, {}
+    for d in range(pr):
+        lb = lev[(d, d)][2]
+        Yd = Y[rk(d, d)][:lb]
+        if lb:
+            U[d] = np.linalg.solve(invT.T, Yd.T).T                       # U invT = Y (cdtrsm R,L,N,N, :172)
+            V[d] = W[d] - 0.5 * Z @ U[d].T                               # V' = W - .5 Z U' (:186)
+        else:
+            U[d], V[d] = Yd, W[d]
+    UVT = {}
+    for i in range(pr):
+        for j in range(pr):
+            ro, co, mb, kb = lev[(i, j)]
+            UVT[(i, j)] = U[i] @ V[j] if (mb and kb) else None           # U along rows, V' along columns (:205-215)
+    for i in range(pr):
+        for j in range(pr):
+            ro, co, mb, kb = lev[(i, j)]
+            if mb and kb:                                                # A -= UV' + (partner's UV')^T (:222-239)
+                A[rk(i, j)][ro:ro + mb, co:co + kb] -= UVT[(i, j)] + UVT[(j, i)].T
+    return rrow2, (rcol + b // b_sub) % pr, invT
+
+
+def f2b_sym_value(n, seed=23):
+    """The dump tool's symmetric test matrix: element (i, j) = off_value(seed, min + max*n)."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(os.path.dirname(_HERE), "tests"))
+    from off_script import off_value
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    lo, hi = np.minimum(i, j), np.maximum(i, j)
+    table = off_value(seed, n * n)
+    return table[lo + hi * n]

@@ -327,6 +327,92 @@ def case_dmat(world, gold, name):
     return ok
 
 
+def diag_comm(world, pr):
+    """test/SE/test_full2band.cxx:161-173: the diagonal ranks are colour 0 of a world split, ordered by grid row; everybody
+    else lands in a communicator nobody uses (the split is collective, so they still take part)."""
+    import ctypes
+    r = world.rank
+    if r % pr == r // pr:
+        return cb.setup_sub_comm(world, r % pr, 0, pr)
+    h = ctypes.c_void_p()
+    cb._lib.check(cb.lib().candmc_comm_split(world.cm, 1, r, ctypes.byref(h)))
+    return cb.CommData_t(cm=h.value, np=world.np - pr, rank=-1)
+
+
+def case_f2b(world, gold, name):
+    """the trailing update of every stored level of the reference's own sym_full2band run (panel QR outputs
+    as inputs), vs the reference's result and the numpy oracle.  rank = myrow + mycol*pr (test/SE/test_full2band.cxx:103)."""
+    from f2b_cases import level_state, stored_levels
+    P, n, b, bs, _ = [int(x) for x in gold[f"{name}.args"]]
+    pr = int(round(P ** 0.5))
+    nl, r = n // pr, world.rank
+    myrow, mycol = r % pr, r // pr
+    crow = cb.setup_sub_comm(world, r // pr, r % pr, pr)      # SETUP_SUB_COMM(cdt_glb, cdt_row, myRank/pr, myRank%pr, pc)
+    ccol = cb.setup_sub_comm(world, r % pr, r // pr, pr)
+    cdiag = diag_comm(world, pr)
+    ok = True
+    for L in stored_levels(gold, name):
+        nn, rrow, rcol, corner = level_state(n, b, bs, pr, L)
+        ro, co, mb, kb = orc.f2b_level(nn, b, bs, pr, rrow, rcol, myrow, mycol)
+        assert cb.sym_full2band_extents(nn, b, bs, pr, myrow, mycol, rrow, rcol) == (ro, co, mb, kb)
+        Ain = [gold[f"{name}.L{L}.r{q}.Ain"].reshape(nl, nl, order="F").copy() for q in range(P)]
+        Ys = []
+        for q in range(P):
+            mq = orc.f2b_level(nn, b, bs, pr, rrow, rcol, q % pr, q // pr)[2]
+            Ys.append(gold[f"{name}.L{L}.r{q}.Y"].reshape(mq, b, order="F"))
+        dA = dev(Ain[r])
+        ldy = mb + 2                                                 # Y out of a padded leading dimension
+        Yp = np.full((ldy, b), 55.0, order="F"); Yp[:mb] = Ys[r]
+        dY = dev(Yp)
+        cr, cc = corner[(myrow, mycol)]
+        pv = cb.pview(rrow, rcol, crow, ccol, world)
+        cb.sym_full2band_update(dA.data_ptr() + 8 * (cr + cc * nl), nl, nn, b, bs, pv, cdiag if myrow == mycol else None, dY, ldy)
+        torch.cuda.synchronize()
+        got = host(dA, nl, nl)
+        views = [Ain[q][corner[(q % pr, q // pr)][0]:, corner[(q % pr, q // pr)][1]:] for q in range(P)]
+        orc.f2b_update(nn, b, bs, pr, rrow, rcol, views, Ys)
+        ok &= record(f"{name}.L{L}:oracle", float(np.abs(got - Ain[r]).max()), 64 * b * EPS)
+        ok &= record(f"{name}.L{L}:golden", float(np.abs(got - gold[f"{name}.L{L}.r{r}.Aout"].reshape(nl, nl, order="F")).max()),
+                     64 * b * EPS)
+    crow.free(); ccol.free(); cdiag.free()
+    return ok
+
+
+def case_f2b_big(world, name, n, b, bs):
+    """the same update at a size where the DMMA GEMM takes its TMA path (even extents, b >= 64), first level only, synthetic
+    panel: numpy oracle, relative Frobenius <= 10*n*eps over the trailing block"""
+    P = world.np
+    pr = int(round(P ** 0.5))
+    nl, r = n // pr, world.rank
+    myrow, mycol = r % pr, r // pr
+    crow = cb.setup_sub_comm(world, mycol, myrow, pr)
+    ccol = cb.setup_sub_comm(world, myrow, mycol, pr)
+    cdiag = diag_comm(world, pr)
+    G = np.random.RandomState(n + b).rand(n, n) - 0.5
+    G = G + G.T
+    A, Ys = [], []
+    for q in range(P):
+        i, j = q % pr, q // pr
+        gr = ((np.arange(nl) // bs) * pr + i) * bs + np.arange(nl) % bs
+        gc = ((np.arange(nl) // bs) * pr + j) * bs + np.arange(nl) % bs
+        A.append(np.asfortranarray(G[np.ix_(gr, gc)]))
+        mq = orc.f2b_level(n, b, bs, pr, 0, 0, i, j)[2]
+        Ys.append(np.asfortranarray(np.random.RandomState(1000 + i).rand(mq, b) - 0.5))   # replicated along the grid row
+    ro, co, mb, kb = orc.f2b_level(n, b, bs, pr, 0, 0, myrow, mycol)
+    dA, dY = dev(A[r]), dev(Ys[r])
+    pv = cb.pview(0, 0, crow, ccol, world)
+    cb.sym_full2band_update(dA, nl, n, b, bs, pv, cdiag if myrow == mycol else None, dY, mb)
+    torch.cuda.synchronize()
+    got = host(dA, nl, nl)
+    before = A[r].copy()
+    orc.f2b_update(n, b, bs, pr, 0, 0, A, Ys)
+    ok = record(f"{name}:oracle", rel_frob(got[ro:ro + mb, co:co + kb], A[r][ro:ro + mb, co:co + kb]), 10 * n * EPS)
+    mask = np.ones((nl, nl), bool); mask[ro:ro + mb, co:co + kb] = False
+    ok &= record(f"{name}:outside_untouched", 0.0 if np.array_equal(got[mask], before[mask]) else 1.0, 0.5)
+    crow.free(); ccol.free(); cdiag.free()
+    return ok
+
+
 def pending_cases(world, golden):
     """Paths that have not run on a B200 yet (tests/test_zz_redist_gpu.py runs these apart from the validated suite)."""
     P = world.np
@@ -342,6 +428,13 @@ def pending_cases(world, golden):
     for name in case_names(dgold):
         if int(dgold[f"{name}.args"][0]) == P:
             case_dmat(world, dgold, name)
+    import f2b_cases
+    fgold = f2b_cases.load_golden()
+    for name in f2b_cases.case_names(fgold):
+        if int(fgold[f"{name}.args"][0]) == P:
+            case_f2b(world, fgold, name)
+    if P in (1, 4):
+        case_f2b_big(world, f"f2b_big_p{P}", 1024 * int(round(P ** 0.5)), 128, 32)
     shapes = {1: [(1,)], 2: [(2,), (1,)], 4: [(2,), (4,), (1,)], 8: [(2,), (4,)]}.get(P, [])
     for (nprow,) in shapes:
         npcol = P // nprow

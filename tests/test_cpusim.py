@@ -46,7 +46,7 @@ def _torchrun(nproc, port, script, *args):
 
 
 DIST_MAIN = [1, 2, 4, 8] if FULL else [4, 8]
-DIST_PENDING = [1, 2, 4, 6, 8, 9] if FULL else [1, 4, 6]
+DIST_PENDING = [1, 2, 4, 6, 8, 9, 16] if FULL else [1, 4, 9]
 GOLD = np.load(os.path.join(HERE, "golden", "lu_offload_ref_outputs.npz"))
 SCRIPTS = sorted(k[: -len("__script")] for k in GOLD.files if k.endswith("__script"))
 REDIST = [(24, 36, 2, 2, 3, 0, 0), (36, 24, 3, 3, 2, 1, 1), (30, 30, 5, 3, 3, 0, 2), (16, 16, 4, 1, 4, 0, 3), (512, 256, 32, 2, 2, 1, 0)]

@@ -138,6 +138,28 @@ def pending(world, rank, ws, timed, report, ccol, Y, Am, mb, kb, k):
                           "GBps_per_gpu_algorithmic": 16.0 * 8192 * 8192 / (ms * 1e-3) / 1e9}), flush=True)
     crow.free(); ccol2.free()
     del src, dst
+    # ---- N4: sym_full2band trailing update, first level of n = 16384 * q with band 512 (2 GEMMs: 2 * 2 * mb * kb * b flop) ----
+    pr = {1: 1, 4: 2}.get(ws)
+    if pr:
+        n4, b4, bs4 = 16384 * pr, 512, 128
+        myrow, mycol = rank % pr, rank // pr
+        crow = cb.setup_sub_comm(world, mycol, myrow, pr); ccol3 = cb.setup_sub_comm(world, myrow, mycol, pr)
+        import ctypes
+        if myrow == mycol:
+            cdiag = cb.setup_sub_comm(world, myrow, 0, pr)
+        else:
+            h = ctypes.c_void_p(); cb._lib.check(cb.lib().candmc_comm_split(world.cm, 1, rank, ctypes.byref(h)))
+            cdiag = cb.CommData_t(cm=h.value, np=ws - pr, rank=-1)
+        ro, co, mb4, kb4 = cb.sym_full2band_extents(n4, b4, bs4, pr, myrow, mycol, 0, 0)
+        A4 = torch.rand((n4 // pr) ** 2, dtype=torch.float64, device="cuda")
+        Y4 = torch.rand(mb4 * b4, dtype=torch.float64, device="cuda") - 0.5
+        pv4 = cb.pview(0, 0, crow, ccol3, world)
+        ms = timed(lambda: cb.sym_full2band_update(A4, n4 // pr, n4, b4, bs4, pv4, cdiag if myrow == mycol else None, Y4, mb4))
+        report(f"N4: sym_full2band_update n={n4} b={b4} on {pr}x{pr}", ws * 2 * 2.0 * mb4 * kb4 * b4, ms,
+               {"note": "flops = W = Y^T A and U V'; invT, Z, the triangular solve, three broadcasts, the partner exchange and the "
+                        "HBM-bound rank-2b update (32 B per trailing element) are inside the time"})
+        crow.free(); ccol3.free(); cdiag.free()
+        del A4, Y4
     # ---- N2: LU seam, one trailing-update step on a 16384^2 local matrix, panel width 512 ----
     from candmc_b200 import lu_offload as lo
     nloc, kp = 16384, 512

@@ -167,8 +167,9 @@ def main():
     ap.add_argument("--bg-ctas", type=int, default=None, help="CTA cap of the overlapped-traffic communicators")
     ap.add_argument("--fused-reduce", type=int, default=None, choices=[0, 1, 2],
                     help="depth sum: 0 NCCL, 1 fused on 1x1xc (default), 2 fused on q x q x c too (experimental)")
-    ap.add_argument("--skip-unused-uploads", action="store_true",
-                    help="e2e leg: do not upload blocks a layer never multiplies (experimental)")
+    ap.add_argument("--skip-unused-uploads", action="store_true", help="(default behaviour now; accepted for old scripts)")
+    ap.add_argument("--upload-all-blocks", action="store_true",
+                    help="e2e leg: upload both host blocks on every rank even when a layer's panels never use them")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -193,8 +194,8 @@ def main():
         cb.lib().candmc_set_background_ctas(args.bg_ctas)
     if args.fused_reduce is not None:
         cb.lib().candmc_set_fused_reduce(args.fused_reduce)
-    if args.skip_unused_uploads:
-        cb.lib().candmc_set_skip_unused_uploads(1)
+    if args.upload_all_blocks:
+        cb.lib().candmc_set_skip_unused_uploads(0)
     world = cb.init_world(rank, world_size, local)
     g = cb.d25_grid(world)
     n, q, c = args.n, g["q"], g["c"]
@@ -301,7 +302,13 @@ def main():
         del chk
         # bytes this rank's call really moves: a 1x1xc grid uploads only its k-slice of A and B, a q x q x c grid both of
         # its blocks; every rank downloads its C block
-        my_h2d = 2 * b * (b // c) * 8 if ksplit else 2 * b * b * 8
+        if ksplit:
+            my_h2d = 2 * b * (b // c) * 8
+        elif args.upload_all_blocks:
+            my_h2d = 2 * b * b * 8
+        else:   # a layer multiplies panels [layer*q/c, (layer+1)*q/c): my A block travels only if my column is one of them, B: my row
+            lo, hi = g["layer"] * (q // c), (g["layer"] + 1) * (q // c)
+            my_h2d = (int(lo <= g["col"] < hi) + int(lo <= g["row"] < hi)) * b * b * 8
         tot = torch.tensor([float(my_h2d), float(b * b * 8)], dtype=torch.float64, device="cuda")
         if world_size > 1:
             dist.all_reduce(tot)
@@ -340,7 +347,7 @@ def main():
                          "flops_per_launch": tfl.value / nl.value if nl.value else None, "traffic": None},
         }
         knobs = {k: v for k, v in (("bg_ctas", args.bg_ctas), ("fused_reduce", args.fused_reduce),
-                                   ("skip_unused_uploads", args.skip_unused_uploads or None)) if v is not None}
+                                   ("upload_all_blocks", args.upload_all_blocks or None)) if v is not None}
         if knobs:
             line["config"]["knobs"] = knobs  # non-default tuning switches used for this run
         if world_size == 1 and not args.no_cpu_baseline:

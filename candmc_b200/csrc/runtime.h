@@ -24,7 +24,7 @@ struct Runtime {
   int* tile_counters = nullptr;         // ring of device counters for the GEMM's dynamic tile scheduler
   unsigned tile_counter_seq = 0;
   bool fused_reduce_grids = false;      // ... also on q x q x c grids (validated so far on 1 x 1 x c only)
-  bool skip_unused_uploads = false;     // host operands: skip the upload of blocks a layer never uses (not yet validated on 8 GPUs)
+  bool skip_unused_uploads = true;      // host operands: a layer's rank uploads only the blocks its panels use (candmc_set_skip_unused_uploads)
   bool fused_reduce = true;             // depth all-reduce fused into the last GEMM's epilogue over peer memory
   bool splitk = true;                   // cut small-tile-count GEMMs along k too
   double* splitk_part = nullptr;        // split-K partial tiles (grow-only) and per-tile arrival counters

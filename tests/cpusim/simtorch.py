@@ -93,6 +93,72 @@ def install():
     torch.cuda.device_count = lambda: 1
     torch.cuda.current_stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=0)
 
+    import time as _time
+
+    class SimEvent:
+        """torch.cuda.Event on the simulator: host wall clock at record() (the simulator has no device timeline)."""
+        def __init__(self, enable_timing=False, **_):
+            self.t = None
+
+        def record(self, stream=None):
+            sim().cpusim_check()
+            self.t = _time.perf_counter()
+
+        def synchronize(self):
+            pass
+
+        def query(self):
+            return True
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+
+    torch.cuda.Event = SimEvent
+    torch.Tensor.pin_memory = lambda self, *a, **k: self
+
+    def pinned(fn):
+        def wrapped(*a, **k):
+            k.pop("pin_memory", None)
+            return fn(*a, **k)
+        return wrapped
+
+    for name in ("full", "zeros", "empty", "ones"):
+        setattr(torch, name, pinned(getattr(torch, name)))
+
+    # results of torch operations on simulated-device tensors live on the simulated device too (bench.py's cuBLAS cross-check
+    # `fb.view(..) @ fa.view(..)`, reductions, clones): a function mode moves fresh outputs over
+    from torch.overrides import TorchFunctionMode
+
+    def _flat(xs):
+        for x in xs:
+            if isinstance(x, torch.Tensor):
+                yield x
+            elif isinstance(x, (list, tuple)):
+                yield from _flat(x)
+
+    class SimDeviceMode(TorchFunctionMode):
+        busy = False
+
+        def __torch_function__(self, func, types, args=(), kwargs=None):
+            out = func(*args, **(kwargs or {}))
+            if SimDeviceMode.busy or not isinstance(out, torch.Tensor) or out.numel() == 0:
+                return out
+            name = getattr(func, "__name__", "")
+            if name in ("cpu", "numpy", "item", "tolist", "__get__", "data_ptr"):
+                return out
+            if sim().cpusim_is_device(out.data_ptr()):
+                return out
+            if any(t.numel() and sim().cpusim_is_device(t.data_ptr()) for t in _flat(list(args) + list((kwargs or {}).values()))):
+                SimDeviceMode.busy = True
+                try:
+                    return _to_sim(out)
+                finally:
+                    SimDeviceMode.busy = False
+            return out
+
+    torch._cpusim_mode = SimDeviceMode()
+    torch._cpusim_mode.__enter__()
+
     real_init = dist.init_process_group
 
     def init_pg(backend=None, *a, **k):

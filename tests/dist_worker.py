@@ -433,6 +433,15 @@ def pending_cases(world, golden):
     for name in f2b_cases.case_names(fgold):
         if int(fgold[f"{name}.args"][0]) == P:
             case_f2b(world, fgold, name)
+    if P == 8:   # host operands on 2x2x2 with the uploads of blocks a layer never multiplies skipped (bench.py --skip-unused-uploads)
+        cb.lib().candmc_set_skip_unused_uploads(1)
+        for min_kc in (1024, 8):
+            cb.set_min_kchunk(min_kc)
+            case_d25(world, golden, f"d25_n1024_c2_host_skip_kc{min_kc}", 1024, 2, 0, use_host=True, check_golden=False)
+            case_d25(world, golden, f"d25_n512_c2_host_skip_pad_ovp_kc{min_kc}", 512, 2, 1, use_host=True, lda_pad=3, check_golden=False)
+            case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0, use_host=True)
+        cb.set_min_kchunk(1024)
+        cb.lib().candmc_set_skip_unused_uploads(0)
     if P in (1, 4):
         case_f2b_big(world, f"f2b_big_p{P}", 1024 * int(round(P ** 0.5)), 128, 32)
     shapes = {1: [(1,)], 2: [(2,), (1,)], 4: [(2,), (4,), (1,)], 8: [(2,), (4,)]}.get(P, [])

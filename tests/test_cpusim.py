@@ -67,6 +67,12 @@ for _m in ("oob", "uninit", "gemm_range"):
     _job(f"probe_{_m}", [sys.executable, os.path.join(SIM, "probe_local.py"), _m])
 for _m, _sched in (("race", "sync"), ("race", "lifo"), ("ordered", "lifo"), ("ordered", "random:5")):
     _job(f"probe_{_m}_{_sched}", [sys.executable, os.path.join(SIM, "probe_local.py"), _m], CPUSIM_SCHED=_sched)
+# bench.py itself (argument handling, byte accounting of the end-to-end leg, JSON contract) on 1 and 8 simulated ranks; the
+# numbers are not measurements.  `--n` travels in CPUSIM_ARGS because torchrun's parser trips over it after the script name.
+for _n in (1, 8):
+    _job(f"bench{_n}", _torchrun(_n, 29790 + _n, os.path.join(SIM, "run_sim.py"), "bench.py", "--gpus", str(_n), "--steps", "1",
+                                 "--warmup", "1", "--no-cpu-baseline"), CPUSIM_ARGS="--n 512")
+
 # the reference's OWN test mains (compiled unmodified against include/, oracle/_ref/dropin — present where /root/reference
 # was available at build time): the simulator build is preloaded in front of libcandmc_b200.so, which exports the same ABI
 DROPIN = os.path.join(ROOT, "oracle", "_ref", "dropin")
@@ -198,6 +204,27 @@ def test_reference_test_mains_pass_on_the_simulator(case):
     rc, so, se = RESULTS[f"dropin_{case}"]
     assert rc == 0, so[-2000:] + se[-2000:]
     assert DROPIN_CASES[case][4] in so and "FAILED" not in so and "test failed" not in so.lower()
+
+
+@pytest.mark.parametrize("nproc", [1, 8])
+def test_bench_script_logic_on_the_simulator(nproc):
+    """bench.py end to end on the simulator: one JSON line with the contract's keys, both legs agree with the cross-check,
+    and the end-to-end byte accounting matches what the ranks really upload (2x2x2: a layer's rank uploads only the blocks
+    its panels use — one block per rank on average instead of two)"""
+    rc, so, se = RESULTS[f"bench{nproc}"]
+    assert rc == 0, so[-2000:] + se[-3000:]
+    lines = [line for line in so.splitlines() if line.startswith('{"metric"')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+        assert key in d, key
+    assert d["n_gpus"] == nproc and d["warmup"] >= 3 and d["dtype"] == "f64" and d["gpu_launches"] > 0
+    assert d["rel_frobenius_vs_cublas_crosscheck"] <= d["tolerance_10_n_eps"]
+    assert d["e2e"]["valid"] and d["e2e"]["rel_frobenius_vs_device_path"] <= d["tolerance_10_n_eps"]
+    b = d["config"]["block"]
+    assert d["e2e"]["d2h_bytes_per_step"] == nproc * b * b * 8
+    assert d["e2e"]["h2d_bytes_per_step"] == (2 if nproc == 1 else 8) * b * b * 8
 
 
 def test_adversarial_scheduler_exposes_a_missing_event():

@@ -140,7 +140,20 @@ def install():
         busy = False
 
         def __torch_function__(self, func, types, args=(), kwargs=None):
-            out = func(*args, **(kwargs or {}))
+            kwargs = dict(kwargs or {})
+            if _is_cuda_device(kwargs.get("device")):        # any factory: torch.eye(..., device="cuda"), x.to(device="cuda")
+                kwargs.pop("device")
+                kwargs.pop("pin_memory", None)
+                out = func(*args, **kwargs)
+                if isinstance(out, torch.Tensor) and not SimDeviceMode.busy:
+                    SimDeviceMode.busy = True
+                    try:
+                        return _to_sim(out)
+                    finally:
+                        SimDeviceMode.busy = False
+                return out
+            kwargs.pop("pin_memory", None)
+            out = func(*args, **kwargs)
             if SimDeviceMode.busy or not isinstance(out, torch.Tensor) or out.numel() == 0:
                 return out
             name = getattr(func, "__name__", "")

@@ -21,6 +21,13 @@ sys.path.insert(0, ROOT)
 import candmc_b200 as cb  # noqa: E402
 
 PEAK = 148 * 4 * 16 * 2 * 1.965e9 / 1e12
+# `--shrink S` divides every extent by S: a dry run of this script's own logic on the CPU simulator
+# (python tests/cpusim/run_sim.py tools/bench_configs.py --pending --shrink 32); numbers of such a run mean nothing
+SHRINK = int(sys.argv[sys.argv.index("--shrink") + 1]) if "--shrink" in sys.argv else 1
+
+
+def sz(x):
+    return max(x // SHRINK, 2)
 
 
 def main():
@@ -61,14 +68,14 @@ def main():
 
     if ws == 4:
         # ---- config 2: SUMMA n = 16384, 2x2 ----
-        n = 16384; g = cb.d25_grid(world, 1); b = n // 2
+        n = sz(16384); g = cb.d25_grid(world, 1); b = n // 2
         A, B, Cm = blocks(b, g["row"] * b, g["col"] * b, n)
         args = cb.ctb_args_t(n=n, lda_A=b, lda_B=b, lda_C=b, buffer_size=4 * b * b * 8)
         ms = timed(lambda: cb.summa(args, A, B, Cm, None, g["cdt_row"], g["cdt_col"]))
         report("config2: summa n=16384 2x2", 2.0 * n ** 3, ms)
         del A, B, Cm
         # ---- config 4a: bcast_cannon_4d as pure Cannon, n = 24576 ----
-        n = 24576; d = cb.dcn_grid(world, 2); b = n // 2
+        n = sz(24576); d = cb.dcn_grid(world, 2); b = n // 2
         A, B, Cm = blocks(b, (d["y1"] * 2 + d["y2"]) * b, (d["x1"] * 2 + d["x2"]) * b, n)
         args = cb.ctb_args_t(n=n, lda_A=b, lda_B=b, lda_C=b, buffer_size=5 * b * b * 8, ovp=1)
         ms = timed(lambda: cb.bcast_cannon_4d(args, A, B, Cm, None, d["cdt_x1"], d["cdt_y1"], d["cdt_x2"], d["cdt_y2"]))
@@ -78,7 +85,7 @@ def main():
         report("config4: kput_cannon 2-ary 2-cube, 12288^3 blocks", 2.0 * n ** 3, ms)
         del A, B, Cm
     # ---- config 5: CAQR trailing update ----
-    m, ncol, k = 65536, 8192, 512
+    m, ncol, k = sz(65536), sz(8192), sz(512)
     nprow, npcol = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[ws]
     prow, pcol = rank % nprow, rank // nprow
     ccol = cb.setup_sub_comm(world, prow, pcol, nprow) if ws > 1 else None   # ranks sharing my grid column
@@ -92,7 +99,7 @@ def main():
            {"note": "flops = the two GEMMs (SURVEY §8d); all-reduce of W and the triangular solve are inside the time"})
     # 1-GPU local GEMM roofline at the Cannon block size (config 4, second half)
     if ws == 1:
-        for n in (12288, 16384):
+        for n in (sz(12288), sz(16384)):
             A, B, Cm = blocks(n, 0, 0, n)
             ms = timed(lambda: cb.cdgemm("N", "N", n, n, n, 1.0, A, n, B, n, 0.0, Cm, n))
             report(f"config4: 1-GPU local GEMM n={n}", 2.0 * n ** 3, ms)
@@ -112,7 +119,7 @@ def pending(world, rank, ws, timed, report, ccol, Y, Am, mb, kb, k):
     ms = timed(lambda: cb.upd_Yamamoto_A(Y, mb, Am, mb, mb, kb, k, T, ccol))
     report("N1: upd_Yamamoto_A m=65536 n=8192 k=512", ws * (2 * 2.0 * mb * kb * k + 2.0 * k * k * kb), ms)
     # ---- N3: permute kernels alone (one GPU plays rank 1 of a 4-rank axis), 8192 x 8192 local piece, nb = 64 ----
-    rows = cols = 8192; nb = 64
+    rows = cols = sz(8192); nb = sz(64)
     X = torch.rand(rows * cols, dtype=torch.float64, device="cuda"); S = torch.empty_like(X)
     st = torch.cuda.current_stream().cuda_stream
     for rows_axis in (1, 0):
@@ -130,18 +137,18 @@ def pending(world, rank, ws, timed, report, ccol, Y, Am, mb, kb, k):
     myrow, mycol = rank % nprow, rank // nprow
     crow = cb.setup_sub_comm(world, mycol, myrow, npcol); ccol2 = cb.setup_sub_comm(world, myrow, mycol, nprow)
     pv = cb.pview(0, 0, crow, ccol2, world)
-    m = 8192 * nprow; n = 8192 * npcol
-    src = torch.rand(8192 * 8192, dtype=torch.float64, device="cuda"); dst = torch.empty_like(src)
-    ms = timed(lambda: cb.cyclic_to_blocked(m, n, 64, src, 8192, dst, 8192, pv))
+    m = rows * nprow; n = cols * npcol
+    src = torch.rand(rows * cols, dtype=torch.float64, device="cuda"); dst = torch.empty_like(src)
+    ms = timed(lambda: cb.cyclic_to_blocked(m, n, nb, src, rows, dst, rows, pv))
     if rank == 0:
         print(json.dumps({"config": f"N3: cyclic_to_blocked {m}x{n} nb=64 on {nprow}x{npcol}", "ms": ms,
-                          "GBps_per_gpu_algorithmic": 16.0 * 8192 * 8192 / (ms * 1e-3) / 1e9}), flush=True)
+                          "GBps_per_gpu_algorithmic": 16.0 * rows * cols / (ms * 1e-3) / 1e9}), flush=True)
     crow.free(); ccol2.free()
     del src, dst
     # ---- N4: sym_full2band trailing update, first level of n = 16384 * q with band 512 (2 GEMMs: 2 * 2 * mb * kb * b flop) ----
     pr = {1: 1, 4: 2}.get(ws)
     if pr:
-        n4, b4, bs4 = 16384 * pr, 512, 128
+        n4, b4, bs4 = sz(16384) * pr, sz(512), sz(128)
         myrow, mycol = rank % pr, rank // pr
         crow = cb.setup_sub_comm(world, mycol, myrow, pr); ccol3 = cb.setup_sub_comm(world, myrow, mycol, pr)
         import ctypes
@@ -162,7 +169,7 @@ def pending(world, rank, ws, timed, report, ccol, Y, Am, mb, kb, k):
         del A4, Y4
     # ---- N2: LU seam, one trailing-update step on a 16384^2 local matrix, panel width 512 ----
     from candmc_b200 import lu_offload as lo
-    nloc, kp = 16384, 512
+    nloc, kp = sz(16384), sz(512)
     lo.alloc_A(nloc * nloc, None); lo.alloc_L(nloc * kp); lo.alloc_U(kp * nloc); lo.alloc_transfer(kp * nloc)
     hA = np.random.rand(nloc * kp) - 0.5
     lo.upload_lda_cpy(nloc, kp, nloc, nloc, hA, 0, lo.OFF_L); lo.upload_lda_cpy(kp, nloc, kp, kp, hA, 0, lo.OFF_U)

@@ -39,6 +39,11 @@ int candmc_set_fused_reduce(int on) {
   return OK;
 }
 
+int candmc_set_early_c_download(int on) {
+  runtime().early_c_download = (on != 0);
+  return OK;
+}
+
 int candmc_set_skip_unused_uploads(int on) {
   runtime().skip_unused_uploads = (on != 0);
   return OK;

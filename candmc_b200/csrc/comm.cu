@@ -49,7 +49,7 @@ int comm_bcast(candmc_comm* c, const double* send, double* recv, int64_t count, 
   return OK;
 }
 
-int comm_allreduce(candmc_comm* c, const double* send, double* recv, int64_t count, cudaStream_t st) {
+int comm_allreduce(candmc_comm* c, const double* send, double* recv, int64_t count, cudaStream_t st, bool background) {
   CANDMC_CHECK(c != nullptr, "allreduce: null communicator");
   if (count <= 0) return OK;
   if (c->size == 1) {
@@ -57,7 +57,9 @@ int comm_allreduce(candmc_comm* c, const double* send, double* recv, int64_t cou
       CANDMC_CUDA(cudaMemcpyAsync(recv, send, sizeof(double) * count, cudaMemcpyDeviceToDevice, st));
     return OK;
   }
-  CANDMC_NCCL(ncclAllReduce(send, recv, (size_t)count, ncclDouble, ncclSum, c->nccl, st));
+  ncclComm_t comm = c->nccl;
+  if (background) CANDMC_TRY(comm_background(c, &comm));
+  CANDMC_NCCL(ncclAllReduce(send, recv, (size_t)count, ncclDouble, ncclSum, comm, st));
   return OK;
 }
 

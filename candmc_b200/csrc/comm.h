@@ -37,7 +37,8 @@ int comm_background(candmc_comm* c, ncclComm_t* out);
 // thin wrappers, device pointers only, size-1 communicators short-circuit (no NCCL call)
 int comm_bcast(candmc_comm* c, const double* send, double* recv, int64_t count, int root, cudaStream_t st,
                bool background = false);
-int comm_allreduce(candmc_comm* c, const double* send, double* recv, int64_t count, cudaStream_t st);
+int comm_allreduce(candmc_comm* c, const double* send, double* recv, int64_t count, cudaStream_t st,
+                   bool background = false);
 // grouped point-to-point exchange: send `scount` doubles to `dst`, receive `rcount` from `src` (either may be
 // skipped with a negative peer); self-exchange degenerates to a device copy.
 int comm_sendrecv(candmc_comm* c, const double* send, int64_t scount, int dst, double* recv, int64_t rcount, int src,

@@ -14,6 +14,7 @@
 // land in the alternate buffer while the current step multiplies (pointer swap instead of the reference's memcpy
 // back, spcannon.cxx:76-77); the transposes of split-dim Cannon are folded into the NT GEMM where possible.
 #include <algorithm>
+#include <functional>
 #include <vector>
 
 #include "../../include/candmc_b200.h"
@@ -100,7 +101,19 @@ struct SummaArgs {
   FusedParams* fused = nullptr;
   double* fused_out = nullptr;
   int64_t fused_ldout = 0;
+  // Early finalisation of C for callers that still have to ship it somewhere slow (host memory): the second half of the
+  // LAST panel's k-chunks is multiplied column slab by column slab (fin_slabs slabs), and slab_done(c0, w) is called once
+  // columns [c0, c0 + w) of C hold their final value of this sweep, while the remaining slabs are still being multiplied.
+  int fin_slabs = 0;
+  std::function<int(int64_t, int64_t)> slab_done;
 };
+
+// number of column slabs a b-wide C block is finalised in (0: not worth it)
+int pick_fin_slabs(int64_t b) {
+  for (int s = 8; s > 1; s >>= 1)
+    if (b % (s * 128) == 0) return s;
+  return 0;
+}
 
 // The fused epilogue only exists in the TMA kernel: give it 16-byte aligned operands with even leading dimensions.
 int tma_ready_operand(const double** p, int64_t* ld, int64_t rows, int64_t cols, double* scratch, cudaStream_t st) {
@@ -214,27 +227,35 @@ int summa_sweep(SummaArgs& a) {
       }
     }
     // ---- multiplies for panel i on the compute stream ----
-    for (int t = 0; t < nchunks; ++t) {
+    auto operands = [&](int t, const double** pa, int64_t* lda, const double** pb, int64_t* ldb) -> int {
       if (ready[t]) CANDMC_CUDA(cudaStreamWaitEvent(a.compute, ready[t], 0));
-      const double* pa;
-      const double* pb;
-      int64_t lda, ldb;
       if (rootA || a.row->size == 1) {
         CANDMC_TRY(wait_ready(a.compute, a.a_ready, t));
-        pa = a.myA + t * kc * a.ldA;
-        lda = a.ldA;
+        *pa = a.myA + t * kc * a.ldA;
+        *lda = a.ldA;
       } else {
-        pa = bufA + t * kc * b;
-        lda = b;
+        *pa = bufA + t * kc * b;
+        *lda = b;
       }
       if (rootB || a.col->size == 1) {
         CANDMC_TRY(wait_ready(a.compute, a.b_ready, t));
-        pb = a.b_chunk_major ? a.myB + t * kc * b : a.myB + t * kc;
-        ldb = a.b_chunk_major ? kc : a.ldB;
+        *pb = a.b_chunk_major ? a.myB + t * kc * b : a.myB + t * kc;
+        *ldb = a.b_chunk_major ? kc : a.ldB;
       } else {
-        pb = bufB + t * kc * b;
-        ldb = kc;  // chunk-major
+        *pb = bufB + t * kc * b;
+        *ldb = kc;  // chunk-major
       }
+      return OK;
+    };
+    // chunks [0, h) are multiplied over the full width; with early finalisation the rest of the last panel goes slab-wise
+    const bool slabs = (i + 1 == a.i1 && a.fin_slabs > 1 && a.slab_done && nchunks >= 2 && a.fused == nullptr &&
+                        is_n(a.tA) && is_n(a.tB) && b % a.fin_slabs == 0);
+    const int h = slabs ? nchunks / 2 : nchunks;
+    for (int t = 0; t < h; ++t) {
+      const double* pa;
+      const double* pb;
+      int64_t lda, ldb;
+      CANDMC_TRY(operands(t, &pa, &lda, &pb, &ldb));
       const bool last = (i + 1 == a.i1 && t + 1 == nchunks);
       if (last && a.fused != nullptr) {
         // operands of this last chunk must be TMA-able; packA / locB chunk slots of this rank are free to use as scratch
@@ -254,6 +275,19 @@ int summa_sweep(SummaArgs& a) {
         done_prev[t] = g_events.get();
         CANDMC_CHECK(done_prev[t] != nullptr, "event pool exhausted");
         CANDMC_CUDA(cudaEventRecord(done_prev[t], a.compute));
+      }
+    }
+    if (slabs) {
+      const int64_t w = b / a.fin_slabs;
+      std::vector<const double*> pa(nchunks), pb(nchunks);
+      std::vector<int64_t> lda(nchunks), ldb(nchunks);
+      for (int t = h; t < nchunks; ++t) CANDMC_TRY(operands(t, &pa[t], &lda[t], &pb[t], &ldb[t]));
+      for (int j = 0; j < a.fin_slabs; ++j) {
+        const int64_t c0 = j * w;
+        for (int t = h; t < nchunks; ++t)   // h >= 1, so these always accumulate onto the first half
+          CANDMC_TRY(gemm_f64('N', 'N', b, w, kc, 1.0, pa[t], lda[t], pb[t] + c0 * ldb[t], ldb[t], 1.0, a.C + c0 * a.ldC,
+                              a.ldC, a.compute));
+        CANDMC_TRY(a.slab_done(c0, w));
       }
     }
   }
@@ -515,22 +549,61 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
 
   // depth all-reduce: fused into the epilogue of the last GEMM over peer memory when the block shape allows it
   // (whole 128-wide tile columns per depth rank, CUDA IPC available), otherwise ncclAllReduce
+  // A HOST C block is the slowest thing this call moves (PCIe, after the last multiply): when the multiply is pipelined in
+  // k-chunks anyway, the second half of the last panel's chunks is multiplied column slab by column slab, and every slab is
+  // summed over the depth (background communicator) and downloaded while the next slabs still multiply — only the last
+  // slab's transfer stays exposed.  The fused depth sum works on whole square blocks, so it stays off on this path.
+  const int fin_slabs = (sC.staged() && nn && runtime().early_c_download) ? pick_fin_slabs(b) : 0;
+  const int nch_consumer = ksplit ? (chunked ? up_chunks : 1) : sweep_chunks(b, args->trans_A, args->trans_B, cdt_row, cdt_col);
+  const bool slab_mode = fin_slabs > 1 && nch_consumer >= 2 && !(c > 1 && !ksplit && runtime().fused_reduce_grids);
+  int slabs_out = 0;
+  cudaStream_t d2h = runtime().aux_stream;
+  auto slab_done = [&](int64_t c0, int64_t w) -> int {
+    cudaEvent_t e = g_events.get();
+    CANDMC_CHECK(e != nullptr, "event pool exhausted");
+    CANDMC_CUDA(cudaEventRecord(e, st));
+    if (c > 1) {   // depth sum of the slab in place in bufC (ld = b: the slab is contiguous), then straight to the host
+      cudaStream_t cs = runtime().comm_stream;
+      CANDMC_CUDA(cudaStreamWaitEvent(cs, e, 0));
+      CANDMC_TRY(comm_allreduce(cdt_kdir, bufC + c0 * b, bufC + c0 * b, b * w, cs, true));
+      cudaEvent_t r = g_events.get();
+      CANDMC_CHECK(r != nullptr, "event pool exhausted");
+      CANDMC_CUDA(cudaEventRecord(r, cs));
+      CANDMC_CUDA(cudaStreamWaitEvent(d2h, r, 0));
+      CANDMC_TRY(sC.close_out_cols(bufC + c0 * b, b, c0, w, d2h));
+    } else {
+      CANDMC_CUDA(cudaStreamWaitEvent(d2h, e, 0));
+      CANDMC_TRY(sC.close_out_cols(sC.ptr() + c0 * sC.ld(), sC.ld(), c0, w, d2h));
+    }
+    ++slabs_out;
+    return OK;
+  };
+
   FusedCtx* fctx = nullptr;
   FusedParams fparams;
   // (on q > 1 grids the fused path is opt-in until it has been validated on 8 GPUs: candmc_set_fused_reduce(2))
-  if (c > 1 && (ksplit || runtime().fused_reduce_grids)) CANDMC_TRY(fused_ctx_get(cdt_kdir, b, &fctx));
+  if (c > 1 && !slab_mode && (ksplit || runtime().fused_reduce_grids)) CANDMC_TRY(fused_ctx_get(cdt_kdir, b, &fctx));
   if (fctx) fused_params_next(fctx, layer, &fparams);
 
   if (ksplit) {
     // my k-slice, multiplied chunk by chunk as the chunks land (one chunk when the operands are already on the device)
     const int nch = chunked ? up_chunks : 1;
     const int64_t kc = kloc / nch;
-    for (int t = 0; t < nch; ++t) {
+    const int h = slab_mode ? nch / 2 : nch;   // chunks [0, h) over the full width, the rest slab-wise (see slab_done)
+    auto operands = [&](int t, const double** pa, int64_t* lda, const double** pb, int64_t* ldb) -> int {
       if (t < (int)a_ready.size() && a_ready[t]) CANDMC_CUDA(cudaStreamWaitEvent(st, a_ready[t], 0));
       if (t < (int)b_ready.size() && b_ready[t]) CANDMC_CUDA(cudaStreamWaitEvent(st, b_ready[t], 0));
-      const double* pa = dA_ptr + t * kc * dA_ld;
-      const double* pb = b_chunk_major ? dB_ptr + t * kc * b : dB_ptr + t * kc;
-      int64_t lda = dA_ld, ldb = b_chunk_major ? kc : dB_ld;
+      *pa = dA_ptr + t * kc * dA_ld;
+      *pb = b_chunk_major ? dB_ptr + t * kc * b : dB_ptr + t * kc;
+      *lda = dA_ld;
+      *ldb = b_chunk_major ? kc : dB_ld;
+      return OK;
+    };
+    for (int t = 0; t < h; ++t) {
+      const double* pa;
+      const double* pb;
+      int64_t lda, ldb;
+      CANDMC_TRY(operands(t, &pa, &lda, &pb, &ldb));
       const bool last = (t + 1 == nch);
       if (last && fctx) {
         const bool need_scratch = reinterpret_cast<uintptr_t>(pa) % 16 || lda % 2 || reinterpret_cast<uintptr_t>(pb) % 16 || ldb % 2;
@@ -544,6 +617,19 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
         CANDMC_TRY(gemm_f64_fused('N', 'N', b, b, kc, 1.0, pa, lda, pb, ldb, t ? 1.0 : 0.0, sC.ptr(), sC.ld(), st, &fparams));
       } else {
         CANDMC_TRY(gemm_f64('N', 'N', b, b, kc, 1.0, pa, lda, pb, ldb, t ? 1.0 : 0.0, Cpart, ldCpart, st));
+      }
+    }
+    if (h < nch) {
+      const int64_t w = b / fin_slabs;
+      std::vector<const double*> pa(nch), pb(nch);
+      std::vector<int64_t> lda(nch), ldb(nch);
+      for (int t = h; t < nch; ++t) CANDMC_TRY(operands(t, &pa[t], &lda[t], &pb[t], &ldb[t]));
+      for (int j = 0; j < fin_slabs; ++j) {
+        const int64_t c0 = j * w;
+        for (int t = h; t < nch; ++t)
+          CANDMC_TRY(gemm_f64('N', 'N', b, w, kc, 1.0, pa[t], lda[t], pb[t] + c0 * ldb[t], ldb[t], 1.0, Cpart + c0 * ldCpart,
+                              ldCpart, st));
+        CANDMC_TRY(slab_done(c0, w));
       }
     }
   } else {
@@ -563,7 +649,19 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
       a.fused_out = sC.ptr();
       a.fused_ldout = sC.ld();
     }
+    if (slab_mode) {
+      a.fin_slabs = fin_slabs;
+      a.slab_done = slab_done;
+    }
     CANDMC_TRY(summa_sweep(a));
+  }
+  if (slabs_out > 0) {
+    // every slab has been summed over the depth and is on its way to the host: nothing left but to wait for the transfers
+    CANDMC_CHECK(slabs_out == fin_slabs, "d25_summa: %d of %d C slabs finalised", slabs_out, fin_slabs);
+    CANDMC_TRY(stream_wait(st, d2h));
+    CANDMC_TRY(stream_wait(st, runtime().comm_stream));
+    CANDMC_CUDA(cudaStreamSynchronize(st));
+    return OK;
   }
   if (fctx) {
     CANDMC_TRY(fused_finish(fctx, layer, fparams, sC.ptr(), sC.ld(), st));

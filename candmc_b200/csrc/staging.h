@@ -65,6 +65,13 @@ class StagedMatrix {
                                   stream));
     return OK;
   }
+  // columns [c0, c0 + w) of a device matrix `src` (leading dimension ld_src) to the same columns of the caller's host matrix
+  int close_out_cols(const double* src, int64_t ld_src, int64_t c0, int64_t w, cudaStream_t stream) {
+    if (!staged_ || w <= 0) return OK;
+    CANDMC_CUDA(cudaMemcpy2DAsync(user_ + c0 * user_ld_, user_ld_ * 8, src, ld_src * 8, rows_ * 8, w, cudaMemcpyDeviceToHost,
+                                  stream));
+    return OK;
+  }
   double* ptr() const { return dev_; }
   int64_t ld() const { return ld_; }
   bool staged() const { return staged_; }

@@ -52,9 +52,12 @@ unsigned long long candmc_launch_count(void);
  * on 2 GPUs only so far, hence opt-in); 0 uses ncclAllReduce after the GEMM (also the automatic fallback when IPC is
  * unavailable or the block is not a multiple of 128*c).  Must be the same on all ranks. */
 int candmc_set_fused_reduce(int on);
-/* Host operands on q x q x c grids: 1 skips the upload of an A (B) block whose grid column (row) is not one of the layer's
- * panels (default 0: upload both). */
+/* Host operands on q x q x c grids: 1 (default) skips the upload of an A (B) block whose grid column (row) is not one of the
+ * layer's panels — the multiply never reads it there; 0 uploads both blocks on every rank. */
 int candmc_set_skip_unused_uploads(int on);
+/* Host C blocks in candmc_d25_summa: 1 (default) = the second half of the last panel's k-chunks is multiplied column slab by
+ * column slab, each slab is summed over the depth and downloaded while the next ones multiply; 0 = one download at the end. */
+int candmc_set_early_c_download(int on);
 /* Test/measurement hook: 0 disables the split-K path the GEMM takes for small tile counts (default on). */
 int candmc_debug_splitk(int on);
 /* Test/measurement hook: 1 makes the GEMM walk its tiles round-robin instead of claiming them from an atomic counter. */

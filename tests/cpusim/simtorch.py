@@ -51,6 +51,21 @@ def _to_sim(t):
     return out
 
 
+def _to_pinned(t):
+    """CPU tensor -> tensor in simulator PINNED host memory (cudaMallocHost): copies to and from it are truly asynchronous
+    under the deferred stream scheduler, as on a GPU, while pageable memory makes them host-synchronous."""
+    import torch
+
+    t = t.detach().contiguous()
+    nbytes = max(t.numel() * t.element_size(), 8)
+    ptr = C.c_void_p()
+    assert sim().cudaMallocHost(C.byref(ptr), C.c_size_t(nbytes)) == 0
+    buf = (C.c_char * nbytes).from_address(ptr.value)
+    out = torch.frombuffer(buf, dtype=t.dtype, count=t.numel()).reshape(t.shape)
+    out.copy_(t)
+    return out
+
+
 def _is_cuda_device(d):
     return d is not None and str(d).startswith("cuda")
 
@@ -114,12 +129,13 @@ def install():
             return (other.t - self.t) * 1e3
 
     torch.cuda.Event = SimEvent
-    torch.Tensor.pin_memory = lambda self, *a, **k: self
+    torch.Tensor.pin_memory = lambda self, *a, **k: _to_pinned(self)
 
     def pinned(fn):
         def wrapped(*a, **k):
-            k.pop("pin_memory", None)
-            return fn(*a, **k)
+            pin = k.pop("pin_memory", None)
+            out = fn(*a, **k)
+            return _to_pinned(out) if pin else out
         return wrapped
 
     for name in ("full", "zeros", "empty", "ones"):
@@ -135,6 +151,9 @@ def install():
                 yield x
             elif isinstance(x, (list, tuple)):
                 yield from _flat(x)
+
+    _METADATA = {"data_ptr", "numel", "size", "dim", "stride", "element_size", "is_contiguous", "__get__", "storage_offset",
+                 "__len__", "nelement", "is_floating_point"}
 
     class SimDeviceMode(TorchFunctionMode):
         busy = False
@@ -152,12 +171,24 @@ def install():
                     finally:
                         SimDeviceMode.busy = False
                 return out
-            kwargs.pop("pin_memory", None)
+            if kwargs.pop("pin_memory", None) and not SimDeviceMode.busy:
+                SimDeviceMode.busy = True
+                try:
+                    return _to_pinned(func(*args, **kwargs))
+                finally:
+                    SimDeviceMode.busy = False
+            # torch's own operations are stream-ordered with the library's work on a GPU; here they run eagerly on the host, so
+            # everything queued on the simulated device has to have happened first
+            name = getattr(func, "__name__", "")
+            if name in _METADATA:
+                return func(*args, **kwargs)
+            if not SimDeviceMode.busy and any(t.numel() and sim().cpusim_is_device(t.data_ptr())
+                                              for t in _flat(list(args) + list(kwargs.values()))):
+                sim().cpusim_check()
             out = func(*args, **kwargs)
             if SimDeviceMode.busy or not isinstance(out, torch.Tensor) or out.numel() == 0:
                 return out
-            name = getattr(func, "__name__", "")
-            if name in ("cpu", "numpy", "item", "tolist", "__get__", "data_ptr"):
+            if name in ("cpu", "numpy", "item", "tolist"):
                 return out
             if sim().cpusim_is_device(out.data_ptr()):
                 return out

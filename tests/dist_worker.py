@@ -525,6 +525,11 @@ def main():
             n_host = 512 if os.environ.get("CANDMC_CPUSIM") == "1" else 4096   # plain-loop GEMM in the simulator
             case_d25(world, golden, f"d25_ksplit_host_n{n_host}_{tag}", n_host, 2, 0, use_host=True, check_golden=False, oracle=False)
             case_d25(world, golden, f"d25_ksplit_host_n96_{tag}", 96, 2, 0, use_host=True, lda_pad=2)
+            # k-slice of 1024 -> four upload chunks; the last two are multiplied slab-wise with the C slabs summed and downloaded early
+            case_d25(world, golden, f"d25_ksplit_host_n2048_slabs_{tag}", 2048, 2, 0, use_host=True, check_golden=False, oracle=False)
+            cb.lib().candmc_set_early_c_download(0)
+            case_d25(world, golden, f"d25_ksplit_host_n2048_late_{tag}", 2048, 2, 0, use_host=True, check_golden=False, oracle=False)
+            cb.lib().candmc_set_early_c_download(1)
         if P == 4:
             case_d25(world, golden, "d25_n96_q2_c1_ovp0", 96, 1, 0)
             case_d25(world, golden, "d25_n96_q2_c1_ovp1", 96, 1, 1)

@@ -71,7 +71,7 @@ for _m, _sched in (("race", "sync"), ("race", "lifo"), ("ordered", "lifo"), ("or
 # numbers are not measurements.  `--n` travels in CPUSIM_ARGS because torchrun's parser trips over it after the script name.
 for _n in (1, 8):
     _job(f"bench{_n}", _torchrun(_n, 29790 + _n, os.path.join(SIM, "run_sim.py"), "bench.py", "--gpus", str(_n), "--steps", "1",
-                                 "--warmup", "1", "--no-cpu-baseline"), CPUSIM_ARGS="--n 512")
+                                 "--warmup", "1", "--no-cpu-baseline"), CPUSIM_ARGS="--n 512", CPUSIM_SCHED="sync" if _n == 1 else "lifo")
 
 # the reference's OWN test mains (compiled unmodified against include/, oracle/_ref/dropin — present where /root/reference
 # was available at build time): the simulator build is preloaded in front of libcandmc_b200.so, which exports the same ABI

@@ -551,7 +551,7 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   // (whole 128-wide tile columns per depth rank, CUDA IPC available), otherwise ncclAllReduce
   // A HOST C block is the slowest thing this call moves (PCIe, after the last multiply): when the multiply is pipelined in
   // k-chunks anyway, the second half of the last panel's chunks is multiplied column slab by column slab, and every slab is
-  // summed over the depth (background communicator) and downloaded while the next slabs still multiply — only the last
+  // summed over the depth and downloaded while the next slabs still multiply — only the last
   // slab's transfer stays exposed.  The fused depth sum works on whole square blocks, so it stays off on this path.
   const int fin_slabs = (sC.staged() && nn && runtime().early_c_download) ? pick_fin_slabs(b) : 0;
   const int nch_consumer = ksplit ? (chunked ? up_chunks : 1) : sweep_chunks(b, args->trans_A, args->trans_B, cdt_row, cdt_col);
@@ -565,7 +565,9 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
     if (c > 1) {   // depth sum of the slab in place in bufC (ld = b: the slab is contiguous), then straight to the host
       cudaStream_t cs = runtime().comm_stream;
       CANDMC_CUDA(cudaStreamWaitEvent(cs, e, 0));
-      CANDMC_TRY(comm_allreduce(cdt_kdir, bufC + c0 * b, bufC + c0 * b, b * w, cs, true));
+      // full-width communicator: the one the single depth sum has always used (an all-reduce on a CTA-capped communicator has
+      // never run on this NCCL; grouped send/recv on one hung).  It shares SMs with the slab multiplies.
+      CANDMC_TRY(comm_allreduce(cdt_kdir, bufC + c0 * b, bufC + c0 * b, b * w, cs, false));
       cudaEvent_t r = g_events.get();
       CANDMC_CHECK(r != nullptr, "event pool exhausted");
       CANDMC_CUDA(cudaEventRecord(r, cs));

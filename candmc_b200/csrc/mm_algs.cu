@@ -302,7 +302,9 @@ int summa_sweep(SummaArgs& a) {
 // C panel are exposed.  Three streams: H2D (aux), compute (caller's), D2H (comm — idle on a 1x1 grid).
 int host_pipelined_gemm_nn(int64_t m, int64_t n, int64_t k, const double* hA, int64_t lda, const double* hB, int64_t ldb,
                            double* hC, int64_t ldc, cudaStream_t st) {
-  const int NP = 8;
+  // exposed = the first A slab + B chunk on the way in and the last C panel on the way out: 1/NP of A and of C each.  Panels
+  // of >= 2048 columns still keep the 128 x 128-tile GEMM at 28+ waves, so large products are cut finer.
+  const int NP = runtime().host_pipeline_panels > 0 ? runtime().host_pipeline_panels : ((n >= 32768 && k >= 32768) ? 16 : 8);
   const int64_t nb = ((n + NP - 1) / NP + 127) / 128 * 128;   // panel width (multiple of the CTA tile)
   const int64_t kc = ((k + NP - 1) / NP + 15) / 16 * 16;      // k-chunk of the first panel
   const int npanels = (int)((n + nb - 1) / nb), nchunks = (int)((k + kc - 1) / kc);
@@ -424,6 +426,12 @@ int trsm_llnn(int64_t b, int64_t kb, const double* T, int64_t ldt, double* W, in
 using namespace candmc;
 
 extern "C" {
+
+int candmc_set_host_pipeline_panels(int panels) {
+  CANDMC_CHECK(panels >= 0 && panels <= 64, "candmc_set_host_pipeline_panels: 0 (automatic) .. 64");
+  runtime().host_pipeline_panels = panels;
+  return OK;
+}
 
 int candmc_set_host_pipeline_min(int64_t min_n) {
   CANDMC_CHECK(min_n >= 1, "candmc_set_host_pipeline_min: must be >= 1");

@@ -202,6 +202,8 @@ int candmc_set_min_kchunk(int64_t min_kchunk);
 /* Tuning: on a 1x1x1 grid with HOST operands and n >= this (default 2048) the multiply is streamed through PCIe in
  * column panels (upload of panel j+1 and download of panel j-1 under the GEMM of panel j) instead of staged whole. */
 int candmc_set_host_pipeline_min(int64_t min_n);
+/* ... and into how many column panels (= k-chunks of the first panel) it is cut: 0 = automatic (16 when n, k >= 32768, else 8). */
+int candmc_set_host_pipeline_panels(int panels);
 
 /* ---- symmetric full -> band reduction, trailing update ----------------------------------------
  * One level of sym_full2band (alg/SE/full_to_band.cxx:28-250) after its panel QR (:96): given the aggregated Householder

@@ -509,6 +509,10 @@ def main():
             cb.lib().candmc_set_host_pipeline_min(64)   # stream host operands panel-wise even at this size
             case_d25(world, golden, f"d25_hostpipe_n320_{tag}", 320, 1, 0, use_host=True, check_golden=False)
             case_d25(world, golden, f"d25_hostpipe_n200_pad_{tag}", 200, 1, 0, lda_pad=3, use_host=True, check_golden=False)
+            cb.lib().candmc_set_host_pipeline_panels(16)    # the cut bench.py's n = 32768 gets
+            case_d25(world, golden, f"d25_hostpipe16_n2304_{tag}", 2304, 1, 0, use_host=True, check_golden=False, oracle=False)
+            case_d25(world, golden, f"d25_hostpipe16_n200_pad_{tag}", 200, 1, 0, lda_pad=3, use_host=True, check_golden=False)
+            cb.lib().candmc_set_host_pipeline_panels(0)
             cb.lib().candmc_set_host_pipeline_min(2048)
         if P == 2:
             case_d25(world, golden, f"d25_ksplit_n64_{tag}", 64, 2, 0)

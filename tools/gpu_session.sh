@@ -3,7 +3,7 @@
 #   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh lu ncu'            (1 GPU)
 #   gpurun --gpus 4 --timeout 1200 -- 'bash tools/gpu_session.sh dist4'    (4 GPUs)
 #   gpurun --gpus 8 --timeout 1200 -- 'bash tools/gpu_session.sh dist8'    (8 GPUs)
-# Sections: lu (LU seam tests + LU bench host vs GPU), pending1 (redistribution / Yamamoto tests + their measurements), ncu (full capture at n=32768 for roofline.traffic, pack kernels),
+# Sections: e2e1 / e2eN (end-to-end knobs added without a GPU: early C download, upload policy, panel count), lu (LU seam tests + LU bench host vs GPU), pending1 (redistribution / Yamamoto tests + their measurements), ncu (full capture at n=32768 for roofline.traffic, pack kernels),
 #           dist4 (second-pass parity cases, update_A with T), dist8 (fused depth sum on 2x2x2, skip_unused_uploads)
 set -u
 cd "$(dirname "$0")/.."
@@ -52,6 +52,25 @@ for section in "$@"; do
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29536 \
         tools/bench_configs.py --pending > gpurun_out/bench_pending_4gpu.jsonl 2> gpurun_out/bench_pending_4gpu.err
       cat gpurun_out/bench_pending_4gpu.jsonl
+      ;;
+    e2e1)
+      # one GPU: the host-streamed multiply with 8 / 16 / 32 column panels (16 is the new default at n = 32768, never measured)
+      for knobs in "--host-panels 8" "" "--host-panels 32"; do
+        echo "== bench 1 GPU $knobs" >> gpurun_out/e2e1_bench.log
+        timeout 400 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline $knobs >> gpurun_out/e2e1_bench.log 2>&1
+      done
+      grep -E "==|\"metric\"" gpurun_out/e2e1_bench.log | cut -c1-300
+      ;;
+    e2eN)
+      # run under `gpurun --gpus N`: end-to-end leg with C leaving early (new default) vs one download at the end, and the old
+      # upload-everything policy; N taken from the visible devices
+      N=$(python -c "import torch; print(torch.cuda.device_count())")
+      for knobs in "" "--late-c-download" "--upload-all-blocks --late-c-download"; do
+        echo "== bench $N GPUs $knobs" >> gpurun_out/e2e${N}_bench.log
+        timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29537 \
+          bench.py --gpus $N --steps 3 --warmup 3 $knobs >> gpurun_out/e2e${N}_bench.log 2>&1
+      done
+      grep -E "==|\"metric\"" gpurun_out/e2e${N}_bench.log | cut -c1-300
       ;;
     dist8)
       for knobs in "" "--fused-reduce 2" "--upload-all-blocks"; do

@@ -265,6 +265,55 @@ def _edge_cases(seed: int) -> str:
     return "\n".join(L) + "\n"
 
 
+def random_script(seed: int, nops: int = 60) -> str:
+    """A random, valid operation sequence over the three offloaded matrices, almost without waits: uploads, downloads, GEMMs
+    (output matrix distinct from both inputs, as every call of the reference has it) and sparse row traffic with in-bounds
+    random blocks — what the scoreboard of the two-stream seam has to order correctly.  Checked against the oracle, which is
+    pinned to the unmodified lu_offload.cxx by the committed scripts."""
+    rng = np.random.RandomState(seed)
+    size = {0: 64 * 64, 1: 48 * 40, 2: 40 * 48}
+    L = [f"alloc {m} {n}" for m, n in size.items()] + [f"fill {m} {seed + m}" for m in size]
+    s = seed + 10
+
+    def block(mat, rows, cols):
+        """random (offset, ld) of a rows x cols block inside matrix `mat`"""
+        ld = rows + int(rng.randint(0, 5))
+        span = (cols - 1) * ld + rows
+        return int(rng.randint(0, size[mat] - span + 1)), ld
+
+    for _ in range(nops):
+        op = rng.choice(["up", "down", "gemm", "gemm", "sp", "wait"], p=[0.2, 0.25, 0.15, 0.15, 0.2, 0.05])
+        if op == "up":
+            mat = int(rng.randint(0, 3)); nrow, ncol = int(rng.randint(1, 25)), int(rng.randint(1, 13))
+            off, ldb = block(mat, nrow, ncol)
+            L.append(f"up {nrow} {ncol} {nrow + int(rng.randint(0, 4))} {ldb} {off} {mat} {s}"); s += 1
+        elif op == "down":
+            mat = int(rng.randint(0, 3)); nrow, ncol = int(rng.randint(1, 25)), int(rng.randint(1, 13))
+            off, lda = block(mat, nrow, ncol)
+            L.append(f"down {nrow} {ncol} {lda} {nrow + int(rng.randint(0, 3))} {off} {mat}")
+        elif op == "gemm":
+            mc = int(rng.randint(0, 3)); others = [m for m in (0, 1, 2) if m != mc]
+            ma, mb = int(rng.choice(others)), int(rng.choice(others))
+            m, n, k = int(rng.randint(1, 17)), int(rng.randint(1, 17)), int(rng.randint(0, 17))
+            tA, tB = rng.choice(["N", "T"]), rng.choice(["N", "T"])
+            ra, ca = (m, max(k, 1)) if tA == "N" else (max(k, 1), m)
+            rb, cb_ = (max(k, 1), n) if tB == "N" else (n, max(k, 1))
+            offA, ldA = block(ma, ra, ca); offB, ldB = block(mb, rb, cb_); offC, ldC = block(mc, m, n)
+            alpha, beta = rng.choice([1.0, -1.0, 0.5]), rng.choice([0.0, 1.0, -0.5])
+            L.append(f"gemm {tA} {tB} {m} {n} {k} {alpha} {offA} {ma} {ldA} {offB} {mb} {ldB} {beta} {offC} {mc} {ldC}")
+        elif op == "sp":
+            mat = int(rng.randint(0, 3)); rw = rng.choice(["r", "w", "s"])
+            nrow, ncol = int(rng.randint(1, 7)), int(rng.randint(1, 11))
+            ld = 64 if mat == 0 else int(rng.choice([40, 48]))
+            top = size[mat] - (ncol - 1) * ld            # a row starts below this offset
+            starts = rng.permutation(min(top, ld))[:nrow]  # distinct rows inside the first column: no aliasing for w / s
+            offs = " ".join(str(int(o)) for o in starts)
+            L.append(f"sp {rw} {nrow} {ncol} {ld} {ncol + int(rng.randint(0, 3))} {mat} {s} {offs}"); s += 1
+        else:
+            L.append("wait")
+    return "\n".join(L) + "\n"
+
+
 def make_scripts() -> dict:
     return {
         "lu_ld96_b16": _lu_like(96, 16, 1, 100, ragged=False),

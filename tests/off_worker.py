@@ -52,6 +52,28 @@ def do_script(name, overlap):
     print(json.dumps(res))
 
 
+def do_fuzz(seed, overlap, count=6):
+    """random scripts (tests/off_script.py random_script) on the device path vs the oracle: copies bit-exact, GEMM-touched
+    elements to 1e-11 relative to the magnitudes involved"""
+    from off_script import random_script
+    from candmc_b200 import lu_offload as lo
+    worst, waits, exact, total = 0.0, 0, 0, 0
+    for i in range(count):
+        text = random_script(seed * 100 + i)
+        ob = OracleBackend(); want = run_script(text, ob); ob.close()
+        be = GpuBackend(overlap=bool(overlap)); got = run_script(text, be)
+        waits += lo.stats()["cross_stream_waits"]
+        be.close()
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            g = g[: w.size]
+            scale = max(1.0, float(np.abs(w).max()) if w.size else 1.0)
+            worst = max(worst, float(np.abs(g - w).max()) / scale if w.size else 0.0)
+            exact += int((g == w).sum()); total += w.size
+    print(json.dumps({"seed": seed, "overlap": overlap, "scripts": count, "max_rel_vs_oracle": worst, "cross_stream_waits": waits,
+                      "exact_fraction": exact / max(total, 1)}))
+
+
 class OracleLo:
     """The reference-named API (candmc_b200.lu_offload's surface) on top of oracle_off_*, so that the CPU suite can run
     do_trailing's logic against the checker (tests/test_lu_offload_oracle.py)."""
@@ -159,6 +181,10 @@ def do_trailing(n, k, overlap, lo=None):
     print(json.dumps(res))
     return res
 
+
+if __name__ == "__main__" and sys.argv[1] == "fuzz":
+    do_fuzz(int(sys.argv[2]), int(sys.argv[3]))
+    sys.exit(0)
 
 if __name__ == "__main__":
     if sys.argv[1] == "script":

@@ -73,6 +73,15 @@ for _n in (1, 8):
     _job(f"bench{_n}", _torchrun(_n, 29790 + _n, os.path.join(SIM, "run_sim.py"), "bench.py", "--gpus", str(_n), "--steps", "1",
                                  "--warmup", "1", "--no-cpu-baseline"), CPUSIM_ARGS="--n 512", CPUSIM_SCHED="sync" if _n == 1 else "lifo")
 
+# randomised cases (tests/fuzz_worker.py: random grids, sizes, paddings, roots, transposes, host/device operands, knobs)
+FUZZ = [(4, 3, "lifo")] + ([(p, sd, pol) for p in (1, 2, 4, 6, 8, 9, 16) for sd, pol in ((11, "sync"), (12, "lifo"), (13, "random:13"))]
+                           if FULL else [])
+for _p, _sd, _pol in FUZZ:
+    _job(f"fuzz{_p}_{_sd}", _torchrun(_p, 29600 + _p * 20 + _sd, os.path.join(HERE, "fuzz_worker.py"), str(_sd), "24"), CPUSIM_SCHED=_pol)
+
+for _sd, _pol in ((1, "lifo"),) + (((2, "random:2"), (3, "sync"), (4, "lifo")) if FULL else ()):
+    _job(f"lufuzz{_sd}", [sys.executable, os.path.join(HERE, "off_worker.py"), "fuzz", str(_sd), "1"], CPUSIM_SCHED=_pol)
+
 # the reference's OWN test mains (compiled unmodified against include/, oracle/_ref/dropin — present where /root/reference
 # was available at build time): the simulator build is preloaded in front of libcandmc_b200.so, which exports the same ABI
 DROPIN = os.path.join(ROOT, "oracle", "_ref", "dropin")
@@ -204,6 +213,24 @@ def test_reference_test_mains_pass_on_the_simulator(case):
     rc, so, se = RESULTS[f"dropin_{case}"]
     assert rc == 0, so[-2000:] + se[-2000:]
     assert DROPIN_CASES[case][4] in so and "FAILED" not in so and "test failed" not in so.lower()
+
+
+@pytest.mark.parametrize("nproc,seed,policy", FUZZ)
+def test_randomised_cases_on_the_simulator(nproc, seed, policy):
+    rc, so, se = RESULTS[f"fuzz{nproc}_{seed}"]
+    assert rc == 0, so[-3000:] + se[-3000:]
+    out = json.loads([line for line in so.splitlines() if line.startswith("{")][-1])
+    assert out["failed_all_ranks"] == 0 and out["checks_rank0"] > 0
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4] if FULL else [1])
+def test_random_lu_offload_scripts_on_the_simulator(seed):
+    """random op sequences over the three offloaded matrices (tests/off_script.py random_script), two streams, deferred
+    scheduling: the scoreboard must order every transfer behind exactly the GEMMs it conflicts with"""
+    rc, so, se = RESULTS[f"lufuzz{seed}"]
+    assert rc == 0, so[-2000:] + se[-3000:]
+    r = json.loads(so.strip().splitlines()[-1])
+    assert r["max_rel_vs_oracle"] <= 1e-11 and r["exact_fraction"] > 0.8
 
 
 @pytest.mark.parametrize("nproc", [1, 8])

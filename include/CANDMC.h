@@ -14,6 +14,9 @@
 /* block-cyclic <-> blocked layout bridge (no reference counterpart; see the header) */
 #include "candmc/redist.h"
 
+/* trailing update of the symmetric full -> band reduction (the GPU half of alg/SE/full_to_band.cxx's sym_full2band) */
+#include "candmc/full_to_band.h"
+
 /* local multiply + packing */
 #include "candmc/lapack.h"
 #include "candmc/util.h"

@@ -108,3 +108,23 @@ def test_lu_offload_fails_loudly_without_gpu():
     with pytest.raises(cb.CandmcError) as e:
         lo.alloc_L(16)
     assert e.value.code == 5
+
+
+def test_cxx_headers_compile_and_cover_the_widening_entry_points(tmp_path):
+    """include/CANDMC.h is what a reference-style C++ caller includes; the inline wrappers of the widening rows must compile
+    against the C ABI they forward to (g++ only, nothing is run)"""
+    import subprocess
+
+    src = tmp_path / "t.cxx"
+    src.write_text("""
+#include "CANDMC.h"
+void use(pview* pv, double* A, double* Y, double* B) {
+  sym_full2band_update(A, 64, 128, 32, 8, pv, Y, 48);
+  cyclic_to_blocked(64, 64, 8, A, 32, B, 32, pv);
+  blocked_to_cyclic(64, 64, 8, B, 32, A, 32, pv);
+}
+""")
+    inc = os.path.join(ROOT, "include")
+    p = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-I", inc, "-I", os.path.join(inc, "candmc_compat"), str(src)],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-3000:]

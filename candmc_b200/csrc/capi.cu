@@ -39,6 +39,11 @@ int candmc_set_fused_reduce(int on) {
   return OK;
 }
 
+int candmc_set_b_first_chunk_early(int on) {
+  runtime().b_first_chunk_early = (on != 0);
+  return OK;
+}
+
 int candmc_set_early_c_download(int on) {
   runtime().early_c_download = (on != 0);
   return OK;

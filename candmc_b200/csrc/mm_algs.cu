@@ -142,11 +142,21 @@ int upload_chunks(const double* hA, int64_t lda, const double* hB, int64_t ldb, 
   a_ready->assign(nchunks, nullptr);
   b_ready->assign(nchunks, nullptr);
   if (hB) {
-    CANDMC_CUDA(cudaMemcpy2DAsync(dB, k * 8, hB, ldb * 8, k * 8, cols, cudaMemcpyHostToDevice, h2d));  // k x cols, ld = k
+    // opt-in (candmc_set_b_first_chunk_early, not measured yet): the rows of the first k-chunk go ahead in their own 2-D copy
+    // (narrow rows, but only 1/nchunks of B), so the first multiply does not wait for the whole block
+    const int64_t k0 = (runtime().b_first_chunk_early && nchunks > 1) ? kc : 0;
+    if (k0 > 0) {
+      CANDMC_CUDA(cudaMemcpy2DAsync(dB, k * 8, hB, ldb * 8, k0 * 8, cols, cudaMemcpyHostToDevice, h2d));
+      cudaEvent_t e0 = g_events.get();
+      CANDMC_CHECK(e0 != nullptr, "event pool exhausted");
+      CANDMC_CUDA(cudaEventRecord(e0, h2d));
+      (*b_ready)[0] = e0;
+    }
+    CANDMC_CUDA(cudaMemcpy2DAsync(dB + k0, k * 8, hB + k0, ldb * 8, (k - k0) * 8, cols, cudaMemcpyHostToDevice, h2d));  // ld = k
     cudaEvent_t e = g_events.get();
     CANDMC_CHECK(e != nullptr, "event pool exhausted");
     CANDMC_CUDA(cudaEventRecord(e, h2d));
-    for (int t = 0; t < nchunks; ++t) (*b_ready)[t] = e;
+    for (int t = (k0 > 0 ? 1 : 0); t < nchunks; ++t) (*b_ready)[t] = e;
   }
   for (int t = 0; t < nchunks; ++t) {
     if (hA) {

@@ -25,6 +25,7 @@ struct Runtime {
   unsigned tile_counter_seq = 0;
   bool fused_reduce_grids = false;      // ... also on q x q x c grids (validated so far on 1 x 1 x c only)
   bool skip_unused_uploads = true;      // host operands: a layer's rank uploads only the blocks its panels use (candmc_set_skip_unused_uploads)
+  bool b_first_chunk_early = false;     // host B: upload the first k-chunk's rows ahead of the rest (opt-in until measured)
   bool early_c_download = true;         // host C: finalise + download column slabs under the last multiplies (candmc_set_early_c_download)
   bool fused_reduce = true;             // depth all-reduce fused into the last GEMM's epilogue over peer memory
   bool splitk = true;                   // cut small-tile-count GEMMs along k too

@@ -58,6 +58,9 @@ int candmc_set_skip_unused_uploads(int on);
 /* Host C blocks in candmc_d25_summa: 1 (default) = the second half of the last panel's k-chunks is multiplied column slab by
  * column slab, each slab is summed over the depth and downloaded while the next ones multiply; 0 = one download at the end. */
 int candmc_set_early_c_download(int on);
+/* Host B blocks: 1 = the rows of the first k-chunk are uploaded ahead of the rest so the first multiply starts earlier
+ * (default 0: one copy of the whole block, whose wide rows keep the 2-D DMA efficient; the trade-off is not measured yet). */
+int candmc_set_b_first_chunk_early(int on);
 /* Test/measurement hook: 0 disables the split-K path the GEMM takes for small tile counts (default on). */
 int candmc_debug_splitk(int on);
 /* Test/measurement hook: 1 makes the GEMM walk its tiles round-robin instead of claiming them from an atomic counter. */

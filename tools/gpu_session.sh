@@ -65,7 +65,7 @@ for section in "$@"; do
       # run under `gpurun --gpus N`: end-to-end leg with C leaving early (new default) vs one download at the end, and the old
       # upload-everything policy; N taken from the visible devices
       N=$(python -c "import torch; print(torch.cuda.device_count())")
-      for knobs in "" "--late-c-download" "--upload-all-blocks --late-c-download"; do
+      for knobs in "" "--late-c-download" "--upload-all-blocks --late-c-download" "--b-first-chunk-early"; do
         echo "== bench $N GPUs $knobs" >> gpurun_out/e2e${N}_bench.log
         timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29537 \
           bench.py --gpus $N --steps 3 --warmup 3 $knobs >> gpurun_out/e2e${N}_bench.log 2>&1

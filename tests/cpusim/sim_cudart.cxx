@@ -13,7 +13,11 @@
 #include <string.h>
 #include <time.h>
 
+#include <fcntl.h>
 #include <sched.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <deque>
@@ -30,8 +34,13 @@ constexpr unsigned char kCanary = 0xA5;
 
 struct Alloc {
   size_t bytes;
-  bool device;  // false: pinned host
+  bool device;     // false: pinned host
+  bool shm;        // backed by a POSIX shared-memory object (large device allocations): can be exported with cudaIpcGetMemHandle
+  bool peer;       // another process's allocation mapped here by cudaIpcOpenMemHandle (its owner checks the canaries)
+  char name[48];
 };
+constexpr size_t kShmThreshold = 256 * 1024;
+constexpr size_t kShmHeader = 256;
 std::map<uintptr_t, Alloc> g_allocs;   // user base -> allocation
 cudaError_t g_last = cudaSuccess;
 int g_device = 0;
@@ -113,6 +122,7 @@ const Alloc* find_alloc(const void* p, uintptr_t* base = nullptr) {
 
 void check_canaries(const char* when) {
   for (auto& kv : g_allocs) {
+    if (kv.second.peer) continue;
     const unsigned char* lo = (const unsigned char*)kv.first - kGuard;
     const unsigned char* hi = (const unsigned char*)kv.first + kv.second.bytes;
     for (size_t i = 0; i < kGuard; ++i)
@@ -125,36 +135,67 @@ void check_canaries(const char* when) {
   }
 }
 
+void fill_garbage(unsigned char* user, size_t bytes) {
+  // signalling-NaN-ish garbage: 0x7FF4A5A5A5A5A5A5
+  uint64_t pat = 0x7FF4A5A5A5A5A5A5ull;
+  for (size_t i = 0; i + 8 <= bytes; i += 8) memcpy(user + i, &pat, 8);
+  for (size_t i = bytes & ~(size_t)7; i < bytes; ++i) user[i] = 0xA7;
+}
+
 void* sim_alloc(size_t bytes, bool device) {
-  void* raw = nullptr;
-  size_t total = bytes + 2 * kGuard + 256;
-  if (posix_memalign(&raw, 256, total) != 0) return nullptr;
-  // keep the user pointer 256-byte aligned like cudaMalloc: guard sits in the 256 bytes in front of it
-  unsigned char* user = (unsigned char*)raw + 256;
+  Alloc a;
+  memset(&a, 0, sizeof(a));
+  a.bytes = bytes;
+  a.device = device;
+  unsigned char* user = nullptr;
+  if (device && bytes >= kShmThreshold) {
+    // a named shared-memory object, so that another rank-process can map it (CUDA IPC); same layout as the heap case
+    static int counter = 0;
+    snprintf(a.name, sizeof(a.name), "/cpusim.mem.%d.%d", (int)getpid(), counter++);
+    const size_t total = kShmHeader + bytes + kGuard;
+    int fd = shm_open(a.name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)total) != 0) {
+      if (fd >= 0) close(fd);
+      return nullptr;
+    }
+    void* m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) {
+      shm_unlink(a.name);
+      return nullptr;
+    }
+    a.shm = true;
+    user = (unsigned char*)m + kShmHeader;
+  } else {
+    void* raw = nullptr;
+    if (posix_memalign(&raw, 256, bytes + 2 * kGuard + 256) != 0) return nullptr;
+    // keep the user pointer 256-byte aligned like cudaMalloc: guard sits in the 256 bytes in front of it
+    user = (unsigned char*)raw + 256;
+  }
   memset(user - kGuard, kCanary, kGuard);
   memset(user + bytes, kCanary, kGuard);
-  if (device) {
-    // signalling-NaN-ish garbage: 0x7FF4A5A5A5A5A5A5
-    uint64_t pat = 0x7FF4A5A5A5A5A5A5ull;
-    for (size_t i = 0; i + 8 <= bytes; i += 8) memcpy(user + i, &pat, 8);
-    for (size_t i = bytes & ~(size_t)7; i < bytes; ++i) user[i] = 0xA7;
-  }
-  g_allocs[(uintptr_t)user] = Alloc{bytes, device};
+  if (device) fill_garbage(user, bytes);
+  g_allocs[(uintptr_t)user] = a;
   return user;
 }
 
 cudaError_t sim_free(void* p, bool device) {
   if (!p) return cudaSuccess;
   auto it = g_allocs.find((uintptr_t)p);
-  if (it == g_allocs.end() || it->second.device != device) {
+  if (it == g_allocs.end() || it->second.device != device || it->second.peer) {
     fprintf(stderr, "cpusim: %s of a pointer that is not a live %s allocation: %p\n", device ? "cudaFree" : "cudaFreeHost",
             device ? "device" : "pinned", p);
     abort();
   }
   check_canaries(device ? "cudaFree" : "cudaFreeHost");
   memset(p, 0xDD, it->second.bytes);  // use-after-free shows up as garbage
+  if (it->second.shm) {
+    shm_unlink(it->second.name);
+    munmap((unsigned char*)p - kShmHeader, kShmHeader + it->second.bytes + kGuard);
+  } else {
+    free((unsigned char*)p - 256);
+  }
   g_allocs.erase(it);
-  free((unsigned char*)p - 256);
   return cudaSuccess;
 }
 
@@ -315,16 +356,35 @@ void drain_all(const char* why) {
 struct AtExit {
   ~AtExit() {
     check_canaries("process exit");
+    for (auto& kv : g_allocs)
+      if (kv.second.shm && !kv.second.peer) shm_unlink(kv.second.name);   // nothing of ours stays behind in /dev/shm
     if (getenv("CPUSIM_VERBOSE"))
       fprintf(stderr, "cpusim: %llu queued tasks executed, %llu of them after a task that was enqueued later\n",
               (unsigned long long)g_executed, (unsigned long long)g_reordered);
   }
 } g_at_exit;
 
-CUresult fake_encode_tiled(CUtensorMap* out, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+CUresult fake_encode_tiled(CUtensorMap* out, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* gdim,
+                           const cuuint64_t* gstride, const cuuint32_t* box, const cuuint32_t* estride, CUtensorMapInterleave il,
+                           CUtensorMapSwizzle sw, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+  static_assert(sizeof(cpusim::SimTensorMap) <= sizeof(CUtensorMap), "descriptor does not fit");
+  // the driver's own argument rules for what the product encodes (2-D FP64 tiles)
+  if (dt != CU_TENSOR_MAP_DATA_TYPE_FLOAT64 || rank != 2 || il != CU_TENSOR_MAP_INTERLEAVE_NONE) return CUDA_ERROR_INVALID_VALUE;
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0 || gstride[0] % 16 != 0) return CUDA_ERROR_INVALID_VALUE;
+  if (box[0] == 0 || box[1] == 0 || box[0] > 256 || box[1] > 256 || estride[0] != 1 || estride[1] != 1) return CUDA_ERROR_INVALID_VALUE;
+  if (sw == CU_TENSOR_MAP_SWIZZLE_128B && box[0] * 8 > 128) return CUDA_ERROR_INVALID_VALUE;
+  if (sw != CU_TENSOR_MAP_SWIZZLE_128B && sw != CU_TENSOR_MAP_SWIZZLE_NONE) return CUDA_ERROR_INVALID_VALUE;
   memset(out, 0, sizeof(*out));
+  cpusim::SimTensorMap m;
+  m.magic = cpusim::kTensorMapMagic;
+  m.base = static_cast<const char*>(base);
+  m.dim[0] = gdim[0];
+  m.dim[1] = gdim[1];
+  m.stride1 = gstride[0];
+  m.box[0] = box[0];
+  m.box[1] = box[1];
+  m.swizzle128 = sw == CU_TENSOR_MAP_SWIZZLE_128B;
+  memcpy(out, &m, sizeof(m));
   return CUDA_SUCCESS;
 }
 
@@ -564,6 +624,58 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
 }
 
 cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+
+// ---- CUDA IPC: large device allocations are shared-memory objects, the handle is the object's name ------------------------
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  auto it = g_allocs.find((uintptr_t)p);
+  if (it == g_allocs.end() || !it->second.shm || it->second.peer) {
+    g_last = cudaErrorInvalidValue;   // not the base of an exportable allocation
+    return cudaErrorInvalidValue;
+  }
+  memset(h, 0, sizeof(*h));
+  static_assert(sizeof(h->reserved) >= sizeof(it->second.name), "handle too small");
+  memcpy(h->reserved, it->second.name, sizeof(it->second.name));
+  return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+  char name[64];
+  memcpy(name, h.reserved, sizeof(name));
+  name[63] = 0;
+  int fd = shm_open(name, O_RDWR, 0600);
+  struct stat sb;
+  if (fd < 0 || fstat(fd, &sb) != 0) {
+    if (fd >= 0) close(fd);
+    g_last = cudaErrorInvalidValue;
+    return cudaErrorInvalidValue;
+  }
+  void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) {
+    g_last = cudaErrorMemoryAllocation;
+    return cudaErrorMemoryAllocation;
+  }
+  Alloc a;
+  memset(&a, 0, sizeof(a));
+  a.bytes = (size_t)sb.st_size - kShmHeader - kGuard;
+  a.device = true;
+  a.shm = true;
+  a.peer = true;
+  snprintf(a.name, sizeof(a.name), "%s", name);
+  unsigned char* user = (unsigned char*)m + kShmHeader;
+  g_allocs[(uintptr_t)user] = a;
+  *p = user;
+  return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void* p) {
+  auto it = g_allocs.find((uintptr_t)p);
+  if (it == g_allocs.end() || !it->second.peer) {
+    g_last = cudaErrorInvalidValue;
+    return cudaErrorInvalidValue;
+  }
+  munmap((unsigned char*)p - kShmHeader, kShmHeader + it->second.bytes + kGuard);
+  g_allocs.erase(it);
+  return cudaSuccess;
+}
 
 cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* q) {
   if (strcmp(symbol, "cuTensorMapEncodeTiled") == 0) {

@@ -8,8 +8,10 @@
 // sequences on real multi-process grids — before GPU minutes are spent.  The product library never loads or links any of
 // this (tests/test_boundary.py checks), and nothing here is a fallback: libcandmc_b200.so still fails without a B200.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
 #include <string.h>
 
 #include <functional>
@@ -27,6 +29,18 @@ void* dyn_smem();         // dynamic shared memory of the running block
 void sync_threads();      // block barrier
 void sync_warp_exchange(const void* in, void* out, int src_lane, size_t bytes);  // one warp shuffle
 void launch(cudaStream_t stream, dim3 grid, dim3 block, size_t smem, std::function<void()> body);
+// ---- the PTX the hot GEMM kernel is written in (common.cuh), emulated ------------------------------------------------
+uint32_t smem_handle(const void* p);   // "shared-space address": offset inside the block's dynamic shared memory (+4096)
+void* smem_ptr(uint32_t handle);
+void mbar_init(uint32_t bar, uint32_t count);
+void mbar_arrive(uint32_t bar);
+void mbar_expect_tx(uint32_t bar, uint32_t bytes);   // arrive.expect_tx
+bool mbar_try_wait(uint32_t bar, uint32_t parity);   // yields to the other fibers when the phase is not complete yet
+void tma_load_2d(uint32_t dst, const void* tensor_map, uint32_t bar, int c0, int c1);  // tiled, 128 B swizzle, OOB zero fill
+void warp_allgather16(const void* in16, void* out32x16);  // every lane contributes 16 bytes, all get all
+void named_barrier(int id, int count);                 // bar.sync id, count
+void dmma_defer(double* d0, double* d1, double a, double b);   // log one DMMA.8x8x4 of the calling lane
+void dmma_flush();                                     // warp rendezvous: apply every logged DMMA
 
 }  // namespace cpusim
 
@@ -37,6 +51,8 @@ void launch(cudaStream_t stream, dim3 grid, dim3 block, size_t smem, std::functi
 #define warpSize 32
 
 #define __launch_bounds__(...)
+#undef __grid_constant__
+#define __grid_constant__
 #undef __forceinline__
 #define __forceinline__ inline
 // a __shared__ array is shared by the fibers of a block, which run one block at a time on one OS thread: `static` is it
@@ -54,7 +70,7 @@ static inline void launch_args(cudaStream_t stream, dim3 grid, dim3 block, size_
   ::cpusim::launch_args((cudaStream_t)(stream), dim3(grid), dim3(block), (size_t)(smem), kern, ##__VA_ARGS__)
 
 static inline void __syncthreads() { ::cpusim::sync_threads(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline void __syncwarp(unsigned = 0xffffffffu) { ::cpusim::dmma_flush(); }
 
 template <class T>
 static inline T __ldg(const T* p) {
@@ -118,3 +134,29 @@ template <class T>
 static inline cudaError_t cudaFuncSetAttribute(T* f, cudaFuncAttribute a, int v) {
   return ::cudaFuncSetAttribute(reinterpret_cast<const void*>(f), a, v);
 }
+
+// common.cuh's device helpers (there under #ifdef __CUDACC__), same names and signatures, on the emulation above
+namespace candmc {
+static inline uint32_t smem_u32(const void* p) { return ::cpusim::smem_handle(p); }
+static inline void mbar_init(uint64_t* bar, uint32_t count) { ::cpusim::mbar_init(smem_u32(bar), count); }
+static inline void fence_mbar_init() {}
+static inline void fence_proxy_async() {}
+static inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { ::cpusim::mbar_expect_tx(smem_u32(bar), bytes); }
+static inline void mbar_arrive(uint64_t* bar) { ::cpusim::mbar_arrive(smem_u32(bar)); }
+static inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return ::cpusim::mbar_try_wait(smem_u32(bar), parity); }
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+static inline void tma_load_2d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  ::cpusim::tma_load_2d(smem_u32(dst), tmap, smem_u32(bar), c0, c1);
+}
+static inline void tma_prefetch_desc(const CUtensorMap*) {}
+static inline double lds_f64(uint32_t addr) { return *static_cast<const double*>(::cpusim::smem_ptr(addr)); }
+// mma.sync.aligned.m8n8k4.row.col.f64: lane L holds A[L>>2][L&3], B[L&3][L>>2], C/D[L>>2][2*(L&3)+{0,1}].
+// A rendezvous of 32 fibers per DMMA would dominate the run time, so the emulation defers: a call only logs its operands
+// and where its accumulators live; the warp meets once per batch — when an accumulator comes round again (the next k-step)
+// or at __syncwarp(), which the kernel reaches before anything reads the accumulators — and every lane then applies the
+// logged DMMAs in call order.
+static inline void dmma884(double& d0, double& d1, double a, double b) { ::cpusim::dmma_defer(&d0, &d1, a, b); }
+}  // namespace candmc

@@ -6,6 +6,36 @@
 #include <sys/mman.h>
 #include <ucontext.h>
 
+// Fiber switch.  glibc's swapcontext saves the signal mask with a system call on every switch; a kernel emulation makes
+// millions of switches, so x86-64 gets the classic callee-saved-registers-and-stack-pointer switch instead.
+#if defined(__x86_64__)
+#define CPUSIM_FAST_SWITCH 1
+extern "C" void cpusim_ctx_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl cpusim_ctx_switch
+.type cpusim_ctx_switch,@function
+cpusim_ctx_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size cpusim_ctx_switch,.-cpusim_ctx_switch
+)");
+#endif
+
+#include <map>
 #include <vector>
 
 #include "sim_device.h"
@@ -18,38 +48,75 @@ namespace {
 constexpr size_t kStack = 256 * 1024;
 constexpr int kMaxThreads = 1024;
 
+constexpr int kDmmaBatch = 64;
+struct PendingDmma {
+  double *d0, *d1;
+};
 struct Fiber {
+#ifdef CPUSIM_FAST_SWITCH
+  void* sp = nullptr;
+#else
   ucontext_t ctx;
+#endif
   ThreadState st;
   bool started = false, done = false;
+  int npending = 0;                 // DMMAs logged since the last warp rendezvous
+  PendingDmma pending[kDmmaBatch];
 };
 
 struct Warp {
   int alive = 0, arrived = 0;
   unsigned gen = 0;
   alignas(16) unsigned char slot[2][32][16];
+  double dmma_ab[kDmmaBatch][32][2];   // operands (a, b) of every lane for each logged DMMA of the current batch
+};
+
+struct MBar {
+  uint32_t count = 0, pending = 0, phase = 0;
+  int64_t tx = 0;
+};
+struct NamedBar {
+  int arrived = 0;
+  unsigned gen = 0;
 };
 
 struct Block {
   int nthreads = 0, alive = 0, arrived = 0;
   unsigned gen = 0;
   std::vector<Warp> warps;
+  std::map<uint32_t, MBar> mbars;
+  NamedBar named[16];
 };
+uint64_t g_progress = 0;   // anything that lets a waiting fiber go on: a barrier opening, an mbarrier phase completing
 
 char* g_stacks = nullptr;
 Fiber g_fibers[kMaxThreads];
+#ifdef CPUSIM_FAST_SWITCH
+void* g_main_sp = nullptr;
+#else
 ucontext_t g_main;
+#endif
 int g_cur = -1;
 Block g_blk;
-std::vector<unsigned char> g_dyn;
+unsigned char* g_dyn = nullptr;   // dynamic shared memory of the running block, 1024-byte aligned like the hardware window
+size_t g_dyn_size = 0;
+constexpr uint32_t kSmemHandleBase = 4096;
 const std::function<void()>* g_body = nullptr;
 ThreadState g_host_state;
 
+#ifdef CPUSIM_FAST_SWITCH
+void fiber_yield() { cpusim_ctx_switch(&g_fibers[g_cur].sp, g_main_sp); }
+#else
 void fiber_yield() { swapcontext(&g_fibers[g_cur].ctx, &g_main); }
+#endif
 
 void fiber_entry() {
   (*g_body)();
   Fiber& f = g_fibers[g_cur];
+  if (f.npending != 0) {
+    fprintf(stderr, "cpusim: a thread exited with DMMAs that were never synchronised (no __syncwarp before the accumulators' use?)\n");
+    abort();
+  }
   f.done = true;
   // a thread that exits no longer takes part in barriers
   g_blk.alive--;
@@ -63,13 +130,14 @@ void fiber_entry() {
     w.arrived = 0;
     w.gen++;
   }
-  swapcontext(&f.ctx, &g_main);
+  fiber_yield();   // never resumed
+  abort();
 }
 
 }  // namespace
 
 ThreadState& ts() { return g_cur >= 0 ? g_fibers[g_cur].st : g_host_state; }
-void* dyn_smem() { return g_dyn.data(); }
+void* dyn_smem() { return g_dyn; }
 
 void sync_threads() {
   if (g_cur < 0) return;
@@ -98,6 +166,194 @@ void sync_warp_exchange(const void* in, void* out, int src_lane, size_t bytes) {
     while (w.gen == gen) fiber_yield();
   }
   memcpy(out, w.slot[gen & 1][src_lane], bytes);
+}
+
+// ---- emulated PTX of the GEMM kernel ------------------------------------------------------------------------------------
+uint32_t smem_handle(const void* p) {
+  const unsigned char* c = static_cast<const unsigned char*>(p);
+  if (c < g_dyn || c >= g_dyn + g_dyn_size) {
+    fprintf(stderr, "cpusim: shared-space address of a pointer outside the block's dynamic shared memory\n");
+    abort();
+  }
+  return kSmemHandleBase + (uint32_t)(c - g_dyn);
+}
+void* smem_ptr(uint32_t handle) {
+  if (handle < kSmemHandleBase || handle - kSmemHandleBase + 8 > g_dyn_size) {
+    fprintf(stderr, "cpusim: shared-memory access outside the block's window (handle %u)\n", handle);
+    abort();
+  }
+  return g_dyn + (handle - kSmemHandleBase);
+}
+
+static void mbar_check(MBar& b) {
+  if (b.pending == 0 && b.tx == 0) {
+    b.phase ^= 1;
+    b.pending = b.count;
+    ++g_progress;
+  }
+}
+static MBar& mbar_get(uint32_t bar) {
+  auto it = g_blk.mbars.find(bar);
+  if (it == g_blk.mbars.end()) {
+    fprintf(stderr, "cpusim: mbarrier %u used before mbarrier.init\n", bar);
+    abort();
+  }
+  return it->second;
+}
+void mbar_init(uint32_t bar, uint32_t count) {
+  MBar b;
+  b.count = b.pending = count;
+  g_blk.mbars[bar] = b;
+}
+void mbar_arrive(uint32_t bar) {
+  MBar& b = mbar_get(bar);
+  if (b.pending == 0) {
+    fprintf(stderr, "cpusim: more arrivals than the mbarrier expects in one phase\n");
+    abort();
+  }
+  --b.pending;
+  mbar_check(b);
+}
+void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  MBar& b = mbar_get(bar);
+  b.tx += bytes;
+  if (b.pending == 0) {
+    fprintf(stderr, "cpusim: more arrivals than the mbarrier expects in one phase\n");
+    abort();
+  }
+  --b.pending;
+  mbar_check(b);
+}
+bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_get(bar).phase != (parity & 1u)) return true;
+  if (g_cur >= 0) fiber_yield();
+  return mbar_get(bar).phase != (parity & 1u);
+}
+
+void tma_load_2d(uint32_t dst, const void* tensor_map, uint32_t bar, int c0, int c1) {
+  SimTensorMap m;
+  memcpy(&m, tensor_map, sizeof(m));
+  if (m.magic != kTensorMapMagic) {
+    fprintf(stderr, "cpusim: TMA load through something that is not an encoded tensor map\n");
+    abort();
+  }
+  if (m.swizzle128 && dst % 1024 != 0 && (dst % 128 != 0)) {
+    fprintf(stderr, "cpusim: TMA destination %u not 128-byte aligned\n", dst);
+    abort();
+  }
+  for (uint32_t i1 = 0; i1 < m.box[1]; ++i1)
+    for (uint32_t i0 = 0; i0 < m.box[0]; ++i0) {
+      const int64_t g0 = (int64_t)c0 + i0, g1 = (int64_t)c1 + i1;
+      double v = 0.0;  // out-of-range elements are zero-filled
+      if (g0 >= 0 && g1 >= 0 && (uint64_t)g0 < m.dim[0] && (uint64_t)g1 < m.dim[1])
+        memcpy(&v, m.base + g0 * 8 + g1 * (int64_t)m.stride1, 8);
+      uint32_t addr = dst + (i1 * m.box[0] + i0) * 8;
+      if (m.swizzle128) addr ^= ((addr >> 7) & 7u) << 4;   // 16-byte chunk index XOR 128-byte line index, on the shared address
+      memcpy(smem_ptr(addr), &v, 8);
+    }
+  MBar& b = mbar_get(bar);
+  b.tx -= (int64_t)m.box[0] * m.box[1] * 8;
+  mbar_check(b);
+}
+
+void warp_allgather16(const void* in16, void* out32x16) {
+  Warp& w = g_blk.warps[g_cur / 32];
+  const int lane = g_cur % 32;
+  const unsigned gen = w.gen;
+  if (w.alive != 32) {   // nobody can have left: every lane still has this operation in front of it
+    fprintf(stderr, "cpusim: warp-collective operation with exited lanes\n");
+    abort();
+  }
+  memcpy(w.slot[gen & 1][lane], in16, 16);
+  if (++w.arrived == w.alive) {
+    w.arrived = 0;
+    w.gen++;
+    ++g_progress;
+  } else {
+    while (w.gen == gen) fiber_yield();
+  }
+  memcpy(out32x16, w.slot[gen & 1], 32 * 16);
+}
+
+void dmma_flush() {
+  Fiber& f = g_fibers[g_cur];
+  if (f.npending == 0) return;
+  Warp& w = g_blk.warps[g_cur / 32];
+  if (w.alive != 32) {
+    fprintf(stderr, "cpusim: warp-collective operation with exited lanes\n");
+    abort();
+  }
+  const int lane = g_cur % 32, n = f.npending;
+  // rendezvous: everybody's operands of this batch are in w.dmma_ab once all 32 lanes are here (same count on every lane —
+  // mma.sync is warp-uniform by definition, a mismatch is a bug in the kernel)
+  unsigned gen = w.gen;
+  int cnt = n;
+  memcpy(w.slot[gen & 1][lane], &cnt, sizeof(cnt));
+  if (++w.arrived == w.alive) {
+    w.arrived = 0;
+    w.gen++;
+    ++g_progress;
+  } else {
+    while (w.gen == gen) fiber_yield();
+  }
+  for (int l = 0; l < 32; ++l) {
+    int other;
+    memcpy(&other, w.slot[gen & 1][l], sizeof(other));
+    if (other != n) {
+      fprintf(stderr, "cpusim: lanes of a warp issued different numbers of DMMAs (%d vs %d)\n", n, other);
+      abort();
+    }
+  }
+  const int row = lane >> 2, col = 2 * (lane & 3);
+  for (int i = 0; i < n; ++i) {
+    double d0 = *f.pending[i].d0, d1 = *f.pending[i].d1;
+    for (int k = 0; k < 4; ++k) {
+      const double a = w.dmma_ab[i][row * 4 + k][0];
+      d0 = __builtin_fma(a, w.dmma_ab[i][col * 4 + k][1], d0);
+      d1 = __builtin_fma(a, w.dmma_ab[i][(col + 1) * 4 + k][1], d1);
+    }
+    *f.pending[i].d0 = d0;
+    *f.pending[i].d1 = d1;
+  }
+  f.npending = 0;
+  // second rendezvous: nobody may log into dmma_ab for the next batch before everybody has applied this one
+  gen = w.gen;
+  if (++w.arrived == w.alive) {
+    w.arrived = 0;
+    w.gen++;
+    ++g_progress;
+  } else {
+    while (w.gen == gen) fiber_yield();
+  }
+}
+
+void dmma_defer(double* d0, double* d1, double a, double b) {
+  Fiber& f = g_fibers[g_cur];
+  for (int i = 0; i < f.npending; ++i)
+    if (f.pending[i].d0 == d0 || f.pending[i].d1 == d1 || f.pending[i].d0 == d1 || f.pending[i].d1 == d0) {
+      dmma_flush();   // this accumulator still has a logged DMMA in front of it
+      break;
+    }
+  if (f.npending == kDmmaBatch) dmma_flush();
+  Warp& w = g_blk.warps[g_cur / 32];
+  const int lane = g_cur % 32;
+  w.dmma_ab[f.npending][lane][0] = a;
+  w.dmma_ab[f.npending][lane][1] = b;
+  f.pending[f.npending].d0 = d0;
+  f.pending[f.npending].d1 = d1;
+  ++f.npending;
+}
+
+void named_barrier(int id, int count) {
+  NamedBar& nb = g_blk.named[id & 15];
+  const unsigned gen = nb.gen;
+  if (++nb.arrived == count) {
+    nb.arrived = 0;
+    nb.gen++;
+    ++g_progress;
+    return;
+  }
+  while (nb.gen == gen) fiber_yield();
 }
 
 static void execute(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
@@ -135,7 +391,12 @@ static void execute(dim3 grid, dim3 block, size_t smem, const std::function<void
     }
   }
   g_body = &body;
-  g_dyn.assign(smem + 16, 0xCD);  // dynamic shared memory is NOT zeroed on a GPU either
+  if (smem + 16 > g_dyn_size) {
+    free(g_dyn);
+    g_dyn_size = smem + 16;
+    if (posix_memalign(reinterpret_cast<void**>(&g_dyn), 1024, g_dyn_size) != 0) abort();
+  }
+  memset(g_dyn, 0xCD, g_dyn_size);  // dynamic shared memory is NOT zeroed on a GPU either
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -143,9 +404,12 @@ static void execute(dim3 grid, dim3 block, size_t smem, const std::function<void
         g_blk.arrived = 0;
         g_blk.gen = 0;
         g_blk.warps.assign((nthreads + 31) / 32, Warp());
+        g_blk.mbars.clear();
+        for (NamedBar& nb : g_blk.named) nb = NamedBar();
         for (int t = 0; t < nthreads; ++t) {
           Fiber& f = g_fibers[t];
           f.started = f.done = false;
+          f.npending = 0;
           f.st.thread.x = t % block.x;
           f.st.thread.y = (t / block.x) % block.y;
           f.st.thread.z = t / (block.x * block.y);
@@ -164,20 +428,36 @@ static void execute(dim3 grid, dim3 block, size_t smem, const std::function<void
         long idle_rounds = 0;
         while (remaining > 0) {
           int progressed = 0;
+          const uint64_t progress_before = g_progress;
           for (int t = 0; t < nthreads; ++t) {
             Fiber& f = g_fibers[t];
             if (f.done) continue;
             if (!f.started) {
+#ifdef CPUSIM_FAST_SWITCH
+              // stack as cpusim_ctx_switch expects it: six callee-saved registers, then the address `ret` jumps to; the
+              // entry function then sees the alignment of a normal call (rsp = 16n + 8)
+              uintptr_t top = (reinterpret_cast<uintptr_t>(g_stacks + kStack * (t + 1))) & ~(uintptr_t)15;
+              void** sp = reinterpret_cast<void**>(top);
+              *--sp = nullptr;                                    // fake return address of the entry function
+              *--sp = reinterpret_cast<void*>(&fiber_entry);      // ret target
+              for (int r = 0; r < 6; ++r) *--sp = nullptr;        // rbp rbx r12 r13 r14 r15
+              f.sp = sp;
+#else
               getcontext(&f.ctx);
               f.ctx.uc_stack.ss_sp = g_stacks + kStack * t;
               f.ctx.uc_stack.ss_size = kStack;
               f.ctx.uc_link = nullptr;
               makecontext(&f.ctx, fiber_entry, 0);
+#endif
               f.started = true;
             }
             const unsigned bgen = g_blk.gen, wgen = g_blk.warps[t / 32].gen;
             g_cur = t;
+#ifdef CPUSIM_FAST_SWITCH
+            cpusim_ctx_switch(&g_main_sp, f.sp);
+#else
             swapcontext(&g_main, &f.ctx);
+#endif
             g_cur = -1;
             if (f.done) {
               --remaining;
@@ -187,6 +467,7 @@ static void execute(dim3 grid, dim3 block, size_t smem, const std::function<void
             }
           }
           // a full round in which nobody finished and no barrier opened twice in a row = divergent barrier (deadlock)
+          if (g_progress != progress_before) ++progressed;
           idle_rounds = progressed ? 0 : idle_rounds + 1;
           if (idle_rounds > 2) {
             fprintf(stderr, "cpusim: block (%u,%u,%u) deadlocked at a barrier (%d threads waiting, %d alive)\n", bx, by, bz,

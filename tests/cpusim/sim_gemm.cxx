@@ -1,14 +1,15 @@
-// tests/cpusim — stand-ins for the two translation units of the product that cannot be simulated (TEST INFRASTRUCTURE
-// ONLY, see sim_device.h):
-//   gemm_f64.cu  (TMA + DMMA kernel, inline PTX)  ->  the same host entry points, same argument checks, plain loops;
-//   ipc.cu       (CUDA IPC peer windows + the fused depth all-reduce)  ->  "not available", which is the product's own
-//                documented condition for falling back to ncclAllReduce.
+// tests/cpusim — the GEMM entry points of the simulator build (TEST INFRASTRUCTURE ONLY, see sim_device.h): same argument
+// checks as gemm_f64.cu, then either plain loops (default: fast, what the schedule tests need) or the product's own kernel
+// on the PTX emulation (CPUSIM_GEMM=device, and always for the fused GEMM + depth all-reduce).
 // Operand ranges are checked against the simulator's allocation registry, so a wrong pointer / leading dimension / extent
 // handed to the GEMM by a host schedule aborts with a message instead of silently reading a neighbour.
 #include "common.cuh"
 #include "ipc.h"
 #include "runtime.h"
 #include "sim_internal.h"
+
+#include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -17,7 +18,18 @@ extern "C" void cpusim_require_device_range(const void* p, size_t bytes, const c
 
 namespace candmc {
 
+// the product's own gemm_f64.cu, compiled into the simulator with its entry points renamed (Makefile): TMA, mbarriers, the
+// swizzled fragment loads and the DMMA atoms run on the PTX emulation of sim_exec.cxx.  Slow (every DMMA is a warp-wide fiber
+// rendezvous), so it serves the tests that are about the kernel itself: CPUSIM_GEMM=device.
+int gemm_f64_fused_device(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, cudaStream_t stream,
+                          const FusedParams* fused);
+
 namespace {
+bool use_device_kernel() {
+  static const bool on = getenv("CPUSIM_GEMM") && !strcmp(getenv("CPUSIM_GEMM"), "device");
+  return on;
+}
 bool is_trans(char c) { return c == 'T' || c == 't' || c == 'C' || c == 'c'; }
 bool is_notrans(char c) { return c == 'N' || c == 'n'; }
 size_t span(int64_t rows, int64_t cols, int64_t ld) { return rows && cols ? sizeof(double) * ((cols - 1) * ld + rows) : 0; }
@@ -32,7 +44,8 @@ int gemm_f64_fused(char transa, char transb, int64_t m, int64_t n, int64_t k, do
                    const double* B, int64_t ldb, double beta, double* C, int64_t ldc, cudaStream_t stream,
                    const FusedParams* fused) {
   CANDMC_TRY(runtime_require());
-  CANDMC_CHECK(fused == nullptr, "cpusim: the fused GEMM + depth all-reduce cannot be simulated");
+  // the fused GEMM + depth all-reduce only exists as the kernel's epilogue over peer memory: always the emulated kernel
+  if (fused != nullptr) return gemm_f64_fused_device(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, stream, fused);
   CANDMC_CHECK(is_trans(transa) || is_notrans(transa), "dgemm: bad transa '%c'", transa);
   CANDMC_CHECK(is_trans(transb) || is_notrans(transb), "dgemm: bad transb '%c'", transb);
   const bool tA = is_trans(transa), tB = is_trans(transb);
@@ -48,6 +61,7 @@ int gemm_f64_fused(char transa, char transb, int64_t m, int64_t n, int64_t k, do
     cpusim_require_device_range(A, span(rowsA, colsA, lda), "dgemm A");
     cpusim_require_device_range(B, span(rowsB, colsB, ldb), "dgemm B");
   }
+  if (use_device_kernel()) return gemm_f64_fused_device(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, stream, nullptr);
   if ((k == 0 || alpha == 0.0) && beta == 1.0) return OK;
   cpusim::stream_submit(stream, [=]() {
   // op(A) packed m x k, then column-by-column axpy (vectorisable inner loop); summation order over k is 0..k-1
@@ -76,23 +90,6 @@ int gemm_f64_fused(char transa, char transb, int64_t m, int64_t n, int64_t k, do
   });
   runtime().launches++;
   return OK;
-}
-
-// ---- ipc.cu ------------------------------------------------------------------------------------------------------------
-int window_create(candmc_comm*, size_t, PeerWindow** out) {
-  *out = nullptr;
-  set_last_error("cpusim: CUDA IPC is not simulated");
-  return ERR_CUDA;
-}
-void window_destroy(PeerWindow*) {}
-int fused_ctx_get(candmc_comm*, int64_t, FusedCtx** out) {
-  *out = nullptr;  // "the fused path cannot be used (the caller then uses ncclAllReduce)", ipc.h
-  return OK;
-}
-void fused_params_next(FusedCtx*, int, FusedParams*) {}
-int fused_finish(FusedCtx*, int, const FusedParams&, double*, int64_t, cudaStream_t) {
-  set_last_error("cpusim: fused_finish without a fused context");
-  return ERR_INVALID;
 }
 
 }  // namespace candmc

@@ -1,6 +1,7 @@
 // tests/cpusim — interfaces between the simulator's translation units (TEST INFRASTRUCTURE ONLY, see sim_device.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 #include <functional>
 #include <vector>
@@ -25,5 +26,16 @@ bool nccl_done(const NcclBatch* b);
 void nccl_finish(NcclBatch* b);    // reductions + release
 void nccl_describe(const NcclBatch* b);
 void run_batch_blocking(NcclBatch* b);   // host-side setup exchanges (communicator creation)
+
+// what the simulator's cuTensorMapEncodeTiled writes into the opaque 128-byte CUtensorMap (2-D, FP64 only)
+struct SimTensorMap {
+  uint64_t magic;
+  const char* base;
+  uint64_t dim[2];       // elements; dim[0] is contiguous
+  uint64_t stride1;      // bytes between consecutive dim-1 indices
+  uint32_t box[2];
+  uint32_t swizzle128;
+};
+constexpr uint64_t kTensorMapMagic = 0x53494d544d415031ull;
 
 }  // namespace cpusim

@@ -44,7 +44,24 @@ _LAUNCH = re.compile(r"([A-Za-z_][\w:]*(?:<[^<>;(){}]*>)?)\s*<<<")
 _EXTERN_SHARED = re.compile(r"extern\s+__shared__\s+([\w:]+)\s+(\w+)\s*\[\s*\]\s*;")
 
 
+# the few inline-asm statements outside common.cuh's helpers (gemm_f64.cu): rewritten to their meaning
+_ASM_RULES = [
+    (re.compile(r'asm volatile\("setmaxnreg\.(?:dec|inc)\.sync\.aligned\.u32 %0;"\s*::\s*"n"\(\w+\)\);'), "/* setmaxnreg: registers are not modelled */"),
+    (re.compile(r'asm volatile\("bar\.sync (\d+), (\d+);"\s*:::\s*"memory"\);'), r"::cpusim::named_barrier(\1, \2);"),
+    (re.compile(r'asm volatile\("ld\.acquire\.sys\.global\.u32 %0, \[%1\];"\s*:\s*"=r"\((\w+)\)\s*:\s*"l"\(([^)]+)\)\s*:\s*"memory"\);'),
+     r"\1 = __atomic_load_n(reinterpret_cast<const uint32_t*>(\2), __ATOMIC_ACQUIRE);"),
+    (re.compile(r'asm volatile\("st\.release\.sys\.global\.u32 \[%0\], %1;"\s*::\s*"l"\((.+?)\),\s*"r"\(([^)]+)\)\s*:\s*"memory"\);'),
+     r"__atomic_store_n(reinterpret_cast<uint32_t*>(\1), (uint32_t)(\2), __ATOMIC_RELEASE);"),
+    (re.compile(r'asm volatile\("red\.release\.sys\.global\.add\.u32 \[%0\], 1;"\s*::\s*"l"\(([^)]+)\)\s*:\s*"memory"\);'),
+     r"__atomic_fetch_add(reinterpret_cast<uint32_t*>(\1), 1u, __ATOMIC_RELEASE);"),
+]
+
+
 def translate(text):
+    for rx, rep in _ASM_RULES:
+        text = rx.sub(rep, text)
+    if "asm volatile" in text or "asm(" in text:
+        raise ValueError("inline asm the simulator has no rule for")
     text = _EXTERN_SHARED.sub(lambda m: f"{m.group(1)}* {m.group(2)} = ({m.group(1)}*)::cpusim::dyn_smem();", text)
     out, pos = "", 0
     while True:

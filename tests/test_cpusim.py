@@ -45,14 +45,20 @@ def _torchrun(nproc, port, script, *args):
             "--master-port", str(port), script, *args]
 
 
-DIST_MAIN = [1, 2, 4, 8] if FULL else [4, 8]
+DIST_MAIN = [1, 2, 4, 8] if FULL else [2, 4, 8]
 DIST_PENDING = [1, 2, 4, 6, 8, 9, 16] if FULL else [1, 4, 9]
 GOLD = np.load(os.path.join(HERE, "golden", "lu_offload_ref_outputs.npz"))
 SCRIPTS = sorted(k[: -len("__script")] for k in GOLD.files if k.endswith("__script"))
 REDIST = [(24, 36, 2, 2, 3, 0, 0), (36, 24, 3, 3, 2, 1, 1), (30, 30, 5, 3, 3, 0, 2), (16, 16, 4, 1, 4, 0, 3), (512, 256, 32, 2, 2, 1, 0)]
 
-for _n in DIST_MAIN:     # longest first
-    _job(f"main{_n}", _torchrun(_n, 29700 + _n, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0")
+for _n in DIST_MAIN:     # longest first.  On 8 ranks the fused GEMM + depth all-reduce is switched on for the 2x2x2 grid too (opt-in in
+    # the product until a B200 has seen it): the kernel's peer-memory epilogue and ipc.cu run for real, over simulated CUDA IPC
+    _job(f"main{_n}", _torchrun(_n, 29700 + _n, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0",
+         CANDMC_TEST_FUSED_GRIDS="1" if _n == 8 else "0")
+# the hot kernel itself on the PTX emulation, and the 4-rank suite with every GEMM going through it
+_job("kernel", [sys.executable, os.path.join(SIM, "probe_gemm.py")])
+if FULL:
+    _job("main4_device_gemm", _torchrun(4, 29719, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CPUSIM_GEMM="device")
 for _n in DIST_PENDING:
     _job(f"pending{_n}", _torchrun(_n, 29720 + _n, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="1")
 for _m in ("mismatch", "stuck"):
@@ -252,6 +258,20 @@ def test_bench_script_logic_on_the_simulator(nproc):
     b = d["config"]["block"]
     assert d["e2e"]["d2h_bytes_per_step"] == nproc * b * b * 8
     assert d["e2e"]["h2d_bytes_per_step"] == (2 if nproc == 1 else 8) * b * b * 8
+
+
+def test_hot_gemm_kernel_on_the_ptx_emulation():
+    """candmc_b200/csrc/gemm_f64.cu itself — TMA boxes with the 128-byte swizzle and zero fill, the mbarrier ring, the
+    permuted fragment loads, DMMA.8x8x4, split-K, the dynamic and the static tile scheduler, both epilogues — against numpy"""
+    rc, so, se = RESULTS["kernel"]
+    assert rc == 0, so[-2000:] + se[-3000:]
+    r = json.loads(so.strip().splitlines()[-1])
+    assert r["cases"] >= 25 and r["max_rel_err"] <= 1e-13
+
+
+@pytest.mark.skipif(not FULL, reason="CANDMC_CPUSIM_FULL=1")
+def test_distributed_suite_with_every_gemm_on_the_emulated_kernel():
+    _dist("main4_device_gemm")
 
 
 def test_adversarial_scheduler_exposes_a_missing_event():

@@ -172,6 +172,8 @@ def main():
                     help="e2e leg: upload both host blocks on every rank even when a layer's panels never use them")
     ap.add_argument("--late-c-download", action="store_true",
                     help="e2e leg: one download of C after the last multiply instead of slab-wise under the last multiplies")
+    ap.add_argument("--panel-transport", action="store_true",
+                    help="SUMMA panels by copy engines into peer windows instead of ncclBroadcast (experimental)")
     ap.add_argument("--b-first-chunk-early", action="store_true",
                     help="e2e leg on grids: upload the first k-chunk of B ahead of the rest (experimental)")
     ap.add_argument("--host-panels", type=int, default=None,
@@ -206,6 +208,8 @@ def main():
         cb.lib().candmc_set_early_c_download(0)
     if args.b_first_chunk_early:
         cb.lib().candmc_set_b_first_chunk_early(1)
+    if args.panel_transport:
+        cb.lib().candmc_set_panel_transport(1)
     if args.host_panels is not None:
         cb.lib().candmc_set_host_pipeline_panels(args.host_panels)
     world = cb.init_world(rank, world_size, local)
@@ -360,7 +364,7 @@ def main():
         }
         knobs = {k: v for k, v in (("bg_ctas", args.bg_ctas), ("fused_reduce", args.fused_reduce),
                                    ("upload_all_blocks", args.upload_all_blocks or None),
-                                   ("late_c_download", args.late_c_download or None), ("b_first_chunk_early", args.b_first_chunk_early or None), ("host_panels", args.host_panels)) if v is not None}
+                                   ("late_c_download", args.late_c_download or None), ("b_first_chunk_early", args.b_first_chunk_early or None), ("panel_transport", args.panel_transport or None), ("host_panels", args.host_panels)) if v is not None}
         if knobs:
             line["config"]["knobs"] = knobs  # non-default tuning switches used for this run
         if world_size == 1 and not args.no_cpu_baseline:

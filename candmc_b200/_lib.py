@@ -52,6 +52,8 @@ SIGNATURES = {
     "candmc_set_fused_reduce": (C.c_int, [C.c_int]),
     "candmc_set_skip_unused_uploads": (C.c_int, [C.c_int]),
     "candmc_set_early_c_download": (C.c_int, [C.c_int]),
+    "candmc_set_panel_transport": (C.c_int, [C.c_int]),
+    "candmc_panel_transport_sends": (C.c_ulonglong, []),
     "candmc_set_b_first_chunk_early": (C.c_int, [C.c_int]),
     "candmc_profile_enable": (C.c_int, [C.c_int]),
     "candmc_profile_gemm_timeline": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), i64, C.POINTER(i64)]),

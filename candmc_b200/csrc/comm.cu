@@ -9,6 +9,7 @@
 
 #include "../../include/candmc_b200.h"
 #include "ipc.h"
+#include "transport.h"
 #include "runtime.h"
 #include "staging.h"
 
@@ -157,6 +158,10 @@ int candmc_comm_free(candmc_comm_t* comm) {
     cudaDeviceSynchronize();
     candmc::window_destroy(f->win);
     delete f;
+  }
+  if (comm->transport) {
+    cudaDeviceSynchronize();
+    candmc::panel_transport_destroy(static_cast<candmc::PanelTransport*>(comm->transport));
   }
   if (comm->nccl_bg && comm->nccl_bg != comm->nccl) ncclCommDestroy(comm->nccl_bg);
   if (comm->nccl) ncclCommDestroy(comm->nccl);

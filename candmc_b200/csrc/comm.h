@@ -15,6 +15,8 @@ struct candmc_comm {
   int size = 1;
   void* fused_ctx = nullptr;      // candmc::FusedCtx* of the fused GEMM + depth all-reduce (ipc.h), owned by this handle
   bool fused_failed = false;      // CUDA IPC unavailable: stay on ncclAllReduce
+  void* transport = nullptr;      // candmc::PanelTransport* (transport.h): copy-engine panel transport over peer windows
+  bool transport_failed = false;  // peer windows / stream memory operations unavailable: stay on ncclBroadcast
 };
 
 namespace candmc {

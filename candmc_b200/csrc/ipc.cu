@@ -25,6 +25,7 @@ int window_create(candmc_comm* c, size_t bytes, PeerWindow** out) {
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
   if (ok) ok = (cudaIpcGetMemHandle(&mine, local) == cudaSuccess);
+  if (!ok) cudaGetLastError();   // a failed export must not surface as the "last error" of the next kernel launch
   // all-gather {ok flag, handle} through NCCL (device staging), then open the peers' handles
   struct Rec {
     int ok;

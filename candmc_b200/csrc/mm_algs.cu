@@ -23,6 +23,7 @@
 #include "ipc.h"
 #include "runtime.h"
 #include "staging.h"
+#include "transport.h"
 
 namespace candmc {
 
@@ -187,12 +188,21 @@ int summa_sweep(SummaArgs& a) {
     return OK;
   };
 
+  // opt-in: panels by copy engines into peer windows (transport.h) instead of ncclBroadcast, per grid axis
+  PanelTransport *tr_row = nullptr, *tr_col = nullptr;
+  if (runtime().panel_transport && need_comm && (a.i1 - a.i0) * nchunks <= kPanelMaxOps) {
+    if (a.row->size > 1) CANDMC_TRY(panel_transport_get(a.row, (a.i1 - a.i0) * bb, &tr_row));
+    if (a.col->size > 1) CANDMC_TRY(panel_transport_get(a.col, (a.i1 - a.i0) * bb, &tr_col));
+    if (tr_row) panel_transport_begin(tr_row);
+    if (tr_col) panel_transport_begin(tr_col);
+  }
+  const bool all_dma = (a.row->size == 1 || tr_row) && (a.col->size == 1 || tr_col);   // no NCCL kernel in this sweep
   if (need_comm) CANDMC_TRY(stream_wait(comm, a.compute));  // inputs (and earlier users of ws) are ready
   // NCCL moves data with SM-resident kernels, and the persistent GEMM owns every SM it is given (all registers, 193 KiB
   // smem), so a broadcast enqueued while a GEMM runs would only start when that GEMM ends.  While panels are in flight
   // the GEMMs therefore leave as many SMs free as the background communicators may use.
-  ReserveGuard reserve_guard(need_comm ? std::max(runtime().bg_max_ctas, runtime().gemm_reserve_sms)
-                                       : runtime().gemm_reserve_sms);
+  ReserveGuard reserve_guard((need_comm && !all_dma) ? std::max(runtime().bg_max_ctas, runtime().gemm_reserve_sms)
+                                                     : runtime().gemm_reserve_sms);
   std::vector<cudaEvent_t> done_prev(nchunks, nullptr);
   bool first = a.first_beta_zero;
   for (int i = a.i0; i < a.i1; ++i) {
@@ -203,6 +213,7 @@ int summa_sweep(SummaArgs& a) {
       for (int t = 0; t < nchunks; ++t) {
         const bool bg = !(i == a.i0 && t == 0);  // the very first chunk has nothing to hide under: full-width communicator
         if (done_prev[t]) CANDMC_CUDA(cudaStreamWaitEvent(comm, done_prev[t], 0));  // buf slot t is free again
+        const int op = (i - a.i0) * nchunks + t;   // transport slot of this (panel, chunk): its own, never reused in a sweep
         if (a.row->size > 1) {
           double* slot = bufA + t * kc * b;
           if (rootA) {
@@ -212,8 +223,9 @@ int summa_sweep(SummaArgs& a) {
               CANDMC_TRY(lda_copy_f64(b, kc, a.ldA, b, src, packA + t * kc * b, comm));
               src = packA + t * kc * b;
             }
-            CANDMC_TRY(comm_bcast(a.row, src, const_cast<double*>(src), kc * b, i, comm, bg));
-          } else {
+            if (tr_row) CANDMC_TRY(panel_transport_send(tr_row, a.row, op, op * kc * b, src, kc * b, comm));
+            else CANDMC_TRY(comm_bcast(a.row, src, const_cast<double*>(src), kc * b, i, comm, bg));
+          } else if (!tr_row) {
             CANDMC_TRY(comm_bcast(a.row, slot, slot, kc * b, i, comm, bg));
           }
         }
@@ -226,8 +238,9 @@ int summa_sweep(SummaArgs& a) {
               CANDMC_TRY(lda_copy_f64(kc, b, a.ldB, kc, src, locB + t * kc * b, comm));  // chunk-major, ld = kc
               src = locB + t * kc * b;
             }
-            CANDMC_TRY(comm_bcast(a.col, src, const_cast<double*>(src), kc * b, i, comm, bg));
-          } else {
+            if (tr_col) CANDMC_TRY(panel_transport_send(tr_col, a.col, op, op * kc * b, src, kc * b, comm));
+            else CANDMC_TRY(comm_bcast(a.col, src, const_cast<double*>(src), kc * b, i, comm, bg));
+          } else if (!tr_col) {
             CANDMC_TRY(comm_bcast(a.col, slot, slot, kc * b, i, comm, bg));
           }
         }
@@ -243,6 +256,10 @@ int summa_sweep(SummaArgs& a) {
         CANDMC_TRY(wait_ready(a.compute, a.a_ready, t));
         *pa = a.myA + t * kc * a.ldA;
         *lda = a.ldA;
+      } else if (tr_row) {
+        const int op = (i - a.i0) * nchunks + t;
+        CANDMC_TRY(panel_transport_wait(tr_row, a.row, op, op * kc * b, a.compute, pa));
+        *lda = b;
       } else {
         *pa = bufA + t * kc * b;
         *lda = b;
@@ -251,6 +268,10 @@ int summa_sweep(SummaArgs& a) {
         CANDMC_TRY(wait_ready(a.compute, a.b_ready, t));
         *pb = a.b_chunk_major ? a.myB + t * kc * b : a.myB + t * kc;
         *ldb = a.b_chunk_major ? kc : a.ldB;
+      } else if (tr_col) {
+        const int op = (i - a.i0) * nchunks + t;
+        CANDMC_TRY(panel_transport_wait(tr_col, a.col, op, op * kc * b, a.compute, pb));
+        *ldb = kc;  // chunk-major, as the root packed it
       } else {
         *pb = bufB + t * kc * b;
         *ldb = kc;  // chunk-major
@@ -301,6 +322,9 @@ int summa_sweep(SummaArgs& a) {
       }
     }
   }
+  // every multiply of the sweep is enqueued: the peers may reuse the window halves this call read from
+  if (tr_row) CANDMC_TRY(panel_transport_end(tr_row, a.row, a.compute, comm));
+  if (tr_col) CANDMC_TRY(panel_transport_end(tr_col, a.col, a.compute, comm));
   return OK;
 }
 
@@ -436,6 +460,13 @@ int trsm_llnn(int64_t b, int64_t kb, const double* T, int64_t ldt, double* W, in
 using namespace candmc;
 
 extern "C" {
+
+int candmc_set_panel_transport(int on) {
+  runtime().panel_transport = (on != 0);
+  return OK;
+}
+
+unsigned long long candmc_panel_transport_sends(void) { return runtime().transport_sends; }
 
 int candmc_set_host_pipeline_panels(int panels) {
   CANDMC_CHECK(panels >= 0 && panels <= 64, "candmc_set_host_pipeline_panels: 0 (automatic) .. 64");

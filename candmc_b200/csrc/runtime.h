@@ -13,6 +13,7 @@ struct Runtime {
   int num_sms = 0;
   int cc_major = 0, cc_minor = 0;
   bool force_generic = false;        // test hook: route dgemm through the CUDA-core kernel
+  unsigned long long transport_sends = 0;   // panel chunks shipped by copy engines (transport.h)
   unsigned long long launches = 0;   // kernels launched by this library (bench.py's gpu_launches)
   cudaStream_t comm_stream = nullptr;   // NCCL panel traffic
   cudaStream_t aux_stream = nullptr;    // second compute/copy stream
@@ -25,6 +26,7 @@ struct Runtime {
   unsigned tile_counter_seq = 0;
   bool fused_reduce_grids = false;      // ... also on q x q x c grids (validated so far on 1 x 1 x c only)
   bool skip_unused_uploads = true;      // host operands: a layer's rank uploads only the blocks its panels use (candmc_set_skip_unused_uploads)
+  bool panel_transport = false;         // SUMMA panels by copy engines into peer windows instead of ncclBroadcast (transport.h; opt-in)
   bool b_first_chunk_early = false;     // host B: upload the first k-chunk's rows ahead of the rest (opt-in until measured)
   bool early_c_download = true;         // host C: finalise + download column slabs under the last multiplies (candmc_set_early_c_download)
   bool fused_reduce = true;             // depth all-reduce fused into the last GEMM's epilogue over peer memory

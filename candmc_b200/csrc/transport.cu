@@ -1,0 +1,153 @@
+// candmc_b200 — SUMMA panel transport over peer memory with copy engines only (see transport.h).
+#include "transport.h"
+
+#include <cuda.h>
+
+#include "../../include/candmc_b200.h"
+#include "runtime.h"
+
+namespace candmc {
+
+namespace {
+
+typedef CUresult (*PFN_waitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+PFN_waitValue32 g_wait32 = nullptr;
+bool g_wait32_tried = false;
+uint32_t* g_vals = nullptr;   // device array vals[i] = i: the 4-byte sources of the flag DMAs
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__global__ void iota_u32_kernel(uint32_t* v, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = i;
+}
+
+int ensure_globals() {
+  if (!g_wait32_tried) {
+    g_wait32_tried = true;
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess && fn != nullptr &&
+        q == cudaDriverEntryPointSuccess)
+      g_wait32 = reinterpret_cast<PFN_waitValue32>(fn);
+    else
+      cudaGetLastError();
+  }
+  if (g_wait32 == nullptr) return ERR_CUDA;
+  if (g_vals == nullptr) {
+    CANDMC_CUDA(cudaMalloc(&g_vals, sizeof(uint32_t) * kPanelMaxCalls));
+    iota_u32_kernel<<<runtime().num_sms * 4, 256, 0, runtime().aux_stream>>>(g_vals, kPanelMaxCalls);
+    CANDMC_CUDA(cudaGetLastError());
+    CANDMC_CUDA(cudaStreamSynchronize(runtime().aux_stream));
+    runtime().launches++;
+  }
+  return OK;
+}
+
+int stream_wait_geq(cudaStream_t st, const uint32_t* addr, uint32_t value) {
+  CUresult r = g_wait32(reinterpret_cast<CUstream>(st), reinterpret_cast<CUdeviceptr>(addr), value, CU_STREAM_WAIT_VALUE_GEQ);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuStreamWaitValue32 failed (CUresult %d)", (int)r);
+    return ERR_CUDA;
+  }
+  return OK;
+}
+
+}  // namespace
+
+int panel_transport_get(candmc_comm* c, int64_t half_elems, PanelTransport** out) {
+  *out = nullptr;
+  if (c == nullptr || c->size < 2 || c->size > kMaxPeers || c->transport_failed) return OK;
+  PanelTransport* t = static_cast<PanelTransport*>(c->transport);
+  if (t != nullptr && t->half_elems >= half_elems) {
+    *out = t;
+    return OK;
+  }
+  if (ensure_globals() != OK) {   // same outcome on every rank of a node (one driver)
+    c->transport_failed = true;
+    return OK;
+  }
+  if (t != nullptr) {   // grow: every rank gets here in the same call
+    CANDMC_CUDA(cudaDeviceSynchronize());
+    CANDMC_TRY(candmc_comm_barrier(c));   // nobody still copies into the old windows
+    panel_transport_destroy(t);
+    c->transport = nullptr;
+  }
+  t = new PanelTransport();
+  t->half_elems = half_elems;
+  t->off_ready = 0;
+  t->off_done = align_up(sizeof(uint32_t) * 2 * kPanelMaxOps, 256);
+  t->off_data = t->off_done + 256;
+  const size_t total = t->off_data + sizeof(double) * 2 * static_cast<size_t>(half_elems);
+  PeerWindow* w = nullptr;
+  if (window_create(c, total, &w) != OK) {   // zero-filled: every flag starts at 0 = "never"
+    delete t;
+    c->transport_failed = true;   // sticky: NCCL from now on
+    return OK;
+  }
+  t->win = w;
+  c->transport = t;
+  *out = t;
+  return OK;
+}
+
+void panel_transport_begin(PanelTransport* t) {
+  t->call += 1;
+  for (int p = 0; p < kMaxPeers; ++p) t->waited_done[p] = false;
+}
+
+int panel_transport_send(PanelTransport* t, candmc_comm* c, int op, int64_t slot_off, const double* src, int64_t count,
+                         cudaStream_t copy) {
+  CANDMC_CHECK(op >= 0 && op < kPanelMaxOps && slot_off >= 0 && slot_off + count <= t->half_elems, "panel transport: slot out of range");
+  CANDMC_CHECK(t->call < kPanelMaxCalls, "panel transport: call counter exhausted");
+  const int half = static_cast<int>(t->call & 1u);
+  char* mine = t->win->base[c->rank];
+  for (int p = 0; p < c->size; ++p) {
+    if (p == c->rank) continue;
+    if (!t->waited_done[p]) {
+      // peer p has finished the call that used this half before (call - 2); flags start at 0 and calls at 2, so the very
+      // first two calls pass immediately
+      if (t->call >= 4)
+        CANDMC_TRY(stream_wait_geq(copy, reinterpret_cast<const uint32_t*>(mine + t->off_done) + p, t->call - 2));
+      t->waited_done[p] = true;
+    }
+    char* pb = t->win->base[p];
+    double* dst = reinterpret_cast<double*>(pb + t->off_data) + static_cast<int64_t>(half) * t->half_elems + slot_off;
+    CANDMC_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * count, cudaMemcpyDeviceToDevice, copy));
+    uint32_t* flag = reinterpret_cast<uint32_t*>(pb + t->off_ready) + half * kPanelMaxOps + op;
+    CANDMC_CUDA(cudaMemcpyAsync(flag, g_vals + t->call, sizeof(uint32_t), cudaMemcpyDeviceToDevice, copy));
+    runtime().transport_sends++;
+  }
+  return OK;
+}
+
+int panel_transport_wait(PanelTransport* t, candmc_comm* c, int op, int64_t slot_off, cudaStream_t compute, const double** data) {
+  CANDMC_CHECK(op >= 0 && op < kPanelMaxOps, "panel transport: slot out of range");
+  const int half = static_cast<int>(t->call & 1u);
+  char* mine = t->win->base[c->rank];
+  // a ready flag of this half holds the number of the last call that filled the slot: call, or call - 2, - 4, ... before that
+  CANDMC_TRY(stream_wait_geq(compute, reinterpret_cast<const uint32_t*>(mine + t->off_ready) + half * kPanelMaxOps + op, t->call));
+  *data = reinterpret_cast<const double*>(mine + t->off_data) + static_cast<int64_t>(half) * t->half_elems + slot_off;
+  return OK;
+}
+
+int panel_transport_end(PanelTransport* t, candmc_comm* c, cudaStream_t compute, cudaStream_t copy) {
+  cudaEvent_t e;
+  CANDMC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CANDMC_CUDA(cudaEventRecord(e, compute));
+  CANDMC_CUDA(cudaStreamWaitEvent(copy, e, 0));
+  CANDMC_CUDA(cudaEventDestroy(e));   // released when the wait has consumed it
+  for (int p = 0; p < c->size; ++p) {
+    if (p == c->rank) continue;
+    uint32_t* flag = reinterpret_cast<uint32_t*>(t->win->base[p] + t->off_done) + c->rank;
+    CANDMC_CUDA(cudaMemcpyAsync(flag, g_vals + t->call, sizeof(uint32_t), cudaMemcpyDeviceToDevice, copy));
+  }
+  return OK;
+}
+
+void panel_transport_destroy(PanelTransport* t) {
+  if (!t) return;
+  window_destroy(t->win);
+  delete t;
+}
+
+}  // namespace candmc

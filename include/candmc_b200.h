@@ -58,6 +58,14 @@ int candmc_set_skip_unused_uploads(int on);
 /* Host C blocks in candmc_d25_summa: 1 (default) = the second half of the last panel's k-chunks is multiplied column slab by
  * column slab, each slab is summed over the depth and downloaded while the next ones multiply; 0 = one download at the end. */
 int candmc_set_early_c_download(int on);
+/* SUMMA panel chunks (candmc_summa, candmc_d25_summa, the inner level of candmc_bcast_cannon_4d): 1 = the root writes them
+ * into the consumers' CUDA-IPC-mapped windows with copy engines (cudaMemcpyAsync over NVLink + a 4-byte flag DMA, consumers
+ * wait with cuStreamWaitValue32) — no SM, no NCCL kernel, the GEMM keeps all 148 SMs; 0 (default until measured on B200s) =
+ * ncclBroadcast on the CTA-capped background communicators.  Must be the same on all ranks; falls back to NCCL by itself
+ * when peer windows or stream memory operations are unavailable. */
+int candmc_set_panel_transport(int on);
+/* Panel chunks this process has shipped that way so far (0 = the transport is off or fell back to NCCL). */
+unsigned long long candmc_panel_transport_sends(void);
 /* Host B blocks: 1 = the rows of the first k-chunk are uploaded ahead of the rest so the first multiply starts earlier
  * (default 0: one copy of the whole block, whose wide rows keep the 2-D DMA efficient; the trade-off is not measured yet). */
 int candmc_set_b_first_chunk_early(int on);

@@ -39,7 +39,7 @@ struct Alloc {
   bool peer;       // another process's allocation mapped here by cudaIpcOpenMemHandle (its owner checks the canaries)
   char name[48];
 };
-constexpr size_t kShmThreshold = 256 * 1024;
+constexpr size_t kShmThreshold = 4 * 1024;   // device allocations from this size on are shared-memory objects (exportable)
 constexpr size_t kShmHeader = 256;
 std::map<uintptr_t, Alloc> g_allocs;   // user base -> allocation
 cudaError_t g_last = cudaSuccess;
@@ -51,7 +51,7 @@ struct SimEvent {
   uint64_t gen_done = 0;   // ... and executed
 };
 
-enum TaskKind { T_RUN, T_RECORD, T_WAIT, T_NCCL };
+enum TaskKind { T_RUN, T_RECORD, T_WAIT, T_NCCL, T_WAITVAL };
 struct Task {
   TaskKind kind = T_RUN;
   uint64_t seq = 0;
@@ -60,7 +60,20 @@ struct Task {
   uint64_t gen = 0;
   cpusim::NcclBatch* batch = nullptr;
   bool started = false;
+  const uint32_t* addr = nullptr;   // T_WAITVAL: cuStreamWaitValue32
+  uint32_t value = 0;
+  unsigned wflags = 0;
 };
+
+bool waitval_satisfied(const uint32_t* addr, uint32_t value, unsigned flags) {
+  const uint32_t v = __atomic_load_n(addr, __ATOMIC_ACQUIRE);
+  switch (flags & 3u) {
+    case CU_STREAM_WAIT_VALUE_GEQ: return (int32_t)(v - value) >= 0;
+    case CU_STREAM_WAIT_VALUE_EQ: return v == value;
+    case CU_STREAM_WAIT_VALUE_AND: return (v & value) != 0;
+    default: return (~(v | value)) != 0;   // NOR
+  }
+}
 struct SimStream {
   int id = 0;
   std::deque<Task> q;
@@ -262,11 +275,16 @@ void drain(const std::function<bool()>& pred, const char* why) {
     bool any = false;
     SimStream* pick = nullptr;
     int ncand = 0;
+    bool external_wait = false;
     for (SimStream* st : g_streams) {
       if (st->q.empty()) continue;
       Task& t = st->q.front();
       if (t.kind == T_NCCL && t.started) continue;
       if (t.kind == T_WAIT && t.ev->gen_done < t.gen) continue;
+      if (t.kind == T_WAITVAL && !waitval_satisfied(t.addr, t.value, t.wflags)) {
+        external_wait = true;   // another process (or a later task) has to write the value
+        continue;
+      }
       ++ncand;
       if (!pick) {
         pick = st;
@@ -321,7 +339,7 @@ void drain(const std::function<bool()>& pred, const char* why) {
       last = now_s2();
       continue;
     }
-    if (!pick && active.empty()) {
+    if (!pick && active.empty() && !external_wait) {
       fprintf(stderr, "cpusim: %s can never complete: every queued stream waits on an event that nobody will record\n", why);
       abort();
     }
@@ -334,6 +352,10 @@ void drain(const std::function<bool()>& pred, const char* why) {
         fprintf(stderr, "cpusim nccl: NO PROGRESS for %.0f s in %s — deadlock in the communication schedule?  Active operations:\n",
                 timeout, why);
         for (cpusim::NcclBatch* b : active) cpusim::nccl_describe(b);
+        for (SimStream* st : g_streams)
+          if (!st->q.empty() && st->q.front().kind == T_WAITVAL)
+            fprintf(stderr, "  stream %d waits for *%p (now %u) to reach %u\n", st->id, (const void*)st->q.front().addr,
+                    *st->q.front().addr, st->q.front().value);
         abort();
       }
     }
@@ -363,6 +385,9 @@ struct AtExit {
               (unsigned long long)g_executed, (unsigned long long)g_reordered);
   }
 } g_at_exit;
+
+// cuStreamWaitValue32: a stream memory operation — the stream goes on when *addr satisfies the condition
+CUresult fake_stream_wait_value32(CUstream st, CUdeviceptr addr, cuuint32_t value, unsigned int flags);
 
 CUresult fake_encode_tiled(CUtensorMap* out, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* gdim,
                            const cuuint64_t* gstride, const cuuint32_t* box, const cuuint32_t* estride, CUtensorMapInterleave il,
@@ -415,6 +440,39 @@ void stream_submit_nccl(cudaStream_t s, NcclBatch* b) {
 }
 
 }  // namespace cpusim
+
+namespace {
+CUresult fake_stream_wait_value32(CUstream st, CUdeviceptr addr, cuuint32_t value, unsigned int flags) {
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(addr);
+  check_range(p, 4, true, "cuStreamWaitValue32");
+  if (g_policy == P_SYNC) {   // everything before it has executed; wait for the writer (another process) right here
+    static double timeout = getenv("CPUSIM_TIMEOUT") ? atof(getenv("CPUSIM_TIMEOUT")) : 60.0;
+    const double t0 = now_ms();
+    long spins = 0;
+    while (!waitval_satisfied(p, value, flags)) {
+      if (++spins < 200) {
+        sched_yield();
+      } else {
+        timespec ts = {0, 50000};
+        nanosleep(&ts, nullptr);
+        if ((now_ms() - t0) * 1e-3 > timeout) {
+          fprintf(stderr, "cpusim: cuStreamWaitValue32 NO PROGRESS for %.0f s: *%p is %u, waiting for %u\n", timeout, (const void*)p, *p,
+                  value);
+          abort();
+        }
+      }
+    }
+    return CUDA_SUCCESS;
+  }
+  Task t;
+  t.kind = T_WAITVAL;
+  t.addr = p;
+  t.value = value;
+  t.wflags = flags;
+  push(S(reinterpret_cast<cudaStream_t>(st)), std::move(t));
+  return CUDA_SUCCESS;
+}
+}  // namespace
 
 extern "C" {
 
@@ -680,6 +738,11 @@ cudaError_t cudaIpcCloseMemHandle(void* p) {
 cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* q) {
   if (strcmp(symbol, "cuTensorMapEncodeTiled") == 0) {
     *fn = reinterpret_cast<void*>(&fake_encode_tiled);
+    if (q) *q = cudaDriverEntryPointSuccess;
+    return cudaSuccess;
+  }
+  if (strcmp(symbol, "cuStreamWaitValue32") == 0) {
+    *fn = reinterpret_cast<void*>(&fake_stream_wait_value32);
     if (q) *q = cudaDriverEntryPointSuccess;
     return cudaSuccess;
   }

@@ -58,8 +58,8 @@ def record(name, err, tol):
     return ok
 
 
-def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_golden=True, oracle=True):
-    g = cb.d25_grid(world, c)
+def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_golden=True, oracle=True, grid=None):
+    g = grid if grid is not None else cb.d25_grid(world, c)
     q = g["q"]
     b = n // q
     row0, col0 = g["row"] * b, g["col"] * b
@@ -84,8 +84,9 @@ def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_go
     if not oracle:   # too large for the plain-C oracle: numpy (OpenBLAS) product of the regenerated operands instead
         full = orc.unit_block(n, n, 0, 0, n, 0) @ orc.unit_block(n, n, 0, 0, n, 1)
         ok = record(f"{name}:numpy", rel_frob(got, full[row0:row0 + b, col0:col0 + b]), 10 * n * EPS)
-        for k in ("cdt_row", "cdt_col", "cdt_kdir"):
-            g[k].free()
+        if grid is None:
+            for k in ("cdt_row", "cdt_col", "cdt_kdir"):
+                g[k].free()
         return ok
     # oracle for the whole grid
     Ab, Bb = orc.d25_blocks(n, q, c) if not (q == 1 and c > 1) else (
@@ -95,6 +96,20 @@ def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_go
     ok = record(f"{name}:oracle", rel_frob(got, Cb[world.rank]), 10 * n * EPS)
     if check_golden and name in golden:
         ok &= record(f"{name}:golden", rel_frob(got, golden[name][world.rank]), 10 * n * EPS)
+    if grid is None:
+        for k in ("cdt_row", "cdt_col", "cdt_kdir"):
+            g[k].free()
+    return ok
+
+
+def case_repeat(world, golden, name, c, sizes):
+    """many multiplies on ONE grid (the communicators' persistent state: workspaces, fused-reduce windows with their epochs
+    and double-buffered slabs, panel-transport windows with their call counters, done flags and the growth path)"""
+    g = cb.d25_grid(world, c)
+    ok = True
+    for it, n in enumerate(sizes):
+        ok &= case_d25(world, golden, f"{name}.{it}.n{n}", n, c, it % 2, lda_pad=(it % 3 == 2) * 2, check_golden=False, oracle=False,
+                       grid=g)
     for k in ("cdt_row", "cdt_col", "cdt_kdir"):
         g[k].free()
     return ok
@@ -502,6 +517,8 @@ def main():
     world = cb.init_world(rank, world_size, local)
     if os.environ.get("CANDMC_TEST_FUSED_GRIDS") == "1":   # the fused depth sum on q x q x c grids too (opt-in in the product)
         cb.lib().candmc_set_fused_reduce(2)
+    if os.environ.get("CANDMC_TEST_PANEL_TRANSPORT") == "1":   # SUMMA panels by copy engines into peer windows (opt-in in the product)
+        cb.lib().candmc_set_panel_transport(1)
     golden = np.load(os.path.join(ROOT, "tests", "golden", "canmm_ref_outputs.npz"))
     P = world_size
     only_pending = os.environ.get("CANDMC_TEST_PENDING") == "1"
@@ -538,6 +555,7 @@ def main():
             n_host = 512 if os.environ.get("CANDMC_CPUSIM") == "1" else 4096   # plain-loop GEMM in the simulator
             case_d25(world, golden, f"d25_ksplit_host_n{n_host}_{tag}", n_host, 2, 0, use_host=True, check_golden=False, oracle=False)
             case_d25(world, golden, f"d25_ksplit_host_n96_{tag}", 96, 2, 0, use_host=True, lda_pad=2)
+            case_repeat(world, golden, f"repeat_1x1x2_{tag}", 2, [256, 256, 256, 256, 256, 64, 512, 256])
             # k-slice of 1024 -> four upload chunks; the last two are multiplied slab-wise with the C slabs summed and downloaded early
             case_d25(world, golden, f"d25_ksplit_host_n2048_slabs_{tag}", 2048, 2, 0, use_host=True, check_golden=False, oracle=False)
             if os.environ.get("CANDMC_CPUSIM") != "1":   # (on the simulator this is 10 s of emulated fused kernel; n512 above is the same path)
@@ -568,6 +586,7 @@ def main():
             case_update_A(world, golden, "upda_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 0, 0)
             case_update_A(world, golden, "upda_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 2, 0)
             case_update_A(world, golden, f"upda_T_2x2_{tag}", 128, 96, 16, 2, 1, 1, with_T=True)
+            case_repeat(world, golden, f"repeat_2x2_{tag}", 1, [96, 96, 96, 96, 96, 96, 192, 96, 512, 96])
         if P == 8:
             case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0)
             case_d25(world, golden, "d25_n64_q2_c2_ovp1", 64, 2, 1)
@@ -576,6 +595,7 @@ def main():
             case_d25(world, golden, f"d25_n1024_c2_fused_{tag}", 1024, 2, 1)
             case_d25(world, golden, f"d25_n1024_c2_host_{tag}", 1024, 2, 0, use_host=True)
             case_d25(world, golden, f"d25_n512_c2_fused_pad_{tag}", 512, 2, 0, lda_pad=1)
+            case_repeat(world, golden, f"repeat_2x2x2_{tag}", 2, [64, 64, 64, 64, 64, 64, 512, 64, 512, 512, 512])
     cb.set_min_kchunk(1024)
     big = int(os.environ.get("CANDMC_TEST_BIG_N", "0"))
     if big:
@@ -590,7 +610,8 @@ def main():
     if rank == 0:
         print(json.dumps({"world_size": world_size, "checks_rank0": len(RESULTS), "failed_all_ranks": int(flag.item()),
                           "max_err_rank0": max((r[2] for r in RESULTS), default=0.0),
-                          "launches_rank0": cb.launch_count()}), flush=True)
+                          "launches_rank0": cb.launch_count(),
+                          "panel_transport_sends_rank0": int(cb.lib().candmc_panel_transport_sends())}), flush=True)
     world.free()
     if world_size > 1:
         dist.destroy_process_group()

@@ -55,6 +55,12 @@ for _n in DIST_MAIN:     # longest first.  On 8 ranks the fused GEMM + depth all
     # the product until a B200 has seen it): the kernel's peer-memory epilogue and ipc.cu run for real, over simulated CUDA IPC
     _job(f"main{_n}", _torchrun(_n, 29700 + _n, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0",
          CANDMC_TEST_FUSED_GRIDS="1" if _n == 8 else "0")
+# opt-in data paths over peer memory, never seen by a B200: SUMMA panels by copy engines (transport.h) on 2x2 and, together
+# with the fused depth sum, on 2x2x2 — deferred streams, LIFO order
+_job("transport4", _torchrun(4, 29741, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_PANEL_TRANSPORT="1",
+     CPUSIM_SCHED="lifo")
+_job("transport8", _torchrun(8, 29742, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_PANEL_TRANSPORT="1",
+     CANDMC_TEST_FUSED_GRIDS="1", CPUSIM_SCHED="lifo")
 # the hot kernel itself on the PTX emulation, and the 4-rank suite with every GEMM going through it
 _job("kernel", [sys.executable, os.path.join(SIM, "probe_gemm.py")])
 if FULL:
@@ -258,6 +264,15 @@ def test_bench_script_logic_on_the_simulator(nproc):
     b = d["config"]["block"]
     assert d["e2e"]["d2h_bytes_per_step"] == nproc * b * b * 8
     assert d["e2e"]["h2d_bytes_per_step"] == (2 if nproc == 1 else 8) * b * b * 8
+
+
+@pytest.mark.parametrize("nproc", [4, 8])
+def test_copy_engine_panel_transport_on_the_simulator(nproc):
+    """candmc_set_panel_transport(1): panel chunks DMA-written into the consumers' IPC windows, ready / done flags as 4-byte
+    DMAs, cuStreamWaitValue32 on the consumer side — the whole distributed suite incl. repeated multiplies on one grid (window
+    halves reused, windows regrown), no ncclBroadcast left on the path"""
+    out = _dist(f"transport{nproc}")
+    assert out["panel_transport_sends_rank0"] > 50
 
 
 def test_hot_gemm_kernel_on_the_ptx_emulation():

@@ -73,7 +73,7 @@ for section in "$@"; do
       grep -E "==|\"metric\"" gpurun_out/e2e${N}_bench.log | cut -c1-300
       ;;
     dist8)
-      for knobs in "" "--fused-reduce 2" "--upload-all-blocks"; do
+      for knobs in "" "--fused-reduce 2" "--panel-transport" "--panel-transport --fused-reduce 2"; do
         echo "== bench 8 GPUs $knobs" >> gpurun_out/dist8_bench.log
         timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29534 \
           bench.py --gpus 8 --steps 5 --warmup 3 $knobs >> gpurun_out/dist8_bench.log 2>&1

@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -59,6 +60,24 @@ int runtime_init(int device) {
   g_rt.pfn_encode_tiled = fn;
   CANDMC_CUDA(cudaMalloc(&g_rt.tile_counters, sizeof(int) * kTileCounters));
   CANDMC_CUDA(cudaMemset(g_rt.tile_counters, 0, sizeof(int) * kTileCounters));
+  // Tuning switches for callers that cannot call the candmc_set_* functions (the reference's unmodified mains running as
+  // drop-ins): same meaning as the setters, read once when the process binds to its GPU.
+  auto env_int = [](const char* name, long long* out) {
+    const char* e = getenv(name);
+    if (e == nullptr || *e == 0) return false;
+    *out = atoll(e);
+    return true;
+  };
+  long long v;
+  if (env_int("CANDMC_PANEL_TRANSPORT", &v)) g_rt.panel_transport = (v != 0);
+  if (env_int("CANDMC_FUSED_REDUCE", &v)) {
+    g_rt.fused_reduce = (v != 0);
+    g_rt.fused_reduce_grids = (v >= 2);
+  }
+  if (env_int("CANDMC_BG_CTAS", &v) && v >= 0 && v <= 64) g_rt.bg_max_ctas = (int)v;
+  if (env_int("CANDMC_MIN_KCHUNK", &v) && v >= 2) g_rt.min_kchunk = v;
+  if (env_int("CANDMC_EARLY_C_DOWNLOAD", &v)) g_rt.early_c_download = (v != 0);
+  if (env_int("CANDMC_SKIP_UNUSED_UPLOADS", &v)) g_rt.skip_unused_uploads = (v != 0);
   g_rt.initialized = true;
   return OK;
 }

@@ -106,14 +106,18 @@ DROPIN_CASES = {
     "spc_p4_uni": ("candmc_run", 4, "test_spc", ["-bidir", "0", "-m", "64", "-k", "32", "-n", "48"], "Test passed.", "sync"),
     "lu_pp": ("mpirun", 4, "lu_pp_gpu", ["-n", "256", "-b_sm", "8", "-b_lrg", "32"], "test passed", "sync"),
     "lu_tp": ("mpirun", 4, "lu_tp_gpu", ["-n", "256", "-b_sm", "8", "-b_lrg", "32"], "test passed", "lifo"),
+    # the reference's own D25 test with the opt-in peer-memory paths switched on from the environment (an unmodified main
+    # cannot call setters): panels by copy engines, depth sum fused into the GEMM epilogue (n = 1024: b = 512 = 2 * 128 * c)
+    "d25_p8_peer_paths": ("candmc_run", 8, "topo_pdgemm_unit", ["-n", "1024", "-ovp", "0"], "D25 UNIT TEST PASSED", "lifo"),
 }
+DROPIN_ENV = {"d25_p8_peer_paths": dict(CANDMC_PANEL_TRANSPORT="1", CANDMC_FUSED_REDUCE="2", CANDMC_MIN_KCHUNK="64")}
 HAVE_DROPIN = all(os.path.exists(os.path.join(DROPIN, c[2])) for c in DROPIN_CASES.values()) and \
     os.path.exists(os.path.join(ROOT, "tools", "candmc_run")) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "mpirun"))
 if HAVE_DROPIN:
     for _k, (_launcher, _np, _exe, _args, _needle, _sched) in DROPIN_CASES.items():
         _run = os.path.join(ROOT, "tools", "candmc_run") if _launcher == "candmc_run" else os.path.join(ROOT, "oracle", "_ref", "mpirun")
         _job(f"dropin_{_k}", [_run, "-np", str(_np), "-timeout", "200", os.path.join(DROPIN, _exe), *_args], LD_PRELOAD=PRELOAD,
-             CPUSIM_SCHED=_sched)
+             CPUSIM_SCHED=_sched, **DROPIN_ENV.get(_k, {}))
 
 # the same workers with DEFERRED streams: work runs only at host synchronisation points, and among the runnable streams
 # the one whose head was enqueued last goes first (lifo) or a random one — a missing event dependency computes garbage

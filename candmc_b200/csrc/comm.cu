@@ -7,6 +7,8 @@
 
 #include <string.h>
 
+#include <algorithm>
+
 #include "../../include/candmc_b200.h"
 #include "ipc.h"
 #include "transport.h"
@@ -76,6 +78,11 @@ int comm_sendrecv(candmc_comm* c, const double* send, int64_t scount, int dst, d
   }
   CANDMC_CHECK(!(do_send && dst == c->rank) && !(do_recv && src == c->rank), "sendrecv: unmatched self transfer");
   if (!do_send && !do_recv) return OK;
+  if (p2p_transport_usable(c, std::max(do_send ? scount : 0, do_recv ? rcount : 0))) {   // copy engines + flags, no NCCL kernel
+    if (do_send) CANDMC_TRY(p2p_transport_send(c, send, scount, dst, st));
+    if (do_recv) CANDMC_TRY(p2p_transport_recv(c, recv, rcount, src, st));
+    return OK;
+  }
   ncclComm_t comm = c->nccl;
   if (background) CANDMC_TRY(comm_background(c, &comm));
   CANDMC_NCCL(ncclGroupStart());
@@ -162,6 +169,10 @@ int candmc_comm_free(candmc_comm_t* comm) {
   if (comm->transport) {
     cudaDeviceSynchronize();
     candmc::panel_transport_destroy(static_cast<candmc::PanelTransport*>(comm->transport));
+  }
+  if (comm->p2p) {
+    cudaDeviceSynchronize();
+    candmc::p2p_transport_destroy(static_cast<candmc::P2PTransport*>(comm->p2p));
   }
   if (comm->nccl_bg && comm->nccl_bg != comm->nccl) ncclCommDestroy(comm->nccl_bg);
   if (comm->nccl) ncclCommDestroy(comm->nccl);

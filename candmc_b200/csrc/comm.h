@@ -16,6 +16,7 @@ struct candmc_comm {
   void* fused_ctx = nullptr;      // candmc::FusedCtx* of the fused GEMM + depth all-reduce (ipc.h), owned by this handle
   bool fused_failed = false;      // CUDA IPC unavailable: stay on ncclAllReduce
   void* transport = nullptr;      // candmc::PanelTransport* (transport.h): copy-engine panel transport over peer windows
+  void* p2p = nullptr;            // candmc::P2PTransport* (transport.h): the same for point-to-point exchanges
   bool transport_failed = false;  // peer windows / stream memory operations unavailable: stay on ncclBroadcast
 };
 

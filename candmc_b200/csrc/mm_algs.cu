@@ -767,6 +767,9 @@ int candmc_bcast_cannon_4d(const candmc_ctb_args_t* args, const double* mat_A, c
   auto wrap = [](int a, int m) { return ((a % m) + m) % m; };
 
   if (x2_np > 1) {
+    // (opt-in) staggers and shifts by copy engines into peer windows instead of grouped ncclSend/ncclRecv: collective set-up
+    CANDMC_TRY(p2p_transport_prepare(cdt_x2, bb));
+    CANDMC_TRY(p2p_transport_prepare(cdt_y2, bb));
     CANDMC_TRY(stream_wait(shift, st));
     // messages must be contiguous: get the blocks out of their lda first (dual_cannon.cxx:89-102)
     if (ldA != b) {
@@ -877,7 +880,15 @@ int spc_exchange(Spc& s, const std::vector<Xfer>& xs, bool background) {
       any_remote = true;
     }
   }
-  if (any_remote) {
+  int64_t largest = 0;
+  for (const Xfer& x : xs) largest = std::max(largest, x.count);
+  if (any_remote && p2p_transport_usable(s.world, largest)) {
+    // every "put between two fences" of the reference as DMAs into the peers' windows: all sends first, then the receives
+    for (const Xfer& x : xs)
+      if (x.dst != s.rank) CANDMC_TRY(p2p_transport_send(s.world, x.send, x.count, x.dst, s.comm));
+    for (const Xfer& x : xs)
+      if (x.dst != s.rank) CANDMC_TRY(p2p_transport_recv(s.world, x.recv, x.count, x.src, s.comm));
+  } else if (any_remote) {
     ncclComm_t comm = s.world->nccl;
     if (background) CANDMC_TRY(comm_background(s.world, &comm));  // shifts run under the GEMM; the stagger does not
     CANDMC_NCCL(ncclGroupStart());
@@ -998,6 +1009,8 @@ int candmc_spcannon(int bidir, int rank, int kary, int ndim, candmc_comm_t* worl
     if (!tB) CANDMC_TRY(transpose_f64(k, n, sB.ptr(), sB.ld(), s.B[0], n, st));
     else CANDMC_TRY(lda_copy_f64(n, k, sB.ld(), n, sB.ptr(), s.B[0], st));
   }
+  // (opt-in) every put of the stagger and the shifts by copy engines into peer windows; the largest message is a whole slice
+  if (kary > 1 && k > 0) CANDMC_TRY(p2p_transport_prepare(world, 2 * std::max(mk, nk) / ndim + 2));
   CANDMC_TRY(stream_wait(s.comm, st));
   if (kary > 1 && k > 0) CANDMC_TRY(spc_stagger(s, 0));
   CANDMC_TRY(spc_shift(s, bidir, 0, beta));

@@ -150,4 +150,79 @@ void panel_transport_destroy(PanelTransport* t) {
   delete t;
 }
 
+// ---- point-to-point --------------------------------------------------------------------------------------------------------
+int p2p_transport_prepare(candmc_comm* c, int64_t slot_elems) {
+  if (c == nullptr || !runtime().panel_transport || c->size < 2 || c->size > kMaxPeers || c->transport_failed) return OK;
+  P2PTransport* t = static_cast<P2PTransport*>(c->p2p);
+  if (t != nullptr && t->slot_elems >= slot_elems) return OK;
+  if (ensure_globals() != OK) {
+    c->transport_failed = true;
+    return OK;
+  }
+  if (t != nullptr) {   // grow: every rank gets here in the same call; the message counters start over with the new window
+    CANDMC_CUDA(cudaDeviceSynchronize());
+    CANDMC_TRY(candmc_comm_barrier(c));
+    p2p_transport_destroy(t);
+    c->p2p = nullptr;
+  }
+  t = new P2PTransport();
+  t->slot_elems = slot_elems;
+  t->off_ready = 0;
+  t->off_ack = align_up(sizeof(uint32_t) * kMaxPeers * kP2PSlots, 256);
+  t->off_data = t->off_ack + 256;
+  const size_t total = t->off_data + sizeof(double) * static_cast<size_t>(c->size) * kP2PSlots * static_cast<size_t>(slot_elems);
+  PeerWindow* w = nullptr;
+  if (window_create(c, total, &w) != OK) {
+    delete t;
+    c->transport_failed = true;
+    return OK;
+  }
+  t->win = w;
+  c->p2p = t;
+  return OK;
+}
+
+bool p2p_transport_usable(const candmc_comm* c, int64_t count) {
+  const P2PTransport* t = c ? static_cast<const P2PTransport*>(c->p2p) : nullptr;
+  return t != nullptr && count <= t->slot_elems;
+}
+
+int p2p_transport_send(candmc_comm* c, const double* send, int64_t count, int dst, cudaStream_t st) {
+  P2PTransport* t = static_cast<P2PTransport*>(c->p2p);
+  CANDMC_CHECK(t != nullptr && dst >= 0 && dst < c->size && dst != c->rank && count <= t->slot_elems, "p2p transport: bad send");
+  const uint32_t k = ++t->send_seq[dst];
+  CANDMC_CHECK(k < kPanelMaxCalls, "p2p transport: message counter exhausted");
+  const int slot = static_cast<int>(k % kP2PSlots);
+  char* mine = t->win->base[c->rank];
+  if (k > static_cast<uint32_t>(kP2PSlots))   // the message that used this slot before has been copied out by dst
+    CANDMC_TRY(stream_wait_geq(st, reinterpret_cast<const uint32_t*>(mine + t->off_ack) + dst, k - kP2PSlots));
+  char* pb = t->win->base[dst];
+  double* slotp = reinterpret_cast<double*>(pb + t->off_data) + (static_cast<int64_t>(c->rank) * kP2PSlots + slot) * t->slot_elems;
+  CANDMC_CUDA(cudaMemcpyAsync(slotp, send, sizeof(double) * count, cudaMemcpyDeviceToDevice, st));
+  uint32_t* flag = reinterpret_cast<uint32_t*>(pb + t->off_ready) + c->rank * kP2PSlots + slot;
+  CANDMC_CUDA(cudaMemcpyAsync(flag, g_vals + k, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  runtime().transport_sends++;
+  return OK;
+}
+
+int p2p_transport_recv(candmc_comm* c, double* recv, int64_t count, int src, cudaStream_t st) {
+  P2PTransport* t = static_cast<P2PTransport*>(c->p2p);
+  CANDMC_CHECK(t != nullptr && src >= 0 && src < c->size && src != c->rank && count <= t->slot_elems, "p2p transport: bad receive");
+  const uint32_t k = ++t->recv_seq[src];
+  const int slot = static_cast<int>(k % kP2PSlots);
+  char* mine = t->win->base[c->rank];
+  CANDMC_TRY(stream_wait_geq(st, reinterpret_cast<const uint32_t*>(mine + t->off_ready) + src * kP2PSlots + slot, k));
+  const double* slotp = reinterpret_cast<const double*>(mine + t->off_data) + (static_cast<int64_t>(src) * kP2PSlots + slot) * t->slot_elems;
+  CANDMC_CUDA(cudaMemcpyAsync(recv, slotp, sizeof(double) * count, cudaMemcpyDeviceToDevice, st));
+  uint32_t* ack = reinterpret_cast<uint32_t*>(t->win->base[src] + t->off_ack) + c->rank;
+  CANDMC_CUDA(cudaMemcpyAsync(ack, g_vals + k, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  return OK;
+}
+
+void p2p_transport_destroy(P2PTransport* t) {
+  if (!t) return;
+  window_destroy(t->win);
+  delete t;
+}
+
 }  // namespace candmc

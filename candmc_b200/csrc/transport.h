@@ -46,4 +46,28 @@ int panel_transport_wait(PanelTransport* t, candmc_comm* c, int op, int64_t slot
 int panel_transport_end(PanelTransport* t, candmc_comm* c, cudaStream_t compute, cudaStream_t copy);
 void panel_transport_destroy(PanelTransport* t);
 
+// ---- point-to-point exchanges (Cannon staggers and shifts) the same way -------------------------------------------------
+// Every rank's window has, for every possible source rank, a ring of kP2PSlots message slots with a ready flag each, and one
+// acknowledgement flag per destination.  Message number k from s to d (k = 1, 2, ... per ordered pair, counted on both sides):
+//   sender:   wait ack[d] >= k - kP2PSlots (own window)  ->  DMA the data into d's slot k % kP2PSlots of lane s
+//             ->  DMA k into d's ready flag of that slot;
+//   receiver: wait ready[s][k % kP2PSlots] >= k  ->  DMA the slot into the destination buffer  ->  DMA k into s's ack[d].
+// Nothing but copy engines and stream memory operations, so a shift runs under the GEMM of the current step without taking
+// SMs from it (the NCCL version could only run at GEMM boundaries, DESIGN.md §7 "known issue").
+constexpr int kP2PSlots = 2;
+struct P2PTransport {
+  PeerWindow* win = nullptr;
+  int64_t slot_elems = 0;
+  uint32_t send_seq[kMaxPeers] = {0};
+  uint32_t recv_seq[kMaxPeers] = {0};
+  size_t off_ready = 0, off_ack = 0, off_data = 0;
+};
+// Collective over `c`: (re)creates the transport with room for messages of `slot_elems` doubles; c->p2p stays null when the
+// transport is off or unavailable.
+int p2p_transport_prepare(candmc_comm* c, int64_t slot_elems);
+bool p2p_transport_usable(const candmc_comm* c, int64_t count);
+int p2p_transport_send(candmc_comm* c, const double* send, int64_t count, int dst, cudaStream_t st);
+int p2p_transport_recv(candmc_comm* c, double* recv, int64_t count, int src, cudaStream_t st);
+void p2p_transport_destroy(P2PTransport* t);
+
 }  // namespace candmc

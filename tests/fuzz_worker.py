@@ -24,6 +24,10 @@ def main():
     if P > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     world = cb.init_world(rank, P, local)
+    if os.environ.get("CANDMC_TEST_PANEL_TRANSPORT") == "1":
+        cb.lib().candmc_set_panel_transport(1)
+    if os.environ.get("CANDMC_TEST_FUSED_GRIDS") == "1":
+        cb.lib().candmc_set_fused_reduce(2)
     golden = {}
     rng = random.Random(seed * 1000 + P)
     log = []
@@ -110,7 +114,8 @@ def main():
         if flag.item():
             print("cases:", log, flush=True)
         print(json.dumps({"world_size": P, "seed": seed, "cases": len(log), "checks_rank0": len(dw.RESULTS),
-                          "failed_all_ranks": int(flag.item()), "max_err_rank0": max((r[2] for r in dw.RESULTS), default=0.0)}), flush=True)
+                          "failed_all_ranks": int(flag.item()), "max_err_rank0": max((r[2] for r in dw.RESULTS), default=0.0),
+                          "panel_transport_sends_rank0": int(cb.lib().candmc_panel_transport_sends())}), flush=True)
     world.free()
     if P > 1:
         dist.destroy_process_group()

@@ -52,6 +52,14 @@ for section in "$@"; do
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29536 \
         tools/bench_configs.py --pending > gpurun_out/bench_pending_4gpu.jsonl 2> gpurun_out/bench_pending_4gpu.err
       cat gpurun_out/bench_pending_4gpu.jsonl
+      # the opt-in peer-memory paths: parity first (same worker, switches from the environment), then configs 2 / 4 / 5 with
+      # SUMMA panels and Cannon shifts on copy engines
+      CANDMC_TEST_PANEL_TRANSPORT=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
+        --master-port 29538 tests/dist_worker.py > gpurun_out/dist4_transport.log 2>&1
+      tail -4 gpurun_out/dist4_transport.log
+      CANDMC_PANEL_TRANSPORT=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
+        --master-port 29539 tools/bench_configs.py > gpurun_out/bench_configs_4gpu_transport.jsonl 2> gpurun_out/bench_configs_4gpu_transport.err
+      cat gpurun_out/bench_configs_4gpu_transport.jsonl
       ;;
     e2e1)
       # one GPU: the host-streamed multiply with 8 / 16 / 32 column panels (16 is the new default at n = 32768, never measured)
@@ -73,6 +81,9 @@ for section in "$@"; do
       grep -E "==|\"metric\"" gpurun_out/e2e${N}_bench.log | cut -c1-300
       ;;
     dist8)
+      CANDMC_TEST_PANEL_TRANSPORT=1 CANDMC_TEST_FUSED_GRIDS=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+        --master-addr 127.0.0.1 --master-port 29540 tests/dist_worker.py > gpurun_out/dist8_peer_paths.log 2>&1
+      tail -4 gpurun_out/dist8_peer_paths.log
       for knobs in "" "--fused-reduce 2" "--panel-transport" "--panel-transport --fused-reduce 2"; do
         echo "== bench 8 GPUs $knobs" >> gpurun_out/dist8_bench.log
         timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29534 \

@@ -13,6 +13,7 @@ namespace {
 typedef CUresult (*PFN_waitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 PFN_waitValue32 g_wait32 = nullptr;
 bool g_wait32_tried = false;
+unsigned g_wait_flags = CU_STREAM_WAIT_VALUE_GEQ;   // | FLUSH where the device can flush outstanding remote writes behind a wait
 uint32_t* g_vals = nullptr;   // device array vals[i] = i: the 4-byte sources of the flag DMAs
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -31,6 +32,13 @@ int ensure_globals() {
       g_wait32 = reinterpret_cast<PFN_waitValue32>(fn);
     else
       cudaGetLastError();
+    // the flags are written by a peer's copy engine: ask for the remote-write flush behind the wait where it exists, so that
+    // the chunk the flag announces is visible to the kernel that follows
+    int can_flush = 0;
+    if (cudaDeviceGetAttribute(&can_flush, cudaDevAttrCanFlushRemoteWrites, runtime().device) == cudaSuccess && can_flush)
+      g_wait_flags |= CU_STREAM_WAIT_VALUE_FLUSH;
+    else
+      cudaGetLastError();
   }
   if (g_wait32 == nullptr) return ERR_CUDA;
   if (g_vals == nullptr) {
@@ -44,7 +52,7 @@ int ensure_globals() {
 }
 
 int stream_wait_geq(cudaStream_t st, const uint32_t* addr, uint32_t value) {
-  CUresult r = g_wait32(reinterpret_cast<CUstream>(st), reinterpret_cast<CUdeviceptr>(addr), value, CU_STREAM_WAIT_VALUE_GEQ);
+  CUresult r = g_wait32(reinterpret_cast<CUstream>(st), reinterpret_cast<CUdeviceptr>(addr), value, g_wait_flags);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuStreamWaitValue32 failed (CUresult %d)", (int)r);
     return ERR_CUDA;

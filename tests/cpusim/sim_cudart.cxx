@@ -682,6 +682,10 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
 }
 
 cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int* value, cudaDeviceAttr attr, int) {
+  *value = (attr == cudaDevAttrCanFlushRemoteWrites) ? 1 : 0;   // the only one the product asks for
+  return cudaSuccess;
+}
 
 // ---- CUDA IPC: large device allocations are shared-memory objects, the handle is the object's name ------------------------
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {

@@ -464,6 +464,36 @@ def pending_cases(world, golden):
             case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0, use_host=True)
         cb.set_min_kchunk(1024)
         cb.lib().candmc_set_skip_unused_uploads(0)
+    # ---- changes of the end-to-end path made without a GPU: early C download (default on), 16-panel host pipeline, and the
+    # persistent per-communicator state under repeated multiplies
+    for min_kc in (1024, 8):
+        cb.set_min_kchunk(min_kc)
+        tag = f"kc{min_kc}"
+        if P == 1:
+            cb.lib().candmc_set_host_pipeline_min(64)
+            cb.lib().candmc_set_host_pipeline_panels(16)    # the cut bench.py's n = 32768 gets
+            case_d25(world, golden, f"d25_hostpipe16_n2304_{tag}", 2304, 1, 0, use_host=True, check_golden=False, oracle=False)
+            case_d25(world, golden, f"d25_hostpipe16_n200_pad_{tag}", 200, 1, 0, lda_pad=3, use_host=True, check_golden=False)
+            cb.lib().candmc_set_host_pipeline_panels(0)
+            cb.lib().candmc_set_host_pipeline_min(2048)
+        if P == 2:
+            case_repeat(world, golden, f"repeat_1x1x2_{tag}", 2, [256, 256, 256, 256, 256, 64, 512, 256])
+            n_host = 512 if os.environ.get("CANDMC_CPUSIM") == "1" else 4096
+            case_d25(world, golden, f"d25_ksplit_host_early_n{n_host}_{tag}", n_host, 2, 0, use_host=True, check_golden=False, oracle=False)
+            # k-slice of 1024 -> four upload chunks; the last two are multiplied slab-wise with the C slabs summed and downloaded early
+            case_d25(world, golden, f"d25_ksplit_host_early_n2048_slabs_{tag}", 2048, 2, 0, use_host=True, check_golden=False, oracle=False)
+            if os.environ.get("CANDMC_CPUSIM") != "1":   # (on the simulator this is 10 s of emulated fused kernel; n512 above is the same path)
+                cb.lib().candmc_set_early_c_download(0)
+                case_d25(world, golden, f"d25_ksplit_host_early_n2048_late_{tag}", 2048, 2, 0, use_host=True, check_golden=False, oracle=False)
+                cb.lib().candmc_set_early_c_download(1)
+        if P == 4:
+            case_repeat(world, golden, f"repeat_2x2_{tag}", 1, [96, 96, 96, 96, 96, 96, 192, 96, 512, 96])
+            case_d25(world, golden, f"d25_n512_host_early_{tag}", 512, 1, 0, use_host=True, lda_pad=2)
+            case_d25(world, golden, f"d25_n1024_host_early_{tag}", 1024, 1, 1, use_host=True, check_golden=False, oracle=False)
+        if P == 8:
+            case_repeat(world, golden, f"repeat_2x2x2_{tag}", 2, [64, 64, 64, 64, 64, 64, 512, 64, 512, 512, 512])
+            case_d25(world, golden, f"d25_n1024_c2_host_early_{tag}", 1024, 2, 0, use_host=True)
+    cb.set_min_kchunk(1024)
     if P in (1, 4):
         case_f2b_big(world, f"f2b_big_p{P}", 1024 * int(round(P ** 0.5)), 128, 32)
     shapes = {1: [(1,)], 2: [(2,), (1,)], 4: [(2,), (4,), (1,)], 8: [(2,), (4,)]}.get(P, [])
@@ -524,6 +554,11 @@ def main():
     only_pending = os.environ.get("CANDMC_TEST_PENDING") == "1"
     if only_pending:
         pending_cases(world, golden)
+    if not only_pending:
+        # this group is the one B200s have run: host C blocks leave in one piece, as they did then; the slab-wise early download
+        # (today's default) has its cases in the pending group
+        cb.lib().candmc_set_early_c_download(0)
+        cb.lib().candmc_set_skip_unused_uploads(0)   # ... and every rank uploads both of its blocks
     for min_kc in (() if only_pending else (1024, 8)):   # default (whole panels at these sizes) and a tiny chunk to exercise the k-chunk pipeline
         cb.set_min_kchunk(min_kc)
         tag = f"kc{min_kc}"
@@ -535,10 +570,6 @@ def main():
             cb.lib().candmc_set_host_pipeline_min(64)   # stream host operands panel-wise even at this size
             case_d25(world, golden, f"d25_hostpipe_n320_{tag}", 320, 1, 0, use_host=True, check_golden=False)
             case_d25(world, golden, f"d25_hostpipe_n200_pad_{tag}", 200, 1, 0, lda_pad=3, use_host=True, check_golden=False)
-            cb.lib().candmc_set_host_pipeline_panels(16)    # the cut bench.py's n = 32768 gets
-            case_d25(world, golden, f"d25_hostpipe16_n2304_{tag}", 2304, 1, 0, use_host=True, check_golden=False, oracle=False)
-            case_d25(world, golden, f"d25_hostpipe16_n200_pad_{tag}", 200, 1, 0, lda_pad=3, use_host=True, check_golden=False)
-            cb.lib().candmc_set_host_pipeline_panels(0)
             cb.lib().candmc_set_host_pipeline_min(2048)
         if P == 2:
             case_d25(world, golden, f"d25_ksplit_n64_{tag}", 64, 2, 0)
@@ -555,13 +586,6 @@ def main():
             n_host = 512 if os.environ.get("CANDMC_CPUSIM") == "1" else 4096   # plain-loop GEMM in the simulator
             case_d25(world, golden, f"d25_ksplit_host_n{n_host}_{tag}", n_host, 2, 0, use_host=True, check_golden=False, oracle=False)
             case_d25(world, golden, f"d25_ksplit_host_n96_{tag}", 96, 2, 0, use_host=True, lda_pad=2)
-            case_repeat(world, golden, f"repeat_1x1x2_{tag}", 2, [256, 256, 256, 256, 256, 64, 512, 256])
-            # k-slice of 1024 -> four upload chunks; the last two are multiplied slab-wise with the C slabs summed and downloaded early
-            case_d25(world, golden, f"d25_ksplit_host_n2048_slabs_{tag}", 2048, 2, 0, use_host=True, check_golden=False, oracle=False)
-            if os.environ.get("CANDMC_CPUSIM") != "1":   # (on the simulator this is 10 s of emulated fused kernel; n512 above is the same path)
-                cb.lib().candmc_set_early_c_download(0)
-                case_d25(world, golden, f"d25_ksplit_host_n2048_late_{tag}", 2048, 2, 0, use_host=True, check_golden=False, oracle=False)
-                cb.lib().candmc_set_early_c_download(1)
         if P == 4:
             case_d25(world, golden, "d25_n96_q2_c1_ovp0", 96, 1, 0)
             case_d25(world, golden, "d25_n96_q2_c1_ovp1", 96, 1, 1)
@@ -586,7 +610,6 @@ def main():
             case_update_A(world, golden, "upda_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 0, 0)
             case_update_A(world, golden, "upda_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 2, 0)
             case_update_A(world, golden, f"upda_T_2x2_{tag}", 128, 96, 16, 2, 1, 1, with_T=True)
-            case_repeat(world, golden, f"repeat_2x2_{tag}", 1, [96, 96, 96, 96, 96, 96, 192, 96, 512, 96])
         if P == 8:
             case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0)
             case_d25(world, golden, "d25_n64_q2_c2_ovp1", 64, 2, 1)
@@ -595,8 +618,9 @@ def main():
             case_d25(world, golden, f"d25_n1024_c2_fused_{tag}", 1024, 2, 1)
             case_d25(world, golden, f"d25_n1024_c2_host_{tag}", 1024, 2, 0, use_host=True)
             case_d25(world, golden, f"d25_n512_c2_fused_pad_{tag}", 512, 2, 0, lda_pad=1)
-            case_repeat(world, golden, f"repeat_2x2x2_{tag}", 2, [64, 64, 64, 64, 64, 64, 512, 64, 512, 512, 512])
     cb.set_min_kchunk(1024)
+    cb.lib().candmc_set_early_c_download(1)
+    cb.lib().candmc_set_skip_unused_uploads(1)
     big = int(os.environ.get("CANDMC_TEST_BIG_N", "0"))
     if big:
         case_big_d25(world, big, None)

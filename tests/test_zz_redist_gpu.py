@@ -58,3 +58,25 @@ def test_pending_distributed_cases(nproc):
     assert rc == 0, so[-3000:] + se[-3000:]
     out = json.loads([l for l in so.splitlines() if l.startswith("{")][-1])
     assert out["failed_all_ranks"] == 0 and out["checks_rank0"] > 0
+
+
+@pytest.mark.gpu
+@PENDING
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+def test_pending_peer_memory_paths(nproc):
+    """the validated distributed suite once more with the opt-in peer-memory data paths switched on: SUMMA panels and Cannon
+    shifts by copy engines into CUDA-IPC windows (transport.cu), and on 8 GPUs the fused GEMM + depth all-reduce on the
+    2x2x2 grid.  Both pass on the CPU simulator; this is their first contact with hardware."""
+    if _ngpu() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    env = dict(os.environ, CANDMC_TEST_PANEL_TRANSPORT="1", CANDMC_TEST_FUSED_GRIDS="1" if nproc == 8 else "0")
+    env.setdefault("NCCL_DEBUG", "WARN")
+    worker = os.path.join(HERE, "dist_worker.py")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29620 + nproc), worker]
+    rc, so, se = run_guarded("peer_paths", cmd, 400, ROOT, env=env)
+    assert rc == 0, so[-3000:] + se[-3000:]
+    out = json.loads([l for l in so.splitlines() if l.startswith("{")][-1])
+    assert out["failed_all_ranks"] == 0 and out["checks_rank0"] > 0
+    if nproc >= 4:
+        assert out["panel_transport_sends_rank0"] > 0, "the transport fell back to NCCL (peer windows or stream memory operations unavailable)"

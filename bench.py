@@ -176,6 +176,10 @@ def main():
                     help="SUMMA panels by copy engines into peer windows instead of ncclBroadcast (experimental)")
     ap.add_argument("--b-first-chunk-early", action="store_true",
                     help="e2e leg on grids: upload the first k-chunk of B ahead of the rest (experimental)")
+    ap.add_argument("--single-e2e-pass", action="store_true",
+                    help="e2e leg: only the library's current defaults, no first pass with the GPU-validated settings")
+    ap.add_argument("--e2e-watchdog", type=float, default=180.0,
+                    help="seconds the second end-to-end pass may take before the line is printed without it")
     ap.add_argument("--host-panels", type=int, default=None,
                     help="e2e leg on one GPU: column panels of the host-streamed multiply (default: 16 at n >= 32768, else 8)")
     args = ap.parse_args()
@@ -294,13 +298,25 @@ def main():
         del fa, fb, ref
 
     # ---- end-to-end leg: pinned host buffers through the same C-ABI call ----
+    # Two passes unless the command line pins the knobs: first the host-operand settings B200s have already run (8 panels
+    # on one GPU, both blocks uploaded, one C download after the last multiply), then the library's current defaults
+    # (validated on the CPU simulator only so far) under a watchdog.  The faster VALID pass is reported as `e2e`,
+    # both are listed in `e2e_passes`; should the second pass hang, the watchdog prints the line with the first pass and
+    # ends the process instead of losing the whole measurement.
     e2e = None
-    if not args.no_e2e:
-        hA = torch.empty(b * b, dtype=torch.float64, pin_memory=True)
-        hB = torch.empty(b * b, dtype=torch.float64, pin_memory=True)
-        hC = torch.empty(b * b, dtype=torch.float64, pin_memory=True)
-        hA.copy_(dA); hB.copy_(dB)
-        torch.cuda.synchronize()
+    e2e_passes = []
+    pinned_knobs = args.upload_all_blocks or args.late_c_download or args.host_panels is not None
+    passes = [("as_requested", None)] if (pinned_knobs or args.single_e2e_pass) else [
+        ("gpu_validated", {"skip_unused_uploads": 0, "early_c_download": 0, "host_pipeline_panels": 8}),
+        ("library_defaults", {"skip_unused_uploads": 1, "early_c_download": 1, "host_pipeline_panels": 0})]
+
+    def e2e_pass(name, knobs):
+        upload_all = args.upload_all_blocks
+        if knobs is not None:
+            cb.lib().candmc_set_skip_unused_uploads(knobs["skip_unused_uploads"])
+            cb.lib().candmc_set_early_c_download(knobs["early_c_download"])
+            cb.lib().candmc_set_host_pipeline_panels(knobs["host_pipeline_panels"])
+            upload_all = not knobs["skip_unused_uploads"]
         e2e_steps = max(1, min(args.steps, 2))
         step(hA, hB, hC)   # warm-up (allocations, page faults)
         barrier()
@@ -316,11 +332,12 @@ def main():
         d2, r2 = cb.frob_diff(chk, b, dC, b, b, b)
         e2e_rel = max_over_ranks((d2 / r2) ** 0.5)
         del chk
+        hC.zero_()   # the next pass must not pass on this one's result
         # bytes this rank's call really moves: a 1x1xc grid uploads only its k-slice of A and B, a q x q x c grid both of
         # its blocks; every rank downloads its C block
         if ksplit:
             my_h2d = 2 * b * (b // c) * 8
-        elif args.upload_all_blocks:
+        elif upload_all:
             my_h2d = 2 * b * b * 8
         else:   # a layer multiplies panels [layer*q/c, (layer+1)*q/c): my A block travels only if my column is one of them, B: my row
             lo, hi = g["layer"] * (q // c), (g["layer"] + 1) * (q // c)
@@ -328,12 +345,23 @@ def main():
         tot = torch.tensor([float(my_h2d), float(b * b * 8)], dtype=torch.float64, device="cuda")
         if world_size > 1:
             dist.all_reduce(tot)
-        e2e = {"value": 2.0 * n ** 3 / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(tot[0].item()),
-               "d2h_bytes_per_step": int(tot[1].item()), "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "rel_frobenius_vs_device_path": e2e_rel, "valid": bool(e2e_rel <= 10 * n * 2.220446049250313e-16),
-               "path": "candmc_d25_summa (C ABI) with pinned host mat_A/mat_B/mat_C; operands are uploaded in k-chunks "
-                       "under the running multiply, C is downloaded at the end"}
-        del hA, hB, hC
+        return {"value": 2.0 * n ** 3 / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(tot[0].item()),
+                "d2h_bytes_per_step": int(tot[1].item()), "ms_per_step": dt * 1e3, "steps": e2e_steps,
+                "rel_frobenius_vs_device_path": e2e_rel, "valid": bool(e2e_rel <= 10 * n * 2.220446049250313e-16),
+                "host_operand_settings": name,
+                "path": "candmc_d25_summa (C ABI) with pinned host mat_A/mat_B/mat_C; operands are uploaded in k-chunks "
+                        "under the running multiply" + (", C leaves slab-wise under the last multiplies"
+                                                        if (knobs or {}).get("early_c_download", not args.late_c_download)
+                                                        else ", C is downloaded at the end")}
+
+    if not args.no_e2e:
+        hA = torch.empty(b * b, dtype=torch.float64, pin_memory=True)
+        hB = torch.empty(b * b, dtype=torch.float64, pin_memory=True)
+        hC = torch.empty(b * b, dtype=torch.float64, pin_memory=True)
+        hA.copy_(dA); hB.copy_(dB)
+        torch.cuda.synchronize()
+        e2e = e2e_pass(*passes[0])
+        e2e_passes.append(e2e)
 
     if rank == 0:
         achieved = (tfl.value / 1e12) / (tms.value / 1e3) if tms.value > 0 else None
@@ -370,7 +398,40 @@ def main():
         if world_size == 1 and not args.no_cpu_baseline:
             v, info = reference_cpu_run(3, 1)
             line["cpu_baseline"] = dict(info, value=v, unit="TFLOP/s")
+    else:
+        line = None
+
+    # second end-to-end pass (library defaults) under the watchdog; every rank arms its own
+    if e2e is not None and len(passes) > 1:
+        barrier()   # rank 0 may have spent a while in the CPU baseline
+
+        def expired():
+            if rank == 0:
+                line["e2e_passes"] = e2e_passes + [{"host_operand_settings": passes[1][0], "valid": False,
+                                                    "error": f"no result within {args.e2e_watchdog} s; process ended by the watchdog"}]
+                emit(line)
+            os._exit(0)
+
+        dog = threading.Timer(args.e2e_watchdog, expired)
+        dog.daemon = True
+        dog.start()
+        try:
+            second = e2e_pass(*passes[1])
+        except Exception as exc:   # a loud error of the new path must not cost the measured line either
+            second = {"host_operand_settings": passes[1][0], "valid": False, "error": str(exc)[:300]}
+        dog.cancel()
+        e2e_passes.append(second)
+        if second.get("valid") and (not e2e["valid"] or second["value"] > e2e["value"]):
+            e2e = second
+    if e2e is not None:
+        del hA, hB, hC
+    if rank == 0:
+        line["e2e"] = e2e
+        if len(e2e_passes) > 1:
+            line["e2e_passes"] = e2e_passes
         emit(line)
+    if any("error" in p for p in e2e_passes):
+        os._exit(0)   # the line is out; do not tear down communicators a failed pass may have left mid-collective
     for k in ("cdt_row", "cdt_col", "cdt_kdir"):
         g[k].free()
     world.free()

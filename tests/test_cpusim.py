@@ -85,6 +85,9 @@ for _n in (1, 8):
     _job(f"bench{_n}", _torchrun(_n, 29790 + _n, os.path.join(SIM, "run_sim.py"), "bench.py", "--gpus", str(_n), "--steps", "1",
                                  "--warmup", "1", "--no-cpu-baseline"), CPUSIM_ARGS="--n 512", CPUSIM_SCHED="sync" if _n == 1 else "lifo")
 
+_job("bench_watchdog", _torchrun(2, 29795, os.path.join(SIM, "run_sim.py"), "bench.py", "--gpus", "2", "--steps", "1", "--warmup", "1",
+                                 "--no-cpu-baseline", "--e2e-watchdog", "0.0005"), CPUSIM_ARGS="--n 512", CPUSIM_SCHED="sync")
+
 # randomised cases (tests/fuzz_worker.py: random grids, sizes, paddings, roots, transposes, host/device operands, knobs)
 FUZZ = [(4, 3, "lifo")] + ([(p, sd, pol) for p in (1, 2, 4, 6, 8, 9, 16) for sd, pol in ((11, "sync"), (12, "lifo"), (13, "random:13"))]
                            if FULL else [])
@@ -266,8 +269,27 @@ def test_bench_script_logic_on_the_simulator(nproc):
     assert d["rel_frobenius_vs_cublas_crosscheck"] <= d["tolerance_10_n_eps"]
     assert d["e2e"]["valid"] and d["e2e"]["rel_frobenius_vs_device_path"] <= d["tolerance_10_n_eps"]
     b = d["config"]["block"]
-    assert d["e2e"]["d2h_bytes_per_step"] == nproc * b * b * 8
-    assert d["e2e"]["h2d_bytes_per_step"] == (2 if nproc == 1 else 8) * b * b * 8
+    # two end-to-end passes: the host-operand settings B200s have run, then the library's defaults; `e2e` is one of them
+    first, second = d["e2e_passes"]
+    assert (first["host_operand_settings"], second["host_operand_settings"]) == ("gpu_validated", "library_defaults")
+    assert d["e2e"] in (first, second)
+    for p_ in (first, second):
+        assert p_["valid"] and p_["rel_frobenius_vs_device_path"] <= d["tolerance_10_n_eps"]
+        assert p_["d2h_bytes_per_step"] == nproc * b * b * 8
+    assert first["h2d_bytes_per_step"] == 2 * nproc * b * b * 8
+    assert second["h2d_bytes_per_step"] == (2 if nproc == 1 else 8) * b * b * 8
+
+
+def test_bench_watchdog_keeps_the_line_when_the_second_pass_does_not_return():
+    """--e2e-watchdog: a second end-to-end pass that does not come back in time must not cost the measurement — the line is
+    printed with the first pass and the process ends with status 0"""
+    rc, so, se = RESULTS["bench_watchdog"]
+    assert rc == 0, so[-2000:] + se[-3000:]
+    lines = [line for line in so.splitlines() if line.startswith('{"metric"')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["e2e"]["valid"] and d["e2e"]["host_operand_settings"] == "gpu_validated" and d["value"] > 0
+    assert "watchdog" in d["e2e_passes"][1]["error"]
 
 
 @pytest.mark.parametrize("nproc", [4, 8])

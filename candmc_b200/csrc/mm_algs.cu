@@ -1053,6 +1053,20 @@ __global__ void tril_halve_diag_kernel(const double* __restrict__ S, double* __r
   }
 }
 
+// comp_bcast_T_from_W on the root rank (qr_2d.cxx:189-195): L = W^T as a lower-triangular b x b matrix (W is the panel QR's
+// upper-triangular factor, its strict lower triangle is never read), X0 = -Y1 (top b x b of the packed panel); the
+// triangular solve L X = X0 that follows is compute_invT_from_W's cdtrsm('L','U','T','N', alpha = -1) (hh_recon.cxx:26-31)
+__global__ void t_from_w_setup_kernel(const double* __restrict__ W, const double* __restrict__ Ybuf, int64_t ldy,
+                                      double* __restrict__ L, double* __restrict__ X, int64_t b) {
+  const int64_t total = b * b;
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t j = e / b, i = e - j * b;
+    L[e] = (i >= j) ? W[j + i * b] : 0.0;
+    X[e] = (i >= j) ? -Ybuf[i + j * ldy] : 0.0;   // Y1 is unit lower-triangular (copy_lower + 1.0, :157-163)
+  }
+}
+
 int upd_A_impl(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
                const double* T, candmc_comm* ccol, double* W, cudaStream_t st) {
   if (kb == 0) return OK;
@@ -1139,12 +1153,17 @@ int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, in
   g_events.reset();
   CANDMC_CHECK(pv != nullptr && pv->crow != nullptr && pv->ccol != nullptr, "update_A: null processor view");
   CANDMC_CHECK(b > 0 && m >= 0 && k >= 0 && m % b == 0 && k % b == 0, "update_A: m and k must be multiples of b");
-  CANDMC_CHECK(W == nullptr || W_is_T, "update_A: only W == NULL (T from Y) and W_is_T are implemented on the device");
-  CANDMC_CHECK(is_device_ptr(Y) && is_device_ptr(A) && is_device_ptr(W) && is_device_ptr(aggreg_Y),
-               "update_A: operands must be device pointers");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nprow = pv->ccol->size, npcol = pv->crow->size, myrow = pv->ccol->rank, mycol = pv->crow->rank;
   CANDMC_CHECK(pv->rrow >= 0 && pv->rrow < nprow && pv->rcol >= 0 && pv->rcol < npcol, "update_A: bad root row/col");
+  // three forms, chosen by the same (W == NULL, W_is_T) on every rank: T from Y, W is T, or W is the panel QR's factor, which
+  // only the root rank reads (upd_A :244-253) — the other ranks may hand in any non-null pointer, as QR_2D does (:309,325)
+  const bool t_from_w = (W != nullptr && !W_is_T);
+  const bool w_root = t_from_w && myrow == pv->rrow && mycol == pv->rcol;
+  CANDMC_CHECK(is_device_ptr(Y) && is_device_ptr(A) && is_device_ptr(aggreg_Y) && ((t_from_w && !w_root) || is_device_ptr(W)),
+               "update_A: operands must be device pointers");
+  CANDMC_CHECK(!t_from_w || m >= b, "update_A: the panel factor form needs at least b rows (m=%lld, b=%lld)", (long long)m,
+               (long long)b);
   // block-cyclic local extents of the remaining matrix, qr_2d.cxx:140-147
   int64_t mb = (m / b) / nprow;
   if ((myrow + nprow - pv->rrow) % nprow < (m / b) % nprow) mb++;
@@ -1177,6 +1196,20 @@ int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, in
     tril_halve_diag_kernel<<<static_cast<int>((b * b + 255) / 256), 256, 0, st>>>(S, T, b);
     CANDMC_CUDA(cudaGetLastError());
     runtime().launches++;
+    Tuse = T;
+  } else if (t_from_w) {
+    // comp_bcast_T_from_W (:179-208): the root rank solves W^T X = -Y1 and every rank receives X's lower triangle.  The
+    // reference broadcasts over cworld from rank rcol + rrow*npcol (:250), which is the root only when that numbering matches
+    // the grid's (its own drivers number rank = myrow + mycol*nprow); here T travels along the root's grid row and then down
+    // every grid column, which needs no assumption about the world numbering.
+    if (w_root) {
+      t_from_w_setup_kernel<<<static_cast<int>((b * b + 255) / 256), 256, 0, st>>>(W, Ybuf, mb, S, T, b);
+      CANDMC_CUDA(cudaGetLastError());
+      runtime().launches++;
+      CANDMC_TRY(trsm_llnn(b, b, S, b, T, b, st));
+    }
+    if (myrow == pv->rrow && npcol > 1) CANDMC_TRY(comm_bcast(pv->crow, T, T, b * b, pv->rcol, st));
+    if (nprow > 1) CANDMC_TRY(comm_bcast(pv->ccol, T, T, b * b, pv->rrow, st));
     Tuse = T;
   }
   CANDMC_TRY(upd_A_impl(Ybuf, mb, A, lda_A, mb, kb, b, Tuse, pv->ccol, Wbuf, st));

@@ -17,6 +17,9 @@
 /* trailing update of the symmetric full -> band reduction (the GPU half of alg/SE/full_to_band.cxx's sym_full2band) */
 #include "candmc/full_to_band.h"
 
+/* CAQR trailing-matrix updates (the GPU half of alg/QR/qr_2d: update_A / upd_A / update_Yamamoto_A / upd_Yamamoto_A) */
+#include "candmc/qr_2d.h"
+
 /* local multiply + packing */
 #include "candmc/lapack.h"
 #include "candmc/util.h"

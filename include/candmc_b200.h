@@ -191,8 +191,11 @@ typedef struct candmc_pview {
 /* (I - Y T^-1 Y^T) A on a block-cyclic nprow x npcol grid.  Replaces update_A (alg/QR/qr_2d/qr_2d.cxx:124-177): local
  * extents by the block-cyclic formulas (:140-147), Y panel packed with zeroed upper triangle and unit diagonal on the root
  * row (:155-165), MPI_Bcast along the grid row (:168), then upd_A (:224-282); with W == NULL the triangular factor is formed
- * from Y (compute_invT_from_Y, :22-60), with W_is_T != 0 W is the b x b lower-triangular T.  (The third form, W = Y1^T T from
- * the panel factorisation, is not implemented.)  aggreg_Y may be NULL.  All matrix operands are device pointers. */
+ * from Y (compute_invT_from_Y, :22-60), with W_is_T != 0 W is the b x b lower-triangular T, and with W != NULL, W_is_T == 0
+ * (what QR_2D hands in, :325) W is the b x b upper-triangular factor of the panel QR, read on the root rank (rrow, rcol)
+ * only: T = lower(-W^-T Y1) as comp_bcast_T_from_W forms it (:179-208; alg/QR/hh_recon/hh_recon.cxx:26-31), delivered to
+ * every rank along the root's grid row and then down the grid columns (pv->cworld is not used).  The three forms must be
+ * chosen alike on every rank.  aggreg_Y may be NULL.  All matrix operands are device pointers. */
 int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
                     const double* W, const candmc_pview_t* pv, double* aggreg_Y, int64_t lda_aY, int W_is_T,
                     void* stream);

@@ -437,10 +437,28 @@ int oracle_update_A(int nprow, int npcol, int rrow, int rcol, int64_t m, int64_t
         Ybuf[pr][r + j * mb] = v;
       }
   }
-  /* T: mode 1 -> W; mode 0 -> lower triangle of sum_rows Ybuf^T Ybuf with halved diagonal (:36-50), rest zero (:235) */
+  /* T: mode 1 -> W; mode 0 -> lower triangle of sum_rows Ybuf^T Ybuf with halved diagonal (:36-50), rest zero (:235);
+   * mode 2 -> W is the b x b UPPER-triangular factor the panel QR left on the root rank (hh_recon_qr, what QR_2D :325 hands
+   * in with W_is_T == false): the root solves W^T X = -Y1 (comp_bcast_T_from_W :193-195, compute_invT_from_W,
+   * alg/QR/hh_recon/hh_recon.cxx:26-31: cdtrsm('L','U','T','N', alpha = -1)), Y1 = the top b x b of its Ybuf, and every rank
+   * receives the lower triangle of X with its diagonal (pack_lower / MPI_Bcast / unpack_lower into zeros, :198-205) */
   double* T = dalloc((size_t)(b * b));
   if (mode == 1) {
     memcpy(T, W, sizeof(double) * (size_t)(b * b));
+  } else if (mode == 2) {
+    if (mbs[rrow] < b) return -1;
+    const double* Y1 = Ybuf[rrow];
+    const int64_t ldy = mbs[rrow];
+    double* X = dalloc((size_t)(b * b));
+    for (int64_t j = 0; j < b; ++j)
+      for (int64_t i = 0; i < b; ++i) { /* forward substitution with the lower-triangular W^T: (W^T)(i,p) = W(p,i) */
+        double x = -Y1[i + j * ldy];
+        for (int64_t p = 0; p < i; ++p) x -= W[p + i * b] * X[p + j * b];
+        X[i + j * b] = x / W[i + i * b];
+      }
+    for (int64_t j = 0; j < b; ++j)
+      for (int64_t i = j; i < b; ++i) T[i + j * b] = X[i + j * b];
+    free(X);
   } else {
     double* S = dalloc((size_t)(b * b));
     for (int pr = 0; pr < nprow; ++pr)

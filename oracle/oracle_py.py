@@ -225,13 +225,25 @@ def update_A_blocks(nprow, npcol, rrow, rcol, m, k, b):
     return Y, A
 
 
-def update_A(nprow, npcol, rrow, rcol, m, k, b, Y, A, W=None):
-    """All ranks simulated; A blocks are updated in place.  W None -> T from Y; otherwise W is the lower-triangular T."""
+def update_A(nprow, npcol, rrow, rcol, m, k, b, Y, A, W=None, W_is_T=True):
+    """All ranks simulated; A blocks are updated in place.  W None -> T from Y; W_is_T -> W is the lower-triangular T;
+    otherwise W is the upper-triangular factor of the panel QR and T comes from comp_bcast_T_from_W (qr_2d.cxx:179-208)."""
     Yp = [y if y.size else np.zeros(1) for y in Y]
     Ap = [a if a.size else np.zeros(1) for a in A]
     rc = lib().oracle_update_A(nprow, npcol, rrow, rcol, m, k, b, _pp(Yp), _pp(Ap),
-                               _p(W) if W is not None else None, 0 if W is None else 1, None, None)
+                               _p(W) if W is not None else None, 0 if W is None else (1 if W_is_T else 2), None, None)
     assert rc == 0, "oracle_update_A: bad arguments"
+
+
+def panel_W(b):
+    """The b x b upper-triangular W of oracle/ref_dump.cxx's `updw` mode (diagonal in [1, 1.5), small off-diagonal entries;
+    the strict lower triangle is never read: cdtrsm('L','U',...))."""
+    W = np.zeros((b, b), order="F")
+    for j in range(b):
+        for i in range(j + 1):
+            v = _lcg48(333000 + i + j * b)
+            W[i, j] = 1.0 + 0.5 * v if i == j else (v - .5) * 0.2
+    return W
 
 
 def yamamoto_T(b):

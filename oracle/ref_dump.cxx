@@ -8,6 +8,8 @@
 //   ref_dump summa <n> <prefix>                         summa                      (grid + data: :349-486, ctb_unit)
 //   ref_dump dcn   <n> <x2_np> <ovp> <prefix>           bcast_cannon_4d            (grid + data: :13-175, dcn_unit); x2_np must be 1
 //   ref_dump upda  <m> <k> <b> <nprow> <rrow> <rcol> <prefix>   update_A, W == NULL (alg/QR/qr_2d/qr_2d.cxx:124-177)
+//   ref_dump updw  <m> <k> <b> <nprow> <rrow> <rcol> <prefix>   update_A, W = the panel QR's upper-triangular factor, W_is_T == false
+//                                                                (what QR_2D hands in, qr_2d.cxx:325; T by comp_bcast_T_from_W :179-208)
 //   ref_dump updy  <m> <k> <b> <nprow> <rrow> <rcol> <prefix>   update_Yamamoto_A, agg == NULL (alg/QR/qr_2d/qr_y2d.cxx:68-120)
 //   ref_dump spc   <bidir> <ndim> <seed> <n> <m> <k> <alpha> <beta> <tB N|T> <prefix>   kput_cannon / kuni_cannon (test/MM/test_spc.cxx:36-114)
 #include <assert.h>
@@ -176,8 +178,12 @@ static int run_spc(int rank, int numPes, int bidir, int ndim, int seed, int n, i
 // Grid and block-cyclic layout as in test/QR/test_qr_2d.cxx:60-94,367-374: myrow = rank % nprow, mycol = rank / nprow.
 // Local row block lb of the remaining matrix is global block lb*nprow + (myrow - rrow) mod nprow; trailing column block lb
 // is global block lb*npcol + (mycol - rcol - 1) mod npcol.  Elements are seeded by their global coordinates.
+// with_W: the third form — W is the b x b upper-triangular factor on the root rank only (every other rank gets a poisoned
+// buffer: upd_A reads W on the root alone, :250), W_is_T == false.  NB upd_A names the broadcast root rcol + rrow*npcol
+// (:250) while the grid of the reference's own driver is rank = myrow + mycol*nprow (test/QR/test_qr_2d.cxx:367-374): the two
+// agree only where rrow == rcol on square grids, on the zero root and on one-dimensional grids, so fixtures use those.
 static int run_upda(int myRank, int numPes, int64_t m, int64_t k, int64_t b, int nprow, int rrow, int rcol,
-                    const char* prefix) {
+                    const char* prefix, bool with_W = false) {
   const int npcol = numPes / nprow;
   if (nprow * npcol != numPes || m % b || k % b) return 2;
   const int myrow = myRank % nprow, mycol = myRank / nprow;
@@ -208,7 +214,20 @@ static int run_upda(int myRank, int numPes, int64_t m, int64_t k, int64_t b, int
       srand48(900000 + gc * m + gr);
       A[r + cc * mb] = drand48() - .5;
     }
-  update_A(Y, mb, A, mb, m, k, b, NULL, &pv, NULL, 0);
+  if (with_W) {
+    if (rcol + rrow * npcol != rrow + rcol * nprow) return 2;
+    double* W = alloc_d((size_t)b * b);
+    const bool root = (myrow == rrow && mycol == rcol);
+    for (int64_t j = 0; j < b; j++)
+      for (int64_t i = 0; i < b; i++) {
+        srand48(333000 + i + j * b);
+        const double v = drand48();
+        W[i + j * b] = !root ? 77.0 : (i > j ? -55.0 : (i == j ? 1.0 + 0.5 * v : (v - .5) * 0.2));
+      }
+    update_A(Y, mb, A, mb, m, k, b, W, &pv, NULL, 0, false);
+  } else {
+    update_A(Y, mb, A, mb, m, k, b, NULL, &pv, NULL, 0);
+  }
   dump(prefix, myRank, A, (size_t)mb * kb);
   return 0;
 }
@@ -276,6 +295,9 @@ int main(int argc, char** argv) {
   else if (argc >= 9 && !strcmp(argv[1], "upda"))
     rc = run_upda(myRank, numPes, atoll(argv[2]), atoll(argv[3]), atoll(argv[4]), atoi(argv[5]), atoi(argv[6]),
                   atoi(argv[7]), argv[8]);
+  else if (argc >= 9 && !strcmp(argv[1], "updw"))
+    rc = run_upda(myRank, numPes, atoll(argv[2]), atoll(argv[3]), atoll(argv[4]), atoi(argv[5]), atoi(argv[6]),
+                  atoi(argv[7]), argv[8], true);
   else if (argc >= 9 && !strcmp(argv[1], "updy"))
     rc = run_updy(myRank, numPes, atoll(argv[2]), atoll(argv[3]), atoll(argv[4]), atoi(argv[5]), atoi(argv[6]),
                   atoi(argv[7]), argv[8]);

@@ -207,7 +207,7 @@ def case_upd_A(world, name, mb, kb, b):
     return record(f"{name}:oracle", rel_frob(got, A[world.rank]), 10 * mb * P * EPS)
 
 
-def case_update_A(world, golden, name, m, k, b, nprow, rrow, rcol, with_T=False):
+def case_update_A(world, golden, name, m, k, b, nprow, rrow, rcol, with_T=False, with_W=False):
     """update_A on a block-cyclic nprow x npcol grid with rotated roots, vs the reference's own outputs
     (tests/golden, W == NULL) and the oracle.  rank = myrow + mycol*nprow (test/QR/test_qr_2d.cxx:367-374)."""
     P = world.np
@@ -228,11 +228,16 @@ def case_update_A(world, golden, name, m, k, b, nprow, rrow, rcol, with_T=False)
     if with_T:   # W_is_T: a well-conditioned lower-triangular T handed in by the caller
         Wnp = np.asfortranarray(np.eye(b) + 0.01 * np.tril(np.random.default_rng(9).random((b, b))))
         W = dev(Wnp)
+    if with_W:   # the form QR_2D uses (qr_2d.cxx:325): the panel QR's upper-triangular factor, read on the root rank only —
+        # the others hand in a poisoned buffer, and the root's strict lower triangle is poison too (cdtrsm 'U' never reads it)
+        Wnp = orc.panel_W(b)
+        Wd = Wnp + np.tril(np.full((b, b), np.nan), -1) if (myrow == rrow and mycol == rcol) else np.full((b, b), np.nan)
+        W = dev(np.asfortranarray(Wd))
     pv = cb.pview(rrow, rcol, crow, ccol, world)
     cb.update_A(dY, lda_Y, dA, lda_A, m, k, b, W, pv, aggreg_Y=agg, lda_aY=max(mb, 1), W_is_T=with_T)
     torch.cuda.synchronize()
     got = host(dA, mb, kb) if (mb and kb) else np.zeros((mb, kb))
-    orc.update_A(nprow, npcol, rrow, rcol, m, k, b, Y, A, Wnp)
+    orc.update_A(nprow, npcol, rrow, rcol, m, k, b, Y, A, Wnp, W_is_T=not with_W)
     ok = True
     if mb and kb:
         ok &= record(f"{name}:oracle", rel_frob(got, A[world.rank]), 10 * m * EPS)
@@ -445,6 +450,21 @@ def pending_cases(world, golden):
         case_update_Yamamoto_A(world, golden, "updy_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 0, 0)
         case_update_Yamamoto_A(world, golden, "updy_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 2, 0)
         case_update_Yamamoto_A(world, golden, "updy_big_2x2_r11", 1024, 768, 64, 2, 1, 1)
+    # update_A with the panel QR's factor W (comp_bcast_T_from_W): fixtures are the reference's own outputs; the rotated roots of
+    # the last cases have no fixture (the reference names the wrong broadcast root there, oracle/ref_dump.cxx) — oracle only
+    if P == 1:
+        case_update_A(world, golden, "updw_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0, with_W=True)
+        case_update_A(world, golden, "updw_big_1x1", 1024, 512, 128, 1, 0, 0, with_W=True)
+    if P == 3:
+        case_update_A(world, golden, "updw_m48_k72_b8_1x3_r02", 48, 72, 8, 1, 0, 2, with_W=True)
+    if P == 4:
+        case_update_A(world, golden, "updw_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 0, 0, with_W=True)
+        case_update_A(world, golden, "updw_m96_k64_b8_2x2_r11", 96, 64, 8, 2, 1, 1, with_W=True)
+        case_update_A(world, golden, "updw_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 2, 0, with_W=True)
+        case_update_A(world, golden, "updw_big_2x2_r10", 1024, 768, 64, 2, 1, 0, with_W=True)
+    if P == 6:
+        case_update_A(world, golden, "updw_m80_k48_b8_2x3_r00", 80, 48, 8, 2, 0, 0, with_W=True)
+        case_update_A(world, golden, "updw_m80_k48_b8_2x3_r12", 80, 48, 8, 2, 1, 2, with_W=True)
     from dmat_cases import case_names, load_golden
     dgold = load_golden()
     for name in case_names(dgold):

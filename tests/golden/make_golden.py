@@ -47,6 +47,14 @@ CASES = {
     "upda_m80_k48_b8_2x3_r12": (6, ["upda", "80", "48", "8", "2", "1", "2"], None),
     "upda_m64_k32_b16_1x1": (1, ["upda", "64", "32", "16", "1", "0", "0"], None),
     "upda_m72_k40_b8_4x1_r20": (4, ["upda", "72", "40", "8", "4", "2", "0"], None),
+    # update_A with the panel QR's upper-triangular W, W_is_T == false (the form QR_2D itself uses, qr_2d.cxx:325; T by
+    # comp_bcast_T_from_W :179-208).  Roots where the reference's broadcast-root formula (:250) matches its drivers' grid.
+    "updw_m96_k64_b8_2x2_r00": (4, ["updw", "96", "64", "8", "2", "0", "0"], None),
+    "updw_m96_k64_b8_2x2_r11": (4, ["updw", "96", "64", "8", "2", "1", "1"], None),
+    "updw_m80_k48_b8_2x3_r00": (6, ["updw", "80", "48", "8", "2", "0", "0"], None),
+    "updw_m64_k32_b16_1x1": (1, ["updw", "64", "32", "16", "1", "0", "0"], None),
+    "updw_m72_k40_b8_4x1_r20": (4, ["updw", "72", "40", "8", "4", "2", "0"], None),
+    "updw_m48_k72_b8_1x3_r02": (3, ["updw", "48", "72", "8", "1", "0", "2"], None),
     # update_Yamamoto_A (agg == NULL, alg/QR/qr_2d/qr_y2d.cxx:68-120): updy <m> <k> <b> <nprow> <rrow> <rcol>
     "updy_m96_k64_b8_2x2_r00": (4, ["updy", "96", "64", "8", "2", "0", "0"], None),
     "updy_m80_k48_b8_2x3_r12": (6, ["updy", "80", "48", "8", "2", "1", "2"], None),

@@ -122,6 +122,13 @@ void use(pview* pv, double* A, double* Y, double* B) {
   sym_full2band_update(A, 64, 128, 32, 8, pv, Y, 48);
   cyclic_to_blocked(64, 64, 8, A, 32, B, 32, pv);
   blocked_to_cyclic(64, 64, 8, B, 32, A, 32, pv);
+  // CAQR trailing updates under the reference's names and argument lists (alg/QR/qr_2d/qr_2d.h:74-108, qr_y2d.h:59-93)
+  update_A(Y, 64, A, 64, 128, 96, 16, B, pv, NULL, 0);              // W = the panel QR's factor (QR_2D's own call, qr_2d.cxx:325)
+  update_A(Y, 64, A, 64, 128, 96, 16, NULL, pv, B, 64);             // T from Y, panel saved into aggreg_Y
+  update_A(Y, 64, A, 64, 128, 96, 16, B, pv, NULL, 0, true);        // W is T
+  upd_A(Y, 64, A, 64, 64, 48, 16, B, pv, true);
+  update_Yamamoto_A(Y, 64, A, 64, 128, 96, 16, B, pv, NULL);
+  upd_Yamamoto_A(Y, 64, A, 64, 64, 48, 16, B, pv);
 }
 """)
     inc = os.path.join(ROOT, "include")

@@ -46,7 +46,7 @@ def _torchrun(nproc, port, script, *args):
 
 
 DIST_MAIN = [1, 2, 4, 8] if FULL else [2, 4, 8]
-DIST_PENDING = [1, 2, 4, 6, 8, 9, 16] if FULL else [1, 4, 9]
+DIST_PENDING = [1, 2, 3, 4, 6, 8, 9, 16] if FULL else [1, 3, 4, 6, 9]
 GOLD = np.load(os.path.join(HERE, "golden", "lu_offload_ref_outputs.npz"))
 SCRIPTS = sorted(k[: -len("__script")] for k in GOLD.files if k.endswith("__script"))
 REDIST = [(24, 36, 2, 2, 3, 0, 0), (36, 24, 3, 3, 2, 1, 1), (30, 30, 5, 3, 3, 0, 2), (16, 16, 4, 1, 4, 0, 3), (512, 256, 32, 2, 2, 1, 0)]
@@ -175,7 +175,8 @@ def test_validated_distributed_suite_on_the_simulator(nproc):
 
 @pytest.mark.parametrize("nproc", DIST_PENDING)
 def test_widening_rows_on_the_simulator(nproc):
-    """update_Yamamoto_A, the DMatrix pack operations (bit-exact against the unmodified dmatrix.cxx) and
+    """update_Yamamoto_A, update_A with the panel QR's factor W (comp_bcast_T_from_W: the form QR_2D uses; 1x1, 1x3, 2x2, 4x1,
+    2x3 grids, poisoned W everywhere but on the root), the DMatrix pack operations (bit-exact against the unmodified dmatrix.cxx) and
     candmc_redistribute over the simulated NCCL on 1x1, 2x2, 4x1, 1x4, 2x3, ... grids"""
     _dist(f"pending{nproc}")
 

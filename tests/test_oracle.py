@@ -190,6 +190,24 @@ def test_oracle_update_A_matches_reference(golden, name, m, k, b, nprow, npcol, 
             assert rel_frob(A[r], ref) <= 10 * m * EPS, (name, r)
 
 
+UPDW = [("updw_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 2, 0, 0), ("updw_m96_k64_b8_2x2_r11", 96, 64, 8, 2, 2, 1, 1),
+        ("updw_m80_k48_b8_2x3_r00", 80, 48, 8, 2, 3, 0, 0), ("updw_m64_k32_b16_1x1", 64, 32, 16, 1, 1, 0, 0),
+        ("updw_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 1, 2, 0), ("updw_m48_k72_b8_1x3_r02", 48, 72, 8, 1, 3, 0, 2)]
+
+
+@pytest.mark.parametrize("name,m,k,b,nprow,npcol,rrow,rcol", UPDW)
+def test_oracle_update_A_with_panel_W_matches_reference(golden, name, m, k, b, nprow, npcol, rrow, rcol):
+    """SURVEY §8f N1, the form QR_2D itself uses (qr_2d.cxx:325): W is the panel QR's upper-triangular factor on the root rank,
+    W_is_T == false, T = lower(-W^-T Y1) by comp_bcast_T_from_W (:179-208).  Fixture: the reference's own update_A."""
+    Y, A = orc.update_A_blocks(nprow, npcol, rrow, rcol, m, k, b)
+    orc.update_A(nprow, npcol, rrow, rcol, m, k, b, Y, A, orc.panel_W(b), W_is_T=False)
+    for r in range(nprow * npcol):
+        ref = golden[f"{name}.r{r}"]
+        assert A[r].size == ref.size, (name, r)
+        if ref.size:
+            assert rel_frob(A[r], ref) <= 10 * m * EPS, (name, r)
+
+
 UPDY = [("updy_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 2, 0, 0), ("updy_m80_k48_b8_2x3_r12", 80, 48, 8, 2, 3, 1, 2),
         ("updy_m64_k32_b16_1x1", 64, 32, 16, 1, 1, 0, 0), ("updy_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 1, 2, 0)]
 

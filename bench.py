@@ -30,6 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 _REAL_STDOUT = 1
+_FULL_AFFINITY = None   # the process's CPU set before bind_to_gpu_numa_node narrowed it
 N_GLOBAL = 32768
 METRIC = "FP64 TFLOP/s, 2.5D MM n=32768 (strong scaling over 1/2/4/8 B200)"
 # FP64 tensor (DMMA) peak: 148 SMs x 4 sub-partitions x 16 FMA/clk x 2 flop x 1.965 GHz (clocks.max.sm).  MEASURED_PEAKS.json
@@ -91,6 +92,32 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(props):
+    """Keep this rank's threads — and with them the first touch of its pinned host blocks — on the CPUs next to its GPU
+    (sysfs local_cpulist of the GPU's PCI function), as `mpirun --bind-to numa` would for the reference's ranks.  Matters
+    for the end-to-end leg at N > 1, where every rank streams GiB-sized blocks over its own PCIe link at the same time.
+    Best effort: returns a short description, or None when the box gives no usable topology (single node, no sysfs)."""
+    try:
+        dev = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{dev}/local_cpulist") as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        global _FULL_AFFINITY
+        allowed = os.sched_getaffinity(0)
+        _FULL_AFFINITY = set(allowed)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"{dev}: {len(cpus)} of {len(allowed)} CPUs"
+    except Exception:
+        return None
+
+
 def reference_cpu_run(steps, warmup, n_sample=8192, ranks=4):
     """Time the unmodified reference (oracle/_ref) on the host cores: `topo_pdgemm_bench -n n_sample` on a 2x2 grid of
     mini-MPI ranks, all cores busy.  Returns (tflops, dict) or (None, reason)."""
@@ -101,8 +128,14 @@ def reference_cpu_run(steps, warmup, n_sample=8192, ranks=4):
     if os.path.exists(exe) and os.path.exists(run):
         cmd = [run, "-np", str(ranks), "-timeout", "900", "-threads", str(threads), exe, "-n", str(n_sample), "-niter",
                str(max(1, steps)), "-nwarm", str(max(0, warmup)), "-c_rep", "1", "-ovp", "0"]
+        bound = os.sched_getaffinity(0)
         try:
-            out = subprocess.run(cmd, capture_output=True, text=True, timeout=1200).stdout
+            if _FULL_AFFINITY:   # the CPU arm gets every core of the box, not just the ones next to rank 0's GPU
+                os.sched_setaffinity(0, _FULL_AFFINITY)
+            try:
+                out = subprocess.run(cmd, capture_output=True, text=True, timeout=1200).stdout
+            finally:
+                os.sched_setaffinity(0, bound)
             m = re.search(r"Gigaflops:\s*([0-9.eE+-]+)", out)
             t = re.search(r"Time elapsed per iteration:\s*([0-9.eE+-]+)", out)
             if m:
@@ -176,6 +209,8 @@ def main():
                     help="SUMMA panels by copy engines into peer windows instead of ncclBroadcast (experimental)")
     ap.add_argument("--b-first-chunk-early", action="store_true",
                     help="e2e leg on grids: upload the first k-chunk of B ahead of the rest (experimental)")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="do not bind the rank to the CPUs next to its GPU before the pinned host blocks are allocated")
     ap.add_argument("--single-e2e-pass", action="store_true",
                     help="e2e leg: only the library's current defaults, no first pass with the GPU-validated settings")
     ap.add_argument("--e2e-watchdog", type=float, default=180.0,
@@ -200,6 +235,7 @@ def main():
     if not torch.cuda.is_available():
         raise cb.CandmcError(5, "bench.py needs a B200: candmc_b200 has no CPU path")
     torch.cuda.set_device(local)
+    numa = None if args.no_numa_bind else bind_to_gpu_numa_node(torch.cuda.get_device_properties(local))
     if world_size > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.bg_ctas is not None:
@@ -376,7 +412,8 @@ def main():
             "config": {"workload": f"d25_summa FP64 n={n} on a {q}x{q}x{c} grid (block b={b}"
                                    f"{', k split over depth' if ksplit else ''}); one step = one multiply",
                        "n": n, "grid": [q, q, c], "block": b, "l2": "inputs larger than L2 (each operand block >= 2 GiB)",
-                       "generator": "reference unit-test drand48 per-element (test/MM/topo_pdgemm_unit.cxx:250-256)"},
+                       "generator": "reference unit-test drand48 per-element (test/MM/topo_pdgemm_unit.cxx:250-256)",
+                       "cpu_binding_rank0": numa},
             "pct_of_roofline": 100.0 * value / (2.0 * n ** 3 / t_roof / 1e12),
             "roofline_tflops": 2.0 * n ** 3 / t_roof / 1e12,
             "rel_frobenius_vs_cublas_crosscheck": rel, "tolerance_10_n_eps": 10 * n * 2.220446049250313e-16,

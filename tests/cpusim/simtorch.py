@@ -106,6 +106,8 @@ def install():
     torch.cuda.set_device = lambda *a, **k: None
     torch.cuda.is_available = lambda: True
     torch.cuda.device_count = lambda: 1
+    torch.cuda.get_device_properties = lambda *a, **k: types.SimpleNamespace(   # a PCI function that does not exist: no binding
+        name="cpusim", pci_domain_id=0xFFFF, pci_bus_id=0xFF, pci_device_id=0x1F, multi_processor_count=148)
     torch.cuda.current_stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=0)
 
     import time as _time

@@ -11,6 +11,7 @@ from .mm import (  # noqa: F401
     CommData_t,
     ctb_args_t,
     cdgemm,
+    csgemm,
     lda_cpy,
     transpose,
     summa,

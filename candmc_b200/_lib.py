@@ -61,6 +61,9 @@ SIGNATURES = {
     "candmc_profile_gemm_stats": (C.c_int, [C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "candmc_dgemm": (C.c_int, [C.c_char, C.c_char, i64, i64, i64, C.c_double, pd, i64, pd, i64, C.c_double, pd, i64,
                                C.c_void_p]),
+    "candmc_sgemm": (C.c_int, [C.c_char, C.c_char, i64, i64, i64, C.c_float, C.c_void_p, i64, C.c_void_p, i64, C.c_float,
+                               C.c_void_p, i64, C.c_void_p]),
+    "candmc_set_f32_mode": (C.c_int, [C.c_int]),
     "candmc_lda_cpy": (C.c_int, [i64, i64, i64, i64, pd, pd, C.c_void_p]),
     "candmc_lda_cpy_scaled": (C.c_int, [i64, i64, i64, i64, pd, pd, C.c_double, C.c_double, C.c_void_p]),
     "candmc_transpose": (C.c_int, [i64, i64, pd, i64, pd, i64, C.c_void_p]),

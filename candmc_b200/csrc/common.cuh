@@ -45,6 +45,30 @@ const char* last_error();
     if (s__ != ::candmc::OK) return s__;                                                    \
   } while (0)
 
+// ---- tcgen05 descriptor encoders (plain integer arithmetic: also compiled by the CPU test build, which decodes them
+// independently by CUTLASS's bit-field definitions) ---------------------------------------------------------------------
+#ifdef __CUDACC__
+#define CANDMC_HOSTDEV __host__ __device__
+#else
+#define CANDMC_HOSTDEV
+#endif
+
+// Shared-memory matrix descriptor of a K-major operand tile whose rows are 128-byte lines under the 128-byte swizzle (what a
+// TMA box of 32 floats x rows with CU_TENSOR_MAP_SWIZZLE_128B writes): start address >> 4 in bits [0,14), leading byte offset
+// (unused for swizzled K-major) 0 in [16,30), stride byte offset = 8 rows x 128 B = 1024 >> 4 in [32,46), descriptor version 1
+// in [46,48), base offset 0, layout type SWIZZLE_128B = 2 in [61,64)  (cute/arch/mma_sm100_desc.hpp, UMMA::SmemDescriptor).
+CANDMC_HOSTDEV inline uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+// Instruction descriptor of kind::tf32, FP32 accumulate, both operands K-major (UMMA::InstrDescriptor): c_format F32 = 1 in
+// bits [4,6), a_format / b_format TF32 = 2 in [7,10) / [10,13), a_major / b_major K = 0 in [15] / [16], N >> 3 in [17,23),
+// M >> 4 in [24,29).
+CANDMC_HOSTDEV constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
 // ---- device PTX helpers ----------------------------------------------------------------------
 #ifdef __CUDACC__
 
@@ -119,6 +143,65 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(d0), "+d"(d1)
       : "d"(a), "d"(b));
+}
+
+// ---- 5th-generation tensor cores (tcgen05) for the FP32 path: accumulators in TMEM, operands in swizzled shared memory.
+// Spellings as in CUTLASS's cute/arch/{mma_sm100_umma,copy_sm100,tmem_allocator_sm100}.hpp and cutlass/arch/barrier.h.
+
+// Whole warp: allocate `ncols` (power of two >= 32) TMEM columns; the base address lands in *slot (shared memory).
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+
+// Whole warp (the one that allocated).
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// One thread: D[tmem] (+)= A[smem] * B[smem]^T, M x N x 8 TF32 (SASS: UTCMMA).  `accumulate` = 0 overwrites D.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// One thread: the mbarrier gets one arrival once every MMA this thread issued so far has completed (implies
+// tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Whole warp w of an aligned group of four (w = warp index % 4): lane i reads TMEM lane 32*w + i, columns [col, col + 32) of
+// the accumulator at `taddr` (lane in bits [16,32), column in [0,16)) into v[0..31]; returns after tcgen05.wait::ld.
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 16-byte shared-memory accesses by shared-space address (the operand-splitting warps of the FP32 kernel)
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32x4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 #endif  // __CUDACC__

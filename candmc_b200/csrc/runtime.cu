@@ -235,24 +235,34 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int encode_tmap_f64(CUtensorMap* out, const double* base, int64_t dim0, int64_t dim1, int64_t ld, int box0,
-                    int box1) {
+namespace {
+int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, int64_t dim0, int64_t dim1,
+                int64_t ld, int box0, int box1) {
   CANDMC_TRY(runtime_require());
   CANDMC_CHECK(dim0 > 0 && dim1 > 0, "tensor map: empty operand");
   cuuint64_t gdim[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 8};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = reinterpret_cast<PFN_encodeTiled>(g_rt.pfn_encode_tiled)(
-      out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr,
-      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled failed (CUresult %d) dims=%lldx%lld ld=%lld box=%dx%d ptr=%p", (int)r,
-                   (long long)dim0, (long long)dim1, (long long)ld, box0, box1, (const void*)base);
+    set_last_error("cuTensorMapEncodeTiled failed (CUresult %d) dims=%lldx%lld ld=%lld box=%dx%d ptr=%p elem=%d", (int)r,
+                   (long long)dim0, (long long)dim1, (long long)ld, box0, box1, base, elem_bytes);
     return ERR_CUDA;
   }
   return OK;
+}
+}  // namespace
+
+int encode_tmap_f64(CUtensorMap* out, const double* base, int64_t dim0, int64_t dim1, int64_t ld, int box0,
+                    int box1) {
+  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, base, dim0, dim1, ld, box0, box1);
+}
+
+int encode_tmap_f32(CUtensorMap* out, const float* base, int64_t dim0, int64_t dim1, int64_t ld, int box0, int box1) {
+  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dim0, dim1, ld, box0, box1);
 }
 
 }  // namespace candmc

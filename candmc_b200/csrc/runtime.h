@@ -74,7 +74,14 @@ int next_tile_counter(int** out, cudaStream_t stream);
 int encode_tmap_f64(CUtensorMap* out, const double* base, int64_t dim0, int64_t dim1, int64_t ld, int box0,
                     int box1);
 
+// The same for FP32 operands (box0 * 4 bytes <= 128; base 16-byte aligned, ld a multiple of 4).
+int encode_tmap_f32(CUtensorMap* out, const float* base, int64_t dim0, int64_t dim1, int64_t ld, int box0, int box1);
+
 // ---- kernels' host entry points (device pointers only) ---------------------------------------
+// FP32 GEMM on tcgen05 (gemm_f32.cu).  Operands that are not K-major and TMA-readable in place are packed into the library
+// workspace first, so calls on different streams must not overlap.
+int gemm_f32(char transa, char transb, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t lda,
+             const float* B, int64_t ldb, float beta, float* C, int64_t ldc, cudaStream_t stream);
 int gemm_f64(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
              int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
              cudaStream_t stream);

@@ -102,6 +102,11 @@ void cdgemm(char transa, char transb, int m, int n, int k, double a, const doubl
   candmc_shim_check(candmc_dgemm(transa, transb, m, n, k, a, A, lda, B, ldb, b, C, ldc, 0), "cdgemm");
 }
 
+void csgemm(char transa, char transb, int m, int n, int k, float a, const float* A, int lda, const float* B, int ldb, float b,
+            float* C, int ldc) {
+  candmc_shim_check(candmc_sgemm(transa, transb, m, n, k, a, A, lda, B, ldb, b, C, ldc, 0), "csgemm");
+}
+
 void print_matrix(double const* M, int n, int m) { print_matrix(M, n, m, n); }
 void print_matrix(double const* M, int n, int m, int lda) {  // alg/shared/util.cxx print_matrix
   for (int i = 0; i < n; i++) {

@@ -86,6 +86,13 @@ def cdgemm(transa, transb, m, n, k, a, A, lda, B, ldb, b, Cm, ldc, stream=None):
                              _stream(stream)))
 
 
+def csgemm(transa, transb, m, n, k, a, A, lda, B, ldb, b, Cm, ldc, stream=None):
+    """Single-precision companion of cdgemm (float32 device operands, tcgen05 kind::tf32 with split operands; the
+    reference has no counterpart): C = a*op(A)*op(B) + b*C."""
+    check(lib().candmc_sgemm(_ch(transa), _ch(transb), m, n, k, a, _ptr(A), lda, _ptr(B), ldb, b, _ptr(Cm), ldc,
+                             _stream(stream)))
+
+
 def lda_cpy(nrow, ncol, lda_A, lda_B, A, B, a=None, b=None, stream=None):
     """lda_cpy and its scaled overload (alg/shared/util.h:459-501)."""
     if a is None:

@@ -7,4 +7,10 @@
 void cdgemm(char transa, char transb, int m, int n, int k, double a, const double* A, int lda, const double* B, int ldb,
             double b, double* C, int ldc);
 
+/* Single-precision companion of cdgemm (no reference counterpart: the reference multiplies in double only): same by-value
+ * argument list with float data, DEVICE pointers, executed by the tcgen05 kind::tf32 kernel with split operands
+ * (candmc_sgemm in candmc_b200.h states the error bound). */
+void csgemm(char transa, char transb, int m, int n, int k, float a, const float* A, int lda, const float* B, int ldb, float b,
+            float* C, int ldc);
+
 #endif

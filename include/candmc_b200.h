@@ -91,6 +91,15 @@ int candmc_debug_force_generic_gemm(int on);
  * direct dgemm_ wrapper of split-dim Cannon (alg/MM/splitdim_cannon/spcannon_internal.h:51-63). */
 int candmc_dgemm(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                  int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, void* stream);
+/* Single-precision companion (BASELINE north star: "optional FP32"; the reference has no single-precision multiply, so
+ * this mirrors cdgemm's argument list with float data): C = alpha*op(A)*op(B) + beta*C on the 5th-generation tensor cores
+ * (tcgen05.mma kind::tf32, accumulator in tensor memory).  Device pointers only; asynchronous on `stream`.  Operands that
+ * are not K-major and TMA-readable in place are packed into the library workspace first, so calls on different streams must
+ * not overlap.  candmc_set_f32_mode: TF32 products per FP32 product — 3 (default): operands split into TF32 high and low
+ * parts, relative error per product <= 3 * 2^-20 before the FP32 accumulation; 1: plain TF32 inputs (2^-11 per product). */
+int candmc_sgemm(char transa, char transb, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t lda,
+                 const float* B, int64_t ldb, float beta, float* C, int64_t ldc, void* stream);
+int candmc_set_f32_mode(int tf32_products);
 /* B(nrow x ncol, lda_B) = A(nrow x ncol, lda_A).  Replaces lda_cpy (alg/shared/util.h:459-471). */
 int candmc_lda_cpy(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B,
                    void* stream);

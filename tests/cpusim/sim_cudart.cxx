@@ -418,10 +418,12 @@ CUresult fake_encode_tiled(CUtensorMap* out, CUtensorMapDataType dt, cuuint32_t 
                            CUtensorMapSwizzle sw, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
   static_assert(sizeof(cpusim::SimTensorMap) <= sizeof(CUtensorMap), "descriptor does not fit");
   // the driver's own argument rules for what the product encodes (2-D FP64 tiles)
-  if (dt != CU_TENSOR_MAP_DATA_TYPE_FLOAT64 || rank != 2 || il != CU_TENSOR_MAP_INTERLEAVE_NONE) return CUDA_ERROR_INVALID_VALUE;
+  if ((dt != CU_TENSOR_MAP_DATA_TYPE_FLOAT64 && dt != CU_TENSOR_MAP_DATA_TYPE_FLOAT32) || rank != 2 || il != CU_TENSOR_MAP_INTERLEAVE_NONE)
+    return CUDA_ERROR_INVALID_VALUE;
+  const uint32_t es = dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT64 ? 8 : 4;
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0 || gstride[0] % 16 != 0) return CUDA_ERROR_INVALID_VALUE;
   if (box[0] == 0 || box[1] == 0 || box[0] > 256 || box[1] > 256 || estride[0] != 1 || estride[1] != 1) return CUDA_ERROR_INVALID_VALUE;
-  if (sw == CU_TENSOR_MAP_SWIZZLE_128B && box[0] * 8 > 128) return CUDA_ERROR_INVALID_VALUE;
+  if (sw == CU_TENSOR_MAP_SWIZZLE_128B && box[0] * es > 128) return CUDA_ERROR_INVALID_VALUE;
   if (sw != CU_TENSOR_MAP_SWIZZLE_128B && sw != CU_TENSOR_MAP_SWIZZLE_NONE) return CUDA_ERROR_INVALID_VALUE;
   memset(out, 0, sizeof(*out));
   cpusim::SimTensorMap m;
@@ -433,6 +435,7 @@ CUresult fake_encode_tiled(CUtensorMap* out, CUtensorMapDataType dt, cuuint32_t 
   m.box[0] = box[0];
   m.box[1] = box[1];
   m.swizzle128 = sw == CU_TENSOR_MAP_SWIZZLE_128B;
+  m.elem_bytes = es;
   memcpy(out, &m, sizeof(m));
   return CUDA_SUCCESS;
 }

@@ -39,6 +39,13 @@ bool mbar_try_wait(uint32_t bar, uint32_t parity);   // yields to the other fibe
 void tma_load_2d(uint32_t dst, const void* tensor_map, uint32_t bar, int c0, int c1);  // tiled, 128 B swizzle, OOB zero fill
 void warp_allgather16(const void* in16, void* out32x16);  // every lane contributes 16 bytes, all get all
 void named_barrier(int id, int count);                 // bar.sync id, count
+// tcgen05 (gemm_f32.cu): tensor memory, the TF32 UMMA executed when it is issued, commit = immediate mbarrier arrival
+void tmem_alloc(uint32_t slot, uint32_t ncols);
+void tmem_dealloc(uint32_t taddr, uint32_t ncols);
+void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate);
+void umma_commit(uint32_t bar);
+void tmem_ld_32x32(uint32_t taddr, uint32_t* v);
+void smem_rw16(uint32_t handle, void* data, bool write);
 void dmma_defer(double* d0, double* d1, double a, double b);   // log one DMMA.8x8x4 of the calling lane
 void dmma_flush();                                     // warp rendezvous: apply every logged DMMA
 
@@ -119,6 +126,16 @@ template <class T>
 static inline T max(T a, T b) {
   return a > b ? a : b;
 }
+static inline unsigned __float_as_uint(float f) {
+  unsigned v;
+  memcpy(&v, &f, 4);
+  return v;
+}
+static inline float __uint_as_float(unsigned v) {
+  float f;
+  memcpy(&f, &v, 4);
+  return f;
+}
 static inline long long __double_as_longlong(double d) {
   long long v;
   memcpy(&v, &d, 8);
@@ -153,6 +170,21 @@ static inline void tma_load_2d(void* dst, const CUtensorMap* tmap, uint64_t* bar
 }
 static inline void tma_prefetch_desc(const CUtensorMap*) {}
 static inline double lds_f64(uint32_t addr) { return *static_cast<const double*>(::cpusim::smem_ptr(addr)); }
+static inline void tmem_alloc(uint32_t* slot, uint32_t ncols) { ::cpusim::tmem_alloc(smem_u32(slot), ncols); }
+static inline void tmem_dealloc(uint32_t taddr, uint32_t ncols) { ::cpusim::tmem_dealloc(taddr, ncols); }
+static inline void tcgen05_fence_before() {}
+static inline void tcgen05_fence_after() {}
+static inline void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  ::cpusim::umma_tf32(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
+static inline void umma_commit(uint64_t* bar) { ::cpusim::umma_commit(smem_u32(bar)); }
+static inline void tmem_ld_32x32(uint32_t taddr, uint32_t* v) { ::cpusim::tmem_ld_32x32(taddr, v); }
+static inline float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  ::cpusim::smem_rw16(addr, &v, false);
+  return v;
+}
+static inline void sts_f32x4(uint32_t addr, float4 v) { ::cpusim::smem_rw16(addr, &v, true); }
 // mma.sync.aligned.m8n8k4.row.col.f64: lane L holds A[L>>2][L&3], B[L&3][L>>2], C/D[L>>2][2*(L&3)+{0,1}].
 // A rendezvous of 32 fibers per DMMA would dominate the run time, so the emulation defers: a call only logs its operands
 // and where its accumulators live; the warp meets once per batch — when an accumulator comes round again (the next k-step)

@@ -86,7 +86,11 @@ struct Block {
   std::vector<Warp> warps;
   std::map<uint32_t, MBar> mbars;
   NamedBar named[16];
+  std::vector<uint32_t> tmem;      // tensor memory of the SM the block runs on: 128 lanes x 512 columns of 32 bits
+  uint32_t tmem_next = 0;          // bump allocator (columns)
+  int tmem_live = 0;               // allocations not yet returned
 };
+constexpr uint32_t kTmemLanes = 128, kTmemCols = 512;
 uint64_t g_progress = 0;   // anything that lets a waiting fiber go on: a barrier opening, an mbarrier phase completing
 
 char* g_stacks = nullptr;
@@ -244,15 +248,16 @@ void tma_load_2d(uint32_t dst, const void* tensor_map, uint32_t bar, int c0, int
   for (uint32_t i1 = 0; i1 < m.box[1]; ++i1)
     for (uint32_t i0 = 0; i0 < m.box[0]; ++i0) {
       const int64_t g0 = (int64_t)c0 + i0, g1 = (int64_t)c1 + i1;
-      double v = 0.0;  // out-of-range elements are zero-filled
+      const uint32_t es = m.elem_bytes;
+      unsigned char v[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // out-of-range elements are zero-filled
       if (g0 >= 0 && g1 >= 0 && (uint64_t)g0 < m.dim[0] && (uint64_t)g1 < m.dim[1])
-        memcpy(&v, m.base + g0 * 8 + g1 * (int64_t)m.stride1, 8);
-      uint32_t addr = dst + (i1 * m.box[0] + i0) * 8;
+        memcpy(v, m.base + g0 * es + g1 * (int64_t)m.stride1, es);
+      uint32_t addr = dst + (i1 * m.box[0] + i0) * es;
       if (m.swizzle128) addr ^= ((addr >> 7) & 7u) << 4;   // 16-byte chunk index XOR 128-byte line index, on the shared address
-      memcpy(smem_ptr(addr), &v, 8);
+      memcpy(smem_ptr(addr), v, es);
     }
   MBar& b = mbar_get(bar);
-  b.tx -= (int64_t)m.box[0] * m.box[1] * 8;
+  b.tx -= (int64_t)m.box[0] * m.box[1] * m.elem_bytes;
   mbar_check(b);
 }
 
@@ -344,6 +349,118 @@ void dmma_defer(double* d0, double* d1, double a, double b) {
   ++f.npending;
 }
 
+// ---- tcgen05: tensor memory and the TF32 UMMA of gemm_f32.cu ------------------------------------------------------------------
+// Descriptors are DECODED here by the bit fields of CUTLASS's cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor),
+// independently of the product's encoders in common.cuh; anything outside what this emulation implements aborts.
+void tmem_alloc(uint32_t slot, uint32_t ncols) {
+  if (g_cur % 32 != 0) return;   // warp-collective: lane 0 does the bookkeeping
+  if (ncols < 32 || ncols > kTmemCols || (ncols & (ncols - 1)) != 0 || g_blk.tmem_next + ncols > kTmemCols) {
+    fprintf(stderr, "cpusim: tcgen05.alloc of %u columns (%u in use)\n", ncols, g_blk.tmem_next);
+    abort();
+  }
+  if (g_blk.tmem.empty()) g_blk.tmem.assign((size_t)kTmemLanes * kTmemCols, 0xCDCDCDCDu);   // contents undefined
+  const uint32_t base = g_blk.tmem_next;   // lane 0, column `base`
+  g_blk.tmem_next += ncols;
+  g_blk.tmem_live++;
+  memcpy(smem_ptr(slot), &base, 4);
+}
+void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  if (g_cur % 32 != 0) return;
+  if (g_blk.tmem_live <= 0 || (taddr >> 16) != 0 || (taddr & 0xFFFF) + ncols > g_blk.tmem_next) {
+    fprintf(stderr, "cpusim: tcgen05.dealloc of something that was not allocated\n");
+    abort();
+  }
+  g_blk.tmem_live--;
+}
+static float tf32_of(uint32_t bits) {   // what the tensor core reads of a 32-bit word: sign, 8 exponent and 10 mantissa bits
+  bits &= 0xFFFFE000u;
+  float f;
+  memcpy(&f, &bits, 4);
+  return f;
+}
+struct DecodedSmemDesc {
+  uint32_t start, lbo, sbo;
+};
+static DecodedSmemDesc decode_smem_desc(uint64_t d, const char* which) {
+  DecodedSmemDesc o;
+  o.start = (uint32_t)(d & 0x3FFF) << 4;
+  o.lbo = (uint32_t)((d >> 16) & 0x3FFF) << 4;
+  o.sbo = (uint32_t)((d >> 32) & 0x3FFF) << 4;
+  const unsigned version = (unsigned)(d >> 46) & 3, base_offset = (unsigned)(d >> 49) & 7, lbo_mode = (unsigned)(d >> 52) & 1,
+                 layout = (unsigned)(d >> 61) & 7;
+  if (version != 1 || base_offset != 0 || lbo_mode != 0 || layout != 2 /* SWIZZLE_128B */ || o.sbo != 1024) {
+    fprintf(stderr, "cpusim: UMMA %s descriptor outside the emulated subset (version %u base_offset %u lbo_mode %u layout %u sbo %u)\n",
+            which, version, base_offset, lbo_mode, layout, o.sbo);
+    abort();
+  }
+  return o;
+}
+static float umma_operand(const DecodedSmemDesc& d, uint32_t row, uint32_t k) {
+  // K-major, 128-byte swizzle: 8-row groups `sbo` bytes apart, 128 bytes per row, 16-byte chunk index XOR row-in-group on the
+  // ABSOLUTE shared address (so a start address advanced by 32 B inside the swizzle span selects the next K = 8 slice)
+  uint32_t addr = d.start + (row / 8) * d.sbo + (row % 8) * 128 + k * 4;
+  addr ^= ((addr >> 7) & 7u) << 4;
+  uint32_t bits;
+  memcpy(&bits, smem_ptr(addr), 4);
+  return tf32_of(bits);
+}
+void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  const unsigned sparse = idesc & 7, saturate = (idesc >> 3) & 1, cfmt = (idesc >> 4) & 3, afmt = (idesc >> 7) & 7,
+                 bfmt = (idesc >> 10) & 7, neg = (idesc >> 13) & 3, amaj = (idesc >> 15) & 1, bmaj = (idesc >> 16) & 1,
+                 N = ((idesc >> 17) & 0x3F) << 3, M = ((idesc >> 24) & 0x1F) << 4, shift = idesc >> 30;
+  if (sparse || saturate || cfmt != 1 || afmt != 2 || bfmt != 2 || neg || amaj || bmaj || M != 128 || N < 16 || N > 256 || N % 16 ||
+      shift || (idesc & ((1u << 6) | (1u << 23) | (1u << 29)))) {
+    fprintf(stderr, "cpusim: UMMA instruction descriptor 0x%08x outside the emulated subset (kind::tf32, F32 accumulate, K-major, M = 128)\n",
+            idesc);
+    abort();
+  }
+  const uint32_t col0 = tmem_d & 0xFFFF;
+  if ((tmem_d >> 16) != 0 || col0 + N > g_blk.tmem_next) {
+    fprintf(stderr, "cpusim: UMMA accumulator outside the allocated tensor memory\n");
+    abort();
+  }
+  const DecodedSmemDesc a = decode_smem_desc(desc_a, "A"), b = decode_smem_desc(desc_b, "B");
+  static thread_local std::vector<float> av, bv;
+  av.resize((size_t)M * 8);
+  bv.resize((size_t)N * 8);
+  for (uint32_t r = 0; r < M; ++r)
+    for (uint32_t k = 0; k < 8; ++k) av[r * 8 + k] = umma_operand(a, r, k);
+  for (uint32_t r = 0; r < N; ++r)
+    for (uint32_t k = 0; k < 8; ++k) bv[r * 8 + k] = umma_operand(b, r, k);
+  for (uint32_t m = 0; m < M; ++m)
+    for (uint32_t n = 0; n < N; ++n) {
+      uint32_t& cell = g_blk.tmem[(size_t)m * kTmemCols + col0 + n];
+      float acc = 0.0f;
+      if (accumulate) memcpy(&acc, &cell, 4);
+      for (uint32_t k = 0; k < 8; ++k) acc += av[m * 8 + k] * bv[n * 8 + k];   // products of TF32 values are exact in FP32
+      memcpy(&cell, &acc, 4);
+    }
+}
+void umma_commit(uint32_t bar) { mbar_arrive(bar); }   // MMAs complete when issued here, so the arrival is immediate
+void tmem_ld_32x32(uint32_t taddr, uint32_t* v) {
+  const uint32_t lane0 = taddr >> 16, col0 = taddr & 0xFFFF, warp = (uint32_t)g_cur / 32, lane = (uint32_t)g_cur % 32;
+  if (lane0 != 32 * (warp % 4)) {
+    fprintf(stderr, "cpusim: tcgen05.ld.32x32b by warp %u on TMEM lanes %u..: a warp may only read the lane quarter (warp %% 4)\n", warp,
+            lane0);
+    abort();
+  }
+  if (col0 + 32 > g_blk.tmem_next) {
+    fprintf(stderr, "cpusim: tcgen05.ld outside the allocated tensor memory\n");
+    abort();
+  }
+  for (uint32_t j = 0; j < 32; ++j) v[j] = g_blk.tmem[(size_t)(lane0 + lane) * kTmemCols + col0 + j];
+}
+void smem_rw16(uint32_t handle, void* data, bool write) {
+  if (handle % 16 != 0) {
+    fprintf(stderr, "cpusim: misaligned 16-byte shared-memory access\n");
+    abort();
+  }
+  void* lo = smem_ptr(handle);
+  smem_ptr(handle + 8);   // bounds of the upper half
+  if (write) memcpy(lo, data, 16);
+  else memcpy(data, lo, 16);
+}
+
 void named_barrier(int id, int count) {
   NamedBar& nb = g_blk.named[id & 15];
   const unsigned gen = nb.gen;
@@ -405,6 +522,9 @@ static void execute(dim3 grid, dim3 block, size_t smem, const std::function<void
         g_blk.gen = 0;
         g_blk.warps.assign((nthreads + 31) / 32, Warp());
         g_blk.mbars.clear();
+        g_blk.tmem.clear();
+        g_blk.tmem_next = 0;
+        g_blk.tmem_live = 0;
         for (NamedBar& nb : g_blk.named) nb = NamedBar();
         for (int t = 0; t < nthreads; ++t) {
           Fiber& f = g_fibers[t];
@@ -474,6 +594,10 @@ static void execute(dim3 grid, dim3 block, size_t smem, const std::function<void
                     g_blk.arrived, g_blk.alive);
             abort();
           }
+        }
+        if (g_blk.tmem_live != 0) {
+          fprintf(stderr, "cpusim: block (%u,%u,%u) exited with tensor memory still allocated\n", bx, by, bz);
+          abort();
         }
       }
   g_body = nullptr;

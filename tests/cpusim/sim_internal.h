@@ -35,6 +35,7 @@ struct SimTensorMap {
   uint64_t stride1;      // bytes between consecutive dim-1 indices
   uint32_t box[2];
   uint32_t swizzle128;
+  uint32_t elem_bytes;   // 8 (FLOAT64) or 4 (FLOAT32)
 };
 constexpr uint64_t kTensorMapMagic = 0x53494d544d415031ull;
 

@@ -63,6 +63,7 @@ _job("transport8", _torchrun(8, 29742, os.path.join(HERE, "dist_worker.py")), CA
      CANDMC_TEST_FUSED_GRIDS="1", CPUSIM_SCHED="lifo")
 # the hot kernel itself on the PTX emulation, and the 4-rank suite with every GEMM going through it
 _job("kernel", [sys.executable, os.path.join(SIM, "probe_gemm.py")])
+_job("kernel_f32", [sys.executable, os.path.join(HERE, "f32_worker.py")])
 if FULL:
     _job("main4_device_gemm", _torchrun(4, 29719, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CPUSIM_GEMM="device")
 for _n in DIST_PENDING:
@@ -309,6 +310,18 @@ def test_hot_gemm_kernel_on_the_ptx_emulation():
     assert rc == 0, so[-2000:] + se[-3000:]
     r = json.loads(so.strip().splitlines()[-1])
     assert r["cases"] >= 25 and r["max_rel_err"] <= 1e-13
+
+
+def test_fp32_tcgen05_kernel_on_the_emulation():
+    """candmc_b200/csrc/gemm_f32.cu itself — K-major TMA boxes, the operand split in shared memory (hi in place, lo behind), UMMA
+    shared-memory / instruction descriptors decoded by CUTLASS's bit fields, TF32 truncation, the double-buffered accumulator in
+    tensor memory, the 32-lane x 32-column epilogue loads with the warp-quarter rule enforced, the K-major pack of the other
+    transpose cases — against a float64 product: 3xTF32 within 4 * 2^-20 of the summed terms, one TF32 product within 2^-9"""
+    rc, so, se = RESULTS["kernel_f32"]
+    assert rc == 0, so[-2000:] + se[-3000:]
+    r = json.loads(so.strip().splitlines()[-1])
+    assert r["cases"] >= 24 and r["max_rel_err_3xtf32"] <= r["tol_3xtf32"] and r["max_rel_err_1xtf32"] <= 2.0 ** -9
+    assert r["max_rel_err_1xtf32"] > 100 * r["max_rel_err_3xtf32"]   # the split really buys the accuracy
 
 
 @pytest.mark.skipif(not FULL, reason="CANDMC_CPUSIM_FULL=1")

@@ -1,0 +1,28 @@
+"""GPU test of the optional FP32 GEMM (candmc_sgemm: tcgen05.mma kind::tf32 with split operands, accumulator in tensor memory).
+
+STATUS: written after the round's GPU budget was spent — compiled for sm_100a (SASS shows UTCHMMA / UTMALDG / LDTM / UTCBAR),
+every case passes on the CPU simulator's tcgen05 emulation (tests/test_cpusim.py), never run on a B200.  Same policy as the
+other tests/test_zz_*.py: own process group with a timeout, xfail(strict=False) until a round has seen it pass.
+"""
+import json
+import os
+import sys
+
+import pytest
+
+from pending_util import run_guarded
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+PENDING = pytest.mark.xfail(strict=False, reason="FP32 tcgen05 GEMM: first B200 run pending (written after the GPU budget was spent)")
+
+
+@pytest.mark.gpu
+@PENDING
+def test_sgemm_against_float64_product():
+    """all transpose combinations, ragged m / n / k, padded and misaligned operands, alpha / beta, both precision modes, up to
+    4096^3: relative to the size of the summed terms the 3xTF32 result stays within 4 * 2^-20, the single-TF32 one within 2^-9"""
+    rc, out, err = run_guarded("f32", [sys.executable, os.path.join(HERE, "f32_worker.py")], 240, ROOT)
+    assert rc == 0, out[-2000:] + err[-3000:]
+    r = json.loads(out.strip().splitlines()[-1])
+    assert r["cases"] >= 28 and r["max_rel_err_3xtf32"] <= r["tol_3xtf32"] and r["launches"] > 0

@@ -3,7 +3,7 @@
 #   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh lu ncu'            (1 GPU)
 #   gpurun --gpus 4 --timeout 1200 -- 'bash tools/gpu_session.sh dist4'    (4 GPUs)
 #   gpurun --gpus 8 --timeout 1200 -- 'bash tools/gpu_session.sh dist8'    (8 GPUs)
-# Sections: e2e1 / e2eN (end-to-end knobs added without a GPU: early C download, upload policy, panel count), lu (LU seam tests + LU bench host vs GPU), pending1 (redistribution / Yamamoto tests + their measurements), ncu (full capture at n=32768 for roofline.traffic, pack kernels),
+# Sections: f32 (FP32 tcgen05 GEMM: parity, speed, ncu), e2e1 / e2eN (end-to-end knobs added without a GPU: early C download, upload policy, panel count), lu (LU seam tests + LU bench host vs GPU), pending1 (redistribution / Yamamoto tests + their measurements), ncu (full capture at n=32768 for roofline.traffic, pack kernels),
 #           dist4 (second-pass parity cases, update_A with T), dist8 (fused depth sum on 2x2x2, skip_unused_uploads)
 set -u
 cd "$(dirname "$0")/.."
@@ -34,6 +34,14 @@ for section in "$@"; do
       timeout 900 ncu --set full --clock-control none -k regex:'lda_|transpose|sparse_rows' -c 12 \
         -o gpurun_out/ncu_full_pack -f tools/gemm_probe pack 16384 > gpurun_out/ncu_full_pack.log 2>&1
       python tools/ncu_summary.py gpurun_out/ncu_full_pack.ncu-rep gpurun_out/ncu_full_pack.csv | tail -14
+      ;;
+    f32)
+      # the FP32 tcgen05 GEMM: parity (first contact with hardware), first speeds, and an ncu pass that shows the tensor pipe
+      timeout 600 python tests/f32_worker.py --bench > gpurun_out/f32_worker.json 2> gpurun_out/f32_worker.err
+      tail -3 gpurun_out/f32_worker.json; tail -5 gpurun_out/f32_worker.err
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_f32_umma -c 2 -o gpurun_out/f32_gemm \
+        python tests/f32_worker.py > gpurun_out/f32_ncu.log 2>&1
+      ncu -i gpurun_out/f32_gemm.ncu-rep --page raw --csv > gpurun_out/f32_gemm_raw.csv 2>/dev/null
       ;;
     pending1)
       # redistribution / Yamamoto tests on one GPU and the not-yet-measured widening rows

@@ -216,7 +216,8 @@ def main():
     ap.add_argument("--e2e-watchdog", type=float, default=180.0,
                     help="seconds the second end-to-end pass may take before the line is printed without it")
     ap.add_argument("--host-panels", type=int, default=None,
-                    help="e2e leg on one GPU: column panels of the host-streamed multiply (default: 16 at n >= 32768, else 8)")
+                    help="e2e leg on one GPU: equal column panels of the host-streamed multiply (-1: graduated cut; default: graduated "
+                         "at n >= 8192, and a first pass with the measured 8 equal panels)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

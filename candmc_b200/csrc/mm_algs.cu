@@ -328,20 +328,67 @@ int summa_sweep(SummaArgs& a) {
   return OK;
 }
 
+// ---- the cut of the host-streamed multiply below into column panels of C and of its first panel into k-chunks ----  Uniform (NP equal panels, NP equal
+// chunks: what B200s have measured with NP = 8) or graduated (the automatic choice for large products): what stays exposed is
+// the upload in front of the first multiply and the download behind the last one, so the first panel's k-chunks start small
+// and double (k/64, k/64, k/32, ... k/2: the first multiply waits for 1/64 of A instead of 1/NP) while the panel itself stays
+// wide enough (n/8) for its multiplies to cover the rest of A's upload, and the last panels shrink (n/16, n/32, n/32) so that
+// only 1/32 of C is downloaded after the last multiply.  Every piece but the last is a multiple of the CTA tile / the k-tile.
+void host_pipeline_cut(int64_t n, int64_t k, int panels, std::vector<int64_t>* widths, std::vector<int64_t>* kchunks) {
+  auto round_up = [](int64_t x, int64_t q) { return (x + q - 1) / q * q; };
+  widths->clear();
+  kchunks->clear();
+  const bool graduated = panels < 0 || (panels == 0 && n >= 8192 && k >= 8192);
+  if (!graduated) {
+    const int NP = panels > 0 ? panels : 8;
+    const int64_t nb = round_up((n + NP - 1) / NP, 128), kc = round_up((k + NP - 1) / NP, 16);
+    for (int64_t c0 = 0; c0 < n; c0 += nb) widths->push_back(std::min(nb, n - c0));
+    for (int64_t k0 = 0; k0 < k; k0 += kc) kchunks->push_back(std::min(kc, k - k0));
+    return;
+  }
+  const int64_t base = round_up((n + 7) / 8, 128);
+  const int64_t t2 = std::max<int64_t>(128, round_up(base / 2, 128)), t4 = std::max<int64_t>(128, round_up(base / 4, 128));
+  const int64_t tail = t2 + 2 * t4;
+  int64_t rem = n;
+  while (rem - base >= tail) {
+    widths->push_back(base);
+    rem -= base;
+  }
+  const int64_t mid = rem > tail ? (rem - tail) / 128 * 128 : 0;
+  if (mid > 0) {
+    widths->push_back(mid);
+    rem -= mid;
+  }
+  for (int64_t w : {t2, t4}) {
+    if (rem > w) {
+      widths->push_back(w);
+      rem -= w;
+    }
+  }
+  if (rem > 0) widths->push_back(rem);   // <= t4 + 127 <= base
+  const int64_t unit = round_up((k + 63) / 64, 16);
+  int64_t k0 = 0;
+  for (int64_t mult : {1, 1, 2, 4, 8, 16}) {
+    const int64_t kc = std::min(unit * mult, k - k0);
+    if (kc <= 0) break;
+    kchunks->push_back(kc);
+    k0 += kc;
+  }
+  if (k0 < k) kchunks->push_back(k - k0);
+}
+
 // ---- host-resident operands on a 1x1 grid: stream the multiply through PCIe -----------------------------------------
 // C(m x n) = A(m x k) * B(k x n) with A, B, C in HOST memory (what the reference's callers own).  Instead of
 // "copy everything in, multiply, copy everything out" the product is cut into column panels of C: panel j+1's slice of B
 // is uploaded and panel j-1's slice of C is downloaded while panel j multiplies; the first panel is additionally cut
 // along k so that its GEMMs start as soon as the first column slab of A has landed.  Only the first A slab and the last
-// C panel are exposed.  Three streams: H2D (aux), compute (caller's), D2H (comm — idle on a 1x1 grid).
+// C panel are exposed (host_pipeline_cut above decides how large those are).  Three streams: H2D (aux), compute (caller's), D2H (comm — idle on a 1x1 grid).
 int host_pipelined_gemm_nn(int64_t m, int64_t n, int64_t k, const double* hA, int64_t lda, const double* hB, int64_t ldb,
                            double* hC, int64_t ldc, cudaStream_t st) {
-  // exposed = the first A slab + B chunk on the way in and the last C panel on the way out: 1/NP of A and of C each.  Panels
-  // of >= 2048 columns still keep the 128 x 128-tile GEMM at 28+ waves, so large products are cut finer.
-  const int NP = runtime().host_pipeline_panels > 0 ? runtime().host_pipeline_panels : ((n >= 32768 && k >= 32768) ? 16 : 8);
-  const int64_t nb = ((n + NP - 1) / NP + 127) / 128 * 128;   // panel width (multiple of the CTA tile)
-  const int64_t kc = ((k + NP - 1) / NP + 15) / 16 * 16;      // k-chunk of the first panel
-  const int npanels = (int)((n + nb - 1) / nb), nchunks = (int)((k + kc - 1) / kc);
+  std::vector<int64_t> widths, kchunks;
+  host_pipeline_cut(n, k, runtime().host_pipeline_panels, &widths, &kchunks);
+  const int npanels = (int)widths.size(), nchunks = (int)kchunks.size();
+  const int64_t nb = *std::max_element(widths.begin(), widths.end());   // the double buffers hold the widest panel
   cudaStream_t h2d = runtime().aux_stream, d2h = runtime().comm_stream;
   void* wsv = nullptr;
   CANDMC_TRY(workspace_get(sizeof(double) * (m * k + 2 * k * nb + 2 * m * nb + 8), &wsv));
@@ -359,18 +406,21 @@ int host_pipelined_gemm_nn(int64_t m, int64_t n, int64_t k, const double* hA, in
     CANDMC_CUDA(cudaEventRecord(*e, s));
     return OK;
   };
+  int64_t c0 = 0;
   for (int j = 0; j < npanels; ++j) {
     const int slot = j & 1;
-    const int64_t c0 = j * nb, nbj = std::min(nb, n - c0);
+    const int64_t nbj = widths[j];
     if (j == 0) {
+      int64_t k0 = 0;
       for (int t = 0; t < nchunks; ++t) {
-        const int64_t k0 = t * kc, kct = std::min(kc, k - k0);
+        const int64_t kct = kchunks[t];
         CANDMC_CUDA(cudaMemcpy2DAsync(dA + k0 * m, m * 8, hA + k0 * lda, lda * 8, m * 8, kct, cudaMemcpyHostToDevice, h2d));
         CANDMC_CUDA(cudaMemcpy2DAsync(dB[0] + k0, k * 8, hB + k0, ldb * 8, kct * 8, nbj, cudaMemcpyHostToDevice, h2d));
         cudaEvent_t ready;
         CANDMC_TRY(ev(&ready, h2d));
         CANDMC_CUDA(cudaStreamWaitEvent(st, ready, 0));
         CANDMC_TRY(gemm_f64('N', 'N', m, nbj, kct, 1.0, dA + k0 * m, m, dB[0] + k0, k, t ? 1.0 : 0.0, dC[0], m, st));
+        k0 += kct;
       }
     } else {
       if (j >= 2) CANDMC_CUDA(cudaStreamWaitEvent(h2d, g_done[j - 2], 0));  // dB[slot] no longer read
@@ -385,6 +435,7 @@ int host_pipelined_gemm_nn(int64_t m, int64_t n, int64_t k, const double* hA, in
     CANDMC_CUDA(cudaStreamWaitEvent(d2h, g_done[j], 0));
     CANDMC_CUDA(cudaMemcpy2DAsync(hC + c0 * ldc, ldc * 8, dC[slot], m * 8, m * 8, nbj, cudaMemcpyDeviceToHost, d2h));
     CANDMC_TRY(ev(&c_free[j], d2h));
+    c0 += nbj;
   }
   CANDMC_TRY(stream_wait(st, d2h));
   CANDMC_CUDA(cudaStreamSynchronize(st));
@@ -468,8 +519,22 @@ int candmc_set_panel_transport(int on) {
 
 unsigned long long candmc_panel_transport_sends(void) { return runtime().transport_sends; }
 
+int candmc_host_pipeline_cut(int64_t n, int64_t k, int panels, int64_t* widths, int64_t* kchunks, int cap, int* npanels,
+                             int* nchunks) {
+  CANDMC_CHECK(n > 0 && k > 0 && widths && kchunks && npanels && nchunks, "candmc_host_pipeline_cut: bad arguments");
+  std::vector<int64_t> w, c;
+  host_pipeline_cut(n, k, panels, &w, &c);
+  CANDMC_CHECK((int)w.size() <= cap && (int)c.size() <= cap, "candmc_host_pipeline_cut: %zu panels / %zu chunks do not fit", w.size(),
+               c.size());
+  std::copy(w.begin(), w.end(), widths);
+  std::copy(c.begin(), c.end(), kchunks);
+  *npanels = (int)w.size();
+  *nchunks = (int)c.size();
+  return OK;
+}
+
 int candmc_set_host_pipeline_panels(int panels) {
-  CANDMC_CHECK(panels >= 0 && panels <= 64, "candmc_set_host_pipeline_panels: 0 (automatic) .. 64");
+  CANDMC_CHECK(panels >= -1 && panels <= 64, "candmc_set_host_pipeline_panels: -1 (graduated), 0 (automatic), 1 .. 64 (uniform)");
   runtime().host_pipeline_panels = panels;
   return OK;
 }

@@ -38,7 +38,8 @@ struct Runtime {
   bool profile = false;                 // bracket every DMMA GEMM launch with events (bench.py's roofline leg)
   int gemm_reserve_sms = 0;             // SMs a GEMM launch leaves free (set by schedules that overlap NCCL traffic)
   int bg_max_ctas = 2;                  // CTA cap of the communicators used for traffic overlapped with GEMMs (0 = no cap)
-  int host_pipeline_panels = 0;         // column panels / first-panel k-chunks of that pipeline (0: 16 at n, k >= 32768, else 8)
+  int host_pipeline_panels = 0;         // cut of that pipeline: n > 0 uniform panels / first-panel k-chunks, -1 graduated, 0 automatic
+                                        // (graduated at n, k >= 8192, else 8 uniform; host_pipeline_cut in mm_algs.cu)
   int64_t host_pipeline_min = 2048;     // smallest n for which host operands on a 1x1 grid are streamed panel-wise
   int64_t min_kchunk = 1024;            // smallest k-chunk the SUMMA pipeline cuts a panel into
 };

@@ -225,8 +225,15 @@ int candmc_set_min_kchunk(int64_t min_kchunk);
 /* Tuning: on a 1x1x1 grid with HOST operands and n >= this (default 2048) the multiply is streamed through PCIe in
  * column panels (upload of panel j+1 and download of panel j-1 under the GEMM of panel j) instead of staged whole. */
 int candmc_set_host_pipeline_min(int64_t min_n);
-/* ... and into how many column panels (= k-chunks of the first panel) it is cut: 0 = automatic (16 when n, k >= 32768, else 8). */
+/* ... and how it is cut: n > 0 = n equal column panels (and n equal k-chunks of the first panel; 8 is what B200s have
+ * measured), -1 = graduated (first panel n/8 wide with k-chunks doubling from k/64, last panels shrinking to n/32: 1/64 of A
+ * is uploaded before the first multiply and 1/32 of C downloaded after the last), 0 = automatic (graduated when n, k >= 8192,
+ * else 8 equal panels). */
 int candmc_set_host_pipeline_panels(int panels);
+/* The cut itself for an n-column, k-deep product (host arithmetic only; exposed for the CPU-side tests): panel widths and
+ * the first panel's k-chunks, at most `cap` of each. */
+int candmc_host_pipeline_cut(int64_t n, int64_t k, int panels, int64_t* widths, int64_t* kchunks, int cap, int* npanels,
+                             int* nchunks);
 
 /* ---- symmetric full -> band reduction, trailing update ----------------------------------------
  * One level of sym_full2band (alg/SE/full_to_band.cxx:28-250) after its panel QR (:96): given the aggregated Householder

@@ -85,3 +85,42 @@ def test_bootstrap_exchange_world_size_2_gloo(tmp_path):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert p.stdout.count("OK") == 2
+
+
+def _cut(n, k, panels):
+    import ctypes as C
+
+    from candmc_b200._lib import check, lib
+
+    w, c = (C.c_int64 * 128)(), (C.c_int64 * 128)()
+    nw, nc = C.c_int(), C.c_int()
+    check(lib().candmc_host_pipeline_cut(n, k, panels, w, c, 128, C.byref(nw), C.byref(nc)))
+    return list(w[: nw.value]), list(c[: nc.value])
+
+
+def test_host_pipeline_cut_of_the_headline_size():
+    """bench.py's one-GPU end-to-end leg (n = k = 32768): the automatic cut is the graduated one — 1/64 of A in front of the
+    first multiply, the first panel n/8 wide (its multiplies cover the rest of A's upload), 1/32 of C behind the last one"""
+    w, c = _cut(32768, 32768, 0)
+    assert w == [4096] * 7 + [2048, 1024, 1024]
+    assert c == [512, 512, 1024, 2048, 4096, 8192, 16384]
+    assert _cut(32768, 32768, -1) == (w, c)
+    # uniform: what B200s have measured (8), and any explicit count
+    assert _cut(32768, 32768, 8) == ([4096] * 8, [4096] * 8)
+    assert _cut(32768, 32768, 16) == ([2048] * 16, [2048] * 16)
+    # below 8192 the automatic choice stays 8 equal panels (the cut the validated GPU tests run)
+    assert _cut(320, 320, 0) == ([128, 128, 64], [48] * 6 + [32])
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (127, 5), (128, 16), (200, 200), (1100, 77), (2304, 2304), (8192, 8192), (12345, 9999),
+                                 (65536, 512), (40000, 70000)])
+@pytest.mark.parametrize("panels", [-1, 0, 1, 3, 8, 16, 64])
+def test_host_pipeline_cut_covers_the_product_exactly(n, k, panels):
+    """every column and every k exactly once, no empty piece, every panel but the last a multiple of the 128-wide CTA tile and
+    every k-chunk but the last a multiple of the 16-deep k-tile (the GEMM's TMA boxes), any size"""
+    w, c = _cut(n, k, panels)
+    assert sum(w) == n and sum(c) == k and min(w) > 0 and min(c) > 0
+    assert all(x % 128 == 0 for x in w[:-1]) and all(x % 16 == 0 for x in c[:-1])
+    assert len(w) <= 70 and len(c) <= 70
+    if panels < 0 and n >= 2048:   # graduated: the last panel is at most a quarter of the widest (+ the ragged rest)
+        assert w[-1] <= max(w) // 4 + 255 and c[0] <= k // 64 + 16

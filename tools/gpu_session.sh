@@ -70,8 +70,9 @@ for section in "$@"; do
       cat gpurun_out/bench_configs_4gpu_transport.jsonl
       ;;
     e2e1)
-      # one GPU: the host-streamed multiply with 8 / 16 / 32 column panels (16 is the new default at n = 32768, never measured)
-      for knobs in "--host-panels 8" "" "--host-panels 32"; do
+      # one GPU: the host-streamed multiply with 8 equal panels (measured), the graduated cut (default, never measured: the
+      # plain run reports both passes in e2e_passes), 16 and 32 equal panels
+      for knobs in "" "--host-panels 16" "--host-panels 32"; do
         echo "== bench 1 GPU $knobs" >> gpurun_out/e2e1_bench.log
         timeout 400 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline $knobs >> gpurun_out/e2e1_bench.log 2>&1
       done

@@ -95,6 +95,16 @@ if not SIM:   # the same on 148 SMs: several waves of tiles, long k, ragged ever
     run("N", "N", 4096 + 77, 2048 + 13, 1024 + 5, 0.75, 1.0, seed=5, pad=3)
     run("N", "T", 3000, 5000, 777, -1.0, 0.5, seed=6)
     run("T", "T", 2048, 2048, 2048, 1.0, 0.0, seed=7, mode=1)
+# randomised shapes / transposes / scalars / paddings / alignments (`--fuzz SEED COUNT`)
+if "--fuzz" in sys.argv:
+    i = sys.argv.index("--fuzz")
+    frng = np.random.RandomState(int(sys.argv[i + 1]))
+    for _ in range(int(sys.argv[i + 2])):
+        big = 300 if SIM else 1500
+        m, n, k = (int(frng.randint(1, big)) for _ in range(3))
+        run("NT"[frng.randint(2)], "NT"[frng.randint(2)], m, n, k, float(frng.choice([1.0, -0.5, 2.0])),
+            float(frng.choice([0.0, 1.0, -1.5])), pad=int(frng.randint(0, 4)), mode=int(frng.choice([3, 3, 1])),
+            seed=int(frng.randint(1000)), offset=int(frng.randint(0, 2)))
 speed = None
 if not SIM and "--bench" in sys.argv:   # first numbers for the next GPU session (tools/gpu_session.sh f32): device events, 5 launches
     speed = {}

@@ -46,6 +46,9 @@ def test_compute_fails_loudly_without_gpu():
     with pytest.raises(cb.CandmcError) as e:
         cb.cdgemm("N", "N", 2, 2, 2, 1.0, 0, 2, 0, 2, 0.0, 0, 2)
     assert e.value.code == 5  # CANDMC_ERR_NODEVICE
+    with pytest.raises(cb.CandmcError) as e:
+        cb.csgemm("T", "N", 2, 2, 2, 1.0, 0, 2, 0, 2, 0.0, 0, 2)
+    assert e.value.code == 5
     with pytest.raises(cb.CandmcError):
         cb.init_world(0, 1, 0)
 

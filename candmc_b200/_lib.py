@@ -61,6 +61,7 @@ SIGNATURES = {
     "candmc_profile_gemm_stats": (C.c_int, [C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "candmc_dgemm": (C.c_int, [C.c_char, C.c_char, i64, i64, i64, C.c_double, pd, i64, pd, i64, C.c_double, pd, i64,
                                C.c_void_p]),
+    "candmc_set_trsm_variant": (C.c_int, [C.c_int]),
     "candmc_host_pipeline_cut": (C.c_int, [i64, i64, C.c_int, C.POINTER(i64), C.POINTER(i64), C.c_int, C.POINTER(C.c_int),
                                            C.POINTER(C.c_int)]),
     "candmc_sgemm": (C.c_int, [C.c_char, C.c_char, i64, i64, i64, C.c_float, C.c_void_p, i64, C.c_void_p, i64, C.c_float,

@@ -489,8 +489,71 @@ trsm_llnn_kernel(int b, int kb, const double* __restrict__ T, int64_t ldt, doubl
   for (int e = tid; e < b * nc; e += nt) W[(e % b) + static_cast<int64_t>(c0 + e / b) * ldw] = sw[e];
 }
 
+// Variant with one WARP per right-hand side (opt-in, candmc_set_trsm_variant(1); not measured yet).  The kernel above meets at
+// a block barrier twice per row of T (1024 barriers for b = 512); here a column never leaves its warp: lane r of warp w owns
+// row i0 + r of column c0 + w of the current 32-row block, the part of the solution that is already final is applied
+// left-looking from shared memory (T streamed through a 32 x 128 tile that the eight warps of the CTA share), and the
+// 32 x 32 diagonal block is solved with shuffles.  Block barriers: two per T tile, 104 for b = 512.
+constexpr int TRSMW_TILE = 128;
+__global__ void __launch_bounds__(256)
+trsm_llnn_warp_kernel(int b, int kb, const double* __restrict__ T, int64_t ldt, double* __restrict__ W, int64_t ldw) {
+  extern __shared__ double sx[];                         // 8 columns x b (the solution as it becomes final)
+  __shared__ double tt[32][TRSMW_TILE + 1];              // T[i0 + r][j0 + c]; 129 = 1 mod 16: conflict-free across lanes
+  __shared__ double td[32][33];                          // the diagonal block
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * TRSM_NC + warp;
+  const bool live = col < kb;
+  double* x = sx + static_cast<int64_t>(warp) * b;
+  double* wcol = W + static_cast<int64_t>(live ? col : 0) * ldw;
+  for (int i0 = 0; i0 < b; i0 += 32) {
+    const int ib = min(32, b - i0);
+    double acc = 0.0;
+    for (int j0 = 0; j0 < i0; j0 += TRSMW_TILE) {
+      const int jb = min(TRSMW_TILE, i0 - j0);
+      __syncthreads();                                   // the previous tile has been consumed by every warp
+      for (int e = threadIdx.x; e < ib * jb; e += 256) {
+        const int r = e % ib, c = e / ib;                // consecutive threads: consecutive rows of one column of T
+        tt[r][c] = T[(i0 + r) + static_cast<int64_t>(j0 + c) * ldt];
+      }
+      __syncthreads();
+      if (live && lane < ib)
+        for (int c = 0; c < jb; ++c) acc += tt[lane][c] * x[j0 + c];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < ib * ib; e += 256) {
+      const int r = e % ib, c = e / ib;
+      td[r][c] = T[(i0 + r) + static_cast<int64_t>(i0 + c) * ldt];
+    }
+    __syncthreads();
+    double v = (live && lane < ib) ? wcol[i0 + lane] - acc : 0.0;
+    for (int s = 0; s < ib; ++s) {                        // forward substitution inside the block, one row per lane
+      const double xs = __shfl_sync(0xffffffffu, v, s) / td[s][s];
+      if (lane == s) v = xs;
+      else if (lane > s && lane < ib) v -= td[lane][s] * xs;
+    }
+    if (lane < ib) x[i0 + lane] = v;
+    __syncwarp();
+  }
+  if (live)
+    for (int r = lane; r < b; r += 32) wcol[r] = x[r];
+}
+
+int g_trsm_variant = 0;
+
 int trsm_llnn(int64_t b, int64_t kb, const double* T, int64_t ldt, double* W, int64_t ldw, cudaStream_t st) {
   if (b <= 0 || kb <= 0) return OK;
+  if (g_trsm_variant == 1 && sizeof(double) * b * TRSM_NC <= 160 * 1024) {
+    const size_t smem = sizeof(double) * b * TRSM_NC;
+    static size_t configured_w = 0;
+    if (smem > configured_w) {   // the kernel's 41 KiB of static shared memory count towards the 48 KiB default: always opt in
+      CANDMC_CUDA(cudaFuncSetAttribute(trsm_llnn_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_w = smem;
+    }
+    trsm_llnn_warp_kernel<<<(int)((kb + TRSM_NC - 1) / TRSM_NC), 256, smem, st>>>((int)b, (int)kb, T, ldt, W, ldw);
+    CANDMC_CUDA(cudaGetLastError());
+    runtime().launches++;
+    return OK;
+  }
   const size_t smem = sizeof(double) * b * TRSM_NC;
   CANDMC_CHECK(smem <= 200 * 1024, "upd_A: panel width b=%lld too large for the triangular solve kernel", (long long)b);
   static size_t configured = 0;
@@ -518,6 +581,12 @@ int candmc_set_panel_transport(int on) {
 }
 
 unsigned long long candmc_panel_transport_sends(void) { return runtime().transport_sends; }
+
+int candmc_set_trsm_variant(int variant) {
+  CANDMC_CHECK(variant == 0 || variant == 1, "candmc_set_trsm_variant: 0 (block barriers per row) or 1 (one warp per right-hand side)");
+  g_trsm_variant = variant;
+  return OK;
+}
 
 int candmc_host_pipeline_cut(int64_t n, int64_t k, int panels, int64_t* widths, int64_t* kchunks, int cap, int* npanels,
                              int* nchunks) {

@@ -98,6 +98,12 @@ static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   return out;
 }
 template <class T>
+static inline T __shfl_sync(unsigned, T v, int src_lane) {
+  T out;
+  ::cpusim::sync_warp_exchange(&v, &out, src_lane & 31, sizeof(T));
+  return out;
+}
+template <class T>
 static inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
   T out;
   int lane = (int)(::cpusim::ts().thread.x & 31u);

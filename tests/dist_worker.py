@@ -465,6 +465,22 @@ def pending_cases(world, golden):
     if P == 6:
         case_update_A(world, golden, "updw_m80_k48_b8_2x3_r00", 80, 48, 8, 2, 0, 0, with_W=True)
         case_update_A(world, golden, "updw_m80_k48_b8_2x3_r12", 80, 48, 8, 2, 1, 2, with_W=True)
+    # the opt-in triangular solve with one warp per right-hand side (candmc_set_trsm_variant(1)) under the same updates: block
+    # sizes below, at and above its 32-row blocks and 128-column T tiles, ragged right-hand-side counts
+    cb.lib().candmc_set_trsm_variant(1)
+    if P == 1:
+        case_update_A(world, golden, "upda_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0)
+        case_update_A(world, golden, "upda_trsmw_b40_1x1", 400, 120, 40, 1, 0, 0)
+        case_update_A(world, golden, "upda_trsmw_b200_1x1", 1000, 600, 200, 1, 0, 0)
+        case_update_A(world, golden, "updw_big_1x1", 1024, 512, 128, 1, 0, 0, with_W=True)
+    if P == 2:
+        case_upd_A(world, "upd_A_p2_trsmw", 64, 48, 16)
+    if P == 4:
+        case_upd_A(world, "upd_A_p4_trsmw", 96, 80, 32)
+        case_update_A(world, golden, "upda_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 0, 0)
+        case_update_A(world, golden, "upda_T_2x2_trsmw", 640, 480, 160, 2, 1, 1, with_T=True)
+        case_update_A(world, golden, "updw_big_2x2_r10", 1024, 768, 64, 2, 1, 0, with_W=True)
+    cb.lib().candmc_set_trsm_variant(0)
     from dmat_cases import case_names, load_golden
     dgold = load_golden()
     for name in case_names(dgold):

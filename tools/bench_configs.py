@@ -97,6 +97,12 @@ def main():
     ms = timed(lambda: cb.upd_A(Y, mb, Am, mb, mb, kb, k, T, ccol))
     report(f"config5: upd_A m=65536 n=8192 k=512 on {nprow}x{npcol}", 2 * 2.0 * m * ncol * k, ms,
            {"note": "flops = the two GEMMs (SURVEY §8d); all-reduce of W and the triangular solve are inside the time"})
+    # the same with the opt-in triangular solve (one warp per right-hand side instead of a block barrier per row of T)
+    cb.lib().candmc_set_trsm_variant(1)
+    ms = timed(lambda: cb.upd_A(Y, mb, Am, mb, mb, kb, k, T, ccol))
+    cb.lib().candmc_set_trsm_variant(0)
+    report(f"config5: upd_A m=65536 n=8192 k=512 on {nprow}x{npcol}, trsm variant 1", 2 * 2.0 * m * ncol * k, ms,
+           {"note": "candmc_set_trsm_variant(1), opt-in"})
     # 1-GPU local GEMM roofline at the Cannon block size (config 4, second half)
     if ws == 1:
         for n in (sz(12288), sz(16384)):

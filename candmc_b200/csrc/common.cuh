@@ -55,11 +55,13 @@ const char* last_error();
 
 // Shared-memory matrix descriptor of a K-major operand tile whose rows are 128-byte lines under the 128-byte swizzle (what a
 // TMA box of 32 floats x rows with CU_TENSOR_MAP_SWIZZLE_128B writes): start address >> 4 in bits [0,14), leading byte offset
-// (unused for swizzled K-major) 0 in [16,30), stride byte offset = 8 rows x 128 B = 1024 >> 4 in [32,46), descriptor version 1
-// in [46,48), base offset 0, layout type SWIZZLE_128B = 2 in [61,64)  (cute/arch/mma_sm100_desc.hpp, UMMA::SmemDescriptor).
+// in [16,30) (unused for swizzled K-major; 1 as CuTe's make_umma_desc sets it), stride byte offset = 8 rows x 128 B = 1024 >> 4
+// in [32,46), descriptor version 1 in [46,48), base offset 0, layout type SWIZZLE_128B = 2 in [61,64)
+// (cute/arch/mma_sm100_desc.hpp, UMMA::SmemDescriptor).  tests/test_cutlass_descriptors.py compares this and the instruction
+// descriptor below bit for bit with what CuTe itself builds for the same tile.
 CANDMC_HOSTDEV inline uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
-  return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) |
-         (2ull << 61);
+  return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
 }
 
 // Instruction descriptor of kind::tf32, FP32 accumulate, both operands K-major (UMMA::InstrDescriptor): c_format F32 = 1 in

@@ -28,5 +28,16 @@ int main() {
          "\"elem_offset_row1\": %d, \"elem_offset_row8\": %d, \"elem_offset_k8\": %d, \"elem_offset_k24\": %d}\n",
          (unsigned long long)d.desc_, (unsigned long long)candmc::umma_desc_kmajor_sw128(0), (unsigned)id.desc_,
          (unsigned)candmc::umma_idesc_tf32(128, 128), (int)plain(1, 0), (int)plain(8, 0), (int)plain(0, 8), (int)plain(0, 24));
+  // the swizzle itself: CuTe's composed layout against the XOR the simulator's TMA and UMMA emulation apply to byte addresses
+  // of a 1024-byte-aligned tile (16-byte chunk index ^= 128-byte line index mod 8)
+  int mismatches = 0;
+  for (int row = 0; row < 128; ++row)
+    for (int k = 0; k < 32; ++k) {
+      const uint32_t cute_bytes = (uint32_t)((const char*)&s(row, k) - (const char*)&s(0, 0));   // `fake` is 1024-byte aligned
+      uint32_t addr = (uint32_t)row * 128u + (uint32_t)k * 4u;
+      addr ^= ((addr >> 7) & 7u) << 4;
+      if (addr != cute_bytes) ++mismatches;
+    }
+  printf("{\"swizzle_mismatches\": %d}\n", mismatches);
   return 0;
 }

@@ -38,7 +38,9 @@ def test_umma_descriptors_match_cute(tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-3000:]
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
-    r = json.loads([line for line in out.splitlines() if line.startswith("{")][-1])
+    lines = [line for line in out.splitlines() if line.startswith("{")]
+    assert json.loads(lines[1])["swizzle_mismatches"] == 0     # CuTe's Swizzle<3,4,3> == the XOR of the simulator's TMA / UMMA emulation
+    r = json.loads(lines[0])
     assert r["candmc_smem_desc"] == r["cutlass_smem_desc"]     # SBO 1024 B, LBO, version 1, SWIZZLE_128B (start address 0 on the host)
     assert r["candmc_idesc"] == r["cutlass_idesc"]             # kind::tf32, F32 accumulate, K-major x K-major, M = N = 128
     # the address arithmetic of the kernel: rows 128 B apart, 8-row groups 1024 B apart (= SBO), K = 8 steps 32 B apart

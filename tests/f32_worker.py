@@ -25,6 +25,14 @@ import candmc_b200 as cb  # noqa: E402
 from candmc_b200._lib import lib, check  # noqa: E402
 
 check(lib().candmc_init(0))
+if "--one" in sys.argv:   # a single large launch for a profiler (tools/gpu_session.sh f32): no checks, no output worth reading
+    nb = int(sys.argv[sys.argv.index("--one") + 1])
+    x = torch.rand(nb * nb, dtype=torch.float32, device="cuda") - 0.5
+    z = torch.empty(nb * nb, dtype=torch.float32, device="cuda")
+    cb.csgemm("T", "N", nb, nb, nb, 1.0, x, nb, x, nb, 0.0, z, nb)
+    torch.cuda.synchronize()
+    print(json.dumps({"one": nb}))
+    sys.exit(0)
 TOL3 = 4 * 2.0 ** -20      # documented bound of the split scheme (3 * 2^-20 per product) plus FP32 accumulation
 TOL1 = 2.0 ** -9           # one TF32 product: 2 * 2^-11 per product, truncation
 worst = {1: 0.0, 3: 0.0}

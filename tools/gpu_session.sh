@@ -39,8 +39,8 @@ for section in "$@"; do
       # the FP32 tcgen05 GEMM: parity (first contact with hardware), first speeds, and an ncu pass that shows the tensor pipe
       timeout 600 python tests/f32_worker.py --bench > gpurun_out/f32_worker.json 2> gpurun_out/f32_worker.err
       tail -3 gpurun_out/f32_worker.json; tail -5 gpurun_out/f32_worker.err
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_f32_umma -c 2 -o gpurun_out/f32_gemm \
-        python tests/f32_worker.py > gpurun_out/f32_ncu.log 2>&1
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_f32_umma -c 1 -f -o gpurun_out/f32_gemm \
+        python tests/f32_worker.py --one 8192 > gpurun_out/f32_ncu.log 2>&1
       ncu -i gpurun_out/f32_gemm.ncu-rep --page raw --csv > gpurun_out/f32_gemm_raw.csv 2>/dev/null
       ;;
     pending1)
@@ -99,6 +99,10 @@ for section in "$@"; do
           bench.py --gpus 8 --steps 5 --warmup 3 $knobs >> gpurun_out/dist8_bench.log 2>&1
       done
       grep -E "==|\"metric\"" gpurun_out/dist8_bench.log | cut -c1-400
+      ;;
+    all1)
+      # everything that needs one GPU, cheapest first contact first (about 25 minutes of box time)
+      bash "$0" f32 pending1 lu e2e1 ncu
       ;;
     *) echo "unknown section $section";;
   esac

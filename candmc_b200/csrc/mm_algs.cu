@@ -328,12 +328,16 @@ int summa_sweep(SummaArgs& a) {
   return OK;
 }
 
-// ---- the cut of the host-streamed multiply below into column panels of C and of its first panel into k-chunks ----  Uniform (NP equal panels, NP equal
-// chunks: what B200s have measured with NP = 8) or graduated (the automatic choice for large products): what stays exposed is
-// the upload in front of the first multiply and the download behind the last one, so the first panel's k-chunks start small
-// and double (k/64, k/64, k/32, ... k/2: the first multiply waits for 1/64 of A instead of 1/NP) while the panel itself stays
-// wide enough (n/8) for its multiplies to cover the rest of A's upload, and the last panels shrink (n/16, n/32, n/32) so that
-// only 1/32 of C is downloaded after the last multiply.  Every piece but the last is a multiple of the CTA tile / the k-tile.
+// ---- the cut of the host-streamed multiply below into column panels of C and of its first panel into k-chunks ----
+// Uniform (NP equal panels, NP equal chunks: what B200s have measured with NP = 8) or graduated (the automatic choice for large
+// products).  What stays exposed is the upload in front of the first multiply, any upload the first panel's multiplies fail
+// to cover, and the download behind the last multiply.  The first panel has to hide the upload of ALL of A plus its own B
+// row slabs (2-D copies with one narrow row per column: about 2 us per row whatever its width), and chunk t+1 can only be
+// covered by the multiply of chunk t — so chunks that grow fast make the panel upload-bound (doubling chunks are WORSE than
+// equal ones; tools/host_pipeline_model.py).  The graduated cut therefore makes the first panel twice as wide as the others
+// (n/4: twice the multiply time per uploaded byte of A), starts its k-chunks at k/16 and lets them grow by a tenth each, and
+// shrinks the last panels (n/16, n/32, n/32) so that only 1/32 of C is downloaded after the last multiply.  Every piece but
+// the last is a multiple of the CTA tile / the k-tile.
 void host_pipeline_cut(int64_t n, int64_t k, int panels, std::vector<int64_t>* widths, std::vector<int64_t>* kchunks) {
   auto round_up = [](int64_t x, int64_t q) { return (x + q - 1) / q * q; };
   widths->clear();
@@ -354,6 +358,10 @@ void host_pipeline_cut(int64_t n, int64_t k, int panels, std::vector<int64_t>* w
     widths->push_back(base);
     rem -= base;
   }
+  if (widths->size() >= 3) {   // the first panel: two body panels in one
+    widths->erase(widths->begin());
+    (*widths)[0] += base;
+  }
   const int64_t mid = rem > tail ? (rem - tail) / 128 * 128 : 0;
   if (mid > 0) {
     widths->push_back(mid);
@@ -366,15 +374,15 @@ void host_pipeline_cut(int64_t n, int64_t k, int panels, std::vector<int64_t>* w
     }
   }
   if (rem > 0) widths->push_back(rem);   // <= t4 + 127 <= base
-  const int64_t unit = round_up((k + 63) / 64, 16);
-  int64_t k0 = 0;
-  for (int64_t mult : {1, 1, 2, 4, 8, 16}) {
-    const int64_t kc = std::min(unit * mult, k - k0);
-    if (kc <= 0) break;
+  const int64_t first = round_up((k + 15) / 16, 16);
+  double size = static_cast<double>(first);
+  for (int64_t k0 = 0; k0 < k;) {
+    int64_t kc = std::min(round_up(static_cast<int64_t>(size), 16), k - k0);
+    if (k - k0 - kc < first / 2) kc = k - k0;   // no crumb at the end
     kchunks->push_back(kc);
     k0 += kc;
+    size *= 1.1;
   }
-  if (k0 < k) kchunks->push_back(k - k0);
 }
 
 // ---- host-resident operands on a 1x1 grid: stream the multiply through PCIe -----------------------------------------

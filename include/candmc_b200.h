@@ -229,9 +229,9 @@ int candmc_set_min_kchunk(int64_t min_kchunk);
  * column panels (upload of panel j+1 and download of panel j-1 under the GEMM of panel j) instead of staged whole. */
 int candmc_set_host_pipeline_min(int64_t min_n);
 /* ... and how it is cut: n > 0 = n equal column panels (and n equal k-chunks of the first panel; 8 is what B200s have
- * measured), -1 = graduated (first panel n/8 wide with k-chunks doubling from k/64, last panels shrinking to n/32: 1/64 of A
- * is uploaded before the first multiply and 1/32 of C downloaded after the last), 0 = automatic (graduated when n, k >= 8192,
- * else 8 equal panels). */
+ * measured), -1 = graduated (first panel n/4 wide with k-chunks growing by a tenth from k/16, then n/8 panels, last panels
+ * shrinking to n/32: 1/16 of A is uploaded before the first multiply, each further chunk under the previous chunk's multiply,
+ * 1/32 of C downloaded after the last), 0 = automatic (graduated when n, k >= 8192, else 8 equal panels). */
 int candmc_set_host_pipeline_panels(int panels);
 /* The cut itself for an n-column, k-deep product (host arithmetic only; exposed for the CPU-side tests): panel widths and
  * the first panel's k-chunks, at most `cap` of each. */

@@ -510,8 +510,8 @@ def pending_cases(world, golden):
             cb.lib().candmc_set_host_pipeline_panels(16)    # the cut bench.py's n = 32768 gets
             case_d25(world, golden, f"d25_hostpipe16_n2304_{tag}", 2304, 1, 0, use_host=True, check_golden=False, oracle=False)
             case_d25(world, golden, f"d25_hostpipe16_n200_pad_{tag}", 200, 1, 0, lda_pad=3, use_host=True, check_golden=False)
-            # the graduated cut (automatic at n, k >= 8192: first panel n/8 wide with k-chunks doubling from k/64, last
-            # panels shrinking to n/32), forced at test sizes: 2304 = 18 tiles -> panels 384 x 4, 256, 128 x 4 ... and ragged ones
+            # the graduated cut (automatic at n, k >= 8192: first panel n/4 wide with k-chunks growing by a tenth from k/16, last
+            # panels shrinking to n/32), forced at test sizes: 2304 -> panels 768, 384, 384, 256, 256, 128, 128 ... and ragged ones
             cb.lib().candmc_set_host_pipeline_panels(-1)
             if min_kc == 1024:   # (the k-chunk knob belongs to the grid sweeps; the host pipeline does not read it)
                 case_d25(world, golden, f"d25_hostpipe_grad_n2304_{tag}", 2304, 1, 0, use_host=True, check_golden=False, oracle=False)

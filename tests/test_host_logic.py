@@ -99,17 +99,35 @@ def _cut(n, k, panels):
 
 
 def test_host_pipeline_cut_of_the_headline_size():
-    """bench.py's one-GPU end-to-end leg (n = k = 32768): the automatic cut is the graduated one — 1/64 of A in front of the
-    first multiply, the first panel n/8 wide (its multiplies cover the rest of A's upload), 1/32 of C behind the last one"""
+    """bench.py's one-GPU end-to-end leg (n = k = 32768): the automatic cut is the graduated one — first panel twice as wide as
+    the others, its k-chunks starting at k/16 and growing by a tenth (chunk t+1's upload must fit under chunk t's multiply: fast
+    growth makes the panel upload-bound, tools/host_pipeline_model.py), 1/32 of C behind the last multiply"""
     w, c = _cut(32768, 32768, 0)
-    assert w == [4096] * 7 + [2048, 1024, 1024]
-    assert c == [512, 512, 1024, 2048, 4096, 8192, 16384]
+    assert w == [8192] + [4096] * 5 + [2048, 1024, 1024]
+    assert c[0] == 2048 and c[:4] == [2048, 2256, 2480, 2736] and len(c) == 10
+    assert all(c[i + 1] <= 1.13 * c[i] + 16 for i in range(len(c) - 2))   # (the last chunk also takes the remainder)
     assert _cut(32768, 32768, -1) == (w, c)
     # uniform: what B200s have measured (8), and any explicit count
     assert _cut(32768, 32768, 8) == ([4096] * 8, [4096] * 8)
     assert _cut(32768, 32768, 16) == ([2048] * 16, [2048] * 16)
     # below 8192 the automatic choice stays 8 equal panels (the cut the validated GPU tests run)
     assert _cut(320, 320, 0) == ([128, 128, 64], [48] * 6 + [32])
+
+
+def test_host_pipeline_model_prefers_the_default_cut():
+    """tools/host_pipeline_model.py (three-stream timeline with the measured rates) on the library's own cuts: the default is
+    ahead of the measured 8 equal panels over the whole range of PCIe rates and per-row DMA costs considered, 16 equal panels
+    and doubling chunks are behind — a model, kept honest by bench.py measuring both passes"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("host_pipeline_model", os.path.join(ROOT, "tools", "host_pipeline_model.py"))
+    hm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(hm)
+    n = 32768
+    for rc in (0.5e-6, 2e-6):
+        for bw in (45e9, 55e9):
+            t = {p: hm.simulate(n, n, n, *hm.cut(n, n, p), rc, bw) for p in (0, 8, 16)}
+            assert t[0] < t[8] < t[16]
 
 
 @pytest.mark.parametrize("n,k", [(1, 1), (127, 5), (128, 16), (200, 200), (1100, 77), (2304, 2304), (8192, 8192), (12345, 9999),
@@ -122,5 +140,5 @@ def test_host_pipeline_cut_covers_the_product_exactly(n, k, panels):
     assert sum(w) == n and sum(c) == k and min(w) > 0 and min(c) > 0
     assert all(x % 128 == 0 for x in w[:-1]) and all(x % 16 == 0 for x in c[:-1])
     assert len(w) <= 70 and len(c) <= 70
-    if panels < 0 and n >= 2048:   # graduated: the last panel is at most a quarter of the widest (+ the ragged rest)
-        assert w[-1] <= max(w) // 4 + 255 and c[0] <= k // 64 + 16
+    if panels < 0 and n >= 2048:   # graduated: the last panel is at most an eighth of the first (+ the ragged rest)
+        assert w[-1] <= max(w) // 4 + 255 and c[0] <= k // 16 + 16

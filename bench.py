@@ -92,6 +92,46 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def host_unit_entries(n, rows, cols, which):
+    """The reference unit test's per-element generator on the HOST, in numpy integers (test/MM/topo_pdgemm_unit.cxx:250-256:
+    srand48(col*n + row); A = 1st, B = 2nd drand48() draw) for the element lists (rows[i], cols[i]); which = 0: A, 1: B.
+    48-bit LCG X <- (0x5DEECE66D X + 0xB) mod 2^48 from X0 = (seed mod 2^32) * 2^16 + 0x330E, value X / 2^48.  Used for the
+    one full-size check that shares no code with the GPU path (verification (iii))."""
+    import numpy as np
+
+    a, c, mask = np.uint64(0x5DEECE66D), np.uint64(0xB), np.uint64((1 << 48) - 1)
+    lo24 = np.uint64((1 << 24) - 1)
+
+    def step(x):   # a * x mod 2^48 without leaving 64 bits: x = xh * 2^24 + xl
+        xl, xh = x & lo24, x >> np.uint64(24)
+        return (a * xl + (((a * xh) & lo24) << np.uint64(24)) + c) & mask
+
+    seed = (np.asarray(cols, dtype=np.uint64) * np.uint64(n) + np.asarray(rows, dtype=np.uint64)) & np.uint64(0xFFFFFFFF)
+    x = step((seed << np.uint64(16)) | np.uint64(0x330E))
+    if which:
+        x = step(x)
+    return x.astype(np.float64) / float(1 << 48)
+
+
+def sampled_entries_check(torch, dC, b, n, row0, col0, count=48, seed=0):
+    """max over `count` entries of my C block of |C_ij - sum_k A_ik B_kj| / sum_k |A_ik B_kj| with A and B regenerated on the
+    host (float64 numpy).  Independent of every GPU kernel, the device generator included."""
+    import numpy as np
+
+    rng = np.random.default_rng(1234 + seed)
+    il, jl = rng.integers(0, b, count), rng.integers(0, b, count)
+    got = dC[torch.from_numpy(il + jl * b).to(dC.device)].cpu().numpy()
+    ks = np.arange(n, dtype=np.uint64)
+    worst = 0.0
+    for t in range(count):
+        i, j = int(row0 + il[t]), int(col0 + jl[t])
+        arow = host_unit_entries(n, np.full(n, i, dtype=np.uint64), ks, 0)     # A(i, k): row i, column k
+        bcol = host_unit_entries(n, ks, np.full(n, j, dtype=np.uint64), 1)     # B(k, j): row k, column j
+        ref = float(np.dot(arow, bcol))                                        # all terms are >= 0: sum |a b| = ref
+        worst = max(worst, abs(float(got[t]) - ref) / ref)
+    return worst
+
+
 def bind_to_gpu_numa_node(props):
     """Keep this rank's threads — and with them the first touch of its pinned host blocks — on the CPUs next to its GPU
     (sysfs local_cpulist of the GPU's PCI function), as `mpirun --bind-to numa` would for the reference's ranks.  Matters
@@ -334,6 +374,15 @@ def main():
         rel = max_over_ranks((d2 / r2) ** 0.5)
         del fa, fb, ref
 
+    # ... and a check that shares nothing with the GPU code: sampled entries of my block against operands regenerated on the host
+    sampled = None
+    try:
+        sampled = max_over_ranks(sampled_entries_check(torch, dC, b, n, row0, col0, seed=rank))
+    except Exception as exc:   # reported, never fatal: the measurement above stands on its own
+        sys.stderr.write(f"sampled-entries check skipped: {exc}\n")
+        if world_size > 1:
+            max_over_ranks(0.0)   # keep the collective count equal on every rank
+
     # ---- end-to-end leg: pinned host buffers through the same C-ABI call ----
     # Two passes unless the command line pins the knobs: first the host-operand settings B200s have already run (8 panels
     # on one GPU, both blocks uploaded, one C download after the last multiply), then the library's current defaults
@@ -418,6 +467,7 @@ def main():
             "pct_of_roofline": 100.0 * value / (2.0 * n ** 3 / t_roof / 1e12),
             "roofline_tflops": 2.0 * n ** 3 / t_roof / 1e12,
             "rel_frobenius_vs_cublas_crosscheck": rel, "tolerance_10_n_eps": 10 * n * 2.220446049250313e-16,
+            "max_rel_err_sampled_entries_vs_host_regenerated_operands": sampled,
             "exposed_non_gemm_pct": 100.0 * (1.0 - tms.value / ms_total) if ms_total > 0 else None,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "gemm_f64_tma_kernel (TMA + DMMA.8x8x4)", "achieved": achieved,

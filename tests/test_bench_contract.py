@@ -33,3 +33,27 @@ def test_product_arm_needs_a_gpu():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert p.returncode != 0 and p.stdout.strip() == ""   # no number without the CUDA path
+
+
+def test_host_generator_of_the_sampled_entries_check_is_the_reference_generator():
+    """bench.py's full-size check regenerates operands on the host with its own numpy LCG; it must be the reference unit test's
+    per-element generator (test/MM/topo_pdgemm_unit.cxx:250-256) bit for bit — compared with the oracle's blocks"""
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import oracle_py as orc
+
+    n = 48
+    A, B = orc.d25_blocks(n, 1, 1)
+    rows, cols = np.meshgrid(np.arange(n, dtype=np.uint64), np.arange(n, dtype=np.uint64), indexing="ij")
+    for which, ref in ((0, A[0]), (1, B[0])):
+        got = bench.host_unit_entries(n, rows.ravel(), cols.ravel(), which).reshape(n, n)
+        assert np.array_equal(got, np.asarray(ref).reshape(n, n, order="F") if np.asarray(ref).ndim == 1 else np.asarray(ref))
+    # the large seeds of the headline size (col * n + row up to 2^30) through the split 64-bit multiply
+    big = bench.host_unit_entries(32768, np.array([32767, 5], dtype=np.uint64), np.array([32767, 32000], dtype=np.uint64), 1)
+    for v, (r, c) in zip(big, ((32767, 32767), (5, 32000))):
+        x = (((c * 32768 + r) & 0xFFFFFFFF) << 16) | 0x330E
+        for _ in range(2):
+            x = (0x5DEECE66D * x + 0xB) & ((1 << 48) - 1)
+        assert v == x / float(1 << 48)

@@ -269,6 +269,8 @@ def test_bench_script_logic_on_the_simulator(nproc):
         assert key in d, key
     assert d["n_gpus"] == nproc and d["warmup"] >= 3 and d["dtype"] == "f64" and d["gpu_launches"] > 0
     assert d["rel_frobenius_vs_cublas_crosscheck"] <= d["tolerance_10_n_eps"]
+    # ... and the check that shares no code with the device path: sampled entries against operands regenerated on the host
+    assert d["max_rel_err_sampled_entries_vs_host_regenerated_operands"] <= d["tolerance_10_n_eps"]
     assert d["e2e"]["valid"] and d["e2e"]["rel_frobenius_vs_device_path"] <= d["tolerance_10_n_eps"]
     b = d["config"]["block"]
     # two end-to-end passes: the host-operand settings B200s have run, then the library's defaults; `e2e` is one of them

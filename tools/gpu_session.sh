@@ -60,6 +60,10 @@ for section in "$@"; do
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29536 \
         tools/bench_configs.py --pending > gpurun_out/bench_pending_4gpu.jsonl 2> gpurun_out/bench_pending_4gpu.err
       cat gpurun_out/bench_pending_4gpu.jsonl
+      # config 2 (b = 8192) with 2048-deep k-chunks instead of 1024: per-chunk epilogue and tail-wave losses halve
+      CANDMC_MIN_KCHUNK=2048 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
+        --master-port 29541 tools/bench_configs.py > gpurun_out/bench_configs_4gpu_kc2048.jsonl 2> gpurun_out/bench_configs_4gpu_kc2048.err
+      cat gpurun_out/bench_configs_4gpu_kc2048.jsonl
       # the opt-in peer-memory paths: parity first (same worker, switches from the environment), then configs 2 / 4 / 5 with
       # SUMMA panels and Cannon shifts on copy engines
       CANDMC_TEST_PANEL_TRANSPORT=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \

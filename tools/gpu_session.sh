@@ -3,7 +3,7 @@
 #   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh lu ncu'            (1 GPU)
 #   gpurun --gpus 4 --timeout 1200 -- 'bash tools/gpu_session.sh dist4'    (4 GPUs)
 #   gpurun --gpus 8 --timeout 1200 -- 'bash tools/gpu_session.sh dist8'    (8 GPUs)
-# Sections: f32 (FP32 tcgen05 GEMM: parity, speed, ncu), e2e1 / e2eN (end-to-end knobs added without a GPU: early C download, upload policy, panel count), lu (LU seam tests + LU bench host vs GPU), pending1 (redistribution / Yamamoto tests + their measurements), ncu (full capture at n=32768 for roofline.traffic, pack kernels),
+# Sections: f32 (FP32 tcgen05 GEMM: parity, speed, ncu), sanitize (compute-sanitizer memcheck / racecheck on the local kernels), e2e1 / e2eN (end-to-end knobs added without a GPU: early C download, upload policy, panel count), lu (LU seam tests + LU bench host vs GPU), pending1 (redistribution / Yamamoto tests + their measurements), ncu (full capture at n=32768 for roofline.traffic, pack kernels),
 #           dist4 (second-pass parity cases, update_A with T), dist8 (fused depth sum on 2x2x2, skip_unused_uploads)
 set -u
 cd "$(dirname "$0")/.."
@@ -103,6 +103,16 @@ for section in "$@"; do
           bench.py --gpus 8 --steps 5 --warmup 3 $knobs >> gpurun_out/dist8_bench.log 2>&1
       done
       grep -E "==|\"metric\"" gpurun_out/dist8_bench.log | cut -c1-400
+      ;;
+    sanitize)
+      # memcheck / racecheck over the local kernels at small sizes (FP64 GEMM all transposes, pack, FP32 GEMM)
+      for tool in memcheck racecheck; do
+        timeout 900 compute-sanitizer --tool $tool --error-exitcode 1 tools/gemm_probe check \
+          > gpurun_out/sanitize_${tool}_gemm_probe.log 2>&1; echo "$tool gemm_probe: exit $?"
+        timeout 900 compute-sanitizer --tool $tool --error-exitcode 1 python tests/f32_worker.py --one 384 \
+          > gpurun_out/sanitize_${tool}_f32.log 2>&1; echo "$tool f32: exit $?"
+      done
+      grep -h "ERROR SUMMARY" gpurun_out/sanitize_*.log
       ;;
     all1)
       # everything that needs one GPU, cheapest first contact first (about 25 minutes of box time)

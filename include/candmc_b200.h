@@ -96,7 +96,8 @@ int candmc_dgemm(char transa, char transb, int64_t m, int64_t n, int64_t k, doub
  * (tcgen05.mma kind::tf32, accumulator in tensor memory).  Device pointers only; asynchronous on `stream`.  Operands that
  * are not K-major and TMA-readable in place are packed into the library workspace first, so calls on different streams must
  * not overlap.  candmc_set_f32_mode: TF32 products per FP32 product — 3 (default): operands split into TF32 high and low
- * parts, relative error per product <= 3 * 2^-20 before the FP32 accumulation; 1: plain TF32 inputs (2^-11 per product). */
+ * parts, relative error per product <= 3 * 2^-20 before the FP32 accumulation (which adds what every single-precision GEMM
+ * has: of the order of sqrt(k) * 2^-24 of the summed terms); 1: plain TF32 inputs (2^-10 per product). */
 int candmc_sgemm(char transa, char transb, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t lda,
                  const float* B, int64_t ldb, float beta, float* C, int64_t ldc, void* stream);
 int candmc_set_f32_mode(int tf32_products);

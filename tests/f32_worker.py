@@ -33,7 +33,7 @@ if "--one" in sys.argv:   # a single large launch for a profiler (tools/gpu_sess
     torch.cuda.synchronize()
     print(json.dumps({"one": nb}))
     sys.exit(0)
-TOL3 = 4 * 2.0 ** -20      # documented bound of the split scheme (3 * 2^-20 per product) plus FP32 accumulation
+TOL3 = 4 * 2.0 ** -20      # documented bound of the split scheme (3 * 2^-20 per product, rounded up)
 TOL1 = 2.0 ** -9           # one TF32 product: 2 * 2^-11 per product, truncation
 worst = {1: 0.0, 3: 0.0}
 cases = 0
@@ -67,8 +67,10 @@ def run(ta, tb, m, n, k, alpha, beta, pad=0, c_nan=False, mode=3, seed=0, offset
     ref = alpha * (opA @ opB) + (beta * C[:m].astype(np.float64) if beta != 0.0 else 0.0)
     mag = abs(alpha) * (np.abs(opA) @ np.abs(opB)) + (abs(beta) * np.abs(C[:m]) if beta != 0.0 else 0.0)
     err = float((np.abs(got - ref) / np.maximum(mag, 1e-30)).max()) if m and n and (k or beta) else float(np.abs(got - ref).max())
-    tol = TOL3 if mode == 3 else TOL1
-    assert err <= tol, (ta, tb, m, n, k, alpha, beta, pad, mode, err)
+    # the split scheme's bound (per product, K-independent) + the FP32 accumulation every single-precision GEMM has: the
+    # tensor core adds K/8 partial sums per product term in FP32 (rounding unspecified), ~ sqrt(K) * 2^-24 of the summed terms
+    tol = (TOL3 if mode == 3 else TOL1) + 2.0 * max(k, 1) ** 0.5 * 2.0 ** -24
+    assert err <= tol, (ta, tb, m, n, k, alpha, beta, pad, mode, err, tol)
     if pad:   # rows below m are never written
         tail = dC.cpu().numpy().reshape(n, ldc).T[m:]
         assert np.array_equal(tail, C[m:]) or (c_nan and np.isnan(tail).all())

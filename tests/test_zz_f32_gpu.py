@@ -25,4 +25,5 @@ def test_sgemm_against_float64_product():
     rc, out, err = run_guarded("f32", [sys.executable, os.path.join(HERE, "f32_worker.py")], 240, ROOT)
     assert rc == 0, out[-2000:] + err[-3000:]
     r = json.loads(out.strip().splitlines()[-1])
-    assert r["cases"] >= 28 and r["max_rel_err_3xtf32"] <= r["tol_3xtf32"] and r["launches"] > 0
+    # (the worker asserts every case against its own bound: 4 * 2^-20 + 2 sqrt(k) 2^-24 for the split scheme)
+    assert r["cases"] >= 28 and r["max_rel_err_3xtf32"] <= 2e-5 and r["launches"] > 0

@@ -500,7 +500,7 @@ def pending_cases(world, golden):
             case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0, use_host=True)
         cb.set_min_kchunk(1024)
         cb.lib().candmc_set_skip_unused_uploads(0)
-    # ---- changes of the end-to-end path made without a GPU: early C download (default on), 16-panel host pipeline, and the
+    # ---- changes of the end-to-end path made without a GPU: early C download (default on), the cut of the host pipeline (16 equal panels, graduated), and the
     # persistent per-communicator state under repeated multiplies
     for min_kc in (1024, 8):
         cb.set_min_kchunk(min_kc)

@@ -507,7 +507,7 @@ def pending_cases(world, golden):
         tag = f"kc{min_kc}"
         if P == 1:
             cb.lib().candmc_set_host_pipeline_min(64)
-            cb.lib().candmc_set_host_pipeline_panels(16)    # the cut bench.py's n = 32768 gets
+            cb.lib().candmc_set_host_pipeline_panels(16)    # an explicit uniform cut other than the measured 8
             case_d25(world, golden, f"d25_hostpipe16_n2304_{tag}", 2304, 1, 0, use_host=True, check_golden=False, oracle=False)
             case_d25(world, golden, f"d25_hostpipe16_n200_pad_{tag}", 200, 1, 0, lda_pad=3, use_host=True, check_golden=False)
             # the graduated cut (automatic at n, k >= 8192: first panel n/4 wide with k-chunks growing by a tenth from k/16, last

@@ -476,7 +476,12 @@ def main():
                                         "FP64 entry); measured cuBLAS DGEMM on this pool = 36.0 TFLOP/s",
                          "frac_of_cublas_measured": achieved / CUBLAS_DGEMM_MEASURED_TFLOPS if achieved else None,
                          "launches": int(nl.value), "avg_launch_ms": tms.value / nl.value if nl.value else None,
-                         "flops_per_launch": tfl.value / nl.value if nl.value else None, "traffic": None},
+                         "flops_per_launch": tfl.value / nl.value if nl.value else None, "traffic": None,
+                         # no ncu --set full capture of THIS launch size yet (tools/gpu_session.sh ncu); the one that exists:
+                         "traffic_other_capture": {"launch": "8192^3", "dram_bytes": 6.772272e9 + 0.531282e9,
+                                                   "algorithmic_bytes": 3 * 8192 * 8192 * 8,
+                                                   "source": "profiles/r01_ncu_full_gemm_f64_tma_n8192.csv (2.9 % of DRAM peak: the "
+                                                             "kernel is tensor-bound, panels are re-read out of L2, hit rate 81 %)"}},
         }
         knobs = {k: v for k, v in (("bg_ctas", args.bg_ctas), ("fused_reduce", args.fused_reduce),
                                    ("upload_all_blocks", args.upload_all_blocks or None),

@@ -86,6 +86,18 @@ struct Block {
   std::vector<Warp> warps;
   std::map<uint32_t, MBar> mbars;
   NamedBar named[16];
+  // tcgen05.mma is asynchronous: issued operations are queued and executed as LATE as the program allows — when somebody waits
+  // on an mbarrier that a tcgen05.commit behind them will arrive on (or when the block ends).  A kernel that reads its
+  // accumulator without waiting for the commit sees stale tensor memory, one that refills a shared-memory stage without
+  // waiting for the commit has its operands overwritten before the multiply reads them: both show up as wrong results.
+  struct PendingUmma {
+    uint32_t tmem_d, idesc, accumulate;
+    uint64_t desc_a, desc_b;
+  };
+  std::vector<PendingUmma> umma_queue;
+  size_t umma_done = 0;                                    // operations [0, umma_done) have been executed
+  std::vector<std::pair<uint32_t, size_t>> umma_commits;   // (mbarrier, number of operations issued before the commit)
+  size_t commits_done = 0;
   std::vector<uint32_t> tmem;      // tensor memory of the SM the block runs on: 128 lanes x 512 columns of 32 bits
   uint32_t tmem_next = 0;          // bump allocator (columns)
   int tmem_live = 0;               // allocations not yet returned
@@ -228,7 +240,9 @@ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   --b.pending;
   mbar_check(b);
 }
+static void umma_complete_for(uint32_t bar);
 bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  umma_complete_for(bar);   // asynchronous multiplies complete no earlier than somebody waits for them
   if (mbar_get(bar).phase != (parity & 1u)) return true;
   if (g_cur >= 0) fiber_yield();
   return mbar_get(bar).phase != (parity & 1u);
@@ -404,7 +418,7 @@ static float umma_operand(const DecodedSmemDesc& d, uint32_t row, uint32_t k) {
   memcpy(&bits, smem_ptr(addr), 4);
   return tf32_of(bits);
 }
-void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+static void umma_execute(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   const unsigned sparse = idesc & 7, saturate = (idesc >> 3) & 1, cfmt = (idesc >> 4) & 3, afmt = (idesc >> 7) & 7,
                  bfmt = (idesc >> 10) & 7, neg = (idesc >> 13) & 3, amaj = (idesc >> 15) & 1, bmaj = (idesc >> 16) & 1,
                  N = ((idesc >> 17) & 0x3F) << 3, M = ((idesc >> 24) & 0x1F) << 4, shift = idesc >> 30;
@@ -436,7 +450,29 @@ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc
       memcpy(&cell, &acc, 4);
     }
 }
-void umma_commit(uint32_t bar) { mbar_arrive(bar); }   // MMAs complete when issued here, so the arrival is immediate
+void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  g_blk.umma_queue.push_back({tmem_d, idesc, accumulate, desc_a, desc_b});
+}
+void umma_commit(uint32_t bar) { g_blk.umma_commits.emplace_back(bar, g_blk.umma_queue.size()); }
+// Completes every commit up to the LAST pending one that arrives on `bar` (operations complete in issue order, so the commits
+// in front of it complete too); `bar` == 0: everything (block exit).
+static void umma_complete_upto(size_t ncommits) {
+  while (g_blk.commits_done < ncommits) {
+    const auto& cm = g_blk.umma_commits[g_blk.commits_done];
+    for (; g_blk.umma_done < cm.second; ++g_blk.umma_done) {
+      const Block::PendingUmma& u = g_blk.umma_queue[g_blk.umma_done];
+      umma_execute(u.tmem_d, u.desc_a, u.desc_b, u.idesc, u.accumulate);
+    }
+    ++g_blk.commits_done;
+    mbar_arrive(cm.first);
+  }
+}
+static void umma_complete_for(uint32_t bar) {
+  size_t upto = 0;
+  for (size_t i = g_blk.commits_done; i < g_blk.umma_commits.size(); ++i)
+    if (g_blk.umma_commits[i].first == bar) upto = i + 1;
+  if (upto) umma_complete_upto(upto);
+}
 void tmem_ld_32x32(uint32_t taddr, uint32_t* v) {
   const uint32_t lane0 = taddr >> 16, col0 = taddr & 0xFFFF, warp = (uint32_t)g_cur / 32, lane = (uint32_t)g_cur % 32;
   if (lane0 != 32 * (warp % 4)) {
@@ -525,6 +561,9 @@ static void execute(dim3 grid, dim3 block, size_t smem, const std::function<void
         g_blk.tmem.clear();
         g_blk.tmem_next = 0;
         g_blk.tmem_live = 0;
+        g_blk.umma_queue.clear();
+        g_blk.umma_commits.clear();
+        g_blk.umma_done = g_blk.commits_done = 0;
         for (NamedBar& nb : g_blk.named) nb = NamedBar();
         for (int t = 0; t < nthreads; ++t) {
           Fiber& f = g_fibers[t];
@@ -594,6 +633,10 @@ static void execute(dim3 grid, dim3 block, size_t smem, const std::function<void
                     g_blk.arrived, g_blk.alive);
             abort();
           }
+        }
+        if (g_blk.umma_done != g_blk.umma_queue.size() && g_blk.commits_done == g_blk.umma_commits.size()) {
+          fprintf(stderr, "cpusim: block (%u,%u,%u) exited with tcgen05.mma operations that were never committed\n", bx, by, bz);
+          abort();
         }
         if (g_blk.tmem_live != 0) {
           fprintf(stderr, "cpusim: block (%u,%u,%u) exited with tensor memory still allocated\n", bx, by, bz);

@@ -104,9 +104,9 @@ for section in "$@"; do
       done
       # fewer, deeper k-chunks per panel: per-launch epilogue and tail losses against a longer exposed first broadcast
       for kc in 4096 8192; do
-        echo "== bench 8 GPUs CANDMC_MIN_KCHUNK=$kc" >> gpurun_out/dist8_bench.log
-        CANDMC_MIN_KCHUNK=$kc timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
-          --master-port 29534 bench.py --gpus 8 --steps 5 --warmup 3 --no-e2e >> gpurun_out/dist8_bench.log 2>&1
+        echo "== bench 8 GPUs --min-kchunk $kc" >> gpurun_out/dist8_bench.log
+        timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+          --master-port 29534 bench.py --gpus 8 --steps 5 --warmup 3 --no-e2e --min-kchunk $kc >> gpurun_out/dist8_bench.log 2>&1
       done
       grep -E "==|\"metric\"" gpurun_out/dist8_bench.log | cut -c1-400
       ;;

@@ -26,6 +26,7 @@ from .mm import (  # noqa: F401
     fill_drand48,
     frob_diff,
     set_min_kchunk,
+    cdgemm_chunked_b,
     upd_Yamamoto_A,
     update_Yamamoto_A,
     cyclic_to_blocked,

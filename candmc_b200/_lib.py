@@ -54,11 +54,13 @@ SIGNATURES = {
     "candmc_set_early_c_download": (C.c_int, [C.c_int]),
     "candmc_set_panel_transport": (C.c_int, [C.c_int]),
     "candmc_panel_transport_sends": (C.c_ulonglong, []),
+    "candmc_merged_panel_launches": (C.c_ulonglong, [C.c_int]),
     "candmc_set_b_first_chunk_early": (C.c_int, [C.c_int]),
     "candmc_profile_enable": (C.c_int, [C.c_int]),
     "candmc_profile_gemm_timeline": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), i64, C.POINTER(i64)]),
     "candmc_set_background_ctas": (C.c_int, [C.c_int]),
     "candmc_profile_gemm_stats": (C.c_int, [C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "candmc_dgemm_chunked_b": (C.c_int, [C.c_char, i64, i64, i64, i64, C.c_double, pd, i64, pd, C.c_double, pd, i64, C.c_void_p]),
     "candmc_dgemm": (C.c_int, [C.c_char, C.c_char, i64, i64, i64, C.c_double, pd, i64, pd, i64, C.c_double, pd, i64,
                                C.c_void_p]),
     "candmc_set_trsm_variant": (C.c_int, [C.c_int]),
@@ -94,6 +96,7 @@ SIGNATURES = {
     "candmc_sym_full2band_update": (C.c_int, [pd, i64, i64, i64, i64, C.POINTER(PView), comm_p, pd, i64, C.c_void_p]),
     "candmc_sym_full2band_extents": (C.c_int, [i64, i64, i64] + [C.c_int] * 5 + [C.POINTER(i64)] * 4),
     "candmc_set_min_kchunk": (C.c_int, [i64]),
+    "candmc_set_merge_last_panel": (C.c_int, [C.c_int]),
     "candmc_set_host_pipeline_min": (C.c_int, [i64]),
     "candmc_set_host_pipeline_panels": (C.c_int, [C.c_int]),
     "candmc_redistribute": (C.c_int, [C.c_int, i64, i64, i64, pd, i64, pd, i64, C.POINTER(PView), C.c_void_p]),

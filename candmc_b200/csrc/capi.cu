@@ -85,6 +85,15 @@ int candmc_set_background_ctas(int max_ctas) {
   return OK;
 }
 
+int candmc_dgemm_chunked_b(char transa, int64_t m, int64_t n, int64_t k, int64_t kc, double alpha, const double* A, int64_t lda,
+                            const double* B, double beta, double* C, int64_t ldc, void* stream) {
+  CANDMC_TRY(runtime_require());
+  CANDMC_CHECK(m >= 0 && n >= 0 && k > 0 && kc > 0, "dgemm_chunked_b: bad dimensions");
+  if (m == 0 || n == 0) return OK;
+  CANDMC_CHECK(is_device_ptr(A) && is_device_ptr(B) && is_device_ptr(C), "dgemm_chunked_b: device pointers only");
+  return gemm_f64_bchunked(transa, m, n, k, alpha, A, lda, B, kc, beta, C, ldc, as_stream(stream));
+}
+
 int candmc_dgemm(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                  int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, void* stream) {
   CANDMC_TRY(runtime_require());

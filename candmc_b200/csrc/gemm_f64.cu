@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     double* __restrict__ C, int64_t ldc, int M, int N, int K, double alpha, double beta,
                     int tilesM, int tilesN, int* __restrict__ tile_counter, int ksplit, double* __restrict__ part,
-                    int* __restrict__ tile_sem, const __grid_constant__ FusedParams fp) {
+                    int* __restrict__ tile_sem, const __grid_constant__ FusedParams fp, int b_kc) {
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment for the 128 B swizzle atom; pointer arithmetic keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -176,7 +176,14 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int s = 0; s < 8; ++s) tma_load_2d(sa + s * 2048, &tmA, &full_bar[stage], m0 + 16 * s, k0);
           }
           if (B_KMAJ) {
-            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+            // chunk-major B (b_kc > 0; what the SUMMA pipeline receives its panels as): k-chunk ch is its own b_kc x N
+            // matrix behind chunk ch-1, so in tmB the chunks stand side by side as one b_kc x (N * chunks) matrix
+            if (b_kc > 0) {
+              const int ch = k0 / b_kc;
+              tma_load_2d(sb, &tmB, &full_bar[stage], k0 - ch * b_kc, n0 + ch * N);
+            } else {
+              tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+            }
           } else {
 #pragma unroll
             for (int s = 0; s < 8; ++s) tma_load_2d(sb + s * 2048, &tmB, &full_bar[stage], n0 + 16 * s, k0);
@@ -490,7 +497,7 @@ bool is_notrans(char t) { return t == 'N' || t == 'n'; }
 
 template <bool AK, bool BK_, bool FUSED>
 int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_t ldc, int M, int N, int K,
-               double alpha, double beta, cudaStream_t stream, const FusedParams* fused) {
+               double alpha, double beta, cudaStream_t stream, const FusedParams* fused, int b_kc = 0) {
   static bool configured = false;  // per template instantiation
   auto kern = gemm_f64_tma_kernel<AK, BK_, FUSED>;
   if (!configured) {
@@ -537,7 +544,7 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_
   FusedParams fp;
   if (FUSED) fp = *fused;
   kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmB, C, ldc, M, N, K, alpha, beta, tilesM, tilesN, counter, ksplit,
-                                               part, sem, fp);
+                                               part, sem, fp, b_kc);
   CANDMC_CUDA(cudaGetLastError());
   if (runtime().profile) CANDMC_TRY(profile_end_launch(stream));
   runtime().launches++;
@@ -555,6 +562,24 @@ int gemm_f64(char transa, char transb, int64_t m, int64_t n, int64_t k, double a
 int gemm_f64_fused(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                    int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, cudaStream_t stream,
                    const FusedParams* fused) {
+  return gemm_f64_ex(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, stream, fused, 0);
+}
+
+bool gemm_f64_bchunked_ok(const double* A, int64_t lda, const double* B, int64_t n, int64_t k, int64_t b_kc) {
+  return b_kc > 0 && k > 0 && k % b_kc == 0 && b_kc % BK == 0 && n * (k / b_kc) < (1LL << 31) && lda % 2 == 0 &&
+         reinterpret_cast<uintptr_t>(A) % 16 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0 && !runtime().force_generic;
+}
+
+int gemm_f64_bchunked(char transa, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                      const double* B, int64_t b_kc, double beta, double* C, int64_t ldc, cudaStream_t stream) {
+  CANDMC_CHECK(alpha != 0.0 && gemm_f64_bchunked_ok(A, lda, B, n, k, b_kc),
+               "dgemm(chunk-major B): needs k a multiple of the chunk depth, the chunk depth a multiple of %d, aligned operands", BK);
+  return gemm_f64_ex(transa, 'N', m, n, k, alpha, A, lda, B, b_kc, beta, C, ldc, stream, nullptr, b_kc);
+}
+
+int gemm_f64_ex(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                const double* B, int64_t ldb, double beta, double* C, int64_t ldc, cudaStream_t stream,
+                const FusedParams* fused, int64_t b_kc) {
   CANDMC_TRY(runtime_require());
   CANDMC_CHECK(is_trans(transa) || is_notrans(transa), "dgemm: bad transa '%c'", transa);
   CANDMC_CHECK(is_trans(transb) || is_notrans(transb), "dgemm: bad transb '%c'", transb);
@@ -564,7 +589,7 @@ int gemm_f64_fused(char transa, char transb, int64_t m, int64_t n, int64_t k, do
   CANDMC_CHECK(m < (1LL << 31) && n < (1LL << 31) && k < (1LL << 31), "dgemm: dimension exceeds 2^31-1");
   const int64_t rowsA = tA ? k : m, rowsB = tB ? n : k;
   CANDMC_CHECK(lda >= (rowsA > 1 ? rowsA : 1), "dgemm: lda=%lld < %lld", (long long)lda, (long long)rowsA);
-  CANDMC_CHECK(ldb >= (rowsB > 1 ? rowsB : 1), "dgemm: ldb=%lld < %lld", (long long)ldb, (long long)rowsB);
+  CANDMC_CHECK(b_kc > 0 || ldb >= (rowsB > 1 ? rowsB : 1), "dgemm: ldb=%lld < %lld", (long long)ldb, (long long)rowsB);
   CANDMC_CHECK(ldc >= (m > 1 ? m : 1), "dgemm: ldc=%lld < %lld", (long long)ldc, (long long)m);
   if (m == 0 || n == 0) return OK;
   const int M = (int)m, N = (int)n, K = (int)k;
@@ -592,6 +617,12 @@ int gemm_f64_fused(char transa, char transb, int64_t m, int64_t n, int64_t k, do
     const bool AK = tA;    // op(A)(m,kk) = A[kk + m*lda]  -> K contiguous
     const bool BKm = !tB;  // op(B)(kk,n) = B[kk + n*ldb]  -> K contiguous
     CANDMC_TRY(encode_tmap_f64(&tmA, A, AK ? k : m, AK ? m : k, lda, 16, AK ? BM : 16));
+    if (b_kc > 0) {   // chunk-major B: the k / b_kc chunks (b_kc x n, ld = b_kc) side by side
+      CANDMC_TRY(encode_tmap_f64(&tmB, B, b_kc, n * (k / b_kc), b_kc, 16, BN));
+      const int kc = static_cast<int>(b_kc);
+      if (AK) return launch_tma<true, true, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr, kc);
+      return launch_tma<false, true, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr, kc);
+    }
     CANDMC_TRY(encode_tmap_f64(&tmB, B, BKm ? k : n, BKm ? n : k, ldb, 16, BKm ? BN : 16));
     if (fused) {
       if (AK && BKm) return launch_tma<true, true, true>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused);
@@ -605,6 +636,7 @@ int gemm_f64_fused(char transa, char transb, int64_t m, int64_t n, int64_t k, do
     return launch_tma<false, false, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr);
   }
 
+  CANDMC_CHECK(b_kc == 0, "dgemm(chunk-major B): operands not TMA-able");
   dim3 grid((M + GT - 1) / GT, (N + GT - 1) / GT);
   CANDMC_CHECK(grid.y <= 65535, "dgemm(generic path): n too large for unaligned operands");
   gemm_f64_generic_kernel<<<grid, 256, 0, stream>>>(tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);

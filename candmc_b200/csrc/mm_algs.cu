@@ -282,7 +282,39 @@ int summa_sweep(SummaArgs& a) {
     const bool slabs = (i + 1 == a.i1 && a.fin_slabs > 1 && a.slab_done && nchunks >= 2 && a.fused == nullptr &&
                         is_n(a.tA) && is_n(a.tB) && b % a.fin_slabs == 0);
     const int h = slabs ? nchunks / 2 : nchunks;
-    for (int t = 0; t < h; ++t) {
+    // opt-in (candmc_set_merge_last_panel, not measured yet): the last panel of a sweep that has a panel in front of it no longer
+    // pipelines anything inside itself — its chunks were broadcast under the previous panel's multiplies as their slots came
+    // free — so all of its chunks but the last (whose slot was the last to come free: its broadcast hides under this launch)
+    // are multiplied in ONE launch: two epilogues and tail waves per panel instead of nchunks of each.  A's
+    // chunks are consecutive column slabs of one matrix; B's chunk-major slots are read through one tensor map.
+    int t_begin = 0;
+    if (runtime().merge_last_panel && nchunks > 2 && i + 1 == a.i1 && i > a.i0 && !slabs && a.fused == nullptr &&
+        is_n(a.tA) && is_n(a.tB)) {
+      const int mg = nchunks - 1;
+      std::vector<const double*> pa(mg), pb(mg);
+      std::vector<int64_t> lda(mg), ldb(mg);
+      // layouts first (pure pointer arithmetic on what operands() WILL return would duplicate it: ask it, the waits it
+      // enqueues are the ones the merged launch needs anyway, and harmless in front of per-chunk launches)
+      for (int t = 0; t < mg; ++t) CANDMC_TRY(operands(t, &pa[t], &lda[t], &pb[t], &ldb[t]));
+      bool a_one = true, b_plain = true, b_chunked = true;
+      for (int t = 0; t < mg; ++t) {
+        a_one = a_one && lda[t] == lda[0] && pa[t] == pa[0] + t * kc * lda[0];
+        b_plain = b_plain && ldb[t] == ldb[0] && pb[t] == pb[0] + t * kc;
+        b_chunked = b_chunked && ldb[t] == kc && pb[t] == pb[0] + t * kc * b;
+      }
+      const double beta0 = first ? 0.0 : 1.0;
+      if (a_one && b_chunked && gemm_f64_bchunked_ok(pa[0], lda[0], pb[0], b, mg * kc, kc)) {
+        CANDMC_TRY(gemm_f64_bchunked('N', b, b, mg * kc, 1.0, pa[0], lda[0], pb[0], kc, beta0, a.C, a.ldC, a.compute));
+        t_begin = mg;
+        runtime().merged_chunked++;
+      } else if (a_one && b_plain && !b_chunked) {
+        CANDMC_TRY(gemm_f64('N', 'N', b, b, mg * kc, 1.0, pa[0], lda[0], pb[0], ldb[0], beta0, a.C, a.ldC, a.compute));
+        t_begin = mg;
+        runtime().merged_plain++;
+      }
+      if (t_begin > 0) first = false;
+    }
+    for (int t = t_begin; t < h; ++t) {
       const double* pa;
       const double* pb;
       int64_t lda, ldb;
@@ -589,6 +621,9 @@ int candmc_set_panel_transport(int on) {
 }
 
 unsigned long long candmc_panel_transport_sends(void) { return runtime().transport_sends; }
+unsigned long long candmc_merged_panel_launches(int chunk_major_b) {
+  return chunk_major_b ? runtime().merged_chunked : runtime().merged_plain;
+}
 
 int candmc_set_trsm_variant(int variant) {
   CANDMC_CHECK(variant == 0 || variant == 1, "candmc_set_trsm_variant: 0 (block barriers per row) or 1 (one warp per right-hand side)");
@@ -619,6 +654,11 @@ int candmc_set_host_pipeline_panels(int panels) {
 int candmc_set_host_pipeline_min(int64_t min_n) {
   CANDMC_CHECK(min_n >= 1, "candmc_set_host_pipeline_min: must be >= 1");
   runtime().host_pipeline_min = min_n;
+  return OK;
+}
+
+int candmc_set_merge_last_panel(int on) {
+  runtime().merge_last_panel = (on != 0);
   return OK;
 }
 

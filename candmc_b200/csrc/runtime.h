@@ -13,6 +13,7 @@ struct Runtime {
   int num_sms = 0;
   int cc_major = 0, cc_minor = 0;
   bool force_generic = false;        // test hook: route dgemm through the CUDA-core kernel
+  unsigned long long merged_chunked = 0, merged_plain = 0;   // merged last-panel launches (summa_sweep): chunk-major B / plain B
   unsigned long long transport_sends = 0;   // panel chunks shipped by copy engines (transport.h)
   unsigned long long launches = 0;   // kernels launched by this library (bench.py's gpu_launches)
   cudaStream_t comm_stream = nullptr;   // NCCL panel traffic
@@ -42,6 +43,7 @@ struct Runtime {
                                         // (graduated at n, k >= 8192, else 8 uniform; host_pipeline_cut in mm_algs.cu)
   int64_t host_pipeline_min = 2048;     // smallest n for which host operands on a 1x1 grid are streamed panel-wise
   int64_t min_kchunk = 1024;            // smallest k-chunk the SUMMA pipeline cuts a panel into
+  bool merge_last_panel = false;        // SUMMA sweeps: the last panel's k-chunks multiplied in ONE launch (opt-in until measured)
 };
 
 Runtime& runtime();
@@ -91,6 +93,15 @@ struct FusedParams;
 int gemm_f64_fused(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                    int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, cudaStream_t stream,
                    const FusedParams* fused);
+// C = alpha * op(A) * B + beta * C with B in the SUMMA pipeline's chunk-major layout: k / b_kc consecutive chunks, chunk t the
+// rows [t * b_kc, (t+1) * b_kc) of B stored as a b_kc x n matrix with leading dimension b_kc.  One launch over all of k (no
+// per-chunk epilogue or tail wave); TMA path only — gemm_f64_bchunked_ok says whether the operands qualify.
+bool gemm_f64_bchunked_ok(const double* A, int64_t lda, const double* B, int64_t n, int64_t k, int64_t b_kc);
+int gemm_f64_bchunked(char transa, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                      const double* B, int64_t b_kc, double beta, double* C, int64_t ldc, cudaStream_t stream);
+int gemm_f64_ex(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                const double* B, int64_t ldb, double beta, double* C, int64_t ldc, cudaStream_t stream,
+                const FusedParams* fused, int64_t b_kc);
 int lda_copy_f64(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B,
                  cudaStream_t stream);
 int lda_axpby_f64(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B, double a,

@@ -86,6 +86,12 @@ def cdgemm(transa, transb, m, n, k, a, A, lda, B, ldb, b, Cm, ldc, stream=None):
                              _stream(stream)))
 
 
+def cdgemm_chunked_b(transa, m, n, k, kc, a, A, lda, B, b, Cm, ldc, stream=None):
+    """cdgemm with B (k x n, not transposed) in the SUMMA pipeline's chunk-major layout: chunk t = rows [t*kc, (t+1)*kc) stored
+    as a kc x n matrix with leading dimension kc (include/candmc_b200.h: candmc_dgemm_chunked_b)."""
+    check(lib().candmc_dgemm_chunked_b(_ch(transa), m, n, k, kc, a, _ptr(A), lda, _ptr(B), b, _ptr(Cm), ldc, _stream(stream)))
+
+
 def csgemm(transa, transb, m, n, k, a, A, lda, B, ldb, b, Cm, ldc, stream=None):
     """Single-precision companion of cdgemm (float32 device operands, tcgen05 kind::tf32 with split operands; the
     reference has no counterpart): C = a*op(A)*op(B) + b*C."""

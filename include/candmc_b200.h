@@ -66,6 +66,9 @@ int candmc_set_early_c_download(int on);
 int candmc_set_panel_transport(int on);
 /* Panel chunks this process has shipped that way so far (0 = the transport is off or fell back to NCCL). */
 unsigned long long candmc_panel_transport_sends(void);
+/* Merged last-panel launches so far (candmc_set_merge_last_panel): with B read chunk-major through one tensor map (1) or
+ * as a plain matrix on the panel's root (0).  Diagnostics for tests and benches. */
+unsigned long long candmc_merged_panel_launches(int chunk_major_b);
 /* Host B blocks: 1 = the rows of the first k-chunk are uploaded ahead of the rest so the first multiply starts earlier
  * (default 0: one copy of the whole block, whose wide rows keep the 2-D DMA efficient; the trade-off is not measured yet). */
 int candmc_set_b_first_chunk_early(int on);
@@ -91,6 +94,13 @@ int candmc_debug_force_generic_gemm(int on);
  * direct dgemm_ wrapper of split-dim Cannon (alg/MM/splitdim_cannon/spcannon_internal.h:51-63). */
 int candmc_dgemm(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                  int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, void* stream);
+/* The same multiply with op(B) = B (k x n) given in the SUMMA pipeline's CHUNK-MAJOR layout: k / kc consecutive chunks, chunk t
+ * holding rows [t*kc, (t+1)*kc) of B as a kc x n column-major matrix with leading dimension kc — what a rank holds after the
+ * chunk-wise panel broadcasts that replace the MPI_Bcast of summa.cxx:66-89 / d25_summa.cxx:124-136.  One launch over all of k
+ * (candmc_set_merge_last_panel uses it).  Device pointers only; k a multiple of kc, kc a multiple of 16, A and B 16-byte
+ * aligned, lda even, alpha != 0; anything else is an error (the callers inside the library fall back to one launch per chunk). */
+int candmc_dgemm_chunked_b(char transa, int64_t m, int64_t n, int64_t k, int64_t kc, double alpha, const double* A, int64_t lda,
+                           const double* B, double beta, double* C, int64_t ldc, void* stream);
 /* Single-precision companion (BASELINE north star: "optional FP32"; the reference has no single-precision multiply, so
  * this mirrors cdgemm's argument list with float data): C = alpha*op(A)*op(B) + beta*C on the 5th-generation tensor cores
  * (tcgen05.mma kind::tf32, accumulator in tensor memory).  Device pointers only; asynchronous on `stream`.  Operands that
@@ -226,6 +236,11 @@ int candmc_update_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_
  * (default 1024) so the broadcast of chunk t+1 runs under the GEMM of chunk t.  Tests lower it to exercise the
  * chunked path on small matrices. */
 int candmc_set_min_kchunk(int64_t min_kchunk);
+/* Tuning (opt-in, default 0; also CANDMC_MERGE_LAST_PANEL=1): in summa / d25_summa sweeps with at least two panels the LAST
+ * panel's k-chunks — all broadcast under the previous panel's multiplies — are multiplied in one launch (plus one for the chunk
+ * whose buffer slot came free last) instead of one launch per chunk; the reference has no counterpart (its summa.cxx:59-99
+ * multiplies a panel with one blocking dgemm_ after blocking broadcasts). */
+int candmc_set_merge_last_panel(int on);
 /* Tuning: on a 1x1x1 grid with HOST operands and n >= this (default 2048) the multiply is streamed through PCIe in
  * column panels (upload of panel j+1 and download of panel j-1 under the GEMM of panel j) instead of staged whole. */
 int candmc_set_host_pipeline_min(int64_t min_n);

@@ -61,8 +61,13 @@ _job("transport4", _torchrun(4, 29741, os.path.join(HERE, "dist_worker.py")), CA
      CPUSIM_SCHED="lifo")
 _job("transport8", _torchrun(8, 29742, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_PANEL_TRANSPORT="1",
      CANDMC_TEST_FUSED_GRIDS="1", CPUSIM_SCHED="lifo")
+# opt-in: the last panel of a sweep multiplied in one launch over its k-chunks (B read chunk-major through one tensor map by the
+# product's own kernel on the PTX emulation); the validated 2x2 suite with the switch on
+_job("merge4", _torchrun(4, 29743, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_MERGE_LAST_PANEL="1",
+     CPUSIM_SCHED="lifo")
 # the hot kernel itself on the PTX emulation, and the 4-rank suite with every GEMM going through it
 _job("kernel", [sys.executable, os.path.join(SIM, "probe_gemm.py")])
+_job("kernel_bchunk", [sys.executable, os.path.join(HERE, "bchunk_worker.py")])
 _job("kernel_f32", [sys.executable, os.path.join(HERE, "f32_worker.py"), "--fuzz", "17", "12" if not FULL else "80"])
 if FULL:
     _job("main4_device_gemm", _torchrun(4, 29719, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CPUSIM_GEMM="device")
@@ -303,6 +308,23 @@ def test_copy_engine_panel_transport_on_the_simulator(nproc):
     halves reused, windows regrown), no ncclBroadcast left on the path"""
     out = _dist(f"transport{nproc}")
     assert out["panel_transport_sends_rank0"] > 50
+
+
+def test_merged_last_panel_on_the_simulator():
+    """candmc_set_merge_last_panel(1) under the validated 2x2 suite (deferred streams, LIFO): same results, and the merged launch
+    with chunk-major B really ran (the 3x3 grid, ragged tile columns, host operands and the fallbacks are cases of the pending
+    group: test_widening_rows_on_the_simulator)"""
+    out = _dist("merge4")
+    assert out["merged_panel_launches_rank0"][0] > 0
+
+
+def test_hot_kernel_reads_chunk_major_b_through_one_tensor_map():
+    """candmc_dgemm_chunked_b on the PTX emulation: bit for bit the plain-layout launch of the same kernel, within 10 k eps of
+    numpy, loud errors for chunk depths that are not multiples of the k-tile"""
+    rc, so, se = RESULTS["kernel_bchunk"]
+    assert rc == 0, so[-2000:] + se[-3000:]
+    r = json.loads(so.strip().splitlines()[-1])
+    assert r["cases"] >= 10 and not r["failures"] and r["launches"] >= 14
 
 
 def test_hot_gemm_kernel_on_the_ptx_emulation():

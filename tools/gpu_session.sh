@@ -47,6 +47,10 @@ for section in "$@"; do
       # redistribution / Yamamoto tests on one GPU and the not-yet-measured widening rows
       timeout 1200 python -m pytest tests/test_zz_redist_gpu.py -m gpu -q -rA -p no:cacheprovider > gpurun_out/redist_pytest.log 2>&1
       tail -25 gpurun_out/redist_pytest.log
+      # the hot kernel with B chunk-major through one tensor map: parity (bit for bit against the plain launch), then one merged
+      # launch against seven per-chunk launches at b = 8192 / 16384 (the saving candmc_set_merge_last_panel is after)
+      timeout 600 python tests/bchunk_worker.py --bench > gpurun_out/bchunk_worker.json 2> gpurun_out/bchunk_worker.err
+      tail -2 gpurun_out/bchunk_worker.json; tail -3 gpurun_out/bchunk_worker.err
       timeout 900 python tools/bench_configs.py --pending > gpurun_out/bench_pending_1gpu.jsonl 2> gpurun_out/bench_pending_1gpu.err
       cat gpurun_out/bench_pending_1gpu.jsonl
       ;;
@@ -64,6 +68,20 @@ for section in "$@"; do
       CANDMC_MIN_KCHUNK=2048 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
         --master-port 29541 tools/bench_configs.py > gpurun_out/bench_configs_4gpu_kc2048.jsonl 2> gpurun_out/bench_configs_4gpu_kc2048.err
       cat gpurun_out/bench_configs_4gpu_kc2048.jsonl
+      # the last panel of a sweep in one launch over its k-chunks (opt-in): parity of the validated suite with it, then the headline
+      # grid and configs 2 / 4 / 5 (config 2 is where per-chunk epilogues and tails cost most)
+      CANDMC_TEST_MERGE_LAST_PANEL=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
+        --master-port 29542 tests/dist_worker.py > gpurun_out/dist4_merge.log 2>&1
+      tail -3 gpurun_out/dist4_merge.log
+      for knobs in "" "--merge-last-panel"; do
+        echo "== bench 4 GPUs --no-e2e $knobs" >> gpurun_out/dist4_bench_merge.log
+        timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29543 \
+          bench.py --gpus 4 --steps 5 --warmup 3 --no-e2e $knobs >> gpurun_out/dist4_bench_merge.log 2>&1
+      done
+      grep -E "==|\"metric\"" gpurun_out/dist4_bench_merge.log | cut -c1-400
+      CANDMC_MERGE_LAST_PANEL=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
+        --master-port 29544 tools/bench_configs.py > gpurun_out/bench_configs_4gpu_merge.jsonl 2> gpurun_out/bench_configs_4gpu_merge.err
+      cat gpurun_out/bench_configs_4gpu_merge.jsonl
       # the opt-in peer-memory paths: parity first (same worker, switches from the environment), then configs 2 / 4 / 5 with
       # SUMMA panels and Cannon shifts on copy engines
       CANDMC_TEST_PANEL_TRANSPORT=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \

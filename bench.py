@@ -243,6 +243,9 @@ def main():
                          "pay fewer per-launch epilogues and tail waves for a longer exposed first broadcast (DESIGN.md 10)")
     ap.add_argument("--merge-last-panel", action="store_true",
                     help="sweeps with two or more panels: the last panel's k-chunks in one launch (experimental, DESIGN.md 10)")
+    ap.add_argument("--merge-panels", type=int, default=None, choices=[0, 1, 2, 3],
+                    help="1 = --merge-last-panel; 2 = every panel as chunk 0 + one launch over the other chunks; 3 = every panel in "
+                         "doubling groups of chunks 1, 1, 2, 4 (experimental)")
     ap.add_argument("--fused-reduce", type=int, default=None, choices=[0, 1, 2],
                     help="depth sum: 0 NCCL, 1 fused on 1x1xc (default), 2 fused on q x q x c too (experimental)")
     ap.add_argument("--skip-unused-uploads", action="store_true", help="(default behaviour now; accepted for old scripts)")
@@ -292,6 +295,8 @@ def main():
         cb.lib().candmc_set_min_kchunk(args.min_kchunk)
     if args.merge_last_panel:
         cb.lib().candmc_set_merge_last_panel(1)
+    if args.merge_panels is not None:
+        cb.lib().candmc_set_merge_panels(args.merge_panels)
     if args.upload_all_blocks:
         cb.lib().candmc_set_skip_unused_uploads(0)
     if args.late_c_download:
@@ -492,7 +497,7 @@ def main():
                                                    "source": "profiles/r01_ncu_full_gemm_f64_tma_n8192.csv (2.9 % of DRAM peak: the "
                                                              "kernel is tensor-bound, panels are re-read out of L2, hit rate 81 %)"}},
         }
-        knobs = {k: v for k, v in (("bg_ctas", args.bg_ctas), ("fused_reduce", args.fused_reduce), ("min_kchunk", args.min_kchunk), ("merge_last_panel", args.merge_last_panel or None),
+        knobs = {k: v for k, v in (("bg_ctas", args.bg_ctas), ("fused_reduce", args.fused_reduce), ("min_kchunk", args.min_kchunk), ("merge_last_panel", args.merge_last_panel or None), ("merge_panels", args.merge_panels),
                                    ("upload_all_blocks", args.upload_all_blocks or None),
                                    ("late_c_download", args.late_c_download or None), ("b_first_chunk_early", args.b_first_chunk_early or None), ("panel_transport", args.panel_transport or None), ("host_panels", args.host_panels)) if v is not None}
         if knobs:

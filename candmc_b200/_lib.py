@@ -97,6 +97,7 @@ SIGNATURES = {
     "candmc_sym_full2band_extents": (C.c_int, [i64, i64, i64] + [C.c_int] * 5 + [C.POINTER(i64)] * 4),
     "candmc_set_min_kchunk": (C.c_int, [i64]),
     "candmc_set_merge_last_panel": (C.c_int, [C.c_int]),
+    "candmc_set_merge_panels": (C.c_int, [C.c_int]),
     "candmc_set_host_pipeline_min": (C.c_int, [i64]),
     "candmc_set_host_pipeline_panels": (C.c_int, [C.c_int]),
     "candmc_redistribute": (C.c_int, [C.c_int, i64, i64, i64, pd, i64, pd, i64, C.POINTER(PView), C.c_void_p]),

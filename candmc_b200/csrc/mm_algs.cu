@@ -282,39 +282,72 @@ int summa_sweep(SummaArgs& a) {
     const bool slabs = (i + 1 == a.i1 && a.fin_slabs > 1 && a.slab_done && nchunks >= 2 && a.fused == nullptr &&
                         is_n(a.tA) && is_n(a.tB) && b % a.fin_slabs == 0);
     const int h = slabs ? nchunks / 2 : nchunks;
-    // opt-in (candmc_set_merge_last_panel, not measured yet): the last panel of a sweep that has a panel in front of it no longer
-    // pipelines anything inside itself — its chunks were broadcast under the previous panel's multiplies as their slots came
-    // free — so all of its chunks but the last (whose slot was the last to come free: its broadcast hides under this launch)
-    // are multiplied in ONE launch: two epilogues and tail waves per panel instead of nchunks of each.  A's
-    // chunks are consecutive column slabs of one matrix; B's chunk-major slots are read through one tensor map.
-    int t_begin = 0;
-    if (runtime().merge_last_panel && nchunks > 2 && i + 1 == a.i1 && i > a.i0 && !slabs && a.fused == nullptr &&
-        is_n(a.tA) && is_n(a.tB)) {
-      const int mg = nchunks - 1;
-      std::vector<const double*> pa(mg), pb(mg);
-      std::vector<int64_t> lda(mg), ldb(mg);
-      // layouts first (pure pointer arithmetic on what operands() WILL return would duplicate it: ask it, the waits it
-      // enqueues are the ones the merged launch needs anyway, and harmless in front of per-chunk launches)
-      for (int t = 0; t < mg; ++t) CANDMC_TRY(operands(t, &pa[t], &lda[t], &pb[t], &ldb[t]));
-      bool a_one = true, b_plain = true, b_chunked = true;
-      for (int t = 0; t < mg; ++t) {
-        a_one = a_one && lda[t] == lda[0] && pa[t] == pa[0] + t * kc * lda[0];
-        b_plain = b_plain && ldb[t] == ldb[0] && pb[t] == pb[0] + t * kc;
-        b_chunked = b_chunked && ldb[t] == kc && pb[t] == pb[0] + t * kc * b;
+    // opt-in (candmc_set_merge_panels, not measured yet): several k-chunks of a panel in ONE launch — one epilogue and one tail
+    // wave for all of them instead of one per chunk.  A's chunks are consecutive column slabs of one matrix; B's
+    // chunk-major slots are read through one tensor map (gemm_f64_bchunked).  Which chunks:
+    //   mode 2, every panel: chunk 0 alone, then chunks 1 .. nc-1 together.  A chunk's broadcast takes a small fraction of its
+    //     multiply (NVLink against the FP64 pipe), so by the time chunk 0 has been multiplied the rest of the panel has arrived;
+    //     the exposed start of a sweep stays one chunk's broadcast.  (With the fused depth sum the last chunk stays apart: its
+    //     launch is the one with the reducing epilogue.)  Not with operands that are still being uploaded from host memory —
+    //     PCIe is slower than the multiply, that pipeline keeps its per-chunk launches.
+    //   mode 1, only the last panel of a sweep with a panel in front of it: chunks 0 .. nc-2 together (all broadcast under the
+    //     previous panel's multiplies), the last chunk — whose slot came free last — apart.
+    //   mode 3, every panel, for links that are only a few times faster than the multiply: groups that double — chunk 0,
+    //     chunk 1, chunks 2-3, chunks 4-7: each group only has to arrive while the one before it (as deep as all before
+    //     that together) is multiplied.  Four launches per panel of eight chunks.
+    std::vector<int> grp_hi(nchunks);   // chunks [t, grp_hi[t]) go in one launch when t starts a group
+    for (int t = 0; t < nchunks; ++t) grp_hi[t] = t + 1;
+    if (runtime().merge_panels > 0 && nchunks > 2 && !slabs && is_n(a.tA) && is_n(a.tB)) {
+      const bool last_panel = (i + 1 == a.i1);
+      const int mode = runtime().merge_panels;
+      if (mode >= 2 && a.a_ready == nullptr && a.b_ready == nullptr) {
+        const int lim = (last_panel && a.fused != nullptr) ? nchunks - 1 : nchunks;
+        if (mode == 2) {
+          if (lim > 1) grp_hi[1] = lim;
+        } else {
+          for (int lo = 2, sz = 2; lo < lim; lo += sz, sz *= 2) grp_hi[lo] = std::min(lim, lo + sz);
+        }
+      } else if (mode == 1 && last_panel && i > a.i0 && a.fused == nullptr) {
+        grp_hi[0] = nchunks - 1;
       }
-      const double beta0 = first ? 0.0 : 1.0;
-      if (a_one && b_chunked && gemm_f64_bchunked_ok(pa[0], lda[0], pb[0], b, mg * kc, kc)) {
-        CANDMC_TRY(gemm_f64_bchunked('N', b, b, mg * kc, 1.0, pa[0], lda[0], pb[0], kc, beta0, a.C, a.ldC, a.compute));
-        t_begin = mg;
-        runtime().merged_chunked++;
-      } else if (a_one && b_plain && !b_chunked) {
-        CANDMC_TRY(gemm_f64('N', 'N', b, b, mg * kc, 1.0, pa[0], lda[0], pb[0], ldb[0], beta0, a.C, a.ldC, a.compute));
-        t_begin = mg;
-        runtime().merged_plain++;
-      }
-      if (t_begin > 0) first = false;
     }
-    for (int t = t_begin; t < h; ++t) {
+    for (int t = 0; t < h; ++t) {
+      if (grp_hi[t] - t >= 2) {
+        const int mg_lo = t, mg = grp_hi[t] - t;
+        std::vector<const double*> pa(mg), pb(mg);
+        std::vector<int64_t> lda(mg), ldb(mg);
+        // ask operands() for the layouts: the waits it enqueues are the ones the merged launch needs, and harmless in front of
+        // per-chunk launches should the layouts not qualify
+        for (int u = 0; u < mg; ++u) CANDMC_TRY(operands(mg_lo + u, &pa[u], &lda[u], &pb[u], &ldb[u]));
+        bool a_one = true, b_plain = true, b_chunked = true;
+        for (int u = 0; u < mg; ++u) {
+          a_one = a_one && lda[u] == lda[0] && pa[u] == pa[0] + u * kc * lda[0];
+          b_plain = b_plain && ldb[u] == ldb[0] && pb[u] == pb[0] + u * kc;
+          b_chunked = b_chunked && ldb[u] == kc && pb[u] == pb[0] + u * kc * b;
+        }
+        const double beta0 = first ? 0.0 : 1.0;
+        bool done = false;
+        if (a_one && b_chunked && gemm_f64_bchunked_ok(pa[0], lda[0], pb[0], b, mg * kc, kc)) {
+          CANDMC_TRY(gemm_f64_bchunked('N', b, b, mg * kc, 1.0, pa[0], lda[0], pb[0], kc, beta0, a.C, a.ldC, a.compute));
+          runtime().merged_chunked++;
+          done = true;
+        } else if (a_one && b_plain && !b_chunked) {
+          CANDMC_TRY(gemm_f64('N', 'N', b, b, mg * kc, 1.0, pa[0], lda[0], pb[0], ldb[0], beta0, a.C, a.ldC, a.compute));
+          runtime().merged_plain++;
+          done = true;
+        }
+        if (done) {
+          first = false;
+          if (need_comm && i + 1 < a.i1) {   // the slots of all merged chunks come free together
+            cudaEvent_t e = g_events.get();
+            CANDMC_CHECK(e != nullptr, "event pool exhausted");
+            CANDMC_CUDA(cudaEventRecord(e, a.compute));
+            for (int u = 0; u < mg; ++u) done_prev[mg_lo + u] = e;
+          }
+          t = mg_lo + mg - 1;
+          continue;
+        }
+      }
       const double* pa;
       const double* pb;
       int64_t lda, ldb;
@@ -657,8 +690,11 @@ int candmc_set_host_pipeline_min(int64_t min_n) {
   return OK;
 }
 
-int candmc_set_merge_last_panel(int on) {
-  runtime().merge_last_panel = (on != 0);
+int candmc_set_merge_last_panel(int on) { return candmc_set_merge_panels(on ? 1 : 0); }
+
+int candmc_set_merge_panels(int mode) {
+  CANDMC_CHECK(mode >= 0 && mode <= 3, "candmc_set_merge_panels: 0 (off), 1 (last panel), 2 (every panel) or 3 (doubling groups)");
+  runtime().merge_panels = mode;
   return OK;
 }
 

@@ -76,7 +76,8 @@ int runtime_init(int device) {
   }
   if (env_int("CANDMC_BG_CTAS", &v) && v >= 0 && v <= 64) g_rt.bg_max_ctas = (int)v;
   if (env_int("CANDMC_MIN_KCHUNK", &v) && v >= 2) g_rt.min_kchunk = v;
-  if (env_int("CANDMC_MERGE_LAST_PANEL", &v)) g_rt.merge_last_panel = (v != 0);
+  if (env_int("CANDMC_MERGE_LAST_PANEL", &v)) g_rt.merge_panels = (v != 0) ? 1 : 0;
+  if (env_int("CANDMC_MERGE_PANELS", &v) && v >= 0 && v <= 3) g_rt.merge_panels = (int)v;
   if (env_int("CANDMC_EARLY_C_DOWNLOAD", &v)) g_rt.early_c_download = (v != 0);
   if (env_int("CANDMC_SKIP_UNUSED_UPLOADS", &v)) g_rt.skip_unused_uploads = (v != 0);
   g_rt.initialized = true;

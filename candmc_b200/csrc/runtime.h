@@ -43,7 +43,7 @@ struct Runtime {
                                         // (graduated at n, k >= 8192, else 8 uniform; host_pipeline_cut in mm_algs.cu)
   int64_t host_pipeline_min = 2048;     // smallest n for which host operands on a 1x1 grid are streamed panel-wise
   int64_t min_kchunk = 1024;            // smallest k-chunk the SUMMA pipeline cuts a panel into
-  bool merge_last_panel = false;        // SUMMA sweeps: the last panel's k-chunks multiplied in ONE launch (opt-in until measured)
+  int merge_panels = 0;                 // SUMMA sweeps: k-chunks multiplied in merged launches — 0 off, 1 last panel, 2 every panel, 3 doubling groups (opt-in until measured)
 };
 
 Runtime& runtime();

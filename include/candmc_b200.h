@@ -241,6 +241,13 @@ int candmc_set_min_kchunk(int64_t min_kchunk);
  * whose buffer slot came free last) instead of one launch per chunk; the reference has no counterpart (its summa.cxx:59-99
  * multiplies a panel with one blocking dgemm_ after blocking broadcasts). */
 int candmc_set_merge_last_panel(int on);
+/* The same switch with its second mode (also CANDMC_MERGE_PANELS=0/1/2): 0 off, 1 = candmc_set_merge_last_panel(1), 2 = EVERY
+ * panel of a sweep is multiplied as chunk 0 alone — the only chunk whose broadcast nothing hides — followed by ONE launch over
+ * chunks 1 .. nc-1, which have arrived by the time chunk 0 is multiplied (with the fused depth sum the last chunk keeps its own
+ * launch, the one with the reducing epilogue); 3 = every panel in groups that double (chunk 0, chunk 1, chunks 2-3, chunks 4-7):
+ * each group only has to arrive while the one before it is multiplied, for links only a few times faster than the multiply.
+ * Host operands that are still being uploaded keep one launch per chunk. */
+int candmc_set_merge_panels(int mode);
 /* Tuning: on a 1x1x1 grid with HOST operands and n >= this (default 2048) the multiply is streamed through PCIe in
  * column panels (upload of panel j+1 and download of panel j-1 under the GEMM of panel j) instead of staged whole. */
 int candmc_set_host_pipeline_min(int64_t min_n);

@@ -537,33 +537,37 @@ def pending_cases(world, golden):
             case_repeat(world, golden, f"repeat_2x2x2_{tag}", 2, [64, 64, 64, 64, 64, 64, 512, 64, 512, 512, 512])
             case_d25(world, golden, f"d25_n1024_c2_host_early_{tag}", 1024, 2, 0, use_host=True)
     cb.set_min_kchunk(1024)
-    # ---- the last panel of a sweep in ONE launch over its k-chunks (candmc_set_merge_last_panel, opt-in): the last of two (2x2)
-    # and of three (3x3) panels; chunk depths that are / are not multiples of the kernel's k-tile (16), B blocks of whole and
+    # ---- k-chunks of a panel in merged launches (candmc_set_merge_panels, opt-in): on 2x2 (two panels per sweep), 3x3 (three)
+    # and 2x2x2 (one per layer) grids; chunk depths that are / are not multiples of the kernel's k-tile (16), B blocks of whole and
     # ragged tile columns (n0 + 128 reaches into the next chunk's columns: results of columns that are never stored), host
     # operands (chunk-major staging on the root), odd leading dimensions (no TMA: back to one launch per chunk)
-    if P in (4, 9):
-        q = 2 if P == 4 else 3
-        cb.lib().candmc_set_merge_last_panel(1)
+    for mode in ((1, 2, 3) if P in (4, 9) else (2, 3) if P == 8 else ()):
+        q = {4: 2, 8: 2, 9: 3}[P]
+        c = 2 if P == 8 else 1
+        cb.lib().candmc_set_merge_panels(mode)   # 1: the last panel's chunks 0 .. nc-2 in one launch; 2: every panel chunk 0 + the rest; 3: every panel 1, 1, 2, 4
         m0 = [int(cb.lib().candmc_merged_panel_launches(x)) for x in (1, 0)]
         for min_kc, b, ovp, kw in ((8, 128, 0, {}), (48, 192, 1, {}), (16, 64, 0, {}), (8, 256, 0, dict(use_host=True)),
                                    (8, 128, 1, dict(lda_pad=2)), (8, 128, 0, dict(lda_pad=1)), (8, 96, 0, {}),
                                    (8, 128, 0, dict(use_host=True, lda_pad=2))):
             cb.set_min_kchunk(min_kc)
-            case_d25(world, golden, f"d25_merge_q{q}_b{b}_kc{min_kc}_{'_'.join(f'{k}{v}' for k, v in kw.items()) or 'plain'}",
-                     b * q, 1, ovp, check_golden=False, **kw)
+            case_d25(world, golden, f"d25_merge{mode}_q{q}_c{c}_b{b}_kc{min_kc}_{'_'.join(f'{k}{v}' for k, v in kw.items()) or 'plain'}",
+                     b * q, c, ovp, check_golden=False, **kw)
         cb.set_min_kchunk(8)
         if P == 4:
-            case_summa(world, golden, "summa_merge_n256", 256)
-            case_summa(world, golden, "summa_merge_n256_pad", 256, lda_pad=4)
+            case_summa(world, golden, f"summa_merge{mode}_n256", 256)
+            case_summa(world, golden, f"summa_merge{mode}_n256_pad", 256, lda_pad=4)
+        if P == 8:   # ... and under the fused depth sum on the 2x2x2 grid: the last chunk keeps its own (reducing) launch
+            cb.lib().candmc_set_fused_reduce(2)
+            case_d25(world, golden, f"d25_merge{mode}_fused_n1024_c2", 1024, 2, 0, check_golden=False)
+            cb.lib().candmc_set_fused_reduce(1)
         m1 = [int(cb.lib().candmc_merged_panel_launches(x)) for x in (1, 0)]
-        # every rank is off the last panel's root row or column in some case, and on it in others: both forms must have run
+        # every rank is off the panels' root row or column in some case, and on it in others: both forms must have run
         merged = torch.tensor([m1[0] - m0[0], m1[1] - m0[1]], dtype=torch.int64, device="cuda")
-        if P > 1:
-            dist.all_reduce(merged)
-        record(f"merge_last_panel_q{q}:chunk_major_launches", 0.0 if int(merged[0]) > 0 else 1.0, 0.5)
-        record(f"merge_last_panel_q{q}:plain_launches", 0.0 if int(merged[1]) > 0 else 1.0, 0.5)
+        dist.all_reduce(merged)
+        record(f"merge_panels{mode}_q{q}:chunk_major_launches", 0.0 if int(merged[0]) > 0 else 1.0, 0.5)
+        record(f"merge_panels{mode}_q{q}:plain_launches", 0.0 if int(merged[1]) > 0 else 1.0, 0.5)
         cb.set_min_kchunk(1024)
-        cb.lib().candmc_set_merge_last_panel(0)
+        cb.lib().candmc_set_merge_panels(0)
     if P in (1, 4):
         case_f2b_big(world, f"f2b_big_p{P}", 1024 * int(round(P ** 0.5)), 128, 32)
     shapes = {1: [(1,)], 2: [(2,), (1,)], 4: [(2,), (4,), (1,)], 8: [(2,), (4,)]}.get(P, [])
@@ -619,8 +623,8 @@ def main():
         cb.lib().candmc_set_fused_reduce(2)
     if os.environ.get("CANDMC_TEST_PANEL_TRANSPORT") == "1":   # SUMMA panels by copy engines into peer windows (opt-in in the product)
         cb.lib().candmc_set_panel_transport(1)
-    if os.environ.get("CANDMC_TEST_MERGE_LAST_PANEL") == "1":   # last panel of a sweep in one launch over its k-chunks (opt-in in the product)
-        cb.lib().candmc_set_merge_last_panel(1)
+    if os.environ.get("CANDMC_TEST_MERGE_PANELS", "0") != "0":   # k-chunks of a panel in merged launches: 1 last panel, 2 every panel (opt-in in the product)
+        cb.lib().candmc_set_merge_panels(int(os.environ["CANDMC_TEST_MERGE_PANELS"]))
     golden = np.load(os.path.join(ROOT, "tests", "golden", "canmm_ref_outputs.npz"))
     P = world_size
     only_pending = os.environ.get("CANDMC_TEST_PENDING") == "1"
@@ -701,6 +705,10 @@ def main():
     flag = torch.tensor([len(fails)], dtype=torch.int64, device="cuda")
     if world_size > 1:
         dist.all_reduce(flag)
+    merged_all = torch.tensor([int(cb.lib().candmc_merged_panel_launches(1)), int(cb.lib().candmc_merged_panel_launches(0))],
+                              dtype=torch.int64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(merged_all)
     for name, ok, err, tol in fails:
         print(f"[rank {rank}] FAIL {name}: err={err:.3e} tol={tol:.3e}", flush=True)
     if rank == 0:
@@ -708,7 +716,7 @@ def main():
                           "max_err_rank0": max((r[2] for r in RESULTS), default=0.0),
                           "launches_rank0": cb.launch_count(),
                           "panel_transport_sends_rank0": int(cb.lib().candmc_panel_transport_sends()),
-                          "merged_panel_launches_rank0": [int(cb.lib().candmc_merged_panel_launches(1)), int(cb.lib().candmc_merged_panel_launches(0))]}), flush=True)
+                          "merged_panel_launches_all_ranks": [int(merged_all[0]), int(merged_all[1])]}), flush=True)
     world.free()
     if world_size > 1:
         dist.destroy_process_group()

@@ -39,7 +39,7 @@ def main():
             kinds += ["dcn"]
         kind = rng.choice(kinds)
         cb.set_min_kchunk(rng.choice([1024, 8, 2, 16]))
-        cb.lib().candmc_set_merge_last_panel(rng.choice([0, 1]))
+        cb.lib().candmc_set_merge_panels(rng.choice([0, 1, 2, 3]))
         pad = rng.choice([0, 0, 1, 2, 3])
         tag = f"fz{seed}.{it}.{kind}"
         if kind == "d25":

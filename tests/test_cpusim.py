@@ -46,7 +46,7 @@ def _torchrun(nproc, port, script, *args):
 
 
 DIST_MAIN = [1, 2, 4, 8] if FULL else [2, 4, 8]
-DIST_PENDING = [1, 2, 3, 4, 6, 8, 9, 16] if FULL else [1, 3, 4, 6, 9]
+DIST_PENDING = [1, 2, 3, 4, 6, 8, 9, 16] if FULL else [1, 3, 4, 6, 8, 9]
 GOLD = np.load(os.path.join(HERE, "golden", "lu_offload_ref_outputs.npz"))
 SCRIPTS = sorted(k[: -len("__script")] for k in GOLD.files if k.endswith("__script"))
 REDIST = [(24, 36, 2, 2, 3, 0, 0), (36, 24, 3, 3, 2, 1, 1), (30, 30, 5, 3, 3, 0, 2), (16, 16, 4, 1, 4, 0, 3), (512, 256, 32, 2, 2, 1, 0)]
@@ -63,8 +63,15 @@ _job("transport8", _torchrun(8, 29742, os.path.join(HERE, "dist_worker.py")), CA
      CANDMC_TEST_FUSED_GRIDS="1", CPUSIM_SCHED="lifo")
 # opt-in: the last panel of a sweep multiplied in one launch over its k-chunks (B read chunk-major through one tensor map by the
 # product's own kernel on the PTX emulation); the validated 2x2 suite with the switch on
-_job("merge4", _torchrun(4, 29743, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_MERGE_LAST_PANEL="1",
+_job("merge4", _torchrun(4, 29743, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_MERGE_PANELS="1",
      CPUSIM_SCHED="lifo")
+# ... and every panel as chunk 0 + one launch over the rest, on 2x2 and (with the fused depth sum) on 2x2x2
+_job("merge4_all", _torchrun(4, 29744, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_MERGE_PANELS="2",
+     CPUSIM_SCHED="lifo")
+_job("merge4_doubling", _torchrun(4, 29746, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_MERGE_PANELS="3",
+     CPUSIM_SCHED="random:22")
+_job("merge8_all", _torchrun(8, 29745, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_MERGE_PANELS="2",
+     CANDMC_TEST_FUSED_GRIDS="1", CPUSIM_SCHED="random:21")
 # the hot kernel itself on the PTX emulation, and the 4-rank suite with every GEMM going through it
 _job("kernel", [sys.executable, os.path.join(SIM, "probe_gemm.py")])
 _job("kernel_bchunk", [sys.executable, os.path.join(HERE, "bchunk_worker.py")])
@@ -310,12 +317,13 @@ def test_copy_engine_panel_transport_on_the_simulator(nproc):
     assert out["panel_transport_sends_rank0"] > 50
 
 
-def test_merged_last_panel_on_the_simulator():
-    """candmc_set_merge_last_panel(1) under the validated 2x2 suite (deferred streams, LIFO): same results, and the merged launch
-    with chunk-major B really ran (the 3x3 grid, ragged tile columns, host operands and the fallbacks are cases of the pending
-    group: test_widening_rows_on_the_simulator)"""
-    out = _dist("merge4")
-    assert out["merged_panel_launches_rank0"][0] > 0
+@pytest.mark.parametrize("job", ["merge4", "merge4_all", "merge4_doubling", "merge8_all"])
+def test_merged_panel_launches_on_the_simulator(job):
+    """candmc_set_merge_panels(1 / 2 / 3) under the validated 2x2 and 2x2x2 suites (deferred streams, LIFO / random order): same
+    results, and the merged launch with chunk-major B really ran (the 3x3 grid, ragged tile columns, host operands and the
+    fallbacks are cases of the pending group: test_widening_rows_on_the_simulator)"""
+    out = _dist(job)
+    assert out["merged_panel_launches_all_ranks"][0] > 0 and out["merged_panel_launches_all_ranks"][1] > 0
 
 
 def test_hot_kernel_reads_chunk_major_b_through_one_tensor_map():

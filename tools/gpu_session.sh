@@ -70,16 +70,16 @@ for section in "$@"; do
       cat gpurun_out/bench_configs_4gpu_kc2048.jsonl
       # the last panel of a sweep in one launch over its k-chunks (opt-in): parity of the validated suite with it, then the headline
       # grid and configs 2 / 4 / 5 (config 2 is where per-chunk epilogues and tails cost most)
-      CANDMC_TEST_MERGE_LAST_PANEL=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
+      CANDMC_TEST_MERGE_PANELS=2 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
         --master-port 29542 tests/dist_worker.py > gpurun_out/dist4_merge.log 2>&1
       tail -3 gpurun_out/dist4_merge.log
-      for knobs in "" "--merge-last-panel"; do
+      for knobs in "" "--merge-panels 1" "--merge-panels 2" "--merge-panels 3"; do
         echo "== bench 4 GPUs --no-e2e $knobs" >> gpurun_out/dist4_bench_merge.log
         timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29543 \
           bench.py --gpus 4 --steps 5 --warmup 3 --no-e2e $knobs >> gpurun_out/dist4_bench_merge.log 2>&1
       done
       grep -E "==|\"metric\"" gpurun_out/dist4_bench_merge.log | cut -c1-400
-      CANDMC_MERGE_LAST_PANEL=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
+      CANDMC_MERGE_PANELS=2 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
         --master-port 29544 tools/bench_configs.py > gpurun_out/bench_configs_4gpu_merge.jsonl 2> gpurun_out/bench_configs_4gpu_merge.err
       cat gpurun_out/bench_configs_4gpu_merge.jsonl
       # the opt-in peer-memory paths: parity first (same worker, switches from the environment), then configs 2 / 4 / 5 with
@@ -115,7 +115,10 @@ for section in "$@"; do
       CANDMC_TEST_PANEL_TRANSPORT=1 CANDMC_TEST_FUSED_GRIDS=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
         --master-addr 127.0.0.1 --master-port 29540 tests/dist_worker.py > gpurun_out/dist8_peer_paths.log 2>&1
       tail -4 gpurun_out/dist8_peer_paths.log
-      for knobs in "" "--fused-reduce 2" "--panel-transport" "--panel-transport --fused-reduce 2"; do
+      CANDMC_TEST_MERGE_PANELS=2 CANDMC_TEST_FUSED_GRIDS=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+        --master-addr 127.0.0.1 --master-port 29546 tests/dist_worker.py > gpurun_out/dist8_merge.log 2>&1
+      tail -3 gpurun_out/dist8_merge.log
+      for knobs in "" "--merge-panels 2" "--merge-panels 3" "--fused-reduce 2" "--merge-panels 2 --fused-reduce 2" "--panel-transport" "--panel-transport --fused-reduce 2"; do
         echo "== bench 8 GPUs $knobs" >> gpurun_out/dist8_bench.log
         timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29534 \
           bench.py --gpus 8 --steps 5 --warmup 3 $knobs >> gpurun_out/dist8_bench.log 2>&1

@@ -424,6 +424,11 @@ CUresult fake_encode_tiled(CUtensorMap* out, CUtensorMapDataType dt, cuuint32_t 
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0 || gstride[0] % 16 != 0) return CUDA_ERROR_INVALID_VALUE;
   if (box[0] == 0 || box[1] == 0 || box[0] > 256 || box[1] > 256 || estride[0] != 1 || estride[1] != 1) return CUDA_ERROR_INVALID_VALUE;
   if (sw == CU_TENSOR_MAP_SWIZZLE_128B && box[0] * es > 128) return CUDA_ERROR_INVALID_VALUE;
+  // extents: each dimension 1 .. 2^32, row pitch below 2^40 bytes and not shorter than a row, box no larger than the tensor's limits allow
+  for (int d = 0; d < 2; ++d)
+    if (gdim[d] == 0 || gdim[d] > (1ull << 32)) return CUDA_ERROR_INVALID_VALUE;
+  if (gstride[0] >= (1ull << 40) || gstride[0] < gdim[0] * es) return CUDA_ERROR_INVALID_VALUE;
+  if ((box[0] * es) % 16 != 0) return CUDA_ERROR_INVALID_VALUE;   // inner box extent: whole 16-byte units
   if (sw != CU_TENSOR_MAP_SWIZZLE_128B && sw != CU_TENSOR_MAP_SWIZZLE_NONE) return CUDA_ERROR_INVALID_VALUE;
   memset(out, 0, sizeof(*out));
   cpusim::SimTensorMap m;

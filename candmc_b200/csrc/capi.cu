@@ -59,6 +59,22 @@ int candmc_debug_splitk(int on) {
   return OK;
 }
 
+int candmc_debug_transpose_tma(int on) {
+  runtime().transpose_tma = (on != 0);
+  return OK;
+}
+
+int candmc_debug_prefetch_c(int on) {
+  runtime().prefetch_c = (on != 0);
+  return OK;
+}
+
+int candmc_debug_gemm_reserve_sms(int sms) {
+  CANDMC_CHECK(sms >= 0 && sms <= 64, "candmc_debug_gemm_reserve_sms: 0..64");
+  runtime().gemm_reserve_sms = sms;
+  return OK;
+}
+
 int candmc_debug_static_schedule(int on) {
   runtime().static_schedule = (on != 0);
   return OK;

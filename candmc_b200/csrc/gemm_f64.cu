@@ -43,6 +43,7 @@ constexpr int PRODUCER_REGS = 40;                     // 4 warps x 40 + 8 warps 
 constexpr int CONSUMER_REGS = 232;
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers + tile ids*/;
 constexpr int RASTER_GROUP = 8;
+constexpr int PF_WINDOW = 64;      // k-tiles before the end of a unit over which the C tile's L2 prefetch is spread
 constexpr int kSplitSemCount = 4096;  // tiles a split-K launch may have (it is only used for small tile counts)
 
 // index-slot permutation shared by A rows and B cols (see header comment)
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     double* __restrict__ C, int64_t ldc, int M, int N, int K, double alpha, double beta,
                     int tilesM, int tilesN, int* __restrict__ tile_counter, int ksplit, double* __restrict__ part,
-                    int* __restrict__ tile_sem, const __grid_constant__ FusedParams fp, int b_kc) {
+                    int* __restrict__ tile_sem, const __grid_constant__ FusedParams fp, int b_kc, int pf_c) {
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment for the 128 B swizzle atom; pointer arithmetic keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -162,6 +163,14 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const UnitTile tc = unit_tile<FUSED>(t / ksplit, tilesM, tilesN, fp);
         const int m0 = tc.tm * BM, n0 = tc.tn * BN;
         const int kt0 = (t % ksplit) * KTS, kt1 = min(KT, kt0 + KTS);
+        // beta != 0: the tile of C the epilogue will read is pulled into L2 while the last k-tiles of the unit are being
+        // loaded (one bulk prefetch per column, spread over up to PF_WINDOW k-tiles), so the epilogue's loads hit L2
+        // instead of waiting on HBM with the DMMA pipe idle
+        const int pf_w = pf_c ? min(kt1 - kt0, PF_WINDOW) : 0;
+        const int pf_per = pf_w > 0 ? (BN + pf_w - 1) / pf_w : 0;
+        const double* pf_src = FUSED ? fp.Cin : C;
+        const int64_t pf_ld = FUSED ? fp.ldin : ldc;
+        const uint32_t pf_bytes = static_cast<uint32_t>(min(BM, M - m0) & ~1) * 8u;
         for (int kt = kt0; kt < kt1; ++kt) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (kt == kt0) stage_tile[stage] = t;
@@ -187,6 +196,11 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else {
 #pragma unroll
             for (int s = 0; s < 8; ++s) tma_load_2d(sb + s * 2048, &tmB, &full_bar[stage], n0 + 16 * s, k0);
+          }
+          if (pf_w > 0 && kt1 - kt <= pf_w && pf_bytes > 0) {
+            const int c0 = (pf_w - (kt1 - kt)) * pf_per;
+            for (int c = c0; c < min(BN, c0 + pf_per); ++c)
+              if (n0 + c < N) l2_prefetch_bulk(pf_src + m0 + static_cast<int64_t>(n0 + c) * pf_ld, pf_bytes);
           }
           if (++stage == NSTAGE) {
             stage = 0;
@@ -533,7 +547,7 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_
   }
   double* part = nullptr;
   int* sem = nullptr;
-  if (ksplit > 1) CANDMC_TRY(splitk_buffers(tiles * ksplit * BM * BN, &part, &sem));
+  if (ksplit > 1) CANDMC_TRY(splitk_buffers(tiles * ksplit * BM * BN, &part, &sem, stream));
   const int64_t ntiles = tiles * ksplit;
   // leave `gemm_reserve_sms` SMs free when a schedule wants NCCL kernels to run beside this persistent kernel
   const int avail = sms - runtime().gemm_reserve_sms > 0 ? sms - runtime().gemm_reserve_sms : 1;
@@ -543,9 +557,15 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_
   if (runtime().profile) CANDMC_TRY(profile_begin_launch(stream, 2.0 * M * (double)N * (double)K));
   FusedParams fp;
   if (FUSED) fp = *fused;
+  // L2 prefetch of the C tile in front of a beta != 0 epilogue (bulk prefetches need 16-byte aligned column segments)
+  const double* cin = FUSED ? fp.Cin : C;
+  const int64_t ldin = FUSED ? fp.ldin : ldc;
+  const int pf_c = (runtime().prefetch_c && beta != 0.0 && ksplit == 1 && cin != nullptr &&
+                    reinterpret_cast<uintptr_t>(cin) % 16 == 0 && ldin % 2 == 0) ? 1 : 0;
   kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmB, C, ldc, M, N, K, alpha, beta, tilesM, tilesN, counter, ksplit,
-                                               part, sem, fp, b_kc);
+                                               part, sem, fp, b_kc, pf_c);
   CANDMC_CUDA(cudaGetLastError());
+  if (ksplit > 1) CANDMC_TRY(splitk_release(stream));
   if (runtime().profile) CANDMC_TRY(profile_end_launch(stream));
   runtime().launches++;
   return OK;

@@ -6,6 +6,8 @@
 //   frob_diff_f64  : ||X-Y||_F^2 and ||Y||_F^2 for the rel-Frobenius parity bar
 // These are pure streaming kernels: 16 B per thread per access when alignment allows, grid = k * #SMs,
 // algorithmic traffic 16 B/element (copy, transpose) or 24 B/element (axpby).
+#include <algorithm>
+
 #include "common.cuh"
 #include "runtime.h"
 
@@ -16,37 +18,53 @@ namespace {
 constexpr int PACK_THREADS = 256;
 constexpr int PACK_CTAS_PER_SM = 8;
 
-// One "row of work" = a column of the sub-matrix; vector path moves double2.
-template <bool AXPBY>
-__global__ void __launch_bounds__(PACK_THREADS)
-lda_vec2_kernel(int64_t nrow2 /* nrow/2 */, int64_t ncol, int64_t lda2, int64_t ldb2, const double2* __restrict__ A,
-                double2* __restrict__ B, double a, double b) {
-  const int64_t total = nrow2 * ncol;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total; e += stride) {
-    const int64_t c = e / nrow2, r = e - c * nrow2;
-    const double2 va = __ldg(A + c * lda2 + r);
-    double2* bp = B + c * ldb2 + r;
-    if (AXPBY) {
-      const double2 vb = *bp;
-      *bp = make_double2(vb.x * b + va.x * a, vb.y * b + va.y * a);
-    } else {
-      *bp = va;
-    }
-  }
-}
+// Strided sub-matrix copy / axpby in tiles of PACK_ITEMS elements of T (double2 when alignment allows, else double): a tile is
+// 2^tr_log2 consecutive rows x (PACK_ITEMS >> tr_log2) columns, so a thread finds its element with shifts and masks — the only
+// 64-bit division is one per tile, not one per element — and issues all PACK_UNROLL of its loads before the first store.
+// Tall columns give tiles of 1024 rows x 1 column (16 KiB contiguous per tile), short ones pack several columns per tile.
+constexpr int PACK_UNROLL = 4;
+constexpr int PACK_ITEMS = PACK_THREADS * PACK_UNROLL;
 
-template <bool AXPBY>
+template <bool AXPBY, class T>
+__device__ __forceinline__ T axpby_elem(T va, T vb, double a, double b);
+template <>
+__device__ __forceinline__ double axpby_elem<true, double>(double va, double vb, double a, double b) { return vb * b + va * a; }
+template <>
+__device__ __forceinline__ double2 axpby_elem<true, double2>(double2 va, double2 vb, double a, double b) {
+  return make_double2(vb.x * b + va.x * a, vb.y * b + va.y * a);
+}
+template <>
+__device__ __forceinline__ double axpby_elem<false, double>(double va, double, double, double) { return va; }
+template <>
+__device__ __forceinline__ double2 axpby_elem<false, double2>(double2 va, double2, double, double) { return va; }
+
+template <bool AXPBY, class T>
 __global__ void __launch_bounds__(PACK_THREADS)
-lda_scalar_kernel(int64_t nrow, int64_t ncol, int64_t lda, int64_t ldb, const double* __restrict__ A,
-                  double* __restrict__ B, double a, double b) {
-  const int64_t total = nrow * ncol;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total; e += stride) {
-    const int64_t c = e / nrow, r = e - c * nrow;
-    const double va = __ldg(A + c * lda + r);
-    double* bp = B + c * ldb + r;
-    *bp = AXPBY ? (*bp * b + va * a) : va;
+lda_tile_kernel(int64_t nrow /* in units of T */, int64_t ncol, int64_t lda, int64_t ldb, const T* __restrict__ A,
+                T* __restrict__ B, double a, double b, int tr_log2, int64_t tiles_r, int64_t ntiles) {
+  const int tr_mask = (1 << tr_log2) - 1;
+  const int tc = PACK_ITEMS >> tr_log2;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t tile_c = tile / tiles_r, tile_r = tile - tile_c * tiles_r;
+    const int64_t row0 = tile_r << tr_log2, col0 = tile_c * tc;
+    T va[PACK_UNROLL], vb[PACK_UNROLL];
+    bool live[PACK_UNROLL];
+#pragma unroll
+    for (int u = 0; u < PACK_UNROLL; ++u) {
+      const int i = threadIdx.x + u * PACK_THREADS;
+      const int64_t r = row0 + (i & tr_mask), c = col0 + (i >> tr_log2);
+      live[u] = r < nrow && c < ncol;
+      if (live[u]) {
+        va[u] = __ldg(A + c * lda + r);
+        if (AXPBY) vb[u] = B[c * ldb + r];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PACK_UNROLL; ++u) {
+      const int i = threadIdx.x + u * PACK_THREADS;
+      const int64_t r = row0 + (i & tr_mask), c = col0 + (i >> tr_log2);
+      if (live[u]) B[c * ldb + r] = axpby_elem<AXPBY, T>(va[u], vb[u], a, b);
+    }
   }
 }
 
@@ -73,13 +91,22 @@ int lda_dispatch(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const
   }
   const bool vec = (nrow % 2 == 0) && (lda_A % 2 == 0) && (lda_B % 2 == 0) &&
                    (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(B) % 16 == 0);
+  const int64_t nr = vec ? nrow / 2 : nrow;   // rows in units of the element type the kernel moves
+  int tr_log2 = 0;
+  while ((1 << tr_log2) < PACK_ITEMS && (static_cast<int64_t>(1) << tr_log2) < nr) ++tr_log2;
+  const int64_t tiles_r = (nr + (1 << tr_log2) - 1) >> tr_log2;
+  const int tc = PACK_ITEMS >> tr_log2;
+  const int64_t ntiles = tiles_r * ((ncol + tc - 1) / tc);
+  int64_t grid = ntiles;
+  const int64_t cap = static_cast<int64_t>(runtime().num_sms) * PACK_CTAS_PER_SM;
+  if (grid > cap) grid = cap;
   if (vec) {
-    lda_vec2_kernel<AXPBY><<<pack_grid(nrow / 2 * ncol), PACK_THREADS, 0, stream>>>(
-        nrow / 2, ncol, lda_A / 2, lda_B / 2, reinterpret_cast<const double2*>(A), reinterpret_cast<double2*>(B), a,
-        b);
+    lda_tile_kernel<AXPBY, double2><<<static_cast<int>(grid), PACK_THREADS, 0, stream>>>(
+        nr, ncol, lda_A / 2, lda_B / 2, reinterpret_cast<const double2*>(A), reinterpret_cast<double2*>(B), a, b, tr_log2,
+        tiles_r, ntiles);
   } else {
-    lda_scalar_kernel<AXPBY><<<pack_grid(nrow * ncol), PACK_THREADS, 0, stream>>>(nrow, ncol, lda_A, lda_B, A, B, a,
-                                                                                   b);
+    lda_tile_kernel<AXPBY, double><<<static_cast<int>(grid), PACK_THREADS, 0, stream>>>(nr, ncol, lda_A, lda_B, A, B, a, b,
+                                                                                         tr_log2, tiles_r, ntiles);
   }
   CANDMC_CUDA(cudaGetLastError());
   runtime().launches++;
@@ -116,6 +143,76 @@ transpose_kernel(int64_t rows, int64_t cols, const double* __restrict__ A, int64
     }
     __syncthreads();
   }
+}
+
+// The same through the TMA unit (the default whenever both matrices are 16-byte aligned with even leading dimensions): a
+// persistent CTA per SM streams 64 x 64 tiles — four 16-row boxes per tile land by `cp.async.bulk.tensor` under the 128-byte
+// swizzle (TP_NIN tiles in flight per SM, completion on mbarriers), the threads turn a tile around inside shared memory
+// (one conflict-free LDS.128 per pair of rows: the swizzle spreads eight consecutive columns over the eight 16-byte bank
+// groups; the stores along the output's contiguous dimension are 256 B per warp), and the turned tile leaves by one TMA
+// store (TP_NOUT tiles in flight).  No thread computes a global address; ragged edges are clipped / zero-filled by the TMA
+// unit.  Algorithmic traffic 16 B per element.
+constexpr int TP = 64;
+constexpr int TP_BYTES = TP * TP * 8;
+constexpr int TP_NIN = 3, TP_NOUT = 3;
+constexpr int TP_SMEM = (TP_NIN + TP_NOUT) * TP_BYTES + 1024 /*align slack*/ + 64 /*barriers*/;
+
+__global__ void __launch_bounds__(256, 1)
+transpose_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut, int tiles_r,
+                     int tiles_c) {
+  extern __shared__ uint8_t tp_smem_raw[];
+  uint8_t* smem = tp_smem_raw + ((1024u - (smem_u32(tp_smem_raw) & 1023u)) & 1023u);
+  uint8_t* in = smem;                            // TP_NIN tiles: box q (rows 16q .. 16q+15) at q * 8 KiB, one 128 B line per column
+  uint8_t* out = smem + TP_NIN * TP_BYTES;       // TP_NOUT tiles: out[r][c], c contiguous
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (TP_NIN + TP_NOUT) * TP_BYTES);
+  const int64_t ntiles = static_cast<int64_t>(tiles_r) * tiles_c;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto issue_load = [&](int64_t t, int s) {
+    const int r0 = static_cast<int>(t % tiles_r) * TP, c0 = static_cast<int>(t / tiles_r) * TP;
+    mbar_expect_tx(&full[s], TP_BYTES);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tma_load_2d(in + s * TP_BYTES + q * 8192, &tmIn, &full[s], r0 + 16 * q, c0);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TP_NIN; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmIn);
+    tma_prefetch_desc(&tmOut);
+    for (int s = 0; s < TP_NIN; ++s) {
+      const int64_t t = blockIdx.x + static_cast<int64_t>(s) * gridDim.x;
+      if (t < ntiles) issue_load(t, s);
+    }
+  }
+  const int c = (warp & 1) * 32 + lane;   // my column of the input tile = my position along the output's contiguous dimension
+  int i = 0;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+    const int s = i % TP_NIN, o = i % TP_NOUT;
+    mbar_wait(&full[s], (i / TP_NIN) & 1);
+    const uint32_t ibase = smem_u32(in + s * TP_BYTES) + c * 128;
+    double* ob = reinterpret_cast<double*>(out + o * TP_BYTES) + c;
+    // out[o] was last read by the store of tile i - TP_NOUT: complete, thread 0 waited for it before the barrier of tile i - 1
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int p = (warp >> 1) * 8 + u, q = p >> 3, j = p & 7;   // rows 16q + 2j, 16q + 2j + 1
+      const double2 v = lds_f64x2(ibase + q * 8192 + ((j ^ (c & 7)) << 4));
+      ob[(16 * q + 2 * j) * TP] = v.x;
+      ob[(16 * q + 2 * j + 1) * TP] = v.y;
+    }
+    fence_proxy_async();   // my writes of out[o] become visible to the TMA store
+    if (threadIdx.x == 0) tma_store_wait_read<TP_NOUT - 2>();   // the stores up to tile i - 2 have read their buffers
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int r0 = static_cast<int>(t % tiles_r) * TP, c0 = static_cast<int>(t / tiles_r) * TP;
+      tma_store_2d(&tmOut, out + o * TP_BYTES, c0, r0);
+      tma_store_commit();
+      const int64_t tn = t + static_cast<int64_t>(TP_NIN) * gridDim.x;   // in[s] has been read by every thread: refill it
+      if (tn < ntiles) issue_load(tn, s);
+    }
+  }
+  if (threadIdx.x == 0) tma_store_wait_all<0>();
 }
 
 __global__ void fill_kernel(double* __restrict__ X, int64_t count, double v) {
@@ -194,6 +291,24 @@ int transpose_f64(int64_t rows, int64_t cols, const double* A, int64_t lda, doub
   CANDMC_CHECK(rows >= 0 && cols >= 0, "transpose: negative extent");
   CANDMC_CHECK(lda >= rows && ldb >= cols, "transpose: leading dimension too small");
   if (rows == 0 || cols == 0) return OK;
+  const bool tma_ok = runtime().transpose_tma && reinterpret_cast<uintptr_t>(A) % 16 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0 &&
+                      lda % 2 == 0 && ldb % 2 == 0 && rows < (1LL << 31) - TP && cols < (1LL << 31) - TP;
+  if (tma_ok) {
+    CUtensorMap tmIn, tmOut;
+    CANDMC_TRY(encode_tmap_f64(&tmIn, A, rows, cols, lda, 16, TP));
+    CANDMC_TRY(encode_tmap_f64_linear(&tmOut, B, cols, rows, ldb, TP, TP));
+    static bool configured = false;
+    if (!configured) {
+      CANDMC_CUDA(cudaFuncSetAttribute(transpose_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
+      configured = true;
+    }
+    const int64_t ttr = (rows + TP - 1) / TP, ttc = (cols + TP - 1) / TP;
+    const int64_t g = std::min<int64_t>(ttr * ttc, runtime().num_sms);
+    transpose_tma_kernel<<<static_cast<int>(g), 256, TP_SMEM, stream>>>(tmIn, tmOut, static_cast<int>(ttr), static_cast<int>(ttc));
+    CANDMC_CUDA(cudaGetLastError());
+    runtime().launches++;
+    return OK;
+  }
   const int64_t tr = (rows + TT - 1) / TT, tc = (cols + TT - 1) / TT;
   int64_t grid = tr * tc;
   const int64_t cap = static_cast<int64_t>(runtime().num_sms) * 6;

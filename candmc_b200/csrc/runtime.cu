@@ -14,6 +14,12 @@ namespace {
 thread_local char g_err[1024] = "";
 Runtime g_rt;
 constexpr unsigned kTileCounters = 1024;
+// The split-K scratch (partial tiles + per-tile arrival counters) is one buffer per process.  Launches on one stream are
+// ordered by the stream; a launch on ANOTHER stream (the LU seam's GEMM stream next to a caller's stream, two caller streams)
+// first waits for the last launch that used the scratch, so two split-K GEMMs never mix their partials or counters.
+cudaEvent_t g_splitk_last = nullptr;
+cudaStream_t g_splitk_stream = nullptr;
+bool g_splitk_used = false;
 }  // namespace
 
 void set_last_error(const char* fmt, ...) {
@@ -50,7 +56,12 @@ int runtime_init(int device) {
   g_rt.num_sms = prop.multiProcessorCount;
   g_rt.cc_major = prop.major;
   g_rt.cc_minor = prop.minor;
-  CANDMC_CUDA(cudaStreamCreateWithFlags(&g_rt.comm_stream, cudaStreamNonBlocking));
+  // The communication stream gets the highest priority: when a persistent GEMM ends and both the next GEMM's CTAs and an
+  // NCCL kernel's (a panel broadcast, a shift, a slab of the depth sum) are pending, the few communication CTAs are placed
+  // first and the GEMM — whose dynamic tile scheduler does not care how many of its CTAs are resident — takes the rest.
+  int prio_lo = 0, prio_hi = 0;
+  CANDMC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CANDMC_CUDA(cudaStreamCreateWithPriority(&g_rt.comm_stream, cudaStreamNonBlocking, prio_hi));
   CANDMC_CUDA(cudaStreamCreateWithFlags(&g_rt.aux_stream, cudaStreamNonBlocking));
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
@@ -96,6 +107,10 @@ int runtime_finalize() {
   if (g_rt.tile_counters) cudaFree(g_rt.tile_counters);
   if (g_rt.splitk_part) cudaFree(g_rt.splitk_part);
   if (g_rt.splitk_sem) cudaFree(g_rt.splitk_sem);
+  if (g_splitk_last) cudaEventDestroy(g_splitk_last);
+  g_splitk_last = nullptr;
+  g_splitk_stream = nullptr;
+  g_splitk_used = false;
   if (g_rt.comm_stream) cudaStreamDestroy(g_rt.comm_stream);
   if (g_rt.aux_stream) cudaStreamDestroy(g_rt.aux_stream);
   g_rt = Runtime();
@@ -142,7 +157,16 @@ int stage_pool_get(size_t bytes, void** out) {
   return OK;
 }
 
-int splitk_buffers(int64_t part_elems, double** part, int** sem) {
+int splitk_release(cudaStream_t stream) {
+  if (g_splitk_last == nullptr) CANDMC_CUDA(cudaEventCreateWithFlags(&g_splitk_last, cudaEventDisableTiming));
+  CANDMC_CUDA(cudaEventRecord(g_splitk_last, stream));
+  g_splitk_stream = stream;
+  g_splitk_used = true;
+  return OK;
+}
+
+int splitk_buffers(int64_t part_elems, double** part, int** sem, cudaStream_t stream) {
+  if (g_splitk_used && g_splitk_stream != stream) CANDMC_CUDA(cudaStreamWaitEvent(stream, g_splitk_last, 0));
   if (g_rt.splitk_sem == nullptr) {
     CANDMC_CUDA(cudaMalloc(&g_rt.splitk_sem, sizeof(int) * 4096));
     CANDMC_CUDA(cudaMemset(g_rt.splitk_sem, 0, sizeof(int) * 4096));
@@ -239,7 +263,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 namespace {
 int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, int64_t dim0, int64_t dim1,
-                int64_t ld, int box0, int box1) {
+                int64_t ld, int box0, int box1, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   CANDMC_TRY(runtime_require());
   CANDMC_CHECK(dim0 > 0 && dim1 > 0, "tensor map: empty operand");
   cuuint64_t gdim[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
@@ -248,7 +272,7 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const 
   cuuint32_t estr[2] = {1, 1};
   CUresult r = reinterpret_cast<PFN_encodeTiled>(g_rt.pfn_encode_tiled)(
       out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (CUresult %d) dims=%lldx%lld ld=%lld box=%dx%d ptr=%p elem=%d", (int)r,
                    (long long)dim0, (long long)dim1, (long long)ld, box0, box1, base, elem_bytes);
@@ -261,6 +285,11 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const 
 int encode_tmap_f64(CUtensorMap* out, const double* base, int64_t dim0, int64_t dim1, int64_t ld, int box0,
                     int box1) {
   return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, base, dim0, dim1, ld, box0, box1);
+}
+
+int encode_tmap_f64_linear(CUtensorMap* out, const double* base, int64_t dim0, int64_t dim1, int64_t ld, int box0,
+                           int box1) {
+  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, base, dim0, dim1, ld, box0, box1, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 int encode_tmap_f32(CUtensorMap* out, const float* base, int64_t dim0, int64_t dim1, int64_t ld, int box0, int box1) {

@@ -31,7 +31,9 @@ struct Runtime {
   bool b_first_chunk_early = false;     // host B: upload the first k-chunk's rows ahead of the rest (opt-in until measured)
   bool early_c_download = true;         // host C: finalise + download column slabs under the last multiplies (candmc_set_early_c_download)
   bool fused_reduce = true;             // depth all-reduce fused into the last GEMM's epilogue over peer memory
+  bool transpose_tma = true;            // transpose through TMA loads / stores (candmc_debug_transpose_tma(0): the LDG/STG kernel)
   bool splitk = true;                   // cut small-tile-count GEMMs along k too
+  bool prefetch_c = true;               // beta != 0 GEMMs prefetch their C tiles into L2 under the last k-tiles (candmc_debug_prefetch_c)
   double* splitk_part = nullptr;        // split-K partial tiles (grow-only) and per-tile arrival counters
   size_t splitk_part_elems = 0;
   int* splitk_sem = nullptr;
@@ -56,8 +58,10 @@ int runtime_finalize();
 // Grow-only scratch; contents undefined.  Not thread safe (one rank = one host thread, as in the reference).
 int workspace_get(size_t bytes, void** out);
 
-// Scratch for split-K GEMM launches (one launch in flight at a time per process, like the reference's single-threaded ranks).
-int splitk_buffers(int64_t part_elems, double** part, int** sem);
+// Scratch for split-K GEMM launches: one buffer per process.  splitk_buffers makes `stream` wait for the last split-K launch
+// of any OTHER stream; splitk_release(stream) is called right after the launch that uses the scratch.
+int splitk_buffers(int64_t part_elems, double** part, int** sem, cudaStream_t stream);
+int splitk_release(cudaStream_t stream);
 
 // GEMM launch profiling (candmc_profile_*): events around each TMA+DMMA launch on its own stream.
 int profile_begin_launch(cudaStream_t stream, double flops);
@@ -76,6 +80,10 @@ int next_tile_counter(int** out, cudaStream_t stream);
 // box = box0 x box1 elements (box0 * 8 bytes must be <= 128).
 int encode_tmap_f64(CUtensorMap* out, const double* base, int64_t dim0, int64_t dim1, int64_t ld, int box0,
                     int box1);
+
+// The same without swizzle: the box lands (or is read) row after row, box0 x box1 doubles dense (box0 <= 256).
+int encode_tmap_f64_linear(CUtensorMap* out, const double* base, int64_t dim0, int64_t dim1, int64_t ld, int box0,
+                           int box1);
 
 // The same for FP32 operands (box0 * 4 bytes <= 128; base 16-byte aligned, ld a multiple of 4).
 int encode_tmap_f32(CUtensorMap* out, const float* base, int64_t dim0, int64_t dim1, int64_t ld, int box0, int box1);

@@ -74,6 +74,14 @@ unsigned long long candmc_merged_panel_launches(int chunk_major_b);
 int candmc_set_b_first_chunk_early(int on);
 /* Test/measurement hook: 0 disables the split-K path the GEMM takes for small tile counts (default on). */
 int candmc_debug_splitk(int on);
+/* Test/measurement hook: 0 routes candmc_transpose through the LDG/STG kernel instead of the TMA load / TMA store kernel
+ * (which is also the automatic choice for operands that are not 16-byte aligned with even leading dimensions). */
+int candmc_debug_transpose_tma(int on);
+/* Measurement hook: 1 = GEMM launches with beta != 0 pull the C tile their epilogue will read into L2 under the tile's last
+ * k-tiles (bulk L2 prefetches issued by the TMA producer lane); 0 = the epilogue's loads go to HBM. */
+int candmc_debug_prefetch_c(int on);
+/* Measurement hook: GEMM launches leave `sms` SMs free (what the SUMMA sweeps do while NCCL panel traffic is in flight). */
+int candmc_debug_gemm_reserve_sms(int sms);
 /* Test/measurement hook: 1 makes the GEMM walk its tiles round-robin instead of claiming them from an atomic counter. */
 int candmc_debug_static_schedule(int on);
 /* Measurement hook (bench.py's roofline leg): while enabled every TMA+DMMA GEMM launch is bracketed by CUDA events on

@@ -645,6 +645,13 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
   return cudaSuccess;
 }
 cudaError_t cudaStreamCreate(cudaStream_t* s) { return cudaStreamCreateWithFlags(s, 0); }
+// priorities only bias the hardware's block scheduler; the simulator's stream order policies ignore them
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned flags, int) { return cudaStreamCreateWithFlags(s, flags); }
+cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) {
+  if (lo) *lo = 0;
+  if (hi) *hi = -5;
+  return cudaSuccess;
+}
 cudaError_t cudaStreamDestroy(cudaStream_t s) {
   drain_stream(s);  // CUDA lets pending work finish before the stream goes away
   SimStream* st = S(s);

@@ -37,6 +37,7 @@ void mbar_arrive(uint32_t bar);
 void mbar_expect_tx(uint32_t bar, uint32_t bytes);   // arrive.expect_tx
 bool mbar_try_wait(uint32_t bar, uint32_t parity);   // yields to the other fibers when the phase is not complete yet
 void tma_load_2d(uint32_t dst, const void* tensor_map, uint32_t bar, int c0, int c1);  // tiled, 128 B swizzle, OOB zero fill
+void tma_store_2d(const void* tensor_map, uint32_t src, int c0, int c1);   // tiled store, executed when it is issued
 void warp_allgather16(const void* in16, void* out32x16);  // every lane contributes 16 bytes, all get all
 void named_barrier(int id, int count);                 // bar.sync id, count
 // tcgen05 (gemm_f32.cu): tensor memory, the TF32 UMMA executed when it is issued, commit = immediate mbarrier arrival
@@ -174,8 +175,22 @@ static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
 static inline void tma_load_2d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
   ::cpusim::tma_load_2d(smem_u32(dst), tmap, smem_u32(bar), c0, c1);
 }
+static inline void tma_store_2d(const CUtensorMap* tmap, const void* src, int c0, int c1) {
+  ::cpusim::tma_store_2d(tmap, smem_u32(src), c0, c1);
+}
+static inline void tma_store_commit() {}
+template <int N>
+static inline void tma_store_wait_read() {}
+template <int N>
+static inline void tma_store_wait_all() {}
 static inline void tma_prefetch_desc(const CUtensorMap*) {}
+static inline void l2_prefetch_bulk(const void*, uint32_t) {}   // a cache hint: nothing to emulate
 static inline double lds_f64(uint32_t addr) { return *static_cast<const double*>(::cpusim::smem_ptr(addr)); }
+static inline double2 lds_f64x2(uint32_t addr) {
+  double2 v;
+  memcpy(&v, ::cpusim::smem_ptr(addr), 16);
+  return v;
+}
 static inline void tmem_alloc(uint32_t* slot, uint32_t ncols) { ::cpusim::tmem_alloc(smem_u32(slot), ncols); }
 static inline void tmem_dealloc(uint32_t taddr, uint32_t ncols) { ::cpusim::tmem_dealloc(taddr, ncols); }
 static inline void tcgen05_fence_before() {}

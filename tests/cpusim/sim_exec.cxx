@@ -275,6 +275,28 @@ void tma_load_2d(uint32_t dst, const void* tensor_map, uint32_t bar, int c0, int
   mbar_check(b);
 }
 
+void tma_store_2d(const void* tensor_map, uint32_t src, int c0, int c1) {
+  SimTensorMap m;
+  memcpy(&m, tensor_map, sizeof(m));
+  if (m.magic != kTensorMapMagic) {
+    fprintf(stderr, "cpusim: TMA store through something that is not an encoded tensor map\n");
+    abort();
+  }
+  if (src % 128 != 0) {
+    fprintf(stderr, "cpusim: TMA source %u not 128-byte aligned\n", src);
+    abort();
+  }
+  for (uint32_t i1 = 0; i1 < m.box[1]; ++i1)
+    for (uint32_t i0 = 0; i0 < m.box[0]; ++i0) {
+      const int64_t g0 = (int64_t)c0 + i0, g1 = (int64_t)c1 + i1;
+      const uint32_t es = m.elem_bytes;
+      uint32_t addr = src + (i1 * m.box[0] + i0) * es;
+      if (m.swizzle128) addr ^= ((addr >> 7) & 7u) << 4;
+      if (g0 >= 0 && g1 >= 0 && (uint64_t)g0 < m.dim[0] && (uint64_t)g1 < m.dim[1])   // out-of-range elements are not written
+        memcpy(const_cast<char*>(m.base) + g0 * es + g1 * (int64_t)m.stride1, smem_ptr(addr), es);
+    }
+}
+
 void warp_allgather16(const void* in16, void* out32x16) {
   Warp& w = g_blk.warps[g_cur / 32];
   const int lane = g_cur % 32;

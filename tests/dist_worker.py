@@ -58,8 +58,28 @@ def record(name, err, tol):
     return ok
 
 
+# Process grids are built once per shape and shared by the cases (each one costs four ncclCommSplit plus the background
+# communicators: minutes per run at 4 and 8 GPUs when every case builds its own); main() frees them all at the end.
+_GRIDS = {}
+
+
+def shared_grid(world, kind, arg):
+    key = (kind, arg)
+    if key not in _GRIDS:
+        _GRIDS[key] = cb.d25_grid(world, arg) if kind == "d25" else cb.dcn_grid(world, arg)
+    return _GRIDS[key]
+
+
+def free_shared_grids():
+    for g in _GRIDS.values():
+        for k, v in g.items():
+            if k.startswith("cdt_"):
+                v.free()
+    _GRIDS.clear()
+
+
 def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_golden=True, oracle=True, grid=None):
-    g = grid if grid is not None else cb.d25_grid(world, c)
+    g = grid if grid is not None else shared_grid(world, "d25", c)
     q = g["q"]
     b = n // q
     row0, col0 = g["row"] * b, g["col"] * b
@@ -83,11 +103,7 @@ def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_go
         got = host(dC, b, b)
     if not oracle:   # too large for the plain-C oracle: numpy (OpenBLAS) product of the regenerated operands instead
         full = orc.unit_block(n, n, 0, 0, n, 0) @ orc.unit_block(n, n, 0, 0, n, 1)
-        ok = record(f"{name}:numpy", rel_frob(got, full[row0:row0 + b, col0:col0 + b]), 10 * n * EPS)
-        if grid is None:
-            for k in ("cdt_row", "cdt_col", "cdt_kdir"):
-                g[k].free()
-        return ok
+        return record(f"{name}:numpy", rel_frob(got, full[row0:row0 + b, col0:col0 + b]), 10 * n * EPS)
     # oracle for the whole grid
     Ab, Bb = orc.d25_blocks(n, q, c) if not (q == 1 and c > 1) else (
         [orc.unit_block(n, n, 0, 0, n, 0) for _ in range(c)], [orc.unit_block(n, n, 0, 0, n, 1) for _ in range(c)])
@@ -96,16 +112,13 @@ def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_go
     ok = record(f"{name}:oracle", rel_frob(got, Cb[world.rank]), 10 * n * EPS)
     if check_golden and name in golden:
         ok &= record(f"{name}:golden", rel_frob(got, golden[name][world.rank]), 10 * n * EPS)
-    if grid is None:
-        for k in ("cdt_row", "cdt_col", "cdt_kdir"):
-            g[k].free()
     return ok
 
 
 def case_repeat(world, golden, name, c, sizes):
     """many multiplies on ONE grid (the communicators' persistent state: workspaces, fused-reduce windows with their epochs
     and double-buffered slabs, panel-transport windows with their call counters, done flags and the growth path)"""
-    g = cb.d25_grid(world, c)
+    g = cb.d25_grid(world, c)   # its own grid: fresh communicator state at the start, released at the end
     ok = True
     for it, n in enumerate(sizes):
         ok &= case_d25(world, golden, f"{name}.{it}.n{n}", n, c, it % 2, lda_pad=(it % 3 == 2) * 2, check_golden=False, oracle=False,
@@ -116,7 +129,7 @@ def case_repeat(world, golden, name, c, sizes):
 
 
 def case_summa(world, golden, name, n, lda_pad=0, trans=("N", "N")):
-    g = cb.d25_grid(world, 1)
+    g = shared_grid(world, "d25", 1)
     q = g["q"]
     b = n // q
     ld = b + lda_pad
@@ -137,12 +150,11 @@ def case_summa(world, golden, name, n, lda_pad=0, trans=("N", "N")):
     ok = record(f"{name}:oracle", rel_frob(got, Cb[world.rank]), 10 * n * EPS)
     if name in golden and lda_pad == 0 and trans == ("N", "N"):
         ok &= record(f"{name}:golden", rel_frob(got, golden[name][world.rank]), 10 * n * EPS)
-    g["cdt_row"].free(); g["cdt_col"].free(); g["cdt_kdir"].free()
     return ok
 
 
 def case_dcn(world, golden, name, n, x2_np, ovp, lda_pad=0):
-    g = cb.dcn_grid(world, x2_np)
+    g = shared_grid(world, "dcn", x2_np)
     x1_np = g["x1_np"]
     b = n // (x1_np * x2_np)
     row0 = (g["y1"] * x2_np + g["y2"]) * b
@@ -166,8 +178,6 @@ def case_dcn(world, golden, name, n, x2_np, ovp, lda_pad=0):
     # the reference test's own criterion: serial product in the dcn_unit layout, |diff| <= 1e-6
     full = orc.unit_block(n, n, 0, 0, n, 0) @ orc.unit_block(n, n, 0, 0, n, 1)
     ok &= record(f"{name}:serial_abs", float(np.abs(got - full[row0:row0 + b, col0:col0 + b]).max()), 1e-6)
-    for k in ("cdt_x1", "cdt_y1", "cdt_x2", "cdt_y2"):
-        g[k].free()
     return ok
 
 
@@ -630,11 +640,6 @@ def main():
     only_pending = os.environ.get("CANDMC_TEST_PENDING") == "1"
     if only_pending:
         pending_cases(world, golden)
-    if not only_pending:
-        # this group is the one B200s have run: host C blocks leave in one piece, as they did then; the slab-wise early download
-        # (today's default) has its cases in the pending group
-        cb.lib().candmc_set_early_c_download(0)
-        cb.lib().candmc_set_skip_unused_uploads(0)   # ... and every rank uploads both of its blocks
     for min_kc in (() if only_pending else (1024, 8)):   # default (whole panels at these sizes) and a tiny chunk to exercise the k-chunk pipeline
         cb.set_min_kchunk(min_kc)
         tag = f"kc{min_kc}"
@@ -695,8 +700,6 @@ def main():
             case_d25(world, golden, f"d25_n1024_c2_host_{tag}", 1024, 2, 0, use_host=True)
             case_d25(world, golden, f"d25_n512_c2_fused_pad_{tag}", 512, 2, 0, lda_pad=1)
     cb.set_min_kchunk(1024)
-    cb.lib().candmc_set_early_c_download(1)
-    cb.lib().candmc_set_skip_unused_uploads(1)
     big = int(os.environ.get("CANDMC_TEST_BIG_N", "0"))
     if big:
         case_big_d25(world, big, None)
@@ -717,6 +720,7 @@ def main():
                           "launches_rank0": cb.launch_count(),
                           "panel_transport_sends_rank0": int(cb.lib().candmc_panel_transport_sends()),
                           "merged_panel_launches_all_ranks": [int(merged_all[0]), int(merged_all[1])]}), flush=True)
+    free_shared_grids()
     world.free()
     if world_size > 1:
         dist.destroy_process_group()

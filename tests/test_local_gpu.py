@@ -142,6 +142,30 @@ def test_splitk_matches_plain_kernel_and_is_deterministic():
     assert rel_frob(outs[0], outs[2]) <= 10 * k * EPS
 
 
+def test_splitk_launches_on_two_streams_do_not_mix_their_scratch():
+    """The split-K partial tiles and arrival counters are one buffer per process: a split-K GEMM enqueued on a second stream
+    while another one is still in flight must wait for it (runtime.cu: splitk_buffers / splitk_release) — each result is
+    bit-identical to the same multiply run alone."""
+    m, n, k = 512, 384, 16384
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    ops = []
+    for seed in (0, 1):
+        A = torch.empty(m * k, dtype=torch.float64, device="cuda"); B = torch.empty(k * n, dtype=torch.float64, device="cuda")
+        cb.fill_drand48(A, m, k, m, seed * 7, 0, m + 13 * seed, 0); cb.fill_drand48(B, k, n, k, 0, seed * 5, k + seed, 1)
+        alone = torch.zeros(m * n, dtype=torch.float64, device="cuda")
+        cb.cdgemm("N", "N", m, n, k, 1.0, A, m, B, k, 0.0, alone, m)
+        ops.append((A, B, alone))
+    torch.cuda.synchronize()
+    for _ in range(5):
+        outs = [torch.zeros(m * n, dtype=torch.float64, device="cuda") for _ in ops]
+        torch.cuda.synchronize()
+        for (A, B, _), out, st in zip(ops, outs, (s1, s2)):
+            cb.cdgemm("N", "N", m, n, k, 1.0, A, m, B, k, 0.0, out, m, stream=st)
+        torch.cuda.synchronize()
+        for (_, _, alone), out in zip(ops, outs):
+            assert torch.equal(alone, out)
+
+
 def test_frob_diff():
     rng = np.random.default_rng(6)
     X = np.asfortranarray(rng.random((40, 30))); Y = np.asfortranarray(rng.random((44, 30)))

@@ -5,7 +5,11 @@
   config 5: CAQR trailing-update shape m=65536, n=8192, k=512 on 1/2/4 GPUs -> upd_A (TN GEMM, all-reduce, trsm, NN GEMM)
 Launch: python tools/bench_configs.py            (1 GPU: config 5 on a 1x1 grid)
         torchrun --nproc-per-node 4 tools/bench_configs.py
-Prints one JSON line per configuration on rank 0 (device-timed with CUDA events, max over ranks).
+Prints one JSON line per configuration on rank 0 (device-timed with CUDA events, max over ranks).  Every line carries a
+result check at full size, made outside the timed region: the rank's block of the product against an independent cross-check
+(operands regenerated locally with the device generator, multiplied by cuBLAS through torch.matmul — the use of cuBLAS
+BASELINE's north_star allows), relative Frobenius error, max over ranks, against the tolerance 10 * k * eps of north_star
+(k = the contracted dimension).
 `--pending` adds the SURVEY §8f widening rows that have not been measured yet: upd_Yamamoto_A at the config-5 shape, the
 redistribution's permute kernels (GB/s against the HBM copy peak) and candmc_redistribute over NCCL, and the LU seam's
 trailing-update step (GEMM + the panel download queued behind it)."""
@@ -61,6 +65,28 @@ def main():
             line.update(extra or {})
             print(json.dumps(line), flush=True)
 
+    EPS = 2.220446049250313e-16
+
+    def maxr(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if ws > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gen(rows, cols, row0, col0, n, which):
+        """rows x cols block at (row0, col0) of the generated n x n matrix, as a torch matrix M[i, j] (column-major storage)"""
+        X = torch.empty(rows * cols, dtype=torch.float64, device="cuda")
+        cb.fill_drand48(X, rows, cols, rows, row0, col0, n, which)
+        return X.view(cols, rows).T
+
+    def check_block(Cm, b, ref, kdim):
+        """relative Frobenius error of my b x b column-major block against the torch matrix `ref`, max over ranks"""
+        got = Cm.view(b, b).T
+        err = float(torch.linalg.norm(got - ref) / torch.linalg.norm(ref))
+        err = maxr(err)
+        tol = 10 * kdim * EPS
+        return {"rel_frobenius_vs_cublas_crosscheck": err, "tolerance_10_k_eps": tol, "check_passed": bool(err <= tol)}
+
     def blocks(b, row0, col0, n):
         A = torch.empty(b * b, dtype=torch.float64, device="cuda"); B = torch.empty_like(A); Cm = torch.empty_like(A)
         cb.fill_drand48(A, b, b, b, row0, col0, n, 0); cb.fill_drand48(B, b, b, b, row0, col0, n, 1)
@@ -72,17 +98,26 @@ def main():
         A, B, Cm = blocks(b, g["row"] * b, g["col"] * b, n)
         args = cb.ctb_args_t(n=n, lda_A=b, lda_B=b, lda_C=b, buffer_size=4 * b * b * 8)
         ms = timed(lambda: cb.summa(args, A, B, Cm, None, g["cdt_row"], g["cdt_col"]))
-        report("config2: summa n=16384 2x2", 2.0 * n ** 3, ms)
+        chk = check_block(Cm, b, gen(b, n, g["row"] * b, 0, n, 0) @ gen(n, b, 0, g["col"] * b, n, 1), n)
+        report("config2: summa n=16384 2x2", 2.0 * n ** 3, ms, chk)
         del A, B, Cm
         # ---- config 4a: bcast_cannon_4d as pure Cannon, n = 24576 ----
         n = sz(24576); d = cb.dcn_grid(world, 2); b = n // 2
         A, B, Cm = blocks(b, (d["y1"] * 2 + d["y2"]) * b, (d["x1"] * 2 + d["x2"]) * b, n)
         args = cb.ctb_args_t(n=n, lda_A=b, lda_B=b, lda_C=b, buffer_size=5 * b * b * 8, ovp=1)
         ms = timed(lambda: cb.bcast_cannon_4d(args, A, B, Cm, None, d["cdt_x1"], d["cdt_y1"], d["cdt_x2"], d["cdt_y2"]))
-        report("config4: bcast_cannon_4d (Cannon level) n=24576 2x2", 2.0 * n ** 3, ms)
+        row0, col0 = (d["y1"] * 2 + d["y2"]) * b, (d["x1"] * 2 + d["x2"]) * b
+        chk = check_block(Cm, b, gen(b, n, row0, 0, n, 0) @ gen(n, b, 0, col0, n, 1), n)
+        report("config4: bcast_cannon_4d (Cannon level) n=24576 2x2", 2.0 * n ** 3, ms, chk)
         # ---- config 4b: split-dim Cannon kput, 12288^3 blocks ----
+        px, py = rank % 2, rank // 2   # block column / block row of A, B and C alike (test/MM/test_spc.cxx:78-102)
+        cb.fill_drand48(A, b, b, b, py * b, px * b, n, 0); cb.fill_drand48(B, b, b, b, py * b, px * b, n, 1)
+        # (the reference permutes A and B in place, spcannon.cxx:76-77; this implementation works on internal copies)
         ms = timed(lambda: cb.kput_cannon(rank, 2, 2, world, b, b, b, "N", 1.0, A, "T", 0.0, B, Cm))
-        report("config4: kput_cannon 2-ary 2-cube, 12288^3 blocks", 2.0 * n ** 3, ms)
+        # with transp_B = 'T' the local B buffer is the transpose of the rank's block of B: block (k, px) of B is G(k, px)^T
+        ref = sum(gen(b, b, py * b, kk * b, n, 0) @ gen(b, b, kk * b, px * b, n, 1).T for kk in range(2))
+        chk = check_block(Cm, b, ref, n)
+        report("config4: kput_cannon 2-ary 2-cube, 12288^3 blocks", 2.0 * n ** 3, ms, chk)
         del A, B, Cm
     # ---- config 5: CAQR trailing update ----
     m, ncol, k = sz(65536), sz(8192), sz(512)
@@ -95,14 +130,31 @@ def main():
     Y.mul_(1.0 / 256.0)   # keep the update well scaled
     T = (torch.eye(k, dtype=torch.float64, device="cuda") + 0.01 * torch.tril(torch.rand(k, k, dtype=torch.float64, device="cuda"))).T.contiguous()
     ms = timed(lambda: cb.upd_A(Y, mb, Am, mb, mb, kb, k, T, ccol))
+
+    def check_upd():
+        """one application on a fresh A against W = T^-1 (Y^T A) and A - Y W computed by torch from regenerated operands"""
+        cb.fill_drand48(Am, mb, kb, mb, prow * mb, pcol * kb, m, 1)
+        cb.upd_A(Y, mb, Am, mb, mb, kb, k, T, ccol)
+        torch.cuda.synchronize()
+        Yf = gen(m, k, 0, 0, m, 0) * (1.0 / 256.0)
+        W = Yf.T @ gen(m, kb, 0, pcol * kb, m, 1)
+        W = torch.linalg.solve_triangular(T.view(k, k).T, W, upper=False)   # T is stored column-major, lower triangular
+        ref = gen(mb, kb, prow * mb, pcol * kb, m, 1) - Yf[prow * mb:(prow + 1) * mb] @ W
+        got = Am.view(kb, mb).T
+        err = maxr(float(torch.linalg.norm(got - ref) / torch.linalg.norm(ref)))
+        tol = 10 * m * EPS
+        return {"rel_frobenius_vs_cublas_crosscheck": err, "tolerance_10_k_eps": tol, "check_passed": bool(err <= tol)}
+
+    chk5 = check_upd()
     report(f"config5: upd_A m=65536 n=8192 k=512 on {nprow}x{npcol}", 2 * 2.0 * m * ncol * k, ms,
-           {"note": "flops = the two GEMMs (SURVEY §8d); all-reduce of W and the triangular solve are inside the time"})
+           dict(chk5, note="flops = the two GEMMs (SURVEY §8d); all-reduce of W and the triangular solve are inside the time"))
     # the same with the opt-in triangular solve (one warp per right-hand side instead of a block barrier per row of T)
     cb.lib().candmc_set_trsm_variant(1)
     ms = timed(lambda: cb.upd_A(Y, mb, Am, mb, mb, kb, k, T, ccol))
+    chk5 = check_upd()
     cb.lib().candmc_set_trsm_variant(0)
     report(f"config5: upd_A m=65536 n=8192 k=512 on {nprow}x{npcol}, trsm variant 1", 2 * 2.0 * m * ncol * k, ms,
-           {"note": "candmc_set_trsm_variant(1), opt-in"})
+           dict(chk5, note="candmc_set_trsm_variant(1), opt-in"))
     # 1-GPU local GEMM roofline at the Cannon block size (config 4, second half)
     if ws == 1:
         for n in (sz(12288), sz(16384)):

@@ -158,9 +158,10 @@ static void run_cublas(void* p) {
               c->k, &one, c->A, c->lda, c->B, c->ldb, &c->beta, c->C, c->ldc);
 }
 
-static void speed_one(cublasHandle_t h, char ta, char tb, int m, int n, int k, int iters) {
+static void speed_one(cublasHandle_t h, char ta, char tb, int m, int n, int k, int iters, double beta = 0.0,
+                      const char* tag = "speed") {
   GemmCtx c;
-  c.ta = ta; c.tb = tb; c.m = m; c.n = n; c.k = k; c.h = h; c.beta = 0.0;
+  c.ta = ta; c.tb = tb; c.m = m; c.n = n; c.k = k; c.h = h; c.beta = beta;
   const int rowsA = (ta == 'N') ? m : k, colsA = (ta == 'N') ? k : m;
   const int rowsB = (tb == 'N') ? k : n, colsB = (tb == 'N') ? n : k;
   c.lda = rowsA; c.ldb = rowsB; c.ldc = m;
@@ -171,7 +172,11 @@ static void speed_one(cublasHandle_t h, char ta, char tb, int m, int n, int k, i
   CK(cudaMalloc(&ref, (size_t)m * n * 8));
   CC(candmc_fill_drand48(c.A, rowsA, colsA, c.lda, 0, 0, rowsA, 0, 0));
   CC(candmc_fill_drand48(c.B, rowsB, colsB, c.ldb, 0, 0, rowsB, 1, 0));
-  // correctness vs cuBLAS at full size
+  // correctness vs cuBLAS at full size (beta != 0: both start from the same C)
+  if (beta != 0.0) {
+    CC(candmc_fill_drand48(c.C, m, n, c.ldc, 0, 0, m, 0, 0));
+    CK(cudaMemcpy(ref, c.C, (size_t)m * n * 8, cudaMemcpyDeviceToDevice));
+  }
   run_ours(&c);
   double* keep = c.C;
   c.C = ref;
@@ -185,9 +190,9 @@ static void speed_one(cublasHandle_t h, char ta, char tb, int m, int n, int k, i
   for (int w = 0; w < 2; ++w) run_cublas(&c);
   const float ms_cublas = time_loop(iters, 0, run_cublas, &c);
   const double fl = 2.0 * m * n * (double)k;
-  printf("{\"probe\":\"speed\",\"trans\":\"%c%c\",\"m\":%d,\"n\":%d,\"k\":%d,\"ms\":%.4f,\"tflops\":%.3f,"
+  printf("{\"probe\":\"%s\",\"trans\":\"%c%c\",\"m\":%d,\"n\":%d,\"k\":%d,\"beta\":%g,\"ms\":%.4f,\"tflops\":%.3f,"
          "\"cublas_ms\":%.4f,\"cublas_tflops\":%.3f,\"rel_frob_vs_cublas\":%.3e,\"tol_10_k_eps\":%.3e}\n",
-         ta, tb, m, n, k, ms_ours, fl / ms_ours * 1e-9, ms_cublas, fl / ms_cublas * 1e-9, rel,
+         tag, ta, tb, m, n, k, beta, ms_ours, fl / ms_ours * 1e-9, ms_cublas, fl / ms_cublas * 1e-9, rel,
          10.0 * k * 2.220446049250313e-16);
   fflush(stdout);
   cudaFree(c.A); cudaFree(c.B); cudaFree(c.C); cudaFree(ref);
@@ -205,8 +210,8 @@ static void run_pack(void* p) {
   if (c->kind == 2) CC(candmc_transpose(c->rows, c->cols, c->A, c->lda, c->B, c->ldb, 0));
 }
 
-static void pack_speed() {
-  const int64_t n = 8192;  // 512 MiB per matrix (config 2's block), larger than L2
+static void pack_speed(int64_t n) {
+  // n = 8192: 512 MiB per matrix (config 2's block), larger than L2
   PackCtx c;
   c.rows = n; c.cols = n; c.lda = 2 * n; c.ldb = n;
   CK(cudaMalloc(&c.A, (size_t)c.lda * n * 8));
@@ -229,7 +234,20 @@ int main(int argc, char** argv) {
   const char* mode = argc > 1 ? argv[1] : "check";
   if (!strcmp(mode, "check")) return run_check();
   if (!strcmp(mode, "pack")) {
-    pack_speed();
+    pack_speed(argc > 2 ? atoll(argv[2]) : 8192);
+    return 0;
+  }
+  if (!strcmp(mode, "one")) {  // gemm_probe one TA TB m n k beta [reserve_sms] [prefetch_c] [iters]: one shape, for ncu captures
+    if (argc < 8) {
+      printf("usage: gemm_probe one TA TB m n k beta [reserve_sms] [prefetch_c] [iters]\n");
+      return 1;
+    }
+    cublasHandle_t h;
+    cublasCreate(&h);
+    if (argc > 8) candmc_debug_gemm_reserve_sms(atoi(argv[8]));
+    if (argc > 9) candmc_debug_prefetch_c(atoi(argv[9]));
+    speed_one(h, argv[2][0], argv[3][0], atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argc > 10 ? atoi(argv[10]) : 1, atof(argv[7]), "one");
+    cublasDestroy(h);
     return 0;
   }
   if (!strcmp(mode, "sched")) {  // A/B: static round-robin vs dynamic (atomic counter) tile schedule
@@ -243,6 +261,29 @@ int main(int argc, char** argv) {
         speed_one(h, 'N', 'N', 8192, 8192, 8192, 5);
       }
     candmc_debug_static_schedule(0);
+    cublasDestroy(h);
+    return 0;
+  }
+  if (!strcmp(mode, "chunk")) {
+    // the launches a SUMMA / 2.5D sweep is made of: one k-chunk of a panel accumulated onto C (beta = 1), with and without the
+    // SMs the sweep leaves to NCCL, with and without the L2 prefetch of the C tile; plus the CAQR update's second GEMM
+    cublasHandle_t h;
+    cublasCreate(&h);
+    const int shapes[][3] = {{16384, 16384, 2048}, {8192, 8192, 1024}, {12288, 12288, 1536}, {65536, 8192, 512}, {16384, 16384, 14336}};
+    for (int pf = 0; pf <= 1; ++pf)
+      for (int rs = 0; rs <= 2; rs += 2) {
+        candmc_debug_prefetch_c(pf);
+        candmc_debug_gemm_reserve_sms(rs);
+        char tag[64];
+        snprintf(tag, sizeof tag, "chunk_pf%d_reserve%d", pf, rs);
+        for (auto& s : shapes) {
+          if (s[2] == 14336 && (rs == 0 || pf == 0)) continue;
+          speed_one(h, 'N', 'N', s[0], s[1], s[2], s[2] > 4096 ? 2 : 5, 1.0, tag);
+          if (pf == 0) speed_one(h, 'N', 'N', s[0], s[1], s[2], s[2] > 4096 ? 2 : 5, 0.0, tag);
+        }
+      }
+    candmc_debug_prefetch_c(0);
+    candmc_debug_gemm_reserve_sms(0);
     cublasDestroy(h);
     return 0;
   }

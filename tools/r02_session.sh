@@ -1,0 +1,116 @@
+#!/bin/bash
+# Round-2 GPU sessions (one gpurun call each; everything lands in gpurun_out/r02_*).  Sections are independent and each
+# step has its own timeout, so a hang costs minutes, not the call.
+#   gpurun --timeout 1500 -- 'bash tools/r02_session.sh probe ncu1 f32 tests bench1'        (1 GPU)
+#   gpurun --gpus 4 --timeout 900 -- 'bash tools/r02_session.sh parity4 bench4'              (4 GPUs)
+#   gpurun --gpus 8 --timeout 700 -- 'bash tools/r02_session.sh parity8 bench8'              (8 GPUs)
+set -u
+cd "$(dirname "$0")/.."
+O=gpurun_out
+mkdir -p $O
+NG=$(python -c "import torch; print(torch.cuda.device_count())" 2>/dev/null || echo 1)
+trun() {   # trun <port> <script> args...   (one rank per visible GPU)
+  local port=$1; shift
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $port "$@"
+}
+ncu_full() {   # ncu_full <out-stem> <kernel regex> <count> cmd...
+  local stem=$1 rx=$2 cnt=$3; shift 3
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$rx" -c $cnt -f -o $O/$stem "$@" > $O/$stem.log 2>&1
+  python tools/ncu_summary.py $O/$stem.ncu-rep $O/$stem.csv > /dev/null 2>&1 && tail -n +3 $O/$stem.csv | cut -c1-400
+}
+for section in "$@"; do
+  echo "=== section $section ($(date +%T))"
+  case "$section" in
+    probe)
+      # local kernels: the launches the sweeps are made of (beta = 1 chunks, reserved SMs, C-tile L2 prefetch on/off), square and
+      # skinny shapes against the cuBLAS cross-check, pack kernels
+      timeout 300 tools/gemm_probe chunk > $O/r02_gemm_probe_chunk.jsonl 2>&1; cat $O/r02_gemm_probe_chunk.jsonl | cut -c1-230
+      timeout 300 tools/gemm_probe speed 1024 2048 4096 8192 16384 > $O/r02_gemm_probe_speed.jsonl 2>&1; cat $O/r02_gemm_probe_speed.jsonl | cut -c1-230
+      timeout 120 tools/gemm_probe pack 8192 > $O/r02_pack_probe.jsonl 2>&1; timeout 120 tools/gemm_probe pack 16384 >> $O/r02_pack_probe.jsonl 2>&1
+      cat $O/r02_pack_probe.jsonl
+      ;;
+    ncu1)
+      # --set full captures at the shapes that matter: the beta = 1 chunk launch of the sweeps (146 SMs), a TN skinny launch,
+      # the pack kernels, the headline 32768^3 launch (roofline.traffic)
+      ncu_full r02_ncu_gemm_chunk_b1 gemm_f64_tma 1 tools/gemm_probe one N N 16384 16384 2048 1.0 2 0 1
+      ncu_full r02_ncu_gemm_chunk_b1_pf gemm_f64_tma 1 tools/gemm_probe one N N 16384 16384 2048 1.0 2 1 1
+      ncu_full r02_ncu_gemm_tn_skinny gemm_f64_tma 1 tools/gemm_probe one T N 512 8192 65536 0.0 0 0 1
+      ncu_full r02_ncu_pack 'lda_|transpose' 9 tools/gemm_probe pack 8192
+      ncu_full r02_ncu_gemm_n32768 gemm_f64_tma 1 tools/gemm_probe one N N 32768 32768 32768 0.0 0 0 1
+      ;;
+    f32)
+      timeout 400 python tests/f32_worker.py --bench > $O/r02_f32_worker.json 2> $O/r02_f32_worker.err
+      tail -4 $O/r02_f32_worker.json | cut -c1-600; tail -3 $O/r02_f32_worker.err
+      ncu_full r02_ncu_gemm_f32 gemm_f32_umma 1 python tests/f32_worker.py --one 8192
+      ;;
+    tests)
+      timeout 900 python -m pytest tests -m gpu -x -q -rA -p no:cacheprovider > $O/r02_pytest_gpu_${NG}gpus.log 2>&1
+      tail -60 $O/r02_pytest_gpu_${NG}gpus.log | grep -E "passed|failed|PASS|FAIL|XPASS|XFAIL|SKIP|Error" | cut -c1-200 | tail -70
+      ;;
+    bench1)
+      timeout 600 python bench.py --gpus 1 --steps 5 --warmup 3 > $O/r02_bench_n32768_gpus1.json 2> $O/r02_bench_n32768_gpus1.err
+      cut -c1-1500 $O/r02_bench_n32768_gpus1.json
+      # launch list of the same command (per-launch times are cold-cache and serialised: shares, not absolutes)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_ncu_launches_bench_n32768.csv \
+        python bench.py --gpus 1 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $O/r02_ncu_launches_bench.log 2>&1
+      grep -c gemm_f64 $O/r02_ncu_launches_bench_n32768.csv
+      ;;
+    lu)
+      REF=oracle/_ref
+      if [ -x $REF/lu_bench_host ] && [ -x $REF/dropin/lu_bench_gpu ]; then
+        for n in 4096 8192; do
+          echo "== LU bench n=$n host fallback" >> $O/r02_lu_bench.log
+          timeout 300 $REF/mpirun -np 4 -timeout 250 $REF/lu_bench_host -n $n -b_sm 64 -b_lrg 512 -num_iter 2 >> $O/r02_lu_bench.log 2>&1
+          echo "== LU bench n=$n GPU seam" >> $O/r02_lu_bench.log
+          timeout 300 $REF/mpirun -np 4 -timeout 250 $REF/dropin/lu_bench_gpu -n $n -b_sm 64 -b_lrg 512 -num_iter 2 >> $O/r02_lu_bench.log 2>&1
+        done
+        grep -E "==|Gigaflops|elapsed|failed|rror" $O/r02_lu_bench.log | head -20
+      fi
+      ;;
+    pending1)
+      timeout 600 python tools/bench_configs.py --pending > $O/r02_bench_pending_1gpu.jsonl 2> $O/r02_bench_pending_1gpu.err
+      cut -c1-400 $O/r02_bench_pending_1gpu.jsonl; tail -3 $O/r02_bench_pending_1gpu.err
+      ;;
+    parity)
+      # the parity workers at HEAD on every GPU of the box: library defaults, pending group, merged launches, peer-memory paths
+      CANDMC_TEST_VERBOSE=1 timeout 500 bash -c "$(declare -f trun); NG=$NG; trun 29533 tests/dist_worker.py" > $O/r02_parity_${NG}gpus.log 2>&1
+      tail -4 $O/r02_parity_${NG}gpus.log | cut -c1-400
+      CANDMC_TEST_PENDING=1 timeout 400 bash -c "$(declare -f trun); NG=$NG; trun 29535 tests/dist_worker.py" > $O/r02_parity_pending_${NG}gpus.log 2>&1
+      tail -3 $O/r02_parity_pending_${NG}gpus.log | cut -c1-400
+      ;;
+    parity_knobs)
+      CANDMC_TEST_MERGE_PANELS=2 CANDMC_TEST_PANEL_TRANSPORT=1 CANDMC_TEST_FUSED_GRIDS=1 timeout 400 bash -c "$(declare -f trun); NG=$NG; trun 29542 tests/dist_worker.py" > $O/r02_parity_knobs_${NG}gpus.log 2>&1
+      tail -3 $O/r02_parity_knobs_${NG}gpus.log | cut -c1-400
+      ;;
+    dropin)
+      timeout 400 python -m pytest tests/test_dropin_gpu.py -m gpu -q -rA -p no:cacheprovider > $O/r02_dropin_${NG}gpus.log 2>&1
+      tail -12 $O/r02_dropin_${NG}gpus.log | cut -c1-200
+      ;;
+    benchN)
+      # headline grid on this box: default, then the knobs one at a time (device-resident leg only), timeline of rank 0
+      for knobs in "" "--merge-panels 2" "--panel-transport" "--merge-panels 2 --panel-transport" "--merge-panels 2 --panel-transport --fused-reduce 2"; do
+        tag=$(echo "default $knobs" | tr -s ' -' '_')
+        echo "== bench $NG GPUs --no-e2e $knobs"
+        timeout 200 bash -c "$(declare -f trun); NG=$NG; trun 29543 bench.py --gpus $NG --steps 4 --warmup 3 --no-e2e --timeline $knobs" \
+          > $O/r02_bench${NG}_$tag.json 2> $O/r02_bench${NG}_$tag.err
+        cut -c1-120 $O/r02_bench${NG}_$tag.json; grep -o '"exposed_non_gemm_pct": [0-9.]*' $O/r02_bench${NG}_$tag.json
+        grep -o '"avg_launch_ms": [0-9.]*' $O/r02_bench${NG}_$tag.json
+        grep -A12 "GEMM timeline" $O/r02_bench${NG}_$tag.err | head -14
+      done
+      ;;
+    e2eN)
+      for knobs in "" ; do
+        echo "== bench $NG GPUs (with e2e) $knobs"
+        timeout 400 bash -c "$(declare -f trun); NG=$NG; trun 29537 bench.py --gpus $NG --steps 4 --warmup 3 $knobs" \
+          > $O/r02_bench${NG}_e2e.json 2> $O/r02_bench${NG}_e2e.err
+        cut -c1-2500 $O/r02_bench${NG}_e2e.json
+      done
+      ;;
+    configsN)
+      timeout 500 bash -c "$(declare -f trun); NG=$NG; trun 29544 tools/bench_configs.py" > $O/r02_configs_${NG}gpus.jsonl 2> $O/r02_configs_${NG}gpus.err
+      cut -c1-500 $O/r02_configs_${NG}gpus.jsonl; tail -3 $O/r02_configs_${NG}gpus.err
+      ;;
+    *) echo "unknown section $section";;
+  esac
+done
+echo "=== done ($(date +%T))"

@@ -17,6 +17,8 @@ ncu_full() {   # ncu_full <out-stem> <kernel regex> <count> cmd...
   local stem=$1 rx=$2 cnt=$3; shift 3
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$rx" -c $cnt -f -o $O/$stem "$@" > $O/$stem.log 2>&1
   python tools/ncu_summary.py $O/$stem.ncu-rep $O/$stem.csv > /dev/null 2>&1 && tail -n +3 $O/$stem.csv | cut -c1-400
+  # gpurun_out/ only travels back when it stays under 64 MiB: keep the report itself only when it is small
+  [ "$(stat -c %s $O/$stem.ncu-rep 2>/dev/null || echo 0)" -gt 6000000 ] && rm -f $O/$stem.ncu-rep
 }
 for section in "$@"; do
   echo "=== section $section ($(date +%T))"
@@ -66,6 +68,16 @@ for section in "$@"; do
         done
         grep -E "==|Gigaflops|elapsed|failed|rror" $O/r02_lu_bench.log | head -20
       fi
+      ;;
+    pack)
+      # the rewritten pack kernels: bit-exact tests first, then GB/s, then one ncu --set full pass over every pack kernel
+      timeout 600 python -m pytest tests/test_local_gpu.py -m gpu -x -q -p no:cacheprovider 2>&1 | tail -3
+      timeout 120 tools/gemm_probe pack 8192 > $O/r02_pack_probe.jsonl 2>&1; timeout 120 tools/gemm_probe pack 16384 >> $O/r02_pack_probe.jsonl 2>&1
+      cat $O/r02_pack_probe.jsonl
+      timeout 600 ncu --set full --clock-control none -k regex:'lda_tile|transpose' -s 3 -c 1 -f -o $O/r02_ncu_pack_copy tools/gemm_probe pack 8192 > $O/r02_ncu_pack_copy.log 2>&1
+      timeout 600 ncu --set full --clock-control none -k regex:'lda_tile|transpose' -s 16 -c 1 -f -o $O/r02_ncu_pack_axpby tools/gemm_probe pack 8192 > $O/r02_ncu_pack_axpby.log 2>&1
+      timeout 600 ncu --set full --clock-control none -k regex:'lda_tile|transpose' -s 29 -c 1 -f -o $O/r02_ncu_pack_transpose tools/gemm_probe pack 8192 > $O/r02_ncu_pack_transpose.log 2>&1
+      for k in copy axpby transpose; do python tools/ncu_summary.py $O/r02_ncu_pack_$k.ncu-rep $O/r02_ncu_pack_$k.csv > /dev/null 2>&1; tail -n +3 $O/r02_ncu_pack_$k.csv | cut -c1-300; done
       ;;
     pending1)
       timeout 600 python tools/bench_configs.py --pending > $O/r02_bench_pending_1gpu.jsonl 2> $O/r02_bench_pending_1gpu.err

@@ -51,6 +51,7 @@ SIGNATURES = {
     "candmc_debug_splitk": (C.c_int, [C.c_int]),
     "candmc_debug_prefetch_c": (C.c_int, [C.c_int]),
     "candmc_debug_transpose_tma": (C.c_int, [C.c_int]),
+    "candmc_debug_gemm_tile": (C.c_int, [C.c_int]),
     "candmc_debug_gemm_reserve_sms": (C.c_int, [C.c_int]),
     "candmc_set_fused_reduce": (C.c_int, [C.c_int]),
     "candmc_set_skip_unused_uploads": (C.c_int, [C.c_int]),

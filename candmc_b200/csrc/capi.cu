@@ -59,6 +59,12 @@ int candmc_debug_splitk(int on) {
   return OK;
 }
 
+int candmc_debug_gemm_tile(int tile_n) {
+  CANDMC_CHECK(tile_n == 0 || tile_n == 64 || tile_n == 128, "candmc_debug_gemm_tile: 0 (automatic), 64 or 128");
+  runtime().gemm_tile_n = tile_n;
+  return OK;
+}
+
 int candmc_debug_transpose_tma(int on) {
   runtime().transpose_tma = (on != 0);
   return OK;

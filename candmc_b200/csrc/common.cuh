@@ -164,6 +164,23 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
   return v;
 }
 
+// named barrier 1 among the first N threads of the CTA (the consumer warps of the GEMM kernels)
+template <int N>
+__device__ __forceinline__ void consumer_barrier() {
+  asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ unsigned sm_id() {
+  unsigned v;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void nanosleep_ns(unsigned ns) { asm volatile("nanosleep.u32 %0;" ::"r"(ns)); }
+
 __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
   double2 v;
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");

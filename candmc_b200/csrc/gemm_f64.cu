@@ -23,6 +23,8 @@
 //   * Out-of-range rows/cols/k are zero-filled by TMA (exact), stores are predicated: any m,n,k >= 0 works on the
 //     TMA path as long as the base pointers are 16 B aligned and lda/ldb are even.  Otherwise a plain tiled
 //     CUDA-core kernel (`gemm_f64_generic`) is used — still on the GPU; there is no CPU path.
+#include <algorithm>
+
 #include "common.cuh"
 #include "ipc.h"
 #include "runtime.h"
@@ -32,16 +34,29 @@ namespace candmc {
 namespace {
 
 constexpr int BM = 128;            // CTA tile rows
-constexpr int BN = 128;            // CTA tile cols
 constexpr int BK = 16;             // k per stage (one 128 B swizzle span of doubles)
-constexpr int NSTAGE = 6;          // 6 x 32 KiB = 192 KiB
-constexpr int OPER_BYTES = BM * BK * 8;          // 16 KiB per operand per stage
-constexpr int STAGE_BYTES = 2 * OPER_BYTES;      // 32 KiB
-constexpr int NCONSUMER_WARPS = 8;
-constexpr int NTHREADS = (NCONSUMER_WARPS + 4) * 32;  // + 1 producer warpgroup (setmaxnreg works per 4 warps)
-constexpr int PRODUCER_REGS = 40;                     // 4 warps x 40 + 8 warps x 232 regs = 64512 <= 65536
-constexpr int CONSUMER_REGS = 232;
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers + tile ids*/;
+constexpr int OPER_A_BYTES = BM * BK * 8;        // 16 KiB of A per stage
+// Two CTA shapes share one kernel body (TBN = tile columns):
+//   128: one CTA per SM, 8 consumer warps (2 along M x 4 along N), 6 stages of 32 KiB — the least shared-memory traffic per
+//        flop; the shape of long-k launches, where the epilogue is a fraction of a percent of a tile.
+//    64: TWO CTAs per SM, 4 consumer warps each (2 x 2), 4 stages of 24 KiB.  While one CTA of an SM is in its epilogue
+//        (a beta != 0 read-modify-write of C costs several k-tiles of a 128-wide tile's time during which the DMMA pipe of a
+//        lone CTA idles) the other one is in its main loop and has the pipe to itself: the epilogues of short-k launches
+//        (k-chunks of a SUMMA panel, the k = 512 update of the CAQR trailing matrix) disappear behind the neighbour's DMMAs.
+//        The second CTA of every SM starts half a tile late so the two stay out of phase.
+template <int TBN>
+struct Shape {
+  static constexpr int BN = TBN;
+  static constexpr int NSTAGE = TBN == 128 ? 6 : 4;
+  static constexpr int OPER_B_BYTES = TBN * BK * 8;
+  static constexpr int STAGE_BYTES = OPER_A_BYTES + OPER_B_BYTES;
+  static constexpr int NCW = 2 * (TBN / 32);                 // consumer warps, each a 64 x 32 register tile
+  static constexpr int NTHREADS = (NCW + 4) * 32;            // + 1 producer warpgroup (setmaxnreg works per 4 warps)
+  static constexpr int CTAS_PER_SM = TBN == 128 ? 1 : 2;
+  static constexpr int PRODUCER_REGS = 40;                   // 128: 4 x 40 + 8 x 232 regs per lane = 64512 <= 65536 per SM
+  static constexpr int CONSUMER_REGS = TBN == 128 ? 232 : 216;   // 64: 2 x (4 x 40 + 4 x 216) = 65536
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers + tile ids*/;
+};
 constexpr int RASTER_GROUP = 8;
 constexpr int PF_WINDOW = 64;      // k-tiles before the end of a unit over which the C tile's L2 prefetch is spread
 constexpr int kSplitSemCount = 4096;  // tiles a split-K launch may have (it is only used for small tile counts)
@@ -112,12 +127,16 @@ __device__ __forceinline__ UnitTile unit_tile(int tile, int tilesM, int tilesN, 
   return u;
 }
 
-template <bool A_KMAJ, bool B_KMAJ, bool FUSED>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <bool A_KMAJ, bool B_KMAJ, bool FUSED, int TBN>
+__global__ void __launch_bounds__(Shape<TBN>::NTHREADS, Shape<TBN>::CTAS_PER_SM)
 gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     double* __restrict__ C, int64_t ldc, int M, int N, int K, double alpha, double beta,
                     int tilesM, int tilesN, int* __restrict__ tile_counter, int ksplit, double* __restrict__ part,
-                    int* __restrict__ tile_sem, const __grid_constant__ FusedParams fp, int b_kc, int pf_c) {
+                    int* __restrict__ tile_sem, const __grid_constant__ FusedParams fp, int b_kc, int pf_c,
+                    int* __restrict__ sm_slots, unsigned stagger_ns) {
+  using S = Shape<TBN>;
+  constexpr int BN = S::BN, NSTAGE = S::NSTAGE, STAGE_BYTES = S::STAGE_BYTES, OPER_BYTES = OPER_A_BYTES;
+  constexpr int NCONSUMER_WARPS = S::NCW, NCT = S::NCW * 32;
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment for the 128 B swizzle atom; pointer arithmetic keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -145,10 +164,18 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp >= NCONSUMER_WARPS) {
     // ===================== TMA producer warpgroup (one lane works; the rest only donate registers) =========
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(S::PRODUCER_REGS));
     if (warp == NCONSUMER_WARPS && lane == 0) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
+      if (sm_slots != nullptr) {
+        // two CTAs per SM: the one that arrives second on its SM starts half a tile late, so that its epilogues fall into
+        // the other one's main loops (and vice versa) instead of coinciding with them
+        if (atomicAdd(sm_slots + sm_id(), 1) & 1) {
+          const unsigned long long t0 = global_timer_ns();
+          while (global_timer_ns() - t0 < stagger_ns) nanosleep_ns(2000);
+        }
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int iter = 0;; ++iter) {
@@ -195,7 +222,7 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           } else {
 #pragma unroll
-            for (int s = 0; s < 8; ++s) tma_load_2d(sb + s * 2048, &tmB, &full_bar[stage], n0 + 16 * s, k0);
+            for (int s = 0; s < BN / 16; ++s) tma_load_2d(sb + s * 2048, &tmB, &full_bar[stage], n0 + 16 * s, k0);
           }
           if (pf_w > 0 && kt1 - kt <= pf_w && pf_bytes > 0) {
             const int c0 = (pf_w - (kt1 - kt)) * pf_per;
@@ -213,12 +240,12 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 
   // ===================== DMMA consumers =====================
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(S::CONSUMER_REGS));
   const int g = lane >> 2;  // index slot
   const int j = lane & 3;   // k slot
   const int cf = cf_map(g);
   const int wm = warp & 1;   // 2 warps along M (64 rows each)
-  const int wn = warp >> 1;  // 4 warps along N (32 cols each)
+  const int wn = warp >> 1;  // BN / 32 warps along N (32 cols each)
 
   // per-lane smem byte offsets for the 4 k-steps (and, for MN-major, the two slab halves)
   const uint32_t smem_base = smem_u32(smem);
@@ -301,18 +328,18 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int f = 0; f < 8; ++f)
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          __stcg(mine + (f * 8 + h * 2 + 0) * 256, acc[f][h][0]);
-          __stcg(mine + (f * 8 + h * 2 + 1) * 256, acc[f][h][1]);
+          __stcg(mine + (f * 8 + h * 2 + 0) * NCT, acc[f][h][0]);
+          __stcg(mine + (f * 8 + h * 2 + 1) * NCT, acc[f][h][1]);
         }
       __threadfence();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      consumer_barrier<NCT>();
       __shared__ int s_last;
       if (threadIdx.x == 0) {
         const int old = atomicAdd(&tile_sem[tile], 1);
         s_last = (old == ksplit - 1);
         if (s_last) tile_sem[tile] = 0;  // ready for the next launch
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      consumer_barrier<NCT>();
       if (!s_last) continue;
       __threadfence();
       const double* all = part + static_cast<int64_t>(tile) * ksplit * (BM * BN) + threadIdx.x;
@@ -322,8 +349,8 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int h = 0; h < 4; ++h) {
           double s0 = 0.0, s1 = 0.0;
           for (int q2 = 0; q2 < ksplit; ++q2) {
-            s0 += __ldcg(all + static_cast<int64_t>(q2) * (BM * BN) + (f * 8 + h * 2 + 0) * 256);
-            s1 += __ldcg(all + static_cast<int64_t>(q2) * (BM * BN) + (f * 8 + h * 2 + 1) * 256);
+            s0 += __ldcg(all + static_cast<int64_t>(q2) * (BM * BN) + (f * 8 + h * 2 + 0) * NCT);
+            s1 += __ldcg(all + static_cast<int64_t>(q2) * (BM * BN) + (f * 8 + h * 2 + 1) * NCT);
           }
           acc[f][h][0] = s0;
           acc[f][h][1] = s1;
@@ -357,7 +384,7 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } while (v != fp.epoch);
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      consumer_barrier<NCT>();
     }
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
@@ -419,7 +446,7 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (FUSED) {
       __threadfence_system();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      consumer_barrier<NCT>();
       if (threadIdx.x == 0) {
         if (!owned) {
           asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(fp.sflag[tc.owner] + tc.within), "r"(fp.epoch) : "memory");
@@ -509,22 +536,14 @@ __global__ void scale_c_kernel(int M, int N, double beta, double* __restrict__ C
 bool is_trans(char t) { return t == 'T' || t == 't' || t == 'C' || t == 'c'; }
 bool is_notrans(char t) { return t == 'N' || t == 'n'; }
 
-template <bool AK, bool BK_, bool FUSED>
-int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_t ldc, int M, int N, int K,
-               double alpha, double beta, cudaStream_t stream, const FusedParams* fused, int b_kc = 0) {
-  static bool configured = false;  // per template instantiation
-  auto kern = gemm_f64_tma_kernel<AK, BK_, FUSED>;
-  if (!configured) {
-    CANDMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
-  }
-  const int tilesM = (M + BM - 1) / BM, tilesN = (N + BN - 1) / BN;
-  const int64_t tiles = static_cast<int64_t>(tilesM) * tilesN;
-  // split-K when the tiles alone cannot fill a few waves: pick the split that wastes the least of the last wave
-  int ksplit = 1;
+// split-K factor for a launch with 128 x 128 tiles (1 = none): when the tiles alone cannot fill a few waves, pick the split
+// that wastes the least of the last wave
+int pick_ksplit(int M, int N, int K) {
+  const int64_t tiles = static_cast<int64_t>((M + BM - 1) / BM) * ((N + 127) / 128);
   const int sms = runtime().num_sms;
   const int KT = (K + BK - 1) / BK;
-  if (!FUSED && runtime().splitk && tiles < 3 * sms && tiles <= kSplitSemCount) {
+  int ksplit = 1;
+  if (runtime().splitk && tiles < 3 * sms && tiles <= kSplitSemCount) {
     // cost model in k-tile units: waves x (k-tiles per unit + per-unit overhead); the overhead of a split unit (park the
     // partial tile, the last arriver re-reads `sp` of them) was measured at ~9 k-tiles + 1 per partial, an unsplit
     // tile's epilogue at ~3 (profiles/r01_gemm_probe_speed*.jsonl)
@@ -545,15 +564,54 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_
       }
     }
   }
+  return ksplit;
+}
+
+// CTA tile width of a launch (see Shape): the fused epilogue and split-K launches keep 128 x 128 tiles; otherwise two CTAs per
+// SM with 128 x 64 tiles when the epilogue is a noticeable part of a tile (beta != 0 and a short k) or the 128-wide tiles
+// would not fill a few waves.
+int pick_tile_n(int M, int N, int K, double beta, bool fused, int ksplit) {
+  if (fused || ksplit > 1) return 128;
+  if (runtime().gemm_tile_n != 0) return runtime().gemm_tile_n;
+  const int64_t tiles = static_cast<int64_t>((M + BM - 1) / BM) * ((N + 127) / 128);
+  const int KT = (K + BK - 1) / BK;
+  if (beta != 0.0 && KT <= 256) return 64;
+  if (tiles < 3 * runtime().num_sms) return 64;
+  return 128;
+}
+
+template <bool AK, bool BK_, bool FUSED, int TBN>
+int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_t ldc, int M, int N, int K,
+               double alpha, double beta, cudaStream_t stream, const FusedParams* fused, int b_kc, int ksplit) {
+  using S = Shape<TBN>;
+  constexpr int BN = S::BN;
+  static bool configured = false;  // per template instantiation
+  auto kern = gemm_f64_tma_kernel<AK, BK_, FUSED, TBN>;
+  if (!configured) {
+    CANDMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
+    configured = true;
+  }
+  const int tilesM = (M + BM - 1) / BM, tilesN = (N + BN - 1) / BN;
+  const int64_t tiles = static_cast<int64_t>(tilesM) * tilesN;
+  const int sms = runtime().num_sms;
+  const int KT = (K + BK - 1) / BK;
   double* part = nullptr;
   int* sem = nullptr;
   if (ksplit > 1) CANDMC_TRY(splitk_buffers(tiles * ksplit * BM * BN, &part, &sem, stream));
   const int64_t ntiles = tiles * ksplit;
   // leave `gemm_reserve_sms` SMs free when a schedule wants NCCL kernels to run beside this persistent kernel
-  const int avail = sms - runtime().gemm_reserve_sms > 0 ? sms - runtime().gemm_reserve_sms : 1;
+  const int avail = (sms - runtime().gemm_reserve_sms > 0 ? sms - runtime().gemm_reserve_sms : 1) * S::CTAS_PER_SM;
   const int grid = static_cast<int>(ntiles < avail ? ntiles : avail);
   int* counter = nullptr;
   if (!runtime().static_schedule) CANDMC_TRY(next_tile_counter(&counter, stream));
+  // two CTAs per SM: per-SM arrival counters tell the second CTA of an SM to start half a tile late (a 128 x 64 tile's k-tile
+  // takes about 2.08 us while two CTAs share the DMMA pipe: 148 SMs x 64 FMA/clk at 1.965 GHz)
+  int* sm_slots = nullptr;
+  unsigned stagger_ns = 0;
+  if (S::CTAS_PER_SM == 2 && grid > sms) {
+    CANDMC_TRY(next_sm_slots(&sm_slots, stream));
+    stagger_ns = static_cast<unsigned>(std::min<int64_t>((KT + ksplit - 1) / ksplit, 8192) * 1040);
+  }
   if (runtime().profile) CANDMC_TRY(profile_begin_launch(stream, 2.0 * M * (double)N * (double)K));
   FusedParams fp;
   if (FUSED) fp = *fused;
@@ -562,13 +620,22 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_
   const int64_t ldin = FUSED ? fp.ldin : ldc;
   const int pf_c = (runtime().prefetch_c && beta != 0.0 && ksplit == 1 && cin != nullptr &&
                     reinterpret_cast<uintptr_t>(cin) % 16 == 0 && ldin % 2 == 0) ? 1 : 0;
-  kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmB, C, ldc, M, N, K, alpha, beta, tilesM, tilesN, counter, ksplit,
-                                               part, sem, fp, b_kc, pf_c);
+  kern<<<grid, S::NTHREADS, S::SMEM_BYTES, stream>>>(tmA, tmB, C, ldc, M, N, K, alpha, beta, tilesM, tilesN, counter, ksplit,
+                                                     part, sem, fp, b_kc, pf_c, sm_slots, stagger_ns);
   CANDMC_CUDA(cudaGetLastError());
   if (ksplit > 1) CANDMC_TRY(splitk_release(stream));
   if (runtime().profile) CANDMC_TRY(profile_end_launch(stream));
   runtime().launches++;
   return OK;
+}
+
+template <bool FUSED, int TBN>
+int launch_tma_layouts(bool AK, bool BKm, const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_t ldc, int M, int N,
+                       int K, double alpha, double beta, cudaStream_t stream, const FusedParams* fused, int b_kc, int ksplit) {
+  if (AK && BKm) return launch_tma<true, true, FUSED, TBN>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, b_kc, ksplit);
+  if (AK && !BKm) return launch_tma<true, false, FUSED, TBN>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, b_kc, ksplit);
+  if (!AK && BKm) return launch_tma<false, true, FUSED, TBN>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, b_kc, ksplit);
+  return launch_tma<false, false, FUSED, TBN>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, b_kc, ksplit);
 }
 
 }  // namespace
@@ -637,23 +704,17 @@ int gemm_f64_ex(char transa, char transb, int64_t m, int64_t n, int64_t k, doubl
     const bool AK = tA;    // op(A)(m,kk) = A[kk + m*lda]  -> K contiguous
     const bool BKm = !tB;  // op(B)(kk,n) = B[kk + n*ldb]  -> K contiguous
     CANDMC_TRY(encode_tmap_f64(&tmA, A, AK ? k : m, AK ? m : k, lda, 16, AK ? BM : 16));
+    const int ksplit = fused ? 1 : pick_ksplit(M, N, K);
+    const int tbn = pick_tile_n(M, N, K, beta, fused != nullptr, ksplit);
     if (b_kc > 0) {   // chunk-major B: the k / b_kc chunks (b_kc x n, ld = b_kc) side by side
-      CANDMC_TRY(encode_tmap_f64(&tmB, B, b_kc, n * (k / b_kc), b_kc, 16, BN));
-      const int kc = static_cast<int>(b_kc);
-      if (AK) return launch_tma<true, true, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr, kc);
-      return launch_tma<false, true, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr, kc);
+      CANDMC_TRY(encode_tmap_f64(&tmB, B, b_kc, n * (k / b_kc), b_kc, 16, tbn));
+    } else {
+      CANDMC_TRY(encode_tmap_f64(&tmB, B, BKm ? k : n, BKm ? n : k, ldb, 16, BKm ? tbn : 16));
     }
-    CANDMC_TRY(encode_tmap_f64(&tmB, B, BKm ? k : n, BKm ? n : k, ldb, 16, BKm ? BN : 16));
-    if (fused) {
-      if (AK && BKm) return launch_tma<true, true, true>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused);
-      if (AK && !BKm) return launch_tma<true, false, true>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused);
-      if (!AK && BKm) return launch_tma<false, true, true>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused);
-      return launch_tma<false, false, true>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused);
-    }
-    if (AK && BKm) return launch_tma<true, true, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr);
-    if (AK && !BKm) return launch_tma<true, false, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr);
-    if (!AK && BKm) return launch_tma<false, true, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr);
-    return launch_tma<false, false, false>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr);
+    const int kc = static_cast<int>(b_kc);
+    if (fused) return launch_tma_layouts<true, 128>(AK, BKm, tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, kc, 1);
+    if (tbn == 64) return launch_tma_layouts<false, 64>(AK, BKm, tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr, kc, ksplit);
+    return launch_tma_layouts<false, 128>(AK, BKm, tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr, kc, ksplit);
   }
 
   CANDMC_CHECK(b_kc == 0, "dgemm(chunk-major B): operands not TMA-able");

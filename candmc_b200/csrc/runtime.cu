@@ -105,6 +105,7 @@ int runtime_finalize() {
   if (g_rt.workspace) cudaFree(g_rt.workspace);
   if (g_rt.stage_pool) cudaFree(g_rt.stage_pool);
   if (g_rt.tile_counters) cudaFree(g_rt.tile_counters);
+  if (g_rt.sm_slots) cudaFree(g_rt.sm_slots);
   if (g_rt.splitk_part) cudaFree(g_rt.splitk_part);
   if (g_rt.splitk_sem) cudaFree(g_rt.splitk_sem);
   if (g_splitk_last) cudaEventDestroy(g_splitk_last);
@@ -187,6 +188,15 @@ int splitk_buffers(int64_t part_elems, double** part, int** sem, cudaStream_t st
   }
   *part = g_rt.splitk_part;
   *sem = g_rt.splitk_sem;
+  return OK;
+}
+
+int next_sm_slots(int** out, cudaStream_t stream) {
+  constexpr unsigned kRing = 64;
+  if (g_rt.sm_slots == nullptr) CANDMC_CUDA(cudaMalloc(&g_rt.sm_slots, sizeof(int) * kSmSlotInts * kRing));
+  int* c = g_rt.sm_slots + static_cast<size_t>(g_rt.sm_slots_seq++ % kRing) * kSmSlotInts;
+  CANDMC_CUDA(cudaMemsetAsync(c, 0, sizeof(int) * kSmSlotInts, stream));
+  *out = c;
   return OK;
 }
 

@@ -33,6 +33,9 @@ struct Runtime {
   bool fused_reduce = true;             // depth all-reduce fused into the last GEMM's epilogue over peer memory
   bool transpose_tma = true;            // transpose through TMA loads / stores (candmc_debug_transpose_tma(0): the LDG/STG kernel)
   bool splitk = true;                   // cut small-tile-count GEMMs along k too
+  int gemm_tile_n = 0;                  // CTA tile columns of the DMMA GEMM: 0 automatic, 128 (one CTA per SM) or 64 (two per SM); candmc_debug_gemm_tile
+  int* sm_slots = nullptr;              // ring of per-SM arrival counters for launches with two CTAs per SM
+  unsigned sm_slots_seq = 0;
   bool prefetch_c = true;               // beta != 0 GEMMs prefetch their C tiles into L2 under the last k-tiles (candmc_debug_prefetch_c)
   double* splitk_part = nullptr;        // split-K partial tiles (grow-only) and per-tile arrival counters
   size_t splitk_part_elems = 0;
@@ -75,6 +78,9 @@ int stage_pool_get(size_t bytes, void** out);
 
 // Hands out a zeroed device counter (memset is enqueued on `stream`) for one GEMM launch.
 int next_tile_counter(int** out, cudaStream_t stream);
+// ... and a zeroed array of kSmSlotInts per-SM counters (launches with two CTAs per SM: which CTA of an SM came second)
+constexpr int kSmSlotInts = 256;
+int next_sm_slots(int** out, cudaStream_t stream);
 
 // 2-D FP64 tensor map with 128 B swizzle: dim0 contiguous (dim0 x dim1 elements, leading dimension `ld`),
 // box = box0 x box1 elements (box0 * 8 bytes must be <= 128).

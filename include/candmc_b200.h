@@ -74,6 +74,9 @@ unsigned long long candmc_merged_panel_launches(int chunk_major_b);
 int candmc_set_b_first_chunk_early(int on);
 /* Test/measurement hook: 0 disables the split-K path the GEMM takes for small tile counts (default on). */
 int candmc_debug_splitk(int on);
+/* Test/measurement hook: CTA tile of the TMA + DMMA GEMM — 128 (128 x 128 tiles, one CTA per SM), 64 (128 x 64 tiles, two CTAs
+ * per SM whose epilogues hide behind each other's main loops) or 0 = chosen per launch (default). */
+int candmc_debug_gemm_tile(int tile_n);
 /* Test/measurement hook: 0 routes candmc_transpose through the LDG/STG kernel instead of the TMA load / TMA store kernel
  * (which is also the automatic choice for operands that are not 16-byte aligned with even leading dimensions). */
 int candmc_debug_transpose_tma(int on);

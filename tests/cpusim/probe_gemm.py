@@ -81,4 +81,18 @@ check(lib().candmc_debug_splitk(0))
 d = run("T", "N", 128, 128, 16 * 48, 1.0, 0.0, seed=5)
 check(lib().candmc_debug_splitk(1))
 assert np.abs(a - d).max() <= 10 * 768 * EPS
+# the second CTA shape (128 x 64 tiles, two CTAs per SM, 4-stage ring, 4 consumer warps): every transpose combination with ragged
+# edges, more k-tiles than stages, an L2 prefetch of the C tile (beta != 0), and the automatic choice between the shapes
+check(lib().candmc_debug_gemm_tile(64))
+for ta in "NT":
+    for tb in "NT":
+        run(ta, tb, 150, 70, 36, -0.5, 1.0)
+        run(ta, tb, 128, 200, 16 * 6 + 3, 2.0, 0.0, pad=2, c_nan=True)
+run("N", "N", 300, 64, 16, 1.0, 1.0)
+e = run("N", "N", 256, 192, 80, 1.0, 0.5, seed=9)
+check(lib().candmc_debug_gemm_tile(128))
+f = run("N", "N", 256, 192, 80, 1.0, 0.5, seed=9)
+check(lib().candmc_debug_gemm_tile(0))
+g = run("N", "N", 256, 192, 80, 1.0, 0.5, seed=9)
+assert np.array_equal(e, f) and np.array_equal(e, g)   # same sums in the same order, whichever CTA shape multiplies
 print(json.dumps({"cases": cases, "max_rel_err": worst, "launches": int(cb.launch_count())}))

@@ -13,6 +13,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <string.h>
+#include <time.h>
 
 #include <functional>
 
@@ -186,6 +187,15 @@ static inline void tma_store_wait_all() {}
 static inline void tma_prefetch_desc(const CUtensorMap*) {}
 static inline void l2_prefetch_bulk(const void*, uint32_t) {}   // a cache hint: nothing to emulate
 static inline double lds_f64(uint32_t addr) { return *static_cast<const double*>(::cpusim::smem_ptr(addr)); }
+template <int N>
+static inline void consumer_barrier() { ::cpusim::named_barrier(1, N); }
+static inline unsigned sm_id() { return ::cpusim::ts().block.x % 148u; }   // blocks run one after the other: any id will do
+static inline unsigned long long global_timer_ns() {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (unsigned long long)t.tv_sec * 1000000000ull + (unsigned long long)t.tv_nsec;
+}
+static inline void nanosleep_ns(unsigned) {}
 static inline double2 lds_f64x2(uint32_t addr) {
   double2 v;
   memcpy(&v, ::cpusim::smem_ptr(addr), 16);

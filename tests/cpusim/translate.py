@@ -46,7 +46,7 @@ _EXTERN_SHARED = re.compile(r"extern\s+__shared__\s+([\w:]+)\s+(\w+)\s*\[\s*\]\s
 
 # the few inline-asm statements outside common.cuh's helpers (gemm_f64.cu): rewritten to their meaning
 _ASM_RULES = [
-    (re.compile(r'asm volatile\("setmaxnreg\.(?:dec|inc)\.sync\.aligned\.u32 %0;"\s*::\s*"n"\(\w+\)\);'), "/* setmaxnreg: registers are not modelled */"),
+    (re.compile(r'asm volatile\("setmaxnreg\.(?:dec|inc)\.sync\.aligned\.u32 %0;"\s*::\s*"n"\([\w:]+\)\);'), "/* setmaxnreg: registers are not modelled */"),
     (re.compile(r'asm volatile\("bar\.sync (\d+), (\d+);"\s*:::\s*"memory"\);'), r"::cpusim::named_barrier(\1, \2);"),
     (re.compile(r'asm volatile\("ld\.acquire\.sys\.global\.u32 %0, \[%1\];"\s*:\s*"=r"\((\w+)\)\s*:\s*"l"\(([^)]+)\)\s*:\s*"memory"\);'),
      r"\1 = __atomic_load_n(reinterpret_cast<const uint32_t*>(\2), __ATOMIC_ACQUIRE);"),

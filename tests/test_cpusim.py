@@ -74,6 +74,7 @@ _job("merge8_all", _torchrun(8, 29745, os.path.join(HERE, "dist_worker.py")), CA
      CANDMC_TEST_FUSED_GRIDS="1", CPUSIM_SCHED="random:21")
 # the hot kernel itself on the PTX emulation, and the 4-rank suite with every GEMM going through it
 _job("kernel", [sys.executable, os.path.join(SIM, "probe_gemm.py")])
+_job("kernel_pack", [sys.executable, os.path.join(SIM, "probe_pack.py")])
 _job("kernel_bchunk", [sys.executable, os.path.join(HERE, "bchunk_worker.py")])
 _job("kernel_f32", [sys.executable, os.path.join(HERE, "f32_worker.py"), "--fuzz", "17", "12" if not FULL else "80"])
 if FULL:
@@ -335,13 +336,22 @@ def test_hot_kernel_reads_chunk_major_b_through_one_tensor_map():
     assert r["cases"] >= 10 and not r["failures"] and r["launches"] >= 14
 
 
+def test_pack_kernels_on_the_simulator():
+    """candmc_b200/csrc/pack.cu: the tiled lda_cpy / scaled lda_cpy kernels (double2 and scalar paths, ragged tiles) and both
+    transpose kernels — TMA load, turn inside swizzled shared memory, TMA store; and the LDG/STG fallback — bit for bit"""
+    rc, so, se = RESULTS["kernel_pack"]
+    assert rc == 0, so[-2000:] + se[-3000:]
+    r = json.loads(so.strip().splitlines()[-1])
+    assert r["cases"] >= 36 and r["launches"] >= 36
+
+
 def test_hot_gemm_kernel_on_the_ptx_emulation():
     """candmc_b200/csrc/gemm_f64.cu itself — TMA boxes with the 128-byte swizzle and zero fill, the mbarrier ring, the
     permuted fragment loads, DMMA.8x8x4, split-K, the dynamic and the static tile scheduler, both epilogues — against numpy"""
     rc, so, se = RESULTS["kernel"]
     assert rc == 0, so[-2000:] + se[-3000:]
     r = json.loads(so.strip().splitlines()[-1])
-    assert r["cases"] >= 25 and r["max_rel_err"] <= 1e-13
+    assert r["cases"] >= 37 and r["max_rel_err"] <= 1e-13   # 25 with 128 x 128 tiles + 12 with the two-CTAs-per-SM shape
 
 
 def test_fp32_tcgen05_kernel_on_the_emulation():

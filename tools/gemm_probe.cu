@@ -287,6 +287,30 @@ int main(int argc, char** argv) {
     cublasDestroy(h);
     return 0;
   }
+  if (!strcmp(mode, "tile")) {
+    // A/B of the two CTA shapes (128 x 128 tiles, one CTA per SM / 128 x 64 tiles, two CTAs per SM) at the shapes the sweeps and
+    // the CAQR update launch, plus square ones down to where tiles stop filling waves
+    cublasHandle_t h;
+    cublasCreate(&h);
+    struct Sh { char ta, tb; int m, n, k; double beta; int reserve; };
+    const Sh shapes[] = {{'N', 'N', 16384, 16384, 2048, 1.0, 2}, {'N', 'N', 16384, 16384, 2048, 0.0, 2}, {'N', 'N', 8192, 8192, 1024, 1.0, 2},
+                         {'N', 'N', 8192, 8192, 7168, 1.0, 2},   {'N', 'N', 12288, 12288, 1536, 1.0, 0}, {'N', 'T', 12288, 12288, 12288, 1.0, 0},
+                         {'N', 'N', 65536, 8192, 512, 1.0, 0},   {'N', 'N', 65536, 8192, 512, 0.0, 0},   {'N', 'N', 32768, 4096, 512, 1.0, 0},
+                         {'N', 'N', 1024, 1024, 1024, 0.0, 0},   {'N', 'N', 2048, 2048, 2048, 0.0, 0},   {'N', 'N', 4096, 4096, 4096, 0.0, 0},
+                         {'N', 'N', 8192, 8192, 8192, 0.0, 0},   {'T', 'N', 8192, 8192, 8192, 0.0, 0},   {'N', 'N', 16384, 16384, 16384, 0.0, 0}};
+    for (auto& sh : shapes)
+      for (int tile : {128, 64}) {
+        candmc_debug_gemm_tile(tile);
+        candmc_debug_gemm_reserve_sms(sh.reserve);
+        char tag[64];
+        snprintf(tag, sizeof tag, "tile%d_reserve%d", tile, sh.reserve);
+        speed_one(h, sh.ta, sh.tb, sh.m, sh.n, sh.k, sh.k > 8192 ? 2 : 5, sh.beta, tag);
+      }
+    candmc_debug_gemm_tile(0);
+    candmc_debug_gemm_reserve_sms(0);
+    cublasDestroy(h);
+    return 0;
+  }
   if (!strcmp(mode, "speed")) {
     cublasHandle_t h;
     cublasCreate(&h);

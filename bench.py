@@ -37,7 +37,6 @@ METRIC = "FP64 TFLOP/s, 2.5D MM n=32768 (strong scaling over 1/2/4/8 B200)"
 # carries no FP64 figure; the cuBLAS DGEMM cross-check measured on this pool (profiles/r01_gemm_probe_speed.jsonl) is
 # 36.0 TFLOP/s at n = 16384 = 0.967 of this number, with SM clocks pinned at 1965 MHz under FP64 load.
 FP64_PEAK_TFLOPS = 148 * 4 * 16 * 2 * 1.965e9 / 1e12
-CUBLAS_DGEMM_MEASURED_TFLOPS = 36.0
 NVLINK_GBS = 770.0  # measured peer-copy figure from /opt/skills/guides/B200_PROFILING.md
 
 
@@ -254,9 +253,14 @@ def main():
     ap.add_argument("--late-c-download", action="store_true",
                     help="e2e leg: one download of C after the last multiply instead of slab-wise under the last multiplies")
     ap.add_argument("--panel-transport", action="store_true",
-                    help="SUMMA panels by copy engines into peer windows instead of ncclBroadcast (experimental)")
+                    help="(default behaviour now; accepted for old scripts) SUMMA panels by copy engines into peer windows")
+    ap.add_argument("--no-panel-transport", action="store_true",
+                    help="SUMMA panels by ncclBroadcast on CTA-capped communicators instead of copy engines into peer windows")
     ap.add_argument("--b-first-chunk-early", action="store_true",
                     help="e2e leg on grids: upload the first k-chunk of B ahead of the rest (experimental)")
+    ap.add_argument("--no-host-gather", action="store_true",
+                    help="e2e leg on grids: pinned host B blocks are copied whole and re-laid out on the device instead of being gathered "
+                         "chunk by chunk straight out of host memory")
     ap.add_argument("--no-numa-bind", action="store_true",
                     help="do not bind the rank to the CPUs next to its GPU before the pinned host blocks are allocated")
     ap.add_argument("--single-e2e-pass", action="store_true",
@@ -305,6 +309,10 @@ def main():
         cb.lib().candmc_set_b_first_chunk_early(1)
     if args.panel_transport:
         cb.lib().candmc_set_panel_transport(1)
+    if args.no_panel_transport:
+        cb.lib().candmc_set_panel_transport(0)
+    if args.no_host_gather:
+        cb.lib().candmc_set_host_gather(0)
     if args.host_panels is not None:
         cb.lib().candmc_set_host_pipeline_panels(args.host_panels)
     world = cb.init_world(rank, world_size, local)
@@ -365,7 +373,7 @@ def main():
         ts, te, cnt = (C.c_double * cap)(), (C.c_double * cap)(), C.c_int64()
         cb.lib().candmc_profile_gemm_timeline(ts, te, cap, C.byref(cnt))
         per_step = max(1, cnt.value // max(1, args.steps))
-        sys.stderr.write("GEMM timeline, rank 0 (ms since first launch): idx start end dur gap_before\n")
+        sys.stderr.write("GEMM timeline, rank 0 (ms since first launch; zero-length entries mark the start of a call): idx start end dur gap_before\n")
         for i in range(min(cnt.value, 2 * per_step)):
             gap = ts[i] - te[i - 1] if i else 0.0
             sys.stderr.write(f"  {i:3d} {ts[i]:9.3f} {te[i]:9.3f} {te[i] - ts[i]:8.3f} {gap:8.3f}\n")
@@ -388,6 +396,22 @@ def main():
         rel = max_over_ranks((d2 / r2) ** 0.5)
         del fa, fb, ref
 
+    # the cuBLAS DGEMM cross-check figure the roofline is compared with, measured in this run (outside the timed region)
+    cublas_tf = None
+    try:
+        nc = min(8192, n)
+        xa = torch.rand(nc, nc, dtype=torch.float64, device="cuda"); xb = torch.rand(nc, nc, dtype=torch.float64, device="cuda")
+        torch.matmul(xa, xb); torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            torch.matmul(xa, xb)
+        c1.record(); torch.cuda.synchronize()
+        cublas_tf = 3 * 2.0 * nc ** 3 / (c0.elapsed_time(c1) * 1e-3) / 1e12
+        del xa, xb
+    except Exception as exc:
+        sys.stderr.write(f"cuBLAS cross-check timing skipped: {exc}\n")
+
     # ... and a check that shares nothing with the GPU code: sampled entries of my block against operands regenerated on the host
     sampled = None
     try:
@@ -407,8 +431,8 @@ def main():
     e2e_passes = []
     pinned_knobs = args.upload_all_blocks or args.late_c_download or args.host_panels is not None
     passes = [("as_requested", None)] if (pinned_knobs or args.single_e2e_pass) else [
-        ("gpu_validated", {"skip_unused_uploads": 0, "early_c_download": 0, "host_pipeline_panels": 8}),
-        ("library_defaults", {"skip_unused_uploads": 1, "early_c_download": 1, "host_pipeline_panels": 0})]
+        ("round1_settings", {"skip_unused_uploads": 0, "early_c_download": 0, "host_pipeline_panels": 8, "host_gather": 0}),
+        ("library_defaults", {"skip_unused_uploads": 1, "early_c_download": 1, "host_pipeline_panels": 0, "host_gather": 1})]
 
     def e2e_pass(name, knobs):
         upload_all = args.upload_all_blocks
@@ -416,15 +440,29 @@ def main():
             cb.lib().candmc_set_skip_unused_uploads(knobs["skip_unused_uploads"])
             cb.lib().candmc_set_early_c_download(knobs["early_c_download"])
             cb.lib().candmc_set_host_pipeline_panels(knobs["host_pipeline_panels"])
+            cb.lib().candmc_set_host_gather(0 if (args.no_host_gather or not knobs["host_gather"]) else 1)
             upload_all = not knobs["skip_unused_uploads"]
         e2e_steps = max(1, min(args.steps, 2))
         step(hA, hB, hC)   # warm-up (allocations, page faults)
         barrier()
+        if args.timeline:
+            cb.lib().candmc_profile_enable(1)
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             step(hA, hB, hC)   # returns after C is back in host memory
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+        if args.timeline:   # where the end-to-end step spends its time: the multiplies of the step, with the call's entry marked
+            cap = 4096
+            ts, te, cnt = (C.c_double * cap)(), (C.c_double * cap)(), C.c_int64()
+            cb.lib().candmc_profile_gemm_timeline(ts, te, cap, C.byref(cnt))
+            cb.lib().candmc_profile_enable(0)
+            if rank == 0:
+                sys.stderr.write(f"end-to-end timeline ({name}), rank 0, {e2e_steps} steps of {dt * 1e3:.1f} ms (ms since the first call's entry; "
+                                 "zero-length entries mark the start of a call): idx start end dur gap_before\n")
+                for i in range(cnt.value):
+                    gap = ts[i] - te[i - 1] if i else 0.0
+                    sys.stderr.write(f"  {i:3d} {ts[i]:9.3f} {te[i]:9.3f} {te[i] - ts[i]:8.3f} {gap:8.3f}\n")
         # the end-to-end path must deliver the same block as the device-resident path (different k-chunking, so equal to
         # rounding, not bit for bit)
         chk = torch.empty(b * b, dtype=torch.float64, device="cuda")
@@ -487,19 +525,21 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "gemm_f64_tma_kernel (TMA + DMMA.8x8x4)", "achieved": achieved,
                          "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS if achieved else None,
                          "peak_source": "derived FP64 DMMA issue peak 148 SM x 64 FMA/clk x 1.965 GHz (MEASURED_PEAKS.json has no "
-                                        "FP64 entry); measured cuBLAS DGEMM on this pool = 36.0 TFLOP/s",
-                         "frac_of_cublas_measured": achieved / CUBLAS_DGEMM_MEASURED_TFLOPS if achieved else None,
+                                        "FP64 entry); the cuBLAS DGEMM cross-check is timed in this run",
+                         "cublas_dgemm_crosscheck_tflops_this_run": cublas_tf,
+                         "frac_of_cublas_measured": (achieved / cublas_tf) if (achieved and cublas_tf) else None,
                          "launches": int(nl.value), "avg_launch_ms": tms.value / nl.value if nl.value else None,
-                         "flops_per_launch": tfl.value / nl.value if nl.value else None, "traffic": None,
-                         # no ncu --set full capture of THIS launch size yet (tools/gpu_session.sh ncu); the one that exists:
-                         "traffic_other_capture": {"launch": "8192^3", "dram_bytes": 6.772272e9 + 0.531282e9,
-                                                   "algorithmic_bytes": 3 * 8192 * 8192 * 8,
-                                                   "source": "profiles/r01_ncu_full_gemm_f64_tma_n8192.csv (2.9 % of DRAM peak: the "
-                                                             "kernel is tensor-bound, panels are re-read out of L2, hit rate 81 %)"}},
+                         "flops_per_launch": tfl.value / nl.value if nl.value else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the ncu --set full capture of this
+                         # launch shape (N = 1: the 32768^3 launch, profiles/r02_session1_1gpu_stdout.log: 780.5 + 8.8 GB against
+                         # 25.8 GB algorithmic at 5 % of DRAM peak — each wave of 148 tiles streams its own panels, the kernel is
+                         # tensor-bound at 97 % DMMA issue); the grid launches (merged k-chunks) have no capture of their own
+                         "traffic": (780.497255e9 + 8.785575e9) if (world_size == 1 and n == 32768) else None,
+                         "traffic_algorithmic_bytes": 3.0 * 8 * n * n if world_size == 1 else None},
         }
         knobs = {k: v for k, v in (("bg_ctas", args.bg_ctas), ("fused_reduce", args.fused_reduce), ("min_kchunk", args.min_kchunk), ("merge_last_panel", args.merge_last_panel or None), ("merge_panels", args.merge_panels),
                                    ("upload_all_blocks", args.upload_all_blocks or None),
-                                   ("late_c_download", args.late_c_download or None), ("b_first_chunk_early", args.b_first_chunk_early or None), ("panel_transport", args.panel_transport or None), ("host_panels", args.host_panels)) if v is not None}
+                                   ("late_c_download", args.late_c_download or None), ("b_first_chunk_early", args.b_first_chunk_early or None), ("panel_transport", args.panel_transport or None), ("no_panel_transport", args.no_panel_transport or None), ("no_host_gather", args.no_host_gather or None), ("host_panels", args.host_panels)) if v is not None}
         if knobs:
             line["config"]["knobs"] = knobs  # non-default tuning switches used for this run
         if world_size == 1 and not args.no_cpu_baseline:

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(Shape<TBN>::NTHREADS, Shape<TBN>::CTAS_PER_SM)
 gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     double* __restrict__ C, int64_t ldc, int M, int N, int K, double alpha, double beta,
                     int tilesM, int tilesN, int* __restrict__ tile_counter, int ksplit, double* __restrict__ part,
-                    int* __restrict__ tile_sem, const __grid_constant__ FusedParams fp, int b_kc, int pf_c,
+                    int* __restrict__ tile_sem, const __grid_constant__ FusedParams fp, int b_kc, int b_cs, int pf_c,
                     int* __restrict__ sm_slots, unsigned stagger_ns) {
   using S = Shape<TBN>;
   constexpr int BN = S::BN, NSTAGE = S::NSTAGE, STAGE_BYTES = S::STAGE_BYTES, OPER_BYTES = OPER_A_BYTES;
@@ -212,11 +212,12 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int s = 0; s < 8; ++s) tma_load_2d(sa + s * 2048, &tmA, &full_bar[stage], m0 + 16 * s, k0);
           }
           if (B_KMAJ) {
-            // chunk-major B (b_kc > 0; what the SUMMA pipeline receives its panels as): k-chunk ch is its own b_kc x N
-            // matrix behind chunk ch-1, so in tmB the chunks stand side by side as one b_kc x (N * chunks) matrix
+            // chunk-major B (b_kc > 0; what the SUMMA pipeline receives its panels as): k-chunk ch is its own b_kc x b_cs
+            // matrix behind chunk ch-1, so in tmB the chunks stand side by side as one b_kc x (b_cs * chunks) matrix; this
+            // launch multiplies N <= b_cs of every chunk's columns (tmB's base is the first of them)
             if (b_kc > 0) {
               const int ch = k0 / b_kc;
-              tma_load_2d(sb, &tmB, &full_bar[stage], k0 - ch * b_kc, n0 + ch * N);
+              tma_load_2d(sb, &tmB, &full_bar[stage], k0 - ch * b_kc, n0 + ch * b_cs);
             } else {
               tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
             }
@@ -567,22 +568,23 @@ int pick_ksplit(int M, int N, int K) {
   return ksplit;
 }
 
-// CTA tile width of a launch (see Shape): the fused epilogue and split-K launches keep 128 x 128 tiles; otherwise two CTAs per
-// SM with 128 x 64 tiles when the epilogue is a noticeable part of a tile (beta != 0 and a short k) or the 128-wide tiles
-// would not fill a few waves.
+// CTA tile width of a launch (see Shape).  Measured on a B200 (profiles/r02_gemm_probe_tile.jsonl, TFLOP/s 128-wide / 64-wide):
+// 16384^2 x 2048 beta=1 on 146 SMs 33.6 / 35.1, beta=0 35.1 / 35.8; 8192^2 x 1024 beta=1 31.8 / 33.8; 65536 x 8192 x 512 beta=1
+// 31.0 / 32.6; 16384^3 36.0 / 36.1; 8192^3 35.6 / 35.8 — but 4096^3 35.4 / 35.1 and 2048^3 30.6 / 29.5.  So: two CTAs per SM
+// with 128 x 64 tiles whenever the 128-wide tiles fill at least eight waves or a short-k beta != 0 launch makes the epilogue
+// a large part of a tile; 128 x 128 tiles for small products, split-K launches and the fused depth-sum epilogue.
 int pick_tile_n(int M, int N, int K, double beta, bool fused, int ksplit) {
   if (fused || ksplit > 1) return 128;
   if (runtime().gemm_tile_n != 0) return runtime().gemm_tile_n;
   const int64_t tiles = static_cast<int64_t>((M + BM - 1) / BM) * ((N + 127) / 128);
   const int KT = (K + BK - 1) / BK;
   if (beta != 0.0 && KT <= 256) return 64;
-  if (tiles < 3 * runtime().num_sms) return 64;
-  return 128;
+  return tiles >= 8 * runtime().num_sms ? 64 : 128;
 }
 
 template <bool AK, bool BK_, bool FUSED, int TBN>
 int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_t ldc, int M, int N, int K,
-               double alpha, double beta, cudaStream_t stream, const FusedParams* fused, int b_kc, int ksplit) {
+               double alpha, double beta, cudaStream_t stream, const FusedParams* fused, int b_kc, int b_cs, int ksplit) {
   using S = Shape<TBN>;
   constexpr int BN = S::BN;
   static bool configured = false;  // per template instantiation
@@ -621,7 +623,7 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_
   const int pf_c = (runtime().prefetch_c && beta != 0.0 && ksplit == 1 && cin != nullptr &&
                     reinterpret_cast<uintptr_t>(cin) % 16 == 0 && ldin % 2 == 0) ? 1 : 0;
   kern<<<grid, S::NTHREADS, S::SMEM_BYTES, stream>>>(tmA, tmB, C, ldc, M, N, K, alpha, beta, tilesM, tilesN, counter, ksplit,
-                                                     part, sem, fp, b_kc, pf_c, sm_slots, stagger_ns);
+                                                     part, sem, fp, b_kc, b_cs, pf_c, sm_slots, stagger_ns);
   CANDMC_CUDA(cudaGetLastError());
   if (ksplit > 1) CANDMC_TRY(splitk_release(stream));
   if (runtime().profile) CANDMC_TRY(profile_end_launch(stream));
@@ -631,11 +633,11 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_
 
 template <bool FUSED, int TBN>
 int launch_tma_layouts(bool AK, bool BKm, const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_t ldc, int M, int N,
-                       int K, double alpha, double beta, cudaStream_t stream, const FusedParams* fused, int b_kc, int ksplit) {
-  if (AK && BKm) return launch_tma<true, true, FUSED, TBN>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, b_kc, ksplit);
-  if (AK && !BKm) return launch_tma<true, false, FUSED, TBN>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, b_kc, ksplit);
-  if (!AK && BKm) return launch_tma<false, true, FUSED, TBN>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, b_kc, ksplit);
-  return launch_tma<false, false, FUSED, TBN>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, b_kc, ksplit);
+                       int K, double alpha, double beta, cudaStream_t stream, const FusedParams* fused, int b_kc, int b_cs, int ksplit) {
+  if (AK && BKm) return launch_tma<true, true, FUSED, TBN>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, b_kc, b_cs, ksplit);
+  if (AK && !BKm) return launch_tma<true, false, FUSED, TBN>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, b_kc, b_cs, ksplit);
+  if (!AK && BKm) return launch_tma<false, true, FUSED, TBN>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, b_kc, b_cs, ksplit);
+  return launch_tma<false, false, FUSED, TBN>(tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, b_kc, b_cs, ksplit);
 }
 
 }  // namespace
@@ -649,10 +651,11 @@ int gemm_f64(char transa, char transb, int64_t m, int64_t n, int64_t k, double a
 int gemm_f64_fused(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                    int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, cudaStream_t stream,
                    const FusedParams* fused) {
-  return gemm_f64_ex(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, stream, fused, 0);
+  return gemm_f64_ex(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, stream, fused, 0, 0);
 }
 
 bool gemm_f64_bchunked_ok(const double* A, int64_t lda, const double* B, int64_t n, int64_t k, int64_t b_kc) {
+  // (n = columns per chunk: the chunk stride of the tensor map, whatever column range of it a launch multiplies)
   return b_kc > 0 && k > 0 && k % b_kc == 0 && b_kc % BK == 0 && n * (k / b_kc) < (1LL << 31) && lda % 2 == 0 &&
          reinterpret_cast<uintptr_t>(A) % 16 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0 && !runtime().force_generic;
 }
@@ -661,12 +664,22 @@ int gemm_f64_bchunked(char transa, int64_t m, int64_t n, int64_t k, double alpha
                       const double* B, int64_t b_kc, double beta, double* C, int64_t ldc, cudaStream_t stream) {
   CANDMC_CHECK(alpha != 0.0 && gemm_f64_bchunked_ok(A, lda, B, n, k, b_kc),
                "dgemm(chunk-major B): needs k a multiple of the chunk depth, the chunk depth a multiple of %d, aligned operands", BK);
-  return gemm_f64_ex(transa, 'N', m, n, k, alpha, A, lda, B, b_kc, beta, C, ldc, stream, nullptr, b_kc);
+  return gemm_f64_ex(transa, 'N', m, n, k, alpha, A, lda, B, b_kc, beta, C, ldc, stream, nullptr, b_kc, n);
+}
+
+int gemm_f64_bchunked_cols(char transa, int64_t m, int64_t ncols, int64_t k, double alpha, const double* A, int64_t lda,
+                           const double* B, int64_t b_kc, int64_t chunk_cols, int64_t col0, double beta, double* C, int64_t ldc,
+                           cudaStream_t stream) {
+  CANDMC_CHECK(alpha != 0.0 && col0 >= 0 && ncols > 0 && col0 + ncols <= chunk_cols && (col0 * b_kc) % 2 == 0 &&
+                   gemm_f64_bchunked_ok(A, lda, B, chunk_cols, k, b_kc),
+               "dgemm(chunk-major B, column range): needs k a multiple of the chunk depth, the chunk depth a multiple of %d, aligned operands", BK);
+  return gemm_f64_ex(transa, 'N', m, ncols, k, alpha, A, lda, B + col0 * b_kc, b_kc, beta, C, ldc, stream, nullptr, b_kc, chunk_cols);
 }
 
 int gemm_f64_ex(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc, cudaStream_t stream,
-                const FusedParams* fused, int64_t b_kc) {
+                const FusedParams* fused, int64_t b_kc, int64_t b_cs) {
+  NvtxRange nvtx_range("DGEMM");   // spcannon.cxx:116,194; mcdgemm_compute at d25_summa.cxx:185
   CANDMC_TRY(runtime_require());
   CANDMC_CHECK(is_trans(transa) || is_notrans(transa), "dgemm: bad transa '%c'", transa);
   CANDMC_CHECK(is_trans(transb) || is_notrans(transb), "dgemm: bad transb '%c'", transb);
@@ -707,14 +720,15 @@ int gemm_f64_ex(char transa, char transb, int64_t m, int64_t n, int64_t k, doubl
     const int ksplit = fused ? 1 : pick_ksplit(M, N, K);
     const int tbn = pick_tile_n(M, N, K, beta, fused != nullptr, ksplit);
     if (b_kc > 0) {   // chunk-major B: the k / b_kc chunks (b_kc x n, ld = b_kc) side by side
-      CANDMC_TRY(encode_tmap_f64(&tmB, B, b_kc, n * (k / b_kc), b_kc, 16, tbn));
+      // B points at column col0 of chunk 0: the map ends where the last chunk ends
+      CANDMC_TRY(encode_tmap_f64(&tmB, B, b_kc, b_cs * (k / b_kc - 1) + n, b_kc, 16, tbn));
     } else {
       CANDMC_TRY(encode_tmap_f64(&tmB, B, BKm ? k : n, BKm ? n : k, ldb, 16, BKm ? tbn : 16));
     }
-    const int kc = static_cast<int>(b_kc);
-    if (fused) return launch_tma_layouts<true, 128>(AK, BKm, tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, kc, 1);
-    if (tbn == 64) return launch_tma_layouts<false, 64>(AK, BKm, tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr, kc, ksplit);
-    return launch_tma_layouts<false, 128>(AK, BKm, tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr, kc, ksplit);
+    const int kc = static_cast<int>(b_kc), cs = static_cast<int>(b_cs);
+    if (fused) return launch_tma_layouts<true, 128>(AK, BKm, tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, kc, cs, 1);
+    if (tbn == 64) return launch_tma_layouts<false, 64>(AK, BKm, tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr, kc, cs, ksplit);
+    return launch_tma_layouts<false, 128>(AK, BKm, tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr, kc, cs, ksplit);
   }
 
   CANDMC_CHECK(b_kc == 0, "dgemm(chunk-major B): operands not TMA-able");

@@ -125,6 +125,22 @@ int tma_ready_operand(const double** p, int64_t* ld, int64_t rows, int64_t cols,
   return OK;
 }
 
+// CTAs of the kernel that gathers a k-chunk of B out of pinned host memory: 16 x 256 threads x 4 x 16 B = 256 KiB in flight
+// keeps a PCIe link busy (~75 KiB at 50 GB/s x 1.5 us) and fits the two SMs a sweep with traffic in flight leaves free
+constexpr int kHostGatherCtas = 16;
+
+// the device-side address of pinned (page-locked, mapped) host memory, or nullptr for pageable memory
+const double* device_alias_of_pinned(const double* host) {
+  if (host == nullptr || !runtime().host_gather) return nullptr;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (attr.type != cudaMemoryTypeHost || attr.devicePointer == nullptr) return nullptr;
+  return static_cast<const double*>(attr.devicePointer);
+}
+
 // number of k-chunks a sweep over b-wide panels uses (callers that upload operands chunk-wise must agree with it)
 int sweep_chunks(int64_t b, char tA, char tB, const candmc_comm* row, const candmc_comm* col) {
   const bool need_comm = row->size > 1 || col->size > 1;
@@ -136,12 +152,34 @@ int sweep_chunks(int64_t b, char tA, char tB, const candmc_comm* row, const cand
 // whole), so B is moved with full-height columns (one event for every chunk) and re-laid out per chunk on the device by the
 // pack kernel.  A follows in k-chunks (contiguous column slabs), one event each, so the multiply of chunk t starts while
 // chunk t+1 is still on the wire.
+//
+// PINNED host B (what `b_zero_copy` says; cudaHostAlloc / cudaHostRegister memory is addressable from the device): no copy of
+// the whole block in front of the first multiply at all — every k-chunk is gathered STRAIGHT OUT OF HOST MEMORY by the pack
+// kernel (coalesced 16-byte reads over PCIe, a capped grid that fits the SMs the multiplies leave free) and lands chunk-major,
+// ready to send and to multiply; B's chunk t and A's chunk t go up back to back, so the first multiply starts after 1/nchunks
+// of the two blocks instead of after all of B (2 GiB = 40-90 ms of PCIe at the headline sizes).
 int upload_chunks(const double* hA, int64_t lda, const double* hB, int64_t ldb, int64_t rows, int64_t cols, int64_t k,
                   int nchunks, double* dA, double* dB, cudaStream_t h2d, std::vector<cudaEvent_t>* a_ready,
-                  std::vector<cudaEvent_t>* b_ready) {
+                  std::vector<cudaEvent_t>* b_ready, const double* b_zero_copy) {
   const int64_t kc = k / nchunks;
   a_ready->assign(nchunks, nullptr);
   b_ready->assign(nchunks, nullptr);
+  if (hB && b_zero_copy) {
+    for (int t = 0; t < nchunks; ++t) {
+      CANDMC_TRY(lda_copy_f64_capped(kc, cols, ldb, kc, b_zero_copy + t * kc, dB + t * kc * cols, h2d, kHostGatherCtas));
+      (*b_ready)[t] = g_events.get();
+      CANDMC_CHECK((*b_ready)[t] != nullptr, "event pool exhausted");
+      CANDMC_CUDA(cudaEventRecord((*b_ready)[t], h2d));
+      if (hA) {
+        CANDMC_CUDA(cudaMemcpy2DAsync(dA + t * kc * rows, rows * 8, hA + t * kc * lda, lda * 8, rows * 8, kc,
+                                      cudaMemcpyHostToDevice, h2d));
+        (*a_ready)[t] = g_events.get();
+        CANDMC_CHECK((*a_ready)[t] != nullptr, "event pool exhausted");
+        CANDMC_CUDA(cudaEventRecord((*a_ready)[t], h2d));
+      }
+    }
+    return OK;
+  }
   if (hB) {
     // opt-in (candmc_set_b_first_chunk_early, not measured yet): the rows of the first k-chunk go ahead in their own 2-D copy
     // (narrow rows, but only 1/nchunks of B), so the first multiply does not wait for the whole block
@@ -169,6 +207,101 @@ int upload_chunks(const double* hA, int64_t lda, const double* hB, int64_t ldb, 
     }
   }
   return OK;
+}
+
+// ---- one launch group: k-chunks [lo, lo + mg) of a panel (or of a k-slice), multiplied onto C ----------------------------
+// The chunks go in ONE launch when their operands line up: A's chunks are consecutive column slabs of one matrix, B's are
+// either consecutive row slabs of one matrix (the panel's root multiplies out of the caller's block) or the chunk-major slots
+// the panel travels in (one tensor map over all of them, gemm_f64_bchunked).  Otherwise one launch per chunk.  With `slabs`
+// the group is multiplied column slab by column slab and slab_done(c0, w) is called behind each slab's last launch.
+struct GroupLaunch {
+  char tA, tB;
+  int64_t b, kc;
+  double* C;
+  int64_t ldC;
+  cudaStream_t compute;
+  FusedParams* fused = nullptr;   // the group is the single chunk whose epilogue performs the depth sum
+  double* fused_out = nullptr;
+  int64_t fused_ldout = 0;
+  double* scratchA = nullptr;     // kc * b doubles each: TMA-ready copies of the fused chunk's operands if needed
+  double* scratchB = nullptr;
+};
+
+int multiply_group(const GroupLaunch& g, int mg, const std::vector<const double*>& pa, const std::vector<int64_t>& lda,
+                   const std::vector<const double*>& pb, const std::vector<int64_t>& ldb, double beta0,
+                   const std::vector<int64_t>* slabs, const std::function<int(int64_t, int64_t)>& slab_done) {
+  const int64_t b = g.b, kc = g.kc;
+  const bool nn = is_n(g.tA) && is_n(g.tB);
+  bool a_one = true, b_plain = true, b_chunked = true;
+  for (int u = 0; u < mg; ++u) {
+    a_one = a_one && lda[u] == lda[0] && pa[u] == pa[0] + u * kc * lda[0];
+    b_plain = b_plain && ldb[u] == ldb[0] && pb[u] == pb[0] + u * kc;
+    b_chunked = b_chunked && ldb[u] == kc && pb[u] == pb[0] + u * kc * b;
+  }
+  if (mg == 1) b_chunked = false;   // a single chunk is a plain matrix whatever its leading dimension
+  const bool one_launch = mg == 1 || (nn && a_one && ((b_chunked && gemm_f64_bchunked_ok(pa[0], lda[0], pb[0], b, mg * kc, kc)) ||
+                                                      (b_plain && !b_chunked)));
+  // column ranges of this group's launches: the whole width, or the slabs of the early finalisation
+  std::vector<std::pair<int64_t, int64_t>> cols;
+  if (slabs != nullptr) {
+    int64_t c0 = 0;
+    for (int64_t w : *slabs) { cols.push_back({c0, w}); c0 += w; }
+  } else {
+    cols.push_back({0, b});
+  }
+  for (const auto& cw : cols) {
+    const int64_t c0 = cw.first, w = cw.second;
+    double* Cs = g.C + c0 * g.ldC;
+    if (g.fused != nullptr) {
+      // operands of the fused chunk must be TMA-able (16-byte aligned, even leading dimension): repack if they are not
+      CANDMC_CHECK(mg == 1 && slabs == nullptr, "the fused depth sum takes one chunk over the full width");
+      const double* fa = pa[0]; const double* fb = pb[0];
+      int64_t flda = lda[0], fldb = ldb[0];
+      CANDMC_TRY(tma_ready_operand(&fa, &flda, is_t(g.tA) ? kc : b, is_t(g.tA) ? b : kc, g.scratchA, g.compute));
+      CANDMC_TRY(tma_ready_operand(&fb, &fldb, is_t(g.tB) ? b : kc, is_t(g.tB) ? kc : b, g.scratchB, g.compute));
+      g.fused->Cin = g.C;
+      g.fused->ldin = g.ldC;
+      CANDMC_TRY(gemm_f64_fused(g.tA, g.tB, b, b, kc, 1.0, fa, flda, fb, fldb, beta0, g.fused_out, g.fused_ldout, g.compute, g.fused));
+    } else if (one_launch && mg > 1 && b_chunked) {
+      if (w == b) CANDMC_TRY(gemm_f64_bchunked('N', b, b, mg * kc, 1.0, pa[0], lda[0], pb[0], kc, beta0, Cs, g.ldC, g.compute));
+      else CANDMC_TRY(gemm_f64_bchunked_cols('N', b, w, mg * kc, 1.0, pa[0], lda[0], pb[0], kc, b, c0, beta0, Cs, g.ldC, g.compute));
+      runtime().merged_chunked++;
+    } else if (one_launch) {
+      // one chunk, or several that form one plain matrix
+      const int64_t kk = (nn ? mg : 1) * kc;
+      const double* pbs = is_t(g.tB) ? pb[0] + c0 : pb[0] + c0 * ldb[0];
+      CANDMC_TRY(gemm_f64(g.tA, g.tB, b, w, kk, 1.0, pa[0], lda[0], pbs, ldb[0], beta0, Cs, g.ldC, g.compute));
+      if (mg > 1) runtime().merged_plain++;
+    } else {
+      // layouts that do not line up (odd leading dimensions, operands staged whole): one launch per chunk
+      for (int u = 0; u < mg; ++u)
+        CANDMC_TRY(gemm_f64('N', 'N', b, w, kc, 1.0, pa[u], lda[u], pb[u] + c0 * ldb[u], ldb[u], (u == 0) ? beta0 : 1.0, Cs, g.ldC,
+                            g.compute));
+    }
+    if (slabs != nullptr) CANDMC_TRY(slab_done(c0, w));
+  }
+  return OK;
+}
+
+// the launch groups of `nchunks` k-chunks whose operands are still coming up from host memory (about six times slower than
+// they are multiplied): chunk 0, chunks 1-2, the rest; `lim` < nchunks leaves the chunks from lim on to themselves
+void host_upload_groups(int nchunks, int lim, std::vector<int>* grp_hi) {
+  grp_hi->resize(nchunks);
+  for (int t = 0; t < nchunks; ++t) (*grp_hi)[t] = t + 1;
+  if (lim > 2) {
+    (*grp_hi)[1] = std::min(3, lim);
+    if (lim > 3) (*grp_hi)[3] = lim;
+  }
+}
+
+// column slabs a b-wide C block is finalised in: graduated b/2, b/4, b/8, b/8 (the wide first slab has the rest of the multiply
+// to leave under, only the narrow last one is exposed), equal slabs when b does not divide that way, none when it is too ragged
+std::vector<int64_t> fin_slab_widths(int64_t b, int fin_slabs) {
+  std::vector<int64_t> w;
+  if (fin_slabs <= 1) return w;
+  if (b % 1024 == 0) w = {b / 2, b / 4, b / 8, b / 8};
+  else if (b % fin_slabs == 0) w.assign(fin_slabs, b / fin_slabs);
+  return w;
 }
 
 int summa_sweep(SummaArgs& a) {
@@ -205,6 +338,18 @@ int summa_sweep(SummaArgs& a) {
                                                      : runtime().gemm_reserve_sms);
   std::vector<cudaEvent_t> done_prev(nchunks, nullptr);
   bool first = a.first_beta_zero;
+  // Operands that are already on the device are packed for sending BEFORE the first multiply is enqueued (A out of its
+  // leading dimension, B chunk-major; a rank is the root of at most one A and one B panel per sweep): the pack kernels need
+  // SMs, and once a persistent GEMM owns all of them a pack enqueued behind it would only run when that GEMM ends — the
+  // first 4-GPU timeline of the copy-engine transport showed exactly that, 0.4 ms per chunk and 7 ms in front of a merged
+  // launch (profiles/r02_4gpu/).  Operands still coming up from host memory land send-ready (ld = b, B chunk-major).
+  const bool prepacked = need_comm && a.a_ready == nullptr && a.b_ready == nullptr;
+  if (prepacked) {
+    if (a.row->size > 1 && my_col >= a.i0 && my_col < a.i1 && a.ldA != b)
+      CANDMC_TRY(lda_copy_f64(b, b, a.ldA, b, a.myA, packA, comm));
+    if (a.col->size > 1 && my_row >= a.i0 && my_row < a.i1 && !a.b_chunk_major && (nchunks > 1 || a.ldB != b))
+      for (int t = 0; t < nchunks; ++t) CANDMC_TRY(lda_copy_f64(kc, b, a.ldB, kc, a.myB + t * kc, locB + t * kc * b, comm));
+  }
   for (int i = a.i0; i < a.i1; ++i) {
     const bool rootA = (my_col == i), rootB = (my_row == i);
     std::vector<cudaEvent_t> ready(nchunks, nullptr);
@@ -212,7 +357,8 @@ int summa_sweep(SummaArgs& a) {
     if (need_comm) {
       for (int t = 0; t < nchunks; ++t) {
         const bool bg = !(i == a.i0 && t == 0);  // the very first chunk has nothing to hide under: full-width communicator
-        if (done_prev[t]) CANDMC_CUDA(cudaStreamWaitEvent(comm, done_prev[t], 0));  // buf slot t is free again
+        // buf slot t is free again (the copy-engine transport gives every panel and chunk of a sweep its own window slot)
+        if (done_prev[t] && !all_dma) CANDMC_CUDA(cudaStreamWaitEvent(comm, done_prev[t], 0));
         const int op = (i - a.i0) * nchunks + t;   // transport slot of this (panel, chunk): its own, never reused in a sweep
         if (a.row->size > 1) {
           double* slot = bufA + t * kc * b;
@@ -220,7 +366,7 @@ int summa_sweep(SummaArgs& a) {
             CANDMC_TRY(wait_ready(comm, a.a_ready, t));
             const double* src = a.myA + t * kc * a.ldA;  // column slab: contiguous iff ldA == b
             if (a.ldA != b) {
-              CANDMC_TRY(lda_copy_f64(b, kc, a.ldA, b, src, packA + t * kc * b, comm));
+              if (!prepacked) CANDMC_TRY(lda_copy_f64(b, kc, a.ldA, b, src, packA + t * kc * b, comm));
               src = packA + t * kc * b;
             }
             if (tr_row) CANDMC_TRY(panel_transport_send(tr_row, a.row, op, op * kc * b, src, kc * b, comm));
@@ -235,7 +381,7 @@ int summa_sweep(SummaArgs& a) {
             CANDMC_TRY(wait_ready(comm, a.b_ready, t));
             const double* src = a.b_chunk_major ? a.myB + t * kc * b : a.myB + t * kc;  // row slab of B
             if (!a.b_chunk_major && (nchunks > 1 || a.ldB != b)) {
-              CANDMC_TRY(lda_copy_f64(kc, b, a.ldB, kc, src, locB + t * kc * b, comm));  // chunk-major, ld = kc
+              if (!prepacked) CANDMC_TRY(lda_copy_f64(kc, b, a.ldB, kc, src, locB + t * kc * b, comm));  // chunk-major, ld = kc
               src = locB + t * kc * b;
             }
             if (tr_col) CANDMC_TRY(panel_transport_send(tr_col, a.col, op, op * kc * b, src, kc * b, comm));
@@ -278,112 +424,67 @@ int summa_sweep(SummaArgs& a) {
       }
       return OK;
     };
-    // chunks [0, h) are multiplied over the full width; with early finalisation the rest of the last panel goes slab-wise
-    const bool slabs = (i + 1 == a.i1 && a.fin_slabs > 1 && a.slab_done && nchunks >= 2 && a.fused == nullptr &&
-                        is_n(a.tA) && is_n(a.tB) && b % a.fin_slabs == 0);
-    const int h = slabs ? nchunks / 2 : nchunks;
-    // opt-in (candmc_set_merge_panels, not measured yet): several k-chunks of a panel in ONE launch — one epilogue and one tail
-    // wave for all of them instead of one per chunk.  A's chunks are consecutive column slabs of one matrix; B's
-    // chunk-major slots are read through one tensor map (gemm_f64_bchunked).  Which chunks:
-    //   mode 2, every panel: chunk 0 alone, then chunks 1 .. nc-1 together.  A chunk's broadcast takes a small fraction of its
-    //     multiply (NVLink against the FP64 pipe), so by the time chunk 0 has been multiplied the rest of the panel has arrived;
-    //     the exposed start of a sweep stays one chunk's broadcast.  (With the fused depth sum the last chunk stays apart: its
-    //     launch is the one with the reducing epilogue.)  Not with operands that are still being uploaded from host memory —
-    //     PCIe is slower than the multiply, that pipeline keeps its per-chunk launches.
-    //   mode 1, only the last panel of a sweep with a panel in front of it: chunks 0 .. nc-2 together (all broadcast under the
-    //     previous panel's multiplies), the last chunk — whose slot came free last — apart.
-    //   mode 3, every panel, for links that are only a few times faster than the multiply: groups that double — chunk 0,
-    //     chunk 1, chunks 2-3, chunks 4-7: each group only has to arrive while the one before it (as deep as all before
-    //     that together) is multiplied.  Four launches per panel of eight chunks.
+    // ---- which k-chunks go into one launch ----
+    // Every launch pays its own epilogue (a read-modify-write of the C tile) and its own tail wave, so the chunks of a panel
+    // are multiplied in as few launches as the arrival of the data allows:
+    //   * the first panel of a sweep has nothing to hide its transfer under: chunk 0 alone (its transfer is the exposed start
+    //     of the sweep), then everything else in one launch — over NVLink the rest of the panel arrives while chunk 0 is being
+    //     multiplied.  Operands that are still coming up from host memory arrive ~6x slower (PCIe): chunk 0, chunks 1-2, the rest.
+    //   * later panels were moved under the previous panel's multiplies: with the copy-engine transport (own window slot per
+    //     panel and chunk) the whole panel is there — one launch; with ncclBroadcast the chunks' buffer slots only come free as
+    //     the previous panel's launches finish — chunk 0, then the rest (its broadcasts run under chunk 0's multiply).
+    //   * the fused depth sum keeps the last chunk apart: its launch is the one with the reducing epilogue.
+    //   * merge_panels = 0 restores one launch per chunk (tests, A/B measurements); modes 1 and 3 are the earlier experiments.
+    const bool last_panel = (i + 1 == a.i1), first_panel = (i == a.i0);
+    const bool host_ops = (a.a_ready != nullptr || a.b_ready != nullptr);
+    const bool nn = is_n(a.tA) && is_n(a.tB);
     std::vector<int> grp_hi(nchunks);   // chunks [t, grp_hi[t]) go in one launch when t starts a group
     for (int t = 0; t < nchunks; ++t) grp_hi[t] = t + 1;
-    if (runtime().merge_panels > 0 && nchunks > 2 && !slabs && is_n(a.tA) && is_n(a.tB)) {
-      const bool last_panel = (i + 1 == a.i1);
-      const int mode = runtime().merge_panels;
-      if (mode >= 2 && a.a_ready == nullptr && a.b_ready == nullptr) {
-        const int lim = (last_panel && a.fused != nullptr) ? nchunks - 1 : nchunks;
-        if (mode == 2) {
-          if (lim > 1) grp_hi[1] = lim;
-        } else {
-          for (int lo = 2, sz = 2; lo < lim; lo += sz, sz *= 2) grp_hi[lo] = std::min(lim, lo + sz);
+    const int mode = runtime().merge_panels;
+    if (mode > 0 && nchunks > 2 && nn) {
+      const int lim = (last_panel && a.fused != nullptr) ? nchunks - 1 : nchunks;
+      if (mode == 2) {
+        if (first_panel && host_ops) {
+          host_upload_groups(nchunks, lim, &grp_hi);
+        } else if (!first_panel && all_dma) {
+          grp_hi[0] = lim;
+        } else if (lim > 1) {
+          grp_hi[1] = lim;
         }
-      } else if (mode == 1 && last_panel && i > a.i0 && a.fused == nullptr) {
+      } else if (mode == 3 && !host_ops) {
+        for (int lo = 2, sz = 2; lo < lim; lo += sz, sz *= 2) grp_hi[lo] = std::min(lim, lo + sz);
+      } else if (mode == 1 && !host_ops && last_panel && !first_panel && a.fused == nullptr) {
         grp_hi[0] = nchunks - 1;
       }
     }
-    for (int t = 0; t < h; ++t) {
-      if (grp_hi[t] - t >= 2) {
-        const int mg_lo = t, mg = grp_hi[t] - t;
-        std::vector<const double*> pa(mg), pb(mg);
-        std::vector<int64_t> lda(mg), ldb(mg);
-        // ask operands() for the layouts: the waits it enqueues are the ones the merged launch needs, and harmless in front of
-        // per-chunk launches should the layouts not qualify
-        for (int u = 0; u < mg; ++u) CANDMC_TRY(operands(mg_lo + u, &pa[u], &lda[u], &pb[u], &ldb[u]));
-        bool a_one = true, b_plain = true, b_chunked = true;
-        for (int u = 0; u < mg; ++u) {
-          a_one = a_one && lda[u] == lda[0] && pa[u] == pa[0] + u * kc * lda[0];
-          b_plain = b_plain && ldb[u] == ldb[0] && pb[u] == pb[0] + u * kc;
-          b_chunked = b_chunked && ldb[u] == kc && pb[u] == pb[0] + u * kc * b;
-        }
-        const double beta0 = first ? 0.0 : 1.0;
-        bool done = false;
-        if (a_one && b_chunked && gemm_f64_bchunked_ok(pa[0], lda[0], pb[0], b, mg * kc, kc)) {
-          CANDMC_TRY(gemm_f64_bchunked('N', b, b, mg * kc, 1.0, pa[0], lda[0], pb[0], kc, beta0, a.C, a.ldC, a.compute));
-          runtime().merged_chunked++;
-          done = true;
-        } else if (a_one && b_plain && !b_chunked) {
-          CANDMC_TRY(gemm_f64('N', 'N', b, b, mg * kc, 1.0, pa[0], lda[0], pb[0], ldb[0], beta0, a.C, a.ldC, a.compute));
-          runtime().merged_plain++;
-          done = true;
-        }
-        if (done) {
-          first = false;
-          if (need_comm && i + 1 < a.i1) {   // the slots of all merged chunks come free together
-            cudaEvent_t e = g_events.get();
-            CANDMC_CHECK(e != nullptr, "event pool exhausted");
-            CANDMC_CUDA(cudaEventRecord(e, a.compute));
-            for (int u = 0; u < mg; ++u) done_prev[mg_lo + u] = e;
-          }
-          t = mg_lo + mg - 1;
-          continue;
-        }
-      }
-      const double* pa;
-      const double* pb;
-      int64_t lda, ldb;
-      CANDMC_TRY(operands(t, &pa, &lda, &pb, &ldb));
-      const bool last = (i + 1 == a.i1 && t + 1 == nchunks);
-      if (last && a.fused != nullptr) {
-        // operands of this last chunk must be TMA-able; packA / locB chunk slots of this rank are free to use as scratch
-        // only if it is not the root of the panel (a root multiplies out of the caller's matrices), so use bufA/bufB
-        // slots of the chunk, which a root never receives into
-        CANDMC_TRY(tma_ready_operand(&pa, &lda, is_t(a.tA) ? kc : b, is_t(a.tA) ? b : kc, bufA + t * kc * b, a.compute));
-        CANDMC_TRY(tma_ready_operand(&pb, &ldb, is_t(a.tB) ? b : kc, is_t(a.tB) ? kc : b, bufB + t * kc * b, a.compute));
-        a.fused->Cin = a.C;
-        a.fused->ldin = a.ldC;
-        CANDMC_TRY(gemm_f64_fused(a.tA, a.tB, b, b, kc, 1.0, pa, lda, pb, ldb, first ? 0.0 : 1.0, a.fused_out,
-                                  a.fused_ldout, a.compute, a.fused));
-      } else {
-        CANDMC_TRY(gemm_f64(a.tA, a.tB, b, b, kc, 1.0, pa, lda, pb, ldb, first ? 0.0 : 1.0, a.C, a.ldC, a.compute));
-      }
+    // Early finalisation (host C): the LAST launch group of the sweep is cut into column slabs — each slab still covers all of
+    // the group's k, so it is a handful of large launches, not one per chunk and slab — and slab_done() ships a slab (depth
+    // sum, download) while the next ones multiply.  Graduated widths b/2, b/4, b/8, b/8: the wide first slab has the rest of
+    // the multiply to leave under, only the narrow last one is exposed.
+    std::vector<int64_t> slab_w;
+    if (last_panel && a.slab_done && a.fused == nullptr && nn) slab_w = fin_slab_widths(b, a.fin_slabs);
+    int last_group_lo = 0;
+    for (int t = 0; t < nchunks; t = grp_hi[t]) last_group_lo = t;
+
+    for (int t = 0; t < nchunks; t = grp_hi[t]) {
+      const int mg_lo = t, mg = grp_hi[t] - t;
+      const bool slabbed = !slab_w.empty() && mg_lo == last_group_lo;
+      std::vector<const double*> pa(mg), pb(mg);
+      std::vector<int64_t> lda(mg), ldb(mg);
+      // the waits operands() enqueues are the ones the launches below need, merged or not
+      for (int u = 0; u < mg; ++u) CANDMC_TRY(operands(mg_lo + u, &pa[u], &lda[u], &pb[u], &ldb[u]));
+      const bool fused_here = last_panel && mg_lo + mg == nchunks && a.fused != nullptr;
+      GroupLaunch gl;
+      gl.tA = a.tA; gl.tB = a.tB; gl.b = b; gl.kc = kc; gl.C = a.C; gl.ldC = a.ldC; gl.compute = a.compute;
+      gl.fused = fused_here ? a.fused : nullptr; gl.fused_out = a.fused_out; gl.fused_ldout = a.fused_ldout;
+      gl.scratchA = bufA + mg_lo * kc * b; gl.scratchB = bufB + mg_lo * kc * b;
+      CANDMC_TRY(multiply_group(gl, mg, pa, lda, pb, ldb, first ? 0.0 : 1.0, slabbed ? &slab_w : nullptr, a.slab_done));
       first = false;
-      if (need_comm && i + 1 < a.i1) {
-        done_prev[t] = g_events.get();
-        CANDMC_CHECK(done_prev[t] != nullptr, "event pool exhausted");
-        CANDMC_CUDA(cudaEventRecord(done_prev[t], a.compute));
-      }
-    }
-    if (slabs) {
-      const int64_t w = b / a.fin_slabs;
-      std::vector<const double*> pa(nchunks), pb(nchunks);
-      std::vector<int64_t> lda(nchunks), ldb(nchunks);
-      for (int t = h; t < nchunks; ++t) CANDMC_TRY(operands(t, &pa[t], &lda[t], &pb[t], &ldb[t]));
-      for (int j = 0; j < a.fin_slabs; ++j) {
-        const int64_t c0 = j * w;
-        for (int t = h; t < nchunks; ++t)   // h >= 1, so these always accumulate onto the first half
-          CANDMC_TRY(gemm_f64('N', 'N', b, w, kc, 1.0, pa[t], lda[t], pb[t] + c0 * ldb[t], ldb[t], 1.0, a.C + c0 * a.ldC,
-                              a.ldC, a.compute));
-        CANDMC_TRY(a.slab_done(c0, w));
+      if (need_comm && !last_panel) {   // the buffer slots of the group's chunks come free together
+        cudaEvent_t e = g_events.get();
+        CANDMC_CHECK(e != nullptr, "event pool exhausted");
+        CANDMC_CUDA(cudaEventRecord(e, a.compute));
+        for (int u = 0; u < mg; ++u) done_prev[mg_lo + u] = e;
       }
     }
   }
@@ -648,6 +749,11 @@ using namespace candmc;
 
 extern "C" {
 
+int candmc_set_host_gather(int on) {
+  runtime().host_gather = (on != 0);
+  return OK;
+}
+
 int candmc_set_panel_transport(int on) {
   runtime().panel_transport = (on != 0);
   return OK;
@@ -707,6 +813,7 @@ int candmc_set_min_kchunk(int64_t min_kchunk) {
 // ================================================================================================================
 int candmc_summa(const candmc_ctb_args_t* args, const double* mat_A, const double* mat_B, double* mat_C,
                  double* buffer, candmc_comm_t* cdt_row, candmc_comm_t* cdt_col, void* stream) {
+  NvtxRange nvtx_range("d2_topo_bcast_gemm");   // summa.cxx:58
   CANDMC_TRY(runtime_require());
   g_events.reset();
   int64_t b;
@@ -737,6 +844,7 @@ int candmc_summa(const candmc_ctb_args_t* args, const double* mat_A, const doubl
 int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const double* mat_B, double* mat_C,
                      double* buffer, candmc_comm_t* cdt_row, candmc_comm_t* cdt_col, candmc_comm_t* cdt_kdir,
                      int ovp, void* stream) {
+  NvtxRange nvtx_range("d25_summa_gemm");   // d25_summa.cxx:122
   CANDMC_TRY(runtime_require());
   g_events.reset();
   int64_t b;
@@ -752,6 +860,12 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   CANDMC_CHECK(buffer == nullptr || args->buffer_size >= need, "d25_summa: buffer_size %lld < %lld",
                (long long)args->buffer_size, (long long)need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // profiling: a zero-flop entry at the start of the call, so a timeline shows what precedes the first multiply (uploads, the
+  // first panel chunk) and, through the next call's entry, what follows the last one (depth sum, download of C)
+  if (runtime().profile) {
+    CANDMC_TRY(profile_begin_launch(st, 0.0));
+    CANDMC_TRY(profile_end_launch(st));
+  }
   if (q == 1 && c == 1 && b >= runtime().host_pipeline_min && is_n(args->trans_A) && is_n(args->trans_B) && !is_device_ptr(mat_A) &&
       !is_device_ptr(mat_B) && !is_device_ptr(mat_C))
     return host_pipelined_gemm_nn(b, b, b, mat_A, args->lda_A, mat_B, args->lda_B, mat_C, args->lda_C, st);
@@ -780,7 +894,7 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   StagedMatrix sA, sB, sC;
   const double* dA_ptr = nullptr; const double* dB_ptr = nullptr;
   int64_t dA_ld = 0, dB_ld = 0;
-  bool b_chunk_major = false;
+  bool b_chunk_major = false, host_gather_active = false;
   if (chunked) {
     void* pool = nullptr;
     const int64_t needA = hostA ? b * kloc : 0, needB = hostB ? kloc * b : 0;
@@ -791,10 +905,13 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
     CANDMC_TRY(stream_wait(h2d, st));
     const double* hA = hostA ? mat_A + (ksplit ? layer * kloc * args->lda_A : 0) : nullptr;
     const double* hB = hostB ? mat_B + (ksplit ? layer * kloc : 0) : nullptr;
-    CANDMC_TRY(upload_chunks(hA, args->lda_A, hB, args->lda_B, b, b, kloc, up_chunks, upA, upB, h2d, &a_ready, &b_ready));
+    // pinned B: gathered chunk by chunk straight out of host memory, lands chunk-major (even chunk depth: 16-byte accesses)
+    const double* hB_dev = (hostB && up_chunks > 1 && (kloc / up_chunks) % 2 == 0) ? device_alias_of_pinned(hB) : nullptr;
+    CANDMC_TRY(upload_chunks(hA, args->lda_A, hB, args->lda_B, b, b, kloc, up_chunks, upA, upB, h2d, &a_ready, &b_ready, hB_dev));
     if (hostA) { dA_ptr = upA; dA_ld = b; }
     else if (useA) { dA_ptr = mat_A + (ksplit ? layer * kloc * args->lda_A : 0); dA_ld = args->lda_A; }
-    if (hostB) { dB_ptr = upB; dB_ld = kloc; }
+    if (hostB && hB_dev) { dB_ptr = upB; dB_ld = kloc / up_chunks; b_chunk_major = true; host_gather_active = true; }
+    else if (hostB) { dB_ptr = upB; dB_ld = kloc; }
     else if (useB) { dB_ptr = mat_B + (ksplit ? layer * kloc : 0); dB_ld = args->lda_B; }
   } else {
     CANDMC_TRY(sA.open(mat_A, b, b, args->lda_A, true, st));
@@ -822,7 +939,8 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   // slab's transfer stays exposed.  The fused depth sum works on whole square blocks, so it stays off on this path.
   const int fin_slabs = (sC.staged() && nn && runtime().early_c_download) ? pick_fin_slabs(b) : 0;
   const int nch_consumer = ksplit ? (chunked ? up_chunks : 1) : sweep_chunks(b, args->trans_A, args->trans_B, cdt_row, cdt_col);
-  const bool slab_mode = fin_slabs > 1 && nch_consumer >= 2 && !(c > 1 && !ksplit && runtime().fused_reduce_grids);
+  const bool slab_mode = fin_slabs > 1 && nch_consumer >= 2 && !(c > 1 && !ksplit && runtime().fused_reduce_grids) &&
+                         !fin_slab_widths(b, fin_slabs).empty();
   int slabs_out = 0;
   cudaStream_t d2h = runtime().aux_stream;
   auto slab_done = [&](int64_t c0, int64_t w) -> int {
@@ -848,6 +966,8 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
     return OK;
   };
 
+  // the kernels that gather B's k-chunks out of pinned host memory run beside the multiplies: leave them their SMs
+  ReserveGuard gather_guard(host_gather_active ? std::max(2, runtime().gemm_reserve_sms) : runtime().gemm_reserve_sms);
   FusedCtx* fctx = nullptr;
   FusedParams fparams;
   // (on q > 1 grids the fused path is opt-in until it has been validated on 8 GPUs: candmc_set_fused_reduce(2))
@@ -855,10 +975,9 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   if (fctx) fused_params_next(fctx, layer, &fparams);
 
   if (ksplit) {
-    // my k-slice, multiplied chunk by chunk as the chunks land (one chunk when the operands are already on the device)
+    // my k-slice in launch groups of k-chunks as they land (one chunk when the operands are already on the device)
     const int nch = chunked ? up_chunks : 1;
     const int64_t kc = kloc / nch;
-    const int h = slab_mode ? nch / 2 : nch;   // chunks [0, h) over the full width, the rest slab-wise (see slab_done)
     auto operands = [&](int t, const double** pa, int64_t* lda, const double** pb, int64_t* ldb) -> int {
       if (t < (int)a_ready.size() && a_ready[t]) CANDMC_CUDA(cudaStreamWaitEvent(st, a_ready[t], 0));
       if (t < (int)b_ready.size() && b_ready[t]) CANDMC_CUDA(cudaStreamWaitEvent(st, b_ready[t], 0));
@@ -868,38 +987,26 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
       *ldb = b_chunk_major ? kc : dB_ld;
       return OK;
     };
-    for (int t = 0; t < h; ++t) {
-      const double* pa;
-      const double* pb;
-      int64_t lda, ldb;
-      CANDMC_TRY(operands(t, &pa, &lda, &pb, &ldb));
-      const bool last = (t + 1 == nch);
-      if (last && fctx) {
-        const bool need_scratch = reinterpret_cast<uintptr_t>(pa) % 16 || lda % 2 || reinterpret_cast<uintptr_t>(pb) % 16 || ldb % 2;
-        if (need_scratch) {
-          double* s0 = ws + ws_panels + (c > 1 ? b * b : 0) + 2;
-          CANDMC_TRY(tma_ready_operand(&pa, &lda, b, kc, s0, st));
-          CANDMC_TRY(tma_ready_operand(&pb, &ldb, kc, b, s0 + b * kc + (b * kc & 1), st));
-        }
-        fparams.Cin = Cpart;
-        fparams.ldin = ldCpart;
-        CANDMC_TRY(gemm_f64_fused('N', 'N', b, b, kc, 1.0, pa, lda, pb, ldb, t ? 1.0 : 0.0, sC.ptr(), sC.ld(), st, &fparams));
-      } else {
-        CANDMC_TRY(gemm_f64('N', 'N', b, b, kc, 1.0, pa, lda, pb, ldb, t ? 1.0 : 0.0, Cpart, ldCpart, st));
-      }
-    }
-    if (h < nch) {
-      const int64_t w = b / fin_slabs;
-      std::vector<const double*> pa(nch), pb(nch);
-      std::vector<int64_t> lda(nch), ldb(nch);
-      for (int t = h; t < nch; ++t) CANDMC_TRY(operands(t, &pa[t], &lda[t], &pb[t], &ldb[t]));
-      for (int j = 0; j < fin_slabs; ++j) {
-        const int64_t c0 = j * w;
-        for (int t = h; t < nch; ++t)
-          CANDMC_TRY(gemm_f64('N', 'N', b, w, kc, 1.0, pa[t], lda[t], pb[t] + c0 * ldb[t], ldb[t], 1.0, Cpart + c0 * ldCpart,
-                              ldCpart, st));
-        CANDMC_TRY(slab_done(c0, w));
-      }
+    std::vector<int> grp_hi(nch);
+    for (int t = 0; t < nch; ++t) grp_hi[t] = t + 1;
+    if (runtime().merge_panels > 0 && nch > 2) host_upload_groups(nch, fctx ? nch - 1 : nch, &grp_hi);
+    std::vector<int64_t> slab_w;
+    if (slab_mode) slab_w = fin_slab_widths(b, fin_slabs);
+    int last_group_lo = 0;
+    for (int t = 0; t < nch; t = grp_hi[t]) last_group_lo = t;
+    double* scratch = ws + ws_panels + (c > 1 ? b * b : 0) + 2;
+    for (int t = 0; t < nch; t = grp_hi[t]) {
+      const int mg = grp_hi[t] - t;
+      std::vector<const double*> pa(mg), pb(mg);
+      std::vector<int64_t> lda(mg), ldb(mg);
+      for (int u = 0; u < mg; ++u) CANDMC_TRY(operands(t + u, &pa[u], &lda[u], &pb[u], &ldb[u]));
+      const bool fused_here = fctx != nullptr && t + mg == nch;
+      GroupLaunch gl;
+      gl.tA = 'N'; gl.tB = 'N'; gl.b = b; gl.kc = kc; gl.C = Cpart; gl.ldC = ldCpart; gl.compute = st;
+      gl.fused = fused_here ? &fparams : nullptr; gl.fused_out = sC.ptr(); gl.fused_ldout = sC.ld();
+      gl.scratchA = scratch; gl.scratchB = scratch + b * kc + (b * kc & 1);
+      CANDMC_TRY(multiply_group(gl, mg, pa, lda, pb, ldb, t ? 1.0 : 0.0, (!slab_w.empty() && t == last_group_lo) ? &slab_w : nullptr,
+                                slab_done));
     }
   } else {
     SummaArgs a;
@@ -926,7 +1033,8 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   }
   if (slabs_out > 0) {
     // every slab has been summed over the depth and is on its way to the host: nothing left but to wait for the transfers
-    CANDMC_CHECK(slabs_out == fin_slabs, "d25_summa: %d of %d C slabs finalised", slabs_out, fin_slabs);
+    CANDMC_CHECK(slabs_out == (int)fin_slab_widths(b, fin_slabs).size(), "d25_summa: %d C slabs finalised, expected %d", slabs_out,
+                 (int)fin_slab_widths(b, fin_slabs).size());
     CANDMC_TRY(stream_wait(st, d2h));
     CANDMC_TRY(stream_wait(st, runtime().comm_stream));
     CANDMC_CUDA(cudaStreamSynchronize(st));
@@ -953,6 +1061,7 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
 int candmc_bcast_cannon_4d(const candmc_ctb_args_t* args, const double* mat_A, const double* mat_B, double* mat_C,
                            double* buffer, candmc_comm_t* cdt_x1, candmc_comm_t* cdt_y1, candmc_comm_t* cdt_x2,
                            candmc_comm_t* cdt_y2, void* stream) {
+  NvtxRange nvtx_range("bcast_cannon_4d");   // dual_cannon.cxx:40 (the reference opens no timer here)
   CANDMC_TRY(runtime_require());
   g_events.reset();
   CANDMC_CHECK(args && cdt_x1 && cdt_y1 && cdt_x2 && cdt_y2, "bcast_cannon_4d: null argument");
@@ -1230,8 +1339,14 @@ int candmc_spcannon(int bidir, int rank, int kary, int ndim, candmc_comm_t* worl
   // (opt-in) every put of the stagger and the shifts by copy engines into peer windows; the largest message is a whole slice
   if (kary > 1 && k > 0) CANDMC_TRY(p2p_transport_prepare(world, 2 * std::max(mk, nk) / ndim + 2));
   CANDMC_TRY(stream_wait(s.comm, st));
-  if (kary > 1 && k > 0) CANDMC_TRY(spc_stagger(s, 0));
-  CANDMC_TRY(spc_shift(s, bidir, 0, beta));
+  if (kary > 1 && k > 0) {
+    NvtxRange nvtx_range("uni_stagger");   // spcannon.cxx:278,334
+    CANDMC_TRY(spc_stagger(s, 0));
+  }
+  {
+    NvtxRange nvtx_range(bidir ? "bdr_shift" : "uni_shift");   // spcannon.cxx:285,341
+    CANDMC_TRY(spc_shift(s, bidir, 0, beta));
+  }
   CANDMC_TRY(stream_wait(st, s.comm));
   CANDMC_TRY(sC.close_out(st));
   if (sA.staged() || sB.staged() || sC.staged()) CANDMC_CUDA(cudaStreamSynchronize(st));
@@ -1321,6 +1436,7 @@ extern "C" {
 
 int candmc_update_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
                              double* T, const candmc_pview_t* pv, void* stream) {
+  NvtxRange nvtx_range("update_Yamamoto_A");
   CANDMC_TRY(runtime_require());
   g_events.reset();
   CANDMC_CHECK(pv != nullptr && pv->crow != nullptr && pv->ccol != nullptr, "update_Yamamoto_A: null processor view");
@@ -1353,6 +1469,7 @@ int candmc_update_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_
 
 int candmc_upd_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
                           const double* T, candmc_comm_t* ccol, void* stream) {
+  NvtxRange nvtx_range("upd_Yamamoto_A");
   CANDMC_TRY(runtime_require());
   g_events.reset();
   CANDMC_CHECK(mb >= 0 && kb >= 0 && b > 0, "upd_Yamamoto_A: bad extents");
@@ -1367,6 +1484,7 @@ int candmc_upd_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t l
 int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
                     const double* W, const candmc_pview_t* pv, double* aggreg_Y, int64_t lda_aY, int W_is_T,
                     void* stream) {
+  NvtxRange nvtx_range("Bcast_update");
   CANDMC_TRY(runtime_require());
   g_events.reset();
   CANDMC_CHECK(pv != nullptr && pv->crow != nullptr && pv->ccol != nullptr, "update_A: null processor view");
@@ -1437,6 +1555,7 @@ int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, in
 
 int candmc_upd_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
                  const double* T, candmc_comm_t* ccol, void* stream) {
+  NvtxRange nvtx_range("upd_A");
   CANDMC_TRY(runtime_require());
   g_events.reset();
   CANDMC_CHECK(mb >= 0 && kb >= 0 && b > 0, "upd_A: bad extents");

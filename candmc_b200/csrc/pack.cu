@@ -78,7 +78,7 @@ int pack_grid(int64_t work_items) {
 
 template <bool AXPBY>
 int lda_dispatch(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B, double a,
-                 double b, cudaStream_t stream) {
+                 double b, cudaStream_t stream, int max_ctas = 0) {
   CANDMC_TRY(runtime_require());
   CANDMC_CHECK(nrow >= 0 && ncol >= 0, "lda_cpy: negative extent");
   CANDMC_CHECK(lda_A >= nrow && lda_B >= nrow, "lda_cpy: leading dimension smaller than nrow");
@@ -98,7 +98,7 @@ int lda_dispatch(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const
   const int tc = PACK_ITEMS >> tr_log2;
   const int64_t ntiles = tiles_r * ((ncol + tc - 1) / tc);
   int64_t grid = ntiles;
-  const int64_t cap = static_cast<int64_t>(runtime().num_sms) * PACK_CTAS_PER_SM;
+  const int64_t cap = max_ctas > 0 ? max_ctas : static_cast<int64_t>(runtime().num_sms) * PACK_CTAS_PER_SM;
   if (grid > cap) grid = cap;
   if (vec) {
     lda_tile_kernel<AXPBY, double2><<<static_cast<int>(grid), PACK_THREADS, 0, stream>>>(
@@ -278,6 +278,11 @@ frob_diff_kernel(const double* __restrict__ X, int64_t ldx, const double* __rest
 int lda_copy_f64(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B,
                  cudaStream_t stream) {
   return lda_dispatch<false>(nrow, ncol, lda_A, lda_B, A, B, 1.0, 0.0, stream);
+}
+
+int lda_copy_f64_capped(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B,
+                        cudaStream_t stream, int max_ctas) {
+  return lda_dispatch<false>(nrow, ncol, lda_A, lda_B, A, B, 1.0, 0.0, stream, max_ctas);
 }
 
 int lda_axpby_f64(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B, double a,

@@ -239,13 +239,16 @@ int profile_reset() {
 int profile_collect(int64_t* launches, double* total_ms, double* total_flops) {
   CANDMC_CUDA(cudaDeviceSynchronize());
   double ms = 0, fl = 0;
+  int64_t cnt = 0;
   for (ProfRec& r : g_prof) {
+    if (r.flops == 0.0) continue;   // a mark (start of a distributed call), not a launch
     float t = 0;
     CANDMC_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
     ms += t;
     fl += r.flops;
+    ++cnt;
   }
-  *launches = (int64_t)g_prof.size();
+  *launches = cnt;
   *total_ms = ms;
   *total_flops = fl;
   return OK;

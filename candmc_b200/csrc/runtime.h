@@ -5,7 +5,20 @@
 #include <stdint.h>
 #include <stddef.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 namespace candmc {
+
+// NVTX range named after the reference's TAU/CTF_Timer region it stands for (d25_summa_gemm at d25_summa.cxx:122,
+// d2_topo_bcast_gemm at summa.cxx:58, uni_stagger / bdr_shift / uni_shift / DGEMM at spcannon.cxx:116-341, Bcast_update at
+// qr_2d.cxx:167): a profiler timeline of the GPU build lines up with the reference's own timer table.  Header-only NVTX 3;
+// costs nothing when no tool is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct Runtime {
   bool initialized = false;
@@ -27,10 +40,11 @@ struct Runtime {
   unsigned tile_counter_seq = 0;
   bool fused_reduce_grids = false;      // ... also on q x q x c grids (validated so far on 1 x 1 x c only)
   bool skip_unused_uploads = true;      // host operands: a layer's rank uploads only the blocks its panels use (candmc_set_skip_unused_uploads)
-  bool panel_transport = false;         // SUMMA panels by copy engines into peer windows instead of ncclBroadcast (transport.h; opt-in)
+  bool panel_transport = true;          // SUMMA panels and Cannon shifts by copy engines into peer windows instead of NCCL kernels (transport.h)
   bool b_first_chunk_early = false;     // host B: upload the first k-chunk's rows ahead of the rest (opt-in until measured)
   bool early_c_download = true;         // host C: finalise + download column slabs under the last multiplies (candmc_set_early_c_download)
   bool fused_reduce = true;             // depth all-reduce fused into the last GEMM's epilogue over peer memory
+  bool host_gather = true;              // pinned host B blocks: k-chunks gathered straight out of host memory by the pack kernel (candmc_set_host_gather)
   bool transpose_tma = true;            // transpose through TMA loads / stores (candmc_debug_transpose_tma(0): the LDG/STG kernel)
   bool splitk = true;                   // cut small-tile-count GEMMs along k too
   int gemm_tile_n = 0;                  // CTA tile columns of the DMMA GEMM: 0 automatic, 128 (one CTA per SM) or 64 (two per SM); candmc_debug_gemm_tile
@@ -48,7 +62,8 @@ struct Runtime {
                                         // (graduated at n, k >= 8192, else 8 uniform; host_pipeline_cut in mm_algs.cu)
   int64_t host_pipeline_min = 2048;     // smallest n for which host operands on a 1x1 grid are streamed panel-wise
   int64_t min_kchunk = 1024;            // smallest k-chunk the SUMMA pipeline cuts a panel into
-  int merge_panels = 0;                 // SUMMA sweeps: k-chunks multiplied in merged launches — 0 off, 1 last panel, 2 every panel, 3 doubling groups (opt-in until measured)
+  int merge_panels = 2;                 // SUMMA sweeps: k-chunks multiplied in merged launches — 2 (default): as few launches as the data's arrival allows;
+                                        // 0: one launch per chunk; 1 / 3: earlier experiments (last panel only / doubling groups)
 };
 
 Runtime& runtime();
@@ -113,11 +128,19 @@ int gemm_f64_fused(char transa, char transb, int64_t m, int64_t n, int64_t k, do
 bool gemm_f64_bchunked_ok(const double* A, int64_t lda, const double* B, int64_t n, int64_t k, int64_t b_kc);
 int gemm_f64_bchunked(char transa, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                       const double* B, int64_t b_kc, double beta, double* C, int64_t ldc, cudaStream_t stream);
+// The same for the column range [col0, col0 + ncols) of every chunk (chunks are b_kc x chunk_cols): C is the m x ncols block
+// the range belongs to.  What a sweep uses to finish C column slab by column slab in launches that still cover all of k.
+int gemm_f64_bchunked_cols(char transa, int64_t m, int64_t ncols, int64_t k, double alpha, const double* A, int64_t lda,
+                           const double* B, int64_t b_kc, int64_t chunk_cols, int64_t col0, double beta, double* C, int64_t ldc,
+                           cudaStream_t stream);
 int gemm_f64_ex(char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc, cudaStream_t stream,
-                const FusedParams* fused, int64_t b_kc);
+                const FusedParams* fused, int64_t b_kc, int64_t b_cs);
 int lda_copy_f64(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B,
                  cudaStream_t stream);
+// ... with at most max_ctas CTAs (sources that are not HBM: pinned host memory read over PCIe)
+int lda_copy_f64_capped(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B,
+                        cudaStream_t stream, int max_ctas);
 int lda_axpby_f64(int64_t nrow, int64_t ncol, int64_t lda_A, int64_t lda_B, const double* A, double* B, double a,
                   double b, cudaStream_t stream);
 int transpose_f64(int64_t rows, int64_t cols, const double* A, int64_t lda, double* B, int64_t ldb,

@@ -58,6 +58,10 @@ int candmc_set_skip_unused_uploads(int on);
 /* Host C blocks in candmc_d25_summa: 1 (default) = the second half of the last panel's k-chunks is multiplied column slab by
  * column slab, each slab is summed over the depth and downloaded while the next ones multiply; 0 = one download at the end. */
 int candmc_set_early_c_download(int on);
+/* Pinned (page-locked) host B blocks on grids: 1 (default) = every k-chunk is gathered straight out of host memory by the pack
+ * kernel — coalesced reads over PCIe, chunk-major on arrival — so the first multiply starts after 1/8 of the block instead
+ * of after all of it; 0 = one copy of the whole block, re-laid out on the device (also what pageable memory gets). */
+int candmc_set_host_gather(int on);
 /* SUMMA panel chunks (candmc_summa, candmc_d25_summa, the inner level of candmc_bcast_cannon_4d): 1 = the root writes them
  * into the consumers' CUDA-IPC-mapped windows with copy engines (cudaMemcpyAsync over NVLink + a 4-byte flag DMA, consumers
  * wait with cuStreamWaitValue32) — no SM, no NCCL kernel, the GEMM keeps all 148 SMs; 0 (default until measured on B200s) =

@@ -579,7 +579,7 @@ cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* attr, const void* p)
   const Alloc* a = find_alloc(p);
   attr->type = !a ? cudaMemoryTypeUnregistered : (a->device ? cudaMemoryTypeDevice : cudaMemoryTypeHost);
   attr->device = g_device;
-  attr->devicePointer = a && a->device ? const_cast<void*>(p) : nullptr;
+  attr->devicePointer = a ? const_cast<void*>(p) : nullptr;   // pinned host memory is addressable from the device (UVA)
   attr->hostPointer = a && a->device ? nullptr : const_cast<void*>(p);
   return cudaSuccess;
 }

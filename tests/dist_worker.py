@@ -91,7 +91,14 @@ def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_go
     B[:b] = orc.unit_block(b, b, row0, col0, n, 1)
     args = cb.ctb_args_t(n=n, lda_A=ld, lda_B=ld, lda_C=b, buffer_size=5 * b * b * 8)
     fn = cb.d25_summa_ovp if ovp else cb.d25_summa
-    if use_host:
+    if use_host == "pinned":
+        # page-locked host blocks (what bench.py's end-to-end leg passes): B's k-chunks are gathered straight out of host
+        # memory by the pack kernel, C leaves slab by slab
+        hA = torch.from_numpy(np.ascontiguousarray(A.T)).pin_memory(); hB = torch.from_numpy(np.ascontiguousarray(B.T)).pin_memory()
+        hC = torch.full((b * b,), float("nan"), dtype=torch.float64).pin_memory()
+        fn(args, hA, hB, hC, None, g["cdt_row"], g["cdt_col"], g["cdt_kdir"])
+        got = hC.numpy().reshape(b, b).T.copy()
+    elif use_host:
         Ch = np.full((b, b), np.nan, order="F")
         fn(args, A, B, Ch, None, g["cdt_row"], g["cdt_col"], g["cdt_kdir"])
         got = Ch
@@ -667,6 +674,9 @@ def main():
             n_host = 512 if os.environ.get("CANDMC_CPUSIM") == "1" else 4096   # plain-loop GEMM in the simulator
             case_d25(world, golden, f"d25_ksplit_host_n{n_host}_{tag}", n_host, 2, 0, use_host=True, check_golden=False, oracle=False)
             case_d25(world, golden, f"d25_ksplit_host_n96_{tag}", 96, 2, 0, use_host=True, lda_pad=2)
+            case_d25(world, golden, f"d25_ksplit_pinned_n{n_host}_{tag}", n_host, 2, 0, use_host="pinned", check_golden=False, oracle=False)
+            case_d25(world, golden, f"d25_ksplit_pinned_n512_{tag}", 512, 2, 0, use_host="pinned", check_golden=False)
+            case_d25(world, golden, f"d25_ksplit_pinned_n1024_pad_{tag}", 1024, 2, 1, use_host="pinned", lda_pad=2, check_golden=False)
         if P == 4:
             case_d25(world, golden, "d25_n96_q2_c1_ovp0", 96, 1, 0)
             case_d25(world, golden, "d25_n96_q2_c1_ovp1", 96, 1, 1)
@@ -674,6 +684,9 @@ def main():
             case_d25(world, golden, "d25_n96_q2_c1_ovp0", 96, 1, 0, use_host=True)
             case_d25(world, golden, f"d25_n512_{tag}", 512, 1, 0)
             case_d25(world, golden, f"d25_n512_host_{tag}", 512, 1, 0, use_host=True, lda_pad=2)   # chunk-wise upload when kc8
+            case_d25(world, golden, f"d25_n512_pinned_{tag}", 512, 1, 0, use_host="pinned", check_golden=False)
+            case_d25(world, golden, f"d25_n2048_pinned_pad_{tag}", 2048, 1, 1, use_host="pinned", lda_pad=2, check_golden=False,
+                     oracle=os.environ.get("CANDMC_CPUSIM") == "1")
             case_summa(world, golden, "summa_n64_q2", 64)
             case_summa(world, golden, "summa_n64_q2", 64, lda_pad=4)
             case_summa(world, golden, f"summa_n96_TN_{tag}", 96, trans=("T", "N"))
@@ -698,6 +711,8 @@ def main():
             case_d25(world, golden, f"d25_n512_c2_{tag}", 512, 2, 0)            # b = 256: fused depth sum
             case_d25(world, golden, f"d25_n1024_c2_fused_{tag}", 1024, 2, 1)
             case_d25(world, golden, f"d25_n1024_c2_host_{tag}", 1024, 2, 0, use_host=True)
+            case_d25(world, golden, f"d25_n1024_c2_pinned_{tag}", 1024, 2, 0, use_host="pinned", check_golden=False)
+            case_d25(world, golden, f"d25_n2048_c2_pinned_pad_{tag}", 2048, 2, 1, use_host="pinned", lda_pad=2, check_golden=False)
             case_d25(world, golden, f"d25_n512_c2_fused_pad_{tag}", 512, 2, 0, lda_pad=1)
     cb.set_min_kchunk(1024)
     big = int(os.environ.get("CANDMC_TEST_BIG_N", "0"))

@@ -288,7 +288,7 @@ def test_bench_script_logic_on_the_simulator(nproc):
     b = d["config"]["block"]
     # two end-to-end passes: the host-operand settings B200s have run, then the library's defaults; `e2e` is one of them
     first, second = d["e2e_passes"]
-    assert (first["host_operand_settings"], second["host_operand_settings"]) == ("gpu_validated", "library_defaults")
+    assert (first["host_operand_settings"], second["host_operand_settings"]) == ("round1_settings", "library_defaults")
     assert d["e2e"] in (first, second)
     for p_ in (first, second):
         assert p_["valid"] and p_["rel_frobenius_vs_device_path"] <= d["tolerance_10_n_eps"]
@@ -305,7 +305,7 @@ def test_bench_watchdog_keeps_the_line_when_the_second_pass_does_not_return():
     lines = [line for line in so.splitlines() if line.startswith('{"metric"')]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d["e2e"]["valid"] and d["e2e"]["host_operand_settings"] == "gpu_validated" and d["value"] > 0
+    assert d["e2e"]["valid"] and d["e2e"]["host_operand_settings"] == "round1_settings" and d["value"] > 0
     assert "watchdog" in d["e2e_passes"][1]["error"]
 
 

@@ -86,6 +86,8 @@ def knob_env(knobs):
     if "--panel-transport" in knobs:
         env["CANDMC_PANEL_TRANSPORT"] = "1"
         env["CANDMC_TEST_PANEL_TRANSPORT"] = "1"
+    if "--no-panel-transport" in knobs:
+        env["CANDMC_PANEL_TRANSPORT"] = "0"
     if "--fused-reduce" in knobs:
         env["CANDMC_FUSED_REDUCE"] = knobs[knobs.index("--fused-reduce") + 1]
         if env["CANDMC_FUSED_REDUCE"] == "2":
@@ -101,10 +103,13 @@ def main():
     summary = {"n_gpus": NG}
     best_knobs = []
     if want("bench"):
-        cands = [[], ["--merge-panels", "2"], ["--panel-transport"], ["--merge-panels", "2", "--panel-transport"],
-                 ["--merge-panels", "2", "--bg-ctas", "0"]]
+        # the library defaults (merged launches + copy-engine panels since the first 4-GPU session of this round) and what is
+        # still opt-in: the fused depth sum on q x q x c grids; the round-1 schedule once for the record
+        cands = [[]]
         if NG == 8:
-            cands += [["--merge-panels", "2", "--fused-reduce", "2"], ["--merge-panels", "2", "--panel-transport", "--fused-reduce", "2"]]
+            cands += [["--fused-reduce", "2"]]
+        if os.environ.get("R02_WITH_ROUND1"):
+            cands += [["--merge-panels", "0", "--no-panel-transport"]]
         best = None
         for kn in cands:
             tag = f"r02_bench{NG}_" + ("default" if not kn else "_".join(x.strip("-").replace("-", "") for x in kn))
@@ -141,7 +146,7 @@ def main():
         summary["dropin"] = {"rc": rc, "tail": txt.strip().splitlines()[-1:] if txt.strip() else []}
         print("   ", json.dumps(summary["dropin"]), flush=True)
     if want("e2e"):
-        rc, txt = run(f"r02_bench{NG}_e2e", ["bench.py", "--gpus", str(NG), "--steps", "4", "--warmup", "3", "--single-e2e-pass"] + best_knobs, timeout=400)
+        rc, txt = run(f"r02_bench{NG}_e2e", ["bench.py", "--gpus", str(NG), "--steps", "4", "--warmup", "3", "--timeline"] + best_knobs, timeout=500)
         line = last_json(txt)
         summary["e2e"] = {"rc": rc, "value": line and line["value"], "e2e": line and line.get("e2e"),
                           "passes": line and [(p.get("host_operand_settings"), p.get("value"), p.get("valid")) for p in line.get("e2e_passes", [])]}

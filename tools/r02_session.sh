@@ -69,6 +69,10 @@ for section in "$@"; do
         grep -E "==|Gigaflops|elapsed|failed|rror" $O/r02_lu_bench.log | head -20
       fi
       ;;
+    tile)
+      # A/B of the two CTA shapes of the DMMA GEMM (128 x 128 tiles, one CTA per SM / 128 x 64 tiles, two per SM)
+      timeout 600 tools/gemm_probe tile > $O/r02_gemm_probe_tile.jsonl 2>&1; cut -c1-200 $O/r02_gemm_probe_tile.jsonl
+      ;;
     pack)
       # the rewritten pack kernels: bit-exact tests first, then GB/s, then one ncu --set full pass over every pack kernel
       timeout 600 python -m pytest tests/test_local_gpu.py -m gpu -x -q -p no:cacheprovider 2>&1 | tail -3

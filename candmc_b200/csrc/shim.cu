@@ -293,6 +293,10 @@ int MPI_Bcast(void* buf, int count, MPI_Datatype type, int root, MPI_Comm comm) 
   if (bytes == 0 || comm->size == 1) return MPI_SUCCESS;
   cudaStream_t st = runtime().comm_stream;
   if (is_device_ptr(buf)) {
+    // MPI semantics: the buffer is complete when the call is made.  A device buffer may still be being written by an earlier
+    // asynchronous call on some other stream (this library's entry points are asynchronous for device operands), and the
+    // broadcast runs on the library's own stream: drain the device first.
+    cuda_ok(cudaDeviceSynchronize(), "sync before a broadcast of a device buffer");
     nccl_ok(ncclBroadcast(buf, buf, bytes, ncclChar, root, comm->nccl, st), "ncclBroadcast");
     cuda_ok(cudaStreamSynchronize(st), "sync");
     return MPI_SUCCESS;

@@ -1,6 +1,8 @@
 // candmc_b200 — SUMMA panel transport over peer memory with copy engines only (see transport.h).
 #include "transport.h"
 
+#include <algorithm>
+
 #include <cuda.h>
 
 #include "../../include/candmc_b200.h"
@@ -66,10 +68,13 @@ int panel_transport_get(candmc_comm* c, int64_t half_elems, PanelTransport** out
   *out = nullptr;
   if (c == nullptr || c->size < 2 || c->size > kMaxPeers || c->transport_failed) return OK;
   PanelTransport* t = static_cast<PanelTransport*>(c->transport);
-  if (t != nullptr && t->half_elems >= half_elems) {
+  // (a transport whose call counter is about to run out of the flag-value table is rebuilt like one that has to grow: every
+  // rank counts the same calls, so every rank gets here in the same call)
+  if (t != nullptr && t->half_elems >= half_elems && t->call + 8 < kPanelMaxCalls) {
     *out = t;
     return OK;
   }
+  if (t != nullptr && t->half_elems > half_elems) half_elems = t->half_elems;
   if (ensure_globals() != OK) {   // same outcome on every rank of a node (one driver)
     c->transport_failed = true;
     return OK;
@@ -162,7 +167,11 @@ void panel_transport_destroy(PanelTransport* t) {
 int p2p_transport_prepare(candmc_comm* c, int64_t slot_elems) {
   if (c == nullptr || !runtime().panel_transport || c->size < 2 || c->size > kMaxPeers || c->transport_failed) return OK;
   P2PTransport* t = static_cast<P2PTransport*>(c->p2p);
-  if (t != nullptr && t->slot_elems >= slot_elems) return OK;
+  uint32_t max_seq = 0;   // the message counters of the busiest pair; symmetric exchanges keep them equal on every rank
+  if (t != nullptr)
+    for (int p = 0; p < kMaxPeers; ++p) max_seq = std::max(max_seq, std::max(t->send_seq[p], t->recv_seq[p]));
+  if (t != nullptr && t->slot_elems >= slot_elems && max_seq + 4096 < kPanelMaxCalls) return OK;
+  if (t != nullptr && t->slot_elems > slot_elems) slot_elems = t->slot_elems;
   if (ensure_globals() != OK) {
     c->transport_failed = true;
     return OK;

@@ -638,6 +638,9 @@ def main():
     world = cb.init_world(rank, world_size, local)
     if os.environ.get("CANDMC_TEST_FUSED_GRIDS") == "1":   # the fused depth sum on q x q x c grids too (opt-in in the product)
         cb.lib().candmc_set_fused_reduce(2)
+    if os.environ.get("CANDMC_TEST_NCCL_PANELS") == "1":   # round 1's data path: panels and shifts by NCCL kernels, one launch per k-chunk
+        cb.lib().candmc_set_panel_transport(0)
+        cb.lib().candmc_set_merge_panels(0)
     if os.environ.get("CANDMC_TEST_PANEL_TRANSPORT") == "1":   # SUMMA panels by copy engines into peer windows (opt-in in the product)
         cb.lib().candmc_set_panel_transport(1)
     if os.environ.get("CANDMC_TEST_MERGE_PANELS", "0") != "0":   # k-chunks of a panel in merged launches: 1 last panel, 2 every panel (opt-in in the product)

@@ -55,8 +55,10 @@ for _n in DIST_MAIN:     # longest first.  On 8 ranks the fused GEMM + depth all
     # the product until a B200 has seen it): the kernel's peer-memory epilogue and ipc.cu run for real, over simulated CUDA IPC
     _job(f"main{_n}", _torchrun(_n, 29700 + _n, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0",
          CANDMC_TEST_FUSED_GRIDS="1" if _n == 8 else "0")
-# opt-in data paths over peer memory, never seen by a B200: SUMMA panels by copy engines (transport.h) on 2x2 and, together
-# with the fused depth sum, on 2x2x2 — deferred streams, LIFO order
+# the default data path since round 2 (SUMMA panels by copy engines, transport.h) named explicitly on 2x2 and, together with the
+# opt-in fused depth sum, on 2x2x2 — deferred streams, LIFO order; and round 1's path (NCCL kernels, one launch per k-chunk)
+_job("nccl4", _torchrun(4, 29747, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_NCCL_PANELS="1",
+     CPUSIM_SCHED="lifo")
 _job("transport4", _torchrun(4, 29741, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_PANEL_TRANSPORT="1",
      CPUSIM_SCHED="lifo")
 _job("transport8", _torchrun(8, 29742, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_PANEL_TRANSPORT="1",
@@ -316,6 +318,13 @@ def test_copy_engine_panel_transport_on_the_simulator(nproc):
     halves reused, windows regrown), no ncclBroadcast left on the path"""
     out = _dist(f"transport{nproc}")
     assert out["panel_transport_sends_rank0"] > 50
+
+
+def test_nccl_panels_and_per_chunk_launches_on_the_simulator():
+    """round 1's data path, still selectable (candmc_set_panel_transport(0), candmc_set_merge_panels(0)) and the automatic
+    fallback when peer windows are unavailable: ncclBroadcast panels on the capped communicators, one launch per k-chunk"""
+    out = _dist("nccl4")
+    assert out["panel_transport_sends_rank0"] == 0 and out["merged_panel_launches_all_ranks"] == [0, 0]
 
 
 @pytest.mark.parametrize("job", ["merge4", "merge4_all", "merge4_doubling", "merge8_all"])

@@ -3,7 +3,7 @@ candmc_set_merge_last_panel).
 
 STATUS: written after the round's GPU budget was spent — every case passes on the CPU simulator's PTX emulation
 (tests/test_cpusim.py), never run on a B200.  Same policy as the other tests/test_zz_*.py: own process group with a timeout,
-xfail(strict=False) until a round has seen it pass.
+plain tests since round 2 (they passed on the driver's B200 in round 1 and again in round 2's sessions).
 """
 import json
 import os
@@ -15,11 +15,9 @@ from pending_util import run_guarded
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-PENDING = pytest.mark.xfail(strict=False, reason="chunk-major B launch: first B200 run pending (written after the GPU budget was spent)")
 
 
 @pytest.mark.gpu
-@PENDING
 def test_chunk_major_b_launch_equals_plain_launch():
     """whole and ragged tiles, one to eight chunks, both layouts of A, up to the merged launch of a b = 8192 panel (K = 7168 in
     1024-deep chunks): bit for bit the plain-layout launch of the same kernel and within 10 k eps of a float64 numpy product"""

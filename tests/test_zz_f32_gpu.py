@@ -2,7 +2,7 @@
 
 STATUS: written after the round's GPU budget was spent — compiled for sm_100a (SASS shows UTCHMMA / UTMALDG / LDTM / UTCBAR),
 every case passes on the CPU simulator's tcgen05 emulation (tests/test_cpusim.py), never run on a B200.  Same policy as the
-other tests/test_zz_*.py: own process group with a timeout, xfail(strict=False) until a round has seen it pass.
+other tests/test_zz_*.py: own process group with a timeout, plain tests since round 2 (they passed on the driver's B200 in round 1 and again in round 2's sessions).
 """
 import json
 import os
@@ -14,11 +14,9 @@ from pending_util import run_guarded
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-PENDING = pytest.mark.xfail(strict=False, reason="FP32 tcgen05 GEMM: first B200 run pending (written after the GPU budget was spent)")
 
 
 @pytest.mark.gpu
-@PENDING
 def test_sgemm_against_float64_product():
     """all transpose combinations, ragged m / n / k, padded and misaligned operands, alpha / beta, both precision modes, up to
     4096^3: relative to the size of the summed terms the 3xTF32 result stays within 4 * 2^-20, the single-TF32 one within 2^-9"""

@@ -1,10 +1,8 @@
 """GPU tests of the LU accelerator seam (candmc_off_* / candmc_b200.lu_offload / libcandmc_lu_offload.so).
 
-STATUS: this path was written after the round's GPU budget was spent; it has been compiled for sm_100a and its checker is
-pinned to the reference (tests/test_lu_offload_oracle.py), but these tests have not yet run on a B200.  They are therefore
-marked xfail(strict=False) — they report XPASS when the path is right, never mask a failure of the validated suite, and run
-every case in its own process (a CUDA fault cannot poison the session).  The marker goes away once a round has seen them
-pass.  The file name sorts last on purpose.
+STATUS: the checker is pinned to the reference (tests/test_lu_offload_oracle.py); the tests first ran on a B200 in round 1's
+driver session and again in round 2 (profiles/r02_session1_1gpu_stdout.log): green, so they are plain tests now.  Every case
+still runs in its own process (a CUDA fault cannot poison the session).  The file name sorts last on purpose.
 """
 import json
 import os
@@ -19,7 +17,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 GOLD = np.load(os.path.join(HERE, "golden", "lu_offload_ref_outputs.npz"))
 NAMES = sorted(k[: -len("__script")] for k in GOLD.files if k.endswith("__script"))
-PENDING = pytest.mark.xfail(strict=False, reason="LU offload seam: first B200 run pending (written after the GPU budget was spent)")
 
 
 def _worker(*args, timeout=150):
@@ -29,7 +26,6 @@ def _worker(*args, timeout=150):
 
 
 @pytest.mark.gpu
-@PENDING
 @pytest.mark.parametrize("overlap", [0, 1])
 @pytest.mark.parametrize("name", NAMES)
 def test_script_parity_with_reference_outputs(name, overlap):
@@ -45,7 +41,6 @@ def test_script_parity_with_reference_outputs(name, overlap):
 
 
 @pytest.mark.gpu
-@PENDING
 @pytest.mark.parametrize("n,k,overlap", [(1024, 128, 1), (4096, 256, 1), (4096, 256, 0), (2050, 130, 1)])
 def test_trailing_update_pattern_at_size(n, k, overlap):
     """LU step at a size the oracle cannot do in seconds: numpy float64 is the checker, bound 10*k*eps (rel. Frobenius)"""
@@ -69,7 +64,6 @@ def _lu_dropin(exe, *args):
 
 
 @pytest.mark.gpu
-@PENDING
 @pytest.mark.parametrize("exe", ["lu_pp_gpu", "lu_tp_gpu"])
 @pytest.mark.parametrize("args", [["-n", "256", "-b_sm", "8", "-b_lrg", "32"], ["-n", "1024", "-b_sm", "32", "-b_lrg", "128"]])
 def test_reference_lu_unit_test_passes_with_gpu_offload(exe, args):

@@ -1,9 +1,8 @@
 """GPU tests of the block-cyclic <-> blocked redistribution (candmc_redistribute) and of the Yamamoto form
 of the CAQR trailing update (N1, candmc_update_Yamamoto_A).
 
-STATUS: written after the round's GPU budget was spent — compiled for sm_100a, index plan and two-exchange algorithm verified
-on the CPU (tests/test_redist.py), never run on a B200.  Same policy as tests/test_zz_lu_offload_gpu.py: every case in its
-own process, xfail(strict=False) until a round has seen it pass.
+STATUS: first run on B200s in round 1's driver session (1 GPU) and in round 2's 1- and 4-GPU sessions (profiles/r02_*): green.
+Every case still runs in its own process group with a timeout (pending_util.run_guarded), so a hang costs minutes.
 """
 import json
 import os
@@ -15,7 +14,6 @@ from pending_util import run_guarded
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-PENDING = pytest.mark.xfail(strict=False, reason="redistribution: first B200 run pending (written after the GPU budget was spent)")
 
 
 def _ngpu():
@@ -28,7 +26,6 @@ def _ngpu():
 
 
 @pytest.mark.gpu
-@PENDING
 @pytest.mark.parametrize("case", [(24, 36, 2, 2, 3, 0, 0), (36, 24, 3, 3, 2, 1, 1), (30, 30, 5, 3, 3, 0, 2),
                                   (16, 16, 4, 1, 4, 0, 3), (2048, 1024, 64, 2, 2, 1, 0), (8192, 8192, 128, 2, 2, 0, 0)])
 def test_kernels_play_every_rank_on_one_gpu(case):
@@ -41,7 +38,6 @@ def test_kernels_play_every_rank_on_one_gpu(case):
 
 
 @pytest.mark.gpu
-@PENDING
 @pytest.mark.parametrize("nproc", [1, 2, 4, 8])
 def test_pending_distributed_cases(nproc):
     """tests/dist_worker.py's pending group: candmc_redistribute over NCCL (every grid shape the world size allows) and
@@ -61,15 +57,14 @@ def test_pending_distributed_cases(nproc):
 
 
 @pytest.mark.gpu
-@PENDING
 @pytest.mark.parametrize("nproc", [2, 4, 8])
-def test_pending_peer_memory_paths(nproc):
-    """the validated distributed suite once more with the opt-in peer-memory data paths switched on: SUMMA panels and Cannon
-    shifts by copy engines into CUDA-IPC windows (transport.cu), and on 8 GPUs the fused GEMM + depth all-reduce on the
-    2x2x2 grid.  Both pass on the CPU simulator; this is their first contact with hardware."""
+def test_nccl_panel_paths_and_fused_grid_sum(nproc):
+    """the validated distributed suite once more with the data paths that are NOT the default: SUMMA panels and Cannon shifts by
+    NCCL kernels on the CTA-capped communicators (round 1's default; since round 2 panels travel by copy engines into CUDA-IPC
+    windows, transport.cu), and on 8 GPUs the fused GEMM + depth all-reduce on the 2x2x2 grid (opt-in)."""
     if _ngpu() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
-    env = dict(os.environ, CANDMC_TEST_PANEL_TRANSPORT="1", CANDMC_TEST_FUSED_GRIDS="1" if nproc == 8 else "0")
+    env = dict(os.environ, CANDMC_TEST_NCCL_PANELS="1", CANDMC_TEST_FUSED_GRIDS="1" if nproc == 8 else "0")
     env.setdefault("NCCL_DEBUG", "WARN")
     worker = os.path.join(HERE, "dist_worker.py")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
@@ -78,5 +73,4 @@ def test_pending_peer_memory_paths(nproc):
     assert rc == 0, so[-3000:] + se[-3000:]
     out = json.loads([l for l in so.splitlines() if l.startswith("{")][-1])
     assert out["failed_all_ranks"] == 0 and out["checks_rank0"] > 0
-    if nproc >= 4:
-        assert out["panel_transport_sends_rank0"] > 0, "the transport fell back to NCCL (peer windows or stream memory operations unavailable)"
+    assert out["panel_transport_sends_rank0"] == 0

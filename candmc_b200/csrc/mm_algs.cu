@@ -663,7 +663,7 @@ trsm_llnn_kernel(int b, int kb, const double* __restrict__ T, int64_t ldt, doubl
   for (int e = tid; e < b * nc; e += nt) W[(e % b) + static_cast<int64_t>(c0 + e / b) * ldw] = sw[e];
 }
 
-// Variant with one WARP per right-hand side (opt-in, candmc_set_trsm_variant(1); not measured yet).  The kernel above meets at
+// Variant with one WARP per right-hand side (the default since round 2; candmc_set_trsm_variant(0) selects the kernel above).  The kernel above meets at
 // a block barrier twice per row of T (1024 barriers for b = 512); here a column never leaves its warp: lane r of warp w owns
 // row i0 + r of column c0 + w of the current 32-row block, the part of the solution that is already final is applied
 // left-looking from shared memory (T streamed through a 32 x 128 tile that the eight warps of the CTA share), and the
@@ -712,7 +712,7 @@ trsm_llnn_warp_kernel(int b, int kb, const double* __restrict__ T, int64_t ldt, 
     for (int r = lane; r < b; r += 32) wcol[r] = x[r];
 }
 
-int g_trsm_variant = 0;
+int g_trsm_variant = 1;   // one warp per right-hand side: 125.4 against 121.7 TFLOP/s on config 5 (4 x B200, profiles/r02_4gpu_b/), results checked
 
 int trsm_llnn(int64_t b, int64_t kb, const double* T, int64_t ldt, double* W, int64_t ldw, cudaStream_t st) {
   if (b <= 0 || kb <= 0) return OK;

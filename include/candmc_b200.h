@@ -214,8 +214,9 @@ int candmc_spcannon(int bidir, int rank, int kary, int ndim, candmc_comm_t* worl
  * extents), all device pointers.  ccol may be NULL (single process column). */
 int candmc_upd_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
                  const double* T, candmc_comm_t* ccol, void* stream);
-/* Tuning (opt-in, not measured yet): the triangular solve inside upd_A / update_A — 0 = the kernel B200s have run (a block
- * barrier per row of T), 1 = one warp per right-hand side (shuffles inside 32-row blocks, two block barriers per T tile). */
+/* Tuning: the triangular solve inside upd_A / update_A — 1 (default since round 2: 8.77 against 9.04 ms for BASELINE config 5
+ * on 4 B200s) = one warp per right-hand side (shuffles inside 32-row blocks, two block barriers per T tile), 0 = a block
+ * barrier per row of T. */
 int candmc_set_trsm_variant(int variant);
 /* Processor-grid view of the CAQR drivers: mirror of `pview` (alg/shared/comm.h:66-84; the diagonal communicator is not
  * used on this path).  crow: ranks of my grid row (rank = my column); ccol: ranks of my grid column (rank = my row). */

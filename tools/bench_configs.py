@@ -58,6 +58,29 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def timeline(name, fn):
+        """`--timeline`: one more call with every DMMA launch bracketed by events — rank 0's launches with the gaps in front of
+        them (a shift or a panel that was not hidden under the previous multiply shows up as a gap)"""
+        if "--timeline" not in sys.argv:
+            return
+        import ctypes as C
+        torch.cuda.synchronize()
+        if ws > 1:
+            dist.barrier()
+        cb.lib().candmc_profile_enable(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        cap = 512
+        ts, te, cnt = (C.c_double * cap)(), (C.c_double * cap)(), C.c_int64()
+        cb.lib().candmc_profile_gemm_timeline(ts, te, cap, C.byref(cnt))
+        cb.lib().candmc_profile_enable(0)
+        if rank == 0:
+            busy = sum(te[i] - ts[i] for i in range(cnt.value))
+            sys.stderr.write(f"timeline {name}: call {e0.elapsed_time(e1):.3f} ms, {cnt.value} DMMA launches busy {busy:.3f} ms; idx start end dur gap_before\n")
+            for i in range(cnt.value):
+                sys.stderr.write(f"  {i:3d} {ts[i]:9.3f} {te[i]:9.3f} {te[i] - ts[i]:8.3f} {(ts[i] - te[i - 1]) if i else 0.0:8.3f}\n")
+
     def report(name, flops, ms, extra=None):
         if rank == 0:
             tf = flops / (ms * 1e-3) / 1e12
@@ -100,6 +123,7 @@ def main():
         ms = timed(lambda: cb.summa(args, A, B, Cm, None, g["cdt_row"], g["cdt_col"]))
         chk = check_block(Cm, b, gen(b, n, g["row"] * b, 0, n, 0) @ gen(n, b, 0, g["col"] * b, n, 1), n)
         report("config2: summa n=16384 2x2", 2.0 * n ** 3, ms, chk)
+        timeline("config2 summa", lambda: cb.summa(args, A, B, Cm, None, g["cdt_row"], g["cdt_col"]))
         del A, B, Cm
         # ---- config 4a: bcast_cannon_4d as pure Cannon, n = 24576 ----
         n = sz(24576); d = cb.dcn_grid(world, 2); b = n // 2
@@ -109,6 +133,7 @@ def main():
         row0, col0 = (d["y1"] * 2 + d["y2"]) * b, (d["x1"] * 2 + d["x2"]) * b
         chk = check_block(Cm, b, gen(b, n, row0, 0, n, 0) @ gen(n, b, 0, col0, n, 1), n)
         report("config4: bcast_cannon_4d (Cannon level) n=24576 2x2", 2.0 * n ** 3, ms, chk)
+        timeline("config4 bcast_cannon_4d", lambda: cb.bcast_cannon_4d(args, A, B, Cm, None, d["cdt_x1"], d["cdt_y1"], d["cdt_x2"], d["cdt_y2"]))
         # ---- config 4b: split-dim Cannon kput, 12288^3 blocks ----
         px, py = rank % 2, rank // 2   # block column / block row of A, B and C alike (test/MM/test_spc.cxx:78-102)
         cb.fill_drand48(A, b, b, b, py * b, px * b, n, 0); cb.fill_drand48(B, b, b, b, py * b, px * b, n, 1)
@@ -118,6 +143,7 @@ def main():
         ref = sum(gen(b, b, py * b, kk * b, n, 0) @ gen(b, b, kk * b, px * b, n, 1).T for kk in range(2))
         chk = check_block(Cm, b, ref, n)
         report("config4: kput_cannon 2-ary 2-cube, 12288^3 blocks", 2.0 * n ** 3, ms, chk)
+        timeline("config4 kput_cannon", lambda: cb.kput_cannon(rank, 2, 2, world, b, b, b, "N", 1.0, A, "T", 0.0, B, Cm))
         del A, B, Cm
     # ---- config 5: CAQR trailing update ----
     m, ncol, k = sz(65536), sz(8192), sz(512)
@@ -146,15 +172,16 @@ def main():
         return {"rel_frobenius_vs_cublas_crosscheck": err, "tolerance_10_k_eps": tol, "check_passed": bool(err <= tol)}
 
     chk5 = check_upd()
+    timeline("config5 upd_A", lambda: cb.upd_A(Y, mb, Am, mb, mb, kb, k, T, ccol))
     report(f"config5: upd_A m=65536 n=8192 k=512 on {nprow}x{npcol}", 2 * 2.0 * m * ncol * k, ms,
            dict(chk5, note="flops = the two GEMMs (SURVEY §8d); all-reduce of W and the triangular solve are inside the time"))
-    # the same with the opt-in triangular solve (one warp per right-hand side instead of a block barrier per row of T)
-    cb.lib().candmc_set_trsm_variant(1)
+    # the same with round 1's triangular solve (a block barrier per row of T instead of one warp per right-hand side)
+    cb.lib().candmc_set_trsm_variant(0)
     ms = timed(lambda: cb.upd_A(Y, mb, Am, mb, mb, kb, k, T, ccol))
     chk5 = check_upd()
-    cb.lib().candmc_set_trsm_variant(0)
-    report(f"config5: upd_A m=65536 n=8192 k=512 on {nprow}x{npcol}, trsm variant 1", 2 * 2.0 * m * ncol * k, ms,
-           dict(chk5, note="candmc_set_trsm_variant(1), opt-in"))
+    cb.lib().candmc_set_trsm_variant(1)
+    report(f"config5: upd_A m=65536 n=8192 k=512 on {nprow}x{npcol}, trsm variant 0", 2 * 2.0 * m * ncol * k, ms,
+           dict(chk5, note="candmc_set_trsm_variant(0): round 1's kernel"))
     # 1-GPU local GEMM roofline at the Cannon block size (config 4, second half)
     if ws == 1:
         for n in (sz(12288), sz(16384)):

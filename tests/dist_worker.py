@@ -679,6 +679,8 @@ def main():
             case_d25(world, golden, f"d25_ksplit_host_n96_{tag}", 96, 2, 0, use_host=True, lda_pad=2)
             case_d25(world, golden, f"d25_ksplit_pinned_n{n_host}_{tag}", n_host, 2, 0, use_host="pinned", check_golden=False, oracle=False)
             case_d25(world, golden, f"d25_ksplit_pinned_n512_{tag}", 512, 2, 0, use_host="pinned", check_golden=False)
+            # b = 2048, k-slice 1024 in four 256-deep chunks: launch groups [0], [1, 2], [3], the last one in graduated column slabs
+            case_d25(world, golden, f"d25_ksplit_pinned_n2048_{tag}", 2048, 2, 0, use_host="pinned", check_golden=False, oracle=False)
             case_d25(world, golden, f"d25_ksplit_pinned_n1024_pad_{tag}", 1024, 2, 1, use_host="pinned", lda_pad=2, check_golden=False)
         if P == 4:
             case_d25(world, golden, "d25_n96_q2_c1_ovp0", 96, 1, 0)

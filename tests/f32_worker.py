@@ -25,7 +25,7 @@ import candmc_b200 as cb  # noqa: E402
 from candmc_b200._lib import lib, check  # noqa: E402
 
 check(lib().candmc_init(0))
-if "--one" in sys.argv:   # a single large launch for a profiler (tools/gpu_session.sh f32): no checks, no output worth reading
+if "--one" in sys.argv:   # a single large launch for a profiler (tools/r02_session.sh f32): no checks, no output worth reading
     nb = int(sys.argv[sys.argv.index("--one") + 1])
     x = torch.rand(nb * nb, dtype=torch.float32, device="cuda") - 0.5
     z = torch.empty(nb * nb, dtype=torch.float32, device="cuda")
@@ -116,7 +116,7 @@ if "--fuzz" in sys.argv:
             float(frng.choice([0.0, 1.0, -1.5])), pad=int(frng.randint(0, 4)), mode=int(frng.choice([3, 3, 1])),
             seed=int(frng.randint(1000)), offset=int(frng.randint(0, 2)))
 speed = None
-if not SIM and "--bench" in sys.argv:   # first numbers for the next GPU session (tools/gpu_session.sh f32): device events, 5 launches
+if not SIM and "--bench" in sys.argv:   # first numbers for the next GPU session (tools/r02_session.sh f32): device events, 5 launches
     speed = {}
     for nb in (4096, 8192, 16384):
         x = torch.rand(nb * nb, dtype=torch.float32, device="cuda") - 0.5

@@ -48,15 +48,17 @@ int candmc_device_sm_count(int* out);
 unsigned long long candmc_launch_count(void);
 /* Depth sum of the replicated-grid multiplies: 1 (default) fuses the all-reduce over the depth communicator into the
  * epilogue of the last GEMM on 1 x 1 x c grids — partial tiles travel as P2P stores over NVLink into CUDA-IPC-mapped
- * windows of the other depth ranks while the GEMM is still running; 2 also on q x q x c grids (implemented, parity-tested
- * on 2 GPUs only so far, hence opt-in); 0 uses ncclAllReduce after the GEMM (also the automatic fallback when IPC is
+ * windows of the other depth ranks while the GEMM is still running; 2 also on q x q x c grids (parity-green on 8 B200s, but
+ * measured slower there than the NCCL all-reduce it replaces — 277.4 against 280.9 TFLOP/s on 2x2x2, DESIGN.md 4 — hence
+ * opt-in); 0 uses ncclAllReduce after the GEMM (also the automatic fallback when IPC is
  * unavailable or the block is not a multiple of 128*c).  Must be the same on all ranks. */
 int candmc_set_fused_reduce(int on);
 /* Host operands on q x q x c grids: 1 (default) skips the upload of an A (B) block whose grid column (row) is not one of the
  * layer's panels — the multiply never reads it there; 0 uploads both blocks on every rank. */
 int candmc_set_skip_unused_uploads(int on);
-/* Host C blocks in candmc_d25_summa: 1 (default) = the second half of the last panel's k-chunks is multiplied column slab by
- * column slab, each slab is summed over the depth and downloaded while the next ones multiply; 0 = one download at the end. */
+/* Host C blocks in candmc_d25_summa: 1 (default) = the last launch group of the multiply is cut into column slabs of b/2, b/4,
+ * b/8, b/8 columns (each still over all of the group's k), each slab is summed over the depth and downloaded while the next
+ * ones multiply; 0 = one download at the end. */
 int candmc_set_early_c_download(int on);
 /* Pinned (page-locked) host B blocks on grids: 1 (default) = every k-chunk is gathered straight out of host memory by the pack
  * kernel — coalesced reads over PCIe, chunk-major on arrival — so the first multiply starts after 1/8 of the block instead
@@ -64,9 +66,10 @@ int candmc_set_early_c_download(int on);
 int candmc_set_host_gather(int on);
 /* SUMMA panel chunks (candmc_summa, candmc_d25_summa, the inner level of candmc_bcast_cannon_4d): 1 = the root writes them
  * into the consumers' CUDA-IPC-mapped windows with copy engines (cudaMemcpyAsync over NVLink + a 4-byte flag DMA, consumers
- * wait with cuStreamWaitValue32) — no SM, no NCCL kernel, the GEMM keeps all 148 SMs; 0 (default until measured on B200s) =
- * ncclBroadcast on the CTA-capped background communicators.  Must be the same on all ranks; falls back to NCCL by itself
- * when peer windows or stream memory operations are unavailable. */
+ * wait with cuStreamWaitValue32) — no SM, no NCCL kernel, the GEMM keeps all 148 SMs (default since round 2: 4 and 8 B200s,
+ * DESIGN.md 4; the Cannon staggers and shifts of candmc_bcast_cannon_4d / candmc_spcannon travel the same way); 0 =
+ * ncclBroadcast on the CTA-capped background communicators, grouped ncclSend/ncclRecv for the shifts.  Must be the same on all
+ * ranks; falls back to NCCL by itself when peer windows or stream memory operations are unavailable. */
 int candmc_set_panel_transport(int on);
 /* Panel chunks this process has shipped that way so far (0 = the transport is off or fell back to NCCL). */
 unsigned long long candmc_panel_transport_sends(void);
@@ -74,7 +77,8 @@ unsigned long long candmc_panel_transport_sends(void);
  * as a plain matrix on the panel's root (0).  Diagnostics for tests and benches. */
 unsigned long long candmc_merged_panel_launches(int chunk_major_b);
 /* Host B blocks: 1 = the rows of the first k-chunk are uploaded ahead of the rest so the first multiply starts earlier
- * (default 0: one copy of the whole block, whose wide rows keep the 2-D DMA efficient; the trade-off is not measured yet). */
+ * (default 0: one copy of the whole block, whose wide rows keep the 2-D DMA efficient).  Only matters for PAGEABLE host
+ * memory or with candmc_set_host_gather(0): pinned blocks are gathered chunk by chunk anyway. */
 int candmc_set_b_first_chunk_early(int on);
 /* Test/measurement hook: 0 disables the split-K path the GEMM takes for small tile counts (default on). */
 int candmc_debug_splitk(int on);
@@ -252,17 +256,19 @@ int candmc_update_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_
  * (default 1024) so the broadcast of chunk t+1 runs under the GEMM of chunk t.  Tests lower it to exercise the
  * chunked path on small matrices. */
 int candmc_set_min_kchunk(int64_t min_kchunk);
-/* Tuning (opt-in, default 0; also CANDMC_MERGE_LAST_PANEL=1): in summa / d25_summa sweeps with at least two panels the LAST
+/* Earlier experiment, kept for A/B runs (= candmc_set_merge_panels(1); also CANDMC_MERGE_LAST_PANEL=1): in summa / d25_summa sweeps with at least two panels the LAST
  * panel's k-chunks — all broadcast under the previous panel's multiplies — are multiplied in one launch (plus one for the chunk
  * whose buffer slot came free last) instead of one launch per chunk; the reference has no counterpart (its summa.cxx:59-99
  * multiplies a panel with one blocking dgemm_ after blocking broadcasts). */
 int candmc_set_merge_last_panel(int on);
-/* The same switch with its second mode (also CANDMC_MERGE_PANELS=0/1/2): 0 off, 1 = candmc_set_merge_last_panel(1), 2 = EVERY
- * panel of a sweep is multiplied as chunk 0 alone — the only chunk whose broadcast nothing hides — followed by ONE launch over
- * chunks 1 .. nc-1, which have arrived by the time chunk 0 is multiplied (with the fused depth sum the last chunk keeps its own
- * launch, the one with the reducing epilogue); 3 = every panel in groups that double (chunk 0, chunk 1, chunks 2-3, chunks 4-7):
- * each group only has to arrive while the one before it is multiplied, for links only a few times faster than the multiply.
- * Host operands that are still being uploaded keep one launch per chunk. */
+/* How the k-chunks of a panel are grouped into launches (also CANDMC_MERGE_PANELS=0..3).  2 (default since round 2: 16 -> 3
+ * launches per step on 2x2x1, 135 -> 143 TFLOP/s on 4 B200s) = as few launches as the arrival of the data allows: the first
+ * panel of a sweep as chunk 0 alone — the only chunk whose transfer nothing hides — followed by ONE launch over chunks
+ * 1 .. nc-1, which arrive while chunk 0 is multiplied; every later panel in ONE launch when it travelled by copy engines
+ * (chunk 0 + the rest on the NCCL path, whose buffer slots are handed back launch by launch); chunk 0, chunks 1-2, the rest
+ * while operands are still coming up from host memory; with the fused depth sum the last chunk keeps its own launch.
+ * 0 = one launch per chunk (round 1's schedule); 1 = candmc_set_merge_last_panel(1); 3 = groups that double (chunk 0, chunk 1,
+ * chunks 2-3, chunks 4-7), for links only a few times faster than the multiply. */
 int candmc_set_merge_panels(int mode);
 /* Tuning: on a 1x1x1 grid with HOST operands and n >= this (default 2048) the multiply is streamed through PCIe in
  * column panels (upload of panel j+1 and download of panel j-1 under the GEMM of panel j) instead of staged whole. */

@@ -29,6 +29,7 @@ from .mm import (  # noqa: F401
     cdgemm_chunked_b,
     upd_Yamamoto_A,
     update_Yamamoto_A,
+    aggregator,
     cyclic_to_blocked,
     blocked_to_cyclic,
     sym_full2band_update,

@@ -33,6 +33,12 @@ class PView(C.Structure):
     _fields_ = [("rrow", C.c_int), ("rcol", C.c_int), ("crow", C.c_void_p), ("ccol", C.c_void_p), ("cworld", C.c_void_p)]
 
 
+class Aggregator(C.Structure):
+    """candmc_aggregator_t: the reference's aggregator (alg/QR/qr_2d/qr_y2d.h:4-46) with device arrays."""
+    _fields_ = [("lda_aQm", i64), ("lda_aT", i64), ("shift", i64), ("n", i64), ("aQm", C.c_void_p), ("aT", C.c_void_p),
+                ("scratch", C.c_void_p)]
+
+
 class DMat(C.Structure):
     """candmc_dmat_t: DMatrix (alg/SE/dmatrix.h:7-33) without the ScaLAPACK descriptor."""
     _fields_ = [("nrow", i64), ("ncol", i64), ("b", i64), ("lda", i64), ("data", C.c_void_p), ("pv", PView)]
@@ -98,6 +104,12 @@ SIGNATURES = {
     "candmc_update_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, C.POINTER(PView), pd, i64, C.c_int, C.c_void_p]),
     "candmc_upd_Yamamoto_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, comm_p, C.c_void_p]),
     "candmc_update_Yamamoto_A": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, C.POINTER(PView), C.c_void_p]),
+    "candmc_update_Yamamoto_A_agg": (C.c_int, [pd, i64, pd, i64, i64, i64, i64, pd, C.POINTER(PView), C.POINTER(Aggregator), C.c_int,
+                                               C.c_void_p]),
+    "candmc_aggregator_create": (C.c_int, [i64, i64, C.POINTER(Aggregator)]),
+    "candmc_aggregator_reset": (C.c_int, [C.POINTER(Aggregator)]),
+    "candmc_aggregator_shift_down": (C.c_int, [C.POINTER(Aggregator), i64]),
+    "candmc_aggregator_free": (C.c_int, [C.POINTER(Aggregator)]),
     "candmc_sym_full2band_update": (C.c_int, [pd, i64, i64, i64, i64, C.POINTER(PView), comm_p, pd, i64, C.c_void_p]),
     "candmc_sym_full2band_extents": (C.c_int, [i64, i64, i64] + [C.c_int] * 5 + [C.POINTER(i64)] * 4),
     "candmc_set_min_kchunk": (C.c_int, [i64]),

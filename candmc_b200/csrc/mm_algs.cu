@@ -1429,20 +1429,44 @@ int upd_Yamamoto_A_impl(const double* Qm, int64_t lda_Qm, double* A, int64_t lda
   return OK;
 }
 
-}  // namespace
-}  // namespace candmc
+// aggregator::append (alg/QR/qr_2d/qr_y2d.cxx:38-62) on the device: the broadcast panel Qp (mb x b, ld = mb) goes into
+// aQm at column n, row `shift`; the aggregated T grows by one block row:
+//   aT[n.., 0..n] = T * ((Qp^T aQm[shift.., 0..n], summed over the grid column) * aT[0..n, 0..n]),   aT[n.., n..] = T
+// (the reference's comment says -T11 (Y^T Y) T22; its code, which is followed here, has no minus sign).  A rank with no rows
+// of the panel contributes zeros to the sum — the reference clears only b*b of the b*n doubles it then all-reduces (:54-56).
+int aggregator_append(candmc_aggregator_t* agg, int64_t mb, int64_t b, const double* Qp, const double* T, candmc_comm* ccol,
+                      cudaStream_t st) {
+  CANDMC_CHECK(agg != nullptr && agg->aQm != nullptr && agg->aT != nullptr && agg->scratch != nullptr, "aggregator: not created");
+  const int64_t n = agg->n;
+  CANDMC_CHECK(n + b <= agg->lda_aT && agg->shift + mb <= agg->lda_aQm, "aggregator: panel does not fit (n = %lld, b = %lld, lda_aT = %lld; "
+               "shift = %lld, mb = %lld, lda_aQm = %lld)", (long long)n, (long long)b, (long long)agg->lda_aT, (long long)agg->shift,
+               (long long)mb, (long long)agg->lda_aQm);
+  if (mb > 0) CANDMC_TRY(lda_copy_f64(mb, b, mb, agg->lda_aQm, Qp, agg->aQm + n * agg->lda_aQm + agg->shift, st));
+  if (n == 0) {
+    CANDMC_TRY(lda_copy_f64(b, b, b, agg->lda_aT, T, agg->aT, st));
+  } else {
+    double* t1 = agg->scratch;          // b x n
+    double* t2 = t1 + b * n + (b * n & 1);
+    if (mb > 0) CANDMC_TRY(gemm_f64('T', 'N', b, n, mb, 1.0, Qp, mb, agg->aQm + agg->shift, agg->lda_aQm, 0.0, t1, b, st));
+    else CANDMC_TRY(fill_f64(t1, b * n, 0.0, st));
+    if (ccol != nullptr && ccol->size > 1) CANDMC_TRY(comm_allreduce(ccol, t1, t1, b * n, st));
+    CANDMC_TRY(gemm_f64('N', 'N', b, n, n, 1.0, t1, b, agg->aT, agg->lda_aT, 0.0, t2, b, st));
+    CANDMC_TRY(gemm_f64('N', 'N', b, n, b, 1.0, T, b, t2, b, 0.0, agg->aT + n, agg->lda_aT, st));
+    CANDMC_TRY(lda_copy_f64(b, b, b, agg->lda_aT, T, agg->aT + n * agg->lda_aT + n, st));
+  }
+  agg->n += b;
+  return OK;
+}
 
-extern "C" {
-
-int candmc_update_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
-                             double* T, const candmc_pview_t* pv, void* stream) {
+int update_Yamamoto_A_core(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
+                           double* T, const candmc_pview_t* pv, candmc_aggregator_t* agg, bool update, void* stream) {
   NvtxRange nvtx_range("update_Yamamoto_A");
   CANDMC_TRY(runtime_require());
   g_events.reset();
   CANDMC_CHECK(pv != nullptr && pv->crow != nullptr && pv->ccol != nullptr, "update_Yamamoto_A: null processor view");
   CANDMC_CHECK(b > 0 && m >= 0 && k >= 0 && m % b == 0 && k % b == 0, "update_Yamamoto_A: m and k must be multiples of b");
-  CANDMC_CHECK(T != nullptr && is_device_ptr(Qm) && is_device_ptr(A) && is_device_ptr(T),
-               "update_Yamamoto_A: operands must be device pointers");
+  CANDMC_CHECK(T != nullptr && is_device_ptr(Qm) && is_device_ptr(T), "update_Yamamoto_A: operands must be device pointers");
+  CANDMC_CHECK(update || agg != nullptr, "update_Yamamoto_A: nothing to do");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nprow = pv->ccol->size, npcol = pv->crow->size, myrow = pv->ccol->rank, mycol = pv->crow->rank;
   CANDMC_CHECK(pv->rrow >= 0 && pv->rrow < nprow && pv->rcol >= 0 && pv->rcol < npcol, "update_Yamamoto_A: bad root row/col");
@@ -1455,6 +1479,10 @@ int candmc_update_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_
   kb *= b;
   CANDMC_CHECK(mb == 0 || mycol != pv->rcol || (Qm != nullptr && lda_Qm >= mb),
                "update_Yamamoto_A: the root column needs its Qm panel (lda_Qm >= %lld)", (long long)mb);
+  if (!update) kb = 0;   // the last panel of a block column (QR_Yamamoto_2D :266-271): broadcast and append only
+  // (a rank whose share of the trailing matrix is empty may hold a pointer past the end of its array, as the reference's
+  // drivers do after their pointer arithmetic: it is never dereferenced)
+  CANDMC_CHECK(mb == 0 || kb == 0 || is_device_ptr(A), "update_Yamamoto_A: A must be a device pointer");
   void* wsv = nullptr;
   CANDMC_TRY(workspace_get(sizeof(double) * (mb * b + 2 * b * kb + 8), &wsv));
   double* Qbuf = static_cast<double*>(wsv);
@@ -1464,7 +1492,61 @@ int candmc_update_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_
   if (mycol == pv->rcol && mb > 0) CANDMC_TRY(lda_copy_f64(mb, b, lda_Qm, mb, Qm, Qbuf, st));
   if (mb > 0) CANDMC_TRY(comm_bcast(pv->crow, Qbuf, Qbuf, mb * b, pv->rcol, st));
   CANDMC_TRY(comm_bcast(pv->crow, T, T, b * b, pv->rcol, st));
-  return upd_Yamamoto_A_impl(Qbuf, mb, A, lda_A, mb, kb, b, T, pv->ccol, W, W2, st);
+  if (update) CANDMC_TRY(upd_Yamamoto_A_impl(Qbuf, mb, A, lda_A, mb, kb, b, T, pv->ccol, W, W2, st));
+  if (agg != nullptr) CANDMC_TRY(aggregator_append(agg, mb, b, Qbuf, T, pv->ccol, st));   // :117-118
+  return OK;
+}
+
+}  // namespace
+}  // namespace candmc
+
+extern "C" {
+
+int candmc_update_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
+                             double* T, const candmc_pview_t* pv, void* stream) {
+  return update_Yamamoto_A_core(Qm, lda_Qm, A, lda_A, m, k, b, T, pv, nullptr, true, stream);
+}
+
+int candmc_update_Yamamoto_A_agg(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
+                                 double* T, const candmc_pview_t* pv, candmc_aggregator_t* agg, int update, void* stream) {
+  return update_Yamamoto_A_core(Qm, lda_Qm, A, lda_A, m, k, b, T, pv, agg, update != 0, stream);
+}
+
+int candmc_aggregator_create(int64_t lda_aQm, int64_t lda_aT, candmc_aggregator_t* out) {
+  CANDMC_TRY(runtime_require());
+  CANDMC_CHECK(out != nullptr && lda_aQm > 0 && lda_aT > 0, "aggregator: bad sizes");
+  memset(out, 0, sizeof(*out));
+  out->lda_aQm = lda_aQm;
+  out->lda_aT = lda_aT;
+  // aQm: lda_aQm x lda_aT, aT: lda_aT x lda_aT (aggregator::aggregator, qr_y2d.cxx:13-23); scratch: two b x n blocks
+  CANDMC_CUDA(cudaMalloc(&out->aQm, sizeof(double) * lda_aQm * lda_aT));
+  CANDMC_CUDA(cudaMalloc(&out->aT, sizeof(double) * lda_aT * lda_aT));
+  CANDMC_CUDA(cudaMalloc(&out->scratch, sizeof(double) * (2 * lda_aT * lda_aT + 2)));
+  return candmc_aggregator_reset(out);
+}
+
+int candmc_aggregator_reset(candmc_aggregator_t* agg) {   // aggregator::reset, qr_y2d.cxx:25-31
+  CANDMC_CHECK(agg != nullptr && agg->aQm != nullptr && agg->aT != nullptr, "aggregator: not created");
+  agg->n = 0;
+  agg->shift = 0;
+  CANDMC_CUDA(cudaMemset(agg->aQm, 0, sizeof(double) * agg->lda_aQm * agg->lda_aT));
+  CANDMC_CUDA(cudaMemset(agg->aT, 0, sizeof(double) * agg->lda_aT * agg->lda_aT));
+  return OK;
+}
+
+int candmc_aggregator_shift_down(candmc_aggregator_t* agg, int64_t b) {   // aggregator::shift_down, qr_y2d.cxx:34-36
+  CANDMC_CHECK(agg != nullptr && b >= 0, "aggregator: bad shift");
+  agg->shift += b;
+  return OK;
+}
+
+int candmc_aggregator_free(candmc_aggregator_t* agg) {
+  if (agg == nullptr) return OK;
+  if (agg->aQm) cudaFree(agg->aQm);
+  if (agg->aT) cudaFree(agg->aT);
+  if (agg->scratch) cudaFree(agg->scratch);
+  memset(agg, 0, sizeof(*agg));
+  return OK;
 }
 
 int candmc_upd_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,

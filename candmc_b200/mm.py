@@ -199,12 +199,41 @@ def upd_Yamamoto_A(Qm, lda_Qm, A, lda_A, mb, kb, b, T, ccol: CommData_t | None =
                                       _stream(stream)))
 
 
-def update_Yamamoto_A(Qm, lda_Qm, A, lda_A, m, k, b, T, pv: pview, agg=None, stream=None):
-    """update_Yamamoto_A (alg/QR/qr_2d/qr_y2d.h:59-68) with agg == NULL; T is broadcast along the grid row in place."""
-    if agg is not None:
-        raise NotImplementedError("the aggregator (qr_y2d.cxx:12-66) is host-side bookkeeping of the reference's drivers")
+class aggregator:
+    """The reference's aggregator (alg/QR/qr_2d/qr_y2d.h:4-46, qr_y2d.cxx:13-62) with device arrays: the panels of a block column
+    side by side in aQm (lda_aQm x lda_aT), their aggregated T in aT (lda_aT x lda_aT); n panels' columns so far, `shift` rows down."""
+
+    def __init__(self, lda_aQm, lda_aT):
+        self._c = _lib.Aggregator()
+        check(lib().candmc_aggregator_create(lda_aQm, lda_aT, C.byref(self._c)))
+
+    lda_aQm = property(lambda self: self._c.lda_aQm)
+    lda_aT = property(lambda self: self._c.lda_aT)
+    n = property(lambda self: self._c.n)
+    shift = property(lambda self: self._c.shift)
+    aQm = property(lambda self: self._c.aQm)
+    aT = property(lambda self: self._c.aT)
+
+    def reset(self):
+        check(lib().candmc_aggregator_reset(C.byref(self._c)))
+
+    def shift_down(self, b):
+        check(lib().candmc_aggregator_shift_down(C.byref(self._c), b))
+
+    def free(self):
+        check(lib().candmc_aggregator_free(C.byref(self._c)))
+
+
+def update_Yamamoto_A(Qm, lda_Qm, A, lda_A, m, k, b, T, pv: pview, agg: aggregator | None = None, stream=None, update=True):
+    """update_Yamamoto_A (alg/QR/qr_2d/qr_y2d.h:59-68); T is broadcast along the grid row in place.  With an aggregator the
+    broadcast panel and T are appended to it afterwards (aggregator::append, qr_y2d.cxx:38-62); update=False only broadcasts
+    and appends — the last panel of a block column (QR_Yamamoto_2D, :266-271)."""
     cpv = _lib.PView(pv.rrow, pv.rcol, pv.crow.cm, pv.ccol.cm, pv.cworld.cm if pv.cworld else None)
-    check(lib().candmc_update_Yamamoto_A(_ptr(Qm), lda_Qm, _ptr(A), lda_A, m, k, b, _ptr(T), C.byref(cpv), _stream(stream)))
+    if agg is None:
+        check(lib().candmc_update_Yamamoto_A(_ptr(Qm), lda_Qm, _ptr(A), lda_A, m, k, b, _ptr(T), C.byref(cpv), _stream(stream)))
+    else:
+        check(lib().candmc_update_Yamamoto_A_agg(_ptr(Qm), lda_Qm, _ptr(A), lda_A, m, k, b, _ptr(T), C.byref(cpv), C.byref(agg._c),
+                                                 1 if update else 0, _stream(stream)))
 
 
 def sym_full2band_extents(n, b, b_sub, np_, myrow, mycol, rrow, rcol):

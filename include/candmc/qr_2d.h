@@ -21,7 +21,47 @@
 #include "comm.h"
 #include "util.h"
 
-class aggregator;   /* alg/QR/qr_2d/qr_y2d.h: only ever passed as NULL here */
+/* The reference's aggregator (alg/QR/qr_2d/qr_y2d.h:4-46, qr_y2d.cxx:13-62) with the same members and methods; aQm and aT are
+ * DEVICE arrays (zero-filled by the constructor, as the reference's are), n and shift live on the host.  append() happens
+ * inside update_Yamamoto_A as on the reference's side (:117-118); for the last panel of a block column, which
+ * QR_Yamamoto_2D only broadcasts and appends (:266-271), there is append_last_Yamamoto_panel below. */
+class aggregator {
+ public:
+  int64_t lda_aQm;
+  int64_t lda_aT;
+  int64_t shift;
+  double* aQm;
+  double* aT;
+  int64_t n;
+
+  aggregator(int64_t lda_aQm_, int64_t lda_aT_) {
+    candmc_shim_check(candmc_aggregator_create(lda_aQm_, lda_aT_, &impl_), "aggregator");
+    sync_out();
+  }
+  ~aggregator() { candmc_aggregator_free(&impl_); }
+  aggregator(const aggregator&) = delete;
+  aggregator& operator=(const aggregator&) = delete;
+  void reset() {
+    candmc_shim_check(candmc_aggregator_reset(&impl_), "aggregator::reset");
+    sync_out();
+  }
+  void shift_down(int64_t b) {
+    sync_in();
+    candmc_shim_check(candmc_aggregator_shift_down(&impl_, b), "aggregator::shift_down");
+    sync_out();
+  }
+  candmc_aggregator_t* handle() {   /* what the C ABI takes; picks up n / shift a caller may have changed directly */
+    sync_in();
+    return &impl_;
+  }
+  void sync_out() {
+    lda_aQm = impl_.lda_aQm; lda_aT = impl_.lda_aT; shift = impl_.shift; n = impl_.n; aQm = impl_.aQm; aT = impl_.aT;
+  }
+
+ private:
+  void sync_in() { impl_.shift = shift; impl_.n = n; }
+  candmc_aggregator_t impl_;
+};
 
 inline void candmc_qr2d_unsupported(bool bad, const char* what) {
   if (!bad) return;
@@ -45,9 +85,18 @@ inline void upd_A(double const* Ybuf, int64_t lda_Y, double* A, int64_t lda_A, i
 
 inline void update_Yamamoto_A(double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b, double* T,
                               pview* pv, aggregator* agg) {
-  candmc_qr2d_unsupported(agg != nullptr, "update_Yamamoto_A: the aggregator is not supported (agg must be NULL)");
   candmc_pview_t c = {pv->rrow, pv->rcol, pv->crow.cm, pv->ccol.cm, pv->cworld.cm};
-  candmc_shim_check(candmc_update_Yamamoto_A(Qm, lda_Qm, A, lda_A, m, k, b, T, &c, 0), "update_Yamamoto_A");
+  candmc_shim_check(candmc_update_Yamamoto_A_agg(Qm, lda_Qm, A, lda_A, m, k, b, T, &c, agg ? agg->handle() : nullptr, 1, 0),
+                    "update_Yamamoto_A");
+  if (agg) agg->sync_out();
+}
+
+/* The last panel of a block column (QR_Yamamoto_2D, qr_y2d.cxx:266-271): MPI_Bcast of Qm and T along the grid row, then
+ * agg->append — no trailing matrix left to update.  m, b and pv as for update_Yamamoto_A. */
+inline void append_last_Yamamoto_panel(double* Qm, int64_t lda_Qm, int64_t m, int64_t b, double* T, pview* pv, aggregator* agg) {
+  candmc_pview_t c = {pv->rrow, pv->rcol, pv->crow.cm, pv->ccol.cm, pv->cworld.cm};
+  candmc_shim_check(candmc_update_Yamamoto_A_agg(Qm, lda_Qm, Qm, lda_Qm, m, 0, b, T, &c, agg->handle(), 0, 0), "aggregator::append");
+  agg->sync_out();
 }
 
 inline void upd_Yamamoto_A(double const* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,

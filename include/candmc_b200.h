@@ -252,6 +252,28 @@ int candmc_upd_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t l
                           const double* T, candmc_comm_t* ccol, void* stream);
 int candmc_update_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
                              double* T, const candmc_pview_t* pv, void* stream);
+/* The reference's `aggregator` (alg/QR/qr_2d/qr_y2d.h:4-46, qr_y2d.cxx:13-62) with its arrays in device memory: the panels of a
+ * block column appended side by side in aQm (lda_aQm x lda_aT, panel s at column n, row `shift`) and their aggregated T in aT
+ * (lda_aT x lda_aT), so that the whole block column is applied to the trailing matrix by ONE candmc_upd_Yamamoto_A(aQm,
+ * lda_aQm, ..., b = n, aT) — as QR_Yamamoto_2D_2D does (:370).  create zero-fills (the constructor, :13-23), reset = :25-31,
+ * shift_down = :34-36 (host-side field).  `scratch` is private to the library. */
+typedef struct candmc_aggregator {
+  int64_t lda_aQm, lda_aT, shift, n;
+  double* aQm;
+  double* aT;
+  double* scratch;
+} candmc_aggregator_t;
+int candmc_aggregator_create(int64_t lda_aQm, int64_t lda_aT, candmc_aggregator_t* out);
+int candmc_aggregator_reset(candmc_aggregator_t* agg);
+int candmc_aggregator_shift_down(candmc_aggregator_t* agg, int64_t b);
+int candmc_aggregator_free(candmc_aggregator_t* agg);
+/* update_Yamamoto_A with agg != NULL (qr_y2d.cxx:68-120): the update above, then aggregator::append (:38-62) of the broadcast
+ * panel and T — aT[n.., 0..n] = T ((Qm^T aQm[shift.., 0..n], all-reduced over the grid column) aT[0..n, 0..n]), aT[n.., n..] = T.
+ * update == 0 skips the trailing update: the last panel of a block column is only broadcast and appended (QR_Yamamoto_2D
+ * :266-271).  A rank without rows of the panel contributes zeros to the sum (the reference adds an uninitialised buffer
+ * there, :54-56).  agg may be NULL (= candmc_update_Yamamoto_A). */
+int candmc_update_Yamamoto_A_agg(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
+                                 double* T, const candmc_pview_t* pv, candmc_aggregator_t* agg, int update, void* stream);
 /* Tuning: the SUMMA pipeline cuts each b-wide panel into up to 8 k-chunks of at least this many columns
  * (default 1024) so the broadcast of chunk t+1 runs under the GEMM of chunk t.  Tests lower it to exercise the
  * chunked path on small matrices. */

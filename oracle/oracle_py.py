@@ -263,6 +263,62 @@ def update_Yamamoto_A(nprow, npcol, rrow, rcol, m, k, b, Qm, A, T):
     assert rc == 0, "oracle_update_Yamamoto_A: bad arguments"
 
 
+# ---- update_Yamamoto_A with an aggregator (alg/QR/qr_2d/qr_y2d.cxx:38-62,68-120), driven as QR_Yamamoto_2D drives it (:171-277) ----
+# Restated on the GLOBAL block column (every rank's local arrays are block-cyclic pieces of it), pinned to the unmodified
+# reference by the `updyagg_*` fixtures of tests/golden/canmm_ref_outputs.npz (oracle/ref_dump.cxx, mode updyagg).
+def _lcg48_vec(seeds):
+    a, c, mask, lo24 = np.uint64(0x5DEECE66D), np.uint64(0xB), np.uint64((1 << 48) - 1), np.uint64((1 << 24) - 1)
+    x = ((np.asarray(seeds, dtype=np.uint64) & np.uint64(0xFFFFFFFF)) << np.uint64(16)) | np.uint64(0x330E)
+    xl, xh = x & lo24, x >> np.uint64(24)
+    x = (a * xl + (((a * xh) & lo24) << np.uint64(24)) + c) & mask
+    return x.astype(np.float64) / 281474976710656.0
+
+
+def yamamoto_agg_inputs(m, k, b, s=None):
+    """ref_dump's `updyagg` generators: the m x k block column (s is None), or step s's panel Qm (rows s*b .. m of the original
+    matrix, b columns) and its b x b T."""
+    if s is None:
+        gr, gc = np.meshgrid(np.arange(m, dtype=np.uint64), np.arange(k, dtype=np.uint64), indexing="ij")
+        return np.asfortranarray(_lcg48_vec(np.uint64(900000) + gc * np.uint64(m) + gr) - .5)
+    gr, j = np.meshgrid(np.arange(s * b, m, dtype=np.uint64), np.arange(b, dtype=np.uint64), indexing="ij")
+    Qm = (_lcg48_vec(np.uint64(7000 + 131 * s) + gr * np.uint64(b) + j) - .5) * 0.25
+    i, j = np.meshgrid(np.arange(b, dtype=np.uint64), np.arange(b, dtype=np.uint64), indexing="ij")
+    T = (_lcg48_vec(np.uint64(555000 + 977 * s) + i + j * np.uint64(b)) - .5) * 0.5
+    return np.asfortranarray(Qm), np.asfortranarray(T)
+
+
+def yamamoto_aggregate(m, k, b):
+    """Global result of the k/b steps: (A after the trailing updates, aQm (m x k), aT (k x k)).
+    Step s (qr_y2d.cxx:123-169): W = Qm^T A_trail, W2 = -T W, A_trail -= Qm W2 on rows s*b.., columns (s+1)*b..;
+    append (:38-62): aQm[s*b.., n..n+b] = Qm; aT[0:b,0:b] = T for the first panel, afterwards
+    aT[n..n+b, 0..n] = T ((Qm^T aQm[s*b.., 0..n]) aT[0..n,0..n]) and aT[n..n+b, n..n+b] = T."""
+    A = yamamoto_agg_inputs(m, k, b)
+    aQm = np.zeros((m, k), order="F"); aT = np.zeros((k, k), order="F")
+    n = 0
+    for s in range(k // b):
+        Qm, T = yamamoto_agg_inputs(m, k, b, s)
+        if k - s * b - b > 0 and m - s * b - b > 0:
+            tr = A[s * b:, (s + 1) * b:]
+            tr -= Qm @ (-T @ (Qm.T @ tr))
+        aQm[s * b:, n:n + b] = Qm
+        if n == 0:
+            aT[:b, :b] = T
+        else:
+            aT[n:n + b, :n] = T @ ((Qm.T @ aQm[s * b:, :n]) @ aT[:n, :n])
+            aT[n:n + b, n:n + b] = T
+        n += b
+    return A, aQm, aT
+
+
+def cyclic_local(G, b, nprow, npcol, rrow, rcol, myrow, mycol):
+    """rank (myrow, mycol)'s block-cyclic piece of the global matrix G (blocks of b, roots rrow / rcol own block 0)"""
+    rb = [g for g in range(G.shape[0] // b) if (g - (myrow - rrow)) % nprow == 0]
+    cb = [g for g in range(G.shape[1] // b) if (g - (mycol - rcol)) % npcol == 0]
+    rows = np.concatenate([np.arange(g * b, (g + 1) * b) for g in rb]) if rb else np.zeros(0, dtype=int)
+    cols = np.concatenate([np.arange(g * b, (g + 1) * b) for g in cb]) if cb else np.zeros(0, dtype=int)
+    return np.asfortranarray(G[np.ix_(rows, cols)])
+
+
 # ---- DMatrix pack / replication operations (alg/SE/dmatrix.cxx), all ranks simulated in numpy ------------------------------
 # Data movement only (plus one sum), so numpy index arithmetic is the restatement; pinned to the unmodified reference by
 # tests/golden/dmat_ref_outputs.npz (oracle/ref_dmat_dump.cxx).  Grid rank = myrow + mycol*nprow (test_qr_2d.cxx:367-374).

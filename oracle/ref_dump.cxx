@@ -11,6 +11,8 @@
 //   ref_dump updw  <m> <k> <b> <nprow> <rrow> <rcol> <prefix>   update_A, W = the panel QR's upper-triangular factor, W_is_T == false
 //                                                                (what QR_2D hands in, qr_2d.cxx:325; T by comp_bcast_T_from_W :179-208)
 //   ref_dump updy  <m> <k> <b> <nprow> <rrow> <rcol> <prefix>   update_Yamamoto_A, agg == NULL (alg/QR/qr_2d/qr_y2d.cxx:68-120)
+//   ref_dump updyagg <m> <k> <b> <nprow> <rrow> <rcol> <prefix>   update_Yamamoto_A WITH an aggregator over the k/b panels of an m x k
+//                                                                block column, driven the way QR_Yamamoto_2D drives it (qr_y2d.cxx:171-277)
 //   ref_dump spc   <bidir> <ndim> <seed> <n> <m> <k> <alpha> <beta> <tB N|T> <prefix>   kput_cannon / kuni_cannon (test/MM/test_spc.cxx:36-114)
 #include <assert.h>
 #include <math.h>
@@ -277,6 +279,88 @@ static int run_updy(int myRank, int numPes, int64_t m, int64_t k, int64_t b, int
   return 0;
 }
 
+// update_Yamamoto_A with agg != NULL (alg/QR/qr_2d/qr_y2d.cxx:68-120 + aggregator::append :38-62), driven exactly as
+// QR_Yamamoto_2D drives it on an m x k block column with blocks of b (:171-277) — the recursion unrolled into a loop, the panel
+// factorisation (Yamamoto(), host-side TSQR: out of scope) replaced by synthetic Qm / T per step: every step updates the trailing
+// columns with the step's panel, appends the panel to the aggregator, shifts the aggregator down on the root row and rotates
+// the roots; the last panel is only appended (:266-271).  Dumped per rank: the local matrix (mb0 x kb0), then the aggregated
+// panels aQm (lda_aQm = mb0 rows x k columns), then the aggregated aT (k x k).
+static int run_updyagg(int myRank, int numPes, int64_t m, int64_t k, int64_t b, int nprow, int rrow0, int rcol0, const char* prefix) {
+  const int npcol = numPes / nprow;
+  if (nprow * npcol != numPes || m % b || k % b || m < k) return 2;
+  const int myrow = myRank % nprow, mycol = myRank / nprow;
+  CommData_t cdt_glb, cdt_row, cdt_col;
+  SET_COMM(MPI_COMM_WORLD, myRank, numPes, cdt_glb);
+  SETUP_SUB_COMM(cdt_glb, cdt_row, myRank / nprow, myRank % nprow, npcol);
+  SETUP_SUB_COMM(cdt_glb, cdt_col, myRank % nprow, myRank / nprow, nprow);
+  pview pv;
+  pv.rrow = rrow0; pv.rcol = rcol0; pv.crow = cdt_row; pv.ccol = cdt_col; pv.cworld = cdt_glb;
+  int64_t mb0 = (m / b) / nprow;
+  if ((myrow + nprow - rrow0) % nprow < (m / b) % nprow) mb0++;
+  mb0 *= b;
+  int64_t kb0 = (k / b) / npcol;
+  if ((mycol + npcol - rcol0) % npcol < (k / b) % npcol) kb0++;
+  kb0 *= b;
+  const int64_t lda_A = mb0 ? mb0 : 1;
+  double* A = alloc_d((size_t)lda_A * (kb0 ? kb0 : 1));
+  for (int64_t cc = 0; cc < kb0; cc++)
+    for (int64_t r = 0; r < mb0; r++) {
+      const int64_t gr = ((r / b) * nprow + (myrow - rrow0 + nprow) % nprow) * b + r % b;
+      const int64_t gc = ((cc / b) * npcol + (mycol - rcol0 + npcol) % npcol) * b + cc % b;
+      srand48(900000 + gc * m + gr);
+      A[r + cc * lda_A] = drand48() - .5;
+    }
+  aggregator agg(lda_A, k);
+  double* Aptr = A;
+  int64_t ms = m, ks = k;
+  for (int s = 0;; ++s, ms -= b, ks -= b) {
+    int64_t mb = (ms / b) / nprow;
+    if ((myrow + nprow - pv.rrow) % nprow < (ms / b) % nprow) mb++;
+    mb *= b;
+    double* Qm = alloc_d((size_t)(mb ? mb : 1) * b);
+    double* T = alloc_d((size_t)b * b);
+    for (int64_t j = 0; j < b; j++)
+      for (int64_t r = 0; r < mb; r++) {   // global row of the ORIGINAL matrix: s*b + the row inside the remaining matrix
+        const int64_t gr = s * b + ((r / b) * nprow + (myrow - pv.rrow + nprow) % nprow) * b + r % b;
+        srand48(7000 + 131 * s + gr * b + j);
+        Qm[r + j * mb] = mycol == pv.rcol ? (drand48() - .5) * 0.25 : 77.0;   // only the root column's panel counts
+      }
+    for (int64_t j = 0; j < b; j++)
+      for (int64_t i = 0; i < b; i++) {
+        srand48(555000 + 977 * s + i + j * b);
+        T[i + j * b] = mycol == pv.rcol ? (drand48() - .5) * 0.5 : 0.0;
+      }
+    if (ks - b > 0 && ms - b > 0) {
+      int64_t move_ptr = 0;
+      if (pv.crow.rank == pv.rcol) move_ptr = b * lda_A;
+      update_Yamamoto_A(Qm, mb, Aptr + move_ptr, lda_A, ms, ks - b, b, T, &pv, &agg);
+      if (pv.ccol.rank == pv.rrow) move_ptr += b;
+      if (pv.ccol.rank == pv.rrow) agg.shift_down(b);
+      pv.rrow = (pv.rrow + 1) % pv.ccol.np;
+      pv.rcol = (pv.rcol + 1) % pv.crow.np;
+      Aptr += move_ptr;
+      free(Qm);
+      free(T);
+    } else {
+      if (ms - b >= 0) {
+        MPI_Bcast(Qm, mb * b, MPI_DOUBLE, pv.rcol, pv.crow.cm);
+        MPI_Bcast(T, b * b, MPI_DOUBLE, pv.rcol, pv.crow.cm);
+        agg.append(mb, b, Qm, mb, T, &pv);
+      }
+      free(Qm);
+      free(T);
+      break;
+    }
+  }
+  const size_t na = (size_t)mb0 * kb0, nq = (size_t)lda_A * k, nt = (size_t)k * k;
+  double* out = alloc_d(na + nq + nt);
+  for (int64_t cc = 0; cc < kb0; cc++) memcpy(out + cc * mb0, A + cc * lda_A, sizeof(double) * mb0);
+  memcpy(out + na, agg.aQm, sizeof(double) * nq);
+  memcpy(out + na + nq, agg.aT, sizeof(double) * nt);
+  dump(prefix, myRank, out, na + nq + nt);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   int myRank, numPes;
   MPI_Init(&argc, &argv);
@@ -298,6 +382,9 @@ int main(int argc, char** argv) {
   else if (argc >= 9 && !strcmp(argv[1], "updw"))
     rc = run_upda(myRank, numPes, atoll(argv[2]), atoll(argv[3]), atoll(argv[4]), atoi(argv[5]), atoi(argv[6]),
                   atoi(argv[7]), argv[8], true);
+  else if (argc >= 9 && !strcmp(argv[1], "updyagg"))
+    rc = run_updyagg(myRank, numPes, atoll(argv[2]), atoll(argv[3]), atoll(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]),
+                     argv[8]);
   else if (argc >= 9 && !strcmp(argv[1], "updy"))
     rc = run_updy(myRank, numPes, atoll(argv[2]), atoll(argv[3]), atoll(argv[4]), atoi(argv[5]), atoi(argv[6]),
                   atoi(argv[7]), argv[8]);

@@ -60,6 +60,15 @@ CASES = {
     "updy_m80_k48_b8_2x3_r12": (6, ["updy", "80", "48", "8", "2", "1", "2"], None),
     "updy_m64_k32_b16_1x1": (1, ["updy", "64", "32", "16", "1", "0", "0"], None),
     "updy_m72_k40_b8_4x1_r20": (4, ["updy", "72", "40", "8", "4", "2", "0"], None),
+    # update_Yamamoto_A WITH an aggregator over the k/b panels of an m x k block column, driven as QR_Yamamoto_2D drives it
+    # (qr_y2d.cxx:38-62,68-120,171-277): updyagg <m> <k> <b> <nprow> <rrow> <rcol>; per rank A (mb0 x kb0) | aQm (mb0 x k) | aT (k x k).
+    # Sizes keep at least one row block on every rank at every step: with mb == 0 the reference sums an uninitialised buffer
+    # into aT (:54-56 clear b*b of the b*n doubles the all-reduce then adds).
+    "updyagg_m96_k32_b8_2x2_r00": (4, ["updyagg", "96", "32", "8", "2", "0", "0"], None),
+    "updyagg_m96_k32_b8_2x2_r11": (4, ["updyagg", "96", "32", "8", "2", "1", "1"], None),
+    "updyagg_m80_k24_b8_2x3_r12": (6, ["updyagg", "80", "24", "8", "2", "1", "2"], None),
+    "updyagg_m64_k32_b16_1x1": (1, ["updyagg", "64", "32", "16", "1", "0", "0"], None),
+    "updyagg_m72_k24_b8_4x1_r20": (4, ["updyagg", "72", "24", "8", "4", "2", "0"], None),
 }
 
 

@@ -132,6 +132,13 @@ void use(pview* pv, double* A, double* Y, double* B) {
   upd_A(Y, 64, A, 64, 64, 48, 16, B, pv, true);
   update_Yamamoto_A(Y, 64, A, 64, 128, 96, 16, B, pv, NULL);
   upd_Yamamoto_A(Y, 64, A, 64, 64, 48, 16, B, pv);
+  // ... and with the reference's aggregator (qr_y2d.h:4-46), as QR_Yamamoto_2D_2D uses it (qr_y2d.cxx:333-377)
+  aggregator agg(64, 32);
+  update_Yamamoto_A(Y, 64, A, 64, 128, 32, 16, B, pv, &agg);
+  agg.shift_down(16);
+  append_last_Yamamoto_panel(Y, 64, 112, 16, B, pv, &agg);
+  upd_Yamamoto_A(agg.aQm, agg.lda_aQm, A, 64, 64, 48, agg.n, agg.aT, pv);
+  agg.reset();
 }
 """)
     inc = os.path.join(ROOT, "include")

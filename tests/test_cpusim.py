@@ -59,21 +59,14 @@ for _n in DIST_MAIN:     # longest first.  On 8 ranks the fused GEMM + depth all
 # opt-in fused depth sum, on 2x2x2 — deferred streams, LIFO order; and round 1's path (NCCL kernels, one launch per k-chunk)
 _job("nccl4", _torchrun(4, 29747, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_NCCL_PANELS="1",
      CPUSIM_SCHED="lifo")
-_job("transport4", _torchrun(4, 29741, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_PANEL_TRANSPORT="1",
-     CPUSIM_SCHED="lifo")
-_job("transport8", _torchrun(8, 29742, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_PANEL_TRANSPORT="1",
-     CANDMC_TEST_FUSED_GRIDS="1", CPUSIM_SCHED="lifo")
+# (the copy-engine transport and launch groups of mode 2 ARE main4 / main8 since round 2 — and main4@lifo / main8@random below)
 # opt-in: the last panel of a sweep multiplied in one launch over its k-chunks (B read chunk-major through one tensor map by the
 # product's own kernel on the PTX emulation); the validated 2x2 suite with the switch on
 _job("merge4", _torchrun(4, 29743, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_MERGE_PANELS="1",
      CPUSIM_SCHED="lifo")
-# ... and every panel as chunk 0 + one launch over the rest, on 2x2 and (with the fused depth sum) on 2x2x2
-_job("merge4_all", _torchrun(4, 29744, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_MERGE_PANELS="2",
-     CPUSIM_SCHED="lifo")
+# ... and the doubling groups of mode 3 (mode 2 is the default: main4 / main8)
 _job("merge4_doubling", _torchrun(4, 29746, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_MERGE_PANELS="3",
      CPUSIM_SCHED="random:22")
-_job("merge8_all", _torchrun(8, 29745, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_MERGE_PANELS="2",
-     CANDMC_TEST_FUSED_GRIDS="1", CPUSIM_SCHED="random:21")
 # the hot kernel itself on the PTX emulation, and the 4-rank suite with every GEMM going through it
 _job("kernel", [sys.executable, os.path.join(SIM, "probe_gemm.py")])
 _job("kernel_pack", [sys.executable, os.path.join(SIM, "probe_pack.py")])
@@ -159,17 +152,25 @@ def sim_runs():
     subprocess.check_call(["make", "-s", "-C", SIM, "-j8"])
     assert os.path.exists(os.path.join(SIM, "_build", "libcandmc_b200_cpusim.so"))
 
+    import time
+    times = {}
+
     def run(name):
         cmd, extra = JOBS[name]
+        t0 = time.time()
         try:
             p = subprocess.run(cmd, cwd=ROOT, env=_env(**extra), capture_output=True, text=True, timeout=600)
             return name, (p.returncode, p.stdout, p.stderr)
         except subprocess.TimeoutExpired as e:
             return name, (-999, str(e.stdout or ""), "TIMEOUT " + str(e.stderr or ""))
+        finally:
+            times[name] = round(time.time() - t0, 1)
 
     with ThreadPoolExecutor(max_workers=4) as pool:
         for name, res in pool.map(run, list(JOBS)):
             RESULTS[name] = res
+    with open(os.path.join(SIM, "_build", "job_times.json"), "w") as f:   # where the suite's time goes (longest first)
+        json.dump(dict(sorted(times.items(), key=lambda kv: -kv[1])), f, indent=1)
     return RESULTS
 
 
@@ -316,7 +317,7 @@ def test_copy_engine_panel_transport_on_the_simulator(nproc):
     """candmc_set_panel_transport(1): panel chunks DMA-written into the consumers' IPC windows, ready / done flags as 4-byte
     DMAs, cuStreamWaitValue32 on the consumer side — the whole distributed suite incl. repeated multiplies on one grid (window
     halves reused, windows regrown), no ncclBroadcast left on the path"""
-    out = _dist(f"transport{nproc}")
+    out = _dist(f"main{nproc}")
     assert out["panel_transport_sends_rank0"] > 50
 
 
@@ -327,7 +328,7 @@ def test_nccl_panels_and_per_chunk_launches_on_the_simulator():
     assert out["panel_transport_sends_rank0"] == 0 and out["merged_panel_launches_all_ranks"] == [0, 0]
 
 
-@pytest.mark.parametrize("job", ["merge4", "merge4_all", "merge4_doubling", "merge8_all"])
+@pytest.mark.parametrize("job", ["merge4", "main4", "merge4_doubling", "main8"])
 def test_merged_panel_launches_on_the_simulator(job):
     """candmc_set_merge_panels(1 / 2 / 3) under the validated 2x2 and 2x2x2 suites (deferred streams, LIFO / random order): same
     results, and the merged launch with chunk-major B really ran (the 3x3 grid, ragged tile columns, host operands and the

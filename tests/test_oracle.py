@@ -223,3 +223,31 @@ def test_oracle_update_Yamamoto_A_matches_reference(golden, name, m, k, b, nprow
         assert A[r].size == ref.size, (name, r)
         if ref.size:
             assert rel_frob(A[r], ref) <= 10 * m * EPS, (name, r)
+
+
+UPDYAGG = [("updyagg_m96_k32_b8_2x2_r00", 96, 32, 8, 2, 2, 0, 0), ("updyagg_m96_k32_b8_2x2_r11", 96, 32, 8, 2, 2, 1, 1),
+           ("updyagg_m80_k24_b8_2x3_r12", 80, 24, 8, 2, 3, 1, 2), ("updyagg_m64_k32_b16_1x1", 64, 32, 16, 1, 1, 0, 0),
+           ("updyagg_m72_k24_b8_4x1_r20", 72, 24, 8, 4, 1, 2, 0)]
+
+
+def split_updyagg(flat, mb0, kb0, k):
+    """one rank's fixture of ref_dump's `updyagg` mode: A (mb0 x kb0) | aQm (max(mb0, 1) x k) | aT (k x k), column-major"""
+    na, nq = mb0 * kb0, max(mb0, 1) * k
+    assert flat.size == na + nq + k * k
+    A = flat[:na].reshape(kb0, mb0).T if na else np.zeros((mb0, kb0))
+    return A, flat[na:na + nq].reshape(k, max(mb0, 1)).T[:mb0], flat[na + nq:].reshape(k, k).T
+
+
+@pytest.mark.parametrize("name,m,k,b,nprow,npcol,rrow,rcol", UPDYAGG)
+def test_oracle_yamamoto_aggregator_matches_reference(golden, name, m, k, b, nprow, npcol, rrow, rcol):
+    """SURVEY §8f N1, the aggregated form: the reference's own update_Yamamoto_A with an aggregator (aggregator::append,
+    alg/QR/qr_2d/qr_y2d.cxx:38-62) over the k/b panels of a block column, driven as QR_Yamamoto_2D drives it (:171-277):
+    the trailing updates, the aggregated panels aQm and the aggregated T on every rank."""
+    A, aQm, aT = orc.yamamoto_aggregate(m, k, b)
+    for r in range(nprow * npcol):
+        myrow, mycol = r % nprow, r // nprow
+        Al = orc.cyclic_local(A, b, nprow, npcol, rrow, rcol, myrow, mycol)
+        Ql = orc.cyclic_local(aQm, b, nprow, 1, rrow, 0, myrow, 0)   # every grid column holds its grid row's rows of every panel
+        gA, gQ, gT = split_updyagg(golden[f"{name}.r{r}"], Al.shape[0], Al.shape[1], k)
+        assert np.abs(gA - Al).max() <= 10 * m * EPS and np.abs(gT - aT).max() <= 10 * m * EPS, (name, r)
+        assert np.array_equal(gQ, Ql), (name, r)

@@ -324,6 +324,12 @@ def case_update_Yamamoto_A(world, golden, name, m, k, b, nprow, rrow, rcol):
     return ok
 
 
+# The aggregator form was written after round 2's GPU minutes were spent: its cases run in the pending group on the simulator
+# (always) and on GPUs only when asked for (tests/test_zz_aggregator_gpu.py sets CANDMC_TEST_AGG=1 and is the one test still
+# marked xfail(strict=False), until a round has seen it pass on a B200).
+AGG_CASES = os.environ.get("CANDMC_CPUSIM") == "1" or os.environ.get("CANDMC_TEST_AGG") == "1"
+
+
 def case_yamamoto_aggregator(world, golden, name, m, k, b, nprow, rrow0, rcol0):
     """SURVEY §8f N1, the aggregated form: update_Yamamoto_A WITH an aggregator over the k/b panels of an m x k block column,
     driven as QR_Yamamoto_2D drives it (alg/QR/qr_2d/qr_y2d.cxx:171-277; the panel factorisation replaced by the fixture's
@@ -537,15 +543,17 @@ def pending_cases(world, golden):
     P = world.np
     if P == 1:
         case_update_Yamamoto_A(world, golden, "updy_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0)
-        case_yamamoto_aggregator(world, golden, "updyagg_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0)
-        case_yamamoto_aggregator(world, golden, "updyagg_big_1x1", 1024, 256, 64, 1, 0, 0)
+        if AGG_CASES:
+            case_yamamoto_aggregator(world, golden, "updyagg_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0)
+            case_yamamoto_aggregator(world, golden, "updyagg_big_1x1", 1024, 256, 64, 1, 0, 0)
         case_update_Yamamoto_A(world, golden, "updy_big_1x1", 1024, 512, 128, 1, 0, 0)
     if P == 4:
         case_update_Yamamoto_A(world, golden, "updy_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 0, 0)
-        case_yamamoto_aggregator(world, golden, "updyagg_m96_k32_b8_2x2_r00", 96, 32, 8, 2, 0, 0)
-        case_yamamoto_aggregator(world, golden, "updyagg_m96_k32_b8_2x2_r11", 96, 32, 8, 2, 1, 1)
-        case_yamamoto_aggregator(world, golden, "updyagg_m72_k24_b8_4x1_r20", 72, 24, 8, 4, 2, 0)
-        case_yamamoto_aggregator(world, golden, "updyagg_ragged_2x2_r01", 40, 40, 8, 2, 0, 1)   # ranks run out of rows: zeros, not garbage
+        if AGG_CASES:
+            case_yamamoto_aggregator(world, golden, "updyagg_m96_k32_b8_2x2_r00", 96, 32, 8, 2, 0, 0)
+            case_yamamoto_aggregator(world, golden, "updyagg_m96_k32_b8_2x2_r11", 96, 32, 8, 2, 1, 1)
+            case_yamamoto_aggregator(world, golden, "updyagg_m72_k24_b8_4x1_r20", 72, 24, 8, 4, 2, 0)
+            case_yamamoto_aggregator(world, golden, "updyagg_ragged_2x2_r01", 40, 40, 8, 2, 0, 1)   # ranks run out of rows: zeros, not garbage
         case_update_Yamamoto_A(world, golden, "updy_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 2, 0)
         case_update_Yamamoto_A(world, golden, "updy_big_2x2_r11", 1024, 768, 64, 2, 1, 1)
     # update_A with the panel QR's factor W (comp_bcast_T_from_W): fixtures are the reference's own outputs; the rotated roots of
@@ -563,9 +571,10 @@ def pending_cases(world, golden):
     if P == 6:
         case_update_A(world, golden, "updw_m80_k48_b8_2x3_r00", 80, 48, 8, 2, 0, 0, with_W=True)
         case_update_A(world, golden, "updw_m80_k48_b8_2x3_r12", 80, 48, 8, 2, 1, 2, with_W=True)
-    # the opt-in triangular solve with one warp per right-hand side (candmc_set_trsm_variant(1)) under the same updates: block
-    # sizes below, at and above its 32-row blocks and 128-column T tiles, ragged right-hand-side counts
-    cb.lib().candmc_set_trsm_variant(1)
+    # both triangular solves under the same updates — one warp per right-hand side (the default since round 2, already used by
+    # every case above) and round 1's kernel (candmc_set_trsm_variant(0)): block sizes below, at and above the warp kernel's
+    # 32-row blocks and 128-column T tiles, ragged right-hand-side counts
+    cb.lib().candmc_set_trsm_variant(0)
     if P == 1:
         case_update_A(world, golden, "upda_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0)
         case_update_A(world, golden, "upda_trsmw_b40_1x1", 400, 120, 40, 1, 0, 0)
@@ -578,7 +587,7 @@ def pending_cases(world, golden):
         case_update_A(world, golden, "upda_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 0, 0)
         case_update_A(world, golden, "upda_T_2x2_trsmw", 640, 480, 160, 2, 1, 1, with_T=True)
         case_update_A(world, golden, "updw_big_2x2_r10", 1024, 768, 64, 2, 1, 0, with_W=True)
-    cb.lib().candmc_set_trsm_variant(0)
+    cb.lib().candmc_set_trsm_variant(1)
     from dmat_cases import case_names, load_golden
     dgold = load_golden()
     for name in case_names(dgold):

@@ -181,7 +181,7 @@ int upload_chunks(const double* hA, int64_t lda, const double* hB, int64_t ldb, 
     return OK;
   }
   if (hB) {
-    // opt-in (candmc_set_b_first_chunk_early, not measured yet): the rows of the first k-chunk go ahead in their own 2-D copy
+    // opt-in (candmc_set_b_first_chunk_early; only reached for pageable memory or with the host gather off): the rows of the first k-chunk go ahead in their own 2-D copy
     // (narrow rows, but only 1/nchunks of B), so the first multiply does not wait for the whole block
     const int64_t k0 = (runtime().b_first_chunk_early && nchunks > 1) ? kc : 0;
     if (k0 > 0) {
@@ -321,7 +321,7 @@ int summa_sweep(SummaArgs& a) {
     return OK;
   };
 
-  // opt-in: panels by copy engines into peer windows (transport.h) instead of ncclBroadcast, per grid axis
+  // panels by copy engines into peer windows (transport.h; the default) instead of ncclBroadcast, per grid axis
   PanelTransport *tr_row = nullptr, *tr_col = nullptr;
   if (runtime().panel_transport && need_comm && (a.i1 - a.i0) * nchunks <= kPanelMaxOps) {
     if (a.row->size > 1) CANDMC_TRY(panel_transport_get(a.row, (a.i1 - a.i0) * bb, &tr_row));
@@ -957,6 +957,12 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
       CANDMC_CHECK(r != nullptr, "event pool exhausted");
       CANDMC_CUDA(cudaEventRecord(r, cs));
       CANDMC_CUDA(cudaStreamWaitEvent(d2h, r, 0));
+      // The next slab's multiply waits for this slab's depth sum.  Left to itself the all-reduce kernel only becomes eligible
+      // when the slab's GEMM has completed, by which time the next GEMM of the compute stream — eligible at the same instant,
+      // without a cross-stream event in between — owns every SM again: on 8 B200s all four slab sums and with them the whole
+      // download of C ended up BEHIND the last multiply (180 ms tail, profiles/r02_8gpu/r02_timeline8_e2e.txt).  The sum of a
+      // slab over NVLink costs the multiplies a few milliseconds in total; the download it releases is what bounds the step.
+      CANDMC_CUDA(cudaStreamWaitEvent(st, r, 0));
       CANDMC_TRY(sC.close_out_cols(bufC + c0 * b, b, c0, w, d2h));
     } else {
       CANDMC_CUDA(cudaStreamWaitEvent(d2h, e, 0));
@@ -970,7 +976,8 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   ReserveGuard gather_guard(host_gather_active ? std::max(2, runtime().gemm_reserve_sms) : runtime().gemm_reserve_sms);
   FusedCtx* fctx = nullptr;
   FusedParams fparams;
-  // (on q > 1 grids the fused path is opt-in until it has been validated on 8 GPUs: candmc_set_fused_reduce(2))
+  // (on q > 1 grids the fused path is opt-in, candmc_set_fused_reduce(2): parity-green on 8 B200s but slower there than the
+  // all-reduce it replaces — its P2P stores cost the last chunk's launch 6 ms, the all-reduce 4.6 ms)
   if (c > 1 && !slab_mode && (ksplit || runtime().fused_reduce_grids)) CANDMC_TRY(fused_ctx_get(cdt_kdir, b, &fctx));
   if (fctx) fused_params_next(fctx, layer, &fparams);
 
@@ -1094,7 +1101,7 @@ int candmc_bcast_cannon_4d(const candmc_ctb_args_t* args, const double* mat_A, c
   auto wrap = [](int a, int m) { return ((a % m) + m) % m; };
 
   if (x2_np > 1) {
-    // (opt-in) staggers and shifts by copy engines into peer windows instead of grouped ncclSend/ncclRecv: collective set-up
+    // staggers and shifts by copy engines into peer windows (the default) instead of grouped ncclSend/ncclRecv: collective set-up
     CANDMC_TRY(p2p_transport_prepare(cdt_x2, bb));
     CANDMC_TRY(p2p_transport_prepare(cdt_y2, bb));
     CANDMC_TRY(stream_wait(shift, st));
@@ -1336,7 +1343,7 @@ int candmc_spcannon(int bidir, int rank, int kary, int ndim, candmc_comm_t* worl
     if (!tB) CANDMC_TRY(transpose_f64(k, n, sB.ptr(), sB.ld(), s.B[0], n, st));
     else CANDMC_TRY(lda_copy_f64(n, k, sB.ld(), n, sB.ptr(), s.B[0], st));
   }
-  // (opt-in) every put of the stagger and the shifts by copy engines into peer windows; the largest message is a whole slice
+  // every put of the stagger and the shifts by copy engines into peer windows (the default); the largest message is a whole slice
   if (kary > 1 && k > 0) CANDMC_TRY(p2p_transport_prepare(world, 2 * std::max(mk, nk) / ndim + 2));
   CANDMC_TRY(stream_wait(s.comm, st));
   if (kary > 1 && k > 0) {

@@ -41,7 +41,7 @@ struct Runtime {
   bool fused_reduce_grids = false;      // ... also on q x q x c grids (validated so far on 1 x 1 x c only)
   bool skip_unused_uploads = true;      // host operands: a layer's rank uploads only the blocks its panels use (candmc_set_skip_unused_uploads)
   bool panel_transport = true;          // SUMMA panels and Cannon shifts by copy engines into peer windows instead of NCCL kernels (transport.h)
-  bool b_first_chunk_early = false;     // host B: upload the first k-chunk's rows ahead of the rest (opt-in until measured)
+  bool b_first_chunk_early = false;     // pageable host B: upload the first k-chunk's rows ahead of the rest (opt-in)
   bool early_c_download = true;         // host C: finalise + download column slabs under the last multiplies (candmc_set_early_c_download)
   bool fused_reduce = true;             // depth all-reduce fused into the last GEMM's epilogue over peer memory
   bool host_gather = true;              // pinned host B blocks: k-chunks gathered straight out of host memory by the pack kernel (candmc_set_host_gather)

@@ -1,9 +1,11 @@
 #!/bin/bash
 # Round-2 GPU sessions (one gpurun call each; everything lands in gpurun_out/r02_*).  Sections are independent and each
 # step has its own timeout, so a hang costs minutes, not the call.
-#   gpurun --timeout 1500 -- 'bash tools/r02_session.sh probe ncu1 f32 tests bench1'        (1 GPU)
-#   gpurun --gpus 4 --timeout 900 -- 'bash tools/r02_session.sh parity4 bench4'              (4 GPUs)
-#   gpurun --gpus 8 --timeout 700 -- 'bash tools/r02_session.sh parity8 bench8'              (8 GPUs)
+#   gpurun --timeout 1800 -- 'bash tools/r02_session.sh probe ncu1 f32 tests bench1 lu'     (session 1)
+#   gpurun --timeout 900  -- 'bash tools/r02_session.sh pack'                                (session 2)
+#   gpurun --timeout 900  -- 'bash tools/r02_session.sh tile'                                (session 4)
+# The 4- and 8-GPU sessions are tools/r02_multi.py.  Keep gpurun_out/ under 64 MiB or nothing travels back (ncu_full
+# deletes reports over 6 MB after summarising them).
 set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out
@@ -86,45 +88,6 @@ for section in "$@"; do
     pending1)
       timeout 600 python tools/bench_configs.py --pending > $O/r02_bench_pending_1gpu.jsonl 2> $O/r02_bench_pending_1gpu.err
       cut -c1-400 $O/r02_bench_pending_1gpu.jsonl; tail -3 $O/r02_bench_pending_1gpu.err
-      ;;
-    parity)
-      # the parity workers at HEAD on every GPU of the box: library defaults, pending group, merged launches, peer-memory paths
-      CANDMC_TEST_VERBOSE=1 timeout 500 bash -c "$(declare -f trun); NG=$NG; trun 29533 tests/dist_worker.py" > $O/r02_parity_${NG}gpus.log 2>&1
-      tail -4 $O/r02_parity_${NG}gpus.log | cut -c1-400
-      CANDMC_TEST_PENDING=1 timeout 400 bash -c "$(declare -f trun); NG=$NG; trun 29535 tests/dist_worker.py" > $O/r02_parity_pending_${NG}gpus.log 2>&1
-      tail -3 $O/r02_parity_pending_${NG}gpus.log | cut -c1-400
-      ;;
-    parity_knobs)
-      CANDMC_TEST_MERGE_PANELS=2 CANDMC_TEST_PANEL_TRANSPORT=1 CANDMC_TEST_FUSED_GRIDS=1 timeout 400 bash -c "$(declare -f trun); NG=$NG; trun 29542 tests/dist_worker.py" > $O/r02_parity_knobs_${NG}gpus.log 2>&1
-      tail -3 $O/r02_parity_knobs_${NG}gpus.log | cut -c1-400
-      ;;
-    dropin)
-      timeout 400 python -m pytest tests/test_dropin_gpu.py -m gpu -q -rA -p no:cacheprovider > $O/r02_dropin_${NG}gpus.log 2>&1
-      tail -12 $O/r02_dropin_${NG}gpus.log | cut -c1-200
-      ;;
-    benchN)
-      # headline grid on this box: default, then the knobs one at a time (device-resident leg only), timeline of rank 0
-      for knobs in "" "--merge-panels 2" "--panel-transport" "--merge-panels 2 --panel-transport" "--merge-panels 2 --panel-transport --fused-reduce 2"; do
-        tag=$(echo "default $knobs" | tr -s ' -' '_')
-        echo "== bench $NG GPUs --no-e2e $knobs"
-        timeout 200 bash -c "$(declare -f trun); NG=$NG; trun 29543 bench.py --gpus $NG --steps 4 --warmup 3 --no-e2e --timeline $knobs" \
-          > $O/r02_bench${NG}_$tag.json 2> $O/r02_bench${NG}_$tag.err
-        cut -c1-120 $O/r02_bench${NG}_$tag.json; grep -o '"exposed_non_gemm_pct": [0-9.]*' $O/r02_bench${NG}_$tag.json
-        grep -o '"avg_launch_ms": [0-9.]*' $O/r02_bench${NG}_$tag.json
-        grep -A12 "GEMM timeline" $O/r02_bench${NG}_$tag.err | head -14
-      done
-      ;;
-    e2eN)
-      for knobs in "" ; do
-        echo "== bench $NG GPUs (with e2e) $knobs"
-        timeout 400 bash -c "$(declare -f trun); NG=$NG; trun 29537 bench.py --gpus $NG --steps 4 --warmup 3 $knobs" \
-          > $O/r02_bench${NG}_e2e.json 2> $O/r02_bench${NG}_e2e.err
-        cut -c1-2500 $O/r02_bench${NG}_e2e.json
-      done
-      ;;
-    configsN)
-      timeout 500 bash -c "$(declare -f trun); NG=$NG; trun 29544 tools/bench_configs.py" > $O/r02_configs_${NG}gpus.jsonl 2> $O/r02_configs_${NG}gpus.err
-      cut -c1-500 $O/r02_configs_${NG}gpus.jsonl; tail -3 $O/r02_configs_${NG}gpus.err
       ;;
     *) echo "unknown section $section";;
   esac

@@ -854,8 +854,7 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   const bool ksplit = (q == 1 && c > 1);  // extension: 1 x 1 x c grid splits k; the reference asserts q % c == 0
   CANDMC_CHECK(ksplit || q % c == 0, "d25_summa: grid dimension %d not divisible by replication factor %d", q,
                c);  // ASSERT(np_row % c_rep == 0), d25_summa.cxx:63
-  CANDMC_CHECK(!ksplit || (b % c == 0 && is_n(args->trans_A) && is_n(args->trans_B)),
-               "d25_summa (1x1xc k-split): n must be divisible by c and the operands untransposed");
+  CANDMC_CHECK(!ksplit || b % c == 0, "d25_summa (1x1xc k-split): n must be divisible by c");
   const int64_t need = (ovp ? 5 : 3) * b * b * (int64_t)sizeof(double);  // buffer_space_req, d25_summa.cxx:25-31
   CANDMC_CHECK(buffer == nullptr || args->buffer_size >= need, "d25_summa: buffer_size %lld < %lld",
                (long long)args->buffer_size, (long long)need);
@@ -916,8 +915,11 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   } else {
     CANDMC_TRY(sA.open(mat_A, b, b, args->lda_A, true, st));
     CANDMC_TRY(sB.open(mat_B, b, b, args->lda_B, true, st));
-    if (useA) { dA_ptr = sA.ptr() + (ksplit ? layer * kloc * sA.ld() : 0); dA_ld = sA.ld(); }
-    if (useB) { dB_ptr = sB.ptr() + (ksplit ? layer * kloc : 0); dB_ld = sB.ld(); }
+    // my k-slice of the stored operands: columns of A / rows of B, the other way round where an operand is transposed
+    const int64_t offA = !ksplit ? 0 : (is_t(args->trans_A) ? layer * kloc : layer * kloc * sA.ld());
+    const int64_t offB = !ksplit ? 0 : (is_t(args->trans_B) ? layer * kloc * sB.ld() : layer * kloc);
+    if (useA) { dA_ptr = sA.ptr() + offA; dA_ld = sA.ld(); }
+    if (useB) { dB_ptr = sB.ptr() + offB; dB_ld = sB.ld(); }
   }
   CANDMC_TRY(sC.open(mat_C, b, b, args->lda_C, false, st));
   void* wsv = nullptr;
@@ -1009,7 +1011,7 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
       for (int u = 0; u < mg; ++u) CANDMC_TRY(operands(t + u, &pa[u], &lda[u], &pb[u], &ldb[u]));
       const bool fused_here = fctx != nullptr && t + mg == nch;
       GroupLaunch gl;
-      gl.tA = 'N'; gl.tB = 'N'; gl.b = b; gl.kc = kc; gl.C = Cpart; gl.ldC = ldCpart; gl.compute = st;
+      gl.tA = args->trans_A; gl.tB = args->trans_B; gl.b = b; gl.kc = kc; gl.C = Cpart; gl.ldC = ldCpart; gl.compute = st;
       gl.fused = fused_here ? &fparams : nullptr; gl.fused_out = sC.ptr(); gl.fused_ldout = sC.ld();
       gl.scratchA = scratch; gl.scratchB = scratch + b * kc + (b * kc & 1);
       CANDMC_TRY(multiply_group(gl, mg, pa, lda, pb, ldb, t ? 1.0 : 0.0, (!slab_w.empty() && t == last_group_lo) ? &slab_w : nullptr,

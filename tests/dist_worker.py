@@ -78,7 +78,7 @@ def free_shared_grids():
     _GRIDS.clear()
 
 
-def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_golden=True, oracle=True, grid=None):
+def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_golden=True, oracle=True, grid=None, trans=("N", "N")):
     g = grid if grid is not None else shared_grid(world, "d25", c)
     q = g["q"]
     b = n // q
@@ -89,7 +89,13 @@ def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_go
     A = np.zeros((ld, b), order="F"); B = np.zeros((ld, b), order="F")
     A[:b] = orc.unit_block(b, b, row0, col0, n, 0)
     B[:b] = orc.unit_block(b, b, row0, col0, n, 1)
-    args = cb.ctb_args_t(n=n, lda_A=ld, lda_B=ld, lda_C=b, buffer_size=5 * b * b * 8)
+    if trans != ("N", "N"):   # the k-split of a 1 x 1 x c grid with stored transposes: op(stored) is the same operand, so is C
+        assert q == 1 and c > 1
+        if trans[0] == "T":
+            A[:b] = A[:b].T.copy()
+        if trans[1] == "T":
+            B[:b] = B[:b].T.copy()
+    args = cb.ctb_args_t(n=n, lda_A=ld, lda_B=ld, lda_C=b, buffer_size=5 * b * b * 8, trans_A=trans[0], trans_B=trans[1])
     fn = cb.d25_summa_ovp if ovp else cb.d25_summa
     if use_host == "pinned":
         # page-locked host blocks (what bench.py's end-to-end leg passes): B's k-chunks are gathered straight out of host
@@ -760,6 +766,12 @@ def main():
             case_d25(world, golden, f"d25_ksplit_fused_n512_{tag}", 512, 2, 0)
             case_d25(world, golden, f"d25_ksplit_fused_n256_pad_{tag}", 256, 2, 0, lda_pad=3)
             case_d25(world, golden, f"d25_ksplit_fused_n768_again_{tag}", 768, 2, 1)
+            # transposed operands on the k-split (refused until round 2): every combination through the fused epilogue, one
+            # with padded leading dimensions, one with host operands (staged whole, depth sum by NCCL when C is a host block)
+            for tr in (("T", "N"), ("N", "T"), ("T", "T")):
+                case_d25(world, golden, f"d25_ksplit_{tr[0]}{tr[1]}_n512_{tag}", 512, 2, 0, trans=tr, check_golden=False, oracle=False)
+            case_d25(world, golden, f"d25_ksplit_TN_n256_pad_{tag}", 256, 2, 0, lda_pad=3, trans=("T", "N"), check_golden=False, oracle=False)
+            case_d25(world, golden, f"d25_ksplit_NT_n96_host_{tag}", 96, 2, 0, use_host=True, trans=("N", "T"), check_golden=False, oracle=False)
             cb.lib().candmc_set_fused_reduce(0)
             case_d25(world, golden, f"d25_ksplit_nccl_n512_{tag}", 512, 2, 0)
             cb.lib().candmc_set_fused_reduce(1)

@@ -334,8 +334,12 @@ int summa_sweep(SummaArgs& a) {
   // NCCL moves data with SM-resident kernels, and the persistent GEMM owns every SM it is given (all registers, 193 KiB
   // smem), so a broadcast enqueued while a GEMM runs would only start when that GEMM ends.  While panels are in flight
   // the GEMMs therefore leave as many SMs free as the background communicators may use.
-  ReserveGuard reserve_guard((need_comm && !all_dma) ? std::max(runtime().bg_max_ctas, runtime().gemm_reserve_sms)
-                                                     : runtime().gemm_reserve_sms);
+  // (NCCL path with launch groups — the fallback when peer windows are unavailable: a merged launch needs the rest of its panel
+  // within one chunk's multiply, which the 2-CTA background communicators cannot deliver (127 TFLOP/s on 4 B200s); the
+  // full-width communicators between the launches can, with no SM held back: 138 TFLOP/s, profiles/r02_4gpu/ "bgctas_0")
+  const bool nccl_full_width = need_comm && !all_dma && runtime().merge_panels == 2;
+  ReserveGuard reserve_guard((need_comm && !all_dma && !nccl_full_width) ? std::max(runtime().bg_max_ctas, runtime().gemm_reserve_sms)
+                                                                         : runtime().gemm_reserve_sms);
   std::vector<cudaEvent_t> done_prev(nchunks, nullptr);
   bool first = a.first_beta_zero;
   // Operands that are already on the device are packed for sending BEFORE the first multiply is enqueued (A out of its
@@ -356,7 +360,8 @@ int summa_sweep(SummaArgs& a) {
     // ---- communication for panel i, chunk by chunk, on the comm stream ----
     if (need_comm) {
       for (int t = 0; t < nchunks; ++t) {
-        const bool bg = !(i == a.i0 && t == 0);  // the very first chunk has nothing to hide under: full-width communicator
+        // the very first chunk has nothing to hide under: full-width communicator (as is everything when launches are merged)
+        const bool bg = !(i == a.i0 && t == 0) && !nccl_full_width;
         // buf slot t is free again (the copy-engine transport gives every panel and chunk of a sweep its own window slot)
         if (done_prev[t] && !all_dma) CANDMC_CUDA(cudaStreamWaitEvent(comm, done_prev[t], 0));
         const int op = (i - a.i0) * nchunks + t;   // transport slot of this (panel, chunk): its own, never reused in a sweep

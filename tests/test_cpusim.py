@@ -59,6 +59,9 @@ for _n in DIST_MAIN:     # longest first.  On 8 ranks the fused GEMM + depth all
 # opt-in fused depth sum, on 2x2x2 — deferred streams, LIFO order; and round 1's path (NCCL kernels, one launch per k-chunk)
 _job("nccl4", _torchrun(4, 29747, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_NCCL_PANELS="1",
      CPUSIM_SCHED="lifo")
+# ... and the automatic fallback when peer windows are unavailable: NCCL panels (full-width communicators) under the launch groups
+_job("ncclmerge4", _torchrun(4, 29748, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_PANEL_TRANSPORT="0",
+     CPUSIM_SCHED="random:31")
 # (the copy-engine transport and launch groups of mode 2 ARE main4 / main8 since round 2 — and main4@lifo / main8@random below)
 # opt-in: the last panel of a sweep multiplied in one launch over its k-chunks (B read chunk-major through one tensor map by the
 # product's own kernel on the PTX emulation); the validated 2x2 suite with the switch on
@@ -326,6 +329,8 @@ def test_nccl_panels_and_per_chunk_launches_on_the_simulator():
     fallback when peer windows are unavailable: ncclBroadcast panels on the capped communicators, one launch per k-chunk"""
     out = _dist("nccl4")
     assert out["panel_transport_sends_rank0"] == 0 and out["merged_panel_launches_all_ranks"] == [0, 0]
+    out = _dist("ncclmerge4")   # the fallback of the default schedule: launch groups fed by ncclBroadcast
+    assert out["panel_transport_sends_rank0"] == 0 and out["merged_panel_launches_all_ranks"][0] > 0
 
 
 @pytest.mark.parametrize("job", ["merge4", "main4", "merge4_doubling", "main8"])

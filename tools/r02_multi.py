@@ -1,16 +1,21 @@
 #!/usr/bin/env python
-"""Round-2 multi-GPU session (one gpurun call on N = 4 or 8 GPUs; every minute is charged N times, so the order is: the
+"""Round-2 multi-GPU sessions (one gpurun call on N = 4 or 8 GPUs; every minute is charged N times, so the order is: the
 measurement that decides the defaults first, parity of the winner second, everything else after).
 
-  gpurun --gpus 4 --timeout 900 -- 'python tools/r02_multi.py'
-  gpurun --gpus 8 --timeout 700 -- 'python tools/r02_multi.py'
-
-1. bench.py (device-resident leg, per-launch timeline of rank 0) with the library defaults and with each candidate set of
-   schedule knobs; the fastest valid line wins.
-2. tests/dist_worker.py (parity against the oracle and the reference's golden outputs) with the winner's knobs, then its
-   pending group, then the reference's own unmodified test mains as drop-ins.
-3. bench.py with the end-to-end leg and tools/bench_configs.py (BASELINE configs 2 / 4 / 5 with result checks), winner's knobs.
-Everything goes to gpurun_out/r02_*_{N}gpus*; stdout carries a summary."""
+  gpurun --gpus 4 --timeout 1000 -- 'python tools/r02_multi.py'                                   (session 3: knob A/B, 46 GPU-min)
+  gpurun --gpus 4 --timeout 900  -- 'python tools/r02_multi.py bench e2e parity configs'          (session 5: shipped defaults, 33)
+  gpurun --gpus 8 --timeout 800  -- 'python tools/r02_multi.py bench e2e parity dropin configs'   (session 6: 86 — `parity`
+                                                                                                   includes the pending group: 4 min x 8)
+Stages (all by default, or the ones named on the command line):
+  bench    bench.py, device-resident leg with rank 0's per-launch timeline, at the library defaults and with each candidate
+           set of knobs (session 3: merge-panels / panel-transport / bg-ctas combinations; later: fused-reduce 2 on 8 GPUs);
+           the fastest valid line wins and its knobs are handed to the later stages
+  parity   tests/dist_worker.py (oracle + the reference's golden outputs), then its pending group (widening rows)
+  dropin   the reference's own unmodified test mains under tools/candmc_run (tests/test_dropin_gpu.py)
+  e2e      bench.py with the end-to-end leg (both passes) and timelines of the end-to-end steps
+  configs  tools/bench_configs.py: BASELINE configs 2 / 4 / 5 with result checks
+Everything goes to gpurun_out/r02_*_{N}gpus*; stdout carries a summary.  R02_SIM=<ranks> dry-runs the script's own logic on
+the CPU simulator (numbers of such a run mean nothing)."""
 import json
 import os
 import subprocess

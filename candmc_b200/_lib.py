@@ -64,6 +64,8 @@ SIGNATURES = {
     "candmc_set_early_c_download": (C.c_int, [C.c_int]),
     "candmc_set_panel_transport": (C.c_int, [C.c_int]),
     "candmc_set_host_gather": (C.c_int, [C.c_int]),
+    "candmc_debug_launch_groups": (C.c_int, [C.c_int] * 8 + [C.POINTER(C.c_int)]),
+    "candmc_debug_fin_slab_widths": (C.c_int, [i64, C.c_int, C.POINTER(i64), C.c_int, C.POINTER(C.c_int)]),
     "candmc_panel_transport_sends": (C.c_ulonglong, []),
     "candmc_merged_panel_launches": (C.c_ulonglong, [C.c_int]),
     "candmc_set_b_first_chunk_early": (C.c_int, [C.c_int]),

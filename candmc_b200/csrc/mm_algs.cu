@@ -294,6 +294,29 @@ void host_upload_groups(int nchunks, int lim, std::vector<int>* grp_hi) {
   }
 }
 
+// Which k-chunks of a panel go into one launch (summa_sweep has the reasoning): grp_hi[t] = end of the group that starts at
+// chunk t.  Pure arithmetic, exposed to the tests as candmc_debug_launch_groups.
+void plan_launch_groups(int nchunks, int mode, bool first_panel, bool last_panel, bool host_ops, bool all_dma, bool fused, bool nn,
+                        std::vector<int>* grp_hi) {
+  grp_hi->resize(nchunks);
+  for (int t = 0; t < nchunks; ++t) (*grp_hi)[t] = t + 1;
+  if (mode <= 0 || nchunks <= 2 || !nn) return;
+  const int lim = (last_panel && fused) ? nchunks - 1 : nchunks;   // the fused depth sum's chunk keeps its own launch
+  if (mode == 2) {
+    if (first_panel && host_ops) {
+      host_upload_groups(nchunks, lim, grp_hi);
+    } else if (!first_panel && all_dma) {
+      (*grp_hi)[0] = lim;
+    } else if (lim > 1) {
+      (*grp_hi)[1] = lim;
+    }
+  } else if (mode == 3 && !host_ops) {
+    for (int lo = 2, sz = 2; lo < lim; lo += sz, sz *= 2) (*grp_hi)[lo] = std::min(lim, lo + sz);
+  } else if (mode == 1 && !host_ops && last_panel && !first_panel && !fused) {
+    (*grp_hi)[0] = nchunks - 1;
+  }
+}
+
 // column slabs a b-wide C block is finalised in: graduated b/2, b/4, b/8, b/8 (the wide first slab has the rest of the multiply
 // to leave under, only the narrow last one is exposed), equal slabs when b does not divide that way, none when it is too ragged
 std::vector<int64_t> fin_slab_widths(int64_t b, int fin_slabs) {
@@ -443,25 +466,8 @@ int summa_sweep(SummaArgs& a) {
     const bool last_panel = (i + 1 == a.i1), first_panel = (i == a.i0);
     const bool host_ops = (a.a_ready != nullptr || a.b_ready != nullptr);
     const bool nn = is_n(a.tA) && is_n(a.tB);
-    std::vector<int> grp_hi(nchunks);   // chunks [t, grp_hi[t]) go in one launch when t starts a group
-    for (int t = 0; t < nchunks; ++t) grp_hi[t] = t + 1;
-    const int mode = runtime().merge_panels;
-    if (mode > 0 && nchunks > 2 && nn) {
-      const int lim = (last_panel && a.fused != nullptr) ? nchunks - 1 : nchunks;
-      if (mode == 2) {
-        if (first_panel && host_ops) {
-          host_upload_groups(nchunks, lim, &grp_hi);
-        } else if (!first_panel && all_dma) {
-          grp_hi[0] = lim;
-        } else if (lim > 1) {
-          grp_hi[1] = lim;
-        }
-      } else if (mode == 3 && !host_ops) {
-        for (int lo = 2, sz = 2; lo < lim; lo += sz, sz *= 2) grp_hi[lo] = std::min(lim, lo + sz);
-      } else if (mode == 1 && !host_ops && last_panel && !first_panel && a.fused == nullptr) {
-        grp_hi[0] = nchunks - 1;
-      }
-    }
+    std::vector<int> grp_hi;   // chunks [t, grp_hi[t]) go in one launch when t starts a group
+    plan_launch_groups(nchunks, runtime().merge_panels, first_panel, last_panel, host_ops, all_dma, a.fused != nullptr, nn, &grp_hi);
     // Early finalisation (host C): the LAST launch group of the sweep is cut into column slabs — each slab still covers all of
     // the group's k, so it is a handful of large launches, not one per chunk and slab — and slab_done() ships a slab (depth
     // sum, download) while the next ones multiply.  Graduated widths b/2, b/4, b/8, b/8: the wide first slab has the rest of
@@ -753,6 +759,24 @@ int trsm_llnn(int64_t b, int64_t kb, const double* T, int64_t ldt, double* W, in
 using namespace candmc;
 
 extern "C" {
+
+int candmc_debug_launch_groups(int nchunks, int mode, int first_panel, int last_panel, int host_ops, int all_dma, int fused, int nn,
+                               int* grp_hi) {
+  CANDMC_CHECK(nchunks >= 1 && nchunks <= 64 && grp_hi != nullptr, "candmc_debug_launch_groups: bad arguments");
+  std::vector<int> g;
+  plan_launch_groups(nchunks, mode, first_panel != 0, last_panel != 0, host_ops != 0, all_dma != 0, fused != 0, nn != 0, &g);
+  std::copy(g.begin(), g.end(), grp_hi);
+  return OK;
+}
+
+int candmc_debug_fin_slab_widths(int64_t b, int fin_slabs, int64_t* widths, int cap, int* count) {
+  CANDMC_CHECK(widths != nullptr && count != nullptr, "candmc_debug_fin_slab_widths: null output");
+  const std::vector<int64_t> w = fin_slab_widths(b, fin_slabs);
+  CANDMC_CHECK((int)w.size() <= cap, "candmc_debug_fin_slab_widths: %zu slabs do not fit", w.size());
+  std::copy(w.begin(), w.end(), widths);
+  *count = (int)w.size();
+  return OK;
+}
 
 int candmc_set_host_gather(int on) {
   runtime().host_gather = (on != 0);

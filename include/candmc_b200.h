@@ -60,6 +60,12 @@ int candmc_set_skip_unused_uploads(int on);
  * b/8, b/8 columns (each still over all of the group's k), each slab is summed over the depth and downloaded while the next
  * ones multiply; 0 = one download at the end. */
 int candmc_set_early_c_download(int on);
+/* Test hooks (pure host arithmetic, no device needed): the launch groups a sweep cuts a panel's k-chunks into — grp_hi[t] = end
+ * of the group that starts at chunk t (mode = candmc_set_merge_panels' value) — and the column slabs a host C block is
+ * finalised in (candmc_set_early_c_download; fin_slabs = 8 / 4 / 2 equal slabs is the fallback when b is not a multiple of 1024). */
+int candmc_debug_launch_groups(int nchunks, int mode, int first_panel, int last_panel, int host_ops, int all_dma, int fused, int nn,
+                               int* grp_hi);
+int candmc_debug_fin_slab_widths(int64_t b, int fin_slabs, int64_t* widths, int cap, int* count);
 /* Pinned (page-locked) host B blocks on grids: 1 (default) = every k-chunk is gathered straight out of host memory by the pack
  * kernel — coalesced reads over PCIe, chunk-major on arrival — so the first multiply starts after 1/8 of the block instead
  * of after all of it; 0 = one copy of the whole block, re-laid out on the device (also what pageable memory gets). */

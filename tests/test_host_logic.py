@@ -142,3 +142,58 @@ def test_host_pipeline_cut_covers_the_product_exactly(n, k, panels):
     assert len(w) <= 70 and len(c) <= 70
     if panels < 0 and n >= 2048:   # graduated: the last panel is at most an eighth of the first (+ the ragged rest)
         assert w[-1] <= max(w) // 4 + 255 and c[0] <= k // 16 + 16
+
+
+def _groups(nchunks, mode, first, last, host_ops, all_dma, fused, nn=True):
+    import ctypes as C
+
+    from candmc_b200._lib import lib
+
+    out = (C.c_int * nchunks)()
+    assert lib().candmc_debug_launch_groups(nchunks, mode, int(first), int(last), int(host_ops), int(all_dma), int(fused), int(nn), out) == 0
+    hi, t, groups = list(out), 0, []
+    while t < nchunks:
+        assert t < hi[t] <= nchunks, (t, hi)
+        groups.append((t, hi[t]))
+        t = hi[t]
+    return groups
+
+
+def test_launch_groups_partition_the_chunks_and_keep_the_fused_chunk_apart():
+    """summa_sweep's launch plan for every combination of its inputs: the groups partition [0, nchunks) in order,
+    the chunk whose launch carries the fused depth sum is always alone, and the shapes the defaults ship are the documented ones"""
+    import itertools
+
+    for nchunks, mode, first, last, host_ops, all_dma, fused, nn in itertools.product(
+            (1, 2, 3, 4, 8), (0, 1, 2, 3), (0, 1), (0, 1), (0, 1), (0, 1), (0, 1), (0, 1)):
+        g = _groups(nchunks, mode, first, last, host_ops, all_dma, fused, nn)
+        assert g[0][0] == 0 and g[-1][1] == nchunks and all(a[1] == b[0] for a, b in zip(g, g[1:]))
+        if fused and last:
+            assert g[-1] == (nchunks - 1, nchunks)
+        if mode == 0 or not nn or nchunks <= 2:
+            assert g == [(t, t + 1) for t in range(nchunks)]
+    # the default (mode 2) on device operands by copy engines: chunk 0 + the rest on the first panel, one launch per later panel
+    assert _groups(8, 2, True, False, False, True, False) == [(0, 1), (1, 8)]
+    assert _groups(8, 2, False, True, False, True, False) == [(0, 8)]
+    assert _groups(8, 2, True, True, False, True, True) == [(0, 1), (1, 7), (7, 8)]      # 2x2x2 with the fused depth sum
+    # ... on the NCCL path the chunks' buffer slots come back launch by launch: chunk 0 + the rest for every panel
+    assert _groups(8, 2, False, True, False, False, False) == [(0, 1), (1, 8)]
+    # ... and while operands are still coming up from host memory: chunk 0, chunks 1-2, the rest
+    assert _groups(8, 2, True, True, True, True, False) == [(0, 1), (1, 3), (3, 8)]
+    assert _groups(4, 2, True, True, True, True, False) == [(0, 1), (1, 3), (3, 4)]
+    assert _groups(8, 3, True, True, False, True, False) == [(0, 1), (1, 2), (2, 4), (4, 8)]   # doubling groups
+    assert _groups(8, 1, False, True, False, True, False) == [(0, 7), (7, 8)]                  # last panel only
+
+
+def test_early_c_slabs_cover_the_block():
+    """the column slabs a host C block is finalised in: graduated b/2, b/4, b/8, b/8 where b allows, equal slabs otherwise"""
+    import ctypes as C
+
+    from candmc_b200._lib import lib
+
+    for b, fin, want in ((16384, 8, [8192, 4096, 2048, 2048]), (1024, 8, [512, 256, 128, 128]), (512, 4, [128] * 4),
+                         (768, 2, [384, 384]), (2048, 0, []), (2048, 1, [])):
+        w, cnt = (C.c_int64 * 16)(), C.c_int()
+        assert lib().candmc_debug_fin_slab_widths(b, fin, w, 16, C.byref(cnt)) == 0
+        got = list(w)[:cnt.value]
+        assert got == want and (not got or sum(got) == b), (b, fin, got)

@@ -40,6 +40,7 @@ def main():
         kind = rng.choice(kinds)
         cb.set_min_kchunk(rng.choice([1024, 8, 2, 16]))
         cb.lib().candmc_set_merge_panels(rng.choice([0, 1, 2, 3]))
+        cb.lib().candmc_set_panel_transport(rng.choice([1, 1, 0]))   # copy engines (the default) or the NCCL fallback; same on every rank
         pad = rng.choice([0, 0, 1, 2, 3])
         tag = f"fz{seed}.{it}.{kind}"
         if kind == "d25":

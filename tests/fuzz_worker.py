@@ -57,9 +57,13 @@ def main():
                 cb.lib().candmc_set_early_c_download(rng.choice([0, 1]))
                 cb.lib().candmc_set_skip_unused_uploads(rng.choice([0, 1]))
                 cb.lib().candmc_set_b_first_chunk_early(rng.choice([0, 1]))
+                cb.lib().candmc_set_host_gather(rng.choice([0, 1, 1]))
+                if rng.random() < 0.5:
+                    host = "pinned"   # page-locked blocks: B gathered chunk-wise out of host memory (where the chunking allows)
             log.append((tag, dict(n=b * q, c=c, pad=pad, host=host)))
             dw.case_d25(world, golden, tag, b * q, c, rng.choice([0, 1]), lda_pad=pad, use_host=host, check_golden=False)
             cb.lib().candmc_set_host_pipeline_min(2048); cb.lib().candmc_set_early_c_download(1); cb.lib().candmc_set_skip_unused_uploads(1)
+            cb.lib().candmc_set_host_gather(1)
             cb.lib().candmc_set_b_first_chunk_early(0)
         elif kind == "summa":
             q = int(round(P ** 0.5))

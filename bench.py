@@ -513,7 +513,9 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"d25_summa FP64 n={n} on a {q}x{q}x{c} grid (block b={b}"
                                    f"{', k split over depth' if ksplit else ''}); one step = one multiply",
-                       "n": n, "grid": [q, q, c], "block": b, "l2": "inputs larger than L2 (each operand block >= 2 GiB)",
+                       "n": n, "grid": [q, q, c], "block": b,
+                       "l2": (f"inputs larger than L2 (each operand block {8 * b * b / 2**30:.3g} GiB vs 126 MB)" if 8 * b * b > 126e6
+                              else f"NOT larger than L2 (operand block {8 * b * b / 2**20:.3g} MiB): a reduced --n run, no bench value"),
                        "generator": "reference unit-test drand48 per-element (test/MM/topo_pdgemm_unit.cxx:250-256)",
                        "cpu_binding_rank0": numa},
             "pct_of_roofline": 100.0 * value / (2.0 * n ** 3 / t_roof / 1e12),

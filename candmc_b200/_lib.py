@@ -61,6 +61,7 @@ SIGNATURES = {
     "candmc_debug_gemm_reserve_sms": (C.c_int, [C.c_int]),
     "candmc_set_fused_reduce": (C.c_int, [C.c_int]),
     "candmc_set_skip_unused_uploads": (C.c_int, [C.c_int]),
+    "candmc_set_check_peer_args": (C.c_int, [C.c_int]),
     "candmc_set_early_c_download": (C.c_int, [C.c_int]),
     "candmc_set_panel_transport": (C.c_int, [C.c_int]),
     "candmc_set_host_gather": (C.c_int, [C.c_int]),

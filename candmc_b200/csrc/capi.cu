@@ -54,6 +54,11 @@ int candmc_set_skip_unused_uploads(int on) {
   return OK;
 }
 
+int candmc_set_check_peer_args(int on) {
+  runtime().check_peer_args = (on != 0);
+  return OK;
+}
+
 int candmc_debug_splitk(int on) {
   runtime().splitk = (on != 0);
   return OK;

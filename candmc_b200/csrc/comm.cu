@@ -66,6 +66,21 @@ int comm_allreduce(candmc_comm* c, const double* send, double* recv, int64_t cou
   return OK;
 }
 
+int comm_flags_agree(candmc_comm* c, int flag, bool* agree, cudaStream_t st) {
+  CANDMC_CHECK(c != nullptr && agree != nullptr, "flags_agree: null argument");
+  *agree = true;
+  if (c->size == 1) return OK;
+  static double* dev = nullptr;   // one process-lifetime scratch word (calls are collective and serialised by the sync below)
+  if (!dev) CANDMC_CUDA(cudaMalloc(&dev, sizeof(double)));
+  double v = flag ? 1.0 : 0.0;
+  CANDMC_CUDA(cudaMemcpyAsync(dev, &v, sizeof(double), cudaMemcpyHostToDevice, st));
+  CANDMC_NCCL(ncclAllReduce(dev, dev, 1, ncclDouble, ncclSum, c->nccl, st));
+  CANDMC_CUDA(cudaMemcpyAsync(&v, dev, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CANDMC_CUDA(cudaStreamSynchronize(st));
+  *agree = (v == 0.0 || v == static_cast<double>(c->size));
+  return OK;
+}
+
 int comm_sendrecv(candmc_comm* c, const double* send, int64_t scount, int dst, double* recv, int64_t rcount, int src,
                   cudaStream_t st, bool background) {
   CANDMC_CHECK(c != nullptr, "sendrecv: null communicator");

@@ -40,6 +40,8 @@ int comm_background(candmc_comm* c, ncclComm_t* out);
 // thin wrappers, device pointers only, size-1 communicators short-circuit (no NCCL call)
 int comm_bcast(candmc_comm* c, const double* send, double* recv, int64_t count, int root, cudaStream_t st,
                bool background = false);
+// Do all ranks of `c` hold the same 0/1 `flag`?  One 8-byte all-reduce on `st` and a synchronisation of `st`; collective.
+int comm_flags_agree(candmc_comm* c, int flag, bool* agree, cudaStream_t st);
 int comm_allreduce(candmc_comm* c, const double* send, double* recv, int64_t count, cudaStream_t st,
                    bool background = false);
 // grouped point-to-point exchange: send `scount` doubles to `dst`, receive `rcount` from `src` (either may be

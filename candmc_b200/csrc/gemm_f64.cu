@@ -726,7 +726,11 @@ int gemm_f64_ex(char transa, char transb, int64_t m, int64_t n, int64_t k, doubl
       CANDMC_TRY(encode_tmap_f64(&tmB, B, BKm ? k : n, BKm ? n : k, ldb, 16, BKm ? tbn : 16));
     }
     const int kc = static_cast<int>(b_kc), cs = static_cast<int>(b_cs);
-    if (fused) return launch_tma_layouts<true, 128>(AK, BKm, tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, kc, cs, 1);
+    if (fused) {
+      CANDMC_TRY((launch_tma_layouts<true, 128>(AK, BKm, tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, fused, kc, cs, 1)));
+      runtime().fused_launches++;   // the epoch this launch belongs to is now in flight (FusedEpochGuard, ipc.h)
+      return OK;
+    }
     if (tbn == 64) return launch_tma_layouts<false, 64>(AK, BKm, tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr, kc, cs, ksplit);
     return launch_tma_layouts<false, 128>(AK, BKm, tmA, tmB, C, ldc, M, N, K, alpha, beta, stream, nullptr, kc, cs, ksplit);
   }

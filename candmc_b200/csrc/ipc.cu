@@ -35,21 +35,35 @@ int window_create(candmc_comm* c, size_t bytes, PeerWindow** out) {
   rec.ok = ok;
   rec.h = mine;
   std::vector<Rec> all(c->size);
+  // Both exchanges below are collective: a rank whose local CUDA call fails must still take part in them (with ok = 0), or
+  // its peers would wait in the all-gather for good.  Only an NCCL error — the communicator itself is broken — returns early.
+  cudaStream_t st = runtime().comm_stream;
+  auto gather = [&](const void* mine_rec, void* all_recs, size_t rec_bytes, bool* local_ok) -> int {
+    char *ds = nullptr, *dr = nullptr;
+    bool good = cudaMalloc(&ds, rec_bytes) == cudaSuccess && cudaMalloc(&dr, rec_bytes * c->size) == cudaSuccess;
+    good = good && cudaMemcpyAsync(ds, mine_rec, rec_bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    int rc = OK;
+    if (good) {   // (without device scratch there is nothing to take part with; that rank's peers see an NCCL timeout)
+      ncclResult_t nr = ncclAllGather(ds, dr, rec_bytes, ncclChar, c->nccl, st);
+      if (nr != ncclSuccess) { set_last_error("peer window: ncclAllGather failed"); rc = ERR_NCCL; }
+      good = rc == OK && cudaMemcpyAsync(all_recs, dr, rec_bytes * c->size, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+             cudaStreamSynchronize(st) == cudaSuccess;
+    }
+    if (!good) cudaGetLastError();
+    cudaFree(ds);
+    cudaFree(dr);
+    *local_ok = good;
+    return rc;
+  };
+  bool all_ok = true;
   if (c->size == 1) {
     all[0] = rec;
   } else {
-    cudaStream_t st = runtime().comm_stream;
-    Rec *ds = nullptr, *dr = nullptr;
-    CANDMC_CUDA(cudaMalloc(&ds, sizeof(Rec)));
-    CANDMC_CUDA(cudaMalloc(&dr, sizeof(Rec) * c->size));
-    CANDMC_CUDA(cudaMemcpyAsync(ds, &rec, sizeof(Rec), cudaMemcpyHostToDevice, st));
-    CANDMC_NCCL(ncclAllGather(ds, dr, sizeof(Rec), ncclChar, c->nccl, st));
-    CANDMC_CUDA(cudaMemcpyAsync(all.data(), dr, sizeof(Rec) * c->size, cudaMemcpyDeviceToHost, st));
-    CANDMC_CUDA(cudaStreamSynchronize(st));
-    cudaFree(ds);
-    cudaFree(dr);
+    bool got = false;
+    int rc = gather(&rec, all.data(), sizeof(Rec), &got);
+    if (rc != OK) { if (local) cudaFree(local); delete w; return rc; }
+    if (!got) { all_ok = false; for (int r = 0; r < c->size; ++r) all[r].ok = 0; }
   }
-  bool all_ok = true;
   for (int r = 0; r < c->size; ++r) all_ok = all_ok && all[r].ok;
   if (all_ok) {
     for (int r = 0; r < c->size && all_ok; ++r) {
@@ -67,17 +81,12 @@ int window_create(candmc_comm* c, size_t bytes, PeerWindow** out) {
   }
   // agree on the outcome (one more tiny all-gather) so that either every rank uses the window or none does
   if (c->size > 1) {
-    cudaStream_t st = runtime().comm_stream;
-    int *ds = nullptr, *dr = nullptr, mine_ok = all_ok ? 1 : 0;
-    std::vector<int> oks(c->size);
-    CANDMC_CUDA(cudaMalloc(&ds, sizeof(int)));
-    CANDMC_CUDA(cudaMalloc(&dr, sizeof(int) * c->size));
-    CANDMC_CUDA(cudaMemcpyAsync(ds, &mine_ok, sizeof(int), cudaMemcpyHostToDevice, st));
-    CANDMC_NCCL(ncclAllGather(ds, dr, sizeof(int), ncclChar, c->nccl, st));
-    CANDMC_CUDA(cudaMemcpyAsync(oks.data(), dr, sizeof(int) * c->size, cudaMemcpyDeviceToHost, st));
-    CANDMC_CUDA(cudaStreamSynchronize(st));
-    cudaFree(ds);
-    cudaFree(dr);
+    int mine_ok = all_ok ? 1 : 0;
+    std::vector<int> oks(c->size, 0);
+    bool got = false;
+    int rc = gather(&mine_ok, oks.data(), sizeof(int), &got);
+    if (rc != OK) { w->base[c->rank] = static_cast<char*>(local); window_destroy(w); return rc; }
+    all_ok = all_ok && got;
     for (int r = 0; r < c->size; ++r) all_ok = all_ok && oks[r];
   }
   if (!all_ok) {

@@ -57,6 +57,22 @@ struct FusedCtx {
 int fused_ctx_get(candmc_comm* kdir, int64_t b, FusedCtx** out);
 // Fill the kernel parameters for the next fused call (advances the epoch).
 void fused_params_next(FusedCtx* ctx, int me, FusedParams* p);
+// The epoch and the delivery count are advanced before the steps that can still fail (operand checks, tensor maps, the launch).
+// A call that returns an error before its fused launch was enqueued takes both back, so that the next call on the communicator
+// does not wait for deliveries that were never made.  (Argument errors are the same on every depth rank; a peer that dies
+// mid-call still leaves the others spinning — there is no timeout in the kernels.)
+struct FusedEpochGuard {
+  FusedCtx* ctx = nullptr;
+  uint32_t epoch0 = 0, done0 = 0;
+  unsigned long long launches0 = 0;
+  void arm(FusedCtx* c, unsigned long long fused_launches_now) {   // call BEFORE fused_params_next
+    ctx = c; epoch0 = c->epoch; done0 = c->done_expected; launches0 = fused_launches_now;
+  }
+  void settle(unsigned long long fused_launches_now) {
+    if (ctx && fused_launches_now == launches0) { ctx->epoch = epoch0; ctx->done_expected = done0; }
+    ctx = nullptr;
+  }
+};
 // After the fused GEMM: wait (on `st`) until every peer delivered its owned tiles, then copy them into C (ld ldc).
 int fused_finish(FusedCtx* ctx, int me, const FusedParams& p, double* C, int64_t ldc, cudaStream_t st);
 

@@ -950,6 +950,11 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
     if (useA) { dA_ptr = sA.ptr() + offA; dA_ld = sA.ld(); }
     if (useB) { dB_ptr = sB.ptr() + offB; dB_ld = sB.ld(); }
   }
+  if (c > 1 && runtime().check_peer_args) {   // the depth-sum protocol below follows from the kind of mat_C (candmc_b200.h)
+    bool agree = true;
+    CANDMC_TRY(comm_flags_agree(cdt_kdir, is_device_ptr(mat_C) ? 0 : 1, &agree, runtime().comm_stream));
+    CANDMC_CHECK(agree, "d25_summa: the ranks of a depth group must all pass host or all pass device memory for mat_C");
+  }
   CANDMC_TRY(sC.open(mat_C, b, b, args->lda_C, false, st));
   void* wsv = nullptr;
   // packA | locB | bufA | bufB only when panels travel (q > 1); bufC only when there is a depth sum (c > 1)
@@ -1010,7 +1015,14 @@ int candmc_d25_summa(const candmc_ctb_args_t* args, const double* mat_A, const d
   // (on q > 1 grids the fused path is opt-in, candmc_set_fused_reduce(2): parity-green on 8 B200s but slower there than the
   // all-reduce it replaces — its P2P stores cost the last chunk's launch 6 ms, the all-reduce 4.6 ms)
   if (c > 1 && !slab_mode && (ksplit || runtime().fused_reduce_grids)) CANDMC_TRY(fused_ctx_get(cdt_kdir, b, &fctx));
-  if (fctx) fused_params_next(fctx, layer, &fparams);
+  struct EpochScope {   // an error return below, before the fused launch is enqueued, takes the epoch back (ipc.h)
+    FusedEpochGuard g;
+    ~EpochScope() { g.settle(runtime().fused_launches); }
+  } epoch_scope;
+  if (fctx) {
+    epoch_scope.g.arm(fctx, runtime().fused_launches);
+    fused_params_next(fctx, layer, &fparams);
+  }
 
   if (ksplit) {
     // my k-slice in launch groups of k-chunks as they land (one chunk when the operands are already on the device)

@@ -91,6 +91,7 @@ int runtime_init(int device) {
   if (env_int("CANDMC_MERGE_PANELS", &v) && v >= 0 && v <= 3) g_rt.merge_panels = (int)v;
   if (env_int("CANDMC_EARLY_C_DOWNLOAD", &v)) g_rt.early_c_download = (v != 0);
   if (env_int("CANDMC_SKIP_UNUSED_UPLOADS", &v)) g_rt.skip_unused_uploads = (v != 0);
+  if (env_int("CANDMC_CHECK_PEER_ARGS", &v)) g_rt.check_peer_args = (v != 0);
   g_rt.initialized = true;
   return OK;
 }

@@ -29,6 +29,7 @@ struct Runtime {
   unsigned long long merged_chunked = 0, merged_plain = 0;   // merged last-panel launches (summa_sweep): chunk-major B / plain B
   unsigned long long transport_sends = 0;   // panel chunks shipped by copy engines (transport.h)
   unsigned long long launches = 0;   // kernels launched by this library (bench.py's gpu_launches)
+  unsigned long long fused_launches = 0;   // fused GEMM + depth-sum launches enqueued (FusedEpochGuard, ipc.h)
   cudaStream_t comm_stream = nullptr;   // NCCL panel traffic
   cudaStream_t aux_stream = nullptr;    // second compute/copy stream
   void* workspace = nullptr;            // grow-only device scratch
@@ -39,6 +40,7 @@ struct Runtime {
   int* tile_counters = nullptr;         // ring of device counters for the GEMM's dynamic tile scheduler
   unsigned tile_counter_seq = 0;
   bool fused_reduce_grids = false;      // ... also on q x q x c grids (validated so far on 1 x 1 x c only)
+  bool check_peer_args = false;         // d25_summa on c > 1: verify that the depth ranks agree on the kind of C pointer (candmc_set_check_peer_args)
   bool skip_unused_uploads = true;      // host operands: a layer's rank uploads only the blocks its panels use (candmc_set_skip_unused_uploads)
   bool panel_transport = true;          // SUMMA panels and Cannon shifts by copy engines into peer windows instead of NCCL kernels (transport.h)
   bool b_first_chunk_early = false;     // pageable host B: upload the first k-chunk's rows ahead of the rest (opt-in)

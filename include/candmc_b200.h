@@ -56,6 +56,13 @@ int candmc_set_fused_reduce(int on);
 /* Host operands on q x q x c grids: 1 (default) skips the upload of an A (B) block whose grid column (row) is not one of the
  * layer's panels — the multiply never reads it there; 0 uploads both blocks on every rank. */
 int candmc_set_skip_unused_uploads(int on);
+/* candmc_d25_summa on grids with c > 1 picks the protocol of its depth sum from the kind of mat_C it is given (a host block
+ * leaves in column slabs, each summed by its own all-reduce; a device block takes one all-reduce or the fused epilogue), so
+ * ALL RANKS OF A DEPTH GROUP MUST PASS THE SAME KIND OF POINTER FOR mat_C — as every caller of the reference does.  A mixed
+ * group issues mismatched collectives and hangs the GPUs.  1 = verify it first (one 8-byte all-reduce over the depth
+ * communicator and a stream synchronisation per call; a mismatch returns CANDMC_ERR_INVALID on every rank of the group);
+ * 0 (default) = trust the caller.  Also the environment variable CANDMC_CHECK_PEER_ARGS. */
+int candmc_set_check_peer_args(int on);
 /* Host C blocks in candmc_d25_summa: 1 (default) = the last launch group of the multiply is cut into column slabs of b/2, b/4,
  * b/8, b/8 columns (each still over all of the group's k), each slab is summed over the depth and downloaded while the next
  * ones multiply; 0 = one download at the end. */

@@ -739,6 +739,15 @@ cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
   return cudaSuccess;
 }
 cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+  // fault injection: CPUSIM_IPC_FAIL_RANK=r makes every mapping attempt of rank r fail (the library must then agree, on all
+  // ranks of the communicator, to stay on NCCL)
+  if (const char* fr = getenv("CPUSIM_IPC_FAIL_RANK")) {
+    const char* me = getenv("RANK");
+    if (me && atoi(me) == atoi(fr)) {
+      g_last = cudaErrorInvalidValue;
+      return cudaErrorInvalidValue;
+    }
+  }
   char name[64];
   memcpy(name, h.reserved, sizeof(name));
   name[63] = 0;

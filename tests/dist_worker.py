@@ -128,6 +128,46 @@ def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_go
     return ok
 
 
+def case_fused_error_recovery(world, golden, tag):
+    """A fused GEMM + depth-sum call that fails on every depth rank BEFORE its launch (the test hook makes the operands
+    un-TMA-able, which the fused path refuses) must leave the window's epoch and delivery count where they were: the next
+    call on the same communicator would otherwise wait for deliveries that were never made (ipc.h, FusedEpochGuard)."""
+    cb.lib().candmc_debug_force_generic_gemm(1)
+    try:   # (where CUDA IPC is unavailable the depth sum is an NCCL all-reduce and the call simply works on the CUDA-core kernel)
+        refused = not case_d25(world, golden, f"d25_ksplit_generic_nccl_sum_{tag}", 512, 2, 0, check_golden=False)
+        outcome = 1.0 if refused else 0.0
+    except cb.CandmcError:
+        outcome = 0.0
+    finally:
+        cb.lib().candmc_debug_force_generic_gemm(0)
+    ok = record(f"d25_ksplit_fused_refused_{tag}:error_returned_or_right", outcome, 0.5)
+    return ok & case_d25(world, golden, f"d25_ksplit_fused_after_error_{tag}", 512, 2, 0, check_golden=False)
+
+
+def case_mixed_c_kinds_refused(world, golden, tag):
+    """candmc_set_check_peer_args(1): a depth group whose ranks pass different kinds of mat_C (host on one, device on the other
+    — the two would issue different collectives for the depth sum) is refused on every rank instead of hanging; the next
+    call works."""
+    g = shared_grid(world, "d25", 2)
+    n = b = 256
+    A = np.asfortranarray(orc.unit_block(b, b, 0, 0, n, 0)); B = np.asfortranarray(orc.unit_block(b, b, 0, 0, n, 1))
+    args = cb.ctb_args_t(n=n, lda_A=b, lda_B=b, lda_C=b, buffer_size=5 * b * b * 8)
+    dA, dB = dev(A), dev(B)
+    dC = torch.zeros(b * b, dtype=torch.float64, device="cuda")
+    hC = np.zeros((b, b), order="F")
+    cb.lib().candmc_set_check_peer_args(1)
+    try:
+        cb.d25_summa(args, dA, dB, hC if world.rank % 2 == 0 else dC, None, g["cdt_row"], g["cdt_col"], g["cdt_kdir"])
+        refused = False
+    except cb.CandmcError as e:
+        refused = "mat_C" in str(e)
+    ok = record(f"d25_mixed_c_kinds_{tag}:refused", 0.0 if refused else 1.0, 0.5)
+    ok &= case_d25(world, golden, f"d25_checked_peer_args_n256_{tag}", 256, 2, 0, check_golden=False)   # the check passes, device C
+    ok &= case_d25(world, golden, f"d25_checked_peer_args_host_n96_{tag}", 96, 2, 0, use_host=True, check_golden=False)
+    cb.lib().candmc_set_check_peer_args(0)
+    return ok
+
+
 def case_repeat(world, golden, name, c, sizes):
     """many multiplies on ONE grid (the communicators' persistent state: workspaces, fused-reduce windows with their epochs
     and double-buffered slabs, panel-transport windows with their call counters, done flags and the growth path)"""
@@ -746,7 +786,9 @@ def main():
     only_pending = os.environ.get("CANDMC_TEST_PENDING") == "1"
     if only_pending:
         pending_cases(world, golden)
-    for min_kc in (() if only_pending else (1024, 8)):   # default (whole panels at these sizes) and a tiny chunk to exercise the k-chunk pipeline
+    # (CANDMC_TEST_KC=8: only the chunked variant — the simulator's fault-injection jobs, tests/test_cpusim.py)
+    main_kcs = tuple(int(x) for x in os.environ.get("CANDMC_TEST_KC", "1024,8").split(","))
+    for min_kc in (() if only_pending else main_kcs):   # default (whole panels at these sizes) and a tiny chunk to exercise the k-chunk pipeline
         cb.set_min_kchunk(min_kc)
         tag = f"kc{min_kc}"
         if P == 1:
@@ -766,6 +808,8 @@ def main():
             case_d25(world, golden, f"d25_ksplit_fused_n512_{tag}", 512, 2, 0)
             case_d25(world, golden, f"d25_ksplit_fused_n256_pad_{tag}", 256, 2, 0, lda_pad=3)
             case_d25(world, golden, f"d25_ksplit_fused_n768_again_{tag}", 768, 2, 1)
+            case_fused_error_recovery(world, golden, tag)
+            case_mixed_c_kinds_refused(world, golden, tag)
             # transposed operands on the k-split (refused until round 2): every combination through the fused epilogue, one
             # with padded leading dimensions, one with host operands (staged whole, depth sum by NCCL when C is a host block)
             for tr in (("T", "N"), ("N", "T"), ("T", "T")):

@@ -62,6 +62,12 @@ _job("nccl4", _torchrun(4, 29747, os.path.join(HERE, "dist_worker.py")), CANDMC_
 # ... and the automatic fallback when peer windows are unavailable: NCCL panels (full-width communicators) under the launch groups
 _job("ncclmerge4", _torchrun(4, 29748, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_PANEL_TRANSPORT="0",
      CPUSIM_SCHED="random:31")
+# fault injection: one rank cannot map its peers' memory (cudaIpcOpenMemHandle fails there) — every communicator that rank is in
+# must agree to stay on NCCL (panels AND the depth sum), the others keep their windows
+_job("ipcfail2", _torchrun(2, 29749, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_KC="8", CPUSIM_IPC_FAIL_RANK="1",
+     CPUSIM_SCHED="lifo")
+_job("ipcfail4", _torchrun(4, 29750, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_KC="8", CPUSIM_IPC_FAIL_RANK="2",
+     CPUSIM_SCHED="lifo")
 # (the copy-engine transport and launch groups of mode 2 ARE main4 / main8 since round 2 — and main4@lifo / main8@random below)
 # opt-in: the last panel of a sweep multiplied in one launch over its k-chunks (B read chunk-major through one tensor map by the
 # product's own kernel on the PTX emulation); the validated 2x2 suite with the switch on
@@ -331,6 +337,17 @@ def test_nccl_panels_and_per_chunk_launches_on_the_simulator():
     assert out["panel_transport_sends_rank0"] == 0 and out["merged_panel_launches_all_ranks"] == [0, 0]
     out = _dist("ncclmerge4")   # the fallback of the default schedule: launch groups fed by ncclBroadcast
     assert out["panel_transport_sends_rank0"] == 0 and out["merged_panel_launches_all_ranks"][0] > 0
+
+
+def test_ranks_agree_to_leave_peer_windows_when_one_cannot_map_them():
+    """a local failure inside the collective window set-up becomes the agreed outcome instead of leaving
+    the peers inside an all-gather.  Rank 1 of 2 / rank 2 of 4 cannot open IPC handles: the whole validated suite still passes,
+    the 1x1x2 depth sum and every communicator with that rank in it on NCCL, rank 0's row communicator (ranks 0, 1 of 4)
+    still on copy engines."""
+    out = _dist("ipcfail2")
+    assert out["panel_transport_sends_rank0"] == 0
+    out = _dist("ipcfail4")
+    assert out["panel_transport_sends_rank0"] > 0
 
 
 @pytest.mark.parametrize("job", ["merge4", "main4", "merge4_doubling", "main8"])

@@ -1118,8 +1118,10 @@ int candmc_bcast_cannon_4d(const candmc_ctb_args_t* args, const double* mat_A, c
   const int x1_np = cdt_x1->size, x2_np = cdt_x2->size;
   CANDMC_CHECK(x1_np == cdt_y1->size && x2_np == cdt_y2->size, "bcast_cannon_4d: grids must be square");  // :71-72
   CANDMC_CHECK(args->n > 0 && args->n % ((int64_t)x1_np * x2_np) == 0, "bcast_cannon_4d: n %% (x1_np*x2_np) != 0");
-  CANDMC_CHECK(is_n(args->trans_A) && is_n(args->trans_B),
-               "bcast_cannon_4d: only 'N','N' (the reference passes the flags to the local dgemm only)");
+  // trans_A / trans_B: as in the reference (dual_cannon.cxx:163-166,188-194) the flags reach the local multiply only — the
+  // square b x b blocks travel as they are stored and every block product is op(A block) * op(B block)
+  CANDMC_CHECK((is_n(args->trans_A) || is_t(args->trans_A)) && (is_n(args->trans_B) || is_t(args->trans_B)),
+               "bcast_cannon_4d: trans_A / trans_B must be 'N' or 'T'");
   const int64_t b = args->n / ((int64_t)x1_np * x2_np), bb = b * b;
   const int64_t need = (args->ovp ? 5 : 3) * bb * (int64_t)sizeof(double);  // dual_cannon.cxx:31-37
   CANDMC_CHECK(buffer == nullptr || args->buffer_size >= need, "bcast_cannon_4d: buffer_size too small");
@@ -1171,9 +1173,10 @@ int candmc_bcast_cannon_4d(const candmc_ctb_args_t* args, const double* mat_A, c
     CANDMC_TRY(stream_wait(st, shift));
   }
 
-  // NOTE: the shifts use the full-width communicators — grouped ncclSend/ncclRecv on the CTA-capped background
-  // communicators hung in the 4-GPU parity run (profiles/r01_cannon_bg_hang.txt), so their overlap with the multiplies
-  // is only as good as the SMs NCCL can get at GEMM boundaries; a copy-engine transport is the planned fix.
+  // The shifts travel by copy engines into the neighbours' peer windows (p2p_transport_prepare above; default since round 2:
+  // 90.6 -> 94.4 % at n = 24576 on 4 B200s, profiles/r02_4gpu_b/) and so run under the multiplies.  The NCCL fallback uses the
+  // full-width communicators — grouped ncclSend/ncclRecv on the CTA-capped ones hung (profiles/r01_cannon_bg_hang.txt) — and
+  // only gets SMs at GEMM boundaries.
   for (int i2 = 0; i2 < x2_np; ++i2) {
     const double* nxtA = curA;
     const double* nxtB = curB;
@@ -1191,7 +1194,7 @@ int candmc_bcast_cannon_4d(const candmc_ctb_args_t* args, const double* mat_A, c
       CANDMC_CUDA(cudaEventRecord(shift_done, shift));
     }
     SummaArgs a;
-    a.tA = 'N'; a.tB = 'N'; a.b = b; a.i0 = 0; a.i1 = x1_np;
+    a.tA = args->trans_A; a.tB = args->trans_B; a.b = b; a.i0 = 0; a.i1 = x1_np;
     a.myA = curA; a.ldA = ldA; a.myB = curB; a.ldB = ldB;
     a.C = sC.ptr(); a.ldC = sC.ld(); a.first_beta_zero = (i2 == 0);  // beta = (i1>0 || i2>0), dual_cannon.cxx:188
     a.row = cdt_x1; a.col = cdt_y1; a.ws = ws; a.compute = st;

@@ -188,8 +188,9 @@ int candmc_comm_allreduce_sum(candmc_comm_t* comm, const double* sendbuf, double
 /* ---- distributed multiplies (alg/MM) ---------------------------------------------------------------------- */
 /* Same fields and meaning as ctb_args_t (alg/MM/topo_pdgemm/topo_pdgemm_algs.h:6-15). */
 typedef struct candmc_ctb_args {
-  char trans_A;
-  char trans_B;
+  char trans_A;        /* 'N' / 'T': as in the reference the flags reach the LOCAL multiply only (summa.cxx:97, d25_summa.cxx:185, */
+  char trans_B;        /* dual_cannon.cxx:163-166) — blocks travel as stored, each block product is op(A blk)*op(B blk); pinned  */
+                       /* to the unmodified reference's outputs (golden *_TN / *_NT / *_TT).  On a 1 x 1 x c grid: op(A)*op(B).   */
   int64_t n;           /* global matrix dimension */
   int64_t lda_A;
   int64_t lda_B;

@@ -200,8 +200,17 @@ int oracle_d25_summa(int64_t n, int q, int c, int ovp, char trans_A, char trans_
  * ---------------------------------------------------------------------------------------------------------- */
 static int wrap(int a, int b) { return ((a % b) + b) % b; }
 
+int oracle_bcast_cannon_4d_t(int64_t n, int x1_np, int x2_np, int ovp, char trans_A, char trans_B, double* const* A,
+                             double* const* B, double* const* C);
 int oracle_bcast_cannon_4d(int64_t n, int x1_np, int x2_np, int ovp, double* const* A, double* const* B,
                            double* const* C) {
+  return oracle_bcast_cannon_4d_t(n, x1_np, x2_np, ovp, 'N', 'N', A, B, C);
+}
+
+/* trans_A / trans_B go to the local multiply only (cdgemm(p->trans_A, p->trans_B, ...), dual_cannon.cxx:163-166,188-194):
+ * the b x b blocks are staggered, broadcast and shifted as they are stored. */
+int oracle_bcast_cannon_4d_t(int64_t n, int x1_np, int x2_np, int ovp, char trans_A, char trans_B, double* const* A,
+                             double* const* B, double* const* C) {
   (void)ovp; /* only changes when the multiply is issued (:163-166,191-194), not what is summed */
   if (x1_np <= 0 || x2_np <= 0 || n % ((int64_t)x1_np * x2_np) != 0) return -1;
   const int64_t b = n / ((int64_t)x1_np * x2_np);
@@ -226,7 +235,7 @@ int oracle_bcast_cannon_4d(int64_t n, int x1_np, int x2_np, int ovp, double* con
             for (int x1 = 0; x1 < x1_np; ++x1) {
               const double* mul_A = curA[RK(i1, y1, x2, y2)]; /* bcast along cdt_x1, root i1 */
               const double* mul_B = curB[RK(x1, i1, x2, y2)]; /* bcast along cdt_y1, root i1 */
-              oracle_dgemm('N', 'N', b, b, b, 1.0, mul_A, b, mul_B, b, (i1 > 0 || i2 > 0) * 1.0,
+              oracle_dgemm(trans_A, trans_B, b, b, b, 1.0, mul_A, b, mul_B, b, (i1 > 0 || i2 > 0) * 1.0,
                            C[RK(x1, y1, x2, y2)], b);
             }
     if (i2 < x2_np - 1) {

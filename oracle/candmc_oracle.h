@@ -42,6 +42,8 @@ int oracle_summa(int64_t n, int q, char trans_A, char trans_B, double* const* A,
                  int64_t lda_B, double* const* C, int64_t lda_C);
 int oracle_d25_summa(int64_t n, int q, int c, int ovp, char trans_A, char trans_B, double* const* A, double* const* B,
                      double* const* C);
+int oracle_bcast_cannon_4d_t(int64_t n, int x1_np, int x2_np, int ovp, char trans_A, char trans_B, double* const* A,
+                             double* const* B, double* const* C);
 int oracle_bcast_cannon_4d(int64_t n, int x1_np, int x2_np, int ovp, double* const* A, double* const* B,
                            double* const* C);
 int oracle_spcannon(int bidir, int kary, int ndim, int n, int m, int k, char transp_A, double alpha, double* const* A,

@@ -45,6 +45,7 @@ def lib() -> C.CDLL:
         L.oracle_summa.argtypes = [_i64, C.c_int, C.c_char, C.c_char, _ppd, _i64, _ppd, _i64, _ppd, _i64]
         L.oracle_d25_summa.argtypes = [_i64, C.c_int, C.c_int, C.c_int, C.c_char, C.c_char, _ppd, _ppd, _ppd]
         L.oracle_bcast_cannon_4d.argtypes = [_i64, C.c_int, C.c_int, C.c_int, _ppd, _ppd, _ppd]
+        L.oracle_bcast_cannon_4d_t.argtypes = [_i64, C.c_int, C.c_int, C.c_int, C.c_char, C.c_char, _ppd, _ppd, _ppd]
         L.oracle_spcannon.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char, C.c_double,
                                       _ppd, C.c_char, C.c_double, _ppd, _ppd]
         L.oracle_upd_A.argtypes = [C.c_int, C.POINTER(_i64), _i64, _i64, _ppd, C.POINTER(_i64), _ppd,
@@ -120,8 +121,8 @@ def d25_summa(n, q, c, ovp, A, B, Cb, trans_A="N", trans_B="N"):
     assert rc == 0, "oracle_d25_summa: bad grid"
 
 
-def bcast_cannon_4d(n, x1_np, x2_np, ovp, A, B, Cb):
-    rc = lib().oracle_bcast_cannon_4d(n, x1_np, x2_np, ovp, _pp(A), _pp(B), _pp(Cb))
+def bcast_cannon_4d(n, x1_np, x2_np, ovp, A, B, Cb, trans_A="N", trans_B="N"):
+    rc = lib().oracle_bcast_cannon_4d_t(n, x1_np, x2_np, ovp, _ch(trans_A), _ch(trans_B), _pp(A), _pp(B), _pp(Cb))
     assert rc == 0, "oracle_bcast_cannon_4d: bad grid"
 
 

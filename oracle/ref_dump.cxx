@@ -7,6 +7,9 @@
 //   ref_dump d25   <n> <c_rep> <ovp 0|1> <prefix>      d25_summa / d25_summa_ovp  (grid + data: test/MM/topo_pdgemm_unit.cxx:178-283)
 //   ref_dump summa <n> <prefix>                         summa                      (grid + data: :349-486, ctb_unit)
 //   ref_dump dcn   <n> <x2_np> <ovp> <prefix>           bcast_cannon_4d            (grid + data: :13-175, dcn_unit); x2_np must be 1
+//   ref_dump d25t  <n> <c_rep> <ovp> <tA> <tB> <prefix> | summat <n> <tA> <tB> <prefix> | dcnt <n> <x2_np> <ovp> <tA> <tB> <prefix>
+//                                                       the same three with trans_A / trans_B set (the reference hands the flags to
+//                                                       its local dgemm only: every block product is op(A block) * op(B block))
 //   ref_dump upda  <m> <k> <b> <nprow> <rrow> <rcol> <prefix>   update_A, W == NULL (alg/QR/qr_2d/qr_2d.cxx:124-177)
 //   ref_dump updw  <m> <k> <b> <nprow> <rrow> <rcol> <prefix>   update_A, W = the panel QR's upper-triangular factor, W_is_T == false
 //                                                                (what QR_2D hands in, qr_2d.cxx:325; T by comp_bcast_T_from_W :179-208)
@@ -40,7 +43,8 @@ static double* alloc_d(size_t n) {
   return (double*)p;
 }
 
-static int run_d25(int myRank, int numPes, int64_t n, int c_rep, int ovp, const char* prefix, bool use_summa) {
+static int run_d25(int myRank, int numPes, int64_t n, int c_rep, int ovp, const char* prefix, bool use_summa, char tA = 'N',
+                   char tB = 'N') {
   const int num_pes_dim = (int)sqrt((double)(numPes / c_rep));
   if (num_pes_dim * num_pes_dim * c_rep != numPes || n % num_pes_dim != 0) {
     if (myRank == 0) fprintf(stderr, "ref_dump: grid mismatch\n");
@@ -69,8 +73,8 @@ static int run_d25(int myRank, int numPes, int64_t n, int c_rep, int ovp, const 
   p.lda_B = b;
   p.lda_C = b;
   p.buffer_size = 5 * b * b * sizeof(double);
-  p.trans_A = 'N';
-  p.trans_B = 'N';
+  p.trans_A = tA;   // the reference hands the flags to the local dgemm only (summa.cxx:97, d25_summa.cxx:185)
+  p.trans_B = tB;
   p.ovp = ovp;
   if (use_summa)
     summa(&p, mat_A, mat_B, mat_C, buffer, cdt_row, cdt_col);
@@ -82,7 +86,7 @@ static int run_d25(int myRank, int numPes, int64_t n, int c_rep, int ovp, const 
   return 0;
 }
 
-static int run_dcn(int myRank, int numPes, int64_t n, int x2_np, int ovp, const char* prefix) {
+static int run_dcn(int myRank, int numPes, int64_t n, int x2_np, int ovp, const char* prefix, char tA = 'N', char tB = 'N') {
   // grid + generator of dcn_unit (test/MM/topo_pdgemm_unit.cxx:13-175)
   const int x1_np = (int)sqrt((double)(numPes / (x2_np * x2_np)));
   if (x1_np * x1_np * x2_np * x2_np != numPes || x2_np != 1) {
@@ -117,8 +121,8 @@ static int run_dcn(int myRank, int numPes, int64_t n, int x2_np, int ovp, const 
   p.lda_B = b;
   p.lda_C = b;
   p.buffer_size = 5 * b * b * sizeof(double);
-  p.trans_A = 'N';
-  p.trans_B = 'N';
+  p.trans_A = tA;   // ... and so does bcast_cannon_4d (dual_cannon.cxx:163-166,188-194)
+  p.trans_B = tB;
   p.ovp = ovp;
   bcast_cannon_4d(&p, mat_A, mat_B, mat_C, buffer, cdt_x1, cdt_y1, cdt_x2, cdt_y2);
   dump(prefix, myRank, mat_C, b * b);
@@ -373,6 +377,12 @@ int main(int argc, char** argv) {
     rc = run_d25(myRank, numPes, atoll(argv[2]), 1, 0, argv[3], true);
   else if (argc >= 6 && !strcmp(argv[1], "dcn"))
     rc = run_dcn(myRank, numPes, atoll(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5]);
+  else if (argc >= 8 && !strcmp(argv[1], "dcnt"))
+    rc = run_dcn(myRank, numPes, atoll(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[7], argv[5][0], argv[6][0]);
+  else if (argc >= 6 && !strcmp(argv[1], "summat"))
+    rc = run_d25(myRank, numPes, atoll(argv[2]), 1, 0, argv[5], true, argv[3][0], argv[4][0]);
+  else if (argc >= 8 && !strcmp(argv[1], "d25t"))
+    rc = run_d25(myRank, numPes, atoll(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[7], false, argv[5][0], argv[6][0]);
   else if (argc >= 12 && !strcmp(argv[1], "spc"))
     rc = run_spc(myRank, numPes, atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]),
                  atoi(argv[7]), atof(argv[8]), atof(argv[9]), argv[10][0], argv[11]);

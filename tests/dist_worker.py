@@ -89,8 +89,10 @@ def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_go
     A = np.zeros((ld, b), order="F"); B = np.zeros((ld, b), order="F")
     A[:b] = orc.unit_block(b, b, row0, col0, n, 0)
     B[:b] = orc.unit_block(b, b, row0, col0, n, 1)
-    if trans != ("N", "N"):   # the k-split of a 1 x 1 x c grid with stored transposes: op(stored) is the same operand, so is C
-        assert q == 1 and c > 1
+    # q > 1 with trans flags: as in the reference the flags reach the local multiply only (d25_summa.cxx:185) — blocks stay as
+    # generated, the oracle and the reference's own outputs (golden d25_*_TT / _TN) say what comes out
+    if trans != ("N", "N") and q == 1:   # the k-split of a 1 x 1 x c grid with stored transposes: op(stored) is the same operand, so is C
+        assert c > 1
         if trans[0] == "T":
             A[:b] = A[:b].T.copy()
         if trans[1] == "T":
@@ -121,7 +123,7 @@ def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_go
     Ab, Bb = orc.d25_blocks(n, q, c) if not (q == 1 and c > 1) else (
         [orc.unit_block(n, n, 0, 0, n, 0) for _ in range(c)], [orc.unit_block(n, n, 0, 0, n, 1) for _ in range(c)])
     Cb = [np.zeros((b, b), order="F") for _ in Ab]
-    orc.d25_summa(n, q, c, ovp, Ab, Bb, Cb)
+    orc.d25_summa(n, q, c, ovp, Ab, Bb, Cb, *(trans if q > 1 else ("N", "N")))
     ok = record(f"{name}:oracle", rel_frob(got, Cb[world.rank]), 10 * n * EPS)
     if check_golden and name in golden:
         ok &= record(f"{name}:golden", rel_frob(got, golden[name][world.rank]), 10 * n * EPS)
@@ -201,12 +203,12 @@ def case_summa(world, golden, name, n, lda_pad=0, trans=("N", "N")):
     Cb = [np.zeros((b, b), order="F") for _ in Ab]
     orc.summa(n, q, Ab, Bb, Cb, trans_A=trans[0], trans_B=trans[1])
     ok = record(f"{name}:oracle", rel_frob(got, Cb[world.rank]), 10 * n * EPS)
-    if name in golden and lda_pad == 0 and trans == ("N", "N"):
+    if name in golden and lda_pad == 0:
         ok &= record(f"{name}:golden", rel_frob(got, golden[name][world.rank]), 10 * n * EPS)
     return ok
 
 
-def case_dcn(world, golden, name, n, x2_np, ovp, lda_pad=0):
+def case_dcn(world, golden, name, n, x2_np, ovp, lda_pad=0, trans=("N", "N")):
     g = shared_grid(world, "dcn", x2_np)
     x1_np = g["x1_np"]
     b = n // (x1_np * x2_np)
@@ -218,16 +220,18 @@ def case_dcn(world, golden, name, n, x2_np, ovp, lda_pad=0):
     B[:b] = orc.unit_block(b, b, row0, col0, n, 1)
     dA, dB = dev(A), dev(B)
     dC = torch.full((b * b,), float("nan"), dtype=torch.float64, device="cuda")
-    args = cb.ctb_args_t(n=n, lda_A=ld, lda_B=ld, lda_C=b, buffer_size=5 * b * b * 8, ovp=ovp)
+    args = cb.ctb_args_t(n=n, lda_A=ld, lda_B=ld, lda_C=b, buffer_size=5 * b * b * 8, ovp=ovp, trans_A=trans[0], trans_B=trans[1])
     cb.bcast_cannon_4d(args, dA, dB, dC, None, g["cdt_x1"], g["cdt_y1"], g["cdt_x2"], g["cdt_y2"])
     torch.cuda.synchronize()
     got = host(dC, b, b)
     Ab, Bb = orc.dcn_blocks(n, x1_np, x2_np)
     Cb = [np.zeros((b, b), order="F") for _ in Ab]
-    orc.bcast_cannon_4d(n, x1_np, x2_np, ovp, Ab, Bb, Cb)
+    orc.bcast_cannon_4d(n, x1_np, x2_np, ovp, Ab, Bb, Cb, trans_A=trans[0], trans_B=trans[1])
     ok = record(f"{name}:oracle", rel_frob(got, Cb[world.rank]), 10 * n * EPS)
     if name in golden and lda_pad == 0:
         ok &= record(f"{name}:golden", rel_frob(got, golden[name][world.rank]), 10 * n * EPS)
+    if trans != ("N", "N"):   # the flags reach the local multiply only (dual_cannon.cxx:163-166): sum over k of op(A_ik) op(B_kj),
+        return ok             # blocks as stored — not a product of the assembled matrices, so no serial criterion
     # the reference test's own criterion: serial product in the dcn_unit layout, |diff| <= 1e-6
     full = orc.unit_block(n, n, 0, 0, n, 0) @ orc.unit_block(n, n, 0, 0, n, 1)
     ok &= record(f"{name}:serial_abs", float(np.abs(got - full[row0:row0 + b, col0:col0 + b]).max()), 1e-6)
@@ -844,10 +848,19 @@ def main():
             case_summa(world, golden, "summa_n64_q2", 64, lda_pad=4)
             case_summa(world, golden, f"summa_n96_TN_{tag}", 96, trans=("T", "N"))
             case_summa(world, golden, f"summa_n96_NT_{tag}", 96, trans=("N", "T"))
+            # trans flags against the unmodified reference: they reach the local dgemm only, blocks travel as stored
+            case_summa(world, golden, "summa_n64_q2_TN", 64, trans=("T", "N"))
+            case_summa(world, golden, "summa_n64_q2_NT", 64, trans=("N", "T"))
+            case_d25(world, golden, "d25_n96_q2_c1_ovp1_TN", 96, 1, 1, trans=("T", "N"))
             case_dcn(world, golden, "dcn_n64_x2_1_ovp0", 64, 1, 0)
             case_dcn(world, golden, "dcn_n64_x2_1_ovp1", 64, 1, 1)
             case_dcn(world, golden, f"dcn_n64_x2_2_{tag}", 64, 2, 0)          # pure Cannon: the reference deadlocks here
             case_dcn(world, golden, f"dcn_n96_x2_2_pad_{tag}", 96, 2, 1, lda_pad=2)
+            case_dcn(world, golden, "dcn_n64_x2_1_ovp0_TN", 64, 1, 0, trans=("T", "N"))     # (refused until the end of round 2)
+            case_dcn(world, golden, "dcn_n64_x2_1_ovp1_NT", 64, 1, 1, trans=("N", "T"))
+            case_dcn(world, golden, "dcn_n64_x2_1_ovp0_TT", 64, 1, 0, trans=("T", "T"))
+            case_dcn(world, golden, f"dcn_n64_x2_2_TN_{tag}", 64, 2, 0, trans=("T", "N"))    # Cannon level: oracle only
+            case_dcn(world, golden, f"dcn_n96_x2_2_TT_pad_{tag}", 96, 2, 1, lda_pad=2, trans=("T", "T"))
             case_spc(world, golden, "spc_bidir1_p4_m24_k16_n20_N", 1, 2, 2, 20, 24, 16, "N")
             case_spc(world, golden, "spc_bidir0_p4_m24_k16_n20_N", 0, 2, 2, 20, 24, 16, "N")
             case_spc(world, golden, "spc_bidir1_p4_m24_k16_n20_T", 1, 2, 2, 20, 24, 16, "T")
@@ -861,6 +874,7 @@ def main():
             case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0)
             case_d25(world, golden, "d25_n64_q2_c2_ovp1", 64, 2, 1)
             case_d25(world, golden, "d25_n64_q2_c2_ovp0", 64, 2, 0, lda_pad=2)
+            case_d25(world, golden, "d25_n64_q2_c2_ovp0_TT", 64, 2, 0, trans=("T", "T"))
             case_d25(world, golden, f"d25_n512_c2_{tag}", 512, 2, 0)            # b = 256: fused depth sum
             case_d25(world, golden, f"d25_n1024_c2_fused_{tag}", 1024, 2, 1)
             case_d25(world, golden, f"d25_n1024_c2_host_{tag}", 1024, 2, 0, use_host=True)

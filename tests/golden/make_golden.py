@@ -34,6 +34,15 @@ CASES = {
     # bcast_cannon_4d with x2_np = 1 (the only configuration in which the reference terminates)
     "dcn_n64_x2_1_ovp0": (4, ["dcn", "64", "1", "0"], 32 * 32),
     "dcn_n64_x2_1_ovp1": (4, ["dcn", "64", "1", "1"], 32 * 32),
+    # trans_A / trans_B set: the reference hands them to its local dgemm only (summa.cxx:97, d25_summa.cxx:185,
+    # dual_cannon.cxx:163-166) — every block product is op(A block) * op(B block), blocks travel as stored
+    "summa_n64_q2_TN": (4, ["summat", "64", "T", "N"], 32 * 32),
+    "summa_n64_q2_NT": (4, ["summat", "64", "N", "T"], 32 * 32),
+    "d25_n64_q2_c2_ovp0_TT": (8, ["d25t", "64", "2", "0", "T", "T"], 32 * 32),
+    "d25_n96_q2_c1_ovp1_TN": (4, ["d25t", "96", "1", "1", "T", "N"], 48 * 48),
+    "dcn_n64_x2_1_ovp0_TN": (4, ["dcnt", "64", "1", "0", "T", "N"], 32 * 32),
+    "dcn_n64_x2_1_ovp1_NT": (4, ["dcnt", "64", "1", "1", "N", "T"], 32 * 32),
+    "dcn_n64_x2_1_ovp0_TT": (4, ["dcnt", "64", "1", "0", "T", "T"], 32 * 32),
     # split-dimensional Cannon: spc <bidir> <ndim> <seed> <n> <m> <k> <alpha> <beta> <tB>
     "spc_bidir1_p4_m24_k16_n20_N": (4, ["spc", "1", "2", "3", "20", "24", "16", "1.2", "0.8", "N"], 24 * 20),
     "spc_bidir0_p4_m24_k16_n20_N": (4, ["spc", "0", "2", "3", "20", "24", "16", "1.2", "0.8", "N"], 24 * 20),

@@ -104,6 +104,34 @@ def test_oracle_dcn_matches_reference(golden, ovp):
         assert rel_frob(Cb[r], golden[f"dcn_n64_x2_1_ovp{ovp}"][r]) <= 10 * n * EPS
 
 
+TRANS = [("summa_n64_q2_TN", "summa", 64, 2, 1, 0, "T", "N"), ("summa_n64_q2_NT", "summa", 64, 2, 1, 0, "N", "T"),
+         ("d25_n64_q2_c2_ovp0_TT", "d25", 64, 2, 2, 0, "T", "T"), ("d25_n96_q2_c1_ovp1_TN", "d25", 96, 2, 1, 1, "T", "N"),
+         ("dcn_n64_x2_1_ovp0_TN", "dcn", 64, 2, 1, 0, "T", "N"), ("dcn_n64_x2_1_ovp1_NT", "dcn", 64, 2, 1, 1, "N", "T"),
+         ("dcn_n64_x2_1_ovp0_TT", "dcn", 64, 2, 1, 0, "T", "T")]
+
+
+@pytest.mark.parametrize("name,kind,n,q,c,ovp,tA,tB", TRANS)
+def test_oracle_trans_flags_match_reference(golden, name, kind, n, q, c, ovp, tA, tB):
+    """trans_A / trans_B in the unmodified reference reach the local dgemm only (summa.cxx:97, d25_summa.cxx:185,
+    dual_cannon.cxx:163-166): blocks travel as stored, every block product is op(A block) * op(B block)."""
+    if kind == "dcn":
+        A, B = orc.dcn_blocks(n, q, 1)
+        Cb = zeros_like_blocks(A)
+        orc.bcast_cannon_4d(n, q, 1, ovp, A, B, Cb, trans_A=tA, trans_B=tB)
+    else:
+        A, B = orc.d25_blocks(n, q, c)
+        Cb = zeros_like_blocks(A)
+        if kind == "summa":
+            orc.summa(n, q, A, B, Cb, trans_A=tA, trans_B=tB)
+        else:
+            orc.d25_summa(n, q, c, ovp, A, B, Cb, tA, tB)
+    for r in range(len(A)):
+        assert rel_frob(Cb[r], golden[name][r]) <= 10 * n * EPS, (name, r)
+    # ... which is NOT the product of the assembled transposes: the flagged result differs from the plain one
+    plain = golden[{"summa": "summa_n64_q2", "dcn": f"dcn_n64_x2_1_ovp{ovp}"}.get(kind, name[:-3])]
+    assert rel_frob(golden[name][0], plain[0]) > 1e-3
+
+
 @pytest.mark.parametrize("x1,x2,n", [(1, 2, 32), (2, 2, 64), (1, 3, 48)])
 def test_oracle_dcn_cannon_level_vs_serial(x1, x2, n):
     """x2_np > 1 cannot be run in the reference (it deadlocks); the expected output is by definition the serial product

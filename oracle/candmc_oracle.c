@@ -132,7 +132,8 @@ int oracle_summa(int64_t n, int q, char trans_A, char trans_B, double* const* A,
  * (:125-148); with zeroed buffers its sums are the same panels in the same order.  Finally MPI_Allreduce(SUM) over
  * the depth communicator leaves sum_l buf_C on every layer (:149,221).
  * Extension (NOT in the reference, whose q % c == 0 assert forbids it): q == 1 with c > 1 splits k across the c
- * ranks — rank l multiplies A[:, l*b/c:(l+1)*b/c] * B[l*b/c:(l+1)*b/c, :] — the 2-GPU configuration of SURVEY §8e.
+ * ranks — rank l multiplies op(A)[:, l*b/c:(l+1)*b/c] * op(B)[l*b/c:(l+1)*b/c, :] — the 2-GPU configuration of SURVEY §8e
+ * (there is one block per operand here, so with trans flags the result IS op(A)*op(B)).
  * ---------------------------------------------------------------------------------------------------------- */
 int oracle_d25_summa(int64_t n, int q, int c, int ovp, char trans_A, char trans_B, double* const* A, double* const* B,
                      double* const* C) {
@@ -141,7 +142,7 @@ int oracle_d25_summa(int64_t n, int q, int c, int ovp, char trans_A, char trans_
   const int q2 = q * q;
   const int ksplit = (q == 1 && c > 1);
   if (!ksplit && q % c != 0) return -1; /* :63 */
-  if (ksplit && (b % c != 0 || is_t(trans_A) || is_t(trans_B))) return -1;
+  if (ksplit && b % c != 0) return -1;
   double** buf_C = (double**)malloc(sizeof(double*) * (size_t)(q2 * c));
   for (int l = 0; l < c; ++l)
     for (int row = 0; row < q; ++row)
@@ -150,7 +151,10 @@ int oracle_d25_summa(int64_t n, int q, int c, int ovp, char trans_A, char trans_
         double* bc = buf_C[r] = dalloc((size_t)(b * b));
         if (ksplit) {
           const int64_t kb = b / c;
-          oracle_dgemm('N', 'N', b, b, kb, 1.0, A[r] + l * kb * b, b, B[r] + l * kb, b, 0.0, bc, b);
+          /* my k-slice of op(A) and op(B): columns of a stored A / rows of a stored B, the other way round for a stored transpose */
+          const double* pa = A[r] + (is_t(trans_A) ? l * kb : l * kb * b);
+          const double* pb = B[r] + (is_t(trans_B) ? l * kb * b : l * kb);
+          oracle_dgemm(trans_A, trans_B, b, b, kb, 1.0, pa, b, pb, b, 0.0, bc, b);
           continue;
         }
         if (!ovp) {

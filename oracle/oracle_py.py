@@ -31,8 +31,22 @@ def lib() -> C.CDLL:
     if _LIB is None:
         path = os.path.join(_HERE, "liboracle.so")
         src = os.path.join(_HERE, "candmc_oracle.c")
-        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
-            build()
+
+        def stale():
+            return not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src)
+
+        if stale():
+            # several ranks of one job may get here together (a snapshot that did not keep modification times): one builds, the
+            # others wait for it — a rank must never dlopen a half-written file
+            import fcntl
+
+            with open(os.path.join(_HERE, ".liboracle.lock"), "w") as lock:
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                try:
+                    if stale():
+                        build()
+                finally:
+                    fcntl.flock(lock, fcntl.LOCK_UN)
         L = C.CDLL(path)
         L.oracle_unit_elem.restype = C.c_double
         L.oracle_unit_elem.argtypes = [_i64, _i64, _i64, C.c_int]

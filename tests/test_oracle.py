@@ -179,14 +179,17 @@ def test_oracle_spcannon_matches_reference(golden, name, bidir, kary, ndim, n, m
         assert np.abs(Cb[rank] - full[py * m:(py + 1) * m, px * n:(px + 1) * n]).max() <= 1e-6
 
 
-def test_oracle_d25_ksplit_extension_vs_serial():
-    n, c = 48, 2
-    A = [orc.unit_block(n, n, 0, 0, n, 0) for _ in range(c)]
-    B = [orc.unit_block(n, n, 0, 0, n, 1) for _ in range(c)]
+@pytest.mark.parametrize("tA,tB", [("N", "N"), ("T", "N"), ("N", "T"), ("T", "T")])
+@pytest.mark.parametrize("c", [2, 3])
+def test_oracle_d25_ksplit_extension_vs_serial(tA, tB, c):
+    n = 48
+    A = [np.asfortranarray(orc.unit_block(n, n, 0, 0, n, 0)) for _ in range(c)]
+    B = [np.asfortranarray(orc.unit_block(n, n, 0, 0, n, 1)) for _ in range(c)]
     Cb = zeros_like_blocks(A)
-    orc.d25_summa(n, 1, c, 0, A, B, Cb)
+    orc.d25_summa(n, 1, c, 0, A, B, Cb, tA, tB)
+    want = (A[0].T if tA == "T" else A[0]) @ (B[0].T if tB == "T" else B[0])
     for r in range(c):
-        assert rel_frob(Cb[r], A[0] @ B[0]) <= 10 * n * EPS
+        assert rel_frob(Cb[r], want) <= 10 * n * EPS
 
 
 def test_oracle_upd_A_vs_numpy():

@@ -60,8 +60,11 @@ def main():
                 cb.lib().candmc_set_host_gather(rng.choice([0, 1, 1]))
                 if rng.random() < 0.5:
                     host = "pinned"   # page-locked blocks: B gathered chunk-wise out of host memory (where the chunking allows)
-            log.append((tag, dict(n=b * q, c=c, pad=pad, host=host)))
-            dw.case_d25(world, golden, tag, b * q, c, rng.choice([0, 1]), lda_pad=pad, use_host=host, check_golden=False)
+            # trans flags: on grids they reach the local multiply only (blocks as stored, the oracle follows the reference there);
+            # on 1 x 1 x c the stored transposes are generated so that op(stored) is the same operand (even k-slices)
+            tr = rng.choice([("N", "N"), ("N", "N"), ("T", "N"), ("N", "T"), ("T", "T")]) if (q > 1 or (c > 1 and b % (2 * c) == 0)) else ("N", "N")
+            log.append((tag, dict(n=b * q, c=c, pad=pad, host=host, trans=tr)))
+            dw.case_d25(world, golden, tag, b * q, c, rng.choice([0, 1]), lda_pad=pad, use_host=host, check_golden=False, trans=tr)
             cb.lib().candmc_set_host_pipeline_min(2048); cb.lib().candmc_set_early_c_download(1); cb.lib().candmc_set_skip_unused_uploads(1)
             cb.lib().candmc_set_host_gather(1)
             cb.lib().candmc_set_b_first_chunk_early(0)
@@ -75,7 +78,8 @@ def main():
             x1 = int(round(P ** 0.5)) // x2
             b = rng.choice([4, 8, 12, 32])
             log.append((tag, dict(n=b * x1 * x2, x2=x2)))
-            dw.case_dcn(world, golden, tag, b * x1 * x2, x2, rng.choice([0, 1]), lda_pad=pad)
+            dw.case_dcn(world, golden, tag, b * x1 * x2, x2, rng.choice([0, 1]), lda_pad=pad,
+                        trans=rng.choice([("N", "N"), ("T", "N"), ("N", "T"), ("T", "T")]))
         elif kind == "spc":
             ndim = rng.choice([2, 4]) if P == 16 else 2
             kary = int(round(P ** (1.0 / ndim)))

@@ -1694,11 +1694,37 @@ int candmc_upd_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64
   CANDMC_TRY(runtime_require());
   g_events.reset();
   CANDMC_CHECK(mb >= 0 && kb >= 0 && b > 0, "upd_A: bad extents");
-  CANDMC_CHECK(is_device_ptr(Y) && is_device_ptr(A) && is_device_ptr(T), "upd_A: operands must be device pointers");
-  if (kb == 0) return OK;
+  CANDMC_CHECK(Y != nullptr || mb == 0, "upd_A: null Y");
+  CANDMC_CHECK(A != nullptr || mb == 0 || kb == 0, "upd_A: null A");
+  if (kb == 0) return OK;   // (the reference forms T before it looks at kb; nothing reads it then)
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // host operands (what the reference's QR drivers own, qr_2d.cxx:447-620) are staged for the call, like the multiplies' blocks
+  StagedMatrix sY, sA, sT;
+  CANDMC_TRY(sY.open(Y, mb, b, lda_Y, true, st));
+  CANDMC_TRY(sA.open(A, mb, kb, lda_A, true, st));
+  CANDMC_TRY(sT.open(T, b, b, b, true, st));
   void* wsv = nullptr;
-  CANDMC_TRY(workspace_get(sizeof(double) * b * kb, &wsv));
-  return upd_A_impl(Y, lda_Y, A, lda_A, mb, kb, b, T, ccol, static_cast<double*>(wsv), static_cast<cudaStream_t>(stream));
+  CANDMC_TRY(workspace_get(sizeof(double) * (b * kb + 2 * b * b), &wsv));
+  double* W = static_cast<double*>(wsv);
+  const double* Tuse = sT.ptr();
+  if (T == nullptr) {
+    // W == NULL in the reference (qr_2d.cxx:241-246): T^-1 from Y — lower triangle of the grid column's sum of Y^T Y, diagonal
+    // halved (compute_invT_from_Y :22-60; there the root column computes and broadcasts along the row — every column holds
+    // the same Ybuf rows, so here each computes its own copy and the broadcast disappears)
+    double* S = W + b * kb;
+    double* Tl = S + b * b;
+    if (mb > 0) CANDMC_TRY(gemm_f64('T', 'N', b, b, mb, 1.0, sY.ptr(), sY.ld(), sY.ptr(), sY.ld(), 0.0, S, b, st));
+    else CANDMC_TRY(fill_f64(S, b * b, 0.0, st));
+    if (ccol != nullptr && ccol->size > 1) CANDMC_TRY(comm_allreduce(ccol, S, S, b * b, st));
+    tril_halve_diag_kernel<<<static_cast<int>((b * b + 255) / 256), 256, 0, st>>>(S, Tl, b);
+    CANDMC_CUDA(cudaGetLastError());
+    runtime().launches++;
+    Tuse = Tl;
+  }
+  CANDMC_TRY(upd_A_impl(sY.ptr(), sY.ld(), sA.ptr(), sA.ld(), mb, kb, b, Tuse, ccol, W, st));
+  if (mb > 0) CANDMC_TRY(sA.close_out(st));
+  if (sY.staged() || sA.staged() || sT.staged()) CANDMC_CUDA(cudaStreamSynchronize(st));
+  return OK;
 }
 
 }  // extern "C"

@@ -171,7 +171,8 @@ def kuni_cannon(rank, kary, ndim, comm: CommData_t, n, m, k, transp_A, alpha, A,
 
 
 def upd_A(Y, lda_Y, A, lda_A, mb, kb, b, T, ccol: CommData_t | None = None, stream=None):
-    """The GEMM pair + allreduce + trsm of upd_A (alg/QR/qr_2d/qr_2d.cxx:259-275), W_is_T case."""
+    """The GEMM pair + allreduce + trsm of upd_A (alg/QR/qr_2d/qr_2d.cxx:224-282): T given = the W_is_T form, T None = the
+    reference's W == NULL form (T^-1 from Y, compute_invT_from_Y :22-60).  numpy (host) operands are staged for the call."""
     check(lib().candmc_upd_A(_ptr(Y), lda_Y, _ptr(A), lda_A, mb, kb, b, _ptr(T), ccol.cm if ccol else None,
                              _stream(stream)))
 

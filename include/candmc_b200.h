@@ -221,15 +221,20 @@ int candmc_bcast_cannon_4d(const candmc_ctb_args_t* args, const double* mat_A, c
 /* Split-dimensional Cannon, C <- alpha*A*B + beta*C with rectangular local blocks (A m x k, B k x n or n x k
  * per transp_B, C m x n).  Replaces kput_cannon (bidir != 0) / kuni_cannon (bidir == 0)
  * (alg/MM/splitdim_cannon/spcannon.h:31-59, spcannon.cxx:237-347).  `world` must contain kary^ndim ranks laid out
- * as in spcannon.cxx:59-62; only ndim == 2 is implemented (an NVSwitch crossbar has no torus dimensions to split
- * over).  A and B are preserved (the reference destroys them). */
+ * as in spcannon.cxx:59-62; any even ndim (ndim = 4 needs 16 ranks and has run on the simulator only — an
+ * NVSwitch crossbar has no torus dimensions to split over).  A and B are preserved (the reference destroys them). */
 int candmc_spcannon(int bidir, int rank, int kary, int ndim, candmc_comm_t* world, int n, int m, int k,
                     char transp_A, double alpha, const double* A, char transp_B, double beta, const double* B,
                     double* C, void* stream);
-/* CAQR trailing update A <- A - Y * (T^-1 * (Y^T A)) on one grid column.  Replaces the W_is_T path of upd_A
+/* CAQR trailing update A <- A - Y * (T^-1 * (Y^T A)) on one grid column.  Replaces upd_A
  * (alg/QR/qr_2d/qr_2d.cxx:224-282): cdgemm('T','N') :259, MPI_Allreduce over ccol :265, cdtrsm('L','L','N','N') with the
  * b x b lower-triangular T (ld = b) :271, cdgemm('N','N', alpha=-1, beta=1) :275.  Y is mb x b, A is mb x kb (local
- * extents), all device pointers.  ccol may be NULL (single process column). */
+ * extents).  T != NULL is the W_is_T form (what the pipelined drivers pass, :447-620); T == NULL is the reference's W == NULL
+ * form (:241-246): T^-1 = lower triangle of the grid column's sum of Y^T Y with the diagonal halved (compute_invT_from_Y
+ * :22-60), formed on the device.  The third form (W = the panel QR's factor) needs the whole grid view: candmc_update_A.
+ * Device pointers are used in place and the call is asynchronous; HOST pointers (what the reference's own QR drivers hold)
+ * are staged for the call, which then returns with A written back — that is what integration/qr_2d_upd_A_gpu.cxx, the
+ * upd_A a maintainer links in front of the reference's, passes.  ccol may be NULL (single process column). */
 int candmc_upd_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
                  const double* T, candmc_comm_t* ccol, void* stream);
 /* Tuning: the triangular solve inside upd_A / update_A — 1 (default since round 2: 8.77 against 9.04 ms for BASELINE config 5

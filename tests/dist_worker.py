@@ -259,19 +259,37 @@ def case_spc(world, golden, name, bidir, kary, ndim, n, m, k, tB, use_host=False
     return ok
 
 
-def case_upd_A(world, name, mb, kb, b):
-    """One process column of world.np ranks; every rank owns mb rows of Y and A."""
+def case_upd_A(world, name, mb, kb, b, use_host=False, t_from_y=False, lda_pad=0):
+    """One process column of world.np ranks; every rank owns mb rows of Y and A.  use_host: numpy operands with padded leading
+    dimensions, staged inside the call (what the reference's QR drivers pass through integration/qr_2d_upd_A_gpu.cxx);
+    t_from_y: T = None, the reference's W == NULL form — T^-1 = tril(sum over the column of Y^T Y), diagonal halved."""
     rng = np.random.default_rng(5)
     P = world.np
-    T = np.asfortranarray(np.eye(b) + 0.01 * np.tril(rng.random((b, b))))
     Y = [np.asfortranarray(rng.random((mb, b))) for _ in range(P)]
     A = [np.asfortranarray(rng.random((mb, kb))) for _ in range(P)]
-    dY, dA, dT = dev(Y[world.rank]), dev(A[world.rank]), dev(T)
-    cb.upd_A(dY, mb, dA, mb, mb, kb, b, dT, world)
-    torch.cuda.synchronize()
-    got = host(dA, mb, kb)
+    if t_from_y:   # Householder-like panel: unit lower-trapezoidal on rank 0, small entries below, so that T^-1 is well conditioned
+        for r in range(P):
+            Y[r] *= 0.1
+        Y[0][:b] = np.tril(Y[0][:b], -1) + np.eye(b)
+        S = sum(y.T @ y for y in Y)
+        T = np.asfortranarray(np.tril(S, -1) + 0.5 * np.diag(np.diag(S)))
+    else:
+        T = np.asfortranarray(np.eye(b) + 0.01 * np.tril(rng.random((b, b))))
+    if use_host:
+        ldy, lda = mb + lda_pad, mb + 2 * lda_pad
+        hY = np.zeros((ldy, b), order="F"); hY[:mb] = Y[world.rank]
+        hA = np.full((lda, kb), np.nan, order="F"); hA[:mb] = A[world.rank]
+        cb.upd_A(hY, ldy, hA, lda, mb, kb, b, None if t_from_y else T, world)
+        got = hA[:mb].copy()
+        ok = record(f"{name}:padding_untouched", 0.0 if np.isnan(hA[mb:]).all() else 1.0, 0.5)
+    else:
+        dY, dA, dT = dev(Y[world.rank]), dev(A[world.rank]), dev(T)
+        cb.upd_A(dY, mb, dA, mb, mb, kb, b, None if t_from_y else dT, world)
+        torch.cuda.synchronize()
+        got = host(dA, mb, kb)
+        ok = True
     orc.upd_A([mb] * P, kb, b, Y, [mb] * P, A, [mb] * P, T)
-    return record(f"{name}:oracle", rel_frob(got, A[world.rank]), 10 * mb * P * EPS)
+    return ok & record(f"{name}:oracle", rel_frob(got, A[world.rank]), (1000 if t_from_y else 10) * mb * P * EPS)
 
 
 def case_update_A(world, golden, name, m, k, b, nprow, rrow, rcol, with_T=False, with_W=False):
@@ -800,6 +818,10 @@ def main():
             case_d25(world, golden, "d25_n40_q1_c1_ovp0", 40, 1, 1, use_host=True, check_golden=False)
             case_spc(world, golden, f"spc_p1_{tag}", 1, 1, 2, 20, 24, 16, "N")
             case_update_A(world, golden, "upda_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0)
+            if min_kc == 1024:   # upd_A's other forms (end of round 2): T formed from Y on the device; host operands staged inside
+                case_upd_A(world, "upd_A_p1_TfromY", 96, 40, 8, t_from_y=True)
+                case_upd_A(world, "upd_A_p1_host_pad", 64, 48, 16, use_host=True, lda_pad=3)
+                case_upd_A(world, "upd_A_p1_host_TfromY", 80, 24, 8, use_host=True, t_from_y=True, lda_pad=1)
             cb.lib().candmc_set_host_pipeline_min(64)   # stream host operands panel-wise even at this size
             case_d25(world, golden, f"d25_hostpipe_n320_{tag}", 320, 1, 0, use_host=True, check_golden=False)
             case_d25(world, golden, f"d25_hostpipe_n200_pad_{tag}", 200, 1, 0, lda_pad=3, use_host=True, check_golden=False)
@@ -808,6 +830,9 @@ def main():
             case_d25(world, golden, f"d25_ksplit_n64_{tag}", 64, 2, 0)
             case_d25(world, golden, f"d25_ksplit_n96_pad_{tag}", 96, 2, 1, lda_pad=2)
             case_upd_A(world, f"upd_A_p2_{tag}", 64, 48, 16)
+            if min_kc == 1024:
+                case_upd_A(world, "upd_A_p2_TfromY", 96, 40, 8, t_from_y=True)
+                case_upd_A(world, "upd_A_p2_host_TfromY", 64, 48, 16, use_host=True, t_from_y=True, lda_pad=2)
             # b multiple of 128*c: the depth sum is fused into the GEMM epilogue over peer memory (CUDA IPC windows)
             case_d25(world, golden, f"d25_ksplit_fused_n512_{tag}", 512, 2, 0)
             case_d25(world, golden, f"d25_ksplit_fused_n256_pad_{tag}", 256, 2, 0, lda_pad=3)
@@ -867,6 +892,9 @@ def main():
             case_spc(world, golden, "spc_bidir1_p4_m24_k16_n20_N", 1, 2, 2, 20, 24, 16, "N", use_host=True)
             case_spc(world, golden, f"spc_p4_big_{tag}", 1, 2, 2, 256, 384, 128, "N")
             case_upd_A(world, f"upd_A_p4_{tag}", 96, 80, 32)
+            if min_kc == 1024:
+                case_upd_A(world, "upd_A_p4_TfromY", 96, 80, 32, t_from_y=True)
+                case_upd_A(world, "upd_A_p4_host_pad", 96, 80, 32, use_host=True, lda_pad=1)
             case_update_A(world, golden, "upda_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 0, 0)
             case_update_A(world, golden, "upda_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 2, 0)
             case_update_A(world, golden, f"upda_T_2x2_{tag}", 128, 96, 16, 2, 1, 1, with_T=True)

@@ -130,8 +130,18 @@ DROPIN_CASES = {
     # the reference's own D25 test with the opt-in peer-memory paths switched on from the environment (an unmodified main
     # cannot call setters): panels by copy engines, depth sum fused into the GEMM epilogue (n = 1024: b = 512 = 2 * 128 * c)
     "d25_p8_peer_paths": ("candmc_run", 8, "topo_pdgemm_unit", ["-n", "1024", "-ovp", "0"], "D25 UNIT TEST PASSED", "lifo"),
+    # the reference's own 2D QR test with its trailing updates in the library (integration/qr_2d_upd_A_gpu.cxx): as shipped
+    # (QR_2D_pipe, W_is_T form) and sent through QR_2D_2D (oracle/qr_2d_tap.cxx: T from the panel factor / from the aggregated Y)
+    "qr_pipe_p4": ("mpirun", 4, "test_qr_2d_gpu", ["96", "48", "8", "2"], "Test successful.", "lifo"),
+    "qr_pipe_p1": ("mpirun", 1, "test_qr_2d_gpu", ["64", "32", "4", "1"], "Test successful.", "sync"),
+    "qr_2d_p4": ("mpirun", 4, "test_qr_2d_2d_gpu", ["128", "64", "4", "2"], "Test successful.", "lifo"),
+    "qr_2d_p9": ("mpirun", 9, "test_qr_2d_2d_gpu", ["144", "72", "4", "3"], "Test successful.", "sync"),
+    "qr_2d_p2": ("mpirun", 2, "test_qr_2d_2d_gpu", ["64", "32", "8", "2"], "Test successful.", "lifo"),
 }
-DROPIN_ENV = {"d25_p8_peer_paths": dict(CANDMC_PANEL_TRANSPORT="1", CANDMC_FUSED_REDUCE="2", CANDMC_MIN_KCHUNK="64")}
+DROPIN_ENV = {"d25_p8_peer_paths": dict(CANDMC_PANEL_TRANSPORT="1", CANDMC_FUSED_REDUCE="2", CANDMC_MIN_KCHUNK="64"),
+              "qr_pipe_p4": dict(CANDMC_SEAM_VERBOSE="1"), "qr_pipe_p1": dict(CANDMC_SEAM_VERBOSE="1"),
+              "qr_2d_p4": dict(CANDMC_SEAM_VERBOSE="1", QR_TAP_B2="32"), "qr_2d_p9": dict(CANDMC_SEAM_VERBOSE="1", QR_TAP_B2="24"),
+              "qr_2d_p2": dict(CANDMC_SEAM_VERBOSE="1")}
 HAVE_DROPIN = all(os.path.exists(os.path.join(DROPIN, c[2])) for c in DROPIN_CASES.values()) and \
     os.path.exists(os.path.join(ROOT, "tools", "candmc_run")) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "mpirun"))
 if HAVE_DROPIN:
@@ -252,13 +262,26 @@ def test_stream_dependencies_hold_under_adversarial_scheduling(name, sched):
 
 @pytest.mark.parametrize("case", sorted(DROPIN_CASES))
 def test_reference_test_mains_pass_on_the_simulator(case):
-    """test/MM/topo_pdgemm_unit.cxx, test/MM/test_spc.cxx and the 2.5D LU unit tests (sixteen offload calls served by
-    libcandmc_lu_offload.so) — the reference's own sources and PASS criteria, our C++ drop-in layer and host schedules"""
+    """test/MM/topo_pdgemm_unit.cxx, test/MM/test_spc.cxx, the 2.5D LU unit tests (sixteen offload calls served by
+    libcandmc_lu_offload.so) and test/QR/test_qr_2d.cxx (upd_A served by candmc_upd_A) — the reference's own sources and PASS
+    criteria, our C++ drop-in layer and host schedules"""
     if not HAVE_DROPIN:
         pytest.skip("drop-in binaries not built (needs /root/reference at build time)")
     rc, so, se = RESULTS[f"dropin_{case}"]
     assert rc == 0, so[-2000:] + se[-2000:]
     assert DROPIN_CASES[case][4] in so and "FAILED" not in so and "test failed" not in so.lower()
+    if case.startswith("qr_"):
+        # the reference's QR test (SURVEY 8f N1's pin) prints "Test successful." for a NaN residual too: read the number, and
+        # make sure the trailing updates went through the library (integration/qr_2d_upd_A_gpu.cxx reports each one)
+        import re
+
+        res = float(re.findall(r"\|\|A-QR\|\|_2 = (\S+)", so)[-1])
+        assert res == res and res <= 1e-9, so[-1500:]
+        assert "qr_2d_upd_A_gpu: upd_A" in se
+        if case.startswith("qr_2d_"):
+            assert "form=T from W" in se and ("QR_TAP_B2" not in DROPIN_ENV[case] or "form=T from Y" in se)
+        else:
+            assert "form=W is T" in se
 
 
 @pytest.mark.parametrize("nproc,seed,policy", FUZZ)

@@ -1,0 +1,70 @@
+"""GPU test of the CAQR seam (SURVEY.md §8f N1 names test/QR/test_qr_2d.cxx as the pin of the trailing update): the reference's
+OWN 2D QR test, unmodified, with every trailing update — the GEMM pair, the all-reduce of Y^T A and the triangular solve of
+upd_A (alg/QR/qr_2d/qr_2d.cxx:224-282) — running in libcandmc_b200.so through integration/qr_2d_upd_A_gpu.cxx.  The panels
+(TSQR, Householder reconstruction) stay the reference's host code over the mini-MPI shim and OpenBLAS (`make -C oracle dropin`;
+the binaries travel in oracle/_ref/dropin/).  test_qr_2d_gpu drives QR_2D_pipe as the test is shipped (W_is_T form);
+test_qr_2d_2d_gpu is the same test sent through QR_2D_2D (oracle/qr_2d_tap.cxx): T from the panel's factor and T from the
+aggregated Y.  Criterion: the reference's own ||A - QR|| <= 1e-9 line — parsed, because the test prints "Test successful."
+for a NaN as well.
+
+STATUS: written after round 2's GPU minutes were spent.  Green on the CPU simulator (tests/test_cpusim.py, 1 / 2 / 4 / 9
+ranks); no B200 has run it, hence xfail(strict=False): XPASS when right, and it cannot turn the validated suite red on first
+contact.  The marker goes away once a round has seen it pass.
+"""
+import os
+import re
+
+import pytest
+
+from pending_util import run_guarded
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _ngpu():
+    try:
+        import torch
+
+        return torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:
+        return 0
+
+
+def qr_residual(stdout):
+    """the reference test's verdict line '||A-QR||_2 = 1.80E-14' (test/QR/test_qr_2d.cxx:338)"""
+    m = re.findall(r"\|\|A-QR\|\|_2 = (\S+)", stdout)
+    assert m, stdout[-2000:]
+    return float(m[-1])
+
+
+CASES = [  # np, exe, m, k, b, nprow, outer block of the tapped variant
+    (1, "test_qr_2d_gpu", 256, 128, 16, 1, None),
+    (1, "test_qr_2d_2d_gpu", 256, 128, 16, 1, None),
+    (1, "test_qr_2d_2d_gpu", 256, 128, 16, 1, 64),
+    (1, "test_qr_2d_gpu", 1024, 512, 64, 1, None),
+    (4, "test_qr_2d_gpu", 256, 128, 16, 2, None),
+    (4, "test_qr_2d_2d_gpu", 256, 128, 8, 2, 32),
+    (4, "test_qr_2d_gpu", 2048, 1024, 64, 2, None),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="the reference's QR test over the GPU upd_A seam: first B200 run pending (written after round 2's GPU budget was spent)")
+@pytest.mark.parametrize("np_,exe,m,k,b,nprow,b2", CASES)
+def test_reference_qr_2d_test_passes_with_gpu_trailing_updates(np_, exe, m, k, b, nprow, b2):
+    path = os.path.join(REFDIR, "dropin", exe)
+    if not (os.path.exists(path) and os.path.exists(os.path.join(REFDIR, "mpirun"))):
+        pytest.skip("drop-in binaries not built (needs /root/reference at build time)")
+    if _ngpu() < np_:
+        pytest.skip(f"needs {np_} GPUs")
+    env = dict(os.environ, CANDMC_SEAM_VERBOSE="1")
+    if b2 is not None:
+        env["QR_TAP_B2"] = str(b2)
+    cmd = [os.path.join(REFDIR, "mpirun"), "-np", str(np_), "-timeout", "200", "-threads", "2", path, str(m), str(k), str(b), str(nprow)]
+    rc, so, se = run_guarded("qr_dropin", cmd, 300, ROOT, env=env)
+    assert rc == 0, so[-2000:] + se[-2000:]
+    res = qr_residual(so)
+    assert res == res and res <= 1e-9, so[-1500:]          # the reference's criterion, NaN-proof
+    assert "qr_2d_upd_A_gpu: upd_A" in se                  # ... and the updates really went through the library

@@ -79,6 +79,8 @@ def free_shared_grids():
 
 
 def case_d25(world, golden, name, n, c, ovp, lda_pad=0, use_host=False, check_golden=True, oracle=True, grid=None, trans=("N", "N")):
+    if n >= 2048 and os.environ.get("CANDMC_TEST_QUICK") == "1":   # the simulator's fault-injection jobs: same paths at n <= 1024
+        return True
     g = grid if grid is not None else shared_grid(world, "d25", c)
     q = g["q"]
     b = n // q

@@ -64,9 +64,9 @@ _job("ncclmerge4", _torchrun(4, 29748, os.path.join(HERE, "dist_worker.py")), CA
      CPUSIM_SCHED="random:31")
 # fault injection: one rank cannot map its peers' memory (cudaIpcOpenMemHandle fails there) — every communicator that rank is in
 # must agree to stay on NCCL (panels AND the depth sum), the others keep their windows
-_job("ipcfail2", _torchrun(2, 29749, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_KC="8", CPUSIM_IPC_FAIL_RANK="1",
+_job("ipcfail2", _torchrun(2, 29749, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_KC="8", CANDMC_TEST_QUICK="1", CPUSIM_IPC_FAIL_RANK="1",
      CPUSIM_SCHED="lifo")
-_job("ipcfail4", _torchrun(4, 29750, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_KC="8", CPUSIM_IPC_FAIL_RANK="2",
+_job("ipcfail4", _torchrun(4, 29750, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_KC="8", CANDMC_TEST_QUICK="1", CPUSIM_IPC_FAIL_RANK="2",
      CPUSIM_SCHED="lifo")
 # (the copy-engine transport and launch groups of mode 2 ARE main4 / main8 since round 2 — and main4@lifo / main8@random below)
 # opt-in: the last panel of a sweep multiplied in one launch over its k-chunks (B read chunk-major through one tensor map by the

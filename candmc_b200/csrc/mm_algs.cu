@@ -1608,12 +1608,22 @@ int candmc_upd_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t l
   CANDMC_TRY(runtime_require());
   g_events.reset();
   CANDMC_CHECK(mb >= 0 && kb >= 0 && b > 0, "upd_Yamamoto_A: bad extents");
-  CANDMC_CHECK(is_device_ptr(Qm) && is_device_ptr(A) && is_device_ptr(T), "upd_Yamamoto_A: operands must be device pointers");
+  CANDMC_CHECK((Qm != nullptr && A != nullptr) || mb == 0 || kb == 0, "upd_Yamamoto_A: null operand");
+  CANDMC_CHECK(T != nullptr || mb == 0 || kb == 0, "upd_Yamamoto_A: null T");
   if (kb == 0) return OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // host operands (the reference's QR_Yamamoto drivers, qr_y2d.cxx:113,367) are staged for the call, as in candmc_upd_A
+  StagedMatrix sQ, sA, sT;
+  CANDMC_TRY(sQ.open(Qm, mb, b, lda_Qm, true, st));
+  CANDMC_TRY(sA.open(A, mb, kb, lda_A, true, st));
+  CANDMC_TRY(sT.open(mb > 0 ? T : nullptr, b, b, b, true, st));   // (a rank without rows never reads T, :150)
   void* wsv = nullptr;
   CANDMC_TRY(workspace_get(sizeof(double) * 2 * b * kb, &wsv));
   double* W = static_cast<double*>(wsv);
-  return upd_Yamamoto_A_impl(Qm, lda_Qm, A, lda_A, mb, kb, b, T, ccol, W, W + b * kb, static_cast<cudaStream_t>(stream));
+  CANDMC_TRY(upd_Yamamoto_A_impl(sQ.ptr(), sQ.ld(), sA.ptr(), sA.ld(), mb, kb, b, sT.ptr(), ccol, W, W + b * kb, st));
+  if (mb > 0) CANDMC_TRY(sA.close_out(st));
+  if (sQ.staged() || sA.staged() || sT.staged()) CANDMC_CUDA(cudaStreamSynchronize(st));
+  return OK;
 }
 
 int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,

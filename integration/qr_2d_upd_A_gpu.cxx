@@ -6,7 +6,8 @@
  * -Wl,--allow-multiple-definition and this object first, qr_2d.cxx compiled -fPIC so that its own calls go through the
  * symbol.  Every QR driver of the reference (QR_2D via update_A :170, QR_2D_pipe :447-620, QR_2D_2D :873, QR_2D_25D :934) then
  * runs its trailing-matrix GEMM pair, the all-reduce of Y^T A over the grid column and the triangular solve in
- * libcandmc_b200.so (candmc_upd_A, include/candmc_b200.h); the panel factorisation (TSQR + Householder reconstruction), the
+ * libcandmc_b200.so (candmc_upd_A, include/candmc_b200.h) — and likewise upd_Yamamoto_A (alg/QR/qr_2d/qr_y2d.cxx:123-169) for
+ * QR_Yamamoto_2D / QR_Yamamoto_2D_2D (candmc_upd_Yamamoto_A); the panel factorisation (TSQR + Householder reconstruction), the
  * panel broadcast and the formation of T from the panel's factor stay the reference's host code.
  *
  * The matrices stay where the reference keeps them — in host memory — so candmc_upd_A stages them for the call: this seam is
@@ -124,4 +125,15 @@ void upd_A(double const* Ybuf, int64_t lda_Y, double* A, int64_t lda_A, int64_t 
             W == NULL ? "T from Y" : (W_is_T ? "W is T" : "T from W"));
   seam_check(candmc_upd_A(Ybuf, lda_Y, A, lda_A, mb, kb, b, T, ccol, NULL), "candmc_upd_A");
   if (T_from_W) free(T_from_W);
+}
+
+/* Same name, argument list and meaning as alg/QR/qr_2d/qr_y2d.h:85-93 (definition qr_y2d.cxx:123-169): the Yamamoto form,
+ * A <- A + Qm * (T * (Qm^T A)) with T kept explicitly.  Serves update_Yamamoto_A (:113) and the aggregated block-column update
+ * of QR_Yamamoto_2D_2D (:367); the aggregator itself stays the reference's host code. */
+void upd_Yamamoto_A(double const* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b, double const* T,
+                    pview* pv) {
+  candmc_comm_t* ccol = column_of(pv);
+  if (getenv("CANDMC_SEAM_VERBOSE") && pv->cworld.rank == 0)
+    fprintf(stderr, "qr_2d_upd_A_gpu: upd_Yamamoto_A mb=%lld kb=%lld b=%lld\n", (long long)mb, (long long)kb, (long long)b);
+  seam_check(candmc_upd_Yamamoto_A(Qm, lda_Qm, A, lda_A, mb, kb, b, T, ccol, NULL), "candmc_upd_Yamamoto_A");
 }

@@ -137,11 +137,15 @@ DROPIN_CASES = {
     "qr_2d_p4": ("mpirun", 4, "test_qr_2d_2d_gpu", ["128", "64", "4", "2"], "Test successful.", "lifo"),
     "qr_2d_p9": ("mpirun", 9, "test_qr_2d_2d_gpu", ["144", "72", "4", "3"], "Test successful.", "sync"),
     "qr_2d_p2": ("mpirun", 2, "test_qr_2d_2d_gpu", ["64", "32", "8", "2"], "Test successful.", "lifo"),
+    # ... and test/QR/test_qr_y2d.cxx (QR_Yamamoto_2D_2D with its aggregator): upd_Yamamoto_A served by candmc_upd_Yamamoto_A
+    "qr_y2d_p4": ("mpirun", 4, "test_qr_y2d_gpu", ["96", "48", "8", "2", "16"], "Test successful.", "lifo"),
+    "qr_y2d_p6": ("mpirun", 6, "test_qr_y2d_gpu", ["96", "48", "4", "2", "24"], "Test successful.", "sync"),
 }
 DROPIN_ENV = {"d25_p8_peer_paths": dict(CANDMC_PANEL_TRANSPORT="1", CANDMC_FUSED_REDUCE="2", CANDMC_MIN_KCHUNK="64"),
               "qr_pipe_p4": dict(CANDMC_SEAM_VERBOSE="1"), "qr_pipe_p1": dict(CANDMC_SEAM_VERBOSE="1"),
               "qr_2d_p4": dict(CANDMC_SEAM_VERBOSE="1", QR_TAP_B2="32"), "qr_2d_p9": dict(CANDMC_SEAM_VERBOSE="1", QR_TAP_B2="24"),
-              "qr_2d_p2": dict(CANDMC_SEAM_VERBOSE="1")}
+              "qr_2d_p2": dict(CANDMC_SEAM_VERBOSE="1"), "qr_y2d_p4": dict(CANDMC_SEAM_VERBOSE="1"),
+              "qr_y2d_p6": dict(CANDMC_SEAM_VERBOSE="1")}
 HAVE_DROPIN = all(os.path.exists(os.path.join(DROPIN, c[2])) for c in DROPIN_CASES.values()) and \
     os.path.exists(os.path.join(ROOT, "tools", "candmc_run")) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "mpirun"))
 if HAVE_DROPIN:
@@ -277,8 +281,10 @@ def test_reference_test_mains_pass_on_the_simulator(case):
 
         res = float(re.findall(r"\|\|A-QR\|\|_2 = (\S+)", so)[-1])
         assert res == res and res <= 1e-9, so[-1500:]
-        assert "qr_2d_upd_A_gpu: upd_A" in se
-        if case.startswith("qr_2d_"):
+        assert "qr_2d_upd_A_gpu: upd_" in se
+        if case.startswith("qr_y2d_"):
+            assert "upd_Yamamoto_A" in se
+        elif case.startswith("qr_2d_"):
             assert "form=T from W" in se and ("QR_TAP_B2" not in DROPIN_ENV[case] or "form=T from Y" in se)
         else:
             assert "form=W is T" in se

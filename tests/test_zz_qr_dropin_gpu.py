@@ -4,7 +4,7 @@ upd_A (alg/QR/qr_2d/qr_2d.cxx:224-282) — running in libcandmc_b200.so through 
 (TSQR, Householder reconstruction) stay the reference's host code over the mini-MPI shim and OpenBLAS (`make -C oracle dropin`;
 the binaries travel in oracle/_ref/dropin/).  test_qr_2d_gpu drives QR_2D_pipe as the test is shipped (W_is_T form);
 test_qr_2d_2d_gpu is the same test sent through QR_2D_2D (oracle/qr_2d_tap.cxx): T from the panel's factor and T from the
-aggregated Y.  Criterion: the reference's own ||A - QR|| <= 1e-9 line — parsed, because the test prints "Test successful."
+aggregated Y; test_qr_y2d_gpu is test/QR/test_qr_y2d.cxx (QR_Yamamoto_2D_2D) with upd_Yamamoto_A in the library.  Criterion: the reference's own ||A - QR|| <= 1e-9 line — parsed, because the test prints "Test successful."
 for a NaN as well.
 
 STATUS: written after round 2's GPU minutes were spent.  Green on the CPU simulator (tests/test_cpusim.py, 1 / 2 / 4 / 9
@@ -47,6 +47,10 @@ CASES = [  # np, exe, m, k, b, nprow, outer block of the tapped variant
     (4, "test_qr_2d_gpu", 256, 128, 16, 2, None),
     (4, "test_qr_2d_2d_gpu", 256, 128, 8, 2, 32),
     (4, "test_qr_2d_gpu", 2048, 1024, 64, 2, None),
+    # test/QR/test_qr_y2d.cxx (QR_Yamamoto_2D_2D, aggregator on the host): upd_Yamamoto_A in the library; here the last number is
+    # the test's own fifth argument, the outer block
+    (1, "test_qr_y2d_gpu", 256, 128, 16, 1, 64),
+    (4, "test_qr_y2d_gpu", 512, 256, 16, 2, 64),
 ]
 
 
@@ -63,8 +67,10 @@ def test_reference_qr_2d_test_passes_with_gpu_trailing_updates(np_, exe, m, k, b
     if b2 is not None:
         env["QR_TAP_B2"] = str(b2)
     cmd = [os.path.join(REFDIR, "mpirun"), "-np", str(np_), "-timeout", "200", "-threads", "2", path, str(m), str(k), str(b), str(nprow)]
+    if exe == "test_qr_y2d_gpu":
+        cmd.append(str(b2))
     rc, so, se = run_guarded("qr_dropin", cmd, 300, ROOT, env=env)
     assert rc == 0, so[-2000:] + se[-2000:]
     res = qr_residual(so)
     assert res == res and res <= 1e-9, so[-1500:]          # the reference's criterion, NaN-proof
-    assert "qr_2d_upd_A_gpu: upd_A" in se                  # ... and the updates really went through the library
+    assert "qr_2d_upd_A_gpu: upd_" in se                   # ... and the updates really went through the library

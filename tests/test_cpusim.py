@@ -54,7 +54,8 @@ REDIST = [(24, 36, 2, 2, 3, 0, 0), (36, 24, 3, 3, 2, 1, 1), (30, 30, 5, 3, 3, 0,
 for _n in DIST_MAIN:     # longest first.  On 8 ranks the fused GEMM + depth all-reduce is switched on for the 2x2x2 grid too (opt-in in
     # the product until a B200 has seen it): the kernel's peer-memory epilogue and ipc.cu run for real, over simulated CUDA IPC
     _job(f"main{_n}", _torchrun(_n, 29700 + _n, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0",
-         CANDMC_TEST_FUSED_GRIDS="1" if _n == 8 else "0")
+         CANDMC_TEST_FUSED_GRIDS="1" if _n == 8 else "0", CANDMC_TEST_UNSEEN="1")   # + the cases no B200 has run yet
+_job("unseen1", _torchrun(1, 29745, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_UNSEEN="only")
 # the default data path since round 2 (SUMMA panels by copy engines, transport.h) named explicitly on 2x2 and, together with the
 # opt-in fused depth sum, on 2x2x2 — deferred streams, LIFO order; and round 1's path (NCCL kernels, one launch per k-chunk)
 _job("nccl4", _torchrun(4, 29747, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_NCCL_PANELS="1",
@@ -64,7 +65,7 @@ _job("ncclmerge4", _torchrun(4, 29748, os.path.join(HERE, "dist_worker.py")), CA
      CPUSIM_SCHED="random:31")
 # fault injection: one rank cannot map its peers' memory (cudaIpcOpenMemHandle fails there) — every communicator that rank is in
 # must agree to stay on NCCL (panels AND the depth sum), the others keep their windows
-_job("ipcfail2", _torchrun(2, 29749, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_KC="8", CANDMC_TEST_QUICK="1", CPUSIM_IPC_FAIL_RANK="1",
+_job("ipcfail2", _torchrun(2, 29749, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_KC="8", CANDMC_TEST_QUICK="1", CANDMC_TEST_UNSEEN="1", CPUSIM_IPC_FAIL_RANK="1",
      CPUSIM_SCHED="lifo")
 _job("ipcfail4", _torchrun(4, 29750, os.path.join(HERE, "dist_worker.py")), CANDMC_TEST_PENDING="0", CANDMC_TEST_KC="8", CANDMC_TEST_QUICK="1", CPUSIM_IPC_FAIL_RANK="2",
      CPUSIM_SCHED="lifo")
@@ -366,6 +367,15 @@ def test_nccl_panels_and_per_chunk_launches_on_the_simulator():
     assert out["panel_transport_sends_rank0"] == 0 and out["merged_panel_launches_all_ranks"] == [0, 0]
     out = _dist("ncclmerge4")   # the fallback of the default schedule: launch groups fed by ncclBroadcast
     assert out["panel_transport_sends_rank0"] == 0 and out["merged_panel_launches_all_ranks"][0] > 0
+
+
+def test_cases_no_b200_has_seen_yet_on_the_simulator():
+    """tests/dist_worker.py:unseen_cases — what was written after round 2's GPU minutes were spent (upd_A with T formed from Y
+    and with host operands, error recovery of the fused depth sum, the peer-argument check, trans flags on the k-split, in
+    bcast_cannon_4d and against the reference's flagged outputs).  On 2, 4 and 8 ranks they ride on the main jobs
+    (CANDMC_TEST_UNSEEN=1); this is the single-rank set on its own, the way tests/test_zz_unseen_gpu.py runs it on a B200."""
+    out = _dist("unseen1")
+    assert out["checks_rank0"] >= 4
 
 
 def test_ranks_agree_to_leave_peer_windows_when_one_cannot_map_them():

@@ -141,12 +141,18 @@ DROPIN_CASES = {
     # ... and test/QR/test_qr_y2d.cxx (QR_Yamamoto_2D_2D with its aggregator): upd_Yamamoto_A served by candmc_upd_Yamamoto_A
     "qr_y2d_p4": ("mpirun", 4, "test_qr_y2d_gpu", ["96", "48", "8", "2", "16"], "Test successful.", "lifo"),
     "qr_y2d_p6": ("mpirun", 6, "test_qr_y2d_gpu", ["96", "48", "4", "2", "24"], "Test successful.", "sync"),
+    # integration/cdgemm_gpu.cxx: the reference's cdgemm itself over candmc_dgemm, nothing else replaced (threshold 0: every
+    # product, however small, goes through the library) — its QR test and its 2.5D LU test (offload seam on the host fallback)
+    "cdgemm_qr_p4": ("mpirun", 4, "test_qr_2d_cdgemm_gpu", ["96", "48", "8", "2"], "Test successful.", "lifo"),
+    "cdgemm_lu_p4": ("mpirun", 4, "lu_pp_cdgemm_gpu", ["-n", "256", "-b_sm", "8", "-b_lrg", "32"], "test passed", "sync"),
 }
 DROPIN_ENV = {"d25_p8_peer_paths": dict(CANDMC_PANEL_TRANSPORT="1", CANDMC_FUSED_REDUCE="2", CANDMC_MIN_KCHUNK="64"),
               "qr_pipe_p4": dict(CANDMC_SEAM_VERBOSE="1"), "qr_pipe_p1": dict(CANDMC_SEAM_VERBOSE="1"),
               "qr_2d_p4": dict(CANDMC_SEAM_VERBOSE="1", QR_TAP_B2="32"), "qr_2d_p9": dict(CANDMC_SEAM_VERBOSE="1", QR_TAP_B2="24"),
               "qr_2d_p2": dict(CANDMC_SEAM_VERBOSE="1"), "qr_y2d_p4": dict(CANDMC_SEAM_VERBOSE="1"),
-              "qr_y2d_p6": dict(CANDMC_SEAM_VERBOSE="1")}
+              "qr_y2d_p6": dict(CANDMC_SEAM_VERBOSE="1"),
+              "cdgemm_qr_p4": dict(CANDMC_SEAM_VERBOSE="1", CANDMC_CDGEMM_MIN_FLOP="0"),
+              "cdgemm_lu_p4": dict(CANDMC_SEAM_VERBOSE="1", CANDMC_CDGEMM_MIN_FLOP="0")}
 HAVE_DROPIN = all(os.path.exists(os.path.join(DROPIN, c[2])) for c in DROPIN_CASES.values()) and \
     os.path.exists(os.path.join(ROOT, "tools", "candmc_run")) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "mpirun"))
 if HAVE_DROPIN:
@@ -275,6 +281,16 @@ def test_reference_test_mains_pass_on_the_simulator(case):
     rc, so, se = RESULTS[f"dropin_{case}"]
     assert rc == 0, so[-2000:] + se[-2000:]
     assert DROPIN_CASES[case][4] in so and "FAILED" not in so and "test failed" not in so.lower()
+    if case.startswith("cdgemm_"):
+        import re
+
+        counts = [(int(a), int(b)) for a, b in re.findall(r"cdgemm_gpu: (\d+) products in the library, (\d+) on the host BLAS", se)]
+        assert len(counts) == DROPIN_CASES[case][1] and all(a > 0 and b == 0 for a, b in counts), se[-1500:]
+    if case.startswith("qr_") or case == "cdgemm_qr_p4":
+        import re
+
+        res = float(re.findall(r"\|\|A-QR\|\|_2 = (\S+)", so)[-1])
+        assert res == res and res <= 1e-9, so[-1500:]
     if case.startswith("qr_"):
         # the reference's QR test (SURVEY 8f N1's pin) prints "Test successful." for a NaN residual too: read the number, and
         # make sure the trailing updates went through the library (integration/qr_2d_upd_A_gpu.cxx reports each one)

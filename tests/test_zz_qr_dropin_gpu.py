@@ -51,6 +51,9 @@ CASES = [  # np, exe, m, k, b, nprow, outer block of the tapped variant
     # the test's own fifth argument, the outer block
     (1, "test_qr_y2d_gpu", 256, 128, 16, 1, 64),
     (4, "test_qr_y2d_gpu", 512, 256, 16, 2, 64),
+    # integration/cdgemm_gpu.cxx: the reference's cdgemm itself in the library, nothing else replaced (default size threshold)
+    (1, "test_qr_2d_cdgemm_gpu", 1024, 512, 64, 1, None),
+    (4, "test_qr_2d_cdgemm_gpu", 2048, 1024, 128, 2, None),
 ]
 
 
@@ -73,4 +76,8 @@ def test_reference_qr_2d_test_passes_with_gpu_trailing_updates(np_, exe, m, k, b
     assert rc == 0, so[-2000:] + se[-2000:]
     res = qr_residual(so)
     assert res == res and res <= 1e-9, so[-1500:]          # the reference's criterion, NaN-proof
-    assert "qr_2d_upd_A_gpu: upd_" in se                   # ... and the updates really went through the library
+    if "cdgemm" in exe:
+        lib_calls = [int(x) for x in re.findall(r"cdgemm_gpu: (\d+) products in the library", se)]
+        assert len(lib_calls) == np_ and all(c > 0 for c in lib_calls), se[-1500:]
+    else:
+        assert "qr_2d_upd_A_gpu: upd_" in se               # ... and the updates really went through the library

@@ -145,3 +145,26 @@ void use(pview* pv, double* A, double* Y, double* B) {
     p = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-I", inc, "-I", os.path.join(inc, "candmc_compat"), str(src)],
                        capture_output=True, text=True)
     assert p.returncode == 0, p.stderr[-3000:]
+
+
+def test_integration_seams_compile(tmp_path):
+    """integration/*.cxx are what a maintainer compiles inside the REFERENCE's build.  cdgemm_gpu.cxx needs nothing but the C ABI
+    header; qr_2d_upd_A_gpu.cxx needs the reference's own headers, so it is compiled where /root/reference exists (with the
+    flags of oracle/Makefile, against the mini-MPI shim's mpi.h).  g++ only, nothing is run."""
+    import subprocess
+
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-c", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "integration", "cdgemm_gpu.cxx"), "-o", str(tmp_path / "cdgemm_gpu.o")])
+    syms = subprocess.check_output(["nm", "-C", "--defined-only", str(tmp_path / "cdgemm_gpu.o")], text=True)
+    assert " T cdgemm(char, char, int, int, int, double, double const*, int, double const*, int, double, double*, int)" in syms
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        return
+    subprocess.check_call(["g++", "-c", "-D_POSIX_C_SOURCE=200112L", "-D__STDC_LIMIT_MACROS", "-Drestrict=__restrict__", "-w",
+                           "-I", os.path.join(ROOT, "oracle", "mpi_shim"), "-I", os.path.join(ref, "include"), "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "integration", "qr_2d_upd_A_gpu.cxx"), "-o", str(tmp_path / "qr_seam.o")])
+    syms = subprocess.check_output(["nm", "-C", "--defined-only", str(tmp_path / "qr_seam.o")], text=True)
+    assert " T upd_A(" in syms and " T upd_Yamamoto_A(" in syms
+    # neither seam touches test infrastructure
+    for f in ("cdgemm_gpu.cxx", "qr_2d_upd_A_gpu.cxx"):
+        assert "oracle" not in open(os.path.join(ROOT, "integration", f)).read().replace("oracle/qr_2d_tap", "")

@@ -1712,7 +1712,7 @@ int candmc_upd_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64
   StagedMatrix sY, sA, sT;
   CANDMC_TRY(sY.open(Y, mb, b, lda_Y, true, st));
   CANDMC_TRY(sA.open(A, mb, kb, lda_A, true, st));
-  CANDMC_TRY(sT.open(T, b, b, b, true, st));
+  CANDMC_TRY(sT.open(mb > 0 ? T : nullptr, b, b, b, true, st));   // (a rank without rows never reads T, :268)
   void* wsv = nullptr;
   CANDMC_TRY(workspace_get(sizeof(double) * (b * kb + 2 * b * b), &wsv));
   double* W = static_cast<double*>(wsv);

@@ -11,7 +11,8 @@ Stages (all by default, or the ones named on the command line):
            set of knobs (session 3: merge-panels / panel-transport / bg-ctas combinations; later: fused-reduce 2 on 8 GPUs);
            the fastest valid line wins and its knobs are handed to the later stages
   parity   tests/dist_worker.py (oracle + the reference's golden outputs), then its pending group (widening rows)
-  dropin   the reference's own unmodified test mains under tools/candmc_run (tests/test_dropin_gpu.py)
+  dropin   the reference's own unmodified test mains under tools/candmc_run (tests/test_dropin_gpu.py), its QR tests over the
+           upd_A / cdgemm seams and the cases no B200 has run yet (tests/test_zz_{qr_dropin,unseen,aggregator}_gpu.py)
   e2e      bench.py with the end-to-end leg (both passes) and timelines of the end-to-end steps
   configs  tools/bench_configs.py: BASELINE configs 2 / 4 / 5 with result checks
 Everything goes to gpurun_out/r02_*_{N}gpus*; stdout carries a summary.  R02_SIM=<ranks> dry-runs the script's own logic on
@@ -146,7 +147,8 @@ def main():
         summary["parity_pending"] = {"rc": rc, "line": last_json(txt)}
         print("   ", json.dumps(summary["parity_pending"])[:400], flush=True)
     if want("dropin"):
-        rc, txt = run(f"r02_dropin_{NG}gpus", ["-m", "pytest", "tests/test_dropin_gpu.py", "-m", "gpu", "-q", "-rA", "-p", "no:cacheprovider"],
+        rc, txt = run(f"r02_dropin_{NG}gpus", ["-m", "pytest", "tests/test_dropin_gpu.py", "tests/test_zz_qr_dropin_gpu.py", "tests/test_zz_unseen_gpu.py",
+                                                 "tests/test_zz_aggregator_gpu.py", "-m", "gpu", "-q", "-rA", "-p", "no:cacheprovider"],
                       env=kenv, timeout=300, torchrun=False)
         summary["dropin"] = {"rc": rc, "tail": txt.strip().splitlines()[-1:] if txt.strip() else []}
         print("   ", json.dumps(summary["dropin"]), flush=True)

@@ -161,6 +161,12 @@ if HAVE_DROPIN:
         _job(f"dropin_{_k}", [_run, "-np", str(_np), "-timeout", "200", os.path.join(DROPIN, _exe), *_args], LD_PRELOAD=PRELOAD,
              CPUSIM_SCHED=_sched, **DROPIN_ENV.get(_k, {}))
 
+# the reference's symmetric full -> band reduction with nothing but cdgemm replaced (integration/cdgemm_gpu.cxx), against the
+# all-host outputs of the same driver in tests/golden/f2b_ref_outputs.npz
+if HAVE_DROPIN and os.path.exists(os.path.join(DROPIN, "ref_f2b_dump_cdgemm_gpu")):
+    for _c, _sched in (("f2b_p4_n48_b8_s4", "lifo"), ("f2b_p9_n72_b12_s4", "sync")):
+        _job(f"f2bseam_{_c}", [sys.executable, os.path.join(HERE, "f2b_seam_check.py"), _c], LD_PRELOAD=PRELOAD, CPUSIM_SCHED=_sched)
+
 # the same workers with DEFERRED streams: work runs only at host synchronisation points, and among the runnable streams
 # the one whose head was enqueued last goes first (lifo) or a random one — a missing event dependency computes garbage
 ADVERSARIAL = [("main4", "lifo"), ("pending4", "lifo"), ("main8", "random:7")] + [(f"lu_{_s}_1", "lifo") for _s in SCRIPTS]
@@ -305,6 +311,19 @@ def test_reference_test_mains_pass_on_the_simulator(case):
             assert "form=T from W" in se and ("QR_TAP_B2" not in DROPIN_ENV[case] or "form=T from Y" in se)
         else:
             assert "form=W is T" in se
+
+
+@pytest.mark.parametrize("case", ["f2b_p4_n48_b8_s4", "f2b_p9_n72_b12_s4"])
+def test_reference_full_to_band_with_cdgemm_in_the_library(case):
+    """alg/SE/full_to_band.cxx, unmodified, under the mini-MPI: cdgemm alone comes from integration/cdgemm_gpu.cxx, so the panel
+    QR's updates, Y^T A, U V^T and the rank-2b update of every level multiply in the library; every rank's local array after
+    each recorded level equals the all-host run's (the fixture) to 1e-12, and every rank really sent products to the library"""
+    if f"f2bseam_{case}" not in RESULTS:
+        pytest.skip("drop-in binaries not built (needs /root/reference at build time)")
+    rc, so, se = RESULTS[f"f2bseam_{case}"]
+    assert rc == 0, so[-2000:] + se[-2000:]
+    out = json.loads([line for line in so.splitlines() if line.startswith("{")][-1])
+    assert out["ok"] and out["arrays_compared"] >= 36 and out["max_rel_diff"] <= 1e-12
 
 
 @pytest.mark.parametrize("nproc,seed,policy", FUZZ)

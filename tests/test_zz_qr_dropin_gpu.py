@@ -81,3 +81,22 @@ def test_reference_qr_2d_test_passes_with_gpu_trailing_updates(np_, exe, m, k, b
         assert len(lib_calls) == np_ and all(c > 0 for c in lib_calls), se[-1500:]
     else:
         assert "qr_2d_upd_A_gpu: upd_" in se               # ... and the updates really went through the library
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="the reference's full -> band reduction over the cdgemm seam: first B200 run pending")
+@pytest.mark.parametrize("case,np_", [("f2b_p1_n24_b8_s4", 1), ("f2b_p4_n48_b8_s4", 4)])
+def test_reference_full_to_band_with_cdgemm_in_the_library(case, np_):
+    """alg/SE/full_to_band.cxx, unmodified, with nothing but cdgemm replaced (integration/cdgemm_gpu.cxx, threshold 0: every
+    product in the library) against the all-host outputs in tests/golden/f2b_ref_outputs.npz (tests/f2b_seam_check.py)"""
+    import json
+    import sys
+
+    if not os.path.exists(os.path.join(REFDIR, "dropin", "ref_f2b_dump_cdgemm_gpu")):
+        pytest.skip("drop-in binaries not built (needs /root/reference at build time)")
+    if _ngpu() < np_:
+        pytest.skip(f"needs {np_} GPUs")
+    rc, so, se = run_guarded("qr_dropin", [sys.executable, os.path.join(HERE, "f2b_seam_check.py"), case], 300, ROOT)
+    assert rc == 0, so[-2000:] + se[-2000:]
+    out = json.loads([line for line in so.splitlines() if line.startswith("{")][-1])
+    assert out["ok"] and out["max_rel_diff"] <= 1e-12

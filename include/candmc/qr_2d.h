@@ -75,12 +75,14 @@ inline void update_A(double const* Y, int64_t lda_Y, double* A, int64_t lda_A, i
   candmc_shim_check(candmc_update_A(Y, lda_Y, A, lda_A, m, k, b, W, &c, aggreg_Y, lda_aY, W_is_T ? 1 : 0, 0), "update_A");
 }
 
-/* upd_A (qr_2d.cxx:224-282) after the panel has been broadcast: W == NULL and the panel-factor form need the whole grid view
- * and go through update_A above; this overload is the W_is_T form the pipelined drivers use (qr_2d.cxx:447-620). */
-inline void upd_A(double const* Ybuf, int64_t lda_Y, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b, double const* T,
+/* upd_A (qr_2d.cxx:224-282) after the panel has been broadcast: the W_is_T form the pipelined drivers use (:447-620) and the
+ * W == NULL form (T^-1 from the aggregated Y, QR_2D_2D :873 — formed on the device).  The panel-factor form (W != NULL,
+ * W_is_T == false) needs the whole grid view and goes through update_A above.  Unlike the reference's declaration the default
+ * of W_is_T is true here: with device pointers a non-null W can only be T. */
+inline void upd_A(double const* Ybuf, int64_t lda_Y, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b, double const* W,
                   pview* pv, bool W_is_T = true) {
-  candmc_qr2d_unsupported(!W_is_T || T == nullptr, "upd_A: only the W_is_T form is offered here; use update_A for the other two");
-  candmc_shim_check(candmc_upd_A(Ybuf, lda_Y, A, lda_A, mb, kb, b, T, pv->ccol.cm, 0), "upd_A");
+  candmc_qr2d_unsupported(W != nullptr && !W_is_T, "upd_A: the panel-factor form (W_is_T == false) is offered by update_A");
+  candmc_shim_check(candmc_upd_A(Ybuf, lda_Y, A, lda_A, mb, kb, b, W, pv->ccol.cm, 0), "upd_A");
 }
 
 inline void update_Yamamoto_A(double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b, double* T,

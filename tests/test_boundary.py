@@ -130,6 +130,7 @@ void use(pview* pv, double* A, double* Y, double* B) {
   update_A(Y, 64, A, 64, 128, 96, 16, NULL, pv, B, 64);             // T from Y, panel saved into aggreg_Y
   update_A(Y, 64, A, 64, 128, 96, 16, B, pv, NULL, 0, true);        // W is T
   upd_A(Y, 64, A, 64, 64, 48, 16, B, pv, true);
+  upd_A(Y, 64, A, 64, 64, 48, 16, NULL, pv);                        // W == NULL: T from Y on the device (QR_2D_2D's call, qr_2d.cxx:873)
   update_Yamamoto_A(Y, 64, A, 64, 128, 96, 16, B, pv, NULL);
   upd_Yamamoto_A(Y, 64, A, 64, 64, 48, 16, B, pv);
   // ... and with the reference's aggregator (qr_y2d.h:4-46), as QR_Yamamoto_2D_2D uses it (qr_y2d.cxx:333-377)

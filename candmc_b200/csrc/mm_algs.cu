@@ -1641,8 +1641,6 @@ int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, in
   // only the root rank reads (upd_A :244-253) — the other ranks may hand in any non-null pointer, as QR_2D does (:309,325)
   const bool t_from_w = (W != nullptr && !W_is_T);
   const bool w_root = t_from_w && myrow == pv->rrow && mycol == pv->rcol;
-  CANDMC_CHECK(is_device_ptr(Y) && is_device_ptr(A) && is_device_ptr(aggreg_Y) && ((t_from_w && !w_root) || is_device_ptr(W)),
-               "update_A: operands must be device pointers");
   CANDMC_CHECK(!t_from_w || m >= b, "update_A: the panel factor form needs at least b rows (m=%lld, b=%lld)", (long long)m,
                (long long)b);
   // block-cyclic local extents of the remaining matrix, qr_2d.cxx:140-147
@@ -1652,6 +1650,19 @@ int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, in
   int64_t kb = (k / b) / npcol;
   if ((mycol + npcol - pv->rcol - 1) % npcol < (k / b) % npcol) kb++;
   kb *= b;
+  // Host operands — what QR_2D itself holds (qr_2d.cxx:325) — are staged for the call like the multiplies' blocks: the panel on
+  // the root column only, W where it is read (every rank for W_is_T, the root rank for the panel factor), A and aggreg_Y where the
+  // rank has rows; A and aggreg_Y are written back before the call returns.  Device pointers are used in place, asynchronously.
+  StagedMatrix sYp, sAm, sWm, sAgg;
+  CANDMC_TRY(sYp.open((mycol == pv->rcol && mb > 0) ? Y : nullptr, mb, b, lda_Y, true, st));
+  CANDMC_TRY(sAm.open((mb > 0 && kb > 0) ? A : nullptr, mb, kb, lda_A, true, st));
+  CANDMC_TRY(sWm.open((W != nullptr && (W_is_T ? mb > 0 : w_root)) ? W : nullptr, b, b, b, true, st));
+  CANDMC_TRY(sAgg.open(mb > 0 ? aggreg_Y : nullptr, mb, b, lda_aY, false, st));
+  const bool any_staged = sYp.staged() || sAm.staged() || sWm.staged() || sAgg.staged();
+  Y = sYp.ptr(); lda_Y = sYp.ld();
+  if (mb > 0 && kb > 0) { A = sAm.ptr(); lda_A = sAm.ld(); }
+  if (sWm.staged()) W = sWm.ptr();
+  if (mb > 0 && aggreg_Y != nullptr) { aggreg_Y = sAgg.ptr(); lda_aY = sAgg.ld(); }
   void* wsv = nullptr;
   CANDMC_TRY(workspace_get(sizeof(double) * (mb * b + 2 * b * b + b * kb + 8), &wsv));
   double* Ybuf = static_cast<double*>(wsv);
@@ -1695,6 +1706,11 @@ int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, in
   }
   CANDMC_TRY(upd_A_impl(Ybuf, mb, A, lda_A, mb, kb, b, Tuse, pv->ccol, Wbuf, st));
   if (aggreg_Y != nullptr && mb > 0) CANDMC_TRY(lda_copy_f64(mb, b, mb, lda_aY, Ybuf, aggreg_Y, st));  // :172-174
+  if (any_staged) {
+    CANDMC_TRY(sAm.close_out(st));
+    CANDMC_TRY(sAgg.close_out(st));
+    CANDMC_CUDA(cudaStreamSynchronize(st));
+  }
   return OK;
 }
 

@@ -257,7 +257,9 @@ typedef struct candmc_pview {
  * (what QR_2D hands in, :325) W is the b x b upper-triangular factor of the panel QR, read on the root rank (rrow, rcol)
  * only: T = lower(-W^-T Y1) as comp_bcast_T_from_W forms it (:179-208; alg/QR/hh_recon/hh_recon.cxx:26-31), delivered to
  * every rank along the root's grid row and then down the grid columns (pv->cworld is not used).  The three forms must be
- * chosen alike on every rank.  aggreg_Y may be NULL.  All matrix operands are device pointers. */
+ * chosen alike on every rank.  aggreg_Y may be NULL.  Device pointers are used in place and the call is asynchronous; HOST
+ * pointers — what QR_2D itself holds (:325) — are staged for the call (the panel on the root column, W where it is read, A and
+ * aggreg_Y where the rank has rows) and A / aggreg_Y are written back before it returns. */
 int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,
                     const double* W, const candmc_pview_t* pv, double* aggreg_Y, int64_t lda_aY, int W_is_T,
                     void* stream);

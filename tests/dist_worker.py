@@ -294,7 +294,7 @@ def case_upd_A(world, name, mb, kb, b, use_host=False, t_from_y=False, lda_pad=0
     return ok & record(f"{name}:oracle", rel_frob(got, A[world.rank]), (1000 if t_from_y else 10) * mb * P * EPS)
 
 
-def case_update_A(world, golden, name, m, k, b, nprow, rrow, rcol, with_T=False, with_W=False):
+def case_update_A(world, golden, name, m, k, b, nprow, rrow, rcol, with_T=False, with_W=False, use_host=False):
     """update_A on a block-cyclic nprow x npcol grid with rotated roots, vs the reference's own outputs
     (tests/golden, W == NULL) and the oracle.  rank = myrow + mycol*nprow (test/QR/test_qr_2d.cxx:367-374)."""
     P = world.np
@@ -321,11 +321,21 @@ def case_update_A(world, golden, name, m, k, b, nprow, rrow, rcol, with_T=False,
         Wd = Wnp + np.tril(np.full((b, b), np.nan), -1) if (myrow == rrow and mycol == rcol) else np.full((b, b), np.nan)
         W = dev(np.asfortranarray(Wd))
     pv = cb.pview(rrow, rcol, crow, ccol, world)
-    cb.update_A(dY, lda_Y, dA, lda_A, m, k, b, W, pv, aggreg_Y=agg, lda_aY=max(mb, 1), W_is_T=with_T)
-    torch.cuda.synchronize()
-    got = host(dA, mb, kb) if (mb and kb) else np.zeros((mb, kb))
-    orc.update_A(nprow, npcol, rrow, rcol, m, k, b, Y, A, Wnp, W_is_T=not with_W)
     ok = True
+    if use_host:   # numpy operands, what QR_2D itself holds: staged inside the call, A and aggreg_Y written back on return
+        hA = np.full((lda_A + 1, max(kb, 1)), np.nan, order="F"); hA[:mb, :kb] = Al
+        hagg = np.full((max(mb, 1) + 3, b), np.nan, order="F")
+        hW = None if W is None else np.asfortranarray(host(W, b, b))
+        cb.update_A(Yp, lda_Y, hA, lda_A + 1, m, k, b, hW, pv, aggreg_Y=hagg, lda_aY=max(mb, 1) + 3, W_is_T=with_T)
+        got = hA[:mb, :kb].copy()
+        ok &= record(f"{name}:padding_untouched", 0.0 if (np.isnan(hA[mb:]).all() and np.isnan(hagg[mb:]).all()) else 1.0, 0.5)
+        if mb:   # the broadcast panel as update_A packs it: unit lower-trapezoidal on the root row, the plain rows elsewhere
+            ok &= record(f"{name}:aggreg_Y_written", 0.0 if np.isfinite(hagg[:mb]).all() else 1.0, 0.5)
+    else:
+        cb.update_A(dY, lda_Y, dA, lda_A, m, k, b, W, pv, aggreg_Y=agg, lda_aY=max(mb, 1), W_is_T=with_T)
+        torch.cuda.synchronize()
+        got = host(dA, mb, kb) if (mb and kb) else np.zeros((mb, kb))
+    orc.update_A(nprow, npcol, rrow, rcol, m, k, b, Y, A, Wnp, W_is_T=not with_W)
     if mb and kb:
         ok &= record(f"{name}:oracle", rel_frob(got, A[world.rank]), 10 * m * EPS)
         if not with_T and f"{name}.r{world.rank}" in golden:
@@ -828,6 +838,15 @@ def unseen_cases(world, golden):
                 case_upd_A(world, "upd_A_p4_host_pad", 96, 80, 32, use_host=True, lda_pad=1)
         if P == 8:
             case_d25(world, golden, "d25_n64_q2_c2_ovp0_TT", 64, 2, 0, trans=("T", "T"))
+        if min_kc == 1024:   # update_A with HOST operands (staged inside the call), all three forms of W, against the reference's outputs
+            if P == 1:
+                case_update_A(world, golden, "upda_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0, use_host=True)
+                case_update_A(world, golden, "updw_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0, with_W=True, use_host=True)
+            if P == 4:
+                case_update_A(world, golden, "upda_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 0, 0, use_host=True)
+                case_update_A(world, golden, "updw_m96_k64_b8_2x2_r11", 96, 64, 8, 2, 1, 1, with_W=True, use_host=True)
+                case_update_A(world, golden, "upda_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 2, 0, use_host=True)
+                case_update_A(world, golden, "upda_T_2x2_host", 128, 96, 16, 2, 1, 1, with_T=True, use_host=True)
     cb.set_min_kchunk(1024)
 
 

@@ -1622,7 +1622,7 @@ int candmc_upd_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t l
   double* W = static_cast<double*>(wsv);
   CANDMC_TRY(upd_Yamamoto_A_impl(sQ.ptr(), sQ.ld(), sA.ptr(), sA.ld(), mb, kb, b, sT.ptr(), ccol, W, W + b * kb, st));
   if (mb > 0) CANDMC_TRY(sA.close_out(st));
-  if (sQ.staged() || sA.staged() || sT.staged()) CANDMC_CUDA(cudaStreamSynchronize(st));
+  if (sQ.staged() || sA.staged() || sT.staged() || !is_device_ptr(Qm) || !is_device_ptr(A)) CANDMC_CUDA(cudaStreamSynchronize(st));
   return OK;
 }
 
@@ -1658,7 +1658,8 @@ int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, in
   CANDMC_TRY(sAm.open((mb > 0 && kb > 0) ? A : nullptr, mb, kb, lda_A, true, st));
   CANDMC_TRY(sWm.open((W != nullptr && (W_is_T ? mb > 0 : w_root)) ? W : nullptr, b, b, b, true, st));
   CANDMC_TRY(sAgg.open(mb > 0 ? aggreg_Y : nullptr, mb, b, lda_aY, false, st));
-  const bool any_staged = sYp.staged() || sAm.staged() || sWm.staged() || sAgg.staged();
+  // (a rank without rows stages nothing; it still returns only when its part of the collectives has run, like its peers)
+  const bool any_staged = sYp.staged() || sAm.staged() || sWm.staged() || sAgg.staged() || !is_device_ptr(A) || !is_device_ptr(Y);
   Y = sYp.ptr(); lda_Y = sYp.ld();
   if (mb > 0 && kb > 0) { A = sAm.ptr(); lda_A = sAm.ld(); }
   if (sWm.staged()) W = sWm.ptr();
@@ -1749,7 +1750,7 @@ int candmc_upd_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, int64
   }
   CANDMC_TRY(upd_A_impl(sY.ptr(), sY.ld(), sA.ptr(), sA.ld(), mb, kb, b, Tuse, ccol, W, st));
   if (mb > 0) CANDMC_TRY(sA.close_out(st));
-  if (sY.staged() || sA.staged() || sT.staged()) CANDMC_CUDA(cudaStreamSynchronize(st));
+  if (sY.staged() || sA.staged() || sT.staged() || !is_device_ptr(Y) || !is_device_ptr(A)) CANDMC_CUDA(cudaStreamSynchronize(st));
   return OK;
 }
 

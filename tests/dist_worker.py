@@ -267,6 +267,7 @@ def case_upd_A(world, name, mb, kb, b, use_host=False, t_from_y=False, lda_pad=0
     t_from_y: T = None, the reference's W == NULL form — T^-1 = tril(sum over the column of Y^T Y), diagonal halved."""
     rng = np.random.default_rng(5)
     P = world.np
+    t_from_y = t_from_y and mb >= b   # (the Householder-like panel below needs b rows on rank 0)
     Y = [np.asfortranarray(rng.random((mb, b))) for _ in range(P)]
     A = [np.asfortranarray(rng.random((mb, kb))) for _ in range(P)]
     if t_from_y:   # Householder-like panel: unit lower-trapezoidal on rank 0, small entries below, so that T^-1 is well conditioned

@@ -43,6 +43,8 @@ def main():
         cb.lib().candmc_set_panel_transport(rng.choice([1, 1, 0]))   # copy engines (the default) or the NCCL fallback; same on every rank
         pad = rng.choice([0, 0, 1, 2, 3])
         tag = f"fz{seed}.{it}.{kind}"
+        if os.environ.get("FUZZ_TRACE") == "1":
+            print(f"[rank {rank}] {tag} (previous: {log[-1] if log else None})", file=sys.stderr, flush=True)
         if kind == "d25":
             cs = [c for c in (1, 2, 4) if P % c == 0 and int(round((P // c) ** 0.5)) ** 2 == P // c
                   and (int(round((P // c) ** 0.5)) % c == 0 or P // c == 1)]
@@ -90,8 +92,11 @@ def main():
             dw.case_spc(world, golden, tag, rng.choice([0, 1]), kary, ndim, n, m, k, rng.choice(["N", "T"]), use_host=rng.random() < 0.3)
         elif kind == "upd_A":
             mb, kb, b = rng.choice([8, 24, 64, 96]), rng.choice([4, 16, 40, 80]), rng.choice([2, 4, 8, 16, 32])
-            log.append((tag, dict(mb=mb, kb=kb, b=b)))
-            dw.case_upd_A(world, tag, mb, kb, b)
+            form = dict(use_host=rng.random() < 0.4, t_from_y=rng.random() < 0.4)   # host operands staged inside; T formed from Y
+            if form["use_host"]:
+                form["lda_pad"] = pad
+            log.append((tag, dict(mb=mb, kb=kb, b=b, **form)))
+            dw.case_upd_A(world, tag, mb, kb, b, **form)
         elif kind in ("update_A", "yamamoto", "redist"):
             nprow = rng.choice([d for d in range(1, P + 1) if P % d == 0])
             npcol = P // nprow
@@ -105,7 +110,7 @@ def main():
                 m, k = b * rng.choice([2, 3, 5, 8, 11]), b * rng.choice([1, 2, 4, 7])
                 log.append((tag, dict(m=m, k=k, b=b, grid=(nprow, npcol), roots=(rrow, rcol))))
                 if kind == "update_A":
-                    dw.case_update_A(world, golden, tag, m, k, b, nprow, rrow, rcol, with_T=rng.random() < 0.3)
+                    dw.case_update_A(world, golden, tag, m, k, b, nprow, rrow, rcol, with_T=rng.random() < 0.3, use_host=rng.random() < 0.4)
                 else:
                     dw.case_update_Yamamoto_A(world, golden, tag, m, k, b, nprow, rrow, rcol)
         elif kind == "f2b":

@@ -175,18 +175,18 @@ int candmc_comm_split(candmc_comm_t* parent, int color, int key, candmc_comm_t**
 
 int candmc_comm_free(candmc_comm_t* comm) {
   if (!comm) return OK;
+  // collectives enqueued on this communicator may still be waiting on their streams (every call with device operands is
+  // asynchronous): let them run before the communicator goes away, as MPI_Comm_free lets pending operations complete
+  cudaDeviceSynchronize();
   if (comm->fused_ctx) {
     candmc::FusedCtx* f = static_cast<candmc::FusedCtx*>(comm->fused_ctx);
-    cudaDeviceSynchronize();
     candmc::window_destroy(f->win);
     delete f;
   }
   if (comm->transport) {
-    cudaDeviceSynchronize();
     candmc::panel_transport_destroy(static_cast<candmc::PanelTransport*>(comm->transport));
   }
   if (comm->p2p) {
-    cudaDeviceSynchronize();
     candmc::p2p_transport_destroy(static_cast<candmc::P2PTransport*>(comm->p2p));
   }
   if (comm->nccl_bg && comm->nccl_bg != comm->nccl) ncclCommDestroy(comm->nccl_bg);

@@ -4,6 +4,7 @@
 #   gpurun --timeout 1800 -- 'bash tools/r02_session.sh probe ncu1 f32 tests bench1 lu'     (session 1)
 #   gpurun --timeout 900  -- 'bash tools/r02_session.sh pack'                                (session 2)
 #   gpurun --timeout 900  -- 'bash tools/r02_session.sh tile'                                (session 4)
+#   gpurun --timeout 900  -- 'bash tools/r02_session.sh seams'                               (NOT RUN: written after the budget was spent)
 # The 4- and 8-GPU sessions are tools/r02_multi.py.  Keep gpurun_out/ under 64 MiB or nothing travels back (ncu_full
 # deletes reports over 6 MB after summarising them).
 set -u
@@ -70,6 +71,21 @@ for section in "$@"; do
         done
         grep -E "==|Gigaflops|elapsed|failed|rror" $O/r02_lu_bench.log | head -20
       fi
+      ;;
+    seams)
+      # the reference's own QR / LU / full -> band drivers over the integration/ seams (first B200 contact), then one timing each
+      # of the reference's QR test all-host, with upd_A in the library and with cdgemm in the library (host matrices are
+      # staged per call: this shows the drop-in, not config 5's speed)
+      timeout 900 python -m pytest tests/test_zz_qr_dropin_gpu.py tests/test_zz_unseen_gpu.py tests/test_zz_aggregator_gpu.py -m gpu -q -rA \
+        -p no:cacheprovider > $O/r02_seams_pytest.log 2>&1; tail -5 $O/r02_seams_pytest.log
+      REF=oracle/_ref
+      for exe in test_qr_2d_host dropin/test_qr_2d_gpu dropin/test_qr_2d_cdgemm_gpu; do
+        if [ -x $REF/$exe ]; then
+          echo "== $exe 4096 x 2048, b = 128, 1 rank" >> $O/r02_seams_qr.log
+          ( time timeout 300 $REF/mpirun -np 1 -timeout 250 -threads 8 $REF/$exe 4096 2048 128 1 ) >> $O/r02_seams_qr.log 2>&1
+        fi
+      done
+      grep -E "==|A-QR\|\|_2 =|real" $O/r02_seams_qr.log | head -12
       ;;
     tile)
       # A/B of the two CTA shapes of the DMMA GEMM (128 x 128 tiles, one CTA per SM / 128 x 64 tiles, two per SM)

@@ -1518,7 +1518,7 @@ int update_Yamamoto_A_core(const double* Qm, int64_t lda_Qm, double* A, int64_t 
   g_events.reset();
   CANDMC_CHECK(pv != nullptr && pv->crow != nullptr && pv->ccol != nullptr, "update_Yamamoto_A: null processor view");
   CANDMC_CHECK(b > 0 && m >= 0 && k >= 0 && m % b == 0 && k % b == 0, "update_Yamamoto_A: m and k must be multiples of b");
-  CANDMC_CHECK(T != nullptr && is_device_ptr(Qm) && is_device_ptr(T), "update_Yamamoto_A: operands must be device pointers");
+  CANDMC_CHECK(T != nullptr, "update_Yamamoto_A: null T");
   CANDMC_CHECK(update || agg != nullptr, "update_Yamamoto_A: nothing to do");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nprow = pv->ccol->size, npcol = pv->crow->size, myrow = pv->ccol->rank, mycol = pv->crow->rank;
@@ -1535,7 +1535,16 @@ int update_Yamamoto_A_core(const double* Qm, int64_t lda_Qm, double* A, int64_t 
   if (!update) kb = 0;   // the last panel of a block column (QR_Yamamoto_2D :266-271): broadcast and append only
   // (a rank whose share of the trailing matrix is empty may hold a pointer past the end of its array, as the reference's
   // drivers do after their pointer arithmetic: it is never dereferenced)
-  CANDMC_CHECK(mb == 0 || kb == 0 || is_device_ptr(A), "update_Yamamoto_A: A must be a device pointer");
+  // Host operands — what QR_Yamamoto_2D itself holds (qr_y2d.cxx:214) — are staged for the call: the panel and T on the root
+  // column, A where the rank has a share; A and T (an output on the other columns, :112) are written back before it returns.
+  const bool host_call = !is_device_ptr(Qm) || !is_device_ptr(A) || !is_device_ptr(T);
+  StagedMatrix sQ, sAm, sT;
+  CANDMC_TRY(sQ.open((mycol == pv->rcol && mb > 0) ? Qm : nullptr, mb, b, lda_Qm, true, st));
+  CANDMC_TRY(sAm.open((mb > 0 && kb > 0) ? A : nullptr, mb, kb, lda_A, true, st));
+  CANDMC_TRY(sT.open(T, b, b, b, mycol == pv->rcol, st));
+  Qm = sQ.ptr(); lda_Qm = sQ.ld();
+  if (mb > 0 && kb > 0) { A = sAm.ptr(); lda_A = sAm.ld(); }
+  T = sT.ptr();
   void* wsv = nullptr;
   CANDMC_TRY(workspace_get(sizeof(double) * (mb * b + 2 * b * kb + 8), &wsv));
   double* Qbuf = static_cast<double*>(wsv);
@@ -1547,6 +1556,11 @@ int update_Yamamoto_A_core(const double* Qm, int64_t lda_Qm, double* A, int64_t 
   CANDMC_TRY(comm_bcast(pv->crow, T, T, b * b, pv->rcol, st));
   if (update) CANDMC_TRY(upd_Yamamoto_A_impl(Qbuf, mb, A, lda_A, mb, kb, b, T, pv->ccol, W, W2, st));
   if (agg != nullptr) CANDMC_TRY(aggregator_append(agg, mb, b, Qbuf, T, pv->ccol, st));   // :117-118
+  if (host_call) {
+    CANDMC_TRY(sAm.close_out(st));
+    CANDMC_TRY(sT.close_out(st));
+    CANDMC_CUDA(cudaStreamSynchronize(st));
+  }
   return OK;
 }
 

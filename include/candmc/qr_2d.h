@@ -10,8 +10,8 @@
  *              W != NULL, !W_is_T   W is the panel QR's upper-triangular factor on the root rank (what QR_2D itself passes,
  *                                   qr_2d.cxx:325); T = lower(-W^-T Y1)   (comp_bcast_T_from_W, qr_2d.cxx:179-208)
  * Device pointers are used in place and the calls are asynchronous on the library's default stream (0) like the other candmc/
- * wrappers; update_A, upd_A and upd_Yamamoto_A also take HOST pointers — the reference's own callers hold host matrices — which
- * are staged for the call and written back before it returns (update_Yamamoto_A and the aggregator: device pointers only).
+ * wrappers; update_A, upd_A, update_Yamamoto_A and upd_Yamamoto_A also take HOST pointers — the reference's own callers hold
+ * host matrices — which are staged for the call and written back before it returns (the aggregator's arrays: device memory).
  * Argument errors abort through candmc_shim_check as the reference does through ABORT.
  */
 #ifndef CANDMC_QR_2D_H

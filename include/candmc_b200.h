@@ -269,8 +269,9 @@ int candmc_update_A(const double* Y, int64_t lda_Y, double* A, int64_t lda_A, in
  * candmc_update_Yamamoto_A replaces update_Yamamoto_A (:68-120) with agg == NULL: block-cyclic local extents (:81-88), the
  * root column's panel packed and MPI_Bcast along the grid row (:101-110), T MPI_Bcast along the grid row IN PLACE (:112,
  * so T is an output on the other columns), then the update.  Device pointers; Qm is read on the root column only.
- * candmc_upd_Yamamoto_A also takes HOST pointers (staged for the call, A written back on return) — what
- * integration/qr_2d_upd_A_gpu.cxx passes for the reference's unmodified QR_Yamamoto drivers. */
+ * Both also take HOST pointers (staged for the call; A — and for candmc_update_Yamamoto_A the broadcast T — written back on
+ * return): candmc_upd_Yamamoto_A is what integration/qr_2d_upd_A_gpu.cxx passes for the reference's unmodified QR_Yamamoto
+ * drivers.  The aggregator's arrays always live in device memory. */
 int candmc_upd_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t mb, int64_t kb, int64_t b,
                           const double* T, candmc_comm_t* ccol, void* stream);
 int candmc_update_Yamamoto_A(const double* Qm, int64_t lda_Qm, double* A, int64_t lda_A, int64_t m, int64_t k, int64_t b,

@@ -373,7 +373,7 @@ def case_redistribute(world, name, m, n, nb, nprow, rrow, rcol, pad=0):
     return ok
 
 
-def case_update_Yamamoto_A(world, golden, name, m, k, b, nprow, rrow, rcol):
+def case_update_Yamamoto_A(world, golden, name, m, k, b, nprow, rrow, rcol, use_host=False):
     """update_Yamamoto_A vs the reference's own outputs (tests/golden `updy_*`) and the oracle; as in the
     fixture's run, only the root column starts with the panel and T."""
     P = world.np
@@ -392,10 +392,18 @@ def case_update_Yamamoto_A(world, golden, name, m, k, b, nprow, rrow, rcol):
     dA = dev(A[world.rank]) if A[world.rank].size else torch.zeros(1, dtype=torch.float64, device="cuda")
     dT = dev(T if mycol == rcol else np.zeros((b, b), order="F"))
     pv = cb.pview(rrow, rcol, crow, ccol, world)
-    cb.update_Yamamoto_A(dQ, lda_Q, dA, max(mb, 1), m, k, b, dT, pv)
-    torch.cuda.synchronize()
-    ok = record(f"{name}:T_bcast", 0.0 if np.array_equal(host(dT, b, b), T) else 1.0, 0.5)
-    got = host(dA, mb, kb) if (mb and kb) else np.zeros((mb, kb))
+    if use_host:   # numpy operands, what QR_Yamamoto_2D itself holds: staged inside the call, A and T written back on return
+        hA = np.full((max(mb, 1) + 2, max(kb, 1)), np.nan, order="F"); hA[:mb, :kb] = A[world.rank]
+        hT = np.asfortranarray(T.copy() if mycol == rcol else np.full((b, b), np.nan))
+        cb.update_Yamamoto_A(Qp, lda_Q, hA, max(mb, 1) + 2, m, k, b, hT, pv)
+        ok = record(f"{name}:T_bcast", 0.0 if np.array_equal(hT, T) else 1.0, 0.5)
+        ok &= record(f"{name}:padding_untouched", 0.0 if np.isnan(hA[mb:]).all() else 1.0, 0.5)
+        got = hA[:mb, :kb].copy()
+    else:
+        cb.update_Yamamoto_A(dQ, lda_Q, dA, max(mb, 1), m, k, b, dT, pv)
+        torch.cuda.synchronize()
+        ok = record(f"{name}:T_bcast", 0.0 if np.array_equal(host(dT, b, b), T) else 1.0, 0.5)
+        got = host(dA, mb, kb) if (mb and kb) else np.zeros((mb, kb))
     orc.update_Yamamoto_A(nprow, npcol, rrow, rcol, m, k, b, Qm, A, T)
     if mb and kb:
         ok &= record(f"{name}:oracle", rel_frob(got, A[world.rank]), 10 * m * EPS)
@@ -843,11 +851,14 @@ def unseen_cases(world, golden):
             if P == 1:
                 case_update_A(world, golden, "upda_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0, use_host=True)
                 case_update_A(world, golden, "updw_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0, with_W=True, use_host=True)
+                case_update_Yamamoto_A(world, golden, "updy_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0, use_host=True)
             if P == 4:
                 case_update_A(world, golden, "upda_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 0, 0, use_host=True)
                 case_update_A(world, golden, "updw_m96_k64_b8_2x2_r11", 96, 64, 8, 2, 1, 1, with_W=True, use_host=True)
                 case_update_A(world, golden, "upda_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 2, 0, use_host=True)
                 case_update_A(world, golden, "upda_T_2x2_host", 128, 96, 16, 2, 1, 1, with_T=True, use_host=True)
+                case_update_Yamamoto_A(world, golden, "updy_m96_k64_b8_2x2_r00", 96, 64, 8, 2, 0, 0, use_host=True)
+                case_update_Yamamoto_A(world, golden, "updy_m72_k40_b8_4x1_r20", 72, 40, 8, 4, 2, 0, use_host=True)
     cb.set_min_kchunk(1024)
 
 

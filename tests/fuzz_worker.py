@@ -112,7 +112,7 @@ def main():
                 if kind == "update_A":
                     dw.case_update_A(world, golden, tag, m, k, b, nprow, rrow, rcol, with_T=rng.random() < 0.3, use_host=rng.random() < 0.4)
                 else:
-                    dw.case_update_Yamamoto_A(world, golden, tag, m, k, b, nprow, rrow, rcol)
+                    dw.case_update_Yamamoto_A(world, golden, tag, m, k, b, nprow, rrow, rcol, use_host=rng.random() < 0.4)
         elif kind == "f2b":
             pr = int(round(P ** 0.5))
             bs = rng.choice([2, 4, 8, 16]); b = bs * pr * rng.choice([1, 2, 4]); n = b + bs * pr * rng.choice([1, 2, 3, 6])

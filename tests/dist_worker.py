@@ -847,6 +847,11 @@ def unseen_cases(world, golden):
                 case_upd_A(world, "upd_A_p4_host_pad", 96, 80, 32, use_host=True, lda_pad=1)
         if P == 8:
             case_d25(world, golden, "d25_n64_q2_c2_ovp0_TT", 64, 2, 0, trans=("T", "T"))
+            if min_kc == 8:   # the peer-argument check on the 2x2x2 grid's depth pairs: passes for device C and for host C
+                cb.lib().candmc_set_check_peer_args(1)
+                case_d25(world, golden, "d25_checked_peer_args_n512_c2", 512, 2, 0, check_golden=False)
+                case_d25(world, golden, "d25_checked_peer_args_n512_c2_host", 512, 2, 1, use_host=True, check_golden=False)
+                cb.lib().candmc_set_check_peer_args(0)
         if min_kc == 1024:   # update_A with HOST operands (staged inside the call), all three forms of W, against the reference's outputs
             if P == 1:
                 case_update_A(world, golden, "upda_m64_k32_b16_1x1", 64, 32, 16, 1, 0, 0, use_host=True)
